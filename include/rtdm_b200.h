@@ -1,0 +1,168 @@
+/*
+ * rtdm_b200.h -- C ABI of the B200-native stereo disparity engine (librtdm_b200.so).
+ *
+ * This is the drop-in boundary for rt-depth-map's matcher / filter plugins.  Every entry point
+ * names the reference interface it replaces (file:line under the reference checkout).  The C++
+ * plugin peers (rt-depth-map_b200/host/ headers: CUDAMatcherKonolige, CUDASemiGlobalMatcher,
+ * CUDAMorphologicalFilter) and the Python ctypes mirror (rt-depth-map_b200/rtdm_b200) both call
+ * exactly these functions.  Plain pointers and sizes only; no C++ or torch types.
+ *
+ * Error convention: 0 = ok, negative errno-style code otherwise (the flavour of the reference's
+ * include/errors.h:12-46): -RTDM_EINVAL for parameters cv::StereoBM/SGBM would assert on or that
+ * are outside the bit-exact domain, -RTDM_ENODEV when no CUDA device / kernel image is usable,
+ * -RTDM_ENOMEM on allocation failure, -RTDM_EIO on any other CUDA runtime failure.
+ * There is no CPU fallback: without a GPU every compute call fails with -RTDM_ENODEV.
+ */
+#ifndef RTDM_B200_H_
+#define RTDM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTDM_ABI_VERSION 1
+
+#define RTDM_EIO     5
+#define RTDM_ENOMEM  12
+#define RTDM_ENODEV  19
+#define RTDM_EINVAL  22
+#define RTDM_ENOSYS  38
+
+/* preFilterType values (cv::StereoBM::PREFILTER_*) */
+#define RTDM_PREFILTER_NORMALIZED_RESPONSE 0
+#define RTDM_PREFILTER_XSOBEL              1
+/* SGBM modes (cv::StereoSGBM::MODE_*) */
+#define RTDM_SGBM_MODE_SGBM 0   /* 5 paths; the reference's literal default (sgbm-sw.cpp:15) */
+#define RTDM_SGBM_MODE_HH   1   /* 8 paths, two passes */
+
+/* Matcher parameters.  One POD for both matchers; fields a matcher does not use are ignored.
+ * Mirrors what the reference's constructors set on the OpenCV objects:
+ *   SWMatcherKonolige::SWMatcherKonolige   stereo-matcher/bm-sw.cpp:12-26
+ *   SWSemiGlobalMatcher::SWSemiGlobalMatcher stereo-matcher/sgbm-sw.cpp:12-25 */
+typedef struct rtdm_params {
+    int preFilterType;      /* BM; default XSOBEL                                   */
+    int preFilterSize;      /* BM; default 9 (NORMALIZED_RESPONSE only)             */
+    int preFilterCap;       /* BM: 1..63 (bit-exact domain with disp12>=0: <=31); SGBM: 0 */
+    int blockSize;          /* odd; BM 5..  (bit-exact domain with disp12>=0: <=21) */
+    int minDisparity;
+    int numDisparities;     /* multiple of 16                                       */
+    int textureThreshold;   /* BM                                                   */
+    int uniquenessRatio;
+    int speckleWindowSize;
+    int speckleRange;
+    int disp12MaxDiff;
+    int mode;               /* SGBM: RTDM_SGBM_MODE_*                               */
+    int P1, P2;             /* SGBM                                                 */
+    int roi1[4];            /* x, y, w, h; w*h == 0 means "not set" (whole image)   */
+    int roi2[4];
+} rtdm_params;
+
+typedef struct rtdm_bm rtdm_bm;         /* opaque: Konolige block matcher      */
+typedef struct rtdm_sgbm rtdm_sgbm;     /* opaque: semi-global matcher         */
+typedef struct rtdm_morph rtdm_morph;   /* opaque: morphological filter device */
+
+/* ---- library ----------------------------------------------------------------------------- */
+int rtdm_abi_version(void);
+/* number of usable CUDA devices (0 when none; never negative) */
+int rtdm_device_count(void);
+/* last error message of the calling thread ("" if none) */
+const char *rtdm_last_error(void);
+/* fills *p with the defaults the reference's main.cpp:134-135 passes to SWMatcherKonolige
+ * (cap 31, bs 13, minD 0, tex 10, nd 128, uniq 10, speckle 100/32, disp12 1, XSOBEL, size 9). */
+void rtdm_params_default_bm(rtdm_params *p);
+/* defaults of SWSemiGlobalMatcher (sgbm-sw.cpp:15-24): bs 5, P1 600, P2 2400, MODE_SGBM. */
+void rtdm_params_default_sgbm(rtdm_params *p);
+
+/* ---- SWMatcherKonolige peer -------------------------------------------------------------- */
+/* replaces SWMatcherKonolige::SWMatcherKonolige (bm-sw.cpp:12-26).  max_batch frames of at most
+ * max_width x max_height can be in flight per call. */
+int rtdm_bm_create(rtdm_bm **out, const rtdm_params *p, int max_width, int max_height,
+                   int max_batch, int device);
+void rtdm_bm_destroy(rtdm_bm *h);
+/* replaces SWMatcherKonolige::setROI1 / setROI2 (bm-sw.cpp:40-48) */
+int rtdm_bm_set_roi1(rtdm_bm *h, int x, int y, int w, int hgt);
+int rtdm_bm_set_roi2(rtdm_bm *h, int x, int y, int w, int hgt);
+/* replaces SWMatcherKonolige::compute (bm-sw.cpp:33-38): HOST pointers, CV_8UC1 inputs with
+ * arbitrary row steps (bytes), CV_16SC1 output (x16 fixed point, invalid = (minD-1)*16) with row
+ * step dstep (bytes).  Synchronous: copies in, runs the CUDA pipeline, copies out. */
+int rtdm_bm_compute(rtdm_bm *h, const uint8_t *left, size_t lstep, const uint8_t *right,
+                    size_t rstep, int width, int height, int16_t *disp, size_t dstep);
+/* batched host variant: n frames, frame k at base + k*frame_stride (bytes). */
+int rtdm_bm_compute_batch(rtdm_bm *h, int n, const uint8_t *left, size_t lstep, size_t lframe,
+                          const uint8_t *right, size_t rstep, size_t rframe, int width, int height,
+                          int16_t *disp, size_t dstep, size_t dframe);
+/* device variant: DEVICE pointers, asynchronous on `cuda_stream` (a cudaStream_t, may be NULL =
+ * the handle's own stream).  Inputs/outputs stay resident in HBM. */
+int rtdm_bm_compute_device(rtdm_bm *h, int n, const uint8_t *left, size_t lstep, size_t lframe,
+                           const uint8_t *right, size_t rstep, size_t rframe, int width, int height,
+                           int16_t *disp, size_t dstep, size_t dframe, void *cuda_stream);
+/* number of kernel launches issued by the last compute call on this handle */
+int rtdm_bm_last_launches(const rtdm_bm *h);
+/* test hook: copy intermediate planes of frame 0 of the last compute call to host.
+ * what: 0 = prefiltered left, 1 = prefiltered right (uint8, width bytes per row),
+ *       2 = raw WTA disparity before validate/mask/speckle, 3 = cost (int16, width per row). */
+int rtdm_bm_debug_fetch(rtdm_bm *h, int what, void *dst, size_t dst_bytes);
+
+/* ---- SWSemiGlobalMatcher peer ------------------------------------------------------------ */
+/* replaces SWSemiGlobalMatcher::SWSemiGlobalMatcher (sgbm-sw.cpp:12-25) */
+int rtdm_sgbm_create(rtdm_sgbm **out, const rtdm_params *p, int max_width, int max_height,
+                     int max_batch, int device);
+void rtdm_sgbm_destroy(rtdm_sgbm *h);
+/* replaces SWSemiGlobalMatcher::compute (sgbm-sw.cpp:32-37); same contracts as the BM calls */
+int rtdm_sgbm_compute(rtdm_sgbm *h, const uint8_t *left, size_t lstep, const uint8_t *right,
+                      size_t rstep, int width, int height, int16_t *disp, size_t dstep);
+int rtdm_sgbm_compute_batch(rtdm_sgbm *h, int n, const uint8_t *left, size_t lstep, size_t lframe,
+                            const uint8_t *right, size_t rstep, size_t rframe, int width,
+                            int height, int16_t *disp, size_t dstep, size_t dframe);
+int rtdm_sgbm_compute_device(rtdm_sgbm *h, int n, const uint8_t *left, size_t lstep, size_t lframe,
+                             const uint8_t *right, size_t rstep, size_t rframe, int width,
+                             int height, int16_t *disp, size_t dstep, size_t dframe,
+                             void *cuda_stream);
+int rtdm_sgbm_last_launches(const rtdm_sgbm *h);
+
+/* ---- SWMorphologicalFilter peer ---------------------------------------------------------- */
+/* replaces SWMorphologicalFilter::SWMorphologicalFilter(w, h, bpp) (filter/mf-sw.cpp:10-17);
+ * bpp must be 8.  The in/out frame buffers are PINNED host memory owned by the handle, the
+ * analogue of VideoFilterDevice::video_in / video_out (include/filter/filter.h:33-34). */
+int rtdm_morph_create(rtdm_morph **out, int width, int height, int bpp, int max_batch, int device);
+void rtdm_morph_destroy(rtdm_morph *h);
+/* replace VideoFilterDevice::getVideoInBuffer / getVideoOutBuffer (filter/filter.cpp:45-53) */
+uint8_t *rtdm_morph_in_buffer(rtdm_morph *h);
+uint8_t *rtdm_morph_out_buffer(rtdm_morph *h);
+/* replaces SWMorphologicalFilter::run (filter/mf-sw.cpp:19-28): erode, dilate, dilate, erode with
+ * the 10x10 MORPH_ELLIPSE (MORPH_FILTER_DX/DY, include/filter/mf-sw.h:11-12).  HOST pointers
+ * (tightly packed width*height bytes); in/out may be the handle's own buffers.  Returns 0. */
+int rtdm_morph_run(rtdm_morph *h, const uint8_t *in, uint8_t *out);
+/* device variant: n tightly packed frames, asynchronous on cuda_stream */
+int rtdm_morph_run_device(rtdm_morph *h, int n, const uint8_t *in, uint8_t *out, void *cuda_stream);
+int rtdm_morph_last_launches(const rtdm_morph *h);
+
+/* ---- stand-alone stages (host pointers; used by the parity tests) -------------------------- */
+/* cv::filterSpeckles(img, newVal, maxSpeckleSize, maxDiff) on CV_16SC1, in place */
+int rtdm_filter_speckles(int16_t *img, size_t step, int width, int height, int newVal,
+                         int maxSpeckleSize, int maxDiff, int device);
+/* cv::medianBlur(src, dst, 3) on CV_16SC1 */
+int rtdm_median3_s16(const int16_t *src, size_t sstep, int16_t *dst, size_t dstep, int width,
+                     int height, int device);
+/* cv::erode (op 0) / cv::dilate (op 1) with getStructuringElement(MORPH_ELLIPSE, (kw, kh)),
+ * kw, kh <= 31, default anchor and border */
+int rtdm_morph_op(const uint8_t *src, size_t sstep, uint8_t *dst, size_t dstep, int width,
+                  int height, int kw, int kh, int op, int device);
+/* cv::validateDisparity on CV_16SC1 disparity + CV_16SC1 cost, in place */
+int rtdm_validate_disparity(int16_t *disp, size_t dstep, const int16_t *cost, size_t cstep,
+                            int width, int height, int minDisparity, int numDisparities,
+                            int disp12MaxDiff, int device);
+
+/* ---- measurement helper ------------------------------------------------------------------- */
+/* Measures the integer-ALU issue peak of the device with dependent-free packed-integer loops
+ * (the roofline denominator SURVEY.md 8(d) asks for).  Results in 1e12 lane-ops/s. */
+int rtdm_measure_int_peak(int device, double *tiops_iadd3, double *tiops_vimnmx,
+                          double *tiops_vabsdiff4, double *sm_mhz_est);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTDM_B200_H_ */

@@ -1,0 +1,493 @@
+// api.cu -- the extern "C" boundary (include/rtdm_b200.h): handles, workspaces, pipelines.
+//
+// Host side of the drop-in: what SWMatcherKonolige / SWSemiGlobalMatcher / SWMorphologicalFilter do
+// on the CPU through OpenCV (reference stereo-matcher/bm-sw.cpp, sgbm-sw.cpp, filter/mf-sw.cpp) is
+// issued here as a fixed sequence of sm_100a kernels on a CUDA stream.  No CPU fallback exists: every
+// compute entry point fails with -RTDM_ENODEV when no device is usable.
+#include "common.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+namespace rtdm {
+
+static thread_local std::string g_err;
+void set_error(const std::string &msg) { g_err = msg; }
+
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
+{
+    char buf[512];
+    snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+    g_err = buf;
+    cudaGetLastError();   // clear sticky-less errors
+    if (e == cudaErrorMemoryAllocation) return -RTDM_ENOMEM;
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInvalidDevice ||
+        e == cudaErrorNoKernelImageForDevice || e == cudaErrorInitializationError)
+        return -RTDM_ENODEV;
+    return -RTDM_EIO;
+}
+
+static int check_device(int device)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available (this library has no CPU fallback)");
+        return -RTDM_ENODEV;
+    }
+    if (device < 0 || device >= n) { set_error("invalid device index"); return -RTDM_ENODEV; }
+    return 0;
+}
+
+template <typename T>
+static int dev_alloc(T **p, size_t count)
+{
+    *p = nullptr;
+    if (count == 0) return 0;
+    RTDM_CUDA(cudaMalloc((void **)p, count * sizeof(T)));
+    return 0;
+}
+
+struct ValidRect { int x, y, w, h; };
+
+// getValidDisparityROI (oracle: orc_valid_roi)
+static ValidRect valid_rect(const int roi1[4], const int roi2[4], int W, int H, int minD, int nd, int bs)
+{
+    int r1[4] = {0, 0, W, H}, r2[4] = {0, 0, W, H};
+    if (roi1[2] > 0 && roi1[3] > 0) memcpy(r1, roi1, sizeof r1);
+    if (roi2[2] > 0 && roi2[3] > 0) memcpy(r2, roi2, sizeof r2);
+    int h = bs / 2, maxD = minD + nd - 1;
+    int xmin = std::max(r1[0], r2[0] + maxD) + h;
+    int xmax = std::min(r1[0] + r1[2], r2[0] + r2[2]) - h;
+    int ymin = std::max(r1[1], r2[1]) + h;
+    int ymax = std::min(r1[1] + r1[3], r2[1] + r2[3]) - h;
+    ValidRect v = {0, 0, 0, 0};
+    if (xmax - xmin > 0 && ymax - ymin > 0) { v.x = xmin; v.y = ymin; v.w = xmax - xmin; v.h = ymax - ymin; }
+    return v;
+}
+
+}  // namespace rtdm
+
+using namespace rtdm;
+
+// =================================================================================================
+// BM
+// =================================================================================================
+struct rtdm_bm {
+    rtdm_params p;
+    int maxW, maxH, maxB, dev;
+    cudaStream_t st;
+    // per-batch device workspace (maxB frames)
+    uint8_t *Lp, *Rp;            size_t ppitch, pframe;      // prefiltered planes (bytes)
+    int16_t *raw, *cost;         size_t rpitch, rframe;      // raw WTA disparity + cost (elements)
+    int32_t *labels, *sizes;
+    // staging for the host entry points
+    uint8_t *dL, *dR;            size_t spitch, sframe;      // device copies of the inputs
+    int16_t *dD;                 size_t dpitch, dframe;      // device copy of the output (elements)
+    int launches;
+    int lastW, lastH;
+};
+
+static int bm_check_params(const rtdm_params *p)
+{
+    if (p->preFilterType != RTDM_PREFILTER_NORMALIZED_RESPONSE && p->preFilterType != RTDM_PREFILTER_XSOBEL) { set_error("bm: preFilterType must be 0 or 1"); return -RTDM_EINVAL; }
+    if (p->preFilterSize < 5 || p->preFilterSize > 255 || p->preFilterSize % 2 == 0) { set_error("bm: preFilterSize must be odd and within 5..255"); return -RTDM_EINVAL; }
+    if (p->preFilterCap < 1 || p->preFilterCap > 63) { set_error("bm: preFilterCap must be within 1..63"); return -RTDM_EINVAL; }
+    if (p->blockSize < 5 || p->blockSize > 255 || p->blockSize % 2 == 0) { set_error("bm: blockSize must be odd and within 5..255"); return -RTDM_EINVAL; }
+    if (p->numDisparities <= 0 || p->numDisparities % 16 != 0) { set_error("bm: numDisparities must be positive and divisible by 16"); return -RTDM_EINVAL; }
+    if (p->textureThreshold < 0) { set_error("bm: textureThreshold must be non-negative"); return -RTDM_EINVAL; }
+    if (p->uniquenessRatio < 0) { set_error("bm: uniquenessRatio must be non-negative"); return -RTDM_EINVAL; }
+    // kernel domain (documented in DESIGN.md): 16-bit window sums, at most 256 disparities
+    if (p->numDisparities > 256) { set_error("bm: numDisparities > 256 is not supported"); return -RTDM_EINVAL; }
+    if (2 * p->preFilterCap * p->blockSize * p->blockSize > 65535) { set_error("bm: 2*cap*blockSize^2 exceeds the 16-bit SAD domain"); return -RTDM_EINVAL; }
+    if (p->disp12MaxDiff >= 0 && (p->preFilterCap > 31 || p->blockSize > 21)) {
+        set_error("bm: disp12MaxDiff >= 0 with preFilterCap > 31 or blockSize > 21 is outside the bit-exact domain (SURVEY.md App. B.2)");
+        return -RTDM_EINVAL;
+    }
+    return 0;
+}
+
+extern "C" int rtdm_abi_version(void) { return RTDM_ABI_VERSION; }
+
+extern "C" int rtdm_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" const char *rtdm_last_error(void) { return g_err.c_str(); }
+
+extern "C" void rtdm_params_default_bm(rtdm_params *p)
+{
+    memset(p, 0, sizeof *p);
+    p->preFilterType = RTDM_PREFILTER_XSOBEL; p->preFilterSize = 9; p->preFilterCap = 31;
+    p->blockSize = 13; p->minDisparity = 0; p->numDisparities = 128; p->textureThreshold = 10;
+    p->uniquenessRatio = 10; p->speckleWindowSize = 100; p->speckleRange = 32; p->disp12MaxDiff = 1;
+}
+
+extern "C" void rtdm_params_default_sgbm(rtdm_params *p)
+{
+    memset(p, 0, sizeof *p);
+    p->preFilterType = RTDM_PREFILTER_XSOBEL; p->preFilterSize = 9; p->preFilterCap = 0;
+    p->blockSize = 5; p->minDisparity = 0; p->numDisparities = 128; p->uniquenessRatio = 10;
+    p->speckleWindowSize = 100; p->speckleRange = 32; p->disp12MaxDiff = 1;
+    p->mode = RTDM_SGBM_MODE_SGBM; p->P1 = 8 * 3 * 5 * 5; p->P2 = 32 * 3 * 5 * 5;
+}
+
+extern "C" void rtdm_bm_destroy(rtdm_bm *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->dev);
+    cudaFree(h->Lp); cudaFree(h->Rp); cudaFree(h->raw); cudaFree(h->cost);
+    cudaFree(h->labels); cudaFree(h->sizes); cudaFree(h->dL); cudaFree(h->dR); cudaFree(h->dD);
+    if (h->st) cudaStreamDestroy(h->st);
+    delete h;
+}
+
+extern "C" int rtdm_bm_create(rtdm_bm **out, const rtdm_params *p, int max_width, int max_height,
+                              int max_batch, int device)
+{
+    if (!out || !p) { set_error("bm_create: null argument"); return -RTDM_EINVAL; }
+    *out = nullptr;
+    int rc = bm_check_params(p);
+    if (rc) return rc;
+    if (max_width < 1 || max_height < 1 || max_batch < 1 || max_width > 8000 || max_height > 65535) {
+        set_error("bm_create: bad maximum geometry (width <= 8000, height <= 65535, batch >= 1)");
+        return -RTDM_EINVAL;
+    }
+    rc = check_device(device);
+    if (rc) return rc;
+    RTDM_CUDA(cudaSetDevice(device));
+    rtdm_bm *h = new (std::nothrow) rtdm_bm();
+    if (!h) return -RTDM_ENOMEM;
+    memset(h, 0, sizeof *h);
+    h->p = *p; h->maxW = max_width; h->maxH = max_height; h->maxB = max_batch; h->dev = device;
+    const size_t B = (size_t)max_batch;
+    h->ppitch = align_up((size_t)max_width + 160, 64);          // over-read slack for the band loader
+    h->pframe = h->ppitch * max_height;
+    h->rpitch = align_up((size_t)max_width, 8); h->rframe = h->rpitch * max_height;
+    h->spitch = align_up((size_t)max_width, 64); h->sframe = h->spitch * max_height;
+    h->dpitch = h->rpitch; h->dframe = h->rframe;
+    rc = (int)cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) == cudaSuccess ? 0 : -RTDM_EIO;
+    if (!rc) rc = dev_alloc(&h->Lp, h->pframe * B + 4096);
+    if (!rc) rc = dev_alloc(&h->Rp, h->pframe * B + 4096);
+    if (!rc) rc = dev_alloc(&h->raw, h->rframe * B);
+    if (!rc) rc = dev_alloc(&h->cost, h->rframe * B);
+    if (!rc) rc = dev_alloc(&h->labels, (size_t)max_width * max_height * B);
+    if (!rc) rc = dev_alloc(&h->sizes, (size_t)max_width * max_height * B);
+    if (!rc) rc = dev_alloc(&h->dL, h->sframe * B);
+    if (!rc) rc = dev_alloc(&h->dR, h->sframe * B);
+    if (!rc) rc = dev_alloc(&h->dD, h->dframe * B);
+    if (rc) { rtdm_bm_destroy(h); return rc; }
+    *out = h;
+    return 0;
+}
+
+extern "C" int rtdm_bm_set_roi1(rtdm_bm *h, int x, int y, int w, int hgt)
+{
+    if (!h) return -RTDM_EINVAL;
+    h->p.roi1[0] = x; h->p.roi1[1] = y; h->p.roi1[2] = w; h->p.roi1[3] = hgt;
+    return 0;
+}
+
+extern "C" int rtdm_bm_set_roi2(rtdm_bm *h, int x, int y, int w, int hgt)
+{
+    if (!h) return -RTDM_EINVAL;
+    h->p.roi2[0] = x; h->p.roi2[1] = y; h->p.roi2[2] = w; h->p.roi2[3] = hgt;
+    return 0;
+}
+
+// the kernel pipeline on device-resident frames
+static int bm_pipeline(rtdm_bm *h, int n, PlaneU8 L, PlaneU8 R, int W, int H, PlaneS16 out, cudaStream_t st)
+{
+    const rtdm_params &p = h->p;
+    if (W > h->maxW || H > h->maxH || n > h->maxB || W < 1 || H < 1 || n < 1) {
+        set_error("bm: frame geometry or batch exceeds what the handle was created for");
+        return -RTDM_EINVAL;
+    }
+    if (p.blockSize >= W || p.blockSize >= H) {
+        set_error("bm: blockSize must be smaller than the image"); return -RTDM_EINVAL;
+    }
+    h->lastW = W; h->lastH = H;
+    const int nd = p.numDisparities, minD = p.minDisparity;
+    const int FILT = (minD - 1) * 16;
+    BmGeom g;
+    g.W = W; g.H = H; g.nd = nd; g.minD = minD; g.bs = p.blockSize; g.cap = p.preFilterCap;
+    g.texThr = p.textureThreshold; g.uniq = p.uniquenessRatio;
+    g.lofs = std::max(nd - 1 + minD, 0); g.rofs = -std::min(nd - 1 + minD, 0);
+    g.W1 = W - g.rofs - nd + 1;
+    ValidRect vr = valid_rect(p.roi1, p.roi2, W, H, minD, nd, p.blockSize);
+    int row0 = std::min(std::max(vr.y, 0), H), row1 = std::min(std::max(vr.y + vr.h, 0), H);
+    if (vr.w == 0 || vr.h == 0 || g.lofs >= W || g.rofs >= W || g.W1 < 1) row0 = row1 = 0;
+    g.row0 = row0; g.row1 = row1;
+    int rc = 0;
+    PlaneS16 raw = {h->raw, h->rpitch, h->rframe}, cost = {h->cost, h->rpitch, h->rframe};
+    if (row1 > row0) {
+        PlaneU8W oL = {h->Lp, h->ppitch, h->pframe}, oR = {h->Rp, h->ppitch, h->pframe};
+        rc = launch_prefilter(p.preFilterType, p.preFilterSize, p.preFilterCap, n, W, H, L, R, oL, oR, st, &h->launches);
+        if (rc) return rc;
+        PlaneU8 iL = {h->Lp, h->ppitch, h->pframe}, iR = {h->Rp, h->ppitch, h->pframe};
+        rc = launch_bm_sad_wta(g, n, iL, iR, raw, cost, st, &h->launches);
+        if (rc) return rc;
+    }
+    rc = launch_validate_mask(n, W, H, minD, nd, p.disp12MaxDiff, g.lofs, g.W1,
+                              std::max(vr.x, 0), std::max(vr.x + vr.w, 0), row0, row1, raw, cost, out, st, &h->launches);
+    if (rc) return rc;
+    if (p.speckleRange >= 0 && p.speckleWindowSize > 0)
+        rc = launch_speckle(n, W, H, out, FILT, p.speckleWindowSize, p.speckleRange, h->labels, h->sizes, st, &h->launches);
+    return rc;
+}
+
+extern "C" int rtdm_bm_compute_device(rtdm_bm *h, int n, const uint8_t *left, size_t lstep, size_t lframe,
+                                      const uint8_t *right, size_t rstep, size_t rframe, int width, int height,
+                                      int16_t *disp, size_t dstep, size_t dframe, void *cuda_stream)
+{
+    if (!h || !left || !right || !disp) { set_error("bm_compute_device: null argument"); return -RTDM_EINVAL; }
+    if (dstep % 2 || dframe % 2) { set_error("bm: output steps must be multiples of 2 bytes"); return -RTDM_EINVAL; }
+    RTDM_CUDA(cudaSetDevice(h->dev));
+    h->launches = 0;
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->st;
+    PlaneU8 L = {left, lstep, lframe}, R = {right, rstep, rframe};
+    PlaneS16 out = {disp, dstep / 2, dframe / 2};
+    return bm_pipeline(h, n, L, R, width, height, out, st);
+}
+
+extern "C" int rtdm_bm_compute_batch(rtdm_bm *h, int n, const uint8_t *left, size_t lstep, size_t lframe,
+                                     const uint8_t *right, size_t rstep, size_t rframe, int width, int height,
+                                     int16_t *disp, size_t dstep, size_t dframe)
+{
+    if (!h || !left || !right || !disp) { set_error("bm_compute: null argument"); return -RTDM_EINVAL; }
+    if (n < 1 || n > h->maxB || width > h->maxW || height > h->maxH || width < 1 || height < 1) {
+        set_error("bm: frame geometry or batch exceeds what the handle was created for");
+        return -RTDM_EINVAL;
+    }
+    RTDM_CUDA(cudaSetDevice(h->dev));
+    h->launches = 0;
+    cudaStream_t st = h->st;
+    for (int k = 0; k < n; k++) {
+        RTDM_CUDA(cudaMemcpy2DAsync(h->dL + k * h->sframe, h->spitch, left + k * lframe, lstep, width, height, cudaMemcpyHostToDevice, st));
+        RTDM_CUDA(cudaMemcpy2DAsync(h->dR + k * h->sframe, h->spitch, right + k * rframe, rstep, width, height, cudaMemcpyHostToDevice, st));
+    }
+    PlaneU8 L = {h->dL, h->spitch, h->sframe}, R = {h->dR, h->spitch, h->sframe};
+    PlaneS16 out = {h->dD, h->dpitch, h->dframe};
+    int rc = bm_pipeline(h, n, L, R, width, height, out, st);
+    if (rc) return rc;
+    for (int k = 0; k < n; k++)
+        RTDM_CUDA(cudaMemcpy2DAsync((uint8_t *)disp + k * dframe, dstep, h->dD + k * h->dframe, h->dpitch * 2,
+                                    (size_t)width * 2, height, cudaMemcpyDeviceToHost, st));
+    RTDM_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" int rtdm_bm_compute(rtdm_bm *h, const uint8_t *left, size_t lstep, const uint8_t *right,
+                               size_t rstep, int width, int height, int16_t *disp, size_t dstep)
+{
+    return rtdm_bm_compute_batch(h, 1, left, lstep, 0, right, rstep, 0, width, height, disp, dstep, 0);
+}
+
+extern "C" int rtdm_bm_last_launches(const rtdm_bm *h) { return h ? h->launches : 0; }
+
+extern "C" int rtdm_bm_debug_fetch(rtdm_bm *h, int what, void *dst, size_t dst_bytes)
+{
+    if (!h || !dst || h->lastW <= 0) { set_error("debug_fetch: nothing computed yet"); return -RTDM_EINVAL; }
+    RTDM_CUDA(cudaSetDevice(h->dev));
+    RTDM_CUDA(cudaStreamSynchronize(h->st));
+    const int W = h->lastW, H = h->lastH;
+    if (what == 0 || what == 1) {
+        if (dst_bytes < (size_t)W * H) return -RTDM_EINVAL;
+        RTDM_CUDA(cudaMemcpy2D(dst, W, what ? h->Rp : h->Lp, h->ppitch, W, H, cudaMemcpyDeviceToHost));
+    } else if (what == 2 || what == 3) {
+        if (dst_bytes < (size_t)W * H * 2) return -RTDM_EINVAL;
+        RTDM_CUDA(cudaMemcpy2D(dst, (size_t)W * 2, what == 3 ? h->cost : h->raw, h->rpitch * 2, (size_t)W * 2, H, cudaMemcpyDeviceToHost));
+    } else return -RTDM_EINVAL;
+    return 0;
+}
+
+// =================================================================================================
+// morphological filter
+// =================================================================================================
+struct rtdm_morph {
+    int W, H, maxB, dev;
+    cudaStream_t st;
+    uint8_t *hin, *hout;         // pinned host frame buffers (video_in / video_out)
+    uint8_t *d0, *d1;            // device ping-pong, maxB frames, tightly packed
+    MorphSE se;
+    int launches;
+};
+
+extern "C" void rtdm_morph_destroy(rtdm_morph *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->dev);
+    if (h->hin) cudaFreeHost(h->hin);
+    if (h->hout) cudaFreeHost(h->hout);
+    cudaFree(h->d0); cudaFree(h->d1);
+    if (h->st) cudaStreamDestroy(h->st);
+    delete h;
+}
+
+extern "C" int rtdm_morph_create(rtdm_morph **out, int width, int height, int bpp, int max_batch, int device)
+{
+    if (!out) return -RTDM_EINVAL;
+    *out = nullptr;
+    if (bpp != 8 || width < 1 || height < 1 || max_batch < 1) { set_error("morph_create: bpp must be 8 and geometry positive"); return -RTDM_EINVAL; }
+    int rc = check_device(device);
+    if (rc) return rc;
+    RTDM_CUDA(cudaSetDevice(device));
+    rtdm_morph *h = new (std::nothrow) rtdm_morph();
+    if (!h) return -RTDM_ENOMEM;
+    memset(h, 0, sizeof *h);
+    h->W = width; h->H = height; h->maxB = max_batch; h->dev = device;
+    make_ellipse(10, 10, &h->se);      // MORPH_FILTER_DX x MORPH_FILTER_DY (include/filter/mf-sw.h:11-12)
+    const size_t fb = (size_t)width * height;
+    rc = cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) == cudaSuccess ? 0 : -RTDM_EIO;
+    if (!rc && cudaHostAlloc((void **)&h->hin, fb, cudaHostAllocDefault) != cudaSuccess) rc = -RTDM_ENOMEM;
+    if (!rc && cudaHostAlloc((void **)&h->hout, fb, cudaHostAllocDefault) != cudaSuccess) rc = -RTDM_ENOMEM;
+    if (!rc) rc = dev_alloc(&h->d0, fb * max_batch);
+    if (!rc) rc = dev_alloc(&h->d1, fb * max_batch);
+    if (rc) { rtdm_morph_destroy(h); return rc; }
+    *out = h;
+    return 0;
+}
+
+extern "C" uint8_t *rtdm_morph_in_buffer(rtdm_morph *h) { return h ? h->hin : nullptr; }
+extern "C" uint8_t *rtdm_morph_out_buffer(rtdm_morph *h) { return h ? h->hout : nullptr; }
+extern "C" int rtdm_morph_last_launches(const rtdm_morph *h) { return h ? h->launches : 0; }
+
+// erode, dilate, dilate, erode: src -> a -> b -> a -> dst
+static int morph_pipeline(rtdm_morph *h, int n, const uint8_t *src, uint8_t *dst, uint8_t *ta, uint8_t *tb, cudaStream_t st)
+{
+    const size_t W = h->W, fb = (size_t)h->W * h->H;
+    int rc;
+    rc = launch_morph(n, h->W, h->H, PlaneU8{src, W, fb}, PlaneU8W{ta, W, fb}, h->se, 0, st, &h->launches); if (rc) return rc;
+    rc = launch_morph(n, h->W, h->H, PlaneU8{ta, W, fb}, PlaneU8W{tb, W, fb}, h->se, 1, st, &h->launches); if (rc) return rc;
+    rc = launch_morph(n, h->W, h->H, PlaneU8{tb, W, fb}, PlaneU8W{ta, W, fb}, h->se, 1, st, &h->launches); if (rc) return rc;
+    rc = launch_morph(n, h->W, h->H, PlaneU8{ta, W, fb}, PlaneU8W{dst, W, fb}, h->se, 0, st, &h->launches);
+    return rc;
+}
+
+extern "C" int rtdm_morph_run(rtdm_morph *h, const uint8_t *in, uint8_t *out)
+{
+    if (!h || !in || !out) { set_error("morph_run: null argument"); return -RTDM_EINVAL; }
+    RTDM_CUDA(cudaSetDevice(h->dev));
+    h->launches = 0;
+    const size_t fb = (size_t)h->W * h->H;
+    // d1[0..fb) holds the input copy; results ping-pong between d0 and the tail of... keep it simple:
+    RTDM_CUDA(cudaMemcpyAsync(h->d1, in, fb, cudaMemcpyHostToDevice, h->st));
+    // src=d1 -> d0 -> d1 -> d0 -> d1
+    int rc = morph_pipeline(h, 1, h->d1, h->d1, h->d0, h->d1, h->st);
+    if (rc) return rc;
+    RTDM_CUDA(cudaMemcpyAsync(out, h->d1, fb, cudaMemcpyDeviceToHost, h->st));
+    RTDM_CUDA(cudaStreamSynchronize(h->st));
+    return 0;
+}
+
+extern "C" int rtdm_morph_run_device(rtdm_morph *h, int n, const uint8_t *in, uint8_t *out, void *cuda_stream)
+{
+    if (!h || !in || !out) { set_error("morph_run_device: null argument"); return -RTDM_EINVAL; }
+    if (n < 1 || n > h->maxB) { set_error("morph: batch exceeds what the handle was created for"); return -RTDM_EINVAL; }
+    RTDM_CUDA(cudaSetDevice(h->dev));
+    h->launches = 0;
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->st;
+    return morph_pipeline(h, n, in, out, h->d0, h->d1, st);
+}
+
+// =================================================================================================
+// stand-alone stages (host pointers)
+// =================================================================================================
+extern "C" int rtdm_filter_speckles(int16_t *img, size_t step, int width, int height, int newVal,
+                                    int maxSpeckleSize, int maxDiff, int device)
+{
+    if (!img || width < 1 || height < 1 || step % 2) return -RTDM_EINVAL;
+    int rc = check_device(device);
+    if (rc) return rc;
+    RTDM_CUDA(cudaSetDevice(device));
+    int16_t *d = nullptr; int32_t *lab = nullptr, *siz = nullptr;
+    const size_t N = (size_t)width * height;
+    rc = dev_alloc(&d, N);
+    if (!rc) rc = dev_alloc(&lab, N);
+    if (!rc) rc = dev_alloc(&siz, N);
+    if (!rc) {
+        cudaError_t e = cudaMemcpy2D(d, (size_t)width * 2, img, step, (size_t)width * 2, height, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) rc = cuda_fail(e, "memcpy2d", __FILE__, __LINE__);
+    }
+    if (!rc) rc = launch_speckle(1, width, height, PlaneS16{d, (size_t)width, N}, newVal, maxSpeckleSize, maxDiff, lab, siz, 0, nullptr);
+    if (!rc) {
+        cudaError_t e = cudaMemcpy2D(img, step, d, (size_t)width * 2, (size_t)width * 2, height, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = cuda_fail(e, "memcpy2d", __FILE__, __LINE__);
+    }
+    cudaFree(d); cudaFree(lab); cudaFree(siz);
+    return rc;
+}
+
+extern "C" int rtdm_median3_s16(const int16_t *src, size_t sstep, int16_t *dst, size_t dstep, int width,
+                                int height, int device)
+{
+    if (!src || !dst || width < 1 || height < 1) return -RTDM_EINVAL;
+    int rc = check_device(device);
+    if (rc) return rc;
+    RTDM_CUDA(cudaSetDevice(device));
+    int16_t *a = nullptr, *b = nullptr;
+    const size_t N = (size_t)width * height;
+    rc = dev_alloc(&a, N);
+    if (!rc) rc = dev_alloc(&b, N);
+    if (!rc) { cudaError_t e = cudaMemcpy2D(a, (size_t)width * 2, src, sstep, (size_t)width * 2, height, cudaMemcpyHostToDevice); if (e != cudaSuccess) rc = cuda_fail(e, "memcpy2d", __FILE__, __LINE__); }
+    if (!rc) rc = launch_median3(1, width, height, PlaneS16{a, (size_t)width, N}, PlaneS16{b, (size_t)width, N}, 0, nullptr);
+    if (!rc) { cudaError_t e = cudaMemcpy2D(dst, dstep, b, (size_t)width * 2, (size_t)width * 2, height, cudaMemcpyDeviceToHost); if (e != cudaSuccess) rc = cuda_fail(e, "memcpy2d", __FILE__, __LINE__); }
+    cudaFree(a); cudaFree(b);
+    return rc;
+}
+
+extern "C" int rtdm_morph_op(const uint8_t *src, size_t sstep, uint8_t *dst, size_t dstep, int width,
+                             int height, int kw, int kh, int op, int device)
+{
+    if (!src || !dst || width < 1 || height < 1 || kw < 1 || kh < 1 || kw > 31 || kh > 31 || (op != 0 && op != 1)) return -RTDM_EINVAL;
+    int rc = check_device(device);
+    if (rc) return rc;
+    RTDM_CUDA(cudaSetDevice(device));
+    uint8_t *a = nullptr, *b = nullptr;
+    const size_t N = (size_t)width * height;
+    rc = dev_alloc(&a, N);
+    if (!rc) rc = dev_alloc(&b, N);
+    MorphSE se; make_ellipse(kw, kh, &se);
+    if (!rc) { cudaError_t e = cudaMemcpy2D(a, width, src, sstep, width, height, cudaMemcpyHostToDevice); if (e != cudaSuccess) rc = cuda_fail(e, "memcpy2d", __FILE__, __LINE__); }
+    if (!rc) rc = launch_morph(1, width, height, PlaneU8{a, (size_t)width, N}, PlaneU8W{b, (size_t)width, N}, se, op, 0, nullptr);
+    if (!rc) { cudaError_t e = cudaMemcpy2D(dst, dstep, b, width, width, height, cudaMemcpyDeviceToHost); if (e != cudaSuccess) rc = cuda_fail(e, "memcpy2d", __FILE__, __LINE__); }
+    cudaFree(a); cudaFree(b);
+    return rc;
+}
+
+extern "C" int rtdm_validate_disparity(int16_t *disp, size_t dstep, const int16_t *cost, size_t cstep,
+                                       int width, int height, int minDisparity, int numDisparities,
+                                       int disp12MaxDiff, int device)
+{
+    if (!disp || !cost || width < 1 || height < 1 || width > 8000 || dstep % 2 || cstep % 2) return -RTDM_EINVAL;
+    int rc = check_device(device);
+    if (rc) return rc;
+    RTDM_CUDA(cudaSetDevice(device));
+    int16_t *a = nullptr, *c = nullptr, *o = nullptr;
+    const size_t N = (size_t)width * height;
+    rc = dev_alloc(&a, N);
+    if (!rc) rc = dev_alloc(&c, N);
+    if (!rc) rc = dev_alloc(&o, N);
+    if (!rc) { cudaError_t e = cudaMemcpy2D(a, (size_t)width * 2, disp, dstep, (size_t)width * 2, height, cudaMemcpyHostToDevice); if (e != cudaSuccess) rc = cuda_fail(e, "memcpy2d", __FILE__, __LINE__); }
+    if (!rc) { cudaError_t e = cudaMemcpy2D(c, (size_t)width * 2, cost, cstep, (size_t)width * 2, height, cudaMemcpyHostToDevice); if (e != cudaSuccess) rc = cuda_fail(e, "memcpy2d", __FILE__, __LINE__); }
+    if (!rc) rc = launch_validate_mask(1, width, height, minDisparity, numDisparities, disp12MaxDiff, 0, width, 0, width, 0, height,
+                                       PlaneS16{a, (size_t)width, N}, PlaneS16{c, (size_t)width, N}, PlaneS16{o, (size_t)width, N}, 0, nullptr);
+    if (!rc) { cudaError_t e = cudaMemcpy2D(disp, dstep, o, (size_t)width * 2, (size_t)width * 2, height, cudaMemcpyDeviceToHost); if (e != cudaSuccess) rc = cuda_fail(e, "memcpy2d", __FILE__, __LINE__); }
+    cudaFree(a); cudaFree(c); cudaFree(o);
+    return rc;
+}
+
+extern "C" int rtdm_measure_int_peak(int device, double *tiops_iadd3, double *tiops_vimnmx,
+                                     double *tiops_vabsdiff4, double *sm_mhz_est)
+{
+    int rc = check_device(device);
+    if (rc) return rc;
+    return measure_int_peak(device, tiops_iadd3, tiops_vimnmx, tiops_vabsdiff4, sm_mhz_est);
+}

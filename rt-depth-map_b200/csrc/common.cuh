@@ -1,0 +1,83 @@
+// common.cuh -- shared declarations for the sm_100a stereo kernels and their launchers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <string>
+
+#include "../../include/rtdm_b200.h"
+
+namespace rtdm {
+
+void set_error(const std::string &msg);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define RTDM_CUDA(expr)                                                        \
+    do {                                                                       \
+        cudaError_t _e = (expr);                                               \
+        if (_e != cudaSuccess) return ::rtdm::cuda_fail(_e, #expr, __FILE__, __LINE__); \
+    } while (0)
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---------------------------------------------------------------------------------------------
+// image planes: n frames, `pitch` bytes (u8) or elements (i16) per row, `frame` per frame
+// ---------------------------------------------------------------------------------------------
+struct PlaneU8 { const uint8_t *p; size_t pitch; size_t frame; };
+struct PlaneU8W { uint8_t *p; size_t pitch; size_t frame; };
+struct PlaneS16 { int16_t *p; size_t pitch; size_t frame; };   // pitch / frame in ELEMENTS
+
+// ---- prefilter (prefilter.cu) ------------------------------------------------------------------
+// type: RTDM_PREFILTER_*.  Both images of all n frames in one launch.
+int launch_prefilter(int type, int winsize, int cap, int n, int W, int H,
+                     PlaneU8 left, PlaneU8 right, PlaneU8W outL, PlaneU8W outR,
+                     cudaStream_t st, int *launches);
+
+// ---- block matching core (bm_sad.cu) -----------------------------------------------------------
+struct BmGeom {
+    int W, H, nd, minD, bs, cap, texThr, uniq;
+    int lofs, rofs, W1;
+    int row0, row1;          // rows to compute (valid rect rows)
+};
+size_t bm_sad_smem_bytes(const BmGeom &g, int TW, int BH);
+int launch_bm_sad_wta(const BmGeom &g, int n, PlaneU8 Lp, PlaneU8 Rp, PlaneS16 disp, PlaneS16 cost,
+                      cudaStream_t st, int *launches);
+
+// ---- post-processing (postproc.cu) -------------------------------------------------------------
+// validateDisparity (if d12 >= 0) + valid-rect mask; reads raw disp/cost, writes `out`
+int launch_validate_mask(int n, int W, int H, int minD, int nd, int d12, int lofs, int W1,
+                         int vx0, int vx1, int row0, int row1,
+                         PlaneS16 raw, PlaneS16 cost, PlaneS16 out, cudaStream_t st, int *launches);
+// filterSpeckles on n frames in place; labels: n*W*H int32, sizes: n*W*H int32 scratch
+int launch_speckle(int n, int W, int H, PlaneS16 img, int newVal, int maxSize, int maxDiff,
+                   int32_t *labels, int32_t *sizes, cudaStream_t st, int *launches);
+int launch_median3(int n, int W, int H, PlaneS16 src, PlaneS16 dst, cudaStream_t st, int *launches);
+
+// ---- morphology (morph.cu) ---------------------------------------------------------------------
+struct MorphSE { int kw, kh, ax, ay; int j1[32], j2[32]; };
+void make_ellipse(int kw, int kh, MorphSE *se);
+int launch_morph(int n, int W, int H, PlaneU8 src, PlaneU8W dst, const MorphSE &se, int op,
+                 cudaStream_t st, int *launches);
+
+// ---- SGBM (sgbm.cu) ----------------------------------------------------------------------------
+struct SgbmGeom {
+    int W, H, D, minD, bs, P1, P2, uniq, d12, ftzero, mode;
+    int minX1, maxX1, W1;
+};
+struct SgbmWork {
+    uint8_t *planes;    // per frame: BT planes (see sgbm.cu)
+    int16_t *pix;       // per-pixel cost rows / horizontal sums
+    int16_t *C;         // cost volume      [H][W1][D]
+    int16_t *S;         // aggregated volume [H][W1][D]
+    int16_t *disp2;     // per-row scratch
+    size_t frame_planes, frame_vol;
+};
+size_t sgbm_work_bytes(const SgbmGeom &g, size_t *planes, size_t *vol);
+int launch_sgbm(const SgbmGeom &g, int n, PlaneU8 left, PlaneU8 right, PlaneS16 out, SgbmWork w,
+                cudaStream_t st, int *launches);
+
+// ---- int peak microbenchmark (intpeak.cu) -------------------------------------------------------
+int measure_int_peak(int device, double *iadd3, double *vimnmx, double *vabsdiff4, double *mhz);
+
+}  // namespace rtdm

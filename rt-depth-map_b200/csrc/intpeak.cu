@@ -1,0 +1,84 @@
+// intpeak.cu -- integer-ALU issue-rate microbenchmark (roofline denominator).
+// Dependent-free chains (8 independent accumulators per thread) of IADD3, VIMNMX.U16x2 and
+// VABSDIFF4.U8; result = lane-operations per second over the whole chip.
+#include "common.cuh"
+
+namespace rtdm {
+namespace {
+
+template <int OP>
+__global__ void __launch_bounds__(256)
+intpeak_kernel(uint32_t *out, int iters, uint32_t seed)
+{
+    uint32_t a[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) a[i] = seed * (threadIdx.x + 1) + i * 0x01010101u;
+    uint32_t b = seed ^ 0x00ff00ffu, c = seed + 0x10203040u;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                if (OP == 0) a[i] = a[i] + b + c;                        // IADD3
+                else if (OP == 1) a[i] = __vminu2(a[i] + 0u, b) ^ c;     // VIMNMX.U16x2 (+ LOP3 to keep it live)
+                else a[i] = __vabsdiffu4(a[i], b) + c;                   // VABSDIFF4 (+ IADD)
+            }
+            b += 0x00010001u;
+        }
+    }
+    uint32_t r = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r ^= a[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
+template <int OP>
+int run_one(uint32_t *buf, int blocks, int iters, double ops_per_inner, double *tiops)
+{
+    cudaEvent_t e0, e1;
+    RTDM_CUDA(cudaEventCreate(&e0));
+    RTDM_CUDA(cudaEventCreate(&e1));
+    intpeak_kernel<OP><<<blocks, 256>>>(buf, iters / 8, 12345u);        // warm-up
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; rep++) {
+        RTDM_CUDA(cudaEventRecord(e0));
+        intpeak_kernel<OP><<<blocks, 256>>>(buf, iters, 12345u + rep);
+        RTDM_CUDA(cudaEventRecord(e1));
+        RTDM_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        RTDM_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    double lane_ops = (double)blocks * 256.0 * (double)iters * 64.0 * ops_per_inner;
+    *tiops = lane_ops / (best * 1e-3) / 1e12;
+    return 0;
+}
+}  // namespace
+
+int measure_int_peak(int device, double *iadd3, double *vimnmx, double *vabsdiff4, double *mhz)
+{
+    RTDM_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    RTDM_CUDA(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 8;
+    uint32_t *buf = nullptr;
+    RTDM_CUDA(cudaMalloc(&buf, (size_t)blocks * 256 * sizeof(uint32_t)));
+    const int iters = 4096;
+    int rc = 0;
+    double a = 0, b = 0, c = 0;
+    // ops_per_inner counts every integer instruction of the inner statement (IADD3 = 1;
+    // VIMNMX + LOP3 = 2; VABSDIFF4 + IADD = 2)
+    if (!rc) rc = run_one<0>(buf, blocks, iters, 1.0, &a);
+    if (!rc) rc = run_one<1>(buf, blocks, iters, 2.0, &b);
+    if (!rc) rc = run_one<2>(buf, blocks, iters, 2.0, &c);
+    cudaFree(buf);
+    if (rc) return rc;
+    if (iadd3) *iadd3 = a;
+    if (vimnmx) *vimnmx = b;
+    if (vabsdiff4) *vabsdiff4 = c;
+    if (mhz) *mhz = a * 1e12 / ((double)prop.multiProcessorCount * 64.0) / 1e6;   // clock if IADD3 ran 64 lanes/clk/SM
+    return 0;
+}
+
+}  // namespace rtdm

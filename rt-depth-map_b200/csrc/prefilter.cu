@@ -1,0 +1,107 @@
+// prefilter.cu -- StereoBM prefilters (x-Sobel and normalized response) for both images of a batch.
+//
+// Replaces the prefilter stage inside cv::StereoBM::compute as reached from
+// SWMatcherKonolige::compute (reference stereo-matcher/bm-sw.cpp:33-38); algorithm per
+// SURVEY.md App. A.1.  HBM-bound elementwise work: one thread per 4 output pixels, both images and
+// all frames folded into one launch (blockIdx.z = 2*frame + {0: left, 1: right}).
+#include "common.cuh"
+
+namespace rtdm {
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
+
+// x-Sobel: dst = clip(d(y-1) + 2 d(y) + d(y+1), -cap, cap) + cap with d(r) = r[x+1]-r[x-1];
+// rows reflect-101, first/last column = cap, and an odd last row = cap (OpenCV pairs rows).
+__global__ void __launch_bounds__(256)
+prefilter_xsobel_kernel(PlaneU8 left, PlaneU8 right, PlaneU8W outL, PlaneU8W outR,
+                        int W, int H, int cap)
+{
+    const int img = blockIdx.z & 1, f = blockIdx.z >> 1;
+    const uint8_t *src = (img ? right.p + (size_t)f * right.frame : left.p + (size_t)f * left.frame);
+    const size_t sp = img ? right.pitch : left.pitch;
+    uint8_t *dst = (img ? outR.p + (size_t)f * outR.frame : outL.p + (size_t)f * outL.frame);
+    const size_t dp = img ? outR.pitch : outL.pitch;
+    const int y = blockIdx.y;
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (x0 >= W) return;
+    const int paired = (H > 1) ? (H & ~1) : 0;
+    uint8_t o[4];
+    if (y >= paired) {
+        o[0] = o[1] = o[2] = o[3] = (uint8_t)cap;
+    } else {
+        const int ya = y > 0 ? y - 1 : 1;
+        const int yb = y < H - 1 ? y + 1 : H - 2;
+        const uint8_t *r0 = src + (size_t)ya * sp, *r1 = src + (size_t)y * sp, *r2 = src + (size_t)yb * sp;
+        // column sums c[x] = r0[x] + 2 r1[x] + r2[x] for x0-1 .. x0+4
+        int c[6];
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+            int x = clampi(x0 - 1 + i, 0, W - 1);
+            c[i] = (int)r0[x] + 2 * (int)r1[x] + (int)r2[x];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            int x = x0 + i;
+            int v = c[i + 2] - c[i];
+            v = clampi(v, -cap, cap) + cap;
+            if (x == 0 || x >= W - 1) v = cap;
+            o[i] = (uint8_t)v;
+        }
+    }
+    uint8_t *d = dst + (size_t)y * dp + x0;
+    if (x0 + 3 < W && ((reinterpret_cast<uintptr_t>(d) & 3) == 0)) {
+        *reinterpret_cast<uchar4 *>(d) = make_uchar4(o[0], o[1], o[2], o[3]);
+    } else {
+        for (int i = 0; i < 4 && x0 + i < W; i++) d[i] = o[i];
+    }
+}
+
+// Normalized response: val = ((4c + l + r + u + d) * sg - boxsum * ss) >> 10, clipped to +-cap.
+// boxsum = ws x ws box with replicate-clamped coordinates (equivalent to OpenCV's sliding sums,
+// which never wrap 16 bits for ws <= 255).
+__global__ void __launch_bounds__(256)
+prefilter_norm_kernel(PlaneU8 left, PlaneU8 right, PlaneU8W outL, PlaneU8W outR,
+                      int W, int H, int ws, int cap)
+{
+    const int img = blockIdx.z & 1, f = blockIdx.z >> 1;
+    const uint8_t *src = (img ? right.p + (size_t)f * right.frame : left.p + (size_t)f * left.frame);
+    const size_t sp = img ? right.pitch : left.pitch;
+    uint8_t *dst = (img ? outR.p + (size_t)f * outR.frame : outL.p + (size_t)f * outL.frame);
+    const size_t dp = img ? outR.pitch : outL.pitch;
+    const int y = blockIdx.y;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= W) return;
+    const int h = ws / 2;
+    int sg = ws * ws / 8;
+    const int ss = (1024 + sg) / (sg * 2);
+    sg *= ss;
+    int sum = 0;
+    for (int j = -h; j <= h; j++) {
+        const uint8_t *r = src + (size_t)clampi(y + j, 0, H - 1) * sp;
+        for (int i = -h; i <= h; i++) sum += r[clampi(x + i, 0, W - 1)];
+    }
+    const uint8_t *cur = src + (size_t)y * sp;
+    const int c = cur[x], l = cur[max(x - 1, 0)], r = cur[min(x + 1, W - 1)];
+    const int u = src[(size_t)max(y - 1, 0) * sp + x], d = src[(size_t)min(y + 1, H - 1) * sp + x];
+    int val = ((4 * c + l + r + u + d) * sg - sum * ss) >> 10;
+    dst[(size_t)y * dp + x] = (uint8_t)(clampi(val, -cap, cap) + cap);
+}
+
+int launch_prefilter(int type, int winsize, int cap, int n, int W, int H,
+                     PlaneU8 left, PlaneU8 right, PlaneU8W outL, PlaneU8W outR,
+                     cudaStream_t st, int *launches)
+{
+    if (n <= 0) return 0;
+    if (type == RTDM_PREFILTER_XSOBEL) {
+        dim3 grid(cdiv(cdiv(W, 4), 256), H, 2 * n);
+        prefilter_xsobel_kernel<<<grid, 256, 0, st>>>(left, right, outL, outR, W, H, cap);
+    } else {
+        dim3 grid(cdiv(W, 256), H, 2 * n);
+        prefilter_norm_kernel<<<grid, 256, 0, st>>>(left, right, outL, outR, W, H, winsize, cap);
+    }
+    if (launches) (*launches)++;
+    RTDM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace rtdm

@@ -1,0 +1,349 @@
+"""rtdm_b200 -- Python mirror of rt-depth-map's matcher / filter plugin interface over the C ABI
+of librtdm_b200.so (include/rtdm_b200.h).
+
+The classes keep the reference's names, constructor argument lists and method names:
+
+  CUDAMatcherKonolige      peer of SWMatcherKonolige      (reference include/stereo-matcher/bm-sw.h:25-37)
+  CUDASemiGlobalMatcher    peer of SWSemiGlobalMatcher    (reference include/stereo-matcher/sgbm-sw.h:25-36)
+  CUDAMorphologicalFilter  peer of SWMorphologicalFilter  (reference include/filter/mf-sw.h:16-21,
+                                                           base class include/filter/filter.h:13-37)
+
+Everything computes on the GPU through the shared library.  There is NO CPU fallback: if the library
+is missing, or no CUDA device is present, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_PKG_DIR), "librtdm_b200.so")
+
+EIO, ENOMEM, ENODEV, EINVAL, ENOSYS = 5, 12, 19, 22, 38
+PREFILTER_NORMALIZED_RESPONSE, PREFILTER_XSOBEL = 0, 1
+MODE_SGBM, MODE_HH = 0, 1
+
+
+class RtdmParams(C.Structure):
+    _fields_ = [(n, C.c_int) for n in (
+        "preFilterType", "preFilterSize", "preFilterCap", "blockSize", "minDisparity",
+        "numDisparities", "textureThreshold", "uniquenessRatio", "speckleWindowSize",
+        "speckleRange", "disp12MaxDiff", "mode", "P1", "P2")] + [
+        ("roi1", C.c_int * 4), ("roi2", C.c_int * 4)]
+
+
+class RtdmError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"rtdm error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+# name -> (restype, argtypes).  Must list every symbol include/rtdm_b200.h declares.
+_vp, _sz, _i = C.c_void_p, C.c_size_t, C.c_int
+SIGNATURES = {
+    "rtdm_abi_version": (_i, []),
+    "rtdm_device_count": (_i, []),
+    "rtdm_last_error": (C.c_char_p, []),
+    "rtdm_params_default_bm": (None, [C.POINTER(RtdmParams)]),
+    "rtdm_params_default_sgbm": (None, [C.POINTER(RtdmParams)]),
+    "rtdm_bm_create": (_i, [C.POINTER(_vp), C.POINTER(RtdmParams), _i, _i, _i, _i]),
+    "rtdm_bm_destroy": (None, [_vp]),
+    "rtdm_bm_set_roi1": (_i, [_vp, _i, _i, _i, _i]),
+    "rtdm_bm_set_roi2": (_i, [_vp, _i, _i, _i, _i]),
+    "rtdm_bm_compute": (_i, [_vp, _vp, _sz, _vp, _sz, _i, _i, _vp, _sz]),
+    "rtdm_bm_compute_batch": (_i, [_vp, _i, _vp, _sz, _sz, _vp, _sz, _sz, _i, _i, _vp, _sz, _sz]),
+    "rtdm_bm_compute_device": (_i, [_vp, _i, _vp, _sz, _sz, _vp, _sz, _sz, _i, _i, _vp, _sz, _sz, _vp]),
+    "rtdm_bm_last_launches": (_i, [_vp]),
+    "rtdm_bm_debug_fetch": (_i, [_vp, _i, _vp, _sz]),
+    "rtdm_sgbm_create": (_i, [C.POINTER(_vp), C.POINTER(RtdmParams), _i, _i, _i, _i]),
+    "rtdm_sgbm_destroy": (None, [_vp]),
+    "rtdm_sgbm_compute": (_i, [_vp, _vp, _sz, _vp, _sz, _i, _i, _vp, _sz]),
+    "rtdm_sgbm_compute_batch": (_i, [_vp, _i, _vp, _sz, _sz, _vp, _sz, _sz, _i, _i, _vp, _sz, _sz]),
+    "rtdm_sgbm_compute_device": (_i, [_vp, _i, _vp, _sz, _sz, _vp, _sz, _sz, _i, _i, _vp, _sz, _sz, _vp]),
+    "rtdm_sgbm_last_launches": (_i, [_vp]),
+    "rtdm_morph_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _i]),
+    "rtdm_morph_destroy": (None, [_vp]),
+    "rtdm_morph_in_buffer": (_vp, [_vp]),
+    "rtdm_morph_out_buffer": (_vp, [_vp]),
+    "rtdm_morph_run": (_i, [_vp, _vp, _vp]),
+    "rtdm_morph_run_device": (_i, [_vp, _i, _vp, _vp, _vp]),
+    "rtdm_morph_last_launches": (_i, [_vp]),
+    "rtdm_filter_speckles": (_i, [_vp, _sz, _i, _i, _i, _i, _i, _i]),
+    "rtdm_median3_s16": (_i, [_vp, _sz, _vp, _sz, _i, _i, _i]),
+    "rtdm_morph_op": (_i, [_vp, _sz, _vp, _sz, _i, _i, _i, _i, _i, _i]),
+    "rtdm_validate_disparity": (_i, [_vp, _sz, _vp, _sz, _i, _i, _i, _i, _i, _i]),
+    "rtdm_measure_int_peak": (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                   C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+}
+
+
+def lib():
+    """Loads librtdm_b200.so (built in-tree by `make -C rt-depth-map_b200`).  Fails loudly."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RtdmError(-ENODEV, f"{LIB_PATH} is missing: build it with `make -C rt-depth-map_b200` "
+                                     "(there is no CPU fallback)")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = l
+    return _lib
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise RtdmError(rc, lib().rtdm_last_error().decode("utf-8", "replace"))
+
+
+def device_count() -> int:
+    return lib().rtdm_device_count()
+
+
+def _rect(r):
+    """Accepts a cv::Rect-like (x, y, w, h) tuple or None (= empty Rect)."""
+    return (0, 0, 0, 0) if r is None else tuple(int(v) for v in r)
+
+
+def _u8_2d(a, name):
+    a = np.asarray(a)
+    if a.dtype != np.uint8 or a.ndim != 2:
+        raise RtdmError(-EINVAL, f"{name}: CV_8UC1 (2-D uint8) image required")
+    if a.strides[1] != 1:
+        a = np.ascontiguousarray(a)
+    return a
+
+
+class BlockMatcher:
+    """Abstract matcher, same surface as the reference's BlockMatcher (stereo-matcher.h:13-19)."""
+
+    def compute(self, left, right, out=None):
+        raise NotImplementedError
+
+    def setROI1(self, roi1):
+        raise NotImplementedError
+
+    def setROI2(self, roi2):
+        raise NotImplementedError
+
+
+class _MatcherBase(BlockMatcher):
+    _prefix = ""
+
+    def __init__(self, params: RtdmParams, max_width: int, max_height: int, max_batch: int, device: int):
+        self._l = lib()
+        self._h = _vp()
+        self.params = params
+        self.max_width, self.max_height, self.max_batch, self.device = max_width, max_height, max_batch, device
+        _check(getattr(self._l, self._prefix + "_create")(C.byref(self._h), C.byref(params), max_width,
+                                                          max_height, max_batch, device))
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value and _vp is not None:
+            try:
+                getattr(self._l, self._prefix + "_destroy")(h)
+            except Exception:       # interpreter shutdown
+                pass
+            self._h.value = None
+
+    close = __del__
+
+    def compute(self, left, right, out=None):
+        """compute(left, right[, out]) -> CV_16SC1 disparity (x16).  Returns the disparity array
+        (the reference returns 0 and fills `out`; bm-sw.cpp:33-38)."""
+        left, right = _u8_2d(left, "left"), _u8_2d(right, "right")
+        if left.shape != right.shape:
+            raise RtdmError(-EINVAL, "left and right must have the same size")
+        H, W = left.shape
+        if out is None or out.shape != (H, W) or out.dtype != np.int16 or out.strides[1] != 2:
+            out = np.empty((H, W), np.int16)
+        _check(getattr(self._l, self._prefix + "_compute")(
+            self._h, left.ctypes.data, left.strides[0], right.ctypes.data, right.strides[0], W, H,
+            out.ctypes.data, out.strides[0]))
+        return out
+
+    def compute_batch(self, left, right, out=None):
+        """left/right: (N, H, W) uint8 host arrays -> (N, H, W) int16."""
+        left, right = np.ascontiguousarray(left, np.uint8), np.ascontiguousarray(right, np.uint8)
+        N, H, W = left.shape
+        if out is None:
+            out = np.empty((N, H, W), np.int16)
+        _check(getattr(self._l, self._prefix + "_compute_batch")(
+            self._h, N, left.ctypes.data, W, W * H, right.ctypes.data, W, W * H, W, H,
+            out.ctypes.data, W * 2, W * H * 2))
+        return out
+
+    def compute_device(self, n, left_ptr, lstep, lframe, right_ptr, rstep, rframe, width, height,
+                       disp_ptr, dstep, dframe, stream=0):
+        """Raw device-pointer call (asynchronous on `stream`)."""
+        _check(getattr(self._l, self._prefix + "_compute_device")(
+            self._h, n, left_ptr, lstep, lframe, right_ptr, rstep, rframe, width, height,
+            disp_ptr, dstep, dframe, stream))
+
+    def last_launches(self) -> int:
+        return getattr(self._l, self._prefix + "_last_launches")(self._h)
+
+
+class CUDAMatcherKonolige(_MatcherBase):
+    """B200 peer of SWMatcherKonolige; same constructor arguments (bm-sw.h:28-30).  As in the
+    reference (bm-sw.cpp:12-14 vs :16-25) `roi1`, `roi2` and `maxDisparity` are accepted and unused."""
+    _prefix = "rtdm_bm"
+
+    def __init__(self, roi1, roi2, preFilterCap, blockSize, minDisparity, textureThreshold,
+                 numOfDisparities, maxDisparity, uniquenessRatio, speckleWindowSize, speckleRange,
+                 disp12MaxDiff, *, preFilterType=PREFILTER_XSOBEL, preFilterSize=9,
+                 max_width=1280, max_height=720, max_batch=1, device=0):
+        p = RtdmParams()
+        lib().rtdm_params_default_bm(C.byref(p))
+        p.preFilterType, p.preFilterSize, p.preFilterCap = preFilterType, preFilterSize, preFilterCap
+        p.blockSize, p.minDisparity, p.numDisparities = blockSize, minDisparity, numOfDisparities
+        p.textureThreshold, p.uniquenessRatio = textureThreshold, uniquenessRatio
+        p.speckleWindowSize, p.speckleRange, p.disp12MaxDiff = speckleWindowSize, speckleRange, disp12MaxDiff
+        super().__init__(p, max_width, max_height, max_batch, device)
+
+    def setROI1(self, roi1):
+        _check(self._l.rtdm_bm_set_roi1(self._h, *_rect(roi1)))
+
+    def setROI2(self, roi2):
+        _check(self._l.rtdm_bm_set_roi2(self._h, *_rect(roi2)))
+
+    def debug_fetch(self, what: int, width: int, height: int):
+        dt = np.uint8 if what in (0, 1) else np.int16
+        a = np.empty((height, width), dt)
+        _check(self._l.rtdm_bm_debug_fetch(self._h, what, a.ctypes.data, a.nbytes))
+        return a
+
+
+class CUDASemiGlobalMatcher(_MatcherBase):
+    """B200 peer of SWSemiGlobalMatcher; same constructor arguments (sgbm-sw.h:28-29).  P1/P2 are the
+    reference's hard-coded 8*3*5*5 / 32*3*5*5 (sgbm-sw.cpp:17-18); ROI setters are no-ops
+    (sgbm-sw.h:32-33).  `mode` defaults to MODE_SGBM like the reference; MODE_HH selects 8 paths."""
+    _prefix = "rtdm_sgbm"
+
+    def __init__(self, blockSize, minDisparity, numOfDisparities, uniquenessRatio, speckleWindowSize,
+                 speckleRange, disp12MaxDiff, *, mode=MODE_SGBM, max_width=1280, max_height=720,
+                 max_batch=1, device=0):
+        p = RtdmParams()
+        lib().rtdm_params_default_sgbm(C.byref(p))
+        p.blockSize, p.minDisparity, p.numDisparities = blockSize, minDisparity, numOfDisparities
+        p.uniquenessRatio, p.speckleWindowSize, p.speckleRange = uniquenessRatio, speckleWindowSize, speckleRange
+        p.disp12MaxDiff, p.mode = disp12MaxDiff, mode
+        super().__init__(p, max_width, max_height, max_batch, device)
+
+    def setROI1(self, roi1):
+        pass
+
+    def setROI2(self, roi2):
+        pass
+
+
+class VideoFilterDevice:
+    """Same getters as the reference's VideoFilterDevice (filter/filter.cpp:10-53)."""
+    img_width = img_height = img_bpp = 0
+
+    def getFrameSize(self):
+        return self.img_width * self.img_height * (self.img_bpp >> 3)
+
+    def getBpp(self):
+        return self.img_bpp
+
+    def getWidth(self):
+        return self.img_width
+
+    def getHeight(self):
+        return self.img_height
+
+
+class CUDAMorphologicalFilter(VideoFilterDevice):
+    """B200 peer of SWMorphologicalFilter(w, h, bpp) (mf-sw.cpp:10-28).  The in/out buffers are
+    pinned host memory owned by the device handle, exposed as numpy views."""
+
+    def __init__(self, w, h, bpp, *, max_batch=1, device=0):
+        self._l = lib()
+        self._h = _vp()
+        self.img_width, self.img_height, self.img_bpp = w, h, bpp
+        self.max_batch = max_batch
+        _check(self._l.rtdm_morph_create(C.byref(self._h), w, h, bpp, max_batch, device))
+        n = w * h
+        self._in = np.ctypeslib.as_array((C.c_uint8 * n).from_address(self._l.rtdm_morph_in_buffer(self._h))).reshape(h, w)
+        self._out = np.ctypeslib.as_array((C.c_uint8 * n).from_address(self._l.rtdm_morph_out_buffer(self._h))).reshape(h, w)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value and _vp is not None:
+            self._in = self._out = None
+            try:
+                self._l.rtdm_morph_destroy(h)
+            except Exception:       # interpreter shutdown
+                pass
+            self._h.value = None
+
+    close = __del__
+
+    def getVideoInBuffer(self):
+        return self._in
+
+    def getVideoOutBuffer(self):
+        return self._out
+
+    def run(self, inp=None, out=None):
+        """run(in, out): open then close with the 10x10 ellipse.  With no arguments it filters the
+        device-owned in buffer into the out buffer (how Estimator uses it, estimator.cpp:45,141-142).
+        Returns 0."""
+        inp = self._in if inp is None else np.ascontiguousarray(inp, np.uint8)
+        out = self._out if out is None else out
+        if inp.shape != (self.img_height, self.img_width) or out.shape != inp.shape or not out.flags.c_contiguous:
+            raise RtdmError(-EINVAL, "filter: frame size mismatch")
+        _check(self._l.rtdm_morph_run(self._h, inp.ctypes.data, out.ctypes.data))
+        return 0
+
+    def run_device(self, n, in_ptr, out_ptr, stream=0):
+        _check(self._l.rtdm_morph_run_device(self._h, n, in_ptr, out_ptr, stream))
+
+    def last_launches(self) -> int:
+        return self._l.rtdm_morph_last_launches(self._h)
+
+
+# ---- stand-alone stages ---------------------------------------------------------------------------
+def filter_speckles(img, newVal, maxSpeckleSize, maxDiff, device=0):
+    a = np.ascontiguousarray(img, np.int16).copy()
+    H, W = a.shape
+    _check(lib().rtdm_filter_speckles(a.ctypes.data, W * 2, W, H, int(newVal), int(maxSpeckleSize), int(maxDiff), device))
+    return a
+
+
+def median3_s16(img, device=0):
+    a = np.ascontiguousarray(img, np.int16)
+    H, W = a.shape
+    out = np.empty_like(a)
+    _check(lib().rtdm_median3_s16(a.ctypes.data, W * 2, out.ctypes.data, W * 2, W, H, device))
+    return out
+
+
+def morph_op(img, op, kw=10, kh=10, device=0):
+    a = np.ascontiguousarray(img, np.uint8)
+    H, W = a.shape
+    out = np.empty_like(a)
+    _check(lib().rtdm_morph_op(a.ctypes.data, W, out.ctypes.data, W, W, H, kw, kh, int(op), device))
+    return out
+
+
+def validate_disparity(disp, cost, minD, nd, d12, device=0):
+    d = np.ascontiguousarray(disp, np.int16).copy()
+    c = np.ascontiguousarray(cost, np.int16)
+    H, W = d.shape
+    _check(lib().rtdm_validate_disparity(d.ctypes.data, W * 2, c.ctypes.data, W * 2, W, H, minD, nd, d12, device))
+    return d
+
+
+def measure_int_peak(device=0):
+    a, b, c, m = C.c_double(), C.c_double(), C.c_double(), C.c_double()
+    _check(lib().rtdm_measure_int_peak(device, C.byref(a), C.byref(b), C.byref(c), C.byref(m)))
+    return {"iadd3_tiops": a.value, "vimnmx_lop3_tiops": b.value, "vabsdiff4_iadd_tiops": c.value,
+            "sm_mhz_if_64_lanes": m.value}

@@ -1,0 +1,82 @@
+"""Generates the committed golden fixtures with cv2 4.13.0 (the in-image build of the OpenCV
+routines the reference's SW plugins call).  Run from the repo root:  python tests/golden/make_golden.py
+
+Each .npz holds the inputs, the parameters (as a JSON string) and the cv2 output, so the fixtures
+are self-contained: neither cv2 nor /root/reference is needed to check against them.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "rt-depth-map_b200"))
+from oracle import cv2_ref  # noqa: E402
+from rtdm_b200 import synth  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+BM_CASES = {
+    # name: (W, H, seed, params)
+    "bm_cfg0_320x240_nd64_bs15": (320, 240, 1000, dict(preFilterCap=31, blockSize=15, minDisparity=0, textureThreshold=10, numDisparities=64, uniquenessRatio=10, speckleWindowSize=100, speckleRange=32, disp12MaxDiff=1)),
+    "bm_cfg1_640x480_nd128_bs13": (640, 480, 1001, dict(preFilterCap=31, blockSize=13, minDisparity=0, textureThreshold=10, numDisparities=128, uniquenessRatio=10, speckleWindowSize=100, speckleRange=32, disp12MaxDiff=1)),
+    "bm_raw_240x160_nd32_bs9": (240, 160, 1002, dict(preFilterCap=31, blockSize=9, minDisparity=0, textureThreshold=10, numDisparities=32, uniquenessRatio=10, speckleWindowSize=0, speckleRange=0, disp12MaxDiff=-1)),
+    "bm_oddh_233x157_nd48_bs21": (233, 157, 1003, dict(preFilterCap=31, blockSize=21, minDisparity=0, textureThreshold=10, numDisparities=48, uniquenessRatio=0, speckleWindowSize=100, speckleRange=32, disp12MaxDiff=1)),
+    "bm_roi_320x240_nd64_bs15": (320, 240, 1004, dict(preFilterCap=31, blockSize=15, minDisparity=0, textureThreshold=10, numDisparities=64, uniquenessRatio=10, speckleWindowSize=100, speckleRange=32, disp12MaxDiff=1, roi1=(40, 30, 240, 180), roi2=(10, 20, 280, 200))),
+    "bm_norm_320x240_nd64_bs11": (320, 240, 1005, dict(preFilterCap=25, blockSize=11, minDisparity=0, textureThreshold=20, numDisparities=64, uniquenessRatio=15, speckleWindowSize=50, speckleRange=16, disp12MaxDiff=2, preFilterType=0, preFilterSize=9)),
+    "bm_cap63_200x120_nd48_bs11": (200, 120, 1006, dict(preFilterCap=63, blockSize=11, minDisparity=0, textureThreshold=10, numDisparities=48, uniquenessRatio=10, speckleWindowSize=100, speckleRange=32, disp12MaxDiff=-1)),
+}
+
+SGBM_CASES = {
+    "sgbm_mode0_320x240_nd64_bs5": (320, 240, 2000, dict(blockSize=5, minDisparity=0, numDisparities=64, uniquenessRatio=10, speckleWindowSize=100, speckleRange=32, disp12MaxDiff=1, mode=0)),
+    "sgbm_hh_320x240_nd64_bs5": (320, 240, 2001, dict(blockSize=5, minDisparity=0, numDisparities=64, uniquenessRatio=10, speckleWindowSize=100, speckleRange=32, disp12MaxDiff=1, mode=1)),
+    "sgbm_mode0_233x157_nd32_bs3": (233, 157, 2002, dict(blockSize=3, minDisparity=0, numDisparities=32, uniquenessRatio=5, speckleWindowSize=0, speckleRange=0, disp12MaxDiff=2, mode=0)),
+    "sgbm_hh_233x157_nd48_bs7": (233, 157, 2003, dict(blockSize=7, minDisparity=0, numDisparities=48, uniquenessRatio=15, speckleWindowSize=60, speckleRange=8, disp12MaxDiff=1, mode=1)),
+}
+
+
+def main():
+    cv2 = cv2_ref.cv2_pinned()
+    for name, (W, H, seed, p) in BM_CASES.items():
+        L, R, _ = synth.stereo_pair(W, H, p["numDisparities"], seed)
+        disp = cv2_ref.make_bm(**p).compute(L, R)
+        np.savez_compressed(os.path.join(OUT, name), left=L, right=R, disp=disp, params=json.dumps(p))
+        print(name, disp.shape, float((disp >= 0).mean()))
+    for name, (W, H, seed, p) in SGBM_CASES.items():
+        L, R, _ = synth.stereo_pair(W, H, p["numDisparities"], seed)
+        disp = cv2_ref.make_sgbm(**p).compute(L, R)
+        np.savez_compressed(os.path.join(OUT, name), left=L, right=R, disp=disp, params=json.dumps(p))
+        print(name, disp.shape, float((disp >= 0).mean()))
+    # morphology: the ROI-sized binary mask of the 720p calibration, a full 720p gray image, tiny edge cases
+    for name, img in {
+        "morph_mask_934x404": synth.binary_mask(934, 404, 3000),
+        "morph_gray_320x240": synth.gray_image(320, 240, 3001),
+        "morph_mask_17x13": synth.binary_mask(17, 13, 3002),
+        "morph_mask_10x10": synth.binary_mask(10, 10, 3003),
+    }.items():
+        k = cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (10, 10))
+        np.savez_compressed(os.path.join(OUT, name), src=img, erode=cv2.erode(img, k), dilate=cv2.dilate(img, k),
+                            openclose=cv2_ref.morph_open_close(img), se=k)
+        print(name, img.shape)
+    # speckle / median / validate on a raw BM disparity map
+    L, R, _ = synth.stereo_pair(320, 240, 64, 4000)
+    raw = cv2_ref.make_bm(31, 15, 0, 10, 64, 10, 0, 0, -1).compute(L, R)
+    sp = {}
+    for (ms, md) in [(100, 32), (10, 0), (1000, 16), (1, 1)]:
+        t = raw.copy(); cv2.filterSpeckles(t, -16, ms, md); sp[f"sp_{ms}_{md}"] = t
+    np.savez_compressed(os.path.join(OUT, "post_speckle_320x240"), raw=raw, **sp)
+    rng = np.random.default_rng(4001)
+    a = rng.integers(-16, 2048, (97, 131)).astype(np.int16)
+    np.savez_compressed(os.path.join(OUT, "post_median_131x97"), src=a, median=cv2.medianBlur(a, 3))
+    cost = rng.integers(0, 5000, raw.shape).astype(np.int16)
+    v = {}
+    for d12 in (0, 1, 3):
+        t = raw.copy(); cv2.validateDisparity(t, cost, 0, 64, d12); v[f"d12_{d12}"] = t
+    np.savez_compressed(os.path.join(OUT, "post_validate_320x240"), raw=raw, cost=cost, **v)
+    print("done")
+
+
+if __name__ == "__main__":
+    main()

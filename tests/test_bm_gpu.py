@@ -1,0 +1,157 @@
+"""GPU parity: the CUDA Konolige matcher (through the C ABI) against the oracle and the cv2 golden
+vectors.  Bit-exact: CV_16S disparity maps must be identical."""
+import json
+
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(rt, p, W, H, **kw):
+    m = rt.CUDAMatcherKonolige(None, None, p["preFilterCap"], p["blockSize"], p["minDisparity"],
+                               p["textureThreshold"], p["numDisparities"], p["numDisparities"],
+                               p["uniquenessRatio"], p["speckleWindowSize"], p["speckleRange"],
+                               p["disp12MaxDiff"],
+                               preFilterType=1 if p.get("preFilterType") is None else p["preFilterType"],
+                               preFilterSize=9 if p.get("preFilterSize") is None else p["preFilterSize"],
+                               max_width=W, max_height=H, **kw)
+    if p.get("roi1") is not None:
+        m.setROI1(p["roi1"])
+    if p.get("roi2") is not None:
+        m.setROI2(p["roi2"])
+    return m
+
+
+def _orc_params(orc, p):
+    return orc.make_params(
+        preFilterType=1 if p.get("preFilterType") is None else p["preFilterType"],
+        preFilterSize=9 if p.get("preFilterSize") is None else p["preFilterSize"],
+        preFilterCap=p["preFilterCap"], blockSize=p["blockSize"], minDisparity=p["minDisparity"],
+        numDisparities=p["numDisparities"], textureThreshold=p["textureThreshold"],
+        uniquenessRatio=p["uniquenessRatio"], speckleWindowSize=p["speckleWindowSize"],
+        speckleRange=p["speckleRange"], disp12MaxDiff=p["disp12MaxDiff"], roi1=p.get("roi1"), roi2=p.get("roi2"))
+
+
+@pytest.mark.parametrize("name", golden_names("bm_"))
+def test_bm_matches_cv2_golden(gpu, name):
+    g = load_golden(name)
+    p = json.loads(str(g["params"]))
+    H, W = g["left"].shape
+    m = _mk(gpu, p, W, H)
+    got = m.compute(g["left"], g["right"])
+    assert got.dtype == np.int16 and got.shape == (H, W)
+    assert np.array_equal(got, g["disp"]), f"{name}: {(got != g['disp']).sum()} pixels differ"
+    assert m.last_launches() > 0
+
+
+def test_bm_stages_match_oracle(gpu, orc):
+    """Intermediates: prefiltered images, raw WTA disparity and cost."""
+    from rtdm_b200 import synth
+    W, H, nd, bs, cap = 320, 240, 64, 15, 31
+    L, R, _ = synth.stereo_pair(W, H, nd, 77)
+    p = dict(preFilterCap=cap, blockSize=bs, minDisparity=0, textureThreshold=10, numDisparities=nd,
+             uniquenessRatio=10, speckleWindowSize=100, speckleRange=32, disp12MaxDiff=1)
+    m = _mk(gpu, p, W, H)
+    m.compute(L, R)
+    Lp, Rp = orc.prefilter_xsobel(L, cap), orc.prefilter_xsobel(R, cap)
+    assert np.array_equal(m.debug_fetch(0, W, H), Lp)
+    assert np.array_equal(m.debug_fetch(1, W, H), Rp)
+    h = bs // 2
+    rd, rc = orc.bm_core(Lp, Rp, h, H - h, cap, bs, 0, nd, 10, 10)
+    gd, gc = m.debug_fetch(2, W, H), m.debug_fetch(3, W, H)
+    lofs = nd - 1
+    assert np.array_equal(gd[h:H - h, lofs:], rd[h:H - h, lofs:])
+    valid = rd[h:H - h, lofs:] >= 0
+    assert np.array_equal(gc[h:H - h, lofs:][valid], rc[h:H - h, lofs:][valid])
+
+
+def test_bm_random_params_match_oracle(gpu, orc):
+    from rtdm_b200 import synth
+    rng = np.random.default_rng(11)
+    checked = 0
+    for i in range(16):
+        W, H = int(rng.integers(70, 420)), int(rng.integers(40, 260))
+        nd = 16 * int(rng.integers(1, 9)); bs = 2 * int(rng.integers(2, 11)) + 1
+        if bs >= min(W, H):
+            continue
+        p = dict(preFilterCap=int(rng.integers(1, 32)), blockSize=bs, minDisparity=0,
+                 textureThreshold=int(rng.integers(0, 50)), numDisparities=nd,
+                 uniquenessRatio=int(rng.integers(0, 30)), speckleWindowSize=int(rng.integers(0, 200)),
+                 speckleRange=int(rng.integers(0, 64)), disp12MaxDiff=int(rng.integers(-1, 4)),
+                 preFilterType=int(rng.integers(0, 2)), preFilterSize=2 * int(rng.integers(2, 8)) + 1)
+        L, R, _ = synth.stereo_pair(W, H, nd, 900 + i)
+        ref = orc.bm_compute(L, R, _orc_params(orc, p))
+        got = _mk(gpu, p, W, H).compute(L, R)
+        assert np.array_equal(ref, got), (p, W, H, int((ref != got).sum()))
+        checked += 1
+    assert checked >= 10
+
+
+def test_bm_degenerate_width(gpu, orc):
+    """numDisparities wider than the image: the whole map is FILTERED."""
+    from rtdm_b200 import synth
+    L, R, _ = synth.stereo_pair(100, 60, 16, 5)
+    p = dict(preFilterCap=31, blockSize=9, minDisparity=0, textureThreshold=10, numDisparities=128,
+             uniquenessRatio=10, speckleWindowSize=100, speckleRange=32, disp12MaxDiff=1)
+    got = _mk(gpu, p, 100, 60).compute(L, R)
+    assert np.array_equal(got, orc.bm_compute(L, R, _orc_params(orc, p)))
+    assert (got == -16).all()
+
+
+def test_bm_strided_roi_views(gpu, orc):
+    """Estimator feeds non-contiguous ROI views (estimator.cpp:33,36): row step = full image width."""
+    from rtdm_b200 import synth
+    Lf, Rf, _ = synth.stereo_pair(400, 300, 64, 21)
+    L, R = Lf[20:260, 30:350], Rf[20:260, 30:350]
+    assert not L.flags.c_contiguous
+    p = dict(preFilterCap=31, blockSize=13, minDisparity=0, textureThreshold=10, numDisparities=64,
+             uniquenessRatio=10, speckleWindowSize=100, speckleRange=32, disp12MaxDiff=1)
+    got = _mk(gpu, p, 320, 240).compute(L, R)
+    ref = orc.bm_compute(np.ascontiguousarray(L), np.ascontiguousarray(R), _orc_params(orc, p))
+    assert np.array_equal(got, ref)
+
+
+def test_bm_set_roi_per_frame(gpu, orc):
+    """setROI1 is called every frame (estimator.cpp:54); ROI only changes the valid rectangle."""
+    from rtdm_b200 import synth
+    L, R, _ = synth.stereo_pair(320, 240, 64, 31)
+    p = dict(preFilterCap=31, blockSize=13, minDisparity=0, textureThreshold=10, numDisparities=64,
+             uniquenessRatio=10, speckleWindowSize=100, speckleRange=32, disp12MaxDiff=1)
+    m = _mk(gpu, p, 320, 240)
+    for roi in [(50, 40, 200, 150), (0, 0, 320, 240), (100, 100, 150, 100), None]:
+        m.setROI1(roi)
+        q = dict(p, roi1=roi)
+        assert np.array_equal(m.compute(L, R), orc.bm_compute(L, R, _orc_params(orc, q))), roi
+
+
+def test_bm_720p_full_size_and_batch(gpu, orc):
+    """BASELINE config 2 size: 1280x720, nd=128, reference parameters; batched call == per-frame."""
+    from rtdm_b200 import synth
+    p = dict(preFilterCap=31, blockSize=13, minDisparity=0, textureThreshold=10, numDisparities=128,
+             uniquenessRatio=10, speckleWindowSize=100, speckleRange=32, disp12MaxDiff=1)
+    frames = [synth.stereo_pair(1280, 720, 128, 1000 + i) for i in range(3)]
+    Ls = np.stack([f[0] for f in frames]); Rs = np.stack([f[1] for f in frames])
+    m = _mk(gpu, p, 1280, 720, max_batch=3)
+    out = m.compute_batch(Ls, Rs)
+    for i in range(3):
+        ref = orc.bm_compute(Ls[i], Rs[i], _orc_params(orc, p))
+        assert np.array_equal(out[i], ref), (i, int((out[i] != ref).sum()))
+        # size-independent properties: invalid marker, range, left border
+        assert (out[i][:, :127 + 6] == -16).all()
+        v = out[i][out[i] != -16]
+        assert v.min() >= 0 and v.max() <= 127 * 16 + 15
+    assert np.array_equal(m.compute(Ls[1], Rs[1]), out[1])
+
+
+def test_bm_errors(gpu):
+    with pytest.raises(gpu.RtdmError) as e:
+        gpu.CUDAMatcherKonolige(None, None, 31, 12, 0, 10, 128, 128, 10, 100, 32, 1)
+    assert e.value.code == -gpu.EINVAL
+    m = gpu.CUDAMatcherKonolige(None, None, 31, 13, 0, 10, 64, 64, 10, 100, 32, 1, max_width=64, max_height=64)
+    with pytest.raises(gpu.RtdmError):
+        m.compute(np.zeros((100, 100), np.uint8), np.zeros((100, 100), np.uint8))   # larger than the handle
+    with pytest.raises(gpu.RtdmError):
+        m.compute(np.zeros((10, 10), np.uint8), np.zeros((10, 10), np.uint8))       # block larger than image

@@ -1,0 +1,111 @@
+"""CPU: the oracle (oracle/stereo_oracle.c) against the committed cv2-4.13.0 golden vectors, and
+live against cv2 when it imports.  The reference holds no tests/golden vectors of its own
+(SURVEY.md section 4), so these fixtures are the pin."""
+import json
+
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_golden
+
+
+def _bm_params(orc, p):
+    return orc.make_params(
+        preFilterType=p.get("preFilterType", 1) if p.get("preFilterType") is not None else 1,
+        preFilterSize=p.get("preFilterSize", 9) if p.get("preFilterSize") is not None else 9,
+        preFilterCap=p["preFilterCap"], blockSize=p["blockSize"], minDisparity=p["minDisparity"],
+        numDisparities=p["numDisparities"], textureThreshold=p["textureThreshold"],
+        uniquenessRatio=p["uniquenessRatio"], speckleWindowSize=p["speckleWindowSize"],
+        speckleRange=p["speckleRange"], disp12MaxDiff=p["disp12MaxDiff"],
+        roi1=p.get("roi1"), roi2=p.get("roi2"))
+
+
+@pytest.mark.parametrize("name", golden_names("bm_"))
+def test_bm_oracle_matches_golden(orc, name):
+    g = load_golden(name)
+    p = json.loads(str(g["params"]))
+    got = orc.bm_compute(g["left"], g["right"], _bm_params(orc, p))
+    assert np.array_equal(got, g["disp"]), f"{name}: {(got != g['disp']).sum()} pixels differ"
+
+
+@pytest.mark.parametrize("name", golden_names("morph_"))
+def test_morph_oracle_matches_golden(orc, name):
+    g = load_golden(name)
+    assert np.array_equal(orc.morph(g["src"], 0), g["erode"])
+    assert np.array_equal(orc.morph(g["src"], 1), g["dilate"])
+    assert np.array_equal(orc.morph_open_close(g["src"]), g["openclose"])
+
+
+def test_ellipse_matches_golden(orc):
+    se = load_golden("morph_mask_10x10")["se"]
+    j1, j2 = orc.ellipse_rows(10, 10)
+    for i in range(10):
+        cols = np.nonzero(se[i])[0]
+        assert (cols.min(), cols.max() + 1) == (j1[i], j2[i])
+    assert int(se.sum()) == 83
+
+
+def test_speckle_oracle_matches_golden(orc):
+    g = load_golden("post_speckle_320x240")
+    for key in g.files:
+        if key.startswith("sp_"):
+            _, ms, md = key.split("_")
+            assert np.array_equal(orc.filter_speckles(g["raw"], -16, int(ms), int(md)), g[key]), key
+
+
+def test_median_oracle_matches_golden(orc):
+    g = load_golden("post_median_131x97")
+    assert np.array_equal(orc.median3_s16(g["src"]), g["median"])
+
+
+def test_validate_oracle_matches_golden(orc):
+    g = load_golden("post_validate_320x240")
+    for d12 in (0, 1, 3):
+        assert np.array_equal(orc.validate_disparity(g["raw"], g["cost"], 0, 64, d12), g[f"d12_{d12}"])
+
+
+def test_synth_is_deterministic():
+    """The fixtures store their inputs, but bench/test inputs are regenerated from seeds: guard that."""
+    from rtdm_b200 import synth
+    g = load_golden("bm_cfg0_320x240_nd64_bs15")
+    L, R, _ = synth.stereo_pair(320, 240, 64, 1000)
+    assert np.array_equal(L, g["left"]) and np.array_equal(R, g["right"])
+
+
+# ---- live differential checks against cv2 (skipped only if cv2 cannot be imported) ----------------
+def _cv2():
+    from oracle import cv2_ref
+    if not cv2_ref.have_cv2():
+        pytest.skip("cv2 not importable")
+    return cv2_ref
+
+
+def test_bm_oracle_vs_cv2_random_params(orc):
+    cv2_ref = _cv2()
+    from rtdm_b200 import synth
+    rng = np.random.default_rng(7)
+    checked = 0
+    for i in range(10):
+        W, H = int(rng.integers(100, 360)), int(rng.integers(60, 240))
+        nd = 16 * int(rng.integers(1, 5)); bs = 2 * int(rng.integers(2, 11)) + 1
+        if bs >= min(W, H) or nd + bs >= W:
+            continue
+        p = dict(preFilterCap=int(rng.integers(1, 32)), blockSize=bs, minDisparity=0,
+                 textureThreshold=int(rng.integers(0, 50)), numDisparities=nd,
+                 uniquenessRatio=int(rng.integers(0, 30)), speckleWindowSize=int(rng.integers(0, 200)),
+                 speckleRange=int(rng.integers(0, 64)), disp12MaxDiff=int(rng.integers(-1, 4)))
+        L, R, _ = synth.stereo_pair(W, H, nd, 500 + i)
+        ref = cv2_ref.make_bm(**p).compute(L, R)
+        got = orc.bm_compute(L, R, _bm_params(orc, p))
+        assert np.array_equal(ref, got), (p, int((ref != got).sum()))
+        checked += 1
+    assert checked >= 5
+
+
+def test_bm_oracle_vs_cv2_720p(orc):
+    cv2_ref = _cv2()
+    from rtdm_b200 import synth
+    p = dict(preFilterCap=31, blockSize=13, minDisparity=0, textureThreshold=10, numDisparities=128,
+             uniquenessRatio=10, speckleWindowSize=100, speckleRange=32, disp12MaxDiff=1)
+    L, R, _ = synth.stereo_pair(1280, 720, 128, 1000)
+    assert np.array_equal(cv2_ref.make_bm(**p).compute(L, R), orc.bm_compute(L, R, _bm_params(orc, p)))
