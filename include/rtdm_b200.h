@@ -101,6 +101,12 @@ int rtdm_bm_compute_device(rtdm_bm *h, int n, const uint8_t *left, size_t lstep,
                            int16_t *disp, size_t dstep, size_t dframe, void *cuda_stream);
 /* number of kernel launches issued by the last compute call on this handle */
 int rtdm_bm_last_launches(const rtdm_bm *h);
+/* Per-stage device timing with CUDA events recorded on the launching stream (used by bench.py for
+ * the roofline of the dominant kernel).  While enabled every compute call records 5 events.
+ * rtdm_bm_stage_times synchronises, sums the elapsed milliseconds of all recorded calls per stage
+ * (0 prefilter, 1 SAD+WTA, 2 validate+mask, 3 speckle) into ms_sum[4], and clears the record. */
+int rtdm_bm_set_profiling(rtdm_bm *h, int on);
+int rtdm_bm_stage_times(rtdm_bm *h, double *ms_sum, int *calls);
 /* test hook: copy intermediate planes of frame 0 of the last compute call to host.
  * what: 0 = prefiltered left, 1 = prefiltered right (uint8, width bytes per row),
  *       2 = raw WTA disparity before validate/mask/speckle, 3 = cost (int16, width per row). */
@@ -136,6 +142,8 @@ uint8_t *rtdm_morph_out_buffer(rtdm_morph *h);
  * the 10x10 MORPH_ELLIPSE (MORPH_FILTER_DX/DY, include/filter/mf-sw.h:11-12).  HOST pointers
  * (tightly packed width*height bytes); in/out may be the handle's own buffers.  Returns 0. */
 int rtdm_morph_run(rtdm_morph *h, const uint8_t *in, uint8_t *out);
+/* batched host variant: n tightly packed frames (n <= max_batch) */
+int rtdm_morph_run_batch(rtdm_morph *h, int n, const uint8_t *in, uint8_t *out);
 /* device variant: n tightly packed frames, asynchronous on cuda_stream */
 int rtdm_morph_run_device(rtdm_morph *h, int n, const uint8_t *in, uint8_t *out, void *cuda_stream);
 int rtdm_morph_last_launches(const rtdm_morph *h);

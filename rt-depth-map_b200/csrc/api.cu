@@ -81,6 +81,7 @@ struct rtdm_bm {
     rtdm_params p;
     int maxW, maxH, maxB, dev;
     cudaStream_t st;
+    cudaStream_t lane[3];        // streams of the chunked host-batch pipeline (copy/compute overlap)
     // per-batch device workspace (maxB frames)
     uint8_t *Lp, *Rp;            size_t ppitch, pframe;      // prefiltered planes (bytes)
     int16_t *raw, *cost;         size_t rpitch, rframe;      // raw WTA disparity + cost (elements)
@@ -90,7 +91,12 @@ struct rtdm_bm {
     int16_t *dD;                 size_t dpitch, dframe;      // device copy of the output (elements)
     int launches;
     int lastW, lastH;
+    // optional per-stage CUDA-event timing (rtdm_bm_set_profiling)
+    int prof;
+    std::vector<cudaEvent_t> *ev;     // 5 events per profiled call: before prefilter, after each stage
 };
+
+static const int BM_STAGES = 4;      // prefilter, sad+wta, validate+mask, speckle
 
 static int bm_check_params(const rtdm_params *p)
 {
@@ -145,7 +151,9 @@ extern "C" void rtdm_bm_destroy(rtdm_bm *h)
     cudaSetDevice(h->dev);
     cudaFree(h->Lp); cudaFree(h->Rp); cudaFree(h->raw); cudaFree(h->cost);
     cudaFree(h->labels); cudaFree(h->sizes); cudaFree(h->dL); cudaFree(h->dR); cudaFree(h->dD);
+    if (h->ev) { for (cudaEvent_t e : *h->ev) cudaEventDestroy(e); delete h->ev; }
     if (h->st) cudaStreamDestroy(h->st);
+    for (int i = 0; i < 3; i++) if (h->lane[i]) cudaStreamDestroy(h->lane[i]);
     delete h;
 }
 
@@ -174,6 +182,8 @@ extern "C" int rtdm_bm_create(rtdm_bm **out, const rtdm_params *p, int max_width
     h->spitch = align_up((size_t)max_width, 64); h->sframe = h->spitch * max_height;
     h->dpitch = h->rpitch; h->dframe = h->rframe;
     rc = (int)cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) == cudaSuccess ? 0 : -RTDM_EIO;
+    for (int i = 0; i < 3 && !rc; i++)
+        rc = (int)cudaStreamCreateWithFlags(&h->lane[i], cudaStreamNonBlocking) == cudaSuccess ? 0 : -RTDM_EIO;
     if (!rc) rc = dev_alloc(&h->Lp, h->pframe * B + 4096);
     if (!rc) rc = dev_alloc(&h->Rp, h->pframe * B + 4096);
     if (!rc) rc = dev_alloc(&h->raw, h->rframe * B);
@@ -203,10 +213,10 @@ extern "C" int rtdm_bm_set_roi2(rtdm_bm *h, int x, int y, int w, int hgt)
 }
 
 // the kernel pipeline on device-resident frames
-static int bm_pipeline(rtdm_bm *h, int n, PlaneU8 L, PlaneU8 R, int W, int H, PlaneS16 out, cudaStream_t st)
+static int bm_pipeline(rtdm_bm *h, int n, PlaneU8 L, PlaneU8 R, int W, int H, PlaneS16 out, cudaStream_t st, int f0 = 0)
 {
     const rtdm_params &p = h->p;
-    if (W > h->maxW || H > h->maxH || n > h->maxB || W < 1 || H < 1 || n < 1) {
+    if (W > h->maxW || H > h->maxH || f0 + n > h->maxB || W < 1 || H < 1 || n < 1) {
         set_error("bm: frame geometry or batch exceeds what the handle was created for");
         return -RTDM_EINVAL;
     }
@@ -226,21 +236,68 @@ static int bm_pipeline(rtdm_bm *h, int n, PlaneU8 L, PlaneU8 R, int W, int H, Pl
     if (vr.w == 0 || vr.h == 0 || g.lofs >= W || g.rofs >= W || g.W1 < 1) row0 = row1 = 0;
     g.row0 = row0; g.row1 = row1;
     int rc = 0;
-    PlaneS16 raw = {h->raw, h->rpitch, h->rframe}, cost = {h->cost, h->rpitch, h->rframe};
+    auto mark = [&]() {
+        if (!h->prof) return;
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        cudaEventRecord(e, st);
+        h->ev->push_back(e);
+    };
+    // workspace slices of frames [f0, f0 + n)
+    uint8_t *wLp = h->Lp + (size_t)f0 * h->pframe, *wRp = h->Rp + (size_t)f0 * h->pframe;
+    PlaneS16 raw = {h->raw + (size_t)f0 * h->rframe, h->rpitch, h->rframe};
+    PlaneS16 cost = {h->cost + (size_t)f0 * h->rframe, h->rpitch, h->rframe};
+    int32_t *wlab = h->labels + (size_t)f0 * W * H, *wsiz = h->sizes + (size_t)f0 * W * H;
+    mark();
     if (row1 > row0) {
-        PlaneU8W oL = {h->Lp, h->ppitch, h->pframe}, oR = {h->Rp, h->ppitch, h->pframe};
+        PlaneU8W oL = {wLp, h->ppitch, h->pframe}, oR = {wRp, h->ppitch, h->pframe};
         rc = launch_prefilter(p.preFilterType, p.preFilterSize, p.preFilterCap, n, W, H, L, R, oL, oR, st, &h->launches);
         if (rc) return rc;
-        PlaneU8 iL = {h->Lp, h->ppitch, h->pframe}, iR = {h->Rp, h->ppitch, h->pframe};
+        mark();
+        PlaneU8 iL = {wLp, h->ppitch, h->pframe}, iR = {wRp, h->ppitch, h->pframe};
         rc = launch_bm_sad_wta(g, n, iL, iR, raw, cost, st, &h->launches);
         if (rc) return rc;
-    }
+        mark();
+    } else { mark(); mark(); }
     rc = launch_validate_mask(n, W, H, minD, nd, p.disp12MaxDiff, g.lofs, g.W1,
                               std::max(vr.x, 0), std::max(vr.x + vr.w, 0), row0, row1, raw, cost, out, st, &h->launches);
     if (rc) return rc;
+    mark();
     if (p.speckleRange >= 0 && p.speckleWindowSize > 0)
-        rc = launch_speckle(n, W, H, out, FILT, p.speckleWindowSize, p.speckleRange, h->labels, h->sizes, st, &h->launches);
+        rc = launch_speckle(n, W, H, out, FILT, p.speckleWindowSize, p.speckleRange, wlab, wsiz, st, &h->launches);
+    mark();
     return rc;
+}
+
+extern "C" int rtdm_bm_set_profiling(rtdm_bm *h, int on)
+{
+    if (!h) return -RTDM_EINVAL;
+    if (!h->ev) h->ev = new std::vector<cudaEvent_t>();
+    h->prof = on ? 1 : 0;
+    return 0;
+}
+
+extern "C" int rtdm_bm_stage_times(rtdm_bm *h, double *ms_sum, int *calls)
+{
+    if (!h || !ms_sum || !calls) return -RTDM_EINVAL;
+    for (int i = 0; i < BM_STAGES; i++) ms_sum[i] = 0.0;
+    *calls = 0;
+    if (!h->ev) return 0;
+    RTDM_CUDA(cudaSetDevice(h->dev));
+    std::vector<cudaEvent_t> &ev = *h->ev;
+    const size_t per = BM_STAGES + 1;
+    for (size_t c = 0; c + per <= ev.size(); c += per) {
+        RTDM_CUDA(cudaEventSynchronize(ev[c + per - 1]));
+        for (int i = 0; i < BM_STAGES; i++) {
+            float ms = 0.f;
+            RTDM_CUDA(cudaEventElapsedTime(&ms, ev[c + i], ev[c + i + 1]));
+            ms_sum[i] += ms;
+        }
+        (*calls)++;
+    }
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    ev.clear();
+    return 0;
 }
 
 extern "C" int rtdm_bm_compute_device(rtdm_bm *h, int n, const uint8_t *left, size_t lstep, size_t lframe,
@@ -268,19 +325,31 @@ extern "C" int rtdm_bm_compute_batch(rtdm_bm *h, int n, const uint8_t *left, siz
     }
     RTDM_CUDA(cudaSetDevice(h->dev));
     h->launches = 0;
-    cudaStream_t st = h->st;
-    for (int k = 0; k < n; k++) {
-        RTDM_CUDA(cudaMemcpy2DAsync(h->dL + k * h->sframe, h->spitch, left + k * lframe, lstep, width, height, cudaMemcpyHostToDevice, st));
-        RTDM_CUDA(cudaMemcpy2DAsync(h->dR + k * h->sframe, h->spitch, right + k * rframe, rstep, width, height, cudaMemcpyHostToDevice, st));
+    // chunks of frames round-robin over 3 streams: H2D of chunk c+1 and D2H of chunk c-1 overlap the
+    // kernels of chunk c (each chunk owns its own slice of the per-frame workspace)
+    const int chunk = n >= 12 ? std::max(1, std::min(8, n / 6)) : n;
+    int rc = 0, c = 0;
+    for (int f0 = 0; f0 < n && !rc; f0 += chunk, c++) {
+        const int m = std::min(chunk, n - f0);
+        cudaStream_t st = (chunk == n) ? h->st : h->lane[c % 3];
+        for (int k = f0; k < f0 + m; k++) {
+            RTDM_CUDA(cudaMemcpy2DAsync(h->dL + k * h->sframe, h->spitch, left + k * lframe, lstep, width, height, cudaMemcpyHostToDevice, st));
+            RTDM_CUDA(cudaMemcpy2DAsync(h->dR + k * h->sframe, h->spitch, right + k * rframe, rstep, width, height, cudaMemcpyHostToDevice, st));
+        }
+        PlaneU8 L = {h->dL + (size_t)f0 * h->sframe, h->spitch, h->sframe}, R = {h->dR + (size_t)f0 * h->sframe, h->spitch, h->sframe};
+        PlaneS16 out = {h->dD + (size_t)f0 * h->dframe, h->dpitch, h->dframe};
+        const int prof = h->prof; h->prof = 0;          // stage events are for single-stream calls only
+        rc = bm_pipeline(h, m, L, R, width, height, out, st, f0);
+        h->prof = prof;
+        if (rc) break;
+        for (int k = f0; k < f0 + m; k++)
+            RTDM_CUDA(cudaMemcpy2DAsync((uint8_t *)disp + k * dframe, dstep, h->dD + k * h->dframe, h->dpitch * 2,
+                                        (size_t)width * 2, height, cudaMemcpyDeviceToHost, st));
     }
-    PlaneU8 L = {h->dL, h->spitch, h->sframe}, R = {h->dR, h->spitch, h->sframe};
-    PlaneS16 out = {h->dD, h->dpitch, h->dframe};
-    int rc = bm_pipeline(h, n, L, R, width, height, out, st);
+    cudaError_t e0 = cudaStreamSynchronize(h->st);
+    for (int i = 0; i < 3; i++) { cudaError_t e = cudaStreamSynchronize(h->lane[i]); if (e0 == cudaSuccess) e0 = e; }
     if (rc) return rc;
-    for (int k = 0; k < n; k++)
-        RTDM_CUDA(cudaMemcpy2DAsync((uint8_t *)disp + k * dframe, dstep, h->dD + k * h->dframe, h->dpitch * 2,
-                                    (size_t)width * 2, height, cudaMemcpyDeviceToHost, st));
-    RTDM_CUDA(cudaStreamSynchronize(st));
+    RTDM_CUDA(e0);
     return 0;
 }
 
@@ -383,6 +452,21 @@ extern "C" int rtdm_morph_run(rtdm_morph *h, const uint8_t *in, uint8_t *out)
     int rc = morph_pipeline(h, 1, h->d1, h->d1, h->d0, h->d1, h->st);
     if (rc) return rc;
     RTDM_CUDA(cudaMemcpyAsync(out, h->d1, fb, cudaMemcpyDeviceToHost, h->st));
+    RTDM_CUDA(cudaStreamSynchronize(h->st));
+    return 0;
+}
+
+extern "C" int rtdm_morph_run_batch(rtdm_morph *h, int n, const uint8_t *in, uint8_t *out)
+{
+    if (!h || !in || !out) { set_error("morph_run_batch: null argument"); return -RTDM_EINVAL; }
+    if (n < 1 || n > h->maxB) { set_error("morph: batch exceeds what the handle was created for"); return -RTDM_EINVAL; }
+    RTDM_CUDA(cudaSetDevice(h->dev));
+    h->launches = 0;
+    const size_t fb = (size_t)h->W * h->H;
+    RTDM_CUDA(cudaMemcpyAsync(h->d1, in, fb * n, cudaMemcpyHostToDevice, h->st));
+    int rc = morph_pipeline(h, n, h->d1, h->d1, h->d0, h->d1, h->st);
+    if (rc) return rc;
+    RTDM_CUDA(cudaMemcpyAsync(out, h->d1, fb * n, cudaMemcpyDeviceToHost, h->st));
     RTDM_CUDA(cudaStreamSynchronize(h->st));
     return 0;
 }

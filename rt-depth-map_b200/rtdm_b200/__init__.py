@@ -59,6 +59,8 @@ SIGNATURES = {
     "rtdm_bm_compute_device": (_i, [_vp, _i, _vp, _sz, _sz, _vp, _sz, _sz, _i, _i, _vp, _sz, _sz, _vp]),
     "rtdm_bm_last_launches": (_i, [_vp]),
     "rtdm_bm_debug_fetch": (_i, [_vp, _i, _vp, _sz]),
+    "rtdm_bm_set_profiling": (_i, [_vp, _i]),
+    "rtdm_bm_stage_times": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(_i)]),
     "rtdm_sgbm_create": (_i, [C.POINTER(_vp), C.POINTER(RtdmParams), _i, _i, _i, _i]),
     "rtdm_sgbm_destroy": (None, [_vp]),
     "rtdm_sgbm_compute": (_i, [_vp, _vp, _sz, _vp, _sz, _i, _i, _vp, _sz]),
@@ -70,6 +72,7 @@ SIGNATURES = {
     "rtdm_morph_in_buffer": (_vp, [_vp]),
     "rtdm_morph_out_buffer": (_vp, [_vp]),
     "rtdm_morph_run": (_i, [_vp, _vp, _vp]),
+    "rtdm_morph_run_batch": (_i, [_vp, _i, _vp, _vp]),
     "rtdm_morph_run_device": (_i, [_vp, _i, _vp, _vp, _vp]),
     "rtdm_morph_last_launches": (_i, [_vp]),
     "rtdm_filter_speckles": (_i, [_vp, _sz, _i, _i, _i, _i, _i, _i]),
@@ -213,6 +216,18 @@ class CUDAMatcherKonolige(_MatcherBase):
     def setROI2(self, roi2):
         _check(self._l.rtdm_bm_set_roi2(self._h, *_rect(roi2)))
 
+    STAGES = ("prefilter", "sad_wta", "validate_mask", "speckle")
+
+    def set_profiling(self, on: bool):
+        _check(self._l.rtdm_bm_set_profiling(self._h, int(on)))
+
+    def stage_times(self):
+        """-> ({stage: total ms}, number of profiled calls) since the last query."""
+        ms = (C.c_double * 4)()
+        calls = _i()
+        _check(self._l.rtdm_bm_stage_times(self._h, ms, C.byref(calls)))
+        return dict(zip(self.STAGES, list(ms))), calls.value
+
     def debug_fetch(self, what: int, width: int, height: int):
         dt = np.uint8 if what in (0, 1) else np.int16
         a = np.empty((height, width), dt)
@@ -302,6 +317,14 @@ class CUDAMorphologicalFilter(VideoFilterDevice):
             raise RtdmError(-EINVAL, "filter: frame size mismatch")
         _check(self._l.rtdm_morph_run(self._h, inp.ctypes.data, out.ctypes.data))
         return 0
+
+    def run_batch(self, inp, out=None):
+        """(N, H, W) uint8 host frames -> (N, H, W) filtered frames."""
+        inp = np.ascontiguousarray(inp, np.uint8)
+        if out is None:
+            out = np.empty_like(inp)
+        _check(self._l.rtdm_morph_run_batch(self._h, inp.shape[0], inp.ctypes.data, out.ctypes.data))
+        return out
 
     def run_device(self, n, in_ptr, out_ptr, stream=0):
         _check(self._l.rtdm_morph_run_device(self._h, n, in_ptr, out_ptr, stream))
