@@ -244,16 +244,16 @@ def run_ours(args):
         if filt is not None:
             filt.run_device(B, M.data_ptr(), MO.data_ptr(), st.cuda_stream)
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()         # nvidia-smi needs ~100 ms to deliver its first sample: start before warm-up
     with torch.cuda.stream(st):
         for _ in range(args.warmup):
             step()
     launches_per_step = matcher.last_launches() + (filt.last_launches() if filt is not None else 0)
     if hasattr(matcher, "set_profiling"):
         matcher.set_profiling(True)
-    sampler = ClockSampler(local)
     barrier()
-    if rank == 0:
-        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(st):
         e0.record(st)
@@ -358,7 +358,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="bm720", choices=["bm720", "sgbm720"])

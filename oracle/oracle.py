@@ -126,14 +126,25 @@ def bm_compute(left, right, params: OrcParams):
     return disp
 
 
-def sgbm_compute(left, right, params: OrcParams):
+def sgbm_compute(left, right, params: OrcParams, return_domain_flag=False):
+    """-> disparity (and, optionally, True when the aggregated cost S saturated int16, i.e. the input
+    is outside the bit-exact domain of SURVEY.md App. B.5)."""
     left = _u8(left); right = _u8(right); H, W = left.shape
     disp = np.empty((H, W), np.int16)
     rc = lib().orc_sgbm_compute(_p(left), C.c_int(left.strides[0]), _p(right), C.c_int(right.strides[0]),
                                 W, H, C.byref(params), _p(disp), W)
-    if rc:
+    if rc < 0:
         raise ValueError(f"orc_sgbm_compute: {rc}")
-    return disp
+    return (disp, bool(rc)) if return_domain_flag else disp
+
+
+def sgbm_params(blockSize=5, minDisparity=0, numDisparities=128, uniquenessRatio=10, speckleWindowSize=100,
+                speckleRange=32, disp12MaxDiff=1, mode=0) -> OrcParams:
+    """Parameters as SWSemiGlobalMatcher's constructor sets them (sgbm-sw.cpp:15-24)."""
+    return make_params(preFilterCap=0, blockSize=blockSize, minDisparity=minDisparity,
+                       numDisparities=numDisparities, uniquenessRatio=uniquenessRatio,
+                       speckleWindowSize=speckleWindowSize, speckleRange=speckleRange,
+                       disp12MaxDiff=disp12MaxDiff, mode=mode, P1=8 * 3 * 5 * 5, P2=32 * 3 * 5 * 5)
 
 
 def morph(img, op, kw=10, kh=10):

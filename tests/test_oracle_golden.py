@@ -28,6 +28,15 @@ def test_bm_oracle_matches_golden(orc, name):
     assert np.array_equal(got, g["disp"]), f"{name}: {(got != g['disp']).sum()} pixels differ"
 
 
+@pytest.mark.parametrize("name", golden_names("sgbm_"))
+def test_sgbm_oracle_matches_golden(orc, name):
+    g = load_golden(name)
+    p = json.loads(str(g["params"]))
+    got, outside = orc.sgbm_compute(g["left"], g["right"], orc.sgbm_params(**p), return_domain_flag=True)
+    assert not outside
+    assert np.array_equal(got, g["disp"]), f"{name}: {(got != g['disp']).sum()} pixels differ"
+
+
 @pytest.mark.parametrize("name", golden_names("morph_"))
 def test_morph_oracle_matches_golden(orc, name):
     g = load_golden(name)
@@ -109,3 +118,26 @@ def test_bm_oracle_vs_cv2_720p(orc):
              uniquenessRatio=10, speckleWindowSize=100, speckleRange=32, disp12MaxDiff=1)
     L, R, _ = synth.stereo_pair(1280, 720, 128, 1000)
     assert np.array_equal(cv2_ref.make_bm(**p).compute(L, R), orc.bm_compute(L, R, _bm_params(orc, p)))
+
+
+def test_sgbm_oracle_vs_cv2_random_params(orc):
+    cv2_ref = _cv2()
+    from rtdm_b200 import synth
+    rng = np.random.default_rng(8)
+    checked = 0
+    for i in range(8):
+        W, H = int(rng.integers(120, 360)), int(rng.integers(60, 200))
+        nd = 16 * int(rng.integers(1, 5)); bs = 2 * int(rng.integers(0, 4)) + 1
+        if nd + 2 * bs >= W:
+            continue
+        p = dict(blockSize=bs, minDisparity=0, numDisparities=nd, uniquenessRatio=int(rng.integers(0, 25)),
+                 speckleWindowSize=int(rng.integers(0, 150)), speckleRange=int(rng.integers(0, 8)),
+                 disp12MaxDiff=int(rng.integers(-1, 4)), mode=int(rng.integers(0, 2)))
+        L, R, _ = synth.stereo_pair(W, H, nd, 600 + i)
+        ref = cv2_ref.make_sgbm(**p).compute(L, R)
+        got, outside = orc.sgbm_compute(L, R, orc.sgbm_params(**p), return_domain_flag=True)
+        if outside:
+            continue          # S saturated: cv2 itself is implementation-defined there (App. B.5)
+        assert np.array_equal(ref, got), (p, int((ref != got).sum()))
+        checked += 1
+    assert checked >= 4
