@@ -378,6 +378,186 @@ extern "C" int rtdm_bm_debug_fetch(rtdm_bm *h, int what, void *dst, size_t dst_b
 }
 
 // =================================================================================================
+// SGBM
+// =================================================================================================
+struct rtdm_sgbm {
+    rtdm_params p;
+    int maxW, maxH, maxB, dev;
+    int volB;                    // frames the cost volumes are sized for (sub-batches of the call)
+    cudaStream_t st;
+    uint8_t *planes;  size_t frame_planes;
+    uint16_t *C, *S;  size_t frame_vol;          // elements per frame
+    int16_t *raw;     size_t rpitch, rframe;     // WTA output before median (elements)
+    int32_t *labels, *sizes;
+    uint8_t *dL, *dR; size_t spitch, sframe;
+    int16_t *dD;      size_t dpitch, dframe;
+    int launches;
+};
+
+static int sgbm_check_params(const rtdm_params *p)
+{
+    if (p->numDisparities <= 0 || p->numDisparities % 16 != 0) { set_error("sgbm: numDisparities must be positive and divisible by 16"); return -RTDM_EINVAL; }
+    if (p->blockSize < 1 || p->blockSize % 2 == 0) { set_error("sgbm: blockSize must be odd and >= 1"); return -RTDM_EINVAL; }
+    if (p->numDisparities > 256) { set_error("sgbm: numDisparities > 256 is not supported"); return -RTDM_EINVAL; }
+    if (p->blockSize > 11) { set_error("sgbm: blockSize > 11 is not supported (16-bit cost domain, SURVEY.md App. B.5)"); return -RTDM_EINVAL; }
+    if (p->P1 > 16000 || p->P2 > 16000) { set_error("sgbm: P1/P2 above 16000 leave the 16-bit cost domain"); return -RTDM_EINVAL; }
+    if (p->mode != RTDM_SGBM_MODE_SGBM && p->mode != RTDM_SGBM_MODE_HH) { set_error("sgbm: mode must be MODE_SGBM (0) or MODE_HH (1)"); return -RTDM_EINVAL; }
+    return 0;
+}
+
+static SgbmGeom sgbm_geom(const rtdm_params &p, int W, int H)
+{
+    SgbmGeom g;
+    g.W = W; g.H = H; g.D = p.numDisparities; g.minD = p.minDisparity; g.bs = p.blockSize;
+    g.P1 = p.P1 > 0 ? p.P1 : 2; g.P2 = std::max(p.P2 > 0 ? p.P2 : 5, g.P1 + 1);
+    g.uniq = p.uniquenessRatio >= 0 ? p.uniquenessRatio : 10;
+    g.d12 = p.disp12MaxDiff > 0 ? p.disp12MaxDiff : 1;
+    g.ftzero = std::max(p.preFilterCap, 15) | 1;
+    g.mode = p.mode;
+    const int maxD = g.minD + g.D;
+    g.minX1 = std::max(maxD, 0); g.maxX1 = W + std::min(g.minD, 0); g.W1 = g.maxX1 - g.minX1;
+    return g;
+}
+
+extern "C" void rtdm_sgbm_destroy(rtdm_sgbm *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->dev);
+    cudaFree(h->planes); cudaFree(h->C); cudaFree(h->S); cudaFree(h->raw); cudaFree(h->labels); cudaFree(h->sizes);
+    cudaFree(h->dL); cudaFree(h->dR); cudaFree(h->dD);
+    if (h->st) cudaStreamDestroy(h->st);
+    delete h;
+}
+
+extern "C" int rtdm_sgbm_create(rtdm_sgbm **out, const rtdm_params *p, int max_width, int max_height,
+                                int max_batch, int device)
+{
+    if (!out || !p) { set_error("sgbm_create: null argument"); return -RTDM_EINVAL; }
+    *out = nullptr;
+    int rc = sgbm_check_params(p);
+    if (rc) return rc;
+    if (max_width < 1 || max_height < 1 || max_batch < 1 || max_width > 8000 || max_height > 65535) {
+        set_error("sgbm_create: bad maximum geometry (width <= 8000, height <= 65535, batch >= 1)");
+        return -RTDM_EINVAL;
+    }
+    rc = check_device(device);
+    if (rc) return rc;
+    RTDM_CUDA(cudaSetDevice(device));
+    rtdm_sgbm *h = new (std::nothrow) rtdm_sgbm();
+    if (!h) return -RTDM_ENOMEM;
+    memset(h, 0, sizeof *h);
+    h->p = *p; h->maxW = max_width; h->maxH = max_height; h->maxB = max_batch; h->dev = device;
+    SgbmGeom g = sgbm_geom(*p, max_width, max_height);
+    size_t pl = 0, vol = 0;
+    sgbm_work_bytes(g, &pl, &vol);
+    h->frame_planes = pl; h->frame_vol = vol;
+    // the two cost volumes are the big consumers (2 x 2 bytes x H x W1 x D per frame): keep at most
+    // ~24 GB of them resident and run larger calls as sub-batches
+    const size_t per_frame = std::max<size_t>(1, vol * 4);
+    h->volB = (int)std::max<size_t>(1, std::min<size_t>((size_t)max_batch, (size_t)24e9 / per_frame));
+    const size_t B = (size_t)max_batch, VB = (size_t)h->volB;
+    h->rpitch = align_up((size_t)max_width, 8); h->rframe = h->rpitch * max_height;
+    h->spitch = align_up((size_t)max_width, 64); h->sframe = h->spitch * max_height;
+    h->dpitch = h->rpitch; h->dframe = h->rframe;
+    rc = (int)cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) == cudaSuccess ? 0 : -RTDM_EIO;
+    if (!rc) rc = dev_alloc(&h->planes, pl * VB);
+    if (!rc) rc = dev_alloc(&h->C, vol * VB + 64);
+    if (!rc) rc = dev_alloc(&h->S, vol * VB + 64);
+    if (!rc) rc = dev_alloc(&h->raw, h->rframe * VB);
+    if (!rc) rc = dev_alloc(&h->labels, (size_t)max_width * max_height * VB);
+    if (!rc) rc = dev_alloc(&h->sizes, (size_t)max_width * max_height * VB);
+    if (!rc) rc = dev_alloc(&h->dL, h->sframe * B);
+    if (!rc) rc = dev_alloc(&h->dR, h->sframe * B);
+    if (!rc) rc = dev_alloc(&h->dD, h->dframe * B);
+    if (rc) { rtdm_sgbm_destroy(h); return rc; }
+    *out = h;
+    return 0;
+}
+
+static int sgbm_pipeline(rtdm_sgbm *h, int n, PlaneU8 L, PlaneU8 R, int W, int H, PlaneS16 out, cudaStream_t st)
+{
+    if (W > h->maxW || H > h->maxH || n > h->maxB || W < 1 || H < 1 || n < 1) {
+        set_error("sgbm: frame geometry or batch exceeds what the handle was created for");
+        return -RTDM_EINVAL;
+    }
+    SgbmGeom g = sgbm_geom(h->p, W, H);
+    const int INVS = (g.minD - 1) * 16;
+    size_t pl = 0, vol = 0;
+    sgbm_work_bytes(g, &pl, &vol);
+    for (int f0 = 0; f0 < n; f0 += h->volB) {
+        const int m = std::min(h->volB, n - f0);
+        PlaneU8 l = {L.p + (size_t)f0 * L.frame, L.pitch, L.frame}, r = {R.p + (size_t)f0 * R.frame, R.pitch, R.frame};
+        PlaneS16 o = {out.p + (size_t)f0 * out.frame, out.pitch, out.frame};
+        PlaneS16 raw = {h->raw, h->rpitch, h->rframe};
+        if (g.W1 > 0) {
+            SgbmWork w;
+            memset(&w, 0, sizeof w);
+            w.planes = h->planes; w.C = (int16_t *)h->C; w.S = (int16_t *)h->S; w.frame_planes = pl; w.frame_vol = vol;
+            int rc = launch_sgbm(g, m, l, r, raw, w, st, &h->launches);
+            if (rc) return rc;
+        } else {
+            // no computable column: the whole map is invalid (validate_mask with an empty row range fills it)
+            int rc = launch_validate_mask(m, W, H, g.minD, g.D, -1, 0, 0, 0, 0, 0, 0, raw, raw, raw, st, &h->launches);
+            if (rc) return rc;
+        }
+        int rc = launch_median3(m, W, H, raw, o, st, &h->launches);
+        if (rc) return rc;
+        if (h->p.speckleWindowSize > 0) {
+            rc = launch_speckle(m, W, H, o, INVS, h->p.speckleWindowSize, 16 * h->p.speckleRange, h->labels, h->sizes, st, &h->launches);
+            if (rc) return rc;
+        }
+    }
+    return 0;
+}
+
+extern "C" int rtdm_sgbm_compute_device(rtdm_sgbm *h, int n, const uint8_t *left, size_t lstep, size_t lframe,
+                                        const uint8_t *right, size_t rstep, size_t rframe, int width, int height,
+                                        int16_t *disp, size_t dstep, size_t dframe, void *cuda_stream)
+{
+    if (!h || !left || !right || !disp) { set_error("sgbm_compute_device: null argument"); return -RTDM_EINVAL; }
+    if (dstep % 2 || dframe % 2) { set_error("sgbm: output steps must be multiples of 2 bytes"); return -RTDM_EINVAL; }
+    RTDM_CUDA(cudaSetDevice(h->dev));
+    h->launches = 0;
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->st;
+    return sgbm_pipeline(h, n, PlaneU8{left, lstep, lframe}, PlaneU8{right, rstep, rframe}, width, height,
+                         PlaneS16{disp, dstep / 2, dframe / 2}, st);
+}
+
+extern "C" int rtdm_sgbm_compute_batch(rtdm_sgbm *h, int n, const uint8_t *left, size_t lstep, size_t lframe,
+                                       const uint8_t *right, size_t rstep, size_t rframe, int width, int height,
+                                       int16_t *disp, size_t dstep, size_t dframe)
+{
+    if (!h || !left || !right || !disp) { set_error("sgbm_compute: null argument"); return -RTDM_EINVAL; }
+    if (n < 1 || n > h->maxB || width > h->maxW || height > h->maxH || width < 1 || height < 1) {
+        set_error("sgbm: frame geometry or batch exceeds what the handle was created for");
+        return -RTDM_EINVAL;
+    }
+    RTDM_CUDA(cudaSetDevice(h->dev));
+    h->launches = 0;
+    cudaStream_t st = h->st;
+    for (int k = 0; k < n; k++) {
+        RTDM_CUDA(cudaMemcpy2DAsync(h->dL + k * h->sframe, h->spitch, left + k * lframe, lstep, width, height, cudaMemcpyHostToDevice, st));
+        RTDM_CUDA(cudaMemcpy2DAsync(h->dR + k * h->sframe, h->spitch, right + k * rframe, rstep, width, height, cudaMemcpyHostToDevice, st));
+    }
+    int rc = sgbm_pipeline(h, n, PlaneU8{h->dL, h->spitch, h->sframe}, PlaneU8{h->dR, h->spitch, h->sframe}, width, height,
+                           PlaneS16{h->dD, h->dpitch, h->dframe}, st);
+    if (rc) return rc;
+    for (int k = 0; k < n; k++)
+        RTDM_CUDA(cudaMemcpy2DAsync((uint8_t *)disp + k * dframe, dstep, h->dD + k * h->dframe, h->dpitch * 2,
+                                    (size_t)width * 2, height, cudaMemcpyDeviceToHost, st));
+    RTDM_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" int rtdm_sgbm_compute(rtdm_sgbm *h, const uint8_t *left, size_t lstep, const uint8_t *right,
+                                 size_t rstep, int width, int height, int16_t *disp, size_t dstep)
+{
+    return rtdm_sgbm_compute_batch(h, 1, left, lstep, 0, right, rstep, 0, width, height, disp, dstep, 0);
+}
+
+extern "C" int rtdm_sgbm_last_launches(const rtdm_sgbm *h) { return h ? h->launches : 0; }
+
+// =================================================================================================
 // morphological filter
 // =================================================================================================
 struct rtdm_morph {

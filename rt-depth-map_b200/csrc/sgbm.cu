@@ -1,17 +1,384 @@
-// sgbm.cu -- semi-global matching (placeholder until the kernels land).
+// sgbm.cu -- semi-global matching: Birchfield-Tomasi cost, box aggregation, 5/8-path min-plus
+// aggregation over 16-bit costs, winner-take-all with uniqueness / sub-pixel / left-right check.
+//
+// Replaces computeDisparitySGBM inside cv::StereoSGBM::compute as reached from
+// SWSemiGlobalMatcher::compute (reference stereo-matcher/sgbm-sw.cpp:32-37).  Arithmetic per
+// SURVEY.md App. A.6 (restated and pinned in oracle/sgbm_oracle.c).
+//
+// Pipeline per batch of frames (volumes are [frame][y][x1][d] uint16, x1 in [0, W1)):
+//   sgbm_planes_kernel   : per pixel (value, lo, hi) of the x-Sobel plane and the raw plane, both images
+//   sgbm_cost_hsum_kernel: BT pixel cost of a row tile in shared memory -> horizontal box sum -> Hs volume
+//   sgbm_vsum_kernel     : C = P2 + vertical box sum of Hs (clamped rows)
+//   sgbm_path_kernel     : one launch per path direction; ONE WARP PER PATH CHAIN, the previous L_r
+//                          vector lives in registers (packed u16x2, D/32 words per lane), neighbours
+//                          d-1 / d+1 and min_k L_r(k) through warp shuffles; S += L_r
+//   sgbm_wta_kernel      : per row: warp argmin per pixel, uniqueness, sub-pixel, disp2 by atomicMin
+//                          (OpenCV's right-to-left strict '>' scan == min over (cost, -x)), LR check
+// then launch_median3 and launch_speckle (postproc.cu).
+// Every pixel belongs to exactly one chain per direction, so the S read-modify-write needs no atomics.
 #include "common.cuh"
+
 namespace rtdm {
-size_t sgbm_work_bytes(const SgbmGeom &, size_t *planes, size_t *vol) { if (planes) *planes = 0; if (vol) *vol = 0; return 0; }
-int launch_sgbm(const SgbmGeom &, int, PlaneU8, PlaneU8, PlaneS16, SgbmWork, cudaStream_t, int *)
+namespace {
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
+
+// ------------------------------------------------------------------------------------------------
+// planes: out[img][plane][comp][y][x], comp 0 = value, 1 = lo, 2 = hi (half-pixel interval)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int bt_plane_value(const uint8_t *img, size_t pitch, int W, int H, int x, int y, int plane, int ftzero)
 {
-    set_error("sgbm: not implemented yet");
-    return -RTDM_ENOSYS;
+    if (x <= 0 || x >= W - 1) return ftzero;
+    const uint8_t *r = img + (size_t)y * pitch;
+    if (plane) return r[x];
+    const uint8_t *rn = y > 0 ? r - pitch : r, *rs = y < H - 1 ? r + pitch : r;
+    int g = 2 * ((int)r[x + 1] - (int)r[x - 1]) + ((int)rn[x + 1] - (int)rn[x - 1]) + ((int)rs[x + 1] - (int)rs[x - 1]);
+    return clampi(g, -ftzero, ftzero) + ftzero;
 }
+
+__global__ void __launch_bounds__(256)
+sgbm_planes_kernel(PlaneU8 left, PlaneU8 right, uint8_t *planes, size_t frame_planes, int W, int H, int Wp, int ftzero)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const int f = blockIdx.z >> 1, img = blockIdx.z & 1;
+    if (x >= W) return;
+    const uint8_t *src = img ? right.p + (size_t)f * right.frame : left.p + (size_t)f * left.frame;
+    const size_t sp = img ? right.pitch : left.pitch;
+    uint8_t *out = planes + (size_t)f * frame_planes + (size_t)img * 6 * H * Wp;
+#pragma unroll
+    for (int pl = 0; pl < 2; pl++) {
+        int v = bt_plane_value(src, sp, W, H, x, y, pl, ftzero);
+        int a = x > 0 ? (v + bt_plane_value(src, sp, W, H, x - 1, y, pl, ftzero)) / 2 : v;
+        int b = x < W - 1 ? (v + bt_plane_value(src, sp, W, H, x + 1, y, pl, ftzero)) / 2 : v;
+        uint8_t *o = out + (size_t)(pl * 3) * H * Wp + (size_t)y * Wp + x;
+        o[0] = (uint8_t)v;
+        o[(size_t)H * Wp] = (uint8_t)min(min(a, b), v);
+        o[(size_t)2 * H * Wp] = (uint8_t)max(max(a, b), v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BT cost + horizontal window.  CTA = (tile of TX cost columns, row y, frame).
+// ------------------------------------------------------------------------------------------------
+constexpr int TX = 32;
+
+struct CostArgs {
+    const uint8_t *planes; size_t frame_planes;
+    uint16_t *Hs; size_t frame_vol;
+    int W, H, Wp, D, minD, h, minX1, W1;
+};
+
+__global__ void __launch_bounds__(256)
+sgbm_cost_hsum_kernel(CostArgs a)
+{
+    extern __shared__ __align__(16) uint8_t cs[];
+    const int y = blockIdx.y, f = blockIdx.z;
+    const int x0 = blockIdx.x * TX;                         // first cost column of the tile
+    const int D = a.D, h = a.h;
+    const int NXC = TX + 2 * h;                             // cost columns incl. halo (clamped)
+    const int maxD = a.minD + D;
+    // left image columns needed: xl = clamp(x0 - h + i) + minX1 ; right: xl - d for d in [minD, maxD)
+    const int cl0 = clampi(x0 - h, 0, a.W1 - 1), cl1 = clampi(x0 + TX - 1 + h, 0, a.W1 - 1);
+    const int xl_lo = cl0 + a.minX1, xl_hi = cl1 + a.minX1;
+    const int xr_lo = xl_lo - (maxD - 1), xr_hi = xl_hi - a.minD;
+    const int NL = xl_hi - xl_lo + 1, NR = xr_hi - xr_lo + 1;
+    uint16_t *pix = reinterpret_cast<uint16_t *>(cs);                   // [NXC][D]
+    uint8_t *ls = cs + (size_t)NXC * D * 2;                             // [6][NL]
+    uint8_t *rs = ls + (size_t)6 * NL;                                  // [6][NR]
+    const uint8_t *pf = a.planes + (size_t)f * a.frame_planes;
+    const size_t comp = (size_t)a.H * a.Wp;
+    for (int i = threadIdx.x; i < 6 * NL; i += blockDim.x) {
+        int c = i / NL, k = i - c * NL;
+        ls[i] = pf[(size_t)c * comp + (size_t)y * a.Wp + clampi(xl_lo + k, 0, a.W - 1)];
+    }
+    for (int i = threadIdx.x; i < 6 * NR; i += blockDim.x) {
+        int c = i / NR, k = i - c * NR;
+        rs[i] = pf[(size_t)(6 + c) * comp + (size_t)y * a.Wp + clampi(xr_lo + k, 0, a.W - 1)];
+    }
+    __syncthreads();
+    // pixel cost for each (halo column, d): lanes run over d
+    for (int i = threadIdx.x; i < NXC * D; i += blockDim.x) {
+        const int c = i / D, d = i - c * D;
+        const int xc = clampi(x0 - h + c, 0, a.W1 - 1);
+        const int kl = xc + a.minX1 - xl_lo;
+        const int kr = xc + a.minX1 - (d + a.minD) - xr_lo;
+        int cost = 0;
+#pragma unroll
+        for (int pl = 0; pl < 2; pl++) {
+            const int u = ls[(pl * 3 + 0) * NL + kl], u0 = ls[(pl * 3 + 1) * NL + kl], u1 = ls[(pl * 3 + 2) * NL + kl];
+            const int v = rs[(pl * 3 + 0) * NR + kr], v0 = rs[(pl * 3 + 1) * NR + kr], v1 = rs[(pl * 3 + 2) * NR + kr];
+            const int c0 = max(max(0, u - v1), v0 - u);
+            const int c1 = max(max(0, v - u1), u0 - v);
+            cost += min(c0, c1) >> (pl ? 2 : 0);
+        }
+        pix[i] = (uint16_t)cost;
+    }
+    __syncthreads();
+    uint16_t *out = a.Hs + (size_t)f * a.frame_vol + ((size_t)y * a.W1 + x0) * D;
+    const int ncol = min(TX, a.W1 - x0);
+    for (int i = threadIdx.x; i < ncol * D; i += blockDim.x) {
+        const int c = i / D, d = i - c * D;
+        int s = 0;
+        for (int k = 0; k <= 2 * h; k++) s += pix[(c + k) * D + d];
+        out[i] = (uint16_t)s;
+    }
+}
+
+// C = P2 + sum over clamped rows y-h..y+h of Hs; two disparities (one u16x2 word) per thread
+__global__ void __launch_bounds__(256)
+sgbm_vsum_kernel(const uint32_t *Hs, uint32_t *C, size_t frame_words, size_t row_words, int H, int h, uint32_t P2x2)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y, f = blockIdx.z;
+    if (i >= row_words) return;
+    const uint32_t *src = Hs + (size_t)f * frame_words + i;
+    uint32_t s = P2x2;
+    for (int j = -h; j <= h; j++) s += src[(size_t)clampi(y + j, 0, H - 1) * row_words];
+    C[(size_t)f * frame_words + (size_t)y * row_words + i] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// path aggregation: one warp per chain.  K2 = u16x2 words per lane; lane l owns d in [2*K2*l, 2*K2*(l+1)).
+// ------------------------------------------------------------------------------------------------
+struct PathArgs {
+    const uint32_t *C; uint32_t *S; size_t frame_words;
+    int W1, H, D, P1, P2;
+    int px, py;          // predecessor offset
+    int first;           // 1: S = L (no read), 0: S += L
+    int nchains;
+};
+
+__device__ __forceinline__ uint32_t min2(uint32_t a, uint32_t b) { return __vminu2(a, b); }
+
+template <int K2>
+__global__ void __launch_bounds__(128)
+sgbm_path_kernel(PathArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const int chain = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int f = blockIdx.y;
+    if (chain >= a.nchains) return;
+    const int sx = -a.px, sy = -a.py;
+    // chain start: a pixel whose predecessor lies outside the image
+    int x, y;
+    {
+        const int nrow = sy != 0 ? a.W1 : 0;
+        if (chain < nrow) { x = chain; y = sy > 0 ? 0 : a.H - 1; }
+        else {
+            int j = chain - nrow;
+            x = sx > 0 ? 0 : a.W1 - 1;
+            if (sy > 0) y = j + 1; else if (sy < 0) y = j; else y = j;     // skip the corner owned by the row set
+        }
+    }
+    const int wordsD = a.D / 2;
+    const int nlanes = wordsD / K2;                        // active lanes
+    const bool act = lane < nlanes;
+    const uint32_t P1x2 = (uint32_t)a.P1 * 0x00010001u;
+    const uint32_t *Cf = a.C + (size_t)f * a.frame_words;
+    uint32_t *Sf = a.S + (size_t)f * a.frame_words;
+    uint32_t Lp[K2];
+#pragma unroll
+    for (int k = 0; k < K2; k++) Lp[k] = 0u;               // out-of-image predecessor: L = 0
+    uint32_t minLp = 0u;
+    const long long stepw = ((long long)sy * a.W1 + sx) * wordsD;
+    size_t off = ((size_t)y * a.W1 + x) * wordsD + (size_t)lane * K2;
+    uint32_t c[K2], s[K2];
+#pragma unroll
+    for (int k = 0; k < K2; k++) { c[k] = act ? Cf[off + k] : 0u; s[k] = (act && !a.first) ? Sf[off + k] : 0u; }
+    while (true) {
+        const int xn = x + sx, yn = y + sy;
+        const bool more = (xn >= 0 && xn < a.W1 && yn >= 0 && yn < a.H);
+        // prefetch the next pixel's C and S
+        uint32_t cn[K2], sn[K2];
+        const size_t offn = (size_t)((long long)off + stepw);
+#pragma unroll
+        for (int k = 0; k < K2; k++) {
+            cn[k] = (more && act) ? Cf[offn + k] : 0u;
+            sn[k] = (more && act && !a.first) ? Sf[offn + k] : 0u;
+        }
+        // neighbours across lanes: last half of the left lane, first half of the right lane
+        uint32_t left = __shfl_up_sync(0xFFFFFFFFu, Lp[K2 - 1], 1);
+        uint32_t right = __shfl_down_sync(0xFFFFFFFFu, Lp[0], 1);
+        if (lane == 0) left = 0x7FFF0000u;                 // L[-1] = MAX_COST (upper half is used)
+        if (lane >= nlanes - 1) right = 0x00007FFFu;       // L[D]  = MAX_COST (lower half is used)
+        const uint32_t delta = (uint32_t)a.P2 + minLp;     // < 65536
+        const uint32_t dx2 = delta * 0x00010001u;
+        uint32_t Ln[K2];
+        uint32_t m = 0xFFFFFFFFu;
+#pragma unroll
+        for (int k = 0; k < K2; k++) {
+            const uint32_t prevw = k == 0 ? left : Lp[k - 1];
+            const uint32_t nextw = k == K2 - 1 ? right : Lp[k + 1];
+            const uint32_t lm1 = __byte_perm(prevw, Lp[k], 0x5432);     // (L[d-1], L[d])   for the pair (d, d+1)
+            const uint32_t lp1 = __byte_perm(Lp[k], nextw, 0x5432);     // (L[d+1], L[d+2])
+            uint32_t t = __vimin3_u16x2(Lp[k], __vadd2(lm1, P1x2), __vadd2(lp1, P1x2));
+            t = min2(t, dx2);
+            t = __vsub2(__vadd2(t, c[k]), dx2);
+            Ln[k] = t;
+            m = min2(m, t);
+            if (act) {
+                uint32_t sv = a.first ? t : min2(__vadd2(s[k], t), 0x7FFF7FFFu);
+                Sf[off + k] = sv;
+            }
+        }
+        // min over the chain's D values: inactive lanes must not contribute
+        uint32_t mm = min(m & 0xFFFFu, m >> 16);
+        if (!act) mm = 0xFFFFu;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mm = min(mm, __shfl_xor_sync(0xFFFFFFFFu, mm, o));
+        minLp = mm;
+#pragma unroll
+        for (int k = 0; k < K2; k++) { Lp[k] = Ln[k]; c[k] = cn[k]; s[k] = sn[k]; }
+        if (!more) break;
+        x = xn; y = yn; off = offn;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// WTA + uniqueness + sub-pixel + LR check, one CTA per (row, frame)
+// ------------------------------------------------------------------------------------------------
+struct WtaArgs {
+    const uint16_t *S; size_t frame_vol;
+    PlaneS16 out;
+    int W, H, D, minD, minX1, maxX1, W1, uniq, d12;
+};
+
+__global__ void __launch_bounds__(256)
+sgbm_wta_kernel(WtaArgs a)
+{
+    extern __shared__ __align__(16) uint8_t ws[];
+    uint32_t *key2 = reinterpret_cast<uint32_t *>(ws);                 // [W]  (minS << 16 | 0xFFFF - x1)
+    int16_t *dval = reinterpret_cast<int16_t *>(key2 + a.W);           // [W]  sub-pixel disparity or INV
+    int16_t *best = dval + a.W;                                        // [W1] integer disparity index
+    const int y = blockIdx.x, f = blockIdx.y;
+    const int INV = a.minD - 1, INVS = INV * 16;
+    const int D = a.D;
+    for (int x = threadIdx.x; x < a.W; x += blockDim.x) { key2[x] = 0xFFFFFFFFu; dval[x] = (int16_t)INVS; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const uint16_t *Srow = a.S + (size_t)f * a.frame_vol + (size_t)y * a.W1 * D;
+    for (int x = warp; x < a.W1; x += nw) {
+        const uint16_t *Sp = Srow + (size_t)x * D;
+        uint32_t kmin = 0xFFFFFFFFu;
+        for (int d = lane; d < D; d += 32) kmin = min(kmin, ((uint32_t)Sp[d] << 16) | (uint32_t)d);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) kmin = min(kmin, __shfl_xor_sync(0xFFFFFFFFu, kmin, o));
+        const int minS = (int)(kmin >> 16), bd = (int)(kmin & 0xFFFFu);
+        if (minS >= 32767) { if (lane == 0) best[x] = -1; continue; }          // degenerate (outside the domain)
+        bool viol = false;
+        for (int d = lane; d < D; d += 32)
+            viol = viol || ((int)Sp[d] * (100 - a.uniq) < minS * 100 && abs(bd - d) > 1);
+        viol = __any_sync(0xFFFFFFFFu, viol);
+        if (lane == 0) {
+            best[x] = (int16_t)bd;
+            if (!viol) {
+                const int x2 = x + a.minX1 - bd - a.minD;
+                if (x2 >= 0 && x2 < a.W) atomicMin(&key2[x2], ((uint32_t)minS << 16) | (uint32_t)(0xFFFF - x));
+                int d = bd;
+                if (0 < d && d < D - 1) {
+                    const int sm = Sp[d - 1], sp = Sp[d + 1], s0 = Sp[d];
+                    const int den = max(sm + sp - 2 * s0, 1);
+                    d = d * 16 + ((sm - sp) * 16 + den) / (den * 2);
+                } else d *= 16;
+                dval[x + a.minX1] = (int16_t)(d + a.minD * 16);
+            }
+        }
+    }
+    __syncthreads();
+    int16_t *orow = a.out.p + (size_t)f * a.out.frame + (size_t)y * a.out.pitch;
+    for (int x = threadIdx.x; x < a.W; x += blockDim.x) {
+        int d1 = dval[x];
+        if (x >= a.minX1 && x < a.maxX1 && d1 != INVS) {
+            const int _d = d1 >> 4, d_ = (d1 + 15) >> 4;
+            const int _x = x - _d, x_ = x - d_;
+            bool bad = true;
+            if (0 <= _x && _x < a.W) {
+                const uint32_t k = key2[_x];
+                const int d2 = (k == 0xFFFFFFFFu) ? INV : (int)best[0xFFFF - (int)(k & 0xFFFFu)] + a.minD;
+                bad = bad && d2 >= a.minD && abs(d2 - _d) > a.d12;
+            } else bad = false;
+            if (0 <= x_ && x_ < a.W) {
+                const uint32_t k = key2[x_];
+                const int d2 = (k == 0xFFFFFFFFu) ? INV : (int)best[0xFFFF - (int)(k & 0xFFFFu)] + a.minD;
+                bad = bad && d2 >= a.minD && abs(d2 - d_) > a.d12;
+            } else bad = false;
+            if (bad) d1 = INVS;
+        }
+        orow[x] = (int16_t)d1;
+    }
+}
+
+}  // namespace
+
+size_t sgbm_work_bytes(const SgbmGeom &g, size_t *planes, size_t *vol)
+{
+    const size_t Wp = align_up((size_t)g.W, 16);
+    const size_t pl = (size_t)12 * g.H * Wp;
+    const size_t v = (size_t)g.H * (g.W1 > 0 ? g.W1 : 0) * g.D;        // elements
+    if (planes) *planes = pl;
+    if (vol) *vol = v;
+    return pl + 2 * v * sizeof(uint16_t);
+}
+
+int launch_sgbm(const SgbmGeom &g, int n, PlaneU8 left, PlaneU8 right, PlaneS16 out, SgbmWork w,
+                cudaStream_t st, int *launches)
+{
+    if (n <= 0 || g.W1 <= 0) return 0;
+    const int Wp = (int)align_up((size_t)g.W, 16);
+    const int h = g.bs / 2;
+    // 1. planes
+    sgbm_planes_kernel<<<dim3(cdiv(g.W, 256), g.H, 2 * n), 256, 0, st>>>(left, right, w.planes, w.frame_planes, g.W, g.H, Wp, g.ftzero);
+    // 2. BT cost + horizontal window -> Hs (stored in the S volume, which is rewritten by the first path)
+    {
+        CostArgs a;
+        a.planes = w.planes; a.frame_planes = w.frame_planes;
+        a.Hs = reinterpret_cast<uint16_t *>(w.S); a.frame_vol = w.frame_vol;
+        a.W = g.W; a.H = g.H; a.Wp = Wp; a.D = g.D; a.minD = g.minD; a.h = h; a.minX1 = g.minX1; a.W1 = g.W1;
+        const int NXC = TX + 2 * h;
+        size_t smem = (size_t)NXC * g.D * 2 + (size_t)6 * (NXC + 8) + (size_t)6 * (NXC + g.D + 8);
+        if (smem > 48 * 1024)
+            RTDM_CUDA(cudaFuncSetAttribute(sgbm_cost_hsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sgbm_cost_hsum_kernel<<<dim3(cdiv(g.W1, TX), g.H, n), 256, smem, st>>>(a);
+    }
+    // 3. vertical window + P2 -> C
+    const size_t row_words = (size_t)g.W1 * g.D / 2, frame_words = w.frame_vol / 2;
+    sgbm_vsum_kernel<<<dim3((unsigned)((row_words + 255) / 256), g.H, n), 256, 0, st>>>(
+        reinterpret_cast<const uint32_t *>(w.S), reinterpret_cast<uint32_t *>(w.C), frame_words, row_words, g.H, h,
+        (uint32_t)g.P2 * 0x00010001u);
+    if (launches) (*launches) += 3;
+    RTDM_CUDA(cudaGetLastError());
+    // 4. paths
+    static const int dirs[8][2] = {{-1, 0}, {-1, -1}, {0, -1}, {1, -1}, {1, 0}, {-1, 1}, {0, 1}, {1, 1}};
+    const int ndirs = g.mode == RTDM_SGBM_MODE_HH ? 8 : 5;
+    const int K2 = g.D <= 64 ? 1 : (g.D <= 128 ? 2 : 4);   // u16x2 words per lane (divides D/2 for any D % 16 == 0)
+    for (int k = 0; k < ndirs; k++) {
+        PathArgs a;
+        a.C = reinterpret_cast<const uint32_t *>(w.C); a.S = reinterpret_cast<uint32_t *>(w.S); a.frame_words = frame_words;
+        a.W1 = g.W1; a.H = g.H; a.D = g.D; a.P1 = g.P1; a.P2 = g.P2; a.px = dirs[k][0]; a.py = dirs[k][1];
+        a.first = (k == 0);
+        const int sx = -a.px, sy = -a.py;
+        a.nchains = (sy != 0 ? g.W1 : 0) + (sx != 0 ? (sy != 0 ? g.H - 1 : g.H) : 0);
+        dim3 grid(cdiv(a.nchains, 4), n);
+        switch (K2) {
+            case 1: sgbm_path_kernel<1><<<grid, 128, 0, st>>>(a); break;
+            case 2: sgbm_path_kernel<2><<<grid, 128, 0, st>>>(a); break;
+            default: sgbm_path_kernel<4><<<grid, 128, 0, st>>>(a); break;
+        }
+        if (launches) (*launches)++;
+    }
+    RTDM_CUDA(cudaGetLastError());
+    // 5. WTA
+    {
+        WtaArgs a;
+        a.S = reinterpret_cast<const uint16_t *>(w.S); a.frame_vol = w.frame_vol; a.out = out;
+        a.W = g.W; a.H = g.H; a.D = g.D; a.minD = g.minD; a.minX1 = g.minX1; a.maxX1 = g.maxX1; a.W1 = g.W1;
+        a.uniq = g.uniq; a.d12 = g.d12;
+        size_t smem = (size_t)g.W * 4 + (size_t)g.W * 2 + (size_t)g.W1 * 2 + 16;
+        sgbm_wta_kernel<<<dim3(g.H, n), 256, smem, st>>>(a);
+        if (launches) (*launches)++;
+    }
+    RTDM_CUDA(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace rtdm
-struct rtdm_sgbm { int dummy; };
-extern "C" int rtdm_sgbm_create(rtdm_sgbm **out, const rtdm_params *, int, int, int, int) { if (out) *out = nullptr; rtdm::set_error("sgbm: not implemented yet"); return -RTDM_ENOSYS; }
-extern "C" void rtdm_sgbm_destroy(rtdm_sgbm *) {}
-extern "C" int rtdm_sgbm_compute(rtdm_sgbm *, const uint8_t *, size_t, const uint8_t *, size_t, int, int, int16_t *, size_t) { return -RTDM_ENOSYS; }
-extern "C" int rtdm_sgbm_compute_batch(rtdm_sgbm *, int, const uint8_t *, size_t, size_t, const uint8_t *, size_t, size_t, int, int, int16_t *, size_t, size_t) { return -RTDM_ENOSYS; }
-extern "C" int rtdm_sgbm_compute_device(rtdm_sgbm *, int, const uint8_t *, size_t, size_t, const uint8_t *, size_t, size_t, int, int, int16_t *, size_t, size_t, void *) { return -RTDM_ENOSYS; }
-extern "C" int rtdm_sgbm_last_launches(const rtdm_sgbm *) { return 0; }

@@ -1,0 +1,88 @@
+"""GPU parity: the CUDA semi-global matcher (through the C ABI) against the cv2 golden vectors and
+the oracle.  Bit-exact CV_16S."""
+import json
+
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(rt, p, W, H, **kw):
+    return rt.CUDASemiGlobalMatcher(p["blockSize"], p["minDisparity"], p["numDisparities"], p["uniquenessRatio"],
+                                    p["speckleWindowSize"], p["speckleRange"], p["disp12MaxDiff"],
+                                    mode=p.get("mode", 0), max_width=W, max_height=H, **kw)
+
+
+@pytest.mark.parametrize("name", golden_names("sgbm_"))
+def test_sgbm_matches_cv2_golden(gpu, name):
+    g = load_golden(name)
+    p = json.loads(str(g["params"]))
+    H, W = g["left"].shape
+    m = _mk(gpu, p, W, H)
+    got = m.compute(g["left"], g["right"])
+    assert np.array_equal(got, g["disp"]), f"{name}: {(got != g['disp']).sum()} pixels differ"
+    assert m.last_launches() >= 3 + 5 + 1 + 1
+    m.setROI1((1, 2, 3, 4)); m.setROI2(None)          # no-ops like the reference (sgbm-sw.h:32-33)
+    assert np.array_equal(m.compute(g["left"], g["right"]), g["disp"])
+
+
+def test_sgbm_random_params_match_oracle(gpu, orc):
+    from rtdm_b200 import synth
+    rng = np.random.default_rng(12)
+    checked = 0
+    for i in range(14):
+        W, H = int(rng.integers(100, 400)), int(rng.integers(40, 220))
+        nd = 16 * int(rng.integers(1, 11)); bs = 2 * int(rng.integers(0, 4)) + 1
+        if nd + 8 >= W:
+            continue
+        p = dict(blockSize=bs, minDisparity=0, numDisparities=nd, uniquenessRatio=int(rng.integers(0, 25)),
+                 speckleWindowSize=int(rng.integers(0, 150)), speckleRange=int(rng.integers(0, 8)),
+                 disp12MaxDiff=int(rng.integers(-1, 4)), mode=int(rng.integers(0, 2)))
+        L, R, _ = synth.stereo_pair(W, H, nd, 700 + i)
+        ref, outside = orc.sgbm_compute(L, R, orc.sgbm_params(**p), return_domain_flag=True)
+        if outside:
+            continue
+        got = _mk(gpu, p, W, H).compute(L, R)
+        assert np.array_equal(ref, got), (p, W, H, int((ref != got).sum()))
+        checked += 1
+    assert checked >= 8
+
+
+def test_sgbm_degenerate_width(gpu, orc):
+    from rtdm_b200 import synth
+    L, R, _ = synth.stereo_pair(100, 60, 16, 5)
+    p = dict(blockSize=5, minDisparity=0, numDisparities=112, uniquenessRatio=10, speckleWindowSize=100,
+             speckleRange=32, disp12MaxDiff=1, mode=0)
+    got = _mk(gpu, p, 100, 60).compute(L, R)
+    assert (got == -16).all()
+    assert np.array_equal(got, orc.sgbm_compute(L, R, orc.sgbm_params(**p)))
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_sgbm_720p_full_size(gpu, orc, mode):
+    """BASELINE config 3: 1280x720, nd=128, bs=5, P1=600, P2=2400; MODE_SGBM and MODE_HH; batch of 2."""
+    from rtdm_b200 import synth
+    p = dict(blockSize=5, minDisparity=0, numDisparities=128, uniquenessRatio=10, speckleWindowSize=100,
+             speckleRange=32, disp12MaxDiff=1, mode=mode)
+    frames = [synth.stereo_pair(1280, 720, 128, 1000 + i) for i in range(2)]
+    Ls = np.stack([f[0] for f in frames]); Rs = np.stack([f[1] for f in frames])
+    m = _mk(gpu, p, 1280, 720, max_batch=2)
+    out = m.compute_batch(Ls, Rs)
+    for i in range(2):
+        ref, outside = orc.sgbm_compute(Ls[i], Rs[i], orc.sgbm_params(**p), return_domain_flag=True)
+        assert not outside
+        assert np.array_equal(out[i], ref), (i, int((out[i] != ref).sum()))
+        v = out[i][out[i] != -16]
+        assert v.min() >= 0 and v.max() <= 127 * 16 + 15
+        assert (out[i][:, :127] == -16).all()
+
+
+def test_sgbm_errors(gpu):
+    with pytest.raises(gpu.RtdmError) as e:
+        gpu.CUDASemiGlobalMatcher(5, 0, 100, 10, 100, 32, 1)
+    assert e.value.code == -gpu.EINVAL
+    with pytest.raises(gpu.RtdmError):
+        gpu.CUDASemiGlobalMatcher(4, 0, 64, 10, 100, 32, 1)
