@@ -267,12 +267,9 @@ def run_ours(args):
     if hasattr(matcher, "stage_times"):
         stage_ms, stage_calls = matcher.stage_times()
         matcher.set_profiling(False)
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    frames_total = B * args.steps * world
-    fps = frames_total / (ms_max * 1e-3)
+    from rtdm_b200 import sharding
+    # frames are independent: every rank processed its own B*steps frames; value = all frames / max time
+    fps, ms_max, frames_total = sharding.whole_job_throughput(B * args.steps, ms, 1.0, dist, dev)
     value = fps * mde_per_frame()
 
     # ---- end to end through the host-pointer C ABI with pinned host buffers ------------------------
@@ -295,10 +292,7 @@ def run_ours(args):
     for _ in range(e2e_steps):
         e2e_step()
     torch.cuda.synchronize()
-    t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    e2e_fps = B * e2e_steps * world / float(t_e2e.item())
+    e2e_fps, _, _ = sharding.whole_job_throughput(B * e2e_steps, (time.perf_counter() - t0) * 1e3, 1.0, dist, dev)
     h2d = B * 2 * W * H + (B * W * H if filt is not None else 0)
     d2h = B * W * H * 2 + (B * W * H if filt is not None else 0)
 

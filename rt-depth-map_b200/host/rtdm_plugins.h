@@ -1,0 +1,166 @@
+// rtdm_plugins.h -- C++ plugin peers for rt-depth-map, header-only, over the C ABI (include/rtdm_b200.h).
+//
+//   CUDAMatcherKonolige      : BlockMatcher        peer of SWMatcherKonolige     (reference include/stereo-matcher/bm-sw.h:25-37)
+//   CUDASemiGlobalMatcher    : BlockMatcher        peer of SWSemiGlobalMatcher   (reference include/stereo-matcher/sgbm-sw.h:25-36)
+//   CUDAMorphologicalFilter  : VideoFilterDevice   peer of SWMorphologicalFilter (reference include/filter/mf-sw.h:16-21)
+//
+// Same constructor argument lists, same virtuals, same return conventions, so Estimator
+// (estimator.cpp:45,54-56) needs no change: main.cpp:133-135 picks them with `new` exactly like the SW /
+// HW variants.  Inside the reference tree, define RTDM_REFERENCE_TREE before including this file and the
+// reference's own "stereo-matcher/stereo-matcher.h" / "filter/filter.h" ABCs are used; stand-alone (tests)
+// the identical ABCs below are used.
+//
+// Differences from the SW plugins, by design: compute() runs on the GPU and returns -1 (after printing
+// the library's error text, the HW plugins' convention, generic-hw-filter-ip.cpp:130-135) instead of
+// throwing cv::Exception; constructors throw std::runtime_error when no device is usable (the FPGA
+// plugins call exit(1), bm-hw-ip.cpp:135-168).  There is no CPU fallback.
+#pragma once
+
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+
+#include "../../include/rtdm_b200.h"
+#include "cv_compat.h"
+
+#ifdef RTDM_REFERENCE_TREE
+#include "stereo-matcher/stereo-matcher.h"
+#include "filter/filter.h"
+#else
+// identical to the reference's ABCs (stereo-matcher.h:13-19, filter.h:13-37)
+class BlockMatcher {
+public:
+    virtual ~BlockMatcher() {}
+    virtual int compute(cv::InputArray left, cv::InputArray right, cv::OutputArray out) = 0;
+    virtual void setROI1(cv::Rect roi1) = 0;
+    virtual void setROI2(cv::Rect roi2) = 0;
+};
+
+class VideoFilterDevice {
+public:
+    virtual ~VideoFilterDevice() {}
+    int getFrameSize() const { return img_width * img_height * (img_bpp >> 3); }
+    int getBpp() const { return img_bpp; }
+    void setBpp(int bpp) { img_bpp = bpp; }
+    int getWidth() const { return img_width; }
+    void setWidth(int v) { img_width = v; }
+    int getHeight() const { return img_height; }
+    void setHeight(int v) { img_height = v; }
+    char *getVideoInBuffer() { return video_in; }
+    char *getVideoOutBuffer() { return video_out; }
+    virtual int run(cv::InputArray in, cv::OutputArray out) = 0;
+protected:
+    int img_width = 0, img_height = 0, img_bpp = 0;
+    char *video_in = nullptr;
+    char *video_out = nullptr;
+    const char *dev_name = nullptr;
+    int dev_minor = 0;
+};
+#endif
+
+namespace rtdm_detail {
+inline void fail(const char *what, int rc)
+{
+    throw std::runtime_error(std::string(what) + ": rtdm error " + std::to_string(rc) + ": " + rtdm_last_error());
+}
+}  // namespace rtdm_detail
+
+class CUDAMatcherKonolige : public BlockMatcher {
+public:
+    // same arguments as SWMatcherKonolige (bm-sw.h:28-30); roi1, roi2 and maxDisparity are accepted and
+    // unused exactly as in the reference (bm-sw.cpp:12-14 vs :16-25).  max_width/max_height bound the frames.
+    CUDAMatcherKonolige(cv::Rect &roi1, cv::Rect &roi2, int preFilterCap, int blockSize, int minDisparity,
+                        int textureThreshold, int numOfDisparities, int maxDisparity, int uniquenessRatio,
+                        int speckleWindowSize, int speckleRange, int disp12MaxDiff,
+                        int max_width = 1280, int max_height = 720, int device = 0)
+    {
+        (void)roi1; (void)roi2; (void)maxDisparity;
+        rtdm_params p;
+        rtdm_params_default_bm(&p);
+        p.preFilterCap = preFilterCap; p.blockSize = blockSize; p.minDisparity = minDisparity;
+        p.textureThreshold = textureThreshold; p.numDisparities = numOfDisparities;
+        p.uniquenessRatio = uniquenessRatio; p.speckleWindowSize = speckleWindowSize;
+        p.speckleRange = speckleRange; p.disp12MaxDiff = disp12MaxDiff;
+        int rc = rtdm_bm_create(&h_, &p, max_width, max_height, 1, device);
+        if (rc) rtdm_detail::fail("CUDAMatcherKonolige", rc);
+    }
+    ~CUDAMatcherKonolige() { rtdm_bm_destroy(h_); }
+    void setROI1(cv::Rect r) override { rtdm_bm_set_roi1(h_, r.x, r.y, r.width, r.height); }
+    void setROI2(cv::Rect r) override { rtdm_bm_set_roi2(h_, r.x, r.y, r.width, r.height); }
+    int compute(cv::InputArray left, cv::InputArray right, cv::OutputArray out) override
+    {
+        const cv::Mat l = left.getMat(), r = right.getMat();
+        out.create(l.rows, l.cols, CV_16SC1);
+        cv::Mat d = out.getMat();
+        int rc = rtdm_bm_compute(h_, l.data, l.step, r.data, r.step, l.cols, l.rows, (int16_t *)d.data, d.step);
+        if (rc) { std::fprintf(stderr, "CUDAMatcherKonolige::compute: %s\n", rtdm_last_error()); return -1; }
+        return 0;
+    }
+private:
+    rtdm_bm *h_ = nullptr;
+};
+
+class CUDASemiGlobalMatcher : public BlockMatcher {
+public:
+    // same arguments as SWSemiGlobalMatcher (sgbm-sw.h:28-29); P1 = 8*3*5*5, P2 = 32*3*5*5 as in
+    // sgbm-sw.cpp:17-18.  `mode` keeps the reference's default MODE_SGBM; RTDM_SGBM_MODE_HH selects 8 paths.
+    CUDASemiGlobalMatcher(int blockSize, int minDisparity, int numOfDisparities, int uniquenessRatio,
+                          int speckleWindowSize, int speckleRange, int disp12MaxDiff,
+                          int mode = RTDM_SGBM_MODE_SGBM, int max_width = 1280, int max_height = 720, int device = 0)
+    {
+        rtdm_params p;
+        rtdm_params_default_sgbm(&p);
+        p.blockSize = blockSize; p.minDisparity = minDisparity; p.numDisparities = numOfDisparities;
+        p.uniquenessRatio = uniquenessRatio; p.speckleWindowSize = speckleWindowSize;
+        p.speckleRange = speckleRange; p.disp12MaxDiff = disp12MaxDiff; p.mode = mode;
+        int rc = rtdm_sgbm_create(&h_, &p, max_width, max_height, 1, device);
+        if (rc) rtdm_detail::fail("CUDASemiGlobalMatcher", rc);
+    }
+    ~CUDASemiGlobalMatcher() { rtdm_sgbm_destroy(h_); }
+    void setROI1(cv::Rect) override {}       // no-ops like the reference (sgbm-sw.h:32-33)
+    void setROI2(cv::Rect) override {}
+    int compute(cv::InputArray left, cv::InputArray right, cv::OutputArray out) override
+    {
+        const cv::Mat l = left.getMat(), r = right.getMat();
+        out.create(l.rows, l.cols, CV_16SC1);
+        cv::Mat d = out.getMat();
+        int rc = rtdm_sgbm_compute(h_, l.data, l.step, r.data, r.step, l.cols, l.rows, (int16_t *)d.data, d.step);
+        if (rc) { std::fprintf(stderr, "CUDASemiGlobalMatcher::compute: %s\n", rtdm_last_error()); return -1; }
+        return 0;
+    }
+private:
+    rtdm_sgbm *h_ = nullptr;
+};
+
+class CUDAMorphologicalFilter : public VideoFilterDevice {
+public:
+    // same arguments as SWMorphologicalFilter(w, h, bpp) (mf-sw.cpp:10-17).  video_in / video_out are the
+    // handle's PINNED host buffers: Estimator writes the inRange() mask into video_in (estimator.cpp:43)
+    // and wraps both in cv::Mat headers (estimator.cpp:141-142), so the copies to/from the GPU are DMA.
+    explicit CUDAMorphologicalFilter(int w, int h, int bpp, int device = 0)
+    {
+        int rc = rtdm_morph_create(&h_, w, h, bpp, 1, device);
+        if (rc) rtdm_detail::fail("CUDAMorphologicalFilter", rc);
+        img_width = w; img_height = h; img_bpp = bpp;
+        video_in = (char *)rtdm_morph_in_buffer(h_);
+        video_out = (char *)rtdm_morph_out_buffer(h_);
+    }
+    ~CUDAMorphologicalFilter() { rtdm_morph_destroy(h_); }
+    // erode, dilate, dilate, erode with the 10x10 ellipse (mf-sw.cpp:22-27).  Returns 0 (the reference's
+    // run() has no return statement, mf-sw.cpp:19-28), -1 on failure like the HW filter.
+    int run(cv::InputArray in, cv::OutputArray out) override
+    {
+        const cv::Mat i = in.getMat();
+        out.create(i.rows, i.cols, CV_8UC1);
+        cv::Mat o = out.getMat();
+        if (i.cols != img_width || i.rows != img_height || i.step != (size_t)img_width || o.step != (size_t)img_width) {
+            std::fprintf(stderr, "CUDAMorphologicalFilter::run: frames must be %dx%d, tightly packed\n", img_width, img_height);
+            return -1;
+        }
+        int rc = rtdm_morph_run(h_, i.data, o.data);
+        if (rc) { std::fprintf(stderr, "CUDAMorphologicalFilter::run: %s\n", rtdm_last_error()); return -1; }
+        return 0;
+    }
+private:
+    rtdm_morph *h_ = nullptr;
+};

@@ -1,0 +1,91 @@
+// Drives the C++ plugin peers the way Estimator does (estimator.cpp:45,54-56,141-142).
+//   host_adapter_main probe                      -> prints "nodevice" (exit 3) or "ok" (exit 0)
+//   host_adapter_main bm   W H nd bs left right out [rx ry rw rh]
+//   host_adapter_main sgbm W H nd bs left right out mode
+//   host_adapter_main morph W H in out
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "rtdm_plugins.h"
+
+static std::vector<unsigned char> slurp(const char *path, size_t n)
+{
+    std::vector<unsigned char> b(n);
+    FILE *f = std::fopen(path, "rb");
+    if (!f || std::fread(b.data(), 1, n, f) != n) { std::fprintf(stderr, "cannot read %s\n", path); std::exit(2); }
+    std::fclose(f);
+    return b;
+}
+
+static void dump(const char *path, const void *p, size_t n)
+{
+    FILE *f = std::fopen(path, "wb");
+    if (!f || std::fwrite(p, 1, n, f) != n) { std::fprintf(stderr, "cannot write %s\n", path); std::exit(2); }
+    std::fclose(f);
+}
+
+int main(int argc, char **argv)
+{
+    if (argc < 2) return 2;
+    try {
+        if (!std::strcmp(argv[1], "probe")) {
+            cv::Rect r;
+            CUDAMatcherKonolige m(r, r, 31, 13, 0, 10, 128, 128, 10, 100, 32, 1);
+            std::puts("ok");
+            return 0;
+        }
+        if (!std::strcmp(argv[1], "bm") && argc >= 9) {
+            int W = atoi(argv[2]), H = atoi(argv[3]), nd = atoi(argv[4]), bs = atoi(argv[5]);
+            // a frame embedded in a wider buffer: the matcher sees a non-contiguous ROI view (estimator.cpp:33,36)
+            const int PAD = 24;
+            std::vector<unsigned char> l = slurp(argv[6], (size_t)W * H), r = slurp(argv[7], (size_t)W * H);
+            cv::Mat lf(H, W + PAD, CV_8UC1), rf(H, W + PAD, CV_8UC1);
+            for (int y = 0; y < H; y++) {
+                std::memcpy(lf.ptr<unsigned char>(y) + 8, &l[(size_t)y * W], W);
+                std::memcpy(rf.ptr<unsigned char>(y) + 8, &r[(size_t)y * W], W);
+            }
+            cv::Mat lv = lf(cv::Rect(8, 0, W, H)), rv = rf(cv::Rect(8, 0, W, H));
+            cv::Rect roi;
+            BlockMatcher *bm = new CUDAMatcherKonolige(roi, roi, 31, bs, 0, 10, nd, nd, 10, 100, 32, 1, W, H);
+            if (argc >= 13) bm->setROI1(cv::Rect(atoi(argv[9]), atoi(argv[10]), atoi(argv[11]), atoi(argv[12])));
+            cv::Mat disp;
+            if (bm->compute(lv, rv, disp) != 0) return 4;
+            if (bm->compute(lv, rv, disp) != 0) return 4;      // reused output Mat, second frame
+            std::vector<short> out((size_t)W * H);
+            for (int y = 0; y < H; y++) std::memcpy(&out[(size_t)y * W], disp.ptr<short>(y), (size_t)W * 2);
+            dump(argv[8], out.data(), out.size() * 2);
+            delete bm;
+            return 0;
+        }
+        if (!std::strcmp(argv[1], "sgbm") && argc >= 10) {
+            int W = atoi(argv[2]), H = atoi(argv[3]), nd = atoi(argv[4]), bs = atoi(argv[5]), mode = atoi(argv[9]);
+            std::vector<unsigned char> l = slurp(argv[6], (size_t)W * H), r = slurp(argv[7], (size_t)W * H);
+            cv::Mat lm(H, W, CV_8UC1, l.data()), rm(H, W, CV_8UC1, r.data()), disp;
+            BlockMatcher *bm = new CUDASemiGlobalMatcher(bs, 0, nd, 10, 100, 32, 1, mode, W, H);
+            bm->setROI1(cv::Rect(1, 2, 3, 4));
+            if (bm->compute(lm, rm, disp) != 0) return 4;
+            dump(argv[8], disp.data, (size_t)W * H * 2);
+            delete bm;
+            return 0;
+        }
+        if (!std::strcmp(argv[1], "morph") && argc >= 6) {
+            int W = atoi(argv[2]), H = atoi(argv[3]);
+            std::vector<unsigned char> in = slurp(argv[4], (size_t)W * H);
+            VideoFilterDevice *f = new CUDAMorphologicalFilter(W, H, 8);
+            if (f->getFrameSize() != W * H || f->getWidth() != W || f->getHeight() != H || f->getBpp() != 8) return 5;
+            // Estimator wraps the plugin-owned buffers in Mats and writes the mask into the input buffer
+            cv::Mat fin(H, W, CV_8UC1, f->getVideoInBuffer()), fout(H, W, CV_8UC1, f->getVideoOutBuffer());
+            std::memcpy(fin.data, in.data(), in.size());
+            if (f->run(fin, fout) != 0) return 4;
+            dump(argv[5], fout.data, (size_t)W * H);
+            delete f;
+            return 0;
+        }
+    } catch (const std::exception &e) {
+        std::printf("nodevice: %s\n", e.what());
+        return 3;
+    }
+    return 2;
+}

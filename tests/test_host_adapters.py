@@ -1,0 +1,51 @@
+"""The C++ plugin peers (rt-depth-map_b200/host/rtdm_plugins.h) compiled with g++ against the C ABI
+and driven like Estimator drives the reference plugins."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+PKG = os.path.join(ROOT, "rt-depth-map_b200")
+EXE = os.path.join(PKG, "build", "host_adapter_main")
+
+
+@pytest.fixture(scope="module")
+def exe():
+    os.makedirs(os.path.dirname(EXE), exist_ok=True)
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-I", os.path.join(PKG, "host"),
+                           os.path.join(ROOT, "tests", "cpp", "host_adapter_main.cpp"), "-o", EXE,
+                           "-L", PKG, "-lrtdm_b200", "-Wl,-rpath," + PKG])
+    return EXE
+
+
+def test_adapters_compile_and_fail_loudly_without_device(exe, rt):
+    r = subprocess.run([exe, "probe"], capture_output=True, text=True)
+    if rt.device_count() == 0:
+        assert r.returncode == 3 and "nodevice" in r.stdout and "no CUDA device" in r.stdout
+    else:
+        assert r.returncode == 0 and "ok" in r.stdout
+
+
+@pytest.mark.gpu
+def test_adapters_match_oracle(exe, gpu, orc, tmp_path):
+    from rtdm_b200 import synth
+    W, H, nd, bs = 320, 240, 64, 13
+    L, R, _ = synth.stereo_pair(W, H, nd, 1234)
+    lp, rp, op = (str(tmp_path / n) for n in ("l.raw", "r.raw", "o.raw"))
+    L.tofile(lp); R.tofile(rp)
+    roi = (40, 30, 240, 180)
+    subprocess.check_call([exe, "bm", str(W), str(H), str(nd), str(bs), lp, rp, op] + [str(v) for v in roi])
+    got = np.fromfile(op, np.int16).reshape(H, W)
+    ref = orc.bm_compute(L, R, orc.make_params(blockSize=bs, numDisparities=nd, roi1=roi))
+    assert np.array_equal(got, ref)
+    for mode in (0, 1):
+        subprocess.check_call([exe, "sgbm", str(W), str(H), str(nd), "5", lp, rp, op, str(mode)])
+        got = np.fromfile(op, np.int16).reshape(H, W)
+        assert np.array_equal(got, orc.sgbm_compute(L, R, orc.sgbm_params(numDisparities=nd, mode=mode)))
+    m = synth.binary_mask(W, H, 99)
+    mp = str(tmp_path / "m.raw"); m.tofile(mp)
+    subprocess.check_call([exe, "morph", str(W), str(H), mp, op])
+    assert np.array_equal(np.fromfile(op, np.uint8).reshape(H, W), orc.morph_open_close(m))
