@@ -101,6 +101,9 @@ int rtdm_bm_compute_device(rtdm_bm *h, int n, const uint8_t *left, size_t lstep,
                            int16_t *disp, size_t dstep, size_t dframe, void *cuda_stream);
 /* number of kernel launches issued by the last compute call on this handle */
 int rtdm_bm_last_launches(const rtdm_bm *h);
+/* which SAD/WTA kernel the last compute call used: 1 = generic (bm_sad.cu), 2 = fast path (bm_sad2.cu:
+ * minDisparity 0, blockSize 5..15).  The environment variable RTDM_BM_KERNEL=1 forces the generic one. */
+int rtdm_bm_last_kernel(const rtdm_bm *h);
 /* Per-stage device timing with CUDA events recorded on the launching stream (used by bench.py for
  * the roofline of the dominant kernel).  While enabled every compute call records 5 events.
  * rtdm_bm_stage_times synchronises, sums the elapsed milliseconds of all recorded calls per stage

@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -86,11 +87,13 @@ struct rtdm_bm {
     uint8_t *Lp, *Rp;            size_t ppitch, pframe;      // prefiltered planes (bytes)
     int16_t *raw, *cost;         size_t rpitch, rframe;      // raw WTA disparity + cost (elements)
     int32_t *labels, *sizes;
+    uint16_t *tex;                                           // texture window sums (rpitch / rframe)
     // staging for the host entry points
     uint8_t *dL, *dR;            size_t spitch, sframe;      // device copies of the inputs
     int16_t *dD;                 size_t dpitch, dframe;      // device copy of the output (elements)
     int launches;
     int lastW, lastH;
+    int last_kernel;             // 1 = generic bm_sad.cu kernel, 2 = fast bm_sad2.cu kernel
     // optional per-stage CUDA-event timing (rtdm_bm_set_profiling)
     int prof;
     std::vector<cudaEvent_t> *ev;     // 5 events per profiled call: before prefilter, after each stage
@@ -150,7 +153,7 @@ extern "C" void rtdm_bm_destroy(rtdm_bm *h)
     if (!h) return;
     cudaSetDevice(h->dev);
     cudaFree(h->Lp); cudaFree(h->Rp); cudaFree(h->raw); cudaFree(h->cost);
-    cudaFree(h->labels); cudaFree(h->sizes); cudaFree(h->dL); cudaFree(h->dR); cudaFree(h->dD);
+    cudaFree(h->labels); cudaFree(h->sizes); cudaFree(h->dL); cudaFree(h->dR); cudaFree(h->dD); cudaFree(h->tex);
     if (h->ev) { for (cudaEvent_t e : *h->ev) cudaEventDestroy(e); delete h->ev; }
     if (h->st) cudaStreamDestroy(h->st);
     for (int i = 0; i < 3; i++) if (h->lane[i]) cudaStreamDestroy(h->lane[i]);
@@ -188,6 +191,7 @@ extern "C" int rtdm_bm_create(rtdm_bm **out, const rtdm_params *p, int max_width
     if (!rc) rc = dev_alloc(&h->Rp, h->pframe * B + 4096);
     if (!rc) rc = dev_alloc(&h->raw, h->rframe * B);
     if (!rc) rc = dev_alloc(&h->cost, h->rframe * B);
+    if (!rc) rc = dev_alloc(&h->tex, h->rframe * B);
     if (!rc) rc = dev_alloc(&h->labels, (size_t)max_width * max_height * B);
     if (!rc) rc = dev_alloc(&h->sizes, (size_t)max_width * max_height * B);
     if (!rc) rc = dev_alloc(&h->dL, h->sframe * B);
@@ -255,7 +259,14 @@ static int bm_pipeline(rtdm_bm *h, int n, PlaneU8 L, PlaneU8 R, int W, int H, Pl
         if (rc) return rc;
         mark();
         PlaneU8 iL = {wLp, h->ppitch, h->pframe}, iR = {wRp, h->ppitch, h->pframe};
-        rc = launch_bm_sad_wta(g, n, iL, iR, raw, cost, st, &h->launches);
+        // RTDM_BM_KERNEL=1 forces the generic kernel (A/B runs and tests); default: fast path when it applies
+        const char *force = getenv("RTDM_BM_KERNEL");
+        const bool fast = !(force && force[0] == '1') && bm_sad2_supported(g, n);
+        if (fast)
+            rc = launch_bm_sad2(g, n, iL, iR, raw, cost, h->tex + (size_t)f0 * h->rframe, h->rpitch, h->rframe, st, &h->launches);
+        else
+            rc = launch_bm_sad_wta(g, n, iL, iR, raw, cost, st, &h->launches);
+        h->last_kernel = fast ? 2 : 1;
         if (rc) return rc;
         mark();
     } else { mark(); mark(); }
@@ -360,6 +371,7 @@ extern "C" int rtdm_bm_compute(rtdm_bm *h, const uint8_t *left, size_t lstep, co
 }
 
 extern "C" int rtdm_bm_last_launches(const rtdm_bm *h) { return h ? h->launches : 0; }
+extern "C" int rtdm_bm_last_kernel(const rtdm_bm *h) { return h ? h->last_kernel : 0; }
 
 extern "C" int rtdm_bm_debug_fetch(rtdm_bm *h, int what, void *dst, size_t dst_bytes)
 {
@@ -754,4 +766,14 @@ extern "C" int rtdm_measure_int_peak(int device, double *tiops_iadd3, double *ti
     int rc = check_device(device);
     if (rc) return rc;
     return measure_int_peak(device, tiops_iadd3, tiops_vimnmx, tiops_vabsdiff4, sm_mhz_est);
+}
+
+namespace rtdm { int measure_op_rates(int device, double *out, int n); }
+// development aid (not part of the plugin boundary): statement rates of 15 integer idioms, in 1e12
+// statements/s over the chip (a statement may be 1 or 2 SASS instructions, see intpeak.cu)
+extern "C" int rtdm_dev_op_rates(int device, double *out, int n)
+{
+    int rc = check_device(device);
+    if (rc) return rc;
+    return rtdm::measure_op_rates(device, out, n);
 }

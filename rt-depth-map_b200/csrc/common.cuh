@@ -44,6 +44,11 @@ size_t bm_sad_smem_bytes(const BmGeom &g, int TW, int BH);
 int launch_bm_sad_wta(const BmGeom &g, int n, PlaneU8 Lp, PlaneU8 Rp, PlaneS16 disp, PlaneS16 cost,
                       cudaStream_t st, int *launches);
 
+// fast path (bm_sad2.cu): minDisparity == 0, blockSize 5..15; tex = n * tex_frame uint16 scratch
+bool bm_sad2_supported(const BmGeom &g, int n);
+int launch_bm_sad2(const BmGeom &g, int n, PlaneU8 Lp, PlaneU8 Rp, PlaneS16 disp, PlaneS16 cost,
+                   uint16_t *tex, size_t tex_pitch, size_t tex_frame, cudaStream_t st, int *launches);
+
 // ---- post-processing (postproc.cu) -------------------------------------------------------------
 // validateDisparity (if d12 >= 0) + valid-rect mask; reads raw disp/cost, writes `out`
 int launch_validate_mask(int n, int W, int H, int minD, int nd, int d12, int lofs, int W1,

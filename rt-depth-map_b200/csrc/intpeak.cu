@@ -21,7 +21,19 @@ intpeak_kernel(uint32_t *out, int iters, uint32_t seed)
             for (int i = 0; i < 8; i++) {
                 if (OP == 0) a[i] = a[i] + b + c;                        // IADD3
                 else if (OP == 1) a[i] = __vminu2(a[i] + 0u, b) ^ c;     // VIMNMX.U16x2 (+ LOP3 to keep it live)
-                else a[i] = __vabsdiffu4(a[i], b) + c;                   // VABSDIFF4 (+ IADD)
+                else if (OP == 2) a[i] = __vabsdiffu4(a[i], b) + c;      // VABSDIFF4 (+ IADD)
+                else if (OP == 3) a[i] = __byte_perm(a[i], b, 0x5140);   // PRMT
+                else if (OP == 4) a[i] = __funnelshift_r(a[i], b, 8);    // SHF
+                else if (OP == 5) a[i] = __vadd2(a[i], b);               // VIADD.16x2
+                else if (OP == 6) a[i] = a[i] * 3u + b;                  // IMAD
+                else if (OP == 7) a[i] = __vimin3_u16x2(a[i], b, c);     // VIMNMX3.U16x2
+                else if (OP == 8) a[i] = min(a[i], b);                   // VIMNMX.U32
+                else if (OP == 9) a[i] = (a[i] & b) ^ c;                 // LOP3
+                else if (OP == 10) a[i] = __vimin3_u32(a[i], b, c);      // VIMNMX3.U32
+                else if (OP == 11) a[i] = __vminu2(a[i], b);             // VIMNMX.U16x2 alone
+                else if (OP == 12) a[i] = __vabsdiffu4(a[i], b);         // VABSDIFF4 alone
+                else if (OP == 13) a[i] = __vsub2(a[i], b);              // VIADD.16x2 (sub)
+                else a[i] = __viaddmin_s16x2(a[i], b, c);                // VIADDMNMX.S16x2
             }
             b += 0x00010001u;
         }
@@ -55,6 +67,37 @@ int run_one(uint32_t *buf, int blocks, int iters, double ops_per_inner, double *
     return 0;
 }
 }  // namespace
+
+int measure_op_rates(int device, double *out, int n)
+{
+    RTDM_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    RTDM_CUDA(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 8;
+    uint32_t *buf = nullptr;
+    RTDM_CUDA(cudaMalloc(&buf, (size_t)blocks * 256 * sizeof(uint32_t)));
+    const int iters = 2048;
+    double v[15] = {0};
+    int rc = 0;
+    if (!rc) rc = run_one<0>(buf, blocks, iters, 1.0, &v[0]);
+    if (!rc) rc = run_one<1>(buf, blocks, iters, 1.0, &v[1]);
+    if (!rc) rc = run_one<2>(buf, blocks, iters, 1.0, &v[2]);
+    if (!rc) rc = run_one<3>(buf, blocks, iters, 1.0, &v[3]);
+    if (!rc) rc = run_one<4>(buf, blocks, iters, 1.0, &v[4]);
+    if (!rc) rc = run_one<5>(buf, blocks, iters, 1.0, &v[5]);
+    if (!rc) rc = run_one<6>(buf, blocks, iters, 1.0, &v[6]);
+    if (!rc) rc = run_one<7>(buf, blocks, iters, 1.0, &v[7]);
+    if (!rc) rc = run_one<8>(buf, blocks, iters, 1.0, &v[8]);
+    if (!rc) rc = run_one<9>(buf, blocks, iters, 1.0, &v[9]);
+    if (!rc) rc = run_one<10>(buf, blocks, iters, 1.0, &v[10]);
+    if (!rc) rc = run_one<11>(buf, blocks, iters, 1.0, &v[11]);
+    if (!rc) rc = run_one<12>(buf, blocks, iters, 1.0, &v[12]);
+    if (!rc) rc = run_one<13>(buf, blocks, iters, 1.0, &v[13]);
+    if (!rc) rc = run_one<14>(buf, blocks, iters, 1.0, &v[14]);
+    cudaFree(buf);
+    for (int i = 0; i < n && i < 15; i++) out[i] = v[i];
+    return rc;
+}
 
 int measure_int_peak(int device, double *iadd3, double *vimnmx, double *vabsdiff4, double *mhz)
 {

@@ -59,6 +59,7 @@ SIGNATURES = {
     "rtdm_bm_compute_device": (_i, [_vp, _i, _vp, _sz, _sz, _vp, _sz, _sz, _i, _i, _vp, _sz, _sz, _vp]),
     "rtdm_bm_last_launches": (_i, [_vp]),
     "rtdm_bm_debug_fetch": (_i, [_vp, _i, _vp, _sz]),
+    "rtdm_bm_last_kernel": (_i, [_vp]),
     "rtdm_bm_set_profiling": (_i, [_vp, _i]),
     "rtdm_bm_stage_times": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(_i)]),
     "rtdm_sgbm_create": (_i, [C.POINTER(_vp), C.POINTER(RtdmParams), _i, _i, _i, _i]),
@@ -227,6 +228,9 @@ class CUDAMatcherKonolige(_MatcherBase):
         calls = _i()
         _check(self._l.rtdm_bm_stage_times(self._h, ms, C.byref(calls)))
         return dict(zip(self.STAGES, list(ms))), calls.value
+
+    def last_kernel(self) -> int:
+        return self._l.rtdm_bm_last_kernel(self._h)
 
     def debug_fetch(self, what: int, width: int, height: int):
         dt = np.uint8 if what in (0, 1) else np.int16

@@ -10,6 +10,17 @@ from conftest import golden_names, load_golden
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=["fast", "generic"])
+def bm_kernel(request, monkeypatch):
+    """Runs a test once per SAD/WTA kernel: the fast path (bm_sad2.cu, where it applies) and the generic
+    kernel (bm_sad.cu, forced through RTDM_BM_KERNEL=1)."""
+    if request.param == "generic":
+        monkeypatch.setenv("RTDM_BM_KERNEL", "1")
+    else:
+        monkeypatch.delenv("RTDM_BM_KERNEL", raising=False)
+    return request.param
+
+
 def _mk(rt, p, W, H, **kw):
     m = rt.CUDAMatcherKonolige(None, None, p["preFilterCap"], p["blockSize"], p["minDisparity"],
                                p["textureThreshold"], p["numDisparities"], p["numDisparities"],
@@ -36,18 +47,22 @@ def _orc_params(orc, p):
 
 
 @pytest.mark.parametrize("name", golden_names("bm_"))
-def test_bm_matches_cv2_golden(gpu, name):
+def test_bm_matches_cv2_golden(gpu, name, bm_kernel):
     g = load_golden(name)
     p = json.loads(str(g["params"]))
     H, W = g["left"].shape
     m = _mk(gpu, p, W, H)
     got = m.compute(g["left"], g["right"])
     assert got.dtype == np.int16 and got.shape == (H, W)
-    assert np.array_equal(got, g["disp"]), f"{name}: {(got != g['disp']).sum()} pixels differ"
+    assert np.array_equal(got, g["disp"]), f"{name} [{bm_kernel}]: {(got != g['disp']).sum()} pixels differ"
     assert m.last_launches() > 0
+    if bm_kernel == "generic":
+        assert m.last_kernel() == 1
+    elif p["blockSize"] <= 15 and p["minDisparity"] == 0:
+        assert m.last_kernel() == 2, "the fast path should cover blockSize 5..15 with minDisparity 0"
 
 
-def test_bm_stages_match_oracle(gpu, orc):
+def test_bm_stages_match_oracle(gpu, orc, bm_kernel):
     """Intermediates: prefiltered images, raw WTA disparity and cost."""
     from rtdm_b200 import synth
     W, H, nd, bs, cap = 320, 240, 64, 15, 31
@@ -68,7 +83,7 @@ def test_bm_stages_match_oracle(gpu, orc):
     assert np.array_equal(gc[h:H - h, lofs:][valid], rc[h:H - h, lofs:][valid])
 
 
-def test_bm_random_params_match_oracle(gpu, orc):
+def test_bm_random_params_match_oracle(gpu, orc, bm_kernel):
     from rtdm_b200 import synth
     rng = np.random.default_rng(11)
     checked = 0
@@ -101,7 +116,7 @@ def test_bm_degenerate_width(gpu, orc):
     assert (got == -16).all()
 
 
-def test_bm_strided_roi_views(gpu, orc):
+def test_bm_strided_roi_views(gpu, orc, bm_kernel):
     """Estimator feeds non-contiguous ROI views (estimator.cpp:33,36): row step = full image width."""
     from rtdm_b200 import synth
     Lf, Rf, _ = synth.stereo_pair(400, 300, 64, 21)
@@ -114,7 +129,7 @@ def test_bm_strided_roi_views(gpu, orc):
     assert np.array_equal(got, ref)
 
 
-def test_bm_set_roi_per_frame(gpu, orc):
+def test_bm_set_roi_per_frame(gpu, orc, bm_kernel):
     """setROI1 is called every frame (estimator.cpp:54); ROI only changes the valid rectangle."""
     from rtdm_b200 import synth
     L, R, _ = synth.stereo_pair(320, 240, 64, 31)
@@ -127,7 +142,7 @@ def test_bm_set_roi_per_frame(gpu, orc):
         assert np.array_equal(m.compute(L, R), orc.bm_compute(L, R, _orc_params(orc, q))), roi
 
 
-def test_bm_720p_full_size_and_batch(gpu, orc):
+def test_bm_720p_full_size_and_batch(gpu, orc, bm_kernel):
     """BASELINE config 2 size: 1280x720, nd=128, reference parameters; batched call == per-frame."""
     from rtdm_b200 import synth
     p = dict(preFilterCap=31, blockSize=13, minDisparity=0, textureThreshold=10, numDisparities=128,
