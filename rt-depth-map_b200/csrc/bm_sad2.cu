@@ -23,11 +23,11 @@
 // The cost volume never leaves the SM; HBM traffic is the two prefiltered images in and disparity + cost out.
 #include "common.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 namespace rtdm {
 namespace {
 
-constexpr int NT2 = 192;          // threads per CTA
 // rows in the shared-memory ring: rows y-h-1 .. y+h are live while row y+h+1 is prefetched -> 2h + 3
 __host__ __device__ constexpr int ring_rows(int h) { return 2 * h + 3 <= 16 ? 16 : 32; }
 
@@ -41,98 +41,64 @@ struct Bm2Args {
     int W1, row0, row1;
     int TW, BH, NO, NGT;         // stripe width, band height, octets, thread groups
     int LVP, RVP, PP;            // smem pitches (bytes): Lv row copy, Rv row copy, Pre/Suf column
+    int dbg;                     // timing experiments only: 1 = skip consumer, 2 = skip producer, 4 = skip loader
 };
 
 // ------------------------------------------------------------------------------------------------
 // texture: T(x, y) = sum over the (2h+1)^2 window of |L'[y+j][lcol(x+i)] - cap|, x in [0, W1)
 // ------------------------------------------------------------------------------------------------
-constexpr int TXW = 64, TXH = 32;
-__global__ void __launch_bounds__(256)
+constexpr int TXW = 128, TXH = 64, TXT = 160;      // output columns / rows per CTA, threads (>= TXW + 2h)
+__global__ void __launch_bounds__(TXT)
 bm_texture_kernel(PlaneU8 Lp, uint16_t *tex, size_t tex_pitch, size_t tex_frame, int W, int H, int nd,
                   int cap, int h, int W1, int row0, int row1)
 {
-    extern __shared__ uint16_t tx_s[];
-    const int f = blockIdx.z;
-    const int x0 = blockIdx.x * TXW, y0 = row0 + blockIdx.y * TXH;
-    const int NCc = TXW + 2 * h, NRr = TXH + 2 * h;
-    uint16_t *a = tx_s;                     // [NRr][NCc] |L' - cap|
-    uint16_t *v = a + NRr * NCc;            // [TXH][NCc] vertical sums
-    const uint8_t *L = Lp.p + (size_t)f * Lp.frame;
+    __shared__ int colsum[2][TXT];
+    const int f = blockIdx.z, c = threadIdx.x;
+    const int x0 = blockIdx.x * TXW, y0 = row0 + blockIdx.y * TXH, y1 = min(y0 + TXH, row1);
+    if (y0 >= y1) return;
     const int lofs = nd - 1;
-    for (int i = threadIdx.x; i < NRr * NCc; i += blockDim.x) {
-        int r = i / NCc, c = i - r * NCc;
-        int gy = clampi(y0 - h + r, 0, H - 1);
-        int lc = clampi(x0 - h + c, -lofs, W - lofs - 1) + lofs;
-        a[i] = (uint16_t)abs((int)L[(size_t)gy * Lp.pitch + lc] - cap);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < TXH * NCc; i += blockDim.x) {
-        int r = i / NCc, c = i - r * NCc;
-        int s = 0;
-        for (int j = 0; j <= 2 * h; j++) s += a[(r + j) * NCc + c];
-        v[i] = (uint16_t)s;
-    }
-    __syncthreads();
+    const bool colok = c < TXW + 2 * h;
+    const int lc = clampi(x0 - h + c, -lofs, W - lofs - 1) + lofs;
+    const uint8_t *L = Lp.p + (size_t)f * Lp.frame + lc;
+    // vertical window sum of |L' - cap| for this (virtual) column, sliding down the rows
+    int v = 0;
+    if (colok)
+        for (int r = y0 - h; r < y0 + h; r++) v += abs((int)L[(size_t)clampi(r, 0, H - 1) * Lp.pitch] - cap);
     uint16_t *out = tex + (size_t)f * tex_frame;
-    for (int i = threadIdx.x; i < TXH * TXW; i += blockDim.x) {
-        int r = i / TXW, c = i - r * TXW;
-        int gx = x0 + c, gy = y0 + r;
-        if (gx >= W1 || gy >= row1) continue;
-        int s = 0;
-        for (int k = 0; k <= 2 * h; k++) s += v[r * NCc + c + k];
-        out[(size_t)gy * tex_pitch + gx] = (uint16_t)s;
+    for (int y = y0; y < y1; y++) {
+        if (colok) {
+            v += abs((int)L[(size_t)clampi(y + h, 0, H - 1) * Lp.pitch] - cap);
+            if (y > y0) v -= abs((int)L[(size_t)clampi(y - h - 1, 0, H - 1) * Lp.pitch] - cap);
+        }
+        int *cs = colsum[(y - y0) & 1];             // double buffer: one barrier per row
+        cs[c] = v;
+        __syncthreads();
+        if (c < TXW && x0 + c < W1) {
+            int s = 0;
+            for (int k = 0; k <= 2 * h; k++) s += cs[c + k];
+            out[(size_t)y * tex_pitch + x0 + c] = (uint16_t)s;
+        }
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// producer: |L - R| of one row for CT adjacent columns x 8 disparities
+// one ring word of the loader: where it comes from in the prefiltered image row
 // ------------------------------------------------------------------------------------------------
-// Fast form: the thread's column range is interior, so column kk reads R bytes at (base + kk .. +7):
-// shared words + compile-time funnel shifts.
-template <int CT>
-__device__ __forceinline__ void ad_row_fast(const uint32_t *lw_p, const uint32_t *rw_p, uint32_t (&lo)[CT], uint32_t (&hi)[CT])
-{
-    constexpr int NLW = (CT + 3) / 4, NRW = (CT + 7 + 3) / 4 + 1;
-    uint32_t lw[NLW], rw[NRW];
-#pragma unroll
-    for (int i = 0; i < NLW; i++) lw[i] = lw_p[i];
-#pragma unroll
-    for (int i = 0; i < NRW; i++) rw[i] = rw_p[i];
-#pragma unroll
-    for (int kk = 0; kk < CT; kk++) {
-        const int w = kk >> 2, s = kk & 3;
-        const uint32_t l4 = __byte_perm(lw[w], 0, s == 0 ? 0x0000 : (s == 1 ? 0x1111 : (s == 2 ? 0x2222 : 0x3333)));
-        uint32_t r0, r1;
-        if (s == 0) { r0 = rw[w]; r1 = rw[w + 1]; }
-        else { r0 = __funnelshift_r(rw[w], rw[w + 1], 8 * s); r1 = __funnelshift_r(rw[w + 1], rw[w + 2], 8 * s); }
-        lo[kk] = __vabsdiffu4(l4, r0);
-        hi[kk] = __vabsdiffu4(l4, r1);
-    }
-}
+struct RingWord {
+    int dst;        // byte offset inside a ring slot (Lv area followed by Rv area), -1 = no word
+    int src;        // aligned byte offset inside the image row (left or right plane), -1 = clamped gather
+    int sh;         // funnel shift (bits) for the aligned pair, or first virtual column for a gather
+    int right;      // 1: right image, 0: left image
+};
 
-// Border form: per-column R offset (clamped columns read the R window of the nearest unclamped column)
-template <int CT>
-__device__ __forceinline__ void ad_row_border(const uint8_t *lrow, const uint8_t *rrow0, int c0, int j8, int cmin, int cmax,
-                                              uint32_t (&lo)[CT], uint32_t (&hi)[CT])
-{
-#pragma unroll
-    for (int kk = 0; kk < CT; kk++) {
-        const int c = c0 + kk;
-        const int b = clampi(c, cmin, cmax) + j8;               // byte offset in the unshifted Rv copy
-        const uint32_t *rw = reinterpret_cast<const uint32_t *>(rrow0) + (b >> 2);
-        const int sh = (b & 3) * 8;
-        const uint32_t r0 = __funnelshift_r(rw[0], rw[1], sh), r1 = __funnelshift_r(rw[1], rw[2], sh);
-        const uint32_t l4 = (uint32_t)lrow[c] * 0x01010101u;
-        lo[kk] = __vabsdiffu4(l4, r0);
-        hi[kk] = __vabsdiffu4(l4, r1);
-    }
-}
-
-template <int H_, int KT_>
-__global__ void __launch_bounds__(NT2, 2)
+// NT2 = threads per CTA; SUF_ = also store in-group suffix sums (2 x LDS.128 per octet in the consumer
+// instead of 3, at the price of twice the producer stores)
+template <int H_, int KT_, int NT2, bool SUF_>
+__global__ void __launch_bounds__(NT2, NT2 == 128 ? 3 : 2)
 bm_sad2_kernel(Bm2Args a)
 {
     constexpr int G = 2 * H_, CT = G * KT_, RING = ring_rows(H_);
+    constexpr int NLW = (CT + 3) / 4, NRW = ((CT - 1) >> 2) + 3;
     extern __shared__ __align__(16) uint8_t smem[];
     const int tid = threadIdx.x, f = blockIdx.z;
     const int nd = a.nd, NO = a.NO;
@@ -143,85 +109,146 @@ bm_sad2_kernel(Bm2Args a)
     const int NCT = a.NGT * CT;                        // virtual columns held by the producers
 
     // ---- shared memory carve-up ----------------------------------------------------------------
-    uint8_t *Pre = smem;                                          // [NCT][PP]
-    uint8_t *Suf = Pre + (size_t)NCT * a.PP;                      // [NCT][PP]
-    uint16_t *Smin = reinterpret_cast<uint16_t *>(Suf + (size_t)NCT * a.PP);   // [NO][NT2]
-    uint8_t *Lv = reinterpret_cast<uint8_t *>(Smin + (size_t)NO * NT2);        // [RING][2][LVP]
-    uint8_t *Rv = Lv + (size_t)RING * 2 * a.LVP;                               // [RING][2][RVP]
+    // Pre[buf][c][d]: in-group prefix sums of the vertical sums; column NCT is all zero
+    const size_t PBUF = (size_t)(NCT + 1) * a.PP;
+    uint8_t *Pre = smem;
+    uint8_t *Suf = smem + PBUF;                                                // only with SUF_
+    uint16_t *Smin = reinterpret_cast<uint16_t *>(smem + (SUF_ ? 2 : 1) * PBUF);   // [NO][NT2]
+    uint8_t *Ring = reinterpret_cast<uint8_t *>(Smin + (size_t)NO * NT2);      // [RING][2*LVP + 2*RVP]
+    const int SLOT = 2 * a.LVP + 2 * a.RVP;
 
     const uint8_t *Lg = a.Lp.p + (size_t)f * a.Lp.frame;
     const uint8_t *Rg = a.Rp.p + (size_t)f * a.Rp.frame;
     const int lofs = nd - 1;
 
-    // loader: image row gy -> ring slot (gy & (RING-1)); copy 1 is copy 0 shifted left by 2 bytes
-    auto load_row = [&](int gy) {
-        const int slot = gy & (RING - 1);
-        const int gyc = clampi(gy, 0, a.H - 1);
-        uint8_t *l0 = Lv + (size_t)slot * 2 * a.LVP, *r0 = Rv + (size_t)slot * 2 * a.RVP;
-        const uint8_t *lsrc = Lg + (size_t)gyc * a.Lp.pitch, *rsrc = Rg + (size_t)gyc * a.Rp.pitch;
+    // ---- loader descriptors: each thread owns up to 2 words of every ring row ---------------------
+    RingWord rw_desc[2];
+    {
         const int lwords = a.LVP / 4, rwords = a.RVP / 4;
-        for (int i = tid; i < 2 * lwords; i += NT2) {
-            const int cp = i >= lwords, w = cp ? i - lwords : i;
-            uint32_t v = 0;
+        const int total = 2 * lwords + 2 * rwords;
 #pragma unroll
-            for (int b = 0; b < 4; b++) {
-                const int c = 4 * w + b + 2 * cp;                                     // virtual column
-                const int lc = clampi(x0 - H_ + c, -lofs, a.W - lofs - 1) + lofs;
-                v |= (uint32_t)lsrc[lc] << (8 * b);
+        for (int q = 0; q < 2; q++) {
+            const int i = tid + q * NT2;
+            RingWord d; d.dst = -1; d.src = -1; d.sh = 0; d.right = 0;
+            if (i < total) {
+                d.dst = 4 * i;
+                if (i < 2 * lwords) {
+                    const int cpy = i >= lwords, w = cpy ? i - lwords : i;
+                    const int c = 4 * w + 2 * cpy;                     // first virtual column of the word
+                    const int xa = x0 - H_ + c;
+                    if (xa >= -lofs && xa + 3 <= a.W - lofs - 1) { const int g = xa + lofs; d.src = g & ~3; d.sh = (g & 3) * 8; }
+                    else d.sh = c;
+                } else {
+                    const int k = i - 2 * lwords;
+                    const int cpy = k >= rwords, w = cpy ? k - rwords : k;
+                    const int c = 4 * w + 2 * cpy;
+                    const int xa = x0 - H_ + c;
+                    d.right = 1;
+                    if (xa >= 0 && xa + 3 <= a.W - 1) { d.src = xa & ~3; d.sh = (xa & 3) * 8; }
+                    else d.sh = c;
+                }
             }
-            reinterpret_cast<uint32_t *>(l0 + (size_t)cp * a.LVP)[w] = v;
+            rw_desc[q] = d;
         }
-        for (int i = tid; i < 2 * rwords; i += NT2) {
-            const int cp = i >= rwords, w = cp ? i - rwords : i;
-            uint32_t v = 0;
+    }
+    // fetch (global -> registers) and commit (registers -> ring slot) of one image row
+    // fetch keeps the RAW aligned word pairs in registers (no use of the loaded values, so the loads stay in
+    // flight behind the producer work); commit funnel-shifts them into the ring slot
+    auto fetch_row = [&](int gy, uint32_t (&v)[4]) {
+        const int gyc = clampi(gy, 0, a.H - 1);
+        const uint8_t *lsrc = Lg + (size_t)gyc * a.Lp.pitch, *rsrc = Rg + (size_t)gyc * a.Rp.pitch;
 #pragma unroll
-            for (int b = 0; b < 4; b++) {
-                const int k = 4 * w + b + 2 * cp;
-                v |= (uint32_t)rsrc[clampi(x0 - H_ + k, 0, a.W - 1)] << (8 * b);
+        for (int q = 0; q < 2; q++) {
+            const RingWord d = rw_desc[q];
+            uint32_t w0 = 0, w1 = 0;
+            if (d.dst >= 0) {
+                const uint8_t *src = d.right ? rsrc : lsrc;
+                if (d.src >= 0) {
+                    const uint32_t *pw = reinterpret_cast<const uint32_t *>(src + d.src);
+                    w0 = pw[0]; w1 = pw[1];
+                } else {
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        const int xa = x0 - H_ + d.sh + b;
+                        const int col = d.right ? clampi(xa, 0, a.W - 1) : clampi(xa, -lofs, a.W - lofs - 1) + lofs;
+                        w0 |= (uint32_t)src[col] << (8 * b);
+                    }
+                }
             }
-            reinterpret_cast<uint32_t *>(r0 + (size_t)cp * a.RVP)[w] = v;
+            v[2 * q] = w0; v[2 * q + 1] = w1;
         }
+    };
+    auto commit_row = [&](int gy, const uint32_t (&v)[4]) {
+        uint8_t *slot = Ring + (size_t)(gy & (RING - 1)) * SLOT;
+#pragma unroll
+        for (int q = 0; q < 2; q++)
+            if (rw_desc[q].dst >= 0)
+                *reinterpret_cast<uint32_t *>(slot + rw_desc[q].dst) =
+                    rw_desc[q].src >= 0 ? __funnelshift_r(v[2 * q], v[2 * q + 1], rw_desc[q].sh) : v[2 * q];
     };
 
     // ---- producer task of this thread -------------------------------------------------------------
     const int tg = tid / NO, j = tid - tg * NO;
     const bool prod = tg < a.NGT;
     const int c0 = tg * CT;                             // first virtual column of the thread
-    const int cp = (c0 & 2) ? 1 : 0;                    // which shifted copy keeps the word loads aligned
-    const int lwo = (c0 - 2 * cp) >> 2;                 // word offset of column c0 in copy cp
-    const int rwo = (c0 - 2 * cp + 8 * j) >> 2;         // word offset of R byte (c0 + 8j) in copy cp
+    const int cpy = (c0 & 2) ? 1 : 0;                   // which shifted copy keeps the word loads aligned
+    const int lbo = cpy * a.LVP + (c0 - 2 * cpy);                       // byte offset of column c0 in the slot
+    const int rbo = 2 * a.LVP + cpy * a.RVP + (c0 - 2 * cpy) + 8 * j;   // byte offset of R byte (c0 + 8j)
     // R clamp (App. A.2, minD = 0): rbase(xc) = clip(xc, 0, W - nd); in virtual columns c = xc - x0 + h
     const int cmin = H_ - x0, cmax = (a.W - nd) - x0 + H_;
-    const bool border = (c0 < cmin) || (c0 + CT - 1 > cmax);    // thread-uniform within a column group
+    const bool border = (c0 < cmin) || (c0 + CT - 1 > cmax);
 
     uint32_t V[CT][4];
 #pragma unroll
     for (int kk = 0; kk < CT; kk++) V[kk][0] = V[kk][1] = V[kk][2] = V[kk][3] = 0u;
 
-    auto ad_row = [&](int gy, uint32_t (&lo)[CT], uint32_t (&hi)[CT]) {
-        const int slot = gy & (RING - 1);
-        const uint8_t *lrow = Lv + (size_t)slot * 2 * a.LVP;
-        const uint8_t *rrow = Rv + (size_t)slot * 2 * a.RVP;
-        if (!border)
-            ad_row_fast<CT>(reinterpret_cast<const uint32_t *>(lrow + (size_t)cp * a.LVP) + lwo,
-                            reinterpret_cast<const uint32_t *>(rrow + (size_t)cp * a.RVP) + rwo, lo, hi);
-        else
-            ad_row_border<CT>(lrow, rrow, c0, 8 * j, cmin, cmax, lo, hi);
+    // |L - R| of column kk (8 disparities) of ring row gy
+    auto ad_col = [&](const uint32_t (&lw)[NLW], const uint32_t (&rw)[NRW], const uint8_t *slot, int kk, uint32_t &lo, uint32_t &hi) {
+        if (!border) {
+            const int w = kk >> 2, sft = kk & 3;
+            const uint32_t l4 = __byte_perm(lw[w], 0, sft == 0 ? 0x0000 : (sft == 1 ? 0x1111 : (sft == 2 ? 0x2222 : 0x3333)));
+            uint32_t r0, r1;
+            if (sft == 0) { r0 = rw[w]; r1 = rw[w + 1]; }
+            else { r0 = __funnelshift_r(rw[w], rw[w + 1], 8 * sft); r1 = __funnelshift_r(rw[w + 1], rw[w + 2], 8 * sft); }
+            lo = __vabsdiffu4(l4, r0);
+            hi = __vabsdiffu4(l4, r1);
+        } else {
+            // clamped columns read the R window of the nearest unclamped column (unshifted copy)
+            const int c = c0 + kk;
+            const int bo = clampi(c, cmin, cmax) + 8 * j;
+            const uint32_t *pw = reinterpret_cast<const uint32_t *>(slot + 2 * a.LVP) + (bo >> 2);
+            const int sh = (bo & 3) * 8;
+            const uint32_t l4 = (uint32_t)slot[c] * 0x01010101u;
+            lo = __vabsdiffu4(l4, __funnelshift_r(pw[0], pw[1], sh));
+            hi = __vabsdiffu4(l4, __funnelshift_r(pw[1], pw[2], sh));
+        }
+    };
+    auto load_words = [&](const uint8_t *slot, uint32_t (&lw)[NLW], uint32_t (&rw)[NRW]) {
+        const uint32_t *lp = reinterpret_cast<const uint32_t *>(slot + lbo);
+        const uint32_t *rp = reinterpret_cast<const uint32_t *>(slot + rbo);
+#pragma unroll
+        for (int i = 0; i < NLW; i++) lw[i] = lp[i];
+#pragma unroll
+        for (int i = 0; i < NRW; i++) rw[i] = rp[i];
     };
 
-    // ---- prologue: ring rows y0-h .. y0+h, vertical sums over rows y0-h .. y0+h-1 -----------------
-    for (int r = y0 - H_; r <= y0 + H_; r++) load_row(r);
+    // ---- prologue: ring rows y0-h .. y0+h, zero column, vertical sums over rows y0-h .. y0+h-1 ----
+    for (int r = y0 - H_; r <= y0 + H_; r++) { uint32_t v[4]; fetch_row(r, v); commit_row(r, v); }
+    for (int i = tid; i < a.PP / 4; i += NT2) reinterpret_cast<uint32_t *>(Pre + (size_t)NCT * a.PP)[i] = 0u;
     __syncthreads();
     if (prod) {
         for (int r = y0 - H_; r < y0 + H_; r++) {
-            uint32_t lo[CT], hi[CT];
-            ad_row(r, lo, hi);
+            const uint8_t *slot = Ring + (size_t)(r & (RING - 1)) * SLOT;
+            uint32_t lw[NLW], rw[NRW];
+            if (!border) load_words(slot, lw, rw);
 #pragma unroll
             for (int kk = 0; kk < CT; kk++) {
-                V[kk][0] += __byte_perm(lo[kk], 0, 0x4140);
-                V[kk][1] += __byte_perm(lo[kk], 0, 0x4342);
-                V[kk][2] += __byte_perm(hi[kk], 0, 0x4140);
-                V[kk][3] += __byte_perm(hi[kk], 0, 0x4342);
+                uint32_t lo, hi;
+                ad_col(lw, rw, slot, kk, lo, hi);
+                V[kk][0] += __byte_perm(lo, 0, 0x4140);
+                V[kk][1] += __byte_perm(lo, 0, 0x4342);
+                V[kk][2] += __byte_perm(hi, 0, 0x4140);
+                V[kk][3] += __byte_perm(hi, 0, 0x4342);
             }
         }
     }
@@ -231,94 +258,137 @@ bm_sad2_kernel(Bm2Args a)
     const uint16_t *texf = a.tex + (size_t)f * a.tex_frame;
     const int16_t FILT = (int16_t)(-16);                // (minD - 1) * 16 with minD = 0
 
+    // Consumer pixel assignment.  Warp w runs on SM sub-partition w % 4, and the 6 producer warps load the
+    // sub-partitions (2, 2, 1, 1).  The consumer passes (32 pixels each) therefore go to warps 2 and 3 first
+    // (two passes each), then to warps 0 and 1: pixels [0,32) [64,96) -> warp 2, [32,64) [96,128) -> warp 3,
+    // [128,160) -> warp 0, [160,192) -> warp 1.  Warps 4 and 5 never consume.
+    int cxs[2] = {-1, -1};
+    {
+        const int w = tid >> 5, l = tid & 31;
+        if (NT2 == 192) {
+            if (w == 2) { cxs[0] = l; cxs[1] = 64 + l; }
+            else if (w == 3) { cxs[0] = 32 + l; cxs[1] = 96 + l; }
+            else if (w == 0) cxs[0] = 128 + l;
+            else if (w == 1) cxs[0] = 160 + l;
+        } else {
+            cxs[0] = tid;                                    // other CTA sizes: plain mapping
+            if (NT2 < 192) cxs[1] = NT2 + tid;
+        }
+        if (cxs[0] >= TWc) cxs[0] = -1;
+        if (cxs[1] >= TWc) cxs[1] = -1;
+    }
+
     for (int y = y0; y < y1; y++) {
-        // prefetch the next row into the ring (consumed after the next two barriers)
-        if (y + 1 < y1) load_row(y + 1 + H_);
+        // start fetching the next row and this row's texture sum; both are consumed after the producer work
+        uint32_t nextv[4];
+        const bool have_next = y + 1 < y1;
+        if (have_next && !(a.dbg & 4)) fetch_row(y + 1 + H_, nextv);
+        int tsums[2] = {0, 0};
+#pragma unroll
+        for (int k = 0; k < 2; k++)
+            if (cxs[k] >= 0) tsums[k] = texf[(size_t)y * a.tex_pitch + x0 + cxs[k]];
         // ---------------- producer ---------------------------------------------------------------
-        if (prod) {
-            uint32_t lo[CT], hi[CT];
-            ad_row(y + H_, lo, hi);
-            if (y > y0) {
-                uint32_t olo[CT], ohi[CT];
-                ad_row(y - H_ - 1, olo, ohi);
-#pragma unroll
-                for (int kk = 0; kk < CT; kk++) {
-                    const uint32_t dl = lo[kk] + 0x80808080u - olo[kk];      // per byte: in + 128 - out
-                    const uint32_t dh = hi[kk] + 0x80808080u - ohi[kk];
-                    V[kk][0] += __byte_perm(dl, 0, 0x4140) - 0x00800080u;
-                    V[kk][1] += __byte_perm(dl, 0, 0x4342) - 0x00800080u;
-                    V[kk][2] += __byte_perm(dh, 0, 0x4140) - 0x00800080u;
-                    V[kk][3] += __byte_perm(dh, 0, 0x4342) - 0x00800080u;
-                }
-            } else {
-#pragma unroll
-                for (int kk = 0; kk < CT; kk++) {
-                    V[kk][0] += __byte_perm(lo[kk], 0, 0x4140);
-                    V[kk][1] += __byte_perm(lo[kk], 0, 0x4342);
-                    V[kk][2] += __byte_perm(hi[kk], 0, 0x4140);
-                    V[kk][3] += __byte_perm(hi[kk], 0, 0x4342);
-                }
-            }
-            // in-group prefix and suffix sums
+        if (prod && !(a.dbg & 2)) {
+            const uint8_t *sin = Ring + (size_t)((y + H_) & (RING - 1)) * SLOT;
+            const uint8_t *sout = Ring + (size_t)((y - H_ - 1) & (RING - 1)) * SLOT;
+            uint32_t lwi[NLW], rwi[NRW], lwo[NLW], rwo[NRW];
+            const bool has_out = y > y0;
+            if (!border) { load_words(sin, lwi, rwi); if (has_out) load_words(sout, lwo, rwo); }
+            uint8_t *pdst = Pre + (size_t)c0 * a.PP + 16 * j;
 #pragma unroll
             for (int g = 0; g < KT_; g++) {
                 uint4 p = make_uint4(0, 0, 0, 0);
 #pragma unroll
                 for (int i = 0; i < G; i++) {
                     const int kk = g * G + i;
+                    uint32_t lo, hi;
+                    ad_col(lwi, rwi, sin, kk, lo, hi);
+                    if (has_out) {
+                        uint32_t olo, ohi;
+                        ad_col(lwo, rwo, sout, kk, olo, ohi);
+                        lo = lo + 0x80808080u - olo;                 // per byte: in + 128 - out (no borrow)
+                        hi = hi + 0x80808080u - ohi;
+                        V[kk][0] += __byte_perm(lo, 0, 0x4140) - 0x00800080u;
+                        V[kk][1] += __byte_perm(lo, 0, 0x4342) - 0x00800080u;
+                        V[kk][2] += __byte_perm(hi, 0, 0x4140) - 0x00800080u;
+                        V[kk][3] += __byte_perm(hi, 0, 0x4342) - 0x00800080u;
+                    } else {
+                        V[kk][0] += __byte_perm(lo, 0, 0x4140);
+                        V[kk][1] += __byte_perm(lo, 0, 0x4342);
+                        V[kk][2] += __byte_perm(hi, 0, 0x4140);
+                        V[kk][3] += __byte_perm(hi, 0, 0x4342);
+                    }
                     p.x += V[kk][0]; p.y += V[kk][1]; p.z += V[kk][2]; p.w += V[kk][3];
-                    *reinterpret_cast<uint4 *>(Pre + (size_t)(c0 + kk) * a.PP + 16 * j) = p;
+                    *reinterpret_cast<uint4 *>(pdst + (size_t)kk * a.PP) = p;
                 }
-                uint4 s = make_uint4(0, 0, 0, 0);
+                if (SUF_) {
+                    uint8_t *sdst = Suf + (size_t)c0 * a.PP + 16 * j;
+                    uint4 q = make_uint4(0, 0, 0, 0);
 #pragma unroll
-                for (int i = G - 1; i >= 0; i--) {
-                    const int kk = g * G + i;
-                    s.x += V[kk][0]; s.y += V[kk][1]; s.z += V[kk][2]; s.w += V[kk][3];
-                    *reinterpret_cast<uint4 *>(Suf + (size_t)(c0 + kk) * a.PP + 16 * j) = s;
+                    for (int i = G - 1; i >= 0; i--) {
+                        const int kk = g * G + i;
+                        q.x += V[kk][0]; q.y += V[kk][1]; q.z += V[kk][2]; q.w += V[kk][3];
+                        *reinterpret_cast<uint4 *>(sdst + (size_t)kk * a.PP) = q;
+                    }
                 }
             }
         }
+        if (have_next && !(a.dbg & 4)) commit_row(y + 1 + H_, nextv);
         __syncthreads();
 
         // ---------------- consumer: one thread per pixel -----------------------------------------------
-        for (int x = tid; x < TWc; x += NT2) {
-            const uint8_t *sufp = Suf + (size_t)x * a.PP;
-            const uint8_t *prep = Pre + (size_t)(x + G) * a.PP;
-            const int tsum = texf[(size_t)y * a.tex_pitch + x0 + x];
+#pragma unroll 1
+        for (int k = 0; k < 2; k++) {
+            const int x = cxs[k];
+            if (x < 0 || (a.dbg & 1)) continue;
+            const int tsum = tsums[k];
+            // SAD(x, d) = T_g - Pre[x-1] + Pre[x+G]  (T_g = Pre of the last column of x's group; Pre[-1] = 0)
+            const int gi = x % G;
+            const uint8_t *tp = SUF_ ? Suf + (size_t)x * a.PP : Pre + (size_t)(x - gi + G - 1) * a.PP;
+            const uint8_t *mp = Pre + (size_t)(gi ? x - 1 : NCT) * a.PP;
+            const uint8_t *pp = Pre + (size_t)(x + G) * a.PP;
+            // SAD of one octet as 4 packed u16x2 words
+            auto sad4 = [&](int o, uint32_t (&sv)[4]) {
+                const uint4 t = *reinterpret_cast<const uint4 *>(tp + 16 * o);
+                const uint4 w = *reinterpret_cast<const uint4 *>(pp + 16 * o);
+                if (SUF_) { sv[0] = t.x + w.x; sv[1] = t.y + w.y; sv[2] = t.z + w.z; sv[3] = t.w + w.w; }
+                else {
+                    const uint4 u = *reinterpret_cast<const uint4 *>(mp + 16 * o);
+                    sv[0] = t.x - u.x + w.x; sv[1] = t.y - u.y + w.y; sv[2] = t.z - u.z + w.z; sv[3] = t.w - u.w + w.w;
+                }
+            };
             int16_t dout = FILT;
             if (tsum >= a.texThr) {
                 // pass 1: octet minima and the argmin octet
                 uint32_t best = 0xFFFFFFFFu;
                 for (int o = 0; o < NO; o++) {
-                    const uint4 u = *reinterpret_cast<const uint4 *>(sufp + 16 * o);
-                    const uint4 w = *reinterpret_cast<const uint4 *>(prep + 16 * o);
-                    uint32_t m = __vimin3_u16x2(u.x + w.x, u.y + w.y, u.z + w.z);
-                    m = __vminu2(m, u.w + w.w);
+                    uint32_t sv[4];
+                    sad4(o, sv);
+                    uint32_t m = __vimin3_u16x2(sv[0], sv[1], sv[2]);
+                    m = __vminu2(m, sv[3]);
                     const uint32_t mm = min(m & 0xFFFFu, m >> 16);
                     Smin[o * NT2 + tid] = (uint16_t)mm;
                     best = min(best, mm * 65536u + (uint32_t)o);
                 }
                 const int minsad = (int)(best >> 16), oc = (int)(best & 0xFFFFu);
-                // exact position inside the argmin octet (first minimum)
+                const uint16_t *t16 = reinterpret_cast<const uint16_t *>(tp);
+                const uint16_t *m16 = reinterpret_cast<const uint16_t *>(mp);
+                const uint16_t *p16 = reinterpret_cast<const uint16_t *>(pp);
+                // exact position inside the argmin octet (first minimum) via (value << 3 | index) keys
                 int mind;
                 {
-                    const uint4 u = *reinterpret_cast<const uint4 *>(sufp + 16 * oc);
-                    const uint4 w = *reinterpret_cast<const uint4 *>(prep + 16 * oc);
-                    const uint32_t s0 = u.x + w.x, s1 = u.y + w.y, s2 = u.z + w.z, s3 = u.w + w.w;
-                    int idx = 7;
-                    if ((int)(s3 & 0xFFFFu) == minsad) idx = 6;
-                    if ((int)(s2 >> 16) == minsad) idx = 5;
-                    if ((int)(s2 & 0xFFFFu) == minsad) idx = 4;
-                    if ((int)(s1 >> 16) == minsad) idx = 3;
-                    if ((int)(s1 & 0xFFFFu) == minsad) idx = 2;
-                    if ((int)(s0 >> 16) == minsad) idx = 1;
-                    if ((int)(s0 & 0xFFFFu) == minsad) idx = 0;
-                    mind = 8 * oc + idx;
+                    uint32_t sv[4];
+                    sad4(oc, sv);
+                    const uint32_t s0 = sv[0], s1 = sv[1], s2 = sv[2], s3 = sv[3];
+                    uint32_t k = __vimin3_u32((s0 & 0xFFFFu) * 8u, (s0 >> 16) * 8u + 1u, (s1 & 0xFFFFu) * 8u + 2u);
+                    k = __vimin3_u32(k, (s1 >> 16) * 8u + 3u, (s2 & 0xFFFFu) * 8u + 4u);
+                    k = __vimin3_u32(k, (s2 >> 16) * 8u + 5u, (s3 & 0xFFFFu) * 8u + 6u);
+                    k = min(k, (s3 >> 16) * 8u + 7u);
+                    mind = 8 * oc + (int)(k & 7u);
                 }
-                const uint16_t *suf16 = reinterpret_cast<const uint16_t *>(sufp);
-                const uint16_t *pre16 = reinterpret_cast<const uint16_t *>(prep);
                 const int dp = mind + 1 < nd ? mind + 1 : nd - 2, dn = mind > 0 ? mind - 1 : 1;
-                const int p = (int)suf16[dp] + (int)pre16[dp], n = (int)suf16[dn] + (int)pre16[dn];
+                const int p = (int)t16[dp] - (SUF_ ? 0 : (int)m16[dp]) + (int)p16[dp];
+                const int n = (int)t16[dn] - (SUF_ ? 0 : (int)m16[dn]) + (int)p16[dn];
                 bool ok = true;
                 if (a.uniq > 0) {
                     const int thresh = minsad + (minsad * a.uniq / 100);
@@ -332,16 +402,15 @@ bm_sad2_kernel(Bm2Args a)
                     ok = (int)m2 > thresh;
                     // the (at most two) touching octets: exact check with the neighbourhood masked out
                     for (int oo = olo; ok && oo <= ohi; oo++) {
-                        const uint4 u = *reinterpret_cast<const uint4 *>(sufp + 16 * oo);
-                        const uint4 w = *reinterpret_cast<const uint4 *>(prep + 16 * oo);
+                        uint32_t sv[4];
+                        sad4(oo, sv);
                         const int rel = mind - 8 * oo;                        // -1 .. 8
                         const uint32_t Z = (7u << (rel + 1)) >> 2;            // bit p set: position p is excluded
-                        uint32_t s[4] = {u.x + w.x, u.y + w.y, u.z + w.z, u.w + w.w};
                         uint32_t mz = 0xFFFFFFFFu;
 #pragma unroll
                         for (int r = 0; r < 4; r++) {
-                            uint32_t msk = ((Z >> (2 * r)) & 1u ? 0x0000FFFFu : 0u) | ((Z >> (2 * r + 1)) & 1u ? 0xFFFF0000u : 0u);
-                            mz = __vminu2(mz, s[r] | msk);
+                            const uint32_t msk = (((Z >> (2 * r)) & 1u) ? 0x0000FFFFu : 0u) | (((Z >> (2 * r + 1)) & 1u) ? 0xFFFF0000u : 0u);
+                            mz = __vminu2(mz, sv[r] | msk);
                         }
                         ok = (int)min(mz & 0xFFFFu, mz >> 16) > thresh;
                     }
@@ -355,11 +424,11 @@ bm_sad2_kernel(Bm2Args a)
             }
             dispf[(size_t)y * a.disp.pitch + lofs + x0 + x] = dout;
         }
-        __syncthreads();
+        __syncthreads();        // Pre is rewritten by the next row's producers
     }
 }
 
-struct Tiling2 { int KT, CT, NO, NGT, TW, BH, nstripes, nbands, LVP, RVP, PP; size_t smem; };
+struct Tiling2 { int KT, CT, NO, NGT, TW, BH, nstripes, nbands, LVP, RVP, PP, NT, SUF; size_t smem; };
 
 bool pick_tiling2(const BmGeom &g, int n, Tiling2 *t)
 {
@@ -368,6 +437,13 @@ bool pick_tiling2(const BmGeom &g, int n, Tiling2 *t)
     t->KT = h == 2 ? 3 : (h == 3 ? 2 : 1);
     t->CT = 2 * h * t->KT;
     t->NO = g.nd / 8;
+    // variant: RTDM_BM_VARIANT = 0: 192 threads + suffix sums, 1: 192 prefix-only, 2: 256 + suffix, 3: 256 prefix-only,
+    // 4: 128 + suffix, 5: 128 prefix-only
+    int variant = 0;
+    if (const char *e = getenv("RTDM_BM_VARIANT")) variant = atoi(e);
+    t->NT = variant >= 4 ? 128 : ((variant & 2) ? 256 : 192);
+    t->SUF = (variant & 1) ? 0 : 1;
+    const int NT2 = t->NT;
     t->NGT = std::min(NT2 / t->NO, std::max(1, 192 / t->CT));
     int twmax = t->NGT * t->CT - 2 * h;
     if (twmax < 8) return false;
@@ -383,16 +459,25 @@ bool pick_tiling2(const BmGeom &g, int n, Tiling2 *t)
     t->LVP = (int)align_up(NCT + 8, 4);
     t->RVP = (int)align_up(NCT + g.nd + 16, 4);
     t->PP = g.nd * 2 + 16;
-    t->smem = (size_t)2 * NCT * t->PP + (size_t)t->NO * NT2 * 2 + (size_t)ring_rows(h) * 2 * (t->LVP + t->RVP);
-    return t->smem <= 112 * 1024;
+    t->smem = (size_t)(t->SUF ? 2 : 1) * (NCT + 1) * t->PP + (size_t)t->NO * NT2 * 2 + (size_t)ring_rows(h) * 2 * (t->LVP + t->RVP);
+    if (2 * (t->LVP / 4) + 2 * (t->RVP / 4) > 2 * NT2) return false;     // loader: <= 2 ring words per thread
+    return t->smem <= ((t->NT == 256 && t->SUF) ? 200 : 112) * 1024;
+}
+
+template <int H_, int KT_, int NT2, bool SUF_>
+int launch2v(const Bm2Args &a, const Tiling2 &t, int n, cudaStream_t st)
+{
+    RTDM_CUDA(cudaFuncSetAttribute(bm_sad2_kernel<H_, KT_, NT2, SUF_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(t.smem, 48 * 1024)));
+    bm_sad2_kernel<H_, KT_, NT2, SUF_><<<dim3(t.nstripes, t.nbands, n), NT2, t.smem, st>>>(a);
+    return 0;
 }
 
 template <int H_, int KT_>
 int launch2(const Bm2Args &a, const Tiling2 &t, int n, cudaStream_t st)
 {
-    RTDM_CUDA(cudaFuncSetAttribute(bm_sad2_kernel<H_, KT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-    bm_sad2_kernel<H_, KT_><<<dim3(t.nstripes, t.nbands, n), NT2, t.smem, st>>>(a);
-    return 0;
+    if (t.NT == 128) return t.SUF ? launch2v<H_, KT_, 128, true>(a, t, n, st) : launch2v<H_, KT_, 128, false>(a, t, n, st);
+    if (t.NT == 192) return t.SUF ? launch2v<H_, KT_, 192, true>(a, t, n, st) : launch2v<H_, KT_, 192, false>(a, t, n, st);
+    return t.SUF ? launch2v<H_, KT_, 256, true>(a, t, n, st) : launch2v<H_, KT_, 256, false>(a, t, n, st);
 }
 
 }  // namespace
@@ -412,14 +497,14 @@ int launch_bm_sad2(const BmGeom &g, int n, PlaneU8 Lp, PlaneU8 Rp, PlaneS16 disp
     const int h = g.bs / 2;
     {
         dim3 grid(cdiv(g.W1, TXW), cdiv(g.row1 - g.row0, TXH), n);
-        size_t smem = ((size_t)(TXH + 2 * h) * (TXW + 2 * h) + (size_t)TXH * (TXW + 2 * h)) * sizeof(uint16_t);
-        bm_texture_kernel<<<grid, 256, smem, st>>>(Lp, tex, tex_pitch, tex_frame, g.W, g.H, g.nd, g.cap, h, g.W1, g.row0, g.row1);
+        bm_texture_kernel<<<grid, TXT, 0, st>>>(Lp, tex, tex_pitch, tex_frame, g.W, g.H, g.nd, g.cap, h, g.W1, g.row0, g.row1);
     }
     Bm2Args a;
     a.Lp = Lp; a.Rp = Rp; a.disp = disp; a.cost = cost;
     a.tex = tex; a.tex_pitch = tex_pitch; a.tex_frame = tex_frame;
     a.W = g.W; a.H = g.H; a.nd = g.nd; a.cap = g.cap; a.texThr = g.texThr; a.uniq = g.uniq;
     a.W1 = g.W1; a.row0 = g.row0; a.row1 = g.row1;
+    { const char *e = getenv("RTDM_BM_DEBUG"); a.dbg = e ? atoi(e) : 0; }
     a.TW = t.TW; a.BH = t.BH; a.NO = t.NO; a.NGT = t.NGT; a.LVP = t.LVP; a.RVP = t.RVP; a.PP = t.PP;
     int rc = 0;
     switch (h) {
