@@ -576,7 +576,8 @@ struct rtdm_morph {
     int W, H, maxB, dev;
     cudaStream_t st;
     uint8_t *hin, *hout;         // pinned host frame buffers (video_in / video_out)
-    uint8_t *d0, *d1;            // device ping-pong, maxB frames, tightly packed
+    uint8_t *d0, *d1, *d2, *d3;  // device scratch planes, maxB frames each, tightly packed
+    int *flags;                  // per-frame "not a binary mask" flags
     MorphSE se;
     int launches;
 };
@@ -587,7 +588,7 @@ extern "C" void rtdm_morph_destroy(rtdm_morph *h)
     cudaSetDevice(h->dev);
     if (h->hin) cudaFreeHost(h->hin);
     if (h->hout) cudaFreeHost(h->hout);
-    cudaFree(h->d0); cudaFree(h->d1);
+    cudaFree(h->d0); cudaFree(h->d1); cudaFree(h->d2); cudaFree(h->d3); cudaFree(h->flags);
     if (h->st) cudaStreamDestroy(h->st);
     delete h;
 }
@@ -611,6 +612,9 @@ extern "C" int rtdm_morph_create(rtdm_morph **out, int width, int height, int bp
     if (!rc && cudaHostAlloc((void **)&h->hout, fb, cudaHostAllocDefault) != cudaSuccess) rc = -RTDM_ENOMEM;
     if (!rc) rc = dev_alloc(&h->d0, fb * max_batch);
     if (!rc) rc = dev_alloc(&h->d1, fb * max_batch);
+    if (!rc) rc = dev_alloc(&h->d2, fb * max_batch);
+    if (!rc) rc = dev_alloc(&h->d3, fb * max_batch);
+    if (!rc) rc = dev_alloc(&h->flags, (size_t)max_batch);
     if (rc) { rtdm_morph_destroy(h); return rc; }
     *out = h;
     return 0;
@@ -620,16 +624,12 @@ extern "C" uint8_t *rtdm_morph_in_buffer(rtdm_morph *h) { return h ? h->hin : nu
 extern "C" uint8_t *rtdm_morph_out_buffer(rtdm_morph *h) { return h ? h->hout : nullptr; }
 extern "C" int rtdm_morph_last_launches(const rtdm_morph *h) { return h ? h->launches : 0; }
 
-// erode, dilate, dilate, erode: src -> a -> b -> a -> dst
-static int morph_pipeline(rtdm_morph *h, int n, const uint8_t *src, uint8_t *dst, uint8_t *ta, uint8_t *tb, cudaStream_t st)
+// erode, dilate, dilate, erode (open then close); src and dst may alias
+static int morph_pipeline(rtdm_morph *h, int n, const uint8_t *src, uint8_t *dst, cudaStream_t st)
 {
     const size_t W = h->W, fb = (size_t)h->W * h->H;
-    int rc;
-    rc = launch_morph(n, h->W, h->H, PlaneU8{src, W, fb}, PlaneU8W{ta, W, fb}, h->se, 0, st, &h->launches); if (rc) return rc;
-    rc = launch_morph(n, h->W, h->H, PlaneU8{ta, W, fb}, PlaneU8W{tb, W, fb}, h->se, 1, st, &h->launches); if (rc) return rc;
-    rc = launch_morph(n, h->W, h->H, PlaneU8{tb, W, fb}, PlaneU8W{ta, W, fb}, h->se, 1, st, &h->launches); if (rc) return rc;
-    rc = launch_morph(n, h->W, h->H, PlaneU8{ta, W, fb}, PlaneU8W{dst, W, fb}, h->se, 0, st, &h->launches);
-    return rc;
+    return launch_morph_openclose(n, h->W, h->H, PlaneU8{src, W, fb}, PlaneU8W{dst, W, fb}, PlaneU8W{h->d0, W, fb},
+                                  PlaneU8W{h->d1, W, fb}, PlaneU8W{h->d2, W, fb}, h->flags, h->se, st, &h->launches);
 }
 
 extern "C" int rtdm_morph_run(rtdm_morph *h, const uint8_t *in, uint8_t *out)
@@ -638,12 +638,10 @@ extern "C" int rtdm_morph_run(rtdm_morph *h, const uint8_t *in, uint8_t *out)
     RTDM_CUDA(cudaSetDevice(h->dev));
     h->launches = 0;
     const size_t fb = (size_t)h->W * h->H;
-    // d1[0..fb) holds the input copy; results ping-pong between d0 and the tail of... keep it simple:
-    RTDM_CUDA(cudaMemcpyAsync(h->d1, in, fb, cudaMemcpyHostToDevice, h->st));
-    // src=d1 -> d0 -> d1 -> d0 -> d1
-    int rc = morph_pipeline(h, 1, h->d1, h->d1, h->d0, h->d1, h->st);
+    RTDM_CUDA(cudaMemcpyAsync(h->d3, in, fb, cudaMemcpyHostToDevice, h->st));
+    int rc = morph_pipeline(h, 1, h->d3, h->d3, h->st);
     if (rc) return rc;
-    RTDM_CUDA(cudaMemcpyAsync(out, h->d1, fb, cudaMemcpyDeviceToHost, h->st));
+    RTDM_CUDA(cudaMemcpyAsync(out, h->d3, fb, cudaMemcpyDeviceToHost, h->st));
     RTDM_CUDA(cudaStreamSynchronize(h->st));
     return 0;
 }
@@ -655,10 +653,10 @@ extern "C" int rtdm_morph_run_batch(rtdm_morph *h, int n, const uint8_t *in, uin
     RTDM_CUDA(cudaSetDevice(h->dev));
     h->launches = 0;
     const size_t fb = (size_t)h->W * h->H;
-    RTDM_CUDA(cudaMemcpyAsync(h->d1, in, fb * n, cudaMemcpyHostToDevice, h->st));
-    int rc = morph_pipeline(h, n, h->d1, h->d1, h->d0, h->d1, h->st);
+    RTDM_CUDA(cudaMemcpyAsync(h->d3, in, fb * n, cudaMemcpyHostToDevice, h->st));
+    int rc = morph_pipeline(h, n, h->d3, h->d3, h->st);
     if (rc) return rc;
-    RTDM_CUDA(cudaMemcpyAsync(out, h->d1, fb * n, cudaMemcpyDeviceToHost, h->st));
+    RTDM_CUDA(cudaMemcpyAsync(out, h->d3, fb * n, cudaMemcpyDeviceToHost, h->st));
     RTDM_CUDA(cudaStreamSynchronize(h->st));
     return 0;
 }
@@ -670,7 +668,7 @@ extern "C" int rtdm_morph_run_device(rtdm_morph *h, int n, const uint8_t *in, ui
     RTDM_CUDA(cudaSetDevice(h->dev));
     h->launches = 0;
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->st;
-    return morph_pipeline(h, n, in, out, h->d0, h->d1, st);
+    return morph_pipeline(h, n, in, out, st);
 }
 
 // =================================================================================================

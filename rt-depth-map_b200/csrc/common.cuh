@@ -62,8 +62,12 @@ int launch_median3(int n, int W, int H, PlaneS16 src, PlaneS16 dst, cudaStream_t
 // ---- morphology (morph.cu) ---------------------------------------------------------------------
 struct MorphSE { int kw, kh, ax, ay; int j1[32], j2[32]; };
 void make_ellipse(int kw, int kh, MorphSE *se);
+// need: optional per-frame flags; frames whose flag is 0 are skipped (nullptr = process all)
 int launch_morph(int n, int W, int H, PlaneU8 src, PlaneU8W dst, const MorphSE &se, int op,
-                 cudaStream_t st, int *launches);
+                 cudaStream_t st, int *launches, const int *need = nullptr);
+// erode, dilate, dilate, erode.  ta / tb / fast: n-frame scratch planes, flags: n ints
+int launch_morph_openclose(int n, int W, int H, PlaneU8 src, PlaneU8W dst, PlaneU8W ta, PlaneU8W tb, PlaneU8W fast,
+                           int *flags, const MorphSE &se, cudaStream_t st, int *launches);
 
 // ---- SGBM (sgbm.cu) ----------------------------------------------------------------------------
 struct SgbmGeom {
