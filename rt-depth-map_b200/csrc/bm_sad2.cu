@@ -93,8 +93,8 @@ struct RingWord {
 
 // NT2 = threads per CTA; SUF_ = also store in-group suffix sums (2 x LDS.128 per octet in the consumer
 // instead of 3, at the price of twice the producer stores)
-template <int H_, int KT_, int NT2, bool SUF_>
-__global__ void __launch_bounds__(NT2, 2)
+template <int H_, int KT_, int NT2, bool SUF_, int MINB = 2>
+__global__ void __launch_bounds__(NT2, MINB)
 bm_sad2_kernel(Bm2Args a)
 {
     constexpr int G = 2 * H_, CT = G * KT_, RING = ring_rows(H_);
@@ -448,17 +448,18 @@ bool pick_tiling2(const BmGeom &g, int n, Tiling2 *t)
     return t->smem <= ((t->NT == 256 && t->SUF) ? 200 : 112) * 1024;
 }
 
-template <int H_, int KT_, int NT2, bool SUF_>
+template <int H_, int KT_, int NT2, bool SUF_, int MINB = 2>
 int launch2v(const Bm2Args &a, const Tiling2 &t, int n, cudaStream_t st)
 {
-    RTDM_CUDA(cudaFuncSetAttribute(bm_sad2_kernel<H_, KT_, NT2, SUF_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(t.smem, 48 * 1024)));
-    bm_sad2_kernel<H_, KT_, NT2, SUF_><<<dim3(t.nstripes, t.nbands, n), NT2, t.smem, st>>>(a);
+    RTDM_CUDA(cudaFuncSetAttribute(bm_sad2_kernel<H_, KT_, NT2, SUF_, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(t.smem, 48 * 1024)));
+    bm_sad2_kernel<H_, KT_, NT2, SUF_, MINB><<<dim3(t.nstripes, t.nbands, n), NT2, t.smem, st>>>(a);
     return 0;
 }
 
 template <int H_, int KT_>
 int launch2(const Bm2Args &a, const Tiling2 &t, int n, cudaStream_t st)
 {
+    if (t.NT == 192 && !t.SUF && t.smem <= 74 * 1024 && getenv("RTDM_BM_OCC3")) return launch2v<H_, KT_, 192, false, 3>(a, t, n, st);
     if (t.NT == 192) return t.SUF ? launch2v<H_, KT_, 192, true>(a, t, n, st) : launch2v<H_, KT_, 192, false>(a, t, n, st);
     return t.SUF ? launch2v<H_, KT_, 256, true>(a, t, n, st) : launch2v<H_, KT_, 256, false>(a, t, n, st);
 }

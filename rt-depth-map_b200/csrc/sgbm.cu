@@ -68,73 +68,106 @@ struct CostArgs {
     int W, H, Wp, D, minD, h, minX1, W1;
 };
 
+// Packed version: two disparities per 32-bit word (s16x2 / u16x2 SIMD: VIADD.16x2, VIMNMX3.S16x2).  The right
+// image's (value, lo, hi) arrays are staged REVERSED as u16, so that increasing d is increasing address, in two
+// copies (offset by one element) so that every (d, d+1) pair is one aligned 32-bit load.
 __global__ void __launch_bounds__(256)
 sgbm_cost_hsum_kernel(CostArgs a)
 {
     extern __shared__ __align__(16) uint8_t cs[];
     const int y = blockIdx.y, f = blockIdx.z;
     const int x0 = blockIdx.x * TX;                         // first cost column of the tile
-    const int D = a.D, h = a.h;
+    const int D = a.D, h = a.h, D2 = D / 2;
     const int NXC = TX + 2 * h;                             // cost columns incl. halo (clamped)
     const int maxD = a.minD + D;
-    // left image columns needed: xl = clamp(x0 - h + i) + minX1 ; right: xl - d for d in [minD, maxD)
     const int cl0 = clampi(x0 - h, 0, a.W1 - 1), cl1 = clampi(x0 + TX - 1 + h, 0, a.W1 - 1);
     const int xl_lo = cl0 + a.minX1, xl_hi = cl1 + a.minX1;
     const int xr_lo = xl_lo - (maxD - 1), xr_hi = xl_hi - a.minD;
     const int NL = xl_hi - xl_lo + 1, NR = xr_hi - xr_lo + 1;
-    uint16_t *pix = reinterpret_cast<uint16_t *>(cs);                   // [NXC][D]
-    uint8_t *ls = cs + (size_t)NXC * D * 2;                             // [6][NL]
-    uint8_t *rs = ls + (size_t)6 * NL;                                  // [6][NR]
+    const int NRP = (NR + 3) & ~1;                          // elements per reversed array copy (even, +slack)
+    uint32_t *pix = reinterpret_cast<uint32_t *>(cs);                   // [NXC][D2] packed u16x2
+    uint16_t *rv = reinterpret_cast<uint16_t *>(pix + (size_t)NXC * D2); // [6 arrays][2 copies][NRP]
+    uint8_t *ls = reinterpret_cast<uint8_t *>(rv + (size_t)12 * NRP);   // [6][NL]
     const uint8_t *pf = a.planes + (size_t)f * a.frame_planes;
     const size_t comp = (size_t)a.H * a.Wp;
     for (int i = threadIdx.x; i < 6 * NL; i += blockDim.x) {
         int c = i / NL, k = i - c * NL;
         ls[i] = pf[(size_t)c * comp + (size_t)y * a.Wp + clampi(xl_lo + k, 0, a.W - 1)];
     }
-    for (int i = threadIdx.x; i < 6 * NR; i += blockDim.x) {
-        int c = i / NR, k = i - c * NR;
-        rs[i] = pf[(size_t)(6 + c) * comp + (size_t)y * a.Wp + clampi(xr_lo + k, 0, a.W - 1)];
+    // reversed right arrays: element e of copy 0 = value at xr_hi - e ; copy 1 element e = copy 0 element e + 1
+    for (int i = threadIdx.x; i < 12 * NRP; i += blockDim.x) {
+        int arr = i / (2 * NRP), rem = i - arr * 2 * NRP;
+        int cp = rem >= NRP, e = (cp ? rem - NRP : rem) + cp;
+        int xr = clampi(xr_hi - e, 0, a.W - 1);
+        rv[i] = pf[(size_t)(6 + arr) * comp + (size_t)y * a.Wp + xr];
     }
     __syncthreads();
-    // pixel cost for each (halo column, d): lanes run over d
-    for (int i = threadIdx.x; i < NXC * D; i += blockDim.x) {
-        const int c = i / D, d = i - c * D;
+    // pixel cost: task = (halo column c, pair index dp); lanes run over dp
+    for (int i = threadIdx.x; i < NXC * D2; i += blockDim.x) {
+        const int c = i / D2, dp = i - c * D2;
         const int xc = clampi(x0 - h + c, 0, a.W1 - 1);
         const int kl = xc + a.minX1 - xl_lo;
-        const int kr = xc + a.minX1 - (d + a.minD) - xr_lo;
-        int cost = 0;
+        // disparity d = 2*dp: right pixel xr = xc + minX1 - (d + minD)  ->  reversed index e = xr_hi - xr
+        const int e = xr_hi - (xc + a.minX1 - a.minD) + 2 * dp;
+        const int cp = e & 1;                                // pick the copy in which e is even-aligned
+        const int w = (e - cp) >> 1;
+        uint32_t cost = 0;
 #pragma unroll
         for (int pl = 0; pl < 2; pl++) {
-            const int u = ls[(pl * 3 + 0) * NL + kl], u0 = ls[(pl * 3 + 1) * NL + kl], u1 = ls[(pl * 3 + 2) * NL + kl];
-            const int v = rs[(pl * 3 + 0) * NR + kr], v0 = rs[(pl * 3 + 1) * NR + kr], v1 = rs[(pl * 3 + 2) * NR + kr];
-            const int c0 = max(max(0, u - v1), v0 - u);
-            const int c1 = max(max(0, v - u1), u0 - v);
-            cost += min(c0, c1) >> (pl ? 2 : 0);
+            const uint32_t u = (uint32_t)ls[(pl * 3 + 0) * NL + kl] * 0x00010001u;
+            const uint32_t u0 = (uint32_t)ls[(pl * 3 + 1) * NL + kl] * 0x00010001u;
+            const uint32_t u1 = (uint32_t)ls[(pl * 3 + 2) * NL + kl] * 0x00010001u;
+            const uint32_t v = reinterpret_cast<const uint32_t *>(rv + (size_t)((pl * 3 + 0) * 2 + cp) * NRP)[w];
+            const uint32_t v0 = reinterpret_cast<const uint32_t *>(rv + (size_t)((pl * 3 + 1) * 2 + cp) * NRP)[w];
+            const uint32_t v1 = reinterpret_cast<const uint32_t *>(rv + (size_t)((pl * 3 + 2) * 2 + cp) * NRP)[w];
+            const uint32_t c0 = __vimax3_s16x2(0u, __vsub2(u, v1), __vsub2(v0, u));
+            const uint32_t c1 = __vimax3_s16x2(0u, __vsub2(v, u1), __vsub2(u0, v));
+            uint32_t m = __vmins2(c0, c1);
+            if (pl) m = (m >> 2) & 0x3FFF3FFFu;
+            cost += m;
         }
-        pix[i] = (uint16_t)cost;
+        pix[i] = cost;
     }
     __syncthreads();
-    uint16_t *out = a.Hs + (size_t)f * a.frame_vol + ((size_t)y * a.W1 + x0) * D;
+    uint32_t *out = reinterpret_cast<uint32_t *>(a.Hs + (size_t)f * a.frame_vol + ((size_t)y * a.W1 + x0) * D);
     const int ncol = min(TX, a.W1 - x0);
-    for (int i = threadIdx.x; i < ncol * D; i += blockDim.x) {
-        const int c = i / D, d = i - c * D;
-        int s = 0;
-        for (int k = 0; k <= 2 * h; k++) s += pix[(c + k) * D + d];
-        out[i] = (uint16_t)s;
+    for (int i = threadIdx.x; i < ncol * D2; i += blockDim.x) {
+        const int c = i / D2, dp = i - c * D2;
+        uint32_t sum = 0;
+        for (int k = 0; k <= 2 * h; k++) sum += pix[(c + k) * D2 + dp];
+        out[i] = sum;
     }
 }
 
-// C = P2 + sum over clamped rows y-h..y+h of Hs; two disparities (one u16x2 word) per thread
+// C = P2 + sum over clamped rows y-h..y+h of Hs.  One thread per u16x2 word column and band of rows: the
+// 2h+1 window values live in a register ring (compile-time size), so every Hs word is read once.
+template <int BS>
 __global__ void __launch_bounds__(256)
-sgbm_vsum_kernel(const uint32_t *Hs, uint32_t *C, size_t frame_words, size_t row_words, int H, int h, uint32_t P2x2)
+sgbm_vsum_kernel(const uint32_t *Hs, uint32_t *C, size_t frame_words, size_t row_words, int H, int band, uint32_t P2x2)
 {
+    constexpr int h = BS / 2;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y, f = blockIdx.z;
-    if (i >= row_words) return;
+    const int y0 = blockIdx.y * band, y1 = min(y0 + band, H), f = blockIdx.z;
+    if (i >= row_words || y0 >= y1) return;
     const uint32_t *src = Hs + (size_t)f * frame_words + i;
+    uint32_t *dst = C + (size_t)f * frame_words + i;
+    uint32_t ring[BS];
     uint32_t s = P2x2;
-    for (int j = -h; j <= h; j++) s += src[(size_t)clampi(y + j, 0, H - 1) * row_words];
-    C[(size_t)f * frame_words + (size_t)y * row_words + i] = s;
+#pragma unroll
+    for (int j = 0; j < BS; j++) { ring[j] = src[(size_t)clampi(y0 - h + j, 0, H - 1) * row_words]; s += ring[j]; }
+    // ring[(y - y0 + j) % BS] holds row clamp(y - h + j); slot (y - y0) % BS is the oldest
+    for (int yb = y0; yb < y1; yb += BS) {
+#pragma unroll
+        for (int u = 0; u < BS; u++) {
+            const int y = yb + u;
+            if (y < y1) {
+                dst[(size_t)y * row_words] = s;
+                const uint32_t in = src[(size_t)clampi(y + 1 + h, 0, H - 1) * row_words];
+                s += in - ring[u];
+                ring[u] = in;
+            }
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -257,30 +290,59 @@ sgbm_wta_kernel(WtaArgs a)
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const uint16_t *Srow = a.S + (size_t)f * a.frame_vol + (size_t)y * a.W1 * D;
-    for (int x = warp; x < a.W1; x += nw) {
-        const uint16_t *Sp = Srow + (size_t)x * D;
-        uint32_t kmin = 0xFFFFFFFFu;
-        for (int d = lane; d < D; d += 32) kmin = min(kmin, ((uint32_t)Sp[d] << 16) | (uint32_t)d);
+    const int wordsD = D / 2;
+    // two pixels per warp iteration, S read as u16x2 words (lane l reads words l, l+32, l+64, l+96)
+    for (int xb = warp; xb < a.W1; xb += 2 * nw) {
+        uint32_t v[2][4];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) kmin = min(kmin, __shfl_xor_sync(0xFFFFFFFFu, kmin, o));
-        const int minS = (int)(kmin >> 16), bd = (int)(kmin & 0xFFFFu);
-        if (minS >= 32767) { if (lane == 0) best[x] = -1; continue; }          // degenerate (outside the domain)
-        bool viol = false;
-        for (int d = lane; d < D; d += 32)
-            viol = viol || ((int)Sp[d] * (100 - a.uniq) < minS * 100 && abs(bd - d) > 1);
-        viol = __any_sync(0xFFFFFFFFu, viol);
-        if (lane == 0) {
-            best[x] = (int16_t)bd;
-            if (!viol) {
-                const int x2 = x + a.minX1 - bd - a.minD;
-                if (x2 >= 0 && x2 < a.W) atomicMin(&key2[x2], ((uint32_t)minS << 16) | (uint32_t)(0xFFFF - x));
-                int d = bd;
-                if (0 < d && d < D - 1) {
-                    const int sm = Sp[d - 1], sp = Sp[d + 1], s0 = Sp[d];
-                    const int den = max(sm + sp - 2 * s0, 1);
-                    d = d * 16 + ((sm - sp) * 16 + den) / (den * 2);
-                } else d *= 16;
-                dval[x + a.minX1] = (int16_t)(d + a.minD * 16);
+        for (int q = 0; q < 2; q++) {
+            const int x = xb + q * nw;
+            const uint32_t *Sw = reinterpret_cast<const uint32_t *>(Srow + (size_t)min(x, a.W1 - 1) * D);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int wi = lane + 32 * k;
+                v[q][k] = wi < wordsD ? Sw[wi] : 0xFFFFFFFFu;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const int x = xb + q * nw;
+            if (x >= a.W1) break;                                   // warp-uniform
+            const uint16_t *Sp = Srow + (size_t)x * D;
+            uint32_t kmin = 0xFFFFFFFFu;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t d0 = 2u * (uint32_t)(lane + 32 * k);
+                kmin = min(kmin, min(((v[q][k] & 0xFFFFu) << 16) | d0, (v[q][k] & 0xFFFF0000u) | (d0 + 1u)));
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) kmin = min(kmin, __shfl_xor_sync(0xFFFFFFFFu, kmin, o));
+            const int minS = (int)(kmin >> 16), bd = (int)(kmin & 0xFFFFu);
+            if (minS >= 32767) { if (lane == 0) best[x] = -1; continue; }      // degenerate (outside the domain)
+            bool viol = false;
+            const int lim = minS * 100, mul = 100 - a.uniq;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int d0 = 2 * (lane + 32 * k);
+                if (d0 < D) {
+                    viol = viol || ((int)(v[q][k] & 0xFFFFu) * mul < lim && abs(bd - d0) > 1);
+                    viol = viol || ((int)(v[q][k] >> 16) * mul < lim && abs(bd - d0 - 1) > 1);
+                }
+            }
+            viol = __any_sync(0xFFFFFFFFu, viol);
+            if (lane == 0) {
+                best[x] = (int16_t)bd;
+                if (!viol) {
+                    const int x2 = x + a.minX1 - bd - a.minD;
+                    if (x2 >= 0 && x2 < a.W) atomicMin(&key2[x2], ((uint32_t)minS << 16) | (uint32_t)(0xFFFF - x));
+                    int d = bd;
+                    if (0 < d && d < D - 1) {
+                        const int sm = Sp[d - 1], sp = Sp[d + 1], s0 = Sp[d];
+                        const int den = max(sm + sp - 2 * s0, 1);
+                        d = d * 16 + ((sm - sp) * 16 + den) / (den * 2);
+                    } else d *= 16;
+                    dval[x + a.minX1] = (int16_t)(d + a.minD * 16);
+                }
             }
         }
     }
@@ -335,16 +397,28 @@ int launch_sgbm(const SgbmGeom &g, int n, PlaneU8 left, PlaneU8 right, PlaneS16 
         a.Hs = reinterpret_cast<uint16_t *>(w.S); a.frame_vol = w.frame_vol;
         a.W = g.W; a.H = g.H; a.Wp = Wp; a.D = g.D; a.minD = g.minD; a.h = h; a.minX1 = g.minX1; a.W1 = g.W1;
         const int NXC = TX + 2 * h;
-        size_t smem = (size_t)NXC * g.D * 2 + (size_t)6 * (NXC + 8) + (size_t)6 * (NXC + g.D + 8);
+        size_t smem = (size_t)NXC * g.D * 2 + (size_t)12 * (NXC + g.D + 8) * 2 + (size_t)6 * (NXC + 8) + 16;
         if (smem > 48 * 1024)
             RTDM_CUDA(cudaFuncSetAttribute(sgbm_cost_hsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         sgbm_cost_hsum_kernel<<<dim3(cdiv(g.W1, TX), g.H, n), 256, smem, st>>>(a);
     }
     // 3. vertical window + P2 -> C
     const size_t row_words = (size_t)g.W1 * g.D / 2, frame_words = w.frame_vol / 2;
-    sgbm_vsum_kernel<<<dim3((unsigned)((row_words + 255) / 256), g.H, n), 256, 0, st>>>(
-        reinterpret_cast<const uint32_t *>(w.S), reinterpret_cast<uint32_t *>(w.C), frame_words, row_words, g.H, h,
-        (uint32_t)g.P2 * 0x00010001u);
+    {
+        const int band = 90;
+        dim3 grid((unsigned)((row_words + 255) / 256), cdiv(g.H, band), n);
+        const uint32_t *hs = reinterpret_cast<const uint32_t *>(w.S);
+        uint32_t *cc = reinterpret_cast<uint32_t *>(w.C);
+        const uint32_t p2 = (uint32_t)g.P2 * 0x00010001u;
+        switch (g.bs) {
+            case 1: sgbm_vsum_kernel<1><<<grid, 256, 0, st>>>(hs, cc, frame_words, row_words, g.H, band, p2); break;
+            case 3: sgbm_vsum_kernel<3><<<grid, 256, 0, st>>>(hs, cc, frame_words, row_words, g.H, band, p2); break;
+            case 5: sgbm_vsum_kernel<5><<<grid, 256, 0, st>>>(hs, cc, frame_words, row_words, g.H, band, p2); break;
+            case 7: sgbm_vsum_kernel<7><<<grid, 256, 0, st>>>(hs, cc, frame_words, row_words, g.H, band, p2); break;
+            case 9: sgbm_vsum_kernel<9><<<grid, 256, 0, st>>>(hs, cc, frame_words, row_words, g.H, band, p2); break;
+            default: sgbm_vsum_kernel<11><<<grid, 256, 0, st>>>(hs, cc, frame_words, row_words, g.H, band, p2); break;
+        }
+    }
     if (launches) (*launches) += 3;
     RTDM_CUDA(cudaGetLastError());
     // 4. paths
