@@ -74,7 +74,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                          "-lms", "20", "-i", str(self.index)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -324,6 +324,23 @@ def run_ours(args):
                         "peak_source": hbm_src, "algorithmic_bytes_per_frame": HBM_BYTES_PER_FRAME[wl]},
                 "stage_ms_per_step": {k: v / stage_calls for k, v in stage_ms.items()},
             }
+        if stage_calls and wl == "sgbm720":
+            k_ms = stage_ms["matching"] / stage_calls           # planes + cost + box + 8 path launches + WTA, B frames
+            ip = rt.measure_int_peak(local)
+            de = B * (W - ND) * H * ND
+            hbm_ach = B * HBM_BYTES_PER_FRAME[wl] / (k_ms * 1e-3) / 1e9
+            ach_int = B * W * H * ND * OPS_PER_DE[wl] / (k_ms * 1e-3) / 1e12
+            roofline = {
+                "kernel": "sgbm matching stage (sgbm_path_kernel x8 dominant, + cost/box/WTA)", "bound": "hbm",
+                "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
+                "traffic": 598e6 * 8 * B + 2.1e9 / 4 * B,
+                "traffic_note": "ncu dram bytes, profiles/r01_launches_sgbm.csv: 598 MB per frame per path launch x 8 + cost/box/WTA",
+                "peak_source": hbm_src, "algorithmic_bytes_per_frame": HBM_BYTES_PER_FRAME[wl],
+                "stage_ms_per_launch": k_ms, "frames_per_launch": B,
+                "int_alu": {"achieved": ach_int, "peak": ip["iadd3_tiops"], "unit": "Tiop/s", "frac": ach_int / ip["iadd3_tiops"],
+                            "ops_per_de": OPS_PER_DE[wl]},
+                "stage_ms_per_step": {k: v / stage_calls for k, v in stage_ms.items()},
+            }
         # ---- CPU baseline on a bounded sample (rank 0, N=1 only) -----------------------------------
         cpu = None
         if world == 1 and not args.no_cpu:
@@ -340,7 +357,7 @@ def run_ours(args):
                        "numDisparities": ND, "parallelism": f"frame-sharded x{world} (no collective)",
                        "l2": f"inputs+outputs per step = {(B * 4 * W * H + 2 * B * W * H) / 1e6:.0f} MB > 126 MB L2"},
             "e2e": {"value": e2e_fps * mde_per_frame(), "unit": "Mde/s", "fps": e2e_fps, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "api": "rtdm_bm_compute_batch + rtdm_morph_run_batch, pinned host buffers"},
+                    "d2h_bytes_per_step": d2h, "api": ("rtdm_bm_compute_batch + rtdm_morph_run_batch" if wl == "bm720" else "rtdm_sgbm_compute_batch") + ", pinned host buffers"},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         }
@@ -352,7 +369,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="bm720", choices=["bm720", "sgbm720"])

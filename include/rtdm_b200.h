@@ -131,6 +131,10 @@ int rtdm_sgbm_compute_device(rtdm_sgbm *h, int n, const uint8_t *left, size_t ls
                              int height, int16_t *disp, size_t dstep, size_t dframe,
                              void *cuda_stream);
 int rtdm_sgbm_last_launches(const rtdm_sgbm *h);
+/* CUDA-event stage timing like rtdm_bm_set_profiling: ms_sum[0] = matching (planes, BT cost, box sums, all path
+ * launches, WTA), ms_sum[1] = median + speckle */
+int rtdm_sgbm_set_profiling(rtdm_sgbm *h, int on);
+int rtdm_sgbm_stage_times(rtdm_sgbm *h, double *ms_sum, int *calls);
 
 /* ---- SWMorphologicalFilter peer ---------------------------------------------------------- */
 /* replaces SWMorphologicalFilter::SWMorphologicalFilter(w, h, bpp) (filter/mf-sw.cpp:10-17);

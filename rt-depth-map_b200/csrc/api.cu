@@ -343,9 +343,13 @@ extern "C" int rtdm_bm_compute_batch(rtdm_bm *h, int n, const uint8_t *left, siz
     for (int f0 = 0; f0 < n && !rc; f0 += chunk, c++) {
         const int m = std::min(chunk, n - f0);
         cudaStream_t st = (chunk == n) ? h->st : h->lane[c % 3];
+        const bool lpacked = lstep == (size_t)width && h->spitch == (size_t)width && lframe == h->sframe;
+        const bool rpacked = rstep == (size_t)width && h->spitch == (size_t)width && rframe == h->sframe;
+        if (lpacked) RTDM_CUDA(cudaMemcpyAsync(h->dL + f0 * h->sframe, left + f0 * lframe, (size_t)m * h->sframe, cudaMemcpyHostToDevice, st));
+        if (rpacked) RTDM_CUDA(cudaMemcpyAsync(h->dR + f0 * h->sframe, right + f0 * rframe, (size_t)m * h->sframe, cudaMemcpyHostToDevice, st));
         for (int k = f0; k < f0 + m; k++) {
-            RTDM_CUDA(cudaMemcpy2DAsync(h->dL + k * h->sframe, h->spitch, left + k * lframe, lstep, width, height, cudaMemcpyHostToDevice, st));
-            RTDM_CUDA(cudaMemcpy2DAsync(h->dR + k * h->sframe, h->spitch, right + k * rframe, rstep, width, height, cudaMemcpyHostToDevice, st));
+            if (!lpacked) RTDM_CUDA(cudaMemcpy2DAsync(h->dL + k * h->sframe, h->spitch, left + k * lframe, lstep, width, height, cudaMemcpyHostToDevice, st));
+            if (!rpacked) RTDM_CUDA(cudaMemcpy2DAsync(h->dR + k * h->sframe, h->spitch, right + k * rframe, rstep, width, height, cudaMemcpyHostToDevice, st));
         }
         PlaneU8 L = {h->dL + (size_t)f0 * h->sframe, h->spitch, h->sframe}, R = {h->dR + (size_t)f0 * h->sframe, h->spitch, h->sframe};
         PlaneS16 out = {h->dD + (size_t)f0 * h->dframe, h->dpitch, h->dframe};
@@ -353,7 +357,9 @@ extern "C" int rtdm_bm_compute_batch(rtdm_bm *h, int n, const uint8_t *left, siz
         rc = bm_pipeline(h, m, L, R, width, height, out, st, f0);
         h->prof = prof;
         if (rc) break;
-        for (int k = f0; k < f0 + m; k++)
+        const bool dpacked = dstep == (size_t)width * 2 && h->dpitch == (size_t)width && dframe == h->dframe * 2;
+        if (dpacked) RTDM_CUDA(cudaMemcpyAsync((uint8_t *)disp + f0 * dframe, h->dD + f0 * h->dframe, (size_t)m * dframe, cudaMemcpyDeviceToHost, st));
+        else for (int k = f0; k < f0 + m; k++)
             RTDM_CUDA(cudaMemcpy2DAsync((uint8_t *)disp + k * dframe, dstep, h->dD + k * h->dframe, h->dpitch * 2,
                                         (size_t)width * 2, height, cudaMemcpyDeviceToHost, st));
     }
@@ -404,6 +410,8 @@ struct rtdm_sgbm {
     uint8_t *dL, *dR; size_t spitch, sframe;
     int16_t *dD;      size_t dpitch, dframe;
     int launches;
+    int prof;
+    std::vector<cudaEvent_t> *ev;     // 3 events per profiled sub-batch: start, after matching, after post-filters
 };
 
 static int sgbm_check_params(const rtdm_params *p)
@@ -437,6 +445,7 @@ extern "C" void rtdm_sgbm_destroy(rtdm_sgbm *h)
     cudaSetDevice(h->dev);
     cudaFree(h->planes); cudaFree(h->C); cudaFree(h->S); cudaFree(h->raw); cudaFree(h->labels); cudaFree(h->sizes);
     cudaFree(h->dL); cudaFree(h->dR); cudaFree(h->dD);
+    if (h->ev) { for (cudaEvent_t e : *h->ev) cudaEventDestroy(e); delete h->ev; }
     if (h->st) cudaStreamDestroy(h->st);
     delete h;
 }
@@ -501,6 +510,14 @@ static int sgbm_pipeline(rtdm_sgbm *h, int n, PlaneU8 L, PlaneU8 R, int W, int H
         PlaneU8 l = {L.p + (size_t)f0 * L.frame, L.pitch, L.frame}, r = {R.p + (size_t)f0 * R.frame, R.pitch, R.frame};
         PlaneS16 o = {out.p + (size_t)f0 * out.frame, out.pitch, out.frame};
         PlaneS16 raw = {h->raw, h->rpitch, h->rframe};
+        auto mark = [&]() {
+            if (!h->prof) return;
+            cudaEvent_t e;
+            if (cudaEventCreate(&e) != cudaSuccess) return;
+            cudaEventRecord(e, st);
+            h->ev->push_back(e);
+        };
+        mark();
         if (g.W1 > 0) {
             SgbmWork w;
             memset(&w, 0, sizeof w);
@@ -512,13 +529,45 @@ static int sgbm_pipeline(rtdm_sgbm *h, int n, PlaneU8 L, PlaneU8 R, int W, int H
             int rc = launch_validate_mask(m, W, H, g.minD, g.D, -1, 0, 0, 0, 0, 0, 0, raw, raw, raw, st, &h->launches);
             if (rc) return rc;
         }
+        mark();
         int rc = launch_median3(m, W, H, raw, o, st, &h->launches);
         if (rc) return rc;
         if (h->p.speckleWindowSize > 0) {
             rc = launch_speckle(m, W, H, o, INVS, h->p.speckleWindowSize, 16 * h->p.speckleRange, h->labels, h->sizes, st, &h->launches);
             if (rc) return rc;
         }
+        mark();
     }
+    return 0;
+}
+
+extern "C" int rtdm_sgbm_set_profiling(rtdm_sgbm *h, int on)
+{
+    if (!h) return -RTDM_EINVAL;
+    if (!h->ev) h->ev = new std::vector<cudaEvent_t>();
+    h->prof = on ? 1 : 0;
+    return 0;
+}
+
+extern "C" int rtdm_sgbm_stage_times(rtdm_sgbm *h, double *ms_sum, int *calls)
+{
+    if (!h || !ms_sum || !calls) return -RTDM_EINVAL;
+    ms_sum[0] = ms_sum[1] = 0.0;
+    *calls = 0;
+    if (!h->ev) return 0;
+    RTDM_CUDA(cudaSetDevice(h->dev));
+    std::vector<cudaEvent_t> &ev = *h->ev;
+    for (size_t c = 0; c + 3 <= ev.size(); c += 3) {
+        RTDM_CUDA(cudaEventSynchronize(ev[c + 2]));
+        for (int i = 0; i < 2; i++) {
+            float ms = 0.f;
+            RTDM_CUDA(cudaEventElapsedTime(&ms, ev[c + i], ev[c + i + 1]));
+            ms_sum[i] += ms;
+        }
+        (*calls)++;
+    }
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    ev.clear();
     return 0;
 }
 
@@ -639,9 +688,9 @@ extern "C" int rtdm_morph_run(rtdm_morph *h, const uint8_t *in, uint8_t *out)
     h->launches = 0;
     const size_t fb = (size_t)h->W * h->H;
     RTDM_CUDA(cudaMemcpyAsync(h->d3, in, fb, cudaMemcpyHostToDevice, h->st));
-    int rc = morph_pipeline(h, 1, h->d3, h->d3, h->st);
+    int rc = morph_pipeline(h, 1, h->d3, h->d2, h->st);
     if (rc) return rc;
-    RTDM_CUDA(cudaMemcpyAsync(out, h->d3, fb, cudaMemcpyDeviceToHost, h->st));
+    RTDM_CUDA(cudaMemcpyAsync(out, h->d2, fb, cudaMemcpyDeviceToHost, h->st));
     RTDM_CUDA(cudaStreamSynchronize(h->st));
     return 0;
 }
@@ -654,9 +703,9 @@ extern "C" int rtdm_morph_run_batch(rtdm_morph *h, int n, const uint8_t *in, uin
     h->launches = 0;
     const size_t fb = (size_t)h->W * h->H;
     RTDM_CUDA(cudaMemcpyAsync(h->d3, in, fb * n, cudaMemcpyHostToDevice, h->st));
-    int rc = morph_pipeline(h, n, h->d3, h->d3, h->st);
+    int rc = morph_pipeline(h, n, h->d3, h->d2, h->st);
     if (rc) return rc;
-    RTDM_CUDA(cudaMemcpyAsync(out, h->d3, fb * n, cudaMemcpyDeviceToHost, h->st));
+    RTDM_CUDA(cudaMemcpyAsync(out, h->d2, fb * n, cudaMemcpyDeviceToHost, h->st));
     RTDM_CUDA(cudaStreamSynchronize(h->st));
     return 0;
 }

@@ -60,7 +60,11 @@ int launch_speckle(int n, int W, int H, PlaneS16 img, int newVal, int maxSize, i
 int launch_median3(int n, int W, int H, PlaneS16 src, PlaneS16 dst, cudaStream_t st, int *launches);
 
 // ---- morphology (morph.cu) ---------------------------------------------------------------------
-struct MorphSE { int kw, kh, ax, ay; int j1[32], j2[32]; };
+struct MorphSE {
+    int kw, kh, ax, ay; int j1[32], j2[32];
+    // distinct horizontal runs of the rows (an ellipse has few): run u = [rj1[u], rj1[u] + rL[u]), row k uses run rowrun[k] (-1: empty row)
+    int nrun, rj1[32], rL[32], rowrun[32];
+};
 void make_ellipse(int kw, int kh, MorphSE *se);
 // need: optional per-frame flags; frames whose flag is 0 are skipped (nullptr = process all)
 int launch_morph(int n, int W, int H, PlaneU8 src, PlaneU8W dst, const MorphSE &se, int op,

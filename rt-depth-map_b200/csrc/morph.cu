@@ -29,6 +29,16 @@ void make_ellipse(int kw, int kh, MorphSE *se)
             se->j2[i] = c + dx + 1 < kw ? c + dx + 1 : kw;
         }
     }
+    se->nrun = 0;
+    for (int i = 0; i < 32; i++) { se->rowrun[i] = -1; se->rj1[i] = 0; se->rL[i] = 0; }
+    for (int i = 0; i < kh; i++) {
+        const int L = se->j2[i] - se->j1[i];
+        if (L <= 0) continue;
+        int u = 0;
+        while (u < se->nrun && !(se->rj1[u] == se->j1[i] && se->rL[u] == L)) u++;
+        if (u == se->nrun) { se->rj1[u] = se->j1[i]; se->rL[u] = L; se->nrun++; }
+        se->rowrun[i] = u;
+    }
 }
 
 namespace {
@@ -72,10 +82,14 @@ morph_kernel(int W, int H, PlaneU8 src, PlaneU8W dst, MorphSE se, int op, const 
     const size_t LV = (size_t)TR * TCP;
     uint8_t *m1 = ms, *m2 = m1 + LV, *m4 = m2 + LV, *m8 = m4 + LV, *m16 = m8 + LV;
     const int f = blockIdx.z;
-    const int ox = blockIdx.x * TOW, oy = blockIdx.y * TOH;
     const uint8_t *s = src.p + (size_t)f * src.frame;
     const uint32_t flip = op ? 0xFFu : 0u;            // dilate: work on complemented values
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 word-columns x 8 rows per pass
+    const int tiles_x = (W + TOW - 1) / TOW, tiles = tiles_x * ((H + TOH - 1) / TOH);
+    // bounded grid: each CTA walks over tiles (frames that took the fast path cost only a few empty CTAs)
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int ox = (tile % tiles_x) * TOW, oy = (tile / tiles_x) * TOH;
+    __syncthreads();                                   // the previous tile's readers are done with the smem
     // level 0: tile with identity (255 after flip) outside the image, one word per thread
     for (int r = ty; r < TR; r += 8) {
         const int gy = oy + r - se.ay;
@@ -127,6 +141,7 @@ morph_kernel(int W, int H, PlaneU8 src, PlaneU8W dst, MorphSE se, int op, const 
             d[(size_t)gy * dst.pitch + gx] = (uint8_t)((uint32_t)acc ^ flip);
         }
     }
+    }   // tile loop
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -139,38 +154,29 @@ morph_kernel(int W, int H, PlaneU8 src, PlaneU8W dst, MorphSE se, int op, const 
 constexpr int BT_W = 7, BT_H = 32;               // output tile: 7 words (224 px) x 32 rows
 constexpr int BT_RW = BT_W + 2, BT_HALO = 20, BT_RR = BT_H + 2 * BT_HALO;
 
-__device__ __forceinline__ uint32_t bit_erode_word(const uint32_t *buf, int r, int w, const MorphSE &se)
-{
-    uint32_t acc = 0xFFFFFFFFu;
-    for (int k = 0; k < se.kh; k++) {
-        const int L = se.j2[k] - se.j1[k];
-        if (L <= 0) continue;
-        const int rr = r + k - se.ay;
-        if (rr < 0 || rr >= BT_RR) continue;                       // outside the region: garbage zone anyway
-        const uint32_t *row = buf + rr * BT_RW;
-        const uint32_t prev = w > 0 ? row[w - 1] : 0xFFFFFFFFu, cur = row[w], next = w + 1 < BT_RW ? row[w + 1] : 0xFFFFFFFFu;
-        // R bit j = pixel (32*w + j - 16): 16 pixels of left context
-        const unsigned long long R = (unsigned long long)(prev >> 16) | ((unsigned long long)cur << 16) | ((unsigned long long)next << 48);
-        int p = 1;
-        unsigned long long A = R;
-        while (2 * p <= L) { A &= A >> p; p *= 2; }               // A bit j = AND of R bits j .. j+p-1
-        const int s0 = se.j1[k] - se.ax + 16;                      // run start relative to R's origin
-        acc &= (uint32_t)(A >> s0) & (uint32_t)(A >> (s0 + L - p));
-    }
-    return acc;
-}
+constexpr int BT_MAXRUN = 6;                     // distinct runs the fast path keeps in shared memory
 
+// structuring-element tables: either the kernel argument (generic) or compile-time constants for the
+// reference's 10x10 ellipse (rows 1,7,9,10,10,10,10,10,9,7 wide), which lets the
+// compiler fold every shift amount and unroll both loops
+struct SeView {
+    int kh, ay, ax, nrun;
+    const int *rj1, *rL, *rowrun;
+};
+
+template <bool FIXED10>
 __global__ void __launch_bounds__(256)
 morph_binary_openclose_kernel(int W, int H, PlaneU8 src, PlaneU8W dst, MorphSE se, int *nonbinary)
 {
-    __shared__ uint32_t bufA[BT_RR * BT_RW], bufB[BT_RR * BT_RW], inside[BT_RR * BT_RW];
+    constexpr int NWORD = BT_RR * BT_RW;
+    __shared__ uint32_t buf[NWORD], inside[NWORD], runs[BT_MAXRUN][NWORD];
     const int f = blockIdx.z;
     const int x0 = blockIdx.x * BT_W * 32 - 32, y0 = blockIdx.y * BT_H - BT_HALO;   // region origin
     const uint8_t *s = src.p + (size_t)f * src.frame;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     bool bad = false;
     // 8 independent byte loads in flight per lane before the ballots (the loop is latency-bound otherwise)
-    for (int i0 = warp; i0 < BT_RR * BT_RW; i0 += 64) {
+    for (int i0 = warp; i0 < NWORD; i0 += 64) {
         int v[8];
         bool in[8];
 #pragma unroll
@@ -178,7 +184,7 @@ morph_binary_openclose_kernel(int W, int H, PlaneU8 src, PlaneU8W dst, MorphSE s
             const int i = i0 + 8 * u;
             const int r = i / BT_RW, w = i - r * BT_RW;
             const int gx = x0 + 32 * w + lane, gy = y0 + r;
-            in[u] = i < BT_RR * BT_RW && gx >= 0 && gx < W && gy >= 0 && gy < H;
+            in[u] = i < NWORD && gx >= 0 && gx < W && gy >= 0 && gy < H;
             v[u] = in[u] ? s[(size_t)gy * src.pitch + gx] : 0;
         }
 #pragma unroll
@@ -187,31 +193,66 @@ morph_binary_openclose_kernel(int W, int H, PlaneU8 src, PlaneU8W dst, MorphSE s
             const uint32_t bits = __ballot_sync(0xFFFFFFFFu, v[u] == 255);
             const uint32_t ins = __ballot_sync(0xFFFFFFFFu, in[u]);
             bad = bad || (v[u] != 0 && v[u] != 255);
-            if (lane == 0 && i < BT_RR * BT_RW) { bufA[i] = bits; inside[i] = ins; }
+            if (lane == 0 && i < NWORD) { buf[i] = bits; inside[i] = ins; }
         }
     }
     if (__any_sync(0xFFFFFFFFu, bad) && lane == 0) atomicOr(&nonbinary[f], 1);
     __syncthreads();
+    constexpr int F_KH = 10, F_A = 5, F_NRUN = 4;
+    constexpr int f_rj1[4] = {5, 2, 1, 0}, f_rL[4] = {1, 7, 9, 10}, f_rowrun[10] = {0, 1, 2, 3, 3, 3, 3, 3, 2, 1};
+    const int kh = FIXED10 ? F_KH : se.kh, ay = FIXED10 ? F_A : se.ay, ax = FIXED10 ? F_A : se.ax;
+    const int nrun = FIXED10 ? F_NRUN : se.nrun;
+    const int reach = max(max(ay, kh - 1 - ay), max(ax, (FIXED10 ? 10 : se.kw) - 1 - ax));   // <= BT_HALO / 4
     // pass 1 erode (direct polarity), passes 2+3 dilate (complement polarity), pass 4 erode (direct).
     // In every pass pixels outside the image are the identity of an erode in the current polarity: 1.
-    uint32_t *a = bufA, *b = bufB;
+    // Pass p only has to be right within (3 - p) * reach rows of the output tile.
     for (int pass = 0; pass < 4; pass++) {
         const bool flip = (pass == 1 || pass == 3);                // polarity changes before passes 2 and 4
-        for (int i = threadIdx.x; i < BT_RR * BT_RW; i += 256) a[i] = (flip ? ~a[i] : a[i]) | ~inside[i];
+        const int mo = (3 - pass) * reach;                         // margin of the rows this pass must produce
+        const int ro0 = BT_HALO - mo, ro1 = BT_HALO + BT_H + mo;   // output rows of this pass
+        const int ri0 = max(ro0 - reach, 0), ri1 = min(ro1 + reach, BT_RR);   // input rows it reads
+        for (int i = ri0 * BT_RW + threadIdx.x; i < ri1 * BT_RW; i += 256) buf[i] = (flip ? ~buf[i] : buf[i]) | ~inside[i];
         __syncthreads();
-        for (int i = threadIdx.x; i < BT_RR * BT_RW; i += 256) {
+        // phase A: per (row, word) the AND over every distinct horizontal run, already aligned to the output x
+        for (int i = ri0 * BT_RW + threadIdx.x; i < ri1 * BT_RW; i += 256) {
             const int r = i / BT_RW, w = i - r * BT_RW;
-            b[i] = bit_erode_word(a, r, w, se);
+            const uint32_t *row = buf + r * BT_RW;
+            const uint32_t prev = w > 0 ? row[w - 1] : 0xFFFFFFFFu, cur = row[w], next = w + 1 < BT_RW ? row[w + 1] : 0xFFFFFFFFu;
+            // A1 bit j = pixel (32*w + j - 16): 16 pixels of left context
+            const unsigned long long A1 = (unsigned long long)(prev >> 16) | ((unsigned long long)cur << 16) | ((unsigned long long)next << 48);
+            const unsigned long long A2 = A1 & (A1 >> 1), A4 = A2 & (A2 >> 2), A8 = A4 & (A4 >> 4), A16 = A8 & (A8 >> 8);
+#pragma unroll
+            for (int u = 0; u < (FIXED10 ? F_NRUN : BT_MAXRUN); u++) {
+                if (u < nrun) {
+                    const int L = FIXED10 ? f_rL[u] : se.rL[u], s0 = (FIXED10 ? f_rj1[u] : se.rj1[u]) - ax + 16;
+                    const int p = L >= 16 ? 16 : (L >= 8 ? 8 : (L >= 4 ? 4 : (L >= 2 ? 2 : 1)));
+                    const unsigned long long A = p == 16 ? A16 : (p == 8 ? A8 : (p == 4 ? A4 : (p == 2 ? A2 : A1)));
+                    runs[u][i] = (uint32_t)(A >> s0) & (uint32_t)(A >> (s0 + L - p));
+                }
+            }
         }
         __syncthreads();
-        uint32_t *t = a; a = b; b = t;
+        // phase B: AND over the rows of the structuring element
+        for (int i = ro0 * BT_RW + threadIdx.x; i < ro1 * BT_RW; i += 256) {
+            const int r = i / BT_RW, w = i - r * BT_RW;
+            uint32_t acc = 0xFFFFFFFFu;
+#pragma unroll
+            for (int k = 0; k < (FIXED10 ? F_KH : 16); k++) {
+                if (k < kh) {
+                    const int u = FIXED10 ? f_rowrun[k] : se.rowrun[k], rr = r + k - ay;
+                    if (u >= 0 && rr >= 0 && rr < BT_RR) acc &= runs[u][rr * BT_RW + w];
+                }
+            }
+            buf[i] = acc;
+        }
+        __syncthreads();
     }
     // unpack the centre of the tile: words 1..BT_W, rows BT_HALO..BT_HALO+BT_H
     uint8_t *d = dst.p + (size_t)f * dst.frame;
     for (int i = warp; i < BT_H * BT_W; i += 8) {
         const int r = BT_HALO + i / BT_W, w = 1 + i % BT_W;
         const int gx = x0 + 32 * w + lane, gy = y0 + r;
-        if (gx < W && gy < H) d[(size_t)gy * dst.pitch + gx] = ((a[r * BT_RW + w] >> lane) & 1u) ? 255 : 0;
+        if (gx < W && gy < H) d[(size_t)gy * dst.pitch + gx] = ((buf[r * BT_RW + w] >> lane) & 1u) ? 255 : 0;
     }
 }
 
@@ -239,7 +280,8 @@ int launch_morph(int n, int W, int H, PlaneU8 src, PlaneU8W dst, const MorphSE &
     size_t smem = (size_t)5 * TR * TCP;
     if (smem > 48 * 1024)
         RTDM_CUDA(cudaFuncSetAttribute(morph_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(cdiv(W, TOW), cdiv(H, TOH), n);
+    const int tiles = cdiv(W, TOW) * cdiv(H, TOH);
+    dim3 grid(std::min(tiles, std::max(32, 1184 / n)), 1, n);
     morph_kernel<<<grid, 256, smem, st>>>(W, H, src, dst, se, op, need);
     if (launches) (*launches)++;
     RTDM_CUDA(cudaGetLastError());
@@ -252,11 +294,21 @@ int launch_morph_openclose(int n, int W, int H, PlaneU8 src, PlaneU8W dst, Plane
                            int *flags, const MorphSE &se, cudaStream_t st, int *launches)
 {
     if (n <= 0) return 0;
-    const bool bitpath = se.kw <= 16 && se.kh <= 16;            // 16 px of context per word side, halo 20 >= 4*ax
+    const uint8_t *s0 = src.p, *s1 = src.p + (size_t)n * src.frame, *d0 = dst.p, *d1 = dst.p + (size_t)n * dst.frame;
+    const bool alias = !(s1 <= d0 || d1 <= s0);
+    const bool bitpath = se.kw <= 16 && se.kh <= 16 && se.nrun <= BT_MAXRUN;            // 16 px of context per word side, halo 20 >= 4*ax
     if (bitpath && 4 * std::max(std::max(se.ax, se.kw - 1 - se.ax), std::max(se.ay, se.kh - 1 - se.ay)) <= BT_HALO) {
         RTDM_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * n, st));
         dim3 grid(cdiv(W, BT_W * 32), cdiv(H, BT_H), n);
-        morph_binary_openclose_kernel<<<grid, 256, 0, st>>>(W, H, src, fast, se, flags);
+        // without aliasing the fast path writes dst directly (flagged frames are overwritten by the generic chain)
+        if (!alias) fast = dst;
+        // the reference's 10x10 ellipse gets the compile-time specialisation
+        static const int f_rj1[4] = {5, 2, 1, 0}, f_rL[4] = {1, 7, 9, 10}, f_rowrun[10] = {0, 1, 2, 3, 3, 3, 3, 3, 2, 1};
+        bool fixed10 = se.kw == 10 && se.kh == 10 && se.ax == 5 && se.ay == 5 && se.nrun == 4;
+        for (int u = 0; fixed10 && u < 4; u++) fixed10 = se.rj1[u] == f_rj1[u] && se.rL[u] == f_rL[u];
+        for (int k = 0; fixed10 && k < 10; k++) fixed10 = se.rowrun[k] == f_rowrun[k];
+        if (fixed10) morph_binary_openclose_kernel<true><<<grid, 256, 0, st>>>(W, H, src, fast, se, flags);
+        else morph_binary_openclose_kernel<false><<<grid, 256, 0, st>>>(W, H, src, fast, se, flags);
         if (launches) (*launches)++;
     } else {
         flags = nullptr;                                           // generic chain for every frame
@@ -266,7 +318,7 @@ int launch_morph_openclose(int n, int W, int H, PlaneU8 src, PlaneU8W dst, Plane
     rc = launch_morph(n, W, H, PlaneU8{ta.p, ta.pitch, ta.frame}, tb, se, 1, st, launches, flags); if (rc) return rc;
     rc = launch_morph(n, W, H, PlaneU8{tb.p, tb.pitch, tb.frame}, ta, se, 1, st, launches, flags); if (rc) return rc;
     rc = launch_morph(n, W, H, PlaneU8{ta.p, ta.pitch, ta.frame}, dst, se, 0, st, launches, flags); if (rc) return rc;
-    if (flags) {
+    if (flags && alias) {
         morph_select_kernel<<<dim3(cdiv(cdiv(W, 4), 256), H, n), 256, 0, st>>>(W, H, PlaneU8{fast.p, fast.pitch, fast.frame}, dst, flags);
         if (launches) (*launches)++;
     }

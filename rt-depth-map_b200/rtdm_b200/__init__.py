@@ -68,6 +68,8 @@ SIGNATURES = {
     "rtdm_sgbm_compute_batch": (_i, [_vp, _i, _vp, _sz, _sz, _vp, _sz, _sz, _i, _i, _vp, _sz, _sz]),
     "rtdm_sgbm_compute_device": (_i, [_vp, _i, _vp, _sz, _sz, _vp, _sz, _sz, _i, _i, _vp, _sz, _sz, _vp]),
     "rtdm_sgbm_last_launches": (_i, [_vp]),
+    "rtdm_sgbm_set_profiling": (_i, [_vp, _i]),
+    "rtdm_sgbm_stage_times": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(_i)]),
     "rtdm_morph_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _i]),
     "rtdm_morph_destroy": (None, [_vp]),
     "rtdm_morph_in_buffer": (_vp, [_vp]),
@@ -260,6 +262,17 @@ class CUDASemiGlobalMatcher(_MatcherBase):
 
     def setROI2(self, roi2):
         pass
+
+    STAGES = ("matching", "median_speckle")
+
+    def set_profiling(self, on: bool):
+        _check(self._l.rtdm_sgbm_set_profiling(self._h, int(on)))
+
+    def stage_times(self):
+        ms = (C.c_double * 2)()
+        calls = _i()
+        _check(self._l.rtdm_sgbm_stage_times(self._h, ms, C.byref(calls)))
+        return dict(zip(self.STAGES, list(ms))), calls.value
 
 
 class VideoFilterDevice:

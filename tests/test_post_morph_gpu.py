@@ -105,3 +105,22 @@ def test_filter_binary_fast_path_and_gray_fallback_in_one_batch(gpu, orc):
         single = np.empty((H, W), np.uint8)
         f.run(frames[0], single)
         assert np.array_equal(single, orc.morph_open_close(frames[0]))
+
+
+def test_filter_device_call_in_place_and_out_of_place(gpu, orc):
+    """rtdm_morph_run_device with device pointers: separate output (fast path writes it directly) and
+    in-place (input == output: the fast path goes through a scratch plane)."""
+    import torch
+    from rtdm_b200 import synth
+    W, H = 640, 360
+    frames = np.stack([synth.binary_mask(W, H, 50), synth.gray_image(W, H, 51), synth.binary_mask(W, H, 52)])
+    ref = np.stack([orc.morph_open_close(f) for f in frames])
+    f = gpu.CUDAMorphologicalFilter(W, H, 8, max_batch=3)
+    src = torch.from_numpy(frames).cuda()
+    dst = torch.empty_like(src)
+    f.run_device(3, src.data_ptr(), dst.data_ptr())
+    torch.cuda.synchronize()
+    assert np.array_equal(dst.cpu().numpy(), ref)
+    f.run_device(3, src.data_ptr(), src.data_ptr())
+    torch.cuda.synchronize()
+    assert np.array_equal(src.cpu().numpy(), ref)
