@@ -183,29 +183,33 @@ struct PathArgs {
 
 __device__ __forceinline__ uint32_t min2(uint32_t a, uint32_t b) { return __vminu2(a, b); }
 
-template <int K2>
+// LPC = lanes per chain (32, or 16 / 8 when D/2 words divide evenly: then one warp carries 32/LPC chains, which
+// doubles / quadruples the loads in flight of this latency-bound kernel).  Lanes >= D/2/K2 of a chain are idle.
+template <int K2, int LPC>
 __global__ void __launch_bounds__(128)
 sgbm_path_kernel(PathArgs a)
 {
-    const int lane = threadIdx.x & 31;
-    const int chain = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    constexpr int CPW = 32 / LPC;                          // chains per warp
+    const int lane = threadIdx.x & 31, sl = lane % LPC;
+    const int chain = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * CPW + lane / LPC;
     const int f = blockIdx.y;
-    if (chain >= a.nchains) return;
     const int sx = -a.px, sy = -a.py;
+    bool alive = chain < a.nchains;
+    if (CPW == 1 && !alive) return;                         // whole-warp chains: nothing to keep in step with
     // chain start: a pixel whose predecessor lies outside the image
-    int x, y;
-    {
+    int x = 0, y = 0;
+    if (alive) {
         const int nrow = sy != 0 ? a.W1 : 0;
         if (chain < nrow) { x = chain; y = sy > 0 ? 0 : a.H - 1; }
         else {
-            int j = chain - nrow;
+            const int j = chain - nrow;
             x = sx > 0 ? 0 : a.W1 - 1;
-            if (sy > 0) y = j + 1; else if (sy < 0) y = j; else y = j;     // skip the corner owned by the row set
+            y = sy > 0 ? j + 1 : j;                        // skip the corner owned by the row set
         }
     }
     const int wordsD = a.D / 2;
-    const int nlanes = wordsD / K2;                        // active lanes
-    const bool act = lane < nlanes;
+    const int nlanes = wordsD / K2;                        // active lanes of a chain
+    const bool act = sl < nlanes;
     const uint32_t P1x2 = (uint32_t)a.P1 * 0x00010001u;
     const uint32_t *Cf = a.C + (size_t)f * a.frame_words;
     uint32_t *Sf = a.S + (size_t)f * a.frame_words;
@@ -214,13 +218,13 @@ sgbm_path_kernel(PathArgs a)
     for (int k = 0; k < K2; k++) Lp[k] = 0u;               // out-of-image predecessor: L = 0
     uint32_t minLp = 0u;
     const long long stepw = ((long long)sy * a.W1 + sx) * wordsD;
-    size_t off = ((size_t)y * a.W1 + x) * wordsD + (size_t)lane * K2;
+    size_t off = ((size_t)y * a.W1 + x) * wordsD + (size_t)sl * K2;
     uint32_t c[K2], s[K2];
 #pragma unroll
-    for (int k = 0; k < K2; k++) { c[k] = act ? Cf[off + k] : 0u; s[k] = (act && !a.first) ? Sf[off + k] : 0u; }
-    while (true) {
+    for (int k = 0; k < K2; k++) { c[k] = (alive && act) ? Cf[off + k] : 0u; s[k] = (alive && act && !a.first) ? Sf[off + k] : 0u; }
+    while (CPW == 1 || __any_sync(0xFFFFFFFFu, alive)) {
         const int xn = x + sx, yn = y + sy;
-        const bool more = (xn >= 0 && xn < a.W1 && yn >= 0 && yn < a.H);
+        const bool more = alive && (xn >= 0 && xn < a.W1 && yn >= 0 && yn < a.H);
         // prefetch the next pixel's C and S
         uint32_t cn[K2], sn[K2];
         const size_t offn = (size_t)((long long)off + stepw);
@@ -230,10 +234,10 @@ sgbm_path_kernel(PathArgs a)
             sn[k] = (more && act && !a.first) ? Sf[offn + k] : 0u;
         }
         // neighbours across lanes: last half of the left lane, first half of the right lane
-        uint32_t left = __shfl_up_sync(0xFFFFFFFFu, Lp[K2 - 1], 1);
-        uint32_t right = __shfl_down_sync(0xFFFFFFFFu, Lp[0], 1);
-        if (lane == 0) left = 0x7FFF0000u;                 // L[-1] = MAX_COST (upper half is used)
-        if (lane >= nlanes - 1) right = 0x00007FFFu;       // L[D]  = MAX_COST (lower half is used)
+        uint32_t left = __shfl_up_sync(0xFFFFFFFFu, Lp[K2 - 1], 1, LPC);
+        uint32_t right = __shfl_down_sync(0xFFFFFFFFu, Lp[0], 1, LPC);
+        if (sl == 0) left = 0x7FFF0000u;                   // L[-1] = MAX_COST (upper half is used)
+        if (sl >= nlanes - 1) right = 0x00007FFFu;         // L[D]  = MAX_COST (lower half is used)
         const uint32_t delta = (uint32_t)a.P2 + minLp;     // < 65536
         const uint32_t dx2 = delta * 0x00010001u;
         uint32_t Ln[K2];
@@ -249,7 +253,7 @@ sgbm_path_kernel(PathArgs a)
             t = __vsub2(__vadd2(t, c[k]), dx2);
             Ln[k] = t;
             m = min2(m, t);
-            if (act) {
+            if (alive && act) {
                 uint32_t sv = a.first ? t : min2(__vadd2(s[k], t), 0x7FFF7FFFu);
                 Sf[off + k] = sv;
             }
@@ -258,11 +262,12 @@ sgbm_path_kernel(PathArgs a)
         uint32_t mm = min(m & 0xFFFFu, m >> 16);
         if (!act) mm = 0xFFFFu;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mm = min(mm, __shfl_xor_sync(0xFFFFFFFFu, mm, o));
+        for (int o = LPC / 2; o > 0; o >>= 1) mm = min(mm, __shfl_xor_sync(0xFFFFFFFFu, mm, o));
         minLp = mm;
 #pragma unroll
         for (int k = 0; k < K2; k++) { Lp[k] = Ln[k]; c[k] = cn[k]; s[k] = sn[k]; }
-        if (!more) break;
+        if (CPW == 1 && !more) break;
+        alive = more;
         x = xn; y = yn; off = offn;
     }
 }
@@ -432,11 +437,18 @@ int launch_sgbm(const SgbmGeom &g, int n, PlaneU8 left, PlaneU8 right, PlaneS16 
         a.first = (k == 0);
         const int sx = -a.px, sy = -a.py;
         a.nchains = (sy != 0 ? g.W1 : 0) + (sx != 0 ? (sy != 0 ? g.H - 1 : g.H) : 0);
-        dim3 grid(cdiv(a.nchains, 4), n);
-        switch (K2) {
-            case 1: sgbm_path_kernel<1><<<grid, 128, 0, st>>>(a); break;
-            case 2: sgbm_path_kernel<2><<<grid, 128, 0, st>>>(a); break;
-            default: sgbm_path_kernel<4><<<grid, 128, 0, st>>>(a); break;
+        // sub-warp chains where D/2 words split evenly into 8 or 16 lanes of 4 words (D = 64, 128)
+        // (only when there are enough chains to still fill the machine: ~9.5k resident warps)
+        const bool many = (long long)a.nchains * n >= 2 * 9472;
+        if (g.D == 128 && many) { sgbm_path_kernel<4, 16><<<dim3(cdiv(a.nchains, 8), n), 128, 0, st>>>(a); }
+        else if (g.D == 64 && many) { sgbm_path_kernel<4, 8><<<dim3(cdiv(a.nchains, 16), n), 128, 0, st>>>(a); }
+        else {
+            dim3 grid(cdiv(a.nchains, 4), n);
+            switch (K2) {
+                case 1: sgbm_path_kernel<1, 32><<<grid, 128, 0, st>>>(a); break;
+                case 2: sgbm_path_kernel<2, 32><<<grid, 128, 0, st>>>(a); break;
+                default: sgbm_path_kernel<4, 32><<<grid, 128, 0, st>>>(a); break;
+            }
         }
         if (launches) (*launches)++;
     }
