@@ -86,7 +86,7 @@ struct rtdm_bm {
     // per-batch device workspace (maxB frames)
     uint8_t *Lp, *Rp;            size_t ppitch, pframe;      // prefiltered planes (bytes)
     int16_t *raw, *cost;         size_t rpitch, rframe;      // raw WTA disparity + cost (elements)
-    int32_t *labels, *sizes;
+    int32_t *labels, *sizes, *runlen;
     uint16_t *tex;                                           // texture window sums (rpitch / rframe)
     // staging for the host entry points
     uint8_t *dL, *dR;            size_t spitch, sframe;      // device copies of the inputs
@@ -153,7 +153,7 @@ extern "C" void rtdm_bm_destroy(rtdm_bm *h)
     if (!h) return;
     cudaSetDevice(h->dev);
     cudaFree(h->Lp); cudaFree(h->Rp); cudaFree(h->raw); cudaFree(h->cost);
-    cudaFree(h->labels); cudaFree(h->sizes); cudaFree(h->dL); cudaFree(h->dR); cudaFree(h->dD); cudaFree(h->tex);
+    cudaFree(h->labels); cudaFree(h->sizes); cudaFree(h->runlen); cudaFree(h->dL); cudaFree(h->dR); cudaFree(h->dD); cudaFree(h->tex);
     if (h->ev) { for (cudaEvent_t e : *h->ev) cudaEventDestroy(e); delete h->ev; }
     if (h->st) cudaStreamDestroy(h->st);
     for (int i = 0; i < 3; i++) if (h->lane[i]) cudaStreamDestroy(h->lane[i]);
@@ -194,6 +194,7 @@ extern "C" int rtdm_bm_create(rtdm_bm **out, const rtdm_params *p, int max_width
     if (!rc) rc = dev_alloc(&h->tex, h->rframe * B);
     if (!rc) rc = dev_alloc(&h->labels, (size_t)max_width * max_height * B);
     if (!rc) rc = dev_alloc(&h->sizes, (size_t)max_width * max_height * B);
+    if (!rc) rc = dev_alloc(&h->runlen, (size_t)max_width * max_height * B);
     if (!rc) rc = dev_alloc(&h->dL, h->sframe * B);
     if (!rc) rc = dev_alloc(&h->dR, h->sframe * B);
     if (!rc) rc = dev_alloc(&h->dD, h->dframe * B);
@@ -251,7 +252,7 @@ static int bm_pipeline(rtdm_bm *h, int n, PlaneU8 L, PlaneU8 R, int W, int H, Pl
     uint8_t *wLp = h->Lp + (size_t)f0 * h->pframe, *wRp = h->Rp + (size_t)f0 * h->pframe;
     PlaneS16 raw = {h->raw + (size_t)f0 * h->rframe, h->rpitch, h->rframe};
     PlaneS16 cost = {h->cost + (size_t)f0 * h->rframe, h->rpitch, h->rframe};
-    int32_t *wlab = h->labels + (size_t)f0 * W * H, *wsiz = h->sizes + (size_t)f0 * W * H;
+    int32_t *wlab = h->labels + (size_t)f0 * W * H, *wsiz = h->sizes + (size_t)f0 * W * H, *wrun = h->runlen + (size_t)f0 * W * H;
     mark();
     if (row1 > row0) {
         PlaneU8W oL = {wLp, h->ppitch, h->pframe}, oR = {wRp, h->ppitch, h->pframe};
@@ -275,7 +276,7 @@ static int bm_pipeline(rtdm_bm *h, int n, PlaneU8 L, PlaneU8 R, int W, int H, Pl
     if (rc) return rc;
     mark();
     if (p.speckleRange >= 0 && p.speckleWindowSize > 0)
-        rc = launch_speckle(n, W, H, out, FILT, p.speckleWindowSize, p.speckleRange, wlab, wsiz, st, &h->launches);
+        rc = launch_speckle(n, W, H, out, FILT, p.speckleWindowSize, p.speckleRange, wlab, wsiz, st, &h->launches, wrun);
     mark();
     return rc;
 }
@@ -406,7 +407,7 @@ struct rtdm_sgbm {
     uint8_t *planes;  size_t frame_planes;
     uint16_t *C, *S;  size_t frame_vol;          // elements per frame
     int16_t *raw;     size_t rpitch, rframe;     // WTA output before median (elements)
-    int32_t *labels, *sizes;
+    int32_t *labels, *sizes, *runlen;
     uint8_t *dL, *dR; size_t spitch, sframe;
     int16_t *dD;      size_t dpitch, dframe;
     int launches;
@@ -443,7 +444,7 @@ extern "C" void rtdm_sgbm_destroy(rtdm_sgbm *h)
 {
     if (!h) return;
     cudaSetDevice(h->dev);
-    cudaFree(h->planes); cudaFree(h->C); cudaFree(h->S); cudaFree(h->raw); cudaFree(h->labels); cudaFree(h->sizes);
+    cudaFree(h->planes); cudaFree(h->C); cudaFree(h->S); cudaFree(h->raw); cudaFree(h->labels); cudaFree(h->sizes); cudaFree(h->runlen);
     cudaFree(h->dL); cudaFree(h->dR); cudaFree(h->dD);
     if (h->ev) { for (cudaEvent_t e : *h->ev) cudaEventDestroy(e); delete h->ev; }
     if (h->st) cudaStreamDestroy(h->st);
@@ -487,6 +488,7 @@ extern "C" int rtdm_sgbm_create(rtdm_sgbm **out, const rtdm_params *p, int max_w
     if (!rc) rc = dev_alloc(&h->raw, h->rframe * VB);
     if (!rc) rc = dev_alloc(&h->labels, (size_t)max_width * max_height * VB);
     if (!rc) rc = dev_alloc(&h->sizes, (size_t)max_width * max_height * VB);
+    if (!rc) rc = dev_alloc(&h->runlen, (size_t)max_width * max_height * VB);
     if (!rc) rc = dev_alloc(&h->dL, h->sframe * B);
     if (!rc) rc = dev_alloc(&h->dR, h->sframe * B);
     if (!rc) rc = dev_alloc(&h->dD, h->dframe * B);
@@ -533,7 +535,7 @@ static int sgbm_pipeline(rtdm_sgbm *h, int n, PlaneU8 L, PlaneU8 R, int W, int H
         int rc = launch_median3(m, W, H, raw, o, st, &h->launches);
         if (rc) return rc;
         if (h->p.speckleWindowSize > 0) {
-            rc = launch_speckle(m, W, H, o, INVS, h->p.speckleWindowSize, 16 * h->p.speckleRange, h->labels, h->sizes, st, &h->launches);
+            rc = launch_speckle(m, W, H, o, INVS, h->p.speckleWindowSize, 16 * h->p.speckleRange, h->labels, h->sizes, st, &h->launches, h->runlen);
             if (rc) return rc;
         }
         mark();
@@ -730,21 +732,22 @@ extern "C" int rtdm_filter_speckles(int16_t *img, size_t step, int width, int he
     int rc = check_device(device);
     if (rc) return rc;
     RTDM_CUDA(cudaSetDevice(device));
-    int16_t *d = nullptr; int32_t *lab = nullptr, *siz = nullptr;
+    int16_t *d = nullptr; int32_t *lab = nullptr, *siz = nullptr, *rl = nullptr;
     const size_t N = (size_t)width * height;
     rc = dev_alloc(&d, N);
     if (!rc) rc = dev_alloc(&lab, N);
     if (!rc) rc = dev_alloc(&siz, N);
+    if (!rc) rc = dev_alloc(&rl, N);
     if (!rc) {
         cudaError_t e = cudaMemcpy2D(d, (size_t)width * 2, img, step, (size_t)width * 2, height, cudaMemcpyHostToDevice);
         if (e != cudaSuccess) rc = cuda_fail(e, "memcpy2d", __FILE__, __LINE__);
     }
-    if (!rc) rc = launch_speckle(1, width, height, PlaneS16{d, (size_t)width, N}, newVal, maxSpeckleSize, maxDiff, lab, siz, 0, nullptr);
+    if (!rc) rc = launch_speckle(1, width, height, PlaneS16{d, (size_t)width, N}, newVal, maxSpeckleSize, maxDiff, lab, siz, 0, nullptr, rl);
     if (!rc) {
         cudaError_t e = cudaMemcpy2D(img, step, d, (size_t)width * 2, (size_t)width * 2, height, cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) rc = cuda_fail(e, "memcpy2d", __FILE__, __LINE__);
     }
-    cudaFree(d); cudaFree(lab); cudaFree(siz);
+    cudaFree(d); cudaFree(lab); cudaFree(siz); cudaFree(rl);
     return rc;
 }
 

@@ -54,9 +54,9 @@ int launch_bm_sad2(const BmGeom &g, int n, PlaneU8 Lp, PlaneU8 Rp, PlaneS16 disp
 int launch_validate_mask(int n, int W, int H, int minD, int nd, int d12, int lofs, int W1,
                          int vx0, int vx1, int row0, int row1,
                          PlaneS16 raw, PlaneS16 cost, PlaneS16 out, cudaStream_t st, int *launches);
-// filterSpeckles on n frames in place; labels: n*W*H int32, sizes: n*W*H int32 scratch
+// filterSpeckles on n frames in place; labels, sizes, runlen: n*W*H int32 scratch each
 int launch_speckle(int n, int W, int H, PlaneS16 img, int newVal, int maxSize, int maxDiff,
-                   int32_t *labels, int32_t *sizes, cudaStream_t st, int *launches);
+                   int32_t *labels, int32_t *sizes, cudaStream_t st, int *launches, int32_t *runlen);
 int launch_median3(int n, int W, int H, PlaneS16 src, PlaneS16 dst, cudaStream_t st, int *launches);
 
 // ---- morphology (morph.cu) ---------------------------------------------------------------------

@@ -99,14 +99,18 @@ int launch_validate_mask(int n, int W, int H, int minD, int nd, int d12, int lof
 
 // ------------------------------------------------------------------------------------------------
 // filterSpeckles == delete 4-connected components (edges where both pixels != newVal and
-// |a - b| <= maxDiff) of at most maxSize pixels.  Union-find over the pixel grid:
-//   1. init + row runs : label = index of the first pixel of the pixel's horizontal run
-//   2. vertical merge  : union(run root of (x,y), run root of (x,y-1)) where connected
-//   3. flatten         : label = root
-//   4. count           : sizes[root] += 1 (warp-aggregated)
-//   5. apply           : pixels whose component size <= maxSize become newVal
+// |a - b| <= maxDiff) of at most maxSize pixels.  Union-find over HORIZONTAL RUNS:
+//   1. row runs     : per row, a block-wide max-scan finds every pixel's run start.  Run-start pixels are the
+//                     union-find nodes (label = own index, run length stored, size accumulator cleared); all
+//                     other valid pixels just point at their run start (label = start | RUN_FLAG)
+//   2. vertical merge: union(run of (x,y), run of (x,y-1)) where the two pixels are connected; a link is skipped
+//                     when the pixel pair to the left already joins the same two runs
+//   3. count        : each run start finds its root, flattens, and adds its run length to sizes[root]
+//   4. apply        : pixel -> run start -> root; components with size <= maxSize become newVal
 // The component partition is unique, so the result equals OpenCV's flood fill for any scan order.
 // ------------------------------------------------------------------------------------------------
+constexpr int32_t RUN_FLAG = 0x40000000;       // W*H < 2^30 for every supported geometry
+
 __device__ __forceinline__ int uf_find(const int32_t *lab, int i)
 {
     int p = lab[i];
@@ -127,17 +131,19 @@ __device__ __forceinline__ void uf_union(int32_t *lab, int a, int b)
     }
 }
 
-// one CTA per (row, frame): horizontal runs via a block-wide max-scan of run-start columns
+// one CTA per (row, frame)
 __global__ void __launch_bounds__(256)
-speckle_rowruns_kernel(int W, int H, PlaneS16 img, int newVal, int maxDiff, int32_t *labels, int32_t *sizes)
+speckle_rowruns_kernel(int W, int H, PlaneS16 img, int newVal, int maxDiff, int32_t *labels, int32_t *sizes, int32_t *runlen)
 {
+    extern __shared__ int cnt[];                         // [W] pixels per run, indexed by run-start column
     __shared__ int warp_last[8];
     const int y = blockIdx.x, f = blockIdx.y;
     const int16_t *row = img.p + (size_t)f * img.frame + (size_t)y * img.pitch;
-    int32_t *lab = labels + ((size_t)f * H + y) * W;
-    int32_t *siz = sizes + ((size_t)f * H + y) * W;
+    const size_t rowbase = ((size_t)f * H + y) * W;
+    int32_t *lab = labels + rowbase, *siz = sizes + rowbase, *rlen = runlen + rowbase;
     const int chunk = (W + 255) / 256;
     const int xa = threadIdx.x * chunk, xb = min(xa + chunk, W);
+    for (int x = threadIdx.x; x < W; x += 256) cnt[x] = 0;
     // marker(x) = x where a run starts (or the pixel is invalid), -1 where the run continues
     int run = -1;
     int prev = (xa > 0 && xa < W) ? (int)row[xa - 1] : newVal;
@@ -146,7 +152,6 @@ speckle_rowruns_kernel(int W, int H, PlaneS16 img, int newVal, int maxDiff, int3
         bool cont = (v != newVal) && (x > 0) && (prev != newVal) && (abs(prev - v) <= maxDiff);
         if (!cont) run = x;
         prev = v;
-        siz[x] = 0;
     }
     // exclusive max-scan of `run` over the threads of the block
     int incl = run;
@@ -163,12 +168,25 @@ speckle_rowruns_kernel(int W, int H, PlaneS16 img, int newVal, int maxDiff, int3
     for (int w = 0; w < wid; w++) carry = max(carry, warp_last[w]);
     run = carry;
     prev = (xa > 0 && xa < W) ? (int)row[xa - 1] : newVal;
+    const int rowofs = y * W;                            // frame-local linear index of column 0
+    int pending = 0;                                     // pixels of the current run seen by this thread
     for (int x = xa; x < xb; x++) {
         int v = row[x];
         bool cont = (v != newVal) && (x > 0) && (prev != newVal) && (abs(prev - v) <= maxDiff);
-        if (!cont) run = x;
+        if (!cont) {
+            if (pending) atomicAdd(&cnt[run], pending);
+            pending = 0;
+            run = x;
+        }
         prev = v;
-        lab[x] = (v == newVal) ? -1 : (int)((size_t)y * W + run);
+        if (v == newVal) lab[x] = -1;
+        else { lab[x] = (x == run) ? rowofs + x : ((rowofs + run) | RUN_FLAG); pending++; }
+    }
+    if (pending) atomicAdd(&cnt[run], pending);
+    __syncthreads();
+    for (int x = xa; x < xb; x++) {
+        const int c = cnt[x];
+        if (c > 0) { rlen[x] = c; siz[x] = 0; }          // only run starts own a counter
     }
 }
 
@@ -189,29 +207,25 @@ speckle_vmerge_kernel(int W, int H, PlaneS16 img, int newVal, int maxDiff, int32
         if (vl != newVal && ul != newVal && abs(vl - v) <= maxDiff && abs(ul - u) <= maxDiff &&
             abs(ul - vl) <= maxDiff) return;
     }
-    uf_union(lab, y * W + x, (y - 1) * W + x);
+    int a = lab[y * W + x], b = lab[(y - 1) * W + x];     // pixel -> node (its run start)
+    a = (a & RUN_FLAG) ? (a & ~RUN_FLAG) : y * W + x;
+    b = (b & RUN_FLAG) ? (b & ~RUN_FLAG) : (y - 1) * W + x;
+    uf_union(lab, a, b);
 }
 
 __global__ void __launch_bounds__(256)
-speckle_count_kernel(int W, int H, int32_t *labels, int32_t *sizes)
+speckle_count_kernel(int W, int H, int32_t *labels, int32_t *sizes, const int32_t *runlen)
 {
     const int f = blockIdx.y;
     const size_t N = (size_t)W * H;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
     int32_t *lab = labels + (size_t)f * N;
-    int32_t *siz = sizes + (size_t)f * N;
-    int root = -1;
-    if (i < N && lab[i] >= 0) {
-        root = uf_find(lab, (int)i);
-        lab[i] = root;      // safe: only shortens paths towards the (final) root
-    }
-    // warp-aggregated histogram: one atomic per distinct root per warp
-    unsigned active = __ballot_sync(0xFFFFFFFFu, root >= 0);
-    if (root >= 0) {
-        unsigned peers = __match_any_sync(active, root);
-        int leader = __ffs(peers) - 1;
-        if ((int)(threadIdx.x & 31) == leader) atomicAdd(&siz[root], __popc(peers));
-    }
+    const int l = lab[i];
+    if (l < 0 || (l & RUN_FLAG)) return;                  // invalid pixel or not a run start
+    const int root = uf_find(lab, (int)i);
+    lab[i] = root;                                       // flatten: only shortens the path to the final root
+    atomicAdd(&sizes[(size_t)f * N + root], runlen[(size_t)f * N + i]);
 }
 
 __global__ void __launch_bounds__(256)
@@ -222,21 +236,25 @@ speckle_apply_kernel(int W, int H, PlaneS16 img, int newVal, int maxSize, const 
     const int y = blockIdx.y;
     if (x >= W) return;
     const size_t N = (size_t)W * H;
-    int root = labels[(size_t)f * N + (size_t)y * W + x];
-    if (root < 0) return;
+    const int32_t *lab = labels + (size_t)f * N;
+    int l = lab[(size_t)y * W + x];
+    if (l < 0) return;
+    const int start = (l & RUN_FLAG) ? (l & ~RUN_FLAG) : y * W + x;
+    int root = lab[start];                               // flattened by the count kernel
+    root = (root & RUN_FLAG) ? start : root;             // (cannot happen: starts never carry the flag)
     if (sizes[(size_t)f * N + root] <= maxSize)
         img.p[(size_t)f * img.frame + (size_t)y * img.pitch + x] = (int16_t)newVal;
 }
 
 int launch_speckle(int n, int W, int H, PlaneS16 img, int newVal, int maxSize, int maxDiff,
-                   int32_t *labels, int32_t *sizes, cudaStream_t st, int *launches)
+                   int32_t *labels, int32_t *sizes, cudaStream_t st, int *launches, int32_t *runlen)
 {
     if (n <= 0) return 0;
-    speckle_rowruns_kernel<<<dim3(H, n), 256, 0, st>>>(W, H, img, newVal, maxDiff, labels, sizes);
+    speckle_rowruns_kernel<<<dim3(H, n), 256, (size_t)W * sizeof(int), st>>>(W, H, img, newVal, maxDiff, labels, sizes, runlen);
     if (H > 1)
         speckle_vmerge_kernel<<<dim3(cdiv(W, 256), H - 1, n), 256, 0, st>>>(W, H, img, newVal, maxDiff, labels);
     const size_t N = (size_t)W * H;
-    speckle_count_kernel<<<dim3((unsigned)((N + 255) / 256), n), 256, 0, st>>>(W, H, labels, sizes);
+    speckle_count_kernel<<<dim3((unsigned)((N + 255) / 256), n), 256, 0, st>>>(W, H, labels, sizes, runlen);
     speckle_apply_kernel<<<dim3(cdiv(W, 256), H, n), 256, 0, st>>>(W, H, img, newVal, maxSize, labels, sizes);
     if (launches) (*launches) += (H > 1) ? 4 : 3;
     RTDM_CUDA(cudaGetLastError());
