@@ -151,6 +151,11 @@ uint8_t *rtdm_morph_out_buffer(rtdm_morph *h);
 int rtdm_morph_run(rtdm_morph *h, const uint8_t *in, uint8_t *out);
 /* batched host variant: n tightly packed frames (n <= max_batch) */
 int rtdm_morph_run_batch(rtdm_morph *h, int n, const uint8_t *in, uint8_t *out);
+/* asynchronous batched host variant: enqueues H2D, the kernels and D2H on the handle's stream and returns; in / out
+ * should be pinned host memory and must stay valid until rtdm_morph_sync returns.  Lets the filter's transfers
+ * overlap a matcher call issued in between. */
+int rtdm_morph_run_batch_async(rtdm_morph *h, int n, const uint8_t *in, uint8_t *out);
+int rtdm_morph_sync(rtdm_morph *h);
 /* device variant: n tightly packed frames, asynchronous on cuda_stream */
 int rtdm_morph_run_device(rtdm_morph *h, int n, const uint8_t *in, uint8_t *out, void *cuda_stream);
 int rtdm_morph_last_launches(const rtdm_morph *h);

@@ -97,6 +97,7 @@ struct rtdm_bm {
     // optional per-stage CUDA-event timing (rtdm_bm_set_profiling)
     int prof;
     std::vector<cudaEvent_t> *ev;     // 5 events per profiled call: before prefilter, after each stage
+    std::vector<cudaEvent_t> *pev;    // events of the host-batch pipeline (2 per chunk)
 };
 
 static const int BM_STAGES = 4;      // prefilter, sad+wta, validate+mask, speckle
@@ -155,6 +156,7 @@ extern "C" void rtdm_bm_destroy(rtdm_bm *h)
     cudaFree(h->Lp); cudaFree(h->Rp); cudaFree(h->raw); cudaFree(h->cost);
     cudaFree(h->labels); cudaFree(h->sizes); cudaFree(h->runlen); cudaFree(h->dL); cudaFree(h->dR); cudaFree(h->dD); cudaFree(h->tex);
     if (h->ev) { for (cudaEvent_t e : *h->ev) cudaEventDestroy(e); delete h->ev; }
+    if (h->pev) { for (cudaEvent_t e : *h->pev) cudaEventDestroy(e); delete h->pev; }
     if (h->st) cudaStreamDestroy(h->st);
     for (int i = 0; i < 3; i++) if (h->lane[i]) cudaStreamDestroy(h->lane[i]);
     delete h;
@@ -337,35 +339,50 @@ extern "C" int rtdm_bm_compute_batch(rtdm_bm *h, int n, const uint8_t *left, siz
     }
     RTDM_CUDA(cudaSetDevice(h->dev));
     h->launches = 0;
-    // chunks of frames round-robin over 3 streams: H2D of chunk c+1 and D2H of chunk c-1 overlap the
-    // kernels of chunk c (each chunk owns its own slice of the per-frame workspace)
-    const int chunk = n >= 12 ? std::max(1, std::min(8, n / 6)) : n;
-    int rc = 0, c = 0;
-    for (int f0 = 0; f0 < n && !rc; f0 += chunk, c++) {
-        const int m = std::min(chunk, n - f0);
-        cudaStream_t st = (chunk == n) ? h->st : h->lane[c % 3];
+    // three-stage pipeline over chunks of frames: H2D on lane[0], kernels on the handle's stream, D2H on lane[1],
+    // chained by events.  The kernels always see whole chunks in order (no concurrent kernels from different
+    // chunks fighting for the SMs); the copies of chunk c+1 / c-1 overlap the kernels of chunk c.
+    int chunk = n >= 32 ? 16 : (n >= 8 ? (n + 3) / 4 : n);
+    if (const char *e = getenv("RTDM_BM_CHUNK")) chunk = std::max(1, std::min(n, atoi(e)));
+    const int nchunks = (n + chunk - 1) / chunk;
+    if (!h->pev) h->pev = new std::vector<cudaEvent_t>();
+    while ((int)h->pev->size() < 2 * nchunks) {
+        cudaEvent_t e;
+        RTDM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->pev->push_back(e);
+    }
+    cudaStream_t s_in = h->lane[0], s_out = h->lane[1], s_cmp = h->st;
+    int rc = 0;
+    for (int c = 0; c < nchunks && !rc; c++) {
+        const int f0 = c * chunk, m = std::min(chunk, n - f0);
+        cudaEvent_t ev_in = (*h->pev)[2 * c], ev_done = (*h->pev)[2 * c + 1];
         const bool lpacked = lstep == (size_t)width && h->spitch == (size_t)width && lframe == h->sframe;
         const bool rpacked = rstep == (size_t)width && h->spitch == (size_t)width && rframe == h->sframe;
-        if (lpacked) RTDM_CUDA(cudaMemcpyAsync(h->dL + f0 * h->sframe, left + f0 * lframe, (size_t)m * h->sframe, cudaMemcpyHostToDevice, st));
-        if (rpacked) RTDM_CUDA(cudaMemcpyAsync(h->dR + f0 * h->sframe, right + f0 * rframe, (size_t)m * h->sframe, cudaMemcpyHostToDevice, st));
+        if (lpacked) RTDM_CUDA(cudaMemcpyAsync(h->dL + f0 * h->sframe, left + f0 * lframe, (size_t)m * h->sframe, cudaMemcpyHostToDevice, s_in));
+        if (rpacked) RTDM_CUDA(cudaMemcpyAsync(h->dR + f0 * h->sframe, right + f0 * rframe, (size_t)m * h->sframe, cudaMemcpyHostToDevice, s_in));
         for (int k = f0; k < f0 + m; k++) {
-            if (!lpacked) RTDM_CUDA(cudaMemcpy2DAsync(h->dL + k * h->sframe, h->spitch, left + k * lframe, lstep, width, height, cudaMemcpyHostToDevice, st));
-            if (!rpacked) RTDM_CUDA(cudaMemcpy2DAsync(h->dR + k * h->sframe, h->spitch, right + k * rframe, rstep, width, height, cudaMemcpyHostToDevice, st));
+            if (!lpacked) RTDM_CUDA(cudaMemcpy2DAsync(h->dL + k * h->sframe, h->spitch, left + k * lframe, lstep, width, height, cudaMemcpyHostToDevice, s_in));
+            if (!rpacked) RTDM_CUDA(cudaMemcpy2DAsync(h->dR + k * h->sframe, h->spitch, right + k * rframe, rstep, width, height, cudaMemcpyHostToDevice, s_in));
         }
+        RTDM_CUDA(cudaEventRecord(ev_in, s_in));
+        RTDM_CUDA(cudaStreamWaitEvent(s_cmp, ev_in, 0));
         PlaneU8 L = {h->dL + (size_t)f0 * h->sframe, h->spitch, h->sframe}, R = {h->dR + (size_t)f0 * h->sframe, h->spitch, h->sframe};
         PlaneS16 out = {h->dD + (size_t)f0 * h->dframe, h->dpitch, h->dframe};
-        const int prof = h->prof; h->prof = 0;          // stage events are for single-stream calls only
-        rc = bm_pipeline(h, m, L, R, width, height, out, st, f0);
+        const int prof = h->prof; h->prof = 0;          // stage events are for the device entry point only
+        rc = bm_pipeline(h, m, L, R, width, height, out, s_cmp, f0);
         h->prof = prof;
         if (rc) break;
+        RTDM_CUDA(cudaEventRecord(ev_done, s_cmp));
+        RTDM_CUDA(cudaStreamWaitEvent(s_out, ev_done, 0));
         const bool dpacked = dstep == (size_t)width * 2 && h->dpitch == (size_t)width && dframe == h->dframe * 2;
-        if (dpacked) RTDM_CUDA(cudaMemcpyAsync((uint8_t *)disp + f0 * dframe, h->dD + f0 * h->dframe, (size_t)m * dframe, cudaMemcpyDeviceToHost, st));
+        if (dpacked) RTDM_CUDA(cudaMemcpyAsync((uint8_t *)disp + f0 * dframe, h->dD + f0 * h->dframe, (size_t)m * dframe, cudaMemcpyDeviceToHost, s_out));
         else for (int k = f0; k < f0 + m; k++)
             RTDM_CUDA(cudaMemcpy2DAsync((uint8_t *)disp + k * dframe, dstep, h->dD + k * h->dframe, h->dpitch * 2,
-                                        (size_t)width * 2, height, cudaMemcpyDeviceToHost, st));
+                                        (size_t)width * 2, height, cudaMemcpyDeviceToHost, s_out));
     }
-    cudaError_t e0 = cudaStreamSynchronize(h->st);
-    for (int i = 0; i < 3; i++) { cudaError_t e = cudaStreamSynchronize(h->lane[i]); if (e0 == cudaSuccess) e0 = e; }
+    cudaError_t e0 = cudaStreamSynchronize(s_out);
+    { cudaError_t e = cudaStreamSynchronize(s_cmp); if (e0 == cudaSuccess) e0 = e; }
+    { cudaError_t e = cudaStreamSynchronize(s_in); if (e0 == cudaSuccess) e0 = e; }
     if (rc) return rc;
     RTDM_CUDA(e0);
     return 0;
@@ -694,6 +711,28 @@ extern "C" int rtdm_morph_run(rtdm_morph *h, const uint8_t *in, uint8_t *out)
     if (rc) return rc;
     RTDM_CUDA(cudaMemcpyAsync(out, h->d2, fb, cudaMemcpyDeviceToHost, h->st));
     RTDM_CUDA(cudaStreamSynchronize(h->st));
+    return 0;
+}
+
+extern "C" int rtdm_morph_sync(rtdm_morph *h)
+{
+    if (!h) return -RTDM_EINVAL;
+    RTDM_CUDA(cudaSetDevice(h->dev));
+    RTDM_CUDA(cudaStreamSynchronize(h->st));
+    return 0;
+}
+
+extern "C" int rtdm_morph_run_batch_async(rtdm_morph *h, int n, const uint8_t *in, uint8_t *out)
+{
+    if (!h || !in || !out) { set_error("morph_run_batch_async: null argument"); return -RTDM_EINVAL; }
+    if (n < 1 || n > h->maxB) { set_error("morph: batch exceeds what the handle was created for"); return -RTDM_EINVAL; }
+    RTDM_CUDA(cudaSetDevice(h->dev));
+    h->launches = 0;
+    const size_t fb = (size_t)h->W * h->H;
+    RTDM_CUDA(cudaMemcpyAsync(h->d3, in, fb * n, cudaMemcpyHostToDevice, h->st));
+    int rc = morph_pipeline(h, n, h->d3, h->d2, h->st);
+    if (rc) return rc;
+    RTDM_CUDA(cudaMemcpyAsync(out, h->d2, fb * n, cudaMemcpyDeviceToHost, h->st));
     return 0;
 }
 

@@ -76,6 +76,8 @@ SIGNATURES = {
     "rtdm_morph_out_buffer": (_vp, [_vp]),
     "rtdm_morph_run": (_i, [_vp, _vp, _vp]),
     "rtdm_morph_run_batch": (_i, [_vp, _i, _vp, _vp]),
+    "rtdm_morph_run_batch_async": (_i, [_vp, _i, _vp, _vp]),
+    "rtdm_morph_sync": (_i, [_vp]),
     "rtdm_morph_run_device": (_i, [_vp, _i, _vp, _vp, _vp]),
     "rtdm_morph_last_launches": (_i, [_vp]),
     "rtdm_filter_speckles": (_i, [_vp, _sz, _i, _i, _i, _i, _i, _i]),
@@ -342,6 +344,15 @@ class CUDAMorphologicalFilter(VideoFilterDevice):
             out = np.empty_like(inp)
         _check(self._l.rtdm_morph_run_batch(self._h, inp.shape[0], inp.ctypes.data, out.ctypes.data))
         return out
+
+    def run_batch_async(self, inp, out):
+        """Enqueue-only variant of run_batch (pinned host arrays); call sync() before reading `out`."""
+        if not (inp.flags.c_contiguous and out.flags.c_contiguous and inp.dtype == np.uint8 and out.dtype == np.uint8):
+            raise RtdmError(-EINVAL, "filter: contiguous uint8 arrays required")
+        _check(self._l.rtdm_morph_run_batch_async(self._h, inp.shape[0], inp.ctypes.data, out.ctypes.data))
+
+    def sync(self):
+        _check(self._l.rtdm_morph_sync(self._h))
 
     def run_device(self, n, in_ptr, out_ptr, stream=0):
         _check(self._l.rtdm_morph_run_device(self._h, n, in_ptr, out_ptr, stream))

@@ -170,3 +170,17 @@ def test_bm_errors(gpu):
         m.compute(np.zeros((100, 100), np.uint8), np.zeros((100, 100), np.uint8))   # larger than the handle
     with pytest.raises(gpu.RtdmError):
         m.compute(np.zeros((10, 10), np.uint8), np.zeros((10, 10), np.uint8))       # block larger than image
+
+
+def test_bm_side_by_side_frame(gpu, orc):
+    """BASELINE config 2 input shape: a ZED-style side-by-side frame (left | right in one 2W x H buffer).  The
+    two halves are passed as views with row step 2W -- no repacking on the host."""
+    from rtdm_b200 import synth
+    W, H, nd = 640, 360, 64
+    L, R, _ = synth.stereo_pair(W, H, nd, 77)
+    sbs = np.concatenate([L, R], axis=1)
+    assert sbs.shape == (H, 2 * W)
+    p = dict(preFilterCap=31, blockSize=13, minDisparity=0, textureThreshold=10, numDisparities=nd,
+             uniquenessRatio=10, speckleWindowSize=100, speckleRange=32, disp12MaxDiff=1)
+    got = _mk(gpu, p, W, H).compute(sbs[:, :W], sbs[:, W:])
+    assert np.array_equal(got, orc.bm_compute(L, R, _orc_params(orc, p)))

@@ -124,3 +124,17 @@ def test_filter_device_call_in_place_and_out_of_place(gpu, orc):
     f.run_device(3, src.data_ptr(), src.data_ptr())
     torch.cuda.synchronize()
     assert np.array_equal(src.cpu().numpy(), ref)
+
+
+def test_filter_async_batch(gpu, orc):
+    import torch
+    from rtdm_b200 import synth
+    W, H = 320, 200
+    frames = np.stack([synth.binary_mask(W, H, 60 + i) for i in range(3)])
+    pin = torch.from_numpy(frames).pin_memory()
+    out = torch.empty_like(pin).pin_memory()
+    f = gpu.CUDAMorphologicalFilter(W, H, 8, max_batch=3)
+    f.run_batch_async(pin.numpy(), out.numpy())
+    f.sync()
+    for i in range(3):
+        assert np.array_equal(out.numpy()[i], orc.morph_open_close(frames[i]))
