@@ -184,3 +184,17 @@ def test_bm_side_by_side_frame(gpu, orc):
              uniquenessRatio=10, speckleWindowSize=100, speckleRange=32, disp12MaxDiff=1)
     got = _mk(gpu, p, W, H).compute(sbs[:, :W], sbs[:, W:])
     assert np.array_equal(got, orc.bm_compute(L, R, _orc_params(orc, p)))
+
+
+def test_bm_large_frame_256_disparities(gpu, orc):
+    """Largest disparity count the kernels accept (256) on a 2560x1440 frame: checks index arithmetic far from the
+    720p case (stripes, bands, 32-octet tasks) against the oracle."""
+    from rtdm_b200 import synth
+    W, H, nd = 2560, 1440, 256
+    L, R, _ = synth.stereo_pair(W, H, nd, 4242)
+    for bs in (9, 21):
+        p = dict(preFilterCap=31, blockSize=bs, minDisparity=0, textureThreshold=10, numDisparities=nd,
+                 uniquenessRatio=10, speckleWindowSize=100, speckleRange=32, disp12MaxDiff=1)
+        got = _mk(gpu, p, W, H).compute(L, R)
+        ref = orc.bm_compute(L, R, _orc_params(orc, p))
+        assert np.array_equal(got, ref), (bs, int((got != ref).sum()))
