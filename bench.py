@@ -217,8 +217,8 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    B = args.batch
     wl = args.workload
+    B = args.batch if wl == "bm720" else min(args.batch, 32)      # SGBM keeps 2 x 212 MB of cost volumes per frame
     Lh, Rh, Mh = make_frames(B)
     dev = torch.device("cuda", local)
     L, R, M = (torch.from_numpy(a).to(dev) for a in (Lh, Rh, Mh))
