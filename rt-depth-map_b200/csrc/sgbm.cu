@@ -70,7 +70,9 @@ struct CostArgs {
 
 // Packed version: two disparities per 32-bit word (s16x2 / u16x2 SIMD: VIADD.16x2, VIMNMX3.S16x2).  The right
 // image's (value, lo, hi) arrays are staged REVERSED as u16, so that increasing d is increasing address, in two
-// copies (offset by one element) so that every (d, d+1) pair is one aligned 32-bit load.
+// copies (offset by one element) so that every (d, d+1) pair is one aligned 32-bit load; the left image's six
+// per-column values are staged pre-splatted (value * 0x00010001).  A thread keeps its disparity pair fixed and walks
+// over the tile's columns, so all indices advance incrementally (no divisions in the loops).
 __global__ void __launch_bounds__(256)
 sgbm_cost_hsum_kernel(CostArgs a)
 {
@@ -83,52 +85,83 @@ sgbm_cost_hsum_kernel(CostArgs a)
     const int cl0 = clampi(x0 - h, 0, a.W1 - 1), cl1 = clampi(x0 + TX - 1 + h, 0, a.W1 - 1);
     const int xl_lo = cl0 + a.minX1, xl_hi = cl1 + a.minX1;
     const int xr_lo = xl_lo - (maxD - 1), xr_hi = xl_hi - a.minD;
-    const int NL = xl_hi - xl_lo + 1, NR = xr_hi - xr_lo + 1;
+    const int NR = xr_hi - xr_lo + 1;
     const int NRP = (NR + 3) & ~1;                          // elements per reversed array copy (even, +slack)
     uint32_t *pix = reinterpret_cast<uint32_t *>(cs);                   // [NXC][D2] packed u16x2
-    uint16_t *rv = reinterpret_cast<uint16_t *>(pix + (size_t)NXC * D2); // [6 arrays][2 copies][NRP]
-    uint8_t *ls = reinterpret_cast<uint8_t *>(rv + (size_t)12 * NRP);   // [6][NL]
+    uint32_t *lsw = pix + (size_t)NXC * D2;                             // [NXC][6] splatted left values per halo column
+    uint16_t *rv = reinterpret_cast<uint16_t *>(lsw + (size_t)NXC * 6); // [6 arrays][2 copies][NRP]
     const uint8_t *pf = a.planes + (size_t)f * a.frame_planes;
     const size_t comp = (size_t)a.H * a.Wp;
-    for (int i = threadIdx.x; i < 6 * NL; i += blockDim.x) {
-        int c = i / NL, k = i - c * NL;
-        ls[i] = pf[(size_t)c * comp + (size_t)y * a.Wp + clampi(xl_lo + k, 0, a.W - 1)];
+    const uint8_t *prow = pf + (size_t)y * a.Wp;
+    // left: one (column, component) per thread-iteration; the clamp of the cost column is applied here
+    for (int i = threadIdx.x; i < NXC * 6; i += blockDim.x) {
+        const int c = i / 6, k = i - c * 6;
+        const int xl = clampi(x0 - h + c, 0, a.W1 - 1) + a.minX1;
+        lsw[i] = (uint32_t)prow[(size_t)k * comp + xl] * 0x00010001u;
     }
-    // reversed right arrays: element e of copy 0 = value at xr_hi - e ; copy 1 element e = copy 0 element e + 1
-    for (int i = threadIdx.x; i < 12 * NRP; i += blockDim.x) {
-        int arr = i / (2 * NRP), rem = i - arr * 2 * NRP;
-        int cp = rem >= NRP, e = (cp ? rem - NRP : rem) + cp;
-        int xr = clampi(xr_hi - e, 0, a.W - 1);
-        rv[i] = pf[(size_t)(6 + arr) * comp + (size_t)y * a.Wp + xr];
-    }
-    __syncthreads();
-    // pixel cost: task = (halo column c, pair index dp); lanes run over dp
-    for (int i = threadIdx.x; i < NXC * D2; i += blockDim.x) {
-        const int c = i / D2, dp = i - c * D2;
-        const int xc = clampi(x0 - h + c, 0, a.W1 - 1);
-        const int kl = xc + a.minX1 - xl_lo;
-        // disparity d = 2*dp: right pixel xr = xc + minX1 - (d + minD)  ->  reversed index e = xr_hi - xr
-        const int e = xr_hi - (xc + a.minX1 - a.minD) + 2 * dp;
-        const int cp = e & 1;                                // pick the copy in which e is even-aligned
-        const int w = (e - cp) >> 1;
-        uint32_t cost = 0;
-#pragma unroll
-        for (int pl = 0; pl < 2; pl++) {
-            const uint32_t u = (uint32_t)ls[(pl * 3 + 0) * NL + kl] * 0x00010001u;
-            const uint32_t u0 = (uint32_t)ls[(pl * 3 + 1) * NL + kl] * 0x00010001u;
-            const uint32_t u1 = (uint32_t)ls[(pl * 3 + 2) * NL + kl] * 0x00010001u;
-            const uint32_t v = reinterpret_cast<const uint32_t *>(rv + (size_t)((pl * 3 + 0) * 2 + cp) * NRP)[w];
-            const uint32_t v0 = reinterpret_cast<const uint32_t *>(rv + (size_t)((pl * 3 + 1) * 2 + cp) * NRP)[w];
-            const uint32_t v1 = reinterpret_cast<const uint32_t *>(rv + (size_t)((pl * 3 + 2) * 2 + cp) * NRP)[w];
-            const uint32_t c0 = __vimax3_s16x2(0u, __vsub2(u, v1), __vsub2(v0, u));
-            const uint32_t c1 = __vimax3_s16x2(0u, __vsub2(v, u1), __vsub2(u0, v));
-            uint32_t m = __vmins2(c0, c1);
-            if (pl) m = (m >> 2) & 0x3FFF3FFFu;
-            cost += m;
+    // right, reversed: element e of copy 0 = value at xr_hi - e; copy 1 element e = copy 0 element e + 1
+    for (int arr = 0; arr < 6; arr++) {
+        const uint8_t *src = prow + (size_t)(6 + arr) * comp;
+        uint16_t *d0 = rv + (size_t)(arr * 2) * NRP, *d1 = d0 + NRP;
+        for (int e = threadIdx.x; e <= NRP; e += blockDim.x) {
+            const uint16_t v = src[clampi(xr_hi - e, 0, a.W - 1)];
+            if (e < NRP) d0[e] = v;
+            if (e >= 1) d1[e - 1] = v;
         }
-        pix[i] = cost;
     }
     __syncthreads();
+    // pixel cost: thread = disparity pair dp (fixed), walking over the halo columns with stride blockDim / D2
+    {
+        const int dp = threadIdx.x % D2, cstep = blockDim.x / D2;      // D2 divides 256 for D = 16 .. 256 (powers of two) ...
+        const bool regular = (blockDim.x % D2) == 0;                   // ... otherwise fall back to the generic index
+        if (regular) {
+            for (int c = threadIdx.x / D2; c < NXC; c += cstep) {
+                const int xc = clampi(x0 - h + c, 0, a.W1 - 1);
+                // d = 2*dp: right pixel xr = xc + minX1 - (d + minD) -> reversed index e = xr_hi - xr
+                const int e = xr_hi - (xc + a.minX1 - a.minD) + 2 * dp;
+                const int cp = e & 1, w = (e - cp) >> 1;
+                const uint32_t *lw = lsw + c * 6;
+                const uint32_t *rw = reinterpret_cast<const uint32_t *>(rv + (size_t)cp * NRP) + w;
+                const size_t astep = (size_t)NRP;                      // words between consecutive arrays (2 copies x NRP u16)
+                uint32_t cost = 0;
+#pragma unroll
+                for (int pl = 0; pl < 2; pl++) {
+                    const uint32_t u = lw[pl * 3 + 0], u0 = lw[pl * 3 + 1], u1 = lw[pl * 3 + 2];
+                    const uint32_t v = rw[(pl * 3 + 0) * astep], v0 = rw[(pl * 3 + 1) * astep], v1 = rw[(pl * 3 + 2) * astep];
+                    const uint32_t c0 = __vimax3_s16x2(0u, __vsub2(u, v1), __vsub2(v0, u));
+                    const uint32_t c1 = __vimax3_s16x2(0u, __vsub2(v, u1), __vsub2(u0, v));
+                    uint32_t m = __vmins2(c0, c1);
+                    if (pl) m = (m >> 2) & 0x3FFF3FFFu;
+                    cost += m;
+                }
+                pix[c * D2 + dp] = cost;
+            }
+        } else {
+            for (int i = threadIdx.x; i < NXC * D2; i += blockDim.x) {
+                const int c = i / D2, dq = i - c * D2;
+                const int xc = clampi(x0 - h + c, 0, a.W1 - 1);
+                const int e = xr_hi - (xc + a.minX1 - a.minD) + 2 * dq;
+                const int cp = e & 1, w = (e - cp) >> 1;
+                const uint32_t *lw = lsw + c * 6;
+                const uint32_t *rw = reinterpret_cast<const uint32_t *>(rv + (size_t)cp * NRP) + w;
+                const size_t astep = (size_t)NRP;
+                uint32_t cost = 0;
+#pragma unroll
+                for (int pl = 0; pl < 2; pl++) {
+                    const uint32_t u = lw[pl * 3 + 0], u0 = lw[pl * 3 + 1], u1 = lw[pl * 3 + 2];
+                    const uint32_t v = rw[(pl * 3 + 0) * astep], v0 = rw[(pl * 3 + 1) * astep], v1 = rw[(pl * 3 + 2) * astep];
+                    const uint32_t c0 = __vimax3_s16x2(0u, __vsub2(u, v1), __vsub2(v0, u));
+                    const uint32_t c1 = __vimax3_s16x2(0u, __vsub2(v, u1), __vsub2(u0, v));
+                    uint32_t m = __vmins2(c0, c1);
+                    if (pl) m = (m >> 2) & 0x3FFF3FFFu;
+                    cost += m;
+                }
+                pix[i] = cost;
+            }
+        }
+    }
+    __syncthreads();
+    // horizontal window: thread = pair dp, sliding over the tile's columns
     uint32_t *out = reinterpret_cast<uint32_t *>(a.Hs + (size_t)f * a.frame_vol + ((size_t)y * a.W1 + x0) * D);
     const int ncol = min(TX, a.W1 - x0);
     for (int i = threadIdx.x; i < ncol * D2; i += blockDim.x) {
@@ -324,14 +357,28 @@ sgbm_wta_kernel(WtaArgs a)
             for (int o = 16; o > 0; o >>= 1) kmin = min(kmin, __shfl_xor_sync(0xFFFFFFFFu, kmin, o));
             const int minS = (int)(kmin >> 16), bd = (int)(kmin & 0xFFFFu);
             if (minS >= 32767) { if (lane == 0) best[x] = -1; continue; }      // degenerate (outside the domain)
+            // S[d] * (100 - uniq) < minS * 100   <=>   S[d] < T  with  T = ceil(minS * 100 / (100 - uniq))   (uniq < 100);
+            // lanes beyond D hold 0xFFFF and never qualify
             bool viol = false;
-            const int lim = minS * 100, mul = 100 - a.uniq;
+            const int mul = 100 - a.uniq;
+            if (mul > 0) {
+                const uint32_t T = (uint32_t)((minS * 100 + mul - 1) / mul);
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int d0 = 2 * (lane + 32 * k);
-                if (d0 < D) {
-                    viol = viol || ((int)(v[q][k] & 0xFFFFu) * mul < lim && abs(bd - d0) > 1);
-                    viol = viol || ((int)(v[q][k] >> 16) * mul < lim && abs(bd - d0 - 1) > 1);
+                for (int k = 0; k < 4; k++) {
+                    const int d0 = 2 * (lane + 32 * k);
+                    const uint32_t lo = v[q][k] & 0xFFFFu, hi = v[q][k] >> 16;
+                    viol = viol || (lo < T && (unsigned)(bd - d0 + 1) > 2u);          // |bd - d0| > 1
+                    viol = viol || (hi < T && (unsigned)(bd - d0) > 2u);              // |bd - (d0 + 1)| > 1
+                }
+            } else {
+                const int lim = minS * 100;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int d0 = 2 * (lane + 32 * k);
+                    if (d0 < D) {
+                        viol = viol || ((int)(v[q][k] & 0xFFFFu) * mul < lim && abs(bd - d0) > 1);
+                        viol = viol || ((int)(v[q][k] >> 16) * mul < lim && abs(bd - d0 - 1) > 1);
+                    }
                 }
             }
             viol = __any_sync(0xFFFFFFFFu, viol);
@@ -402,7 +449,7 @@ int launch_sgbm(const SgbmGeom &g, int n, PlaneU8 left, PlaneU8 right, PlaneS16 
         a.Hs = reinterpret_cast<uint16_t *>(w.S); a.frame_vol = w.frame_vol;
         a.W = g.W; a.H = g.H; a.Wp = Wp; a.D = g.D; a.minD = g.minD; a.h = h; a.minX1 = g.minX1; a.W1 = g.W1;
         const int NXC = TX + 2 * h;
-        size_t smem = (size_t)NXC * g.D * 2 + (size_t)12 * (NXC + g.D + 8) * 2 + (size_t)6 * (NXC + 8) + 16;
+        size_t smem = (size_t)NXC * g.D * 2 + (size_t)NXC * 6 * 4 + (size_t)12 * (NXC + g.D + 8) * 2 + 16;
         if (smem > 48 * 1024)
             RTDM_CUDA(cudaFuncSetAttribute(sgbm_cost_hsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         sgbm_cost_hsum_kernel<<<dim3(cdiv(g.W1, TX), g.H, n), 256, smem, st>>>(a);
