@@ -294,9 +294,8 @@ sgbm_path_kernel(PathArgs a)
         // min over the chain's D values: inactive lanes must not contribute
         uint32_t mm = min(m & 0xFFFFu, m >> 16);
         if (!act) mm = 0xFFFFu;
-#pragma unroll
-        for (int o = LPC / 2; o > 0; o >>= 1) mm = min(mm, __shfl_xor_sync(0xFFFFFFFFu, mm, o));
-        minLp = mm;
+        // hardware warp reduction (REDUX.MIN) over the lanes of this chain
+        minLp = __reduce_min_sync(LPC == 32 ? 0xFFFFFFFFu : (((1u << LPC) - 1u) << (lane & ~(LPC - 1))), mm);
 #pragma unroll
         for (int k = 0; k < K2; k++) { Lp[k] = Ln[k]; c[k] = cn[k]; s[k] = sn[k]; }
         if (CPW == 1 && !more) break;
@@ -353,8 +352,7 @@ sgbm_wta_kernel(WtaArgs a)
                 const uint32_t d0 = 2u * (uint32_t)(lane + 32 * k);
                 kmin = min(kmin, min(((v[q][k] & 0xFFFFu) << 16) | d0, (v[q][k] & 0xFFFF0000u) | (d0 + 1u)));
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) kmin = min(kmin, __shfl_xor_sync(0xFFFFFFFFu, kmin, o));
+            kmin = __reduce_min_sync(0xFFFFFFFFu, kmin);
             const int minS = (int)(kmin >> 16), bd = (int)(kmin & 0xFFFFu);
             if (minS >= 32767) { if (lane == 0) best[x] = -1; continue; }      // degenerate (outside the domain)
             // S[d] * (100 - uniq) < minS * 100   <=>   S[d] < T  with  T = ceil(minS * 100 / (100 - uniq))   (uniq < 100);
