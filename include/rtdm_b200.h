@@ -94,6 +94,16 @@ int rtdm_bm_compute(rtdm_bm *h, const uint8_t *left, size_t lstep, const uint8_t
 int rtdm_bm_compute_batch(rtdm_bm *h, int n, const uint8_t *left, size_t lstep, size_t lframe,
                           const uint8_t *right, size_t rstep, size_t rframe, int width, int height,
                           int16_t *disp, size_t dstep, size_t dframe);
+/* streaming variant of rtdm_bm_compute_batch: enqueues the copies and kernels and returns.  Two calls may be in
+ * flight (double-buffered staging), so the H2D of batch k+1 and the D2H of batch k-1 overlap the kernels of batch k;
+ * a third submit blocks until the oldest call has finished.  left / right / disp should be pinned host memory and
+ * must stay valid until rtdm_bm_wait (which drains everything submitted so far) returns. */
+int rtdm_bm_submit_batch(rtdm_bm *h, int n, const uint8_t *left, size_t lstep, size_t lframe,
+                         const uint8_t *right, size_t rstep, size_t rframe, int width, int height,
+                         int16_t *disp, size_t dstep, size_t dframe);
+int rtdm_bm_wait(rtdm_bm *h);
+/* waits for the OLDER of the submissions still in flight (the only one, if one): its `disp` is then complete */
+int rtdm_bm_wait_oldest(rtdm_bm *h);
 /* device variant: DEVICE pointers, asynchronous on `cuda_stream` (a cudaStream_t, may be NULL =
  * the handle's own stream).  Inputs/outputs stay resident in HBM. */
 int rtdm_bm_compute_device(rtdm_bm *h, int n, const uint8_t *left, size_t lstep, size_t lframe,

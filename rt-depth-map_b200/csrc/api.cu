@@ -89,8 +89,10 @@ struct rtdm_bm {
     int32_t *labels, *sizes, *runlen;
     uint16_t *tex;                                           // texture window sums (rpitch / rframe)
     // staging for the host entry points
-    uint8_t *dL, *dR;            size_t spitch, sframe;      // device copies of the inputs
+    uint8_t *dL, *dR;            size_t spitch, sframe;      // device copies of the inputs  (staging set 0)
     int16_t *dD;                 size_t dpitch, dframe;      // device copy of the output (elements)
+    uint8_t *dL2, *dR2; int16_t *dD2;                        // staging set 1 (rtdm_bm_submit_batch alternates)
+    cudaEvent_t done[2]; int busy[2]; unsigned seq;          // completion of the call that last used each set
     int launches;
     int lastW, lastH;
     int last_kernel;             // 1 = generic bm_sad.cu kernel, 2 = fast bm_sad2.cu kernel
@@ -155,6 +157,8 @@ extern "C" void rtdm_bm_destroy(rtdm_bm *h)
     cudaSetDevice(h->dev);
     cudaFree(h->Lp); cudaFree(h->Rp); cudaFree(h->raw); cudaFree(h->cost);
     cudaFree(h->labels); cudaFree(h->sizes); cudaFree(h->runlen); cudaFree(h->dL); cudaFree(h->dR); cudaFree(h->dD); cudaFree(h->tex);
+    cudaFree(h->dL2); cudaFree(h->dR2); cudaFree(h->dD2);
+    for (int i = 0; i < 2; i++) if (h->done[i]) cudaEventDestroy(h->done[i]);
     if (h->ev) { for (cudaEvent_t e : *h->ev) cudaEventDestroy(e); delete h->ev; }
     if (h->pev) { for (cudaEvent_t e : *h->pev) cudaEventDestroy(e); delete h->pev; }
     if (h->st) cudaStreamDestroy(h->st);
@@ -200,6 +204,11 @@ extern "C" int rtdm_bm_create(rtdm_bm **out, const rtdm_params *p, int max_width
     if (!rc) rc = dev_alloc(&h->dL, h->sframe * B);
     if (!rc) rc = dev_alloc(&h->dR, h->sframe * B);
     if (!rc) rc = dev_alloc(&h->dD, h->dframe * B);
+    if (!rc) rc = dev_alloc(&h->dL2, h->sframe * B);
+    if (!rc) rc = dev_alloc(&h->dR2, h->sframe * B);
+    if (!rc) rc = dev_alloc(&h->dD2, h->dframe * B);
+    for (int i = 0; i < 2 && !rc; i++)
+        rc = cudaEventCreateWithFlags(&h->done[i], cudaEventDisableTiming) == cudaSuccess ? 0 : -RTDM_EIO;
     if (rc) { rtdm_bm_destroy(h); return rc; }
     *out = h;
     return 0;
@@ -328,9 +337,31 @@ extern "C" int rtdm_bm_compute_device(rtdm_bm *h, int n, const uint8_t *left, si
     return bm_pipeline(h, n, L, R, width, height, out, st);
 }
 
-extern "C" int rtdm_bm_compute_batch(rtdm_bm *h, int n, const uint8_t *left, size_t lstep, size_t lframe,
-                                     const uint8_t *right, size_t rstep, size_t rframe, int width, int height,
-                                     int16_t *disp, size_t dstep, size_t dframe)
+extern "C" int rtdm_bm_wait(rtdm_bm *h)
+{
+    if (!h) return -RTDM_EINVAL;
+    RTDM_CUDA(cudaSetDevice(h->dev));
+    cudaError_t e0 = cudaStreamSynchronize(h->lane[1]);
+    { cudaError_t e = cudaStreamSynchronize(h->st); if (e0 == cudaSuccess) e0 = e; }
+    { cudaError_t e = cudaStreamSynchronize(h->lane[0]); if (e0 == cudaSuccess) e0 = e; }
+    h->busy[0] = h->busy[1] = 0;
+    RTDM_CUDA(e0);
+    return 0;
+}
+
+extern "C" int rtdm_bm_wait_oldest(rtdm_bm *h)
+{
+    if (!h) return -RTDM_EINVAL;
+    RTDM_CUDA(cudaSetDevice(h->dev));
+    const int newest = (int)((h->seq - 1u) & 1u), oldest = newest ^ 1;
+    const int set = h->busy[oldest] ? oldest : newest;       // only one in flight: that one
+    if (h->busy[set]) { RTDM_CUDA(cudaEventSynchronize(h->done[set])); h->busy[set] = 0; }
+    return 0;
+}
+
+extern "C" int rtdm_bm_submit_batch(rtdm_bm *h, int n, const uint8_t *left, size_t lstep, size_t lframe,
+                                    const uint8_t *right, size_t rstep, size_t rframe, int width, int height,
+                                    int16_t *disp, size_t dstep, size_t dframe)
 {
     if (!h || !left || !right || !disp) { set_error("bm_compute: null argument"); return -RTDM_EINVAL; }
     if (n < 1 || n > h->maxB || width > h->maxW || height > h->maxH || width < 1 || height < 1) {
@@ -346,28 +377,33 @@ extern "C" int rtdm_bm_compute_batch(rtdm_bm *h, int n, const uint8_t *left, siz
     if (const char *e = getenv("RTDM_BM_CHUNK")) chunk = std::max(1, std::min(n, atoi(e)));
     const int nchunks = (n + chunk - 1) / chunk;
     if (!h->pev) h->pev = new std::vector<cudaEvent_t>();
-    while ((int)h->pev->size() < 2 * nchunks) {
+    cudaStream_t s_in = h->lane[0], s_out = h->lane[1], s_cmp = h->st;
+    // staging set of this call; wait (host side) for the call that used it two submissions ago
+    const int set = (int)(h->seq++ & 1u);
+    if (h->busy[set]) { RTDM_CUDA(cudaEventSynchronize(h->done[set])); h->busy[set] = 0; }
+    uint8_t *sL = set ? h->dL2 : h->dL, *sR = set ? h->dR2 : h->dR;
+    int16_t *sD = set ? h->dD2 : h->dD;
+    while ((int)h->pev->size() < 4 * nchunks) {
         cudaEvent_t e;
         RTDM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         h->pev->push_back(e);
     }
-    cudaStream_t s_in = h->lane[0], s_out = h->lane[1], s_cmp = h->st;
     int rc = 0;
     for (int c = 0; c < nchunks && !rc; c++) {
         const int f0 = c * chunk, m = std::min(chunk, n - f0);
-        cudaEvent_t ev_in = (*h->pev)[2 * c], ev_done = (*h->pev)[2 * c + 1];
+        cudaEvent_t ev_in = (*h->pev)[2 * (set * nchunks + c)], ev_done = (*h->pev)[2 * (set * nchunks + c) + 1];
         const bool lpacked = lstep == (size_t)width && h->spitch == (size_t)width && lframe == h->sframe;
         const bool rpacked = rstep == (size_t)width && h->spitch == (size_t)width && rframe == h->sframe;
-        if (lpacked) RTDM_CUDA(cudaMemcpyAsync(h->dL + f0 * h->sframe, left + f0 * lframe, (size_t)m * h->sframe, cudaMemcpyHostToDevice, s_in));
-        if (rpacked) RTDM_CUDA(cudaMemcpyAsync(h->dR + f0 * h->sframe, right + f0 * rframe, (size_t)m * h->sframe, cudaMemcpyHostToDevice, s_in));
+        if (lpacked) RTDM_CUDA(cudaMemcpyAsync(sL + f0 * h->sframe, left + f0 * lframe, (size_t)m * h->sframe, cudaMemcpyHostToDevice, s_in));
+        if (rpacked) RTDM_CUDA(cudaMemcpyAsync(sR + f0 * h->sframe, right + f0 * rframe, (size_t)m * h->sframe, cudaMemcpyHostToDevice, s_in));
         for (int k = f0; k < f0 + m; k++) {
-            if (!lpacked) RTDM_CUDA(cudaMemcpy2DAsync(h->dL + k * h->sframe, h->spitch, left + k * lframe, lstep, width, height, cudaMemcpyHostToDevice, s_in));
-            if (!rpacked) RTDM_CUDA(cudaMemcpy2DAsync(h->dR + k * h->sframe, h->spitch, right + k * rframe, rstep, width, height, cudaMemcpyHostToDevice, s_in));
+            if (!lpacked) RTDM_CUDA(cudaMemcpy2DAsync(sL + k * h->sframe, h->spitch, left + k * lframe, lstep, width, height, cudaMemcpyHostToDevice, s_in));
+            if (!rpacked) RTDM_CUDA(cudaMemcpy2DAsync(sR + k * h->sframe, h->spitch, right + k * rframe, rstep, width, height, cudaMemcpyHostToDevice, s_in));
         }
         RTDM_CUDA(cudaEventRecord(ev_in, s_in));
         RTDM_CUDA(cudaStreamWaitEvent(s_cmp, ev_in, 0));
-        PlaneU8 L = {h->dL + (size_t)f0 * h->sframe, h->spitch, h->sframe}, R = {h->dR + (size_t)f0 * h->sframe, h->spitch, h->sframe};
-        PlaneS16 out = {h->dD + (size_t)f0 * h->dframe, h->dpitch, h->dframe};
+        PlaneU8 L = {sL + (size_t)f0 * h->sframe, h->spitch, h->sframe}, R = {sR + (size_t)f0 * h->sframe, h->spitch, h->sframe};
+        PlaneS16 out = {sD + (size_t)f0 * h->dframe, h->dpitch, h->dframe};
         const int prof = h->prof; h->prof = 0;          // stage events are for the device entry point only
         rc = bm_pipeline(h, m, L, R, width, height, out, s_cmp, f0);
         h->prof = prof;
@@ -375,17 +411,24 @@ extern "C" int rtdm_bm_compute_batch(rtdm_bm *h, int n, const uint8_t *left, siz
         RTDM_CUDA(cudaEventRecord(ev_done, s_cmp));
         RTDM_CUDA(cudaStreamWaitEvent(s_out, ev_done, 0));
         const bool dpacked = dstep == (size_t)width * 2 && h->dpitch == (size_t)width && dframe == h->dframe * 2;
-        if (dpacked) RTDM_CUDA(cudaMemcpyAsync((uint8_t *)disp + f0 * dframe, h->dD + f0 * h->dframe, (size_t)m * dframe, cudaMemcpyDeviceToHost, s_out));
+        if (dpacked) RTDM_CUDA(cudaMemcpyAsync((uint8_t *)disp + f0 * dframe, sD + f0 * h->dframe, (size_t)m * dframe, cudaMemcpyDeviceToHost, s_out));
         else for (int k = f0; k < f0 + m; k++)
-            RTDM_CUDA(cudaMemcpy2DAsync((uint8_t *)disp + k * dframe, dstep, h->dD + k * h->dframe, h->dpitch * 2,
+            RTDM_CUDA(cudaMemcpy2DAsync((uint8_t *)disp + k * dframe, dstep, sD + k * h->dframe, h->dpitch * 2,
                                         (size_t)width * 2, height, cudaMemcpyDeviceToHost, s_out));
     }
-    cudaError_t e0 = cudaStreamSynchronize(s_out);
-    { cudaError_t e = cudaStreamSynchronize(s_cmp); if (e0 == cudaSuccess) e0 = e; }
-    { cudaError_t e = cudaStreamSynchronize(s_in); if (e0 == cudaSuccess) e0 = e; }
-    if (rc) return rc;
-    RTDM_CUDA(e0);
+    if (rc) { rtdm_bm_wait(h); return rc; }
+    RTDM_CUDA(cudaEventRecord(h->done[set], s_out));          // after the last D2H of this call
+    h->busy[set] = 1;
     return 0;
+}
+
+extern "C" int rtdm_bm_compute_batch(rtdm_bm *h, int n, const uint8_t *left, size_t lstep, size_t lframe,
+                                     const uint8_t *right, size_t rstep, size_t rframe, int width, int height,
+                                     int16_t *disp, size_t dstep, size_t dframe)
+{
+    int rc = rtdm_bm_submit_batch(h, n, left, lstep, lframe, right, rstep, rframe, width, height, disp, dstep, dframe);
+    if (rc) return rc;
+    return rtdm_bm_wait(h);
 }
 
 extern "C" int rtdm_bm_compute(rtdm_bm *h, const uint8_t *left, size_t lstep, const uint8_t *right,

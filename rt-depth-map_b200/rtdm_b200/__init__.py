@@ -56,6 +56,9 @@ SIGNATURES = {
     "rtdm_bm_set_roi2": (_i, [_vp, _i, _i, _i, _i]),
     "rtdm_bm_compute": (_i, [_vp, _vp, _sz, _vp, _sz, _i, _i, _vp, _sz]),
     "rtdm_bm_compute_batch": (_i, [_vp, _i, _vp, _sz, _sz, _vp, _sz, _sz, _i, _i, _vp, _sz, _sz]),
+    "rtdm_bm_submit_batch": (_i, [_vp, _i, _vp, _sz, _sz, _vp, _sz, _sz, _i, _i, _vp, _sz, _sz]),
+    "rtdm_bm_wait": (_i, [_vp]),
+    "rtdm_bm_wait_oldest": (_i, [_vp]),
     "rtdm_bm_compute_device": (_i, [_vp, _i, _vp, _sz, _sz, _vp, _sz, _sz, _i, _i, _vp, _sz, _sz, _vp]),
     "rtdm_bm_last_launches": (_i, [_vp]),
     "rtdm_bm_debug_fetch": (_i, [_vp, _i, _vp, _sz]),
@@ -232,6 +235,23 @@ class CUDAMatcherKonolige(_MatcherBase):
         calls = _i()
         _check(self._l.rtdm_bm_stage_times(self._h, ms, C.byref(calls)))
         return dict(zip(self.STAGES, list(ms))), calls.value
+
+    def submit_batch(self, left, right, out):
+        """Streaming variant of compute_batch: (N, H, W) uint8 pinned arrays in, (N, H, W) int16 pinned array out;
+        returns immediately.  At most two submissions are in flight; call wait() before reading `out`."""
+        N, H, W = left.shape
+        if not (left.flags.c_contiguous and right.flags.c_contiguous and out.flags.c_contiguous):
+            raise RtdmError(-EINVAL, "submit_batch: contiguous arrays required")
+        _check(self._l.rtdm_bm_submit_batch(self._h, N, left.ctypes.data, W, W * H, right.ctypes.data, W, W * H, W, H,
+                                            out.ctypes.data, W * 2, W * H * 2))
+
+    def wait(self):
+        """Drains every submission."""
+        _check(self._l.rtdm_bm_wait(self._h))
+
+    def wait_oldest(self):
+        """Waits for the older of the (at most two) submissions in flight; its output array is then complete."""
+        _check(self._l.rtdm_bm_wait_oldest(self._h))
 
     def last_kernel(self) -> int:
         return self._l.rtdm_bm_last_kernel(self._h)

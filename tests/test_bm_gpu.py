@@ -161,6 +161,40 @@ def test_bm_720p_full_size_and_batch(gpu, orc, bm_kernel):
     assert np.array_equal(m.compute(Ls[1], Rs[1]), out[1])
 
 
+def test_bm_streaming_submissions(gpu, orc):
+    """rtdm_bm_submit_batch keeps two batches in flight on alternating staging buffers: every submission's output
+    must equal the blocking call's (and the oracle's), whatever the order of waits."""
+    from rtdm_b200 import synth
+    p = dict(preFilterCap=31, blockSize=9, minDisparity=0, textureThreshold=10, numDisparities=64,
+             uniquenessRatio=10, speckleWindowSize=100, speckleRange=32, disp12MaxDiff=1)
+    W, H, B, S = 320, 240, 4, 5
+    batches = []
+    for s in range(S):
+        fr = [synth.stereo_pair(W, H, 64, 7000 + 10 * s + i) for i in range(B)]
+        batches.append((np.stack([f[0] for f in fr]), np.stack([f[1] for f in fr])))
+    m = _mk(gpu, p, W, H, max_batch=B)
+    want = [m.compute_batch(L, R) for L, R in batches]
+    assert np.array_equal(want[0][0], orc.bm_compute(batches[0][0][0], batches[0][1][0], _orc_params(orc, p)))
+    outs = [np.full((B, H, W), 12345, np.int16) for _ in range(S)]
+    for s, (L, R) in enumerate(batches):
+        m.submit_batch(L, R, outs[s])
+        if s >= 1:
+            m.wait_oldest()
+            assert np.array_equal(outs[s - 1], want[s - 1]), s - 1
+    m.wait()
+    assert np.array_equal(outs[S - 1], want[S - 1])
+    # a blocking call after streaming, and wait() with nothing in flight
+    assert np.array_equal(m.compute_batch(*batches[2]), want[2])
+    m.wait(); m.wait_oldest()
+    # three submissions back to back: the third blocks on the first internally
+    for s in range(3):
+        outs[s][:] = 0
+        m.submit_batch(batches[s][0], batches[s][1], outs[s])
+    m.wait()
+    for s in range(3):
+        assert np.array_equal(outs[s], want[s]), s
+
+
 def test_bm_errors(gpu):
     with pytest.raises(gpu.RtdmError) as e:
         gpu.CUDAMatcherKonolige(None, None, 31, 12, 0, 10, 128, 128, 10, 100, 32, 1)
