@@ -17,6 +17,7 @@
 // then launch_median3 and launch_speckle (postproc.cu).
 // Every pixel belongs to exactly one chain per direction, so the S read-modify-write needs no atomics.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace rtdm {
 namespace {
@@ -212,6 +213,8 @@ struct PathArgs {
     int px, py;          // predecessor offset
     int first;           // 1: S = L (no read), 0: S += L
     int nchains;
+    uint2 *rec; size_t frame_rec;    // fused last path: per-pixel WTA records
+    int mul;                         // 100 - uniquenessRatio
 };
 
 __device__ __forceinline__ uint32_t min2(uint32_t a, uint32_t b) { return __vminu2(a, b); }
@@ -301,6 +304,220 @@ sgbm_path_kernel(PathArgs a)
         if (CPW == 1 && !more) break;
         alive = more;
         x = xn; y = yn; off = offn;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// path aggregation, specialised: D = 8 * LPC (LPC = 16: D 128, LPC = 8: D 64), every lane owns one uint4 = 4 words
+// = 8 disparities of its chain; 32 / LPC chains per warp.  Counted loop over the chain length, pointer stepping,
+// 128-bit loads / stores, the next pixel's C and S in flight while the current one is computed (two steps per
+// loop iteration, so the prefetch registers swap roles without moves).
+// MODE 0: first path (S = L), 1: S += L, 2: last path -- S + L stays in registers and the winner-take-all of the
+// pixel (argmin, uniqueness, the two neighbours for the sub-pixel fit) is taken right there: the finished S volume
+// is never written nor read back; an 8-byte record per pixel goes to sgbm_lr_kernel instead.
+// ------------------------------------------------------------------------------------------------
+template <int LPC>
+__device__ __forceinline__ uint32_t group_min_u32(uint32_t v, int grp)
+{
+    // min over the LPC lanes of each chain: one full-warp REDUX per group, the other groups contribute ~0
+    uint32_t r = 0u;
+#pragma unroll
+    for (int g = 0; g < 32 / LPC; g++) {
+        const uint32_t m = __reduce_min_sync(0xFFFFFFFFu, grp == g ? v : 0xFFFFFFFFu);
+        if (grp == g) r = m;
+    }
+    return r;
+}
+
+// record of one pixel: x = minS | code << 16 (code = best d, | 0x8000 when the uniqueness test failed, 0xFFFF when
+// the pixel is degenerate), y = S[d-1] | S[d+1] << 16
+template <int LPC>
+__device__ __forceinline__ uint2 wta_record(const uint32_t (&sv)[4], int sl, int grp, int mul)
+{
+    const uint32_t dbase = 8u * (uint32_t)sl;
+    uint32_t key = 0xFFFFFFFFu;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint32_t d0 = dbase + 2u * k;
+        key = min(key, min((sv[k] << 16) | d0, (sv[k] & 0xFFFF0000u) | (d0 + 1u)));      // first minimum wins
+    }
+    key = group_min_u32<LPC>(key, grp);
+    const uint32_t minS = key >> 16, bd = key & 0xFFFFu;
+    // smallest S outside [bd - 1, bd + 1]
+    uint32_t m2 = 0xFFFFFFFFu;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint32_t d0 = dbase + 2u * k;
+        uint32_t w = sv[k];
+        if (d0 - bd + 1u <= 2u) w |= 0x0000FFFFu;
+        if (d0 - bd + 2u <= 2u) w |= 0xFFFF0000u;
+        m2 = min2(m2, w);
+    }
+    const uint32_t other = group_min_u32<LPC>(min(m2 & 0xFFFFu, m2 >> 16), grp);
+    const bool viol = other * (uint32_t)mul < minS * 100u;            // exists d: S[d] * (100 - uniq) < minS * 100
+    // neighbours of the winner, fetched from their owner lanes (clamped at the ends; unused there)
+    uint32_t nb[2];
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        const uint32_t dq = q ? min(bd + 1u, 8u * LPC - 1u) : (bd > 0u ? bd - 1u : 0u);
+        const uint32_t wi = (dq >> 1) & 3u;
+        uint32_t v = wi == 0u ? sv[0] : (wi == 1u ? sv[1] : (wi == 2u ? sv[2] : sv[3]));
+        v = __shfl_sync(0xFFFFFFFFu, v, grp * LPC + (int)(dq >> 3));
+        nb[q] = (dq & 1u) ? v >> 16 : v & 0xFFFFu;
+    }
+    uint32_t code = bd | (viol ? 0x8000u : 0u);
+    if (minS >= 32767u) code = 0xFFFFu;
+    return make_uint2(minS | (code << 16), nb[0] | (nb[1] << 16));
+}
+
+template <int LPC, int MODE>
+__device__ __forceinline__ void path_step(uint4 &Lp, uint32_t &minLp, const uint4 c, const uint4 s, uint4 *sp, uint2 *rp,
+                                          bool live, int sl, int grp, uint32_t P1x2, uint32_t P2, int mul)
+{
+    uint32_t left = __shfl_up_sync(0xFFFFFFFFu, Lp.w, 1, LPC);
+    uint32_t right = __shfl_down_sync(0xFFFFFFFFu, Lp.x, 1, LPC);
+    if (sl == 0) left = 0x7FFF0000u;                       // L[-1] = MAX_COST (upper half is used)
+    if (sl == LPC - 1) right = 0x00007FFFu;                // L[D]  = MAX_COST (lower half is used)
+    const uint32_t dx2 = (P2 + minLp) * 0x00010001u;       // P2 + min_k L_r(p - r, k) < 65536
+    const uint32_t w[6] = {left, Lp.x, Lp.y, Lp.z, Lp.w, right};
+    const uint32_t cc[4] = {c.x, c.y, c.z, c.w};
+    uint32_t t[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint32_t lm1 = __byte_perm(w[k], w[k + 1], 0x5432);      // (L[d-1], L[d])   for the pair (d, d+1)
+        const uint32_t lp1 = __byte_perm(w[k + 1], w[k + 2], 0x5432);  // (L[d+1], L[d+2])
+        uint32_t v = __vimin3_u16x2(w[k + 1], __vadd2(lm1, P1x2), __vadd2(lp1, P1x2));
+        v = min2(v, dx2);
+        t[k] = __vsub2(__vadd2(v, cc[k]), dx2);
+    }
+    const uint32_t m = min2(min2(t[0], t[1]), min2(t[2], t[3]));
+    if (MODE == 0) {
+        if (live) *sp = make_uint4(t[0], t[1], t[2], t[3]);
+    } else {
+        const uint32_t sv[4] = {min2(__vadd2(s.x, t[0]), 0x7FFF7FFFu), min2(__vadd2(s.y, t[1]), 0x7FFF7FFFu),
+                                min2(__vadd2(s.z, t[2]), 0x7FFF7FFFu), min2(__vadd2(s.w, t[3]), 0x7FFF7FFFu)};
+        if (MODE == 1) {
+            if (live) *sp = make_uint4(sv[0], sv[1], sv[2], sv[3]);
+        } else {
+            const uint2 rec = wta_record<LPC>(sv, sl, grp, mul);
+            if (live && sl == 0) *rp = rec;
+        }
+    }
+    Lp = make_uint4(t[0], t[1], t[2], t[3]);
+    minLp = group_min_u32<LPC>(min(m & 0xFFFFu, m >> 16), grp);
+}
+
+template <int LPC, int MODE>
+__global__ void __launch_bounds__(128)
+sgbm_path4_kernel(PathArgs a)
+{
+    constexpr int CPW = 32 / LPC;
+    const int lane = threadIdx.x & 31, sl = lane % LPC, grp = lane / LPC;
+    const int chain = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * CPW + grp;
+    const int f = blockIdx.y;
+    const int sx = -a.px, sy = -a.py;
+    // chain start (a pixel whose predecessor lies outside the image) and length
+    int x = 0, y = 0, len = 0;
+    if (chain < a.nchains) {
+        const int nrow = sy != 0 ? a.W1 : 0;
+        if (chain < nrow) { x = chain; y = sy > 0 ? 0 : a.H - 1; }
+        else {
+            const int j = chain - nrow;
+            x = sx > 0 ? 0 : a.W1 - 1;
+            y = sy > 0 ? j + 1 : j;                        // skip the corner owned by the row set
+        }
+        const int nx = sx > 0 ? a.W1 - x : (sx < 0 ? x + 1 : 0x7FFFFFFF);
+        const int ny = sy > 0 ? a.H - y : (sy < 0 ? y + 1 : 0x7FFFFFFF);
+        len = min(nx, ny);
+    }
+    const int maxlen = __reduce_max_sync(0xFFFFFFFFu, len);
+    const uint32_t P1x2 = (uint32_t)a.P1 * 0x00010001u, P2 = (uint32_t)a.P2;
+    const int wordsD = 8 * LPC / 2;
+    const long long stepp = (long long)sy * a.W1 + sx;                        // pixels
+    const long long stepq = stepp * (wordsD / 4);                             // uint4 units
+    const size_t pix0 = (size_t)y * a.W1 + x;
+    const size_t off = (((size_t)f * a.frame_words) + pix0 * wordsD) / 4 + sl;
+    const uint4 *cp = reinterpret_cast<const uint4 *>(a.C) + off;
+    uint4 *sp = reinterpret_cast<uint4 *>(a.S) + off;
+    uint2 *rp = MODE == 2 ? a.rec + (size_t)f * a.frame_rec + pix0 : nullptr;
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    uint4 Lp = z;                                           // out-of-image predecessor: L = 0
+    uint32_t minLp = 0u;
+    uint4 c0 = len > 0 ? __ldg(cp) : z, s0 = (MODE != 0 && len > 0) ? *sp : z, c1, s1;
+    for (int i = 0; i < maxlen; i += 2) {
+        const bool m1 = i + 1 < len;
+        c1 = m1 ? __ldg(cp + stepq) : z;
+        s1 = (MODE != 0 && m1) ? sp[stepq] : z;
+        path_step<LPC, MODE>(Lp, minLp, c0, s0, sp, rp, i < len, sl, grp, P1x2, P2, a.mul);
+        const bool m2 = i + 2 < len;
+        c0 = m2 ? __ldg(cp + 2 * stepq) : z;
+        s0 = (MODE != 0 && m2) ? sp[2 * stepq] : z;
+        path_step<LPC, MODE>(Lp, minLp, c1, s1, sp + stepq, rp + stepp, m1, sl, grp, P1x2, P2, a.mul);
+        cp += 2 * stepq; sp += 2 * stepq;
+        if (MODE == 2) rp += 2 * stepp;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// left-right check and sub-pixel fit from the per-pixel records of the fused last path; one CTA per (row, frame).
+// Same arithmetic as the second half of sgbm_wta_kernel.
+// ------------------------------------------------------------------------------------------------
+struct LrArgs {
+    const uint2 *rec; size_t frame_rec;
+    PlaneS16 out;
+    int W, H, D, minD, minX1, maxX1, W1, d12;
+};
+
+__global__ void __launch_bounds__(256)
+sgbm_lr_kernel(LrArgs a)
+{
+    extern __shared__ __align__(16) uint8_t ws[];
+    uint32_t *key2 = reinterpret_cast<uint32_t *>(ws);                 // [W]  (minS << 16 | 0xFFFF - x1)
+    int16_t *dval = reinterpret_cast<int16_t *>(key2 + a.W);           // [W]  sub-pixel disparity or INV
+    int16_t *best = dval + a.W;                                        // [W1] integer disparity index
+    const int y = blockIdx.x, f = blockIdx.y;
+    const int INV = a.minD - 1, INVS = INV * 16;
+    for (int x = threadIdx.x; x < a.W; x += blockDim.x) { key2[x] = 0xFFFFFFFFu; dval[x] = (int16_t)INVS; }
+    __syncthreads();
+    const uint2 *rrow = a.rec + (size_t)f * a.frame_rec + (size_t)y * a.W1;
+    for (int x = threadIdx.x; x < a.W1; x += blockDim.x) {
+        const uint2 r = rrow[x];
+        const int minS = (int)(r.x & 0xFFFFu), code = (int)(r.x >> 16);
+        if (code == 0xFFFF) { best[x] = -1; continue; }
+        const int bd = code & 0x7FFF;
+        best[x] = (int16_t)bd;
+        if (code & 0x8000) continue;
+        const int x2 = x + a.minX1 - bd - a.minD;
+        if (x2 >= 0 && x2 < a.W) atomicMin(&key2[x2], ((uint32_t)minS << 16) | (uint32_t)(0xFFFF - x));
+        int d = bd;
+        if (0 < d && d < a.D - 1) {
+            const int sm = (int)(r.y & 0xFFFFu), sp = (int)(r.y >> 16);
+            const int den = max(sm + sp - 2 * minS, 1);
+            d = d * 16 + ((sm - sp) * 16 + den) / (den * 2);
+        } else d *= 16;
+        dval[x + a.minX1] = (int16_t)(d + a.minD * 16);
+    }
+    __syncthreads();
+    int16_t *orow = a.out.p + (size_t)f * a.out.frame + (size_t)y * a.out.pitch;
+    for (int x = threadIdx.x; x < a.W; x += blockDim.x) {
+        int d1 = dval[x];
+        if (x >= a.minX1 && x < a.maxX1 && d1 != INVS) {
+            const int _d = d1 >> 4, d_ = (d1 + 15) >> 4;
+            const int _x = x - _d, x_ = x - d_;
+            bool bad = true;
+            if (0 <= _x && _x < a.W) {
+                const uint32_t k = key2[_x];
+                const int d2 = (k == 0xFFFFFFFFu) ? INV : (int)best[0xFFFF - (int)(k & 0xFFFFu)] + a.minD;
+                bad = bad && d2 >= a.minD && abs(d2 - _d) > a.d12;
+            } else bad = false;
+            if (0 <= x_ && x_ < a.W) {
+                const uint32_t k = key2[x_];
+                const int d2 = (k == 0xFFFFFFFFu) ? INV : (int)best[0xFFFF - (int)(k & 0xFFFFu)] + a.minD;
+                bad = bad && d2 >= a.minD && abs(d2 - d_) > a.d12;
+            } else bad = false;
+            if (bad) d1 = INVS;
+        }
+        orow[x] = (int16_t)d1;
     }
 }
 
@@ -471,43 +688,70 @@ int launch_sgbm(const SgbmGeom &g, int n, PlaneU8 left, PlaneU8 right, PlaneS16 
     }
     if (launches) (*launches) += 3;
     RTDM_CUDA(cudaGetLastError());
-    // 4. paths
-    static const int dirs[8][2] = {{-1, 0}, {-1, -1}, {0, -1}, {1, -1}, {1, 0}, {-1, 1}, {0, 1}, {1, 1}};
-    const int ndirs = g.mode == RTDM_SGBM_MODE_HH ? 8 : 5;
+    // 4. paths.  D = 64 / 128: the 4-words-per-lane kernel, horizontal right-to-left path last and fused with the
+    // winner-take-all (S is complete there); other D: generic kernel + separate WTA
+    static const int dirs[8][2] = {{-1, 0}, {-1, -1}, {0, -1}, {1, -1}, {-1, 1}, {0, 1}, {1, 1}, {1, 0}};
+    const bool hh = g.mode == RTDM_SGBM_MODE_HH;
+    const int ndirs = hh ? 8 : 5;
     const int K2 = g.D <= 64 ? 1 : (g.D <= 128 ? 2 : 4);   // u16x2 words per lane (divides D/2 for any D % 16 == 0)
+    const bool fast = (g.D == 128 || g.D == 64) && !getenv("RTDM_SGBM_OLDPATH");
+    const bool fused = fast && g.uniq < 100 && !getenv("RTDM_SGBM_NOFUSE");
+    const size_t frame_rec = w.frame_planes / 8;            // the BT planes are dead by now: their buffer takes the records
     for (int k = 0; k < ndirs; k++) {
+        const int di = (!hh && k == 4) ? 7 : k;
         PathArgs a;
         a.C = reinterpret_cast<const uint32_t *>(w.C); a.S = reinterpret_cast<uint32_t *>(w.S); a.frame_words = frame_words;
-        a.W1 = g.W1; a.H = g.H; a.D = g.D; a.P1 = g.P1; a.P2 = g.P2; a.px = dirs[k][0]; a.py = dirs[k][1];
+        a.W1 = g.W1; a.H = g.H; a.D = g.D; a.P1 = g.P1; a.P2 = g.P2; a.px = dirs[di][0]; a.py = dirs[di][1];
         a.first = (k == 0);
+        a.rec = reinterpret_cast<uint2 *>(w.planes); a.frame_rec = frame_rec; a.mul = 100 - g.uniq;
         const int sx = -a.px, sy = -a.py;
         a.nchains = (sy != 0 ? g.W1 : 0) + (sx != 0 ? (sy != 0 ? g.H - 1 : g.H) : 0);
-        // sub-warp chains where D/2 words split evenly into 8 or 16 lanes of 4 words (D = 64, 128)
-        // (only when there are enough chains to still fill the machine: ~9.5k resident warps)
-        const bool many = (long long)a.nchains * n >= 2 * 9472;
-        if (g.D == 128 && many) { sgbm_path_kernel<4, 16><<<dim3(cdiv(a.nchains, 8), n), 128, 0, st>>>(a); }
-        else if (g.D == 64 && many) { sgbm_path_kernel<4, 8><<<dim3(cdiv(a.nchains, 16), n), 128, 0, st>>>(a); }
-        else {
-            dim3 grid(cdiv(a.nchains, 4), n);
-            switch (K2) {
-                case 1: sgbm_path_kernel<1, 32><<<grid, 128, 0, st>>>(a); break;
-                case 2: sgbm_path_kernel<2, 32><<<grid, 128, 0, st>>>(a); break;
-                default: sgbm_path_kernel<4, 32><<<grid, 128, 0, st>>>(a); break;
+        if (fast) {
+            const int mode = k == 0 ? 0 : ((fused && k == ndirs - 1) ? 2 : 1);
+            const int cpc = g.D == 128 ? 8 : 16;             // chains per 128-thread CTA
+            const dim3 grid(cdiv(a.nchains, cpc), n);
+            if (g.D == 128) {
+                if (mode == 0) sgbm_path4_kernel<16, 0><<<grid, 128, 0, st>>>(a);
+                else if (mode == 1) sgbm_path4_kernel<16, 1><<<grid, 128, 0, st>>>(a);
+                else sgbm_path4_kernel<16, 2><<<grid, 128, 0, st>>>(a);
+            } else {
+                if (mode == 0) sgbm_path4_kernel<8, 0><<<grid, 128, 0, st>>>(a);
+                else if (mode == 1) sgbm_path4_kernel<8, 1><<<grid, 128, 0, st>>>(a);
+                else sgbm_path4_kernel<8, 2><<<grid, 128, 0, st>>>(a);
+            }
+        } else {
+            // sub-warp chains where D/2 words split evenly into 8 or 16 lanes of 4 words (D = 64, 128)
+            // (only when there are enough chains to still fill the machine: ~9.5k resident warps)
+            const bool many = (long long)a.nchains * n >= 2 * 9472;
+            if (g.D == 128 && many) { sgbm_path_kernel<4, 16><<<dim3(cdiv(a.nchains, 8), n), 128, 0, st>>>(a); }
+            else if (g.D == 64 && many) { sgbm_path_kernel<4, 8><<<dim3(cdiv(a.nchains, 16), n), 128, 0, st>>>(a); }
+            else {
+                dim3 grid(cdiv(a.nchains, 4), n);
+                switch (K2) {
+                    case 1: sgbm_path_kernel<1, 32><<<grid, 128, 0, st>>>(a); break;
+                    case 2: sgbm_path_kernel<2, 32><<<grid, 128, 0, st>>>(a); break;
+                    default: sgbm_path_kernel<4, 32><<<grid, 128, 0, st>>>(a); break;
+                }
             }
         }
         if (launches) (*launches)++;
     }
     RTDM_CUDA(cudaGetLastError());
-    // 5. WTA
-    {
+    // 5. WTA (or, after the fused last path, only the left-right check)
+    const size_t smem = (size_t)g.W * 4 + (size_t)g.W * 2 + (size_t)g.W1 * 2 + 16;
+    if (fused) {
+        LrArgs a;
+        a.rec = reinterpret_cast<const uint2 *>(w.planes); a.frame_rec = frame_rec; a.out = out;
+        a.W = g.W; a.H = g.H; a.D = g.D; a.minD = g.minD; a.minX1 = g.minX1; a.maxX1 = g.maxX1; a.W1 = g.W1; a.d12 = g.d12;
+        sgbm_lr_kernel<<<dim3(g.H, n), 256, smem, st>>>(a);
+    } else {
         WtaArgs a;
         a.S = reinterpret_cast<const uint16_t *>(w.S); a.frame_vol = w.frame_vol; a.out = out;
         a.W = g.W; a.H = g.H; a.D = g.D; a.minD = g.minD; a.minX1 = g.minX1; a.maxX1 = g.maxX1; a.W1 = g.W1;
         a.uniq = g.uniq; a.d12 = g.d12;
-        size_t smem = (size_t)g.W * 4 + (size_t)g.W * 2 + (size_t)g.W1 * 2 + 16;
         sgbm_wta_kernel<<<dim3(g.H, n), 256, smem, st>>>(a);
-        if (launches) (*launches)++;
     }
+    if (launches) (*launches)++;
     RTDM_CUDA(cudaGetLastError());
     return 0;
 }
