@@ -173,6 +173,120 @@ sgbm_cost_hsum_kernel(CostArgs a)
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fused cost kernel (D a power of two, 16..256): BT pixel cost -> horizontal window -> vertical window + P2 -> C,
+// without the Hs volume.  CTA = (tile of TXk = (256 / D2) * CSEG cost columns, band of rows, frame); a thread owns
+// one disparity pair and CSEG adjacent columns.  Per row it computes the CSEG + 2h pixel costs of its columns
+// (sliding horizontal sum in registers) and pushes the CSEG horizontal sums into per-column vertical rings that
+// also live in registers (BS x CSEG words); a row of C leaves once the ring is full.  Rows and columns are
+// replicate-clamped exactly like the two-kernel path.  The row's left / right (value, lo, hi) arrays are staged
+// in shared memory, double buffered: one barrier per row.
+// ------------------------------------------------------------------------------------------------
+constexpr int CSEG = 8;
+constexpr int RSTRIDE = 416;            // u16 elements per reversed right array copy (>= TXk + 2h + D + 4)
+
+template <int BS>
+__global__ void __launch_bounds__(256, 2)
+sgbm_cost_fused_kernel(CostArgs a, uint16_t *Cvol, uint32_t P2x2, int BY)
+{
+    constexpr int h = BS / 2, NC = CSEG + 2 * h;
+    extern __shared__ __align__(16) uint8_t cs[];
+    const int D2 = a.D / 2, nseg = 256 / D2, TXk = nseg * CSEG, NXC = TXk + 2 * h;
+    const int dp = threadIdx.x % D2, seg = threadIdx.x / D2;
+    const int x0 = blockIdx.x * TXk, y0 = blockIdx.y * BY, y1 = min(y0 + BY, a.H), f = blockIdx.z;
+    const int maxD = a.minD + a.D;
+    const int cl0 = clampi(x0 - h, 0, a.W1 - 1), cl1 = clampi(x0 + TXk - 1 + h, 0, a.W1 - 1);
+    const int xr_hi = cl1 + a.minX1 - a.minD, xr_lo = cl0 + a.minX1 - (maxD - 1);
+    const int NRP = (xr_hi - xr_lo + 1 + 3) & ~1;
+    // per buffer: left [NXC][8] words (value, lo, hi, -, value', lo', hi', -) splatted; right [6][2][RSTRIDE] u16
+    const size_t lbytes = (size_t)NXC * 32, rbytes = (size_t)12 * RSTRIDE * 2, bbytes = lbytes + rbytes;
+    const uint8_t *pf = a.planes + (size_t)f * a.frame_planes;
+    const size_t comp = (size_t)a.H * a.Wp;
+
+    auto stage = [&](int row, int b) {
+        const uint8_t *prow = pf + (size_t)row * a.Wp;
+        uint32_t *lsw = reinterpret_cast<uint32_t *>(cs + b * bbytes);
+        uint16_t *rv = reinterpret_cast<uint16_t *>(cs + b * bbytes + lbytes);
+        for (int i = threadIdx.x; i < NXC * 6; i += 256) {
+            const int c = i / 6, k = i - c * 6;
+            const int xl = clampi(x0 - h + c, 0, a.W1 - 1) + a.minX1;
+            lsw[c * 8 + k + (k >= 3)] = (uint32_t)prow[(size_t)k * comp + xl] * 0x00010001u;
+        }
+        for (int arr = 0; arr < 6; arr++) {
+            const uint8_t *src = prow + (size_t)(6 + arr) * comp;
+            uint16_t *d0 = rv + (size_t)(arr * 2) * RSTRIDE, *d1 = d0 + RSTRIDE;
+            for (int e = threadIdx.x; e <= NRP; e += 256) {
+                const uint16_t v = src[clampi(xr_hi - e, 0, a.W - 1)];
+                if (e < NRP) d0[e] = v;
+                if (e >= 1) d1[e - 1] = v;
+            }
+        }
+    };
+
+    uint32_t ring[BS][CSEG], V[CSEG];
+#pragma unroll
+    for (int j = 0; j < CSEG; j++) {
+        V[j] = P2x2;
+#pragma unroll
+        for (int u = 0; u < BS; u++) ring[u][j] = 0u;
+    }
+    const int nrows = (y1 - y0) + 2 * h;
+    // e = E0 - xc is the reversed index of the right pixel of cost column xc at disparity pair dp
+    const int E0 = xr_hi - (a.minX1 - a.minD) + 2 * dp;
+    uint32_t *Cf = reinterpret_cast<uint32_t *>(Cvol + (size_t)f * a.frame_vol);
+    stage(clampi(y0 - h, 0, a.H - 1), 0);
+    __syncthreads();
+    for (int base = 0; base < nrows; base += BS) {
+#pragma unroll
+        for (int u = 0; u < BS; u++) {
+            const int i = base + u;
+            if (i < nrows) {                                        // CTA-uniform
+                const int b = i & 1;
+                if (i + 1 < nrows) stage(clampi(y0 - h + i + 1, 0, a.H - 1), b ^ 1);
+                const uint4 *lsw = reinterpret_cast<const uint4 *>(cs + b * bbytes) + (size_t)seg * CSEG * 2;
+                const uint8_t *rvb = cs + b * bbytes + lbytes;
+                uint32_t hc[BS], hs = 0u;
+#pragma unroll
+                for (int c = 0; c < NC; c++) {
+                    const int xc = clampi(x0 - h + seg * CSEG + c, 0, a.W1 - 1);
+                    const int e = E0 - xc, cpar = e & 1;
+                    const uint32_t *rw = reinterpret_cast<const uint32_t *>(rvb + (size_t)cpar * (RSTRIDE * 2) + (size_t)(e - cpar) * 2);
+                    const uint4 l0 = lsw[c * 2], l1 = lsw[c * 2 + 1];
+                    uint32_t cost;
+                    {
+                        const uint32_t v = rw[0], v0 = rw[RSTRIDE], v1 = rw[2 * RSTRIDE];
+                        const uint32_t c0 = __vimax3_s16x2(0u, __vsub2(l0.x, v1), __vsub2(v0, l0.x));
+                        const uint32_t c1 = __vimax3_s16x2(0u, __vsub2(v, l0.z), __vsub2(l0.y, v));
+                        cost = __vmins2(c0, c1);
+                    }
+                    {
+                        const uint32_t v = rw[3 * RSTRIDE], v0 = rw[4 * RSTRIDE], v1 = rw[5 * RSTRIDE];
+                        const uint32_t c0 = __vimax3_s16x2(0u, __vsub2(l1.x, v1), __vsub2(v0, l1.x));
+                        const uint32_t c1 = __vimax3_s16x2(0u, __vsub2(v, l1.z), __vsub2(l1.y, v));
+                        cost += (__vmins2(c0, c1) >> 2) & 0x3FFF3FFFu;
+                    }
+                    if (c >= BS) hs -= hc[c % BS];
+                    hs += cost;
+                    hc[c % BS] = cost;
+                    if (c >= 2 * h) {
+                        const int j = c - 2 * h;
+                        V[j] += hs - ring[u][j];
+                        ring[u][j] = hs;
+                    }
+                }
+                if (i >= 2 * h) {
+                    const int yo = y0 + i - 2 * h;
+                    uint32_t *dst = Cf + ((size_t)yo * a.W1 + x0 + seg * CSEG) * D2 + dp;
+#pragma unroll
+                    for (int j = 0; j < CSEG; j++)
+                        if (x0 + seg * CSEG + j < a.W1) dst[(size_t)j * D2] = V[j];
+                }
+                __syncthreads();
+            }
+        }
+    }
+}
+
 // C = P2 + sum over clamped rows y-h..y+h of Hs.  One thread per u16x2 word column and band of rows: the
 // 2h+1 window values live in a register ring (compile-time size), so every Hs word is read once.
 template <int BS>
@@ -657,6 +771,32 @@ int launch_sgbm(const SgbmGeom &g, int n, PlaneU8 left, PlaneU8 right, PlaneS16 
     const int h = g.bs / 2;
     // 1. planes
     sgbm_planes_kernel<<<dim3(cdiv(g.W, 256), g.H, 2 * n), 256, 0, st>>>(left, right, w.planes, w.frame_planes, g.W, g.H, Wp, g.ftzero);
+    const size_t row_words = (size_t)g.W1 * g.D / 2, frame_words = w.frame_vol / 2;
+    const bool pow2D = (g.D & (g.D - 1)) == 0 && g.D >= 16 && g.D <= 256;
+    if (pow2D && g.bs <= 7 && !getenv("RTDM_SGBM_OLDCOST")) {       // larger windows: the register rings would spill
+        // 2+3. fused: BT cost, horizontal and vertical windows, + P2 -> C
+        CostArgs a;
+        a.planes = w.planes; a.frame_planes = w.frame_planes;
+        a.Hs = nullptr; a.frame_vol = w.frame_vol;
+        a.W = g.W; a.H = g.H; a.Wp = Wp; a.D = g.D; a.minD = g.minD; a.h = h; a.minX1 = g.minX1; a.W1 = g.W1;
+        const int D2 = g.D / 2, TXk = (256 / D2) * CSEG, NXC = TXk + 2 * h, BY = 48;
+        const size_t smem = 2 * ((size_t)NXC * 32 + (size_t)12 * RSTRIDE * 2);
+        const dim3 grid(cdiv(g.W1, TXk), cdiv(g.H, BY), n);
+        const uint32_t p2 = (uint32_t)g.P2 * 0x00010001u;
+        uint16_t *Cv = reinterpret_cast<uint16_t *>(w.C);
+#define RTDM_COST_CASE(BS_)                                                                                             \
+        case BS_:                                                                                                       \
+            RTDM_CUDA(cudaFuncSetAttribute(sgbm_cost_fused_kernel<BS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            sgbm_cost_fused_kernel<BS_><<<grid, 256, smem, st>>>(a, Cv, p2, BY);                                        \
+            break;
+        switch (g.bs) {
+            RTDM_COST_CASE(1) RTDM_COST_CASE(3) RTDM_COST_CASE(5)
+            default: RTDM_CUDA(cudaFuncSetAttribute(sgbm_cost_fused_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                     sgbm_cost_fused_kernel<7><<<grid, 256, smem, st>>>(a, Cv, p2, BY); break;
+        }
+#undef RTDM_COST_CASE
+        if (launches) (*launches) += 2;
+    } else {
     // 2. BT cost + horizontal window -> Hs (stored in the S volume, which is rewritten by the first path)
     {
         CostArgs a;
@@ -670,7 +810,6 @@ int launch_sgbm(const SgbmGeom &g, int n, PlaneU8 left, PlaneU8 right, PlaneS16 
         sgbm_cost_hsum_kernel<<<dim3(cdiv(g.W1, TX), g.H, n), 256, smem, st>>>(a);
     }
     // 3. vertical window + P2 -> C
-    const size_t row_words = (size_t)g.W1 * g.D / 2, frame_words = w.frame_vol / 2;
     {
         const int band = 90;
         dim3 grid((unsigned)((row_words + 255) / 256), cdiv(g.H, band), n);
@@ -687,6 +826,7 @@ int launch_sgbm(const SgbmGeom &g, int n, PlaneU8 left, PlaneU8 right, PlaneS16 
         }
     }
     if (launches) (*launches) += 3;
+    }
     RTDM_CUDA(cudaGetLastError());
     // 4. paths.  D = 64 / 128: the 4-words-per-lane kernel, horizontal right-to-left path last and fused with the
     // winner-take-all (S is complete there); other D: generic kernel + separate WTA
