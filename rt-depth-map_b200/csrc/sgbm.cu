@@ -18,6 +18,7 @@
 // Every pixel belongs to exactly one chain per direction, so the S read-modify-write needs no atomics.
 #include "common.cuh"
 #include <stdlib.h>
+#include <algorithm>
 
 namespace rtdm {
 namespace {
@@ -174,114 +175,224 @@ sgbm_cost_hsum_kernel(CostArgs a)
 }
 
 // ------------------------------------------------------------------------------------------------
-// Fused cost kernel (D a power of two, 16..256): BT pixel cost -> horizontal window -> vertical window + P2 -> C,
-// without the Hs volume.  CTA = (tile of TXk = (256 / D2) * CSEG cost columns, band of rows, frame); a thread owns
+// Fused cost path (D = 64, 128, 256; blockSize <= 7): BT pixel cost -> horizontal window -> vertical window + P2
+// -> C, without the Hs volume.
+//
+// sgbm_planes2_kernel writes the per-pixel (value, lo, hi) of both BT planes in the form the cost kernel consumes,
+// so that staging a row is nothing but 16-byte asynchronous copies:
+//   left  GL[y][x1 + 8][8 words]: (value, -value, lo, -hi) of plane 0 then plane 1, each splatted to s16x2, per COST column
+//         x1 (replicated 8 columns beyond both ends: the window's column clamp becomes a plain read);
+//   right GR[y][6 arrays: value, lo, -hi per plane][2 copies][WR] s16, REVERSED (index eg = W - 1 + 16 - x, so a larger disparity is a larger
+//         address) and stored twice, copy 1 shifted by one element, so that any (d, d + 1) pair is one aligned word.
+// sgbm_cost_fused_kernel: CTA = (tile of TXk = (256 / D2) * CSEG cost columns, band of rows, frame); a thread owns
 // one disparity pair and CSEG adjacent columns.  Per row it computes the CSEG + 2h pixel costs of its columns
 // (sliding horizontal sum in registers) and pushes the CSEG horizontal sums into per-column vertical rings that
-// also live in registers (BS x CSEG words); a row of C leaves once the ring is full.  Rows and columns are
-// replicate-clamped exactly like the two-kernel path.  The row's left / right (value, lo, hi) arrays are staged
-// in shared memory, double buffered: one barrier per row.
+// also live in registers (BS x CSEG words); a row of C leaves once the ring is full.  Rows are replicate-clamped
+// by index; the two tiles at the image's left / right end take the EDGE variant that clamps the cost column.
+// Rows are staged with cp.async two rows ahead, double buffered: one barrier per row, no staging arithmetic.
 // ------------------------------------------------------------------------------------------------
 constexpr int CSEG = 8;
-constexpr int RSTRIDE = 416;            // u16 elements per reversed right array copy (>= TXk + 2h + D + 4)
+constexpr int RSTRIDE = 432;            // u16 elements per staged right array copy (>= TXk + 2h + D + 16)
+constexpr int PADL = 8, PADR = 16;
+
+struct Cost2Args {
+    const uint8_t *planes; size_t frame_planes;   // per frame: GL block then GR block
+    uint16_t *C; size_t frame_vol;
+    int W, H, D, minD, minX1, W1, LW, WR, BY;
+    uint32_t P2x2;
+};
+
+__global__ void __launch_bounds__(256)
+sgbm_planes2_kernel(PlaneU8 left, PlaneU8 right, uint8_t *planes, size_t frame_planes, int W, int H, int ftzero,
+                    int minX1, int W1, int LW, int WR)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const int f = blockIdx.z >> 1, img = blockIdx.z & 1;
+    if (x >= W) return;
+    const uint8_t *src = img ? right.p + (size_t)f * right.frame : left.p + (size_t)f * left.frame;
+    const size_t sp = img ? right.pitch : left.pitch;
+    uint32_t val[6];
+#pragma unroll
+    for (int pl = 0; pl < 2; pl++) {
+        const int v = bt_plane_value(src, sp, W, H, x, y, pl, ftzero);
+        const int a = x > 0 ? (v + bt_plane_value(src, sp, W, H, x - 1, y, pl, ftzero)) / 2 : v;
+        const int b = x < W - 1 ? (v + bt_plane_value(src, sp, W, H, x + 1, y, pl, ftzero)) / 2 : v;
+        val[pl * 3 + 0] = (uint32_t)v; val[pl * 3 + 1] = (uint32_t)min(min(a, b), v); val[pl * 3 + 2] = (uint32_t)max(max(a, b), v);
+    }
+    const auto neg16 = [](uint32_t v) { return (0u - v) & 0xFFFFu; };
+    uint8_t *pf = planes + (size_t)f * frame_planes;
+    if (img == 0) {
+        const int x1 = x - minX1;
+        if (x1 < 0 || x1 >= W1) return;
+        uint4 *row = reinterpret_cast<uint4 *>(pf) + (size_t)y * LW * 2;
+        const uint4 q0 = make_uint4(val[0] * 0x00010001u, neg16(val[0]) * 0x00010001u, val[1] * 0x00010001u, neg16(val[2]) * 0x00010001u);
+        const uint4 q1 = make_uint4(val[3] * 0x00010001u, neg16(val[3]) * 0x00010001u, val[4] * 0x00010001u, neg16(val[5]) * 0x00010001u);
+        const int k0 = x1 == 0 ? 0 : x1 + PADL, k1 = x1 == W1 - 1 ? LW - 1 : x1 + PADL;
+        for (int k = k0; k <= k1; k++) { row[k * 2] = q0; row[k * 2 + 1] = q1; }
+    } else {
+        uint16_t *row = reinterpret_cast<uint16_t *>(pf + (size_t)H * LW * 32) + (size_t)y * 12 * WR;
+        const int eg = W - 1 + PADR - x;
+        const int k0 = x == W - 1 ? 0 : eg, k1 = x == 0 ? WR : eg;        // copy 1 holds index k - 1, so k may reach WR
+        val[2] = neg16(val[2]); val[5] = neg16(val[5]);                    // the hi arrays are stored negated
+#pragma unroll
+        for (int arr = 0; arr < 6; arr++) {
+            uint16_t *c0 = row + (size_t)(arr * 2) * WR, *c1 = c0 + WR;
+            for (int k = k0; k <= k1; k++) {
+                if (k < WR) c0[k] = (uint16_t)val[arr];
+                if (k >= 1) c1[k - 1] = (uint16_t)val[arr];
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
+{
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// l = (u, -u, lo(u), -hi(u)) of the left pixel (splatted), rw -> (v, lo(v), -hi(v)) arrays of the right pixel pair:
+// cost = min(max(0, u - hi(v), lo(v) - u), max(0, v - hi(u), lo(u) - v)), 5 packed ops + the negation of v
+__device__ __forceinline__ uint32_t bt_plane2(const uint4 l, const uint32_t v, const uint32_t v0, const uint32_t nv1)
+{
+    const uint32_t nv = __vadd2(~v, 0x00010001u);
+    const uint32_t c0 = __viaddmax_s16x2_relu(v0, l.y, __vadd2(l.x, nv1));
+    const uint32_t c1 = __viaddmax_s16x2_relu(l.z, nv, __vadd2(v, l.w));
+    return __vmins2(c0, c1);
+}
+
+__device__ __forceinline__ uint32_t bt_cost2(const uint4 l0, const uint4 l1, const uint32_t *rw)
+{
+    const uint32_t m0 = bt_plane2(l0, rw[0], rw[RSTRIDE], rw[2 * RSTRIDE]);
+    const uint32_t m1 = bt_plane2(l1, rw[3 * RSTRIDE], rw[4 * RSTRIDE], rw[5 * RSTRIDE]);
+    return m0 + ((m1 >> 2) & 0x3FFF3FFFu);
+}
 
 template <int BS>
 __global__ void __launch_bounds__(256, 2)
-sgbm_cost_fused_kernel(CostArgs a, uint16_t *Cvol, uint32_t P2x2, int BY)
+sgbm_cost_fused_kernel(Cost2Args a)
 {
     constexpr int h = BS / 2, NC = CSEG + 2 * h;
     extern __shared__ __align__(16) uint8_t cs[];
     const int D2 = a.D / 2, nseg = 256 / D2, TXk = nseg * CSEG, NXC = TXk + 2 * h;
     const int dp = threadIdx.x % D2, seg = threadIdx.x / D2;
-    const int x0 = blockIdx.x * TXk, y0 = blockIdx.y * BY, y1 = min(y0 + BY, a.H), f = blockIdx.z;
-    const int maxD = a.minD + a.D;
-    const int cl0 = clampi(x0 - h, 0, a.W1 - 1), cl1 = clampi(x0 + TXk - 1 + h, 0, a.W1 - 1);
-    const int xr_hi = cl1 + a.minX1 - a.minD, xr_lo = cl0 + a.minX1 - (maxD - 1);
-    const int NRP = (xr_hi - xr_lo + 1 + 3) & ~1;
-    // per buffer: left [NXC][8] words (value, lo, hi, -, value', lo', hi', -) splatted; right [6][2][RSTRIDE] u16
-    const size_t lbytes = (size_t)NXC * 32, rbytes = (size_t)12 * RSTRIDE * 2, bbytes = lbytes + rbytes;
+    const int x0 = blockIdx.x * TXk, y0 = blockIdx.y * a.BY, y1 = min(y0 + a.BY, a.H), f = blockIdx.z;
+    const bool edge = x0 - h < 0 || x0 + TXk - 1 + h > a.W1 - 1;
+    const int cl1 = clampi(x0 + TXk - 1 + h, 0, a.W1 - 1);
+    const int xr_hi = cl1 + a.minX1 - a.minD;                          // right pixel of reversed index e = 0
+    // e = E0 - xc: reversed index of the right pixel of cost column xc at this thread's disparity pair
+    const int E0 = xr_hi - (a.minX1 - a.minD) + 2 * dp;
+    const int xs = x0 - h + seg * CSEG;                                // this thread's first cost column (unclamped)
+    const int p0 = (E0 - xs) & 1;                                      // CTA-uniform: parity of e at even c
+    // staged copy A serves even c (pairs start at parity p0), copy B odd c.  Global sources, 8-element aligned:
+    const int eg0 = a.W - 1 + PADR - xr_hi;
+    const int sA = eg0 + p0, sB = eg0 + 1 - p0;
+    const int srcA = sA & 1, srcB = sB & 1;                            // which global copy
+    const int iA = (sA - srcA) & ~7, iB = (sB - srcB) & ~7;            // first global element staged
+    const int dA = sA - srcA - iA, dB = sB - srcB - iB;                // staged index of e = p0 / e = 1 - p0
+    const int nelem = (cl1 - clampi(x0 - h, 0, a.W1 - 1)) + a.D + 2;   // elements needed from e = 0
+    const int NRC = (nelem + 7 + 7) / 8;                               // chunks per array copy (dA, dB <= 6)
+    const int NL = NXC * 2;
+    const int lbytes = NXC * 32, rbytes = 12 * RSTRIDE * 2, bbytes = lbytes + rbytes;
     const uint8_t *pf = a.planes + (size_t)f * a.frame_planes;
-    const size_t comp = (size_t)a.H * a.Wp;
-
-    auto stage = [&](int row, int b) {
-        const uint8_t *prow = pf + (size_t)row * a.Wp;
-        uint32_t *lsw = reinterpret_cast<uint32_t *>(cs + b * bbytes);
-        uint16_t *rv = reinterpret_cast<uint16_t *>(cs + b * bbytes + lbytes);
-        for (int i = threadIdx.x; i < NXC * 6; i += 256) {
-            const int c = i / 6, k = i - c * 6;
-            const int xl = clampi(x0 - h + c, 0, a.W1 - 1) + a.minX1;
-            lsw[c * 8 + k + (k >= 3)] = (uint32_t)prow[(size_t)k * comp + xl] * 0x00010001u;
+    const uint8_t *gl = pf + (size_t)(x0 - h + PADL) * 32;
+    const uint8_t *gr = pf + (size_t)a.H * a.LW * 32;
+    const size_t lrow = (size_t)a.LW * 32, rrow = (size_t)12 * a.WR * 2;
+    // this thread's (at most two) 16-byte chunks of a row
+    int goff[2], soff[2];
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        const int t = threadIdx.x + q * 256;
+        goff[q] = -1; soff[q] = 0;
+        if (t < NL) { goff[q] = t * 16; soff[q] = t * 16; }
+        else if (t < NL + 12 * NRC) {
+            const int r = t - NL, ac = r / NRC, ch = r - ac * NRC, arr = ac >> 1, cpy = ac & 1;
+            const int gcopy = cpy ? srcB : srcA, gi = (cpy ? iB : iA) + ch * 8;
+            goff[q] = (1 << 30) | (((arr * 2 + gcopy) * a.WR + gi) * 2);
+            soff[q] = lbytes + (ac * RSTRIDE + ch * 8) * 2;
         }
-        for (int arr = 0; arr < 6; arr++) {
-            const uint8_t *src = prow + (size_t)(6 + arr) * comp;
-            uint16_t *d0 = rv + (size_t)(arr * 2) * RSTRIDE, *d1 = d0 + RSTRIDE;
-            for (int e = threadIdx.x; e <= NRP; e += 256) {
-                const uint16_t v = src[clampi(xr_hi - e, 0, a.W - 1)];
-                if (e < NRP) d0[e] = v;
-                if (e >= 1) d1[e - 1] = v;
+    }
+    auto stage = [&](int row, int b) {
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            if (goff[q] >= 0) {
+                const uint8_t *src = (goff[q] >> 30) ? gr + (size_t)row * rrow + (goff[q] & 0x3FFFFFFF) : gl + (size_t)row * lrow + goff[q];
+                cp_async16(cs + b * bbytes + soff[q], src);
             }
         }
+        cp_async_commit();
     };
 
     uint32_t ring[BS][CSEG], V[CSEG];
 #pragma unroll
     for (int j = 0; j < CSEG; j++) {
-        V[j] = P2x2;
+        V[j] = a.P2x2;
 #pragma unroll
         for (int u = 0; u < BS; u++) ring[u][j] = 0u;
     }
     const int nrows = (y1 - y0) + 2 * h;
-    // e = E0 - xc is the reversed index of the right pixel of cost column xc at disparity pair dp
-    const int E0 = xr_hi - (a.minX1 - a.minD) + 2 * dp;
-    uint32_t *Cf = reinterpret_cast<uint32_t *>(Cvol + (size_t)f * a.frame_vol);
+    // byte offsets inside a buffer: even c reads A at ta - 2c, odd c reads B at tb - 2(c - 1)
+    const int ta = lbytes + 2 * (E0 - xs - p0 + dA);
+    const int tb = lbytes + RSTRIDE * 2 + 2 * (E0 - xs - 1 + p0 + dB) - 2;
+    const int tl = seg * CSEG * 32;
+    uint32_t *Cf = reinterpret_cast<uint32_t *>(a.C + (size_t)f * a.frame_vol) + (size_t)(x0 + seg * CSEG) * D2 + dp;
     stage(clampi(y0 - h, 0, a.H - 1), 0);
+    if (nrows > 1) stage(clampi(y0 - h + 1, 0, a.H - 1), 1);
+    cp_async_wait_all();
     __syncthreads();
     for (int base = 0; base < nrows; base += BS) {
 #pragma unroll
         for (int u = 0; u < BS; u++) {
             const int i = base + u;
             if (i < nrows) {                                        // CTA-uniform
-                const int b = i & 1;
-                if (i + 1 < nrows) stage(clampi(y0 - h + i + 1, 0, a.H - 1), b ^ 1);
-                const uint4 *lsw = reinterpret_cast<const uint4 *>(cs + b * bbytes) + (size_t)seg * CSEG * 2;
-                const uint8_t *rvb = cs + b * bbytes + lbytes;
+                const uint8_t *xb = cs + (i & 1) * bbytes;
+                const uint4 *lp = reinterpret_cast<const uint4 *>(xb + tl);
                 uint32_t hc[BS], hs = 0u;
+                if (!edge) {
+                    const uint32_t *pa = reinterpret_cast<const uint32_t *>(xb + ta);
+                    const uint32_t *pb = reinterpret_cast<const uint32_t *>(xb + tb);
 #pragma unroll
-                for (int c = 0; c < NC; c++) {
-                    const int xc = clampi(x0 - h + seg * CSEG + c, 0, a.W1 - 1);
-                    const int e = E0 - xc, cpar = e & 1;
-                    const uint32_t *rw = reinterpret_cast<const uint32_t *>(rvb + (size_t)cpar * (RSTRIDE * 2) + (size_t)(e - cpar) * 2);
-                    const uint4 l0 = lsw[c * 2], l1 = lsw[c * 2 + 1];
-                    uint32_t cost;
-                    {
-                        const uint32_t v = rw[0], v0 = rw[RSTRIDE], v1 = rw[2 * RSTRIDE];
-                        const uint32_t c0 = __vimax3_s16x2(0u, __vsub2(l0.x, v1), __vsub2(v0, l0.x));
-                        const uint32_t c1 = __vimax3_s16x2(0u, __vsub2(v, l0.z), __vsub2(l0.y, v));
-                        cost = __vmins2(c0, c1);
+                    for (int c = 0; c < NC; c++) {
+                        const uint32_t *rw = (c & 1) ? pb - (c - 1) / 2 : pa - c / 2;
+                        const uint32_t cost = bt_cost2(lp[c * 2], lp[c * 2 + 1], rw);
+                        if (c >= BS) hs -= hc[c % BS];
+                        hs += cost;
+                        hc[c % BS] = cost;
+                        if (c >= 2 * h) {
+                            const int j = c - 2 * h;
+                            V[j] += hs - ring[u][j];
+                            ring[u][j] = hs;
+                        }
                     }
-                    {
-                        const uint32_t v = rw[3 * RSTRIDE], v0 = rw[4 * RSTRIDE], v1 = rw[5 * RSTRIDE];
-                        const uint32_t c0 = __vimax3_s16x2(0u, __vsub2(l1.x, v1), __vsub2(v0, l1.x));
-                        const uint32_t c1 = __vimax3_s16x2(0u, __vsub2(v, l1.z), __vsub2(l1.y, v));
-                        cost += (__vmins2(c0, c1) >> 2) & 0x3FFF3FFFu;
-                    }
-                    if (c >= BS) hs -= hc[c % BS];
-                    hs += cost;
-                    hc[c % BS] = cost;
-                    if (c >= 2 * h) {
-                        const int j = c - 2 * h;
-                        V[j] += hs - ring[u][j];
-                        ring[u][j] = hs;
+                } else {
+#pragma unroll
+                    for (int c = 0; c < NC; c++) {
+                        const int xc = clampi(xs + c, 0, a.W1 - 1);
+                        const int e = E0 - xc;
+                        const int off = ((e - p0) & 1) ? lbytes + RSTRIDE * 2 + 2 * (e - 1 + p0 + dB) : lbytes + 2 * (e - p0 + dA);
+                        const uint32_t *rw = reinterpret_cast<const uint32_t *>(xb + off);
+                        const uint32_t cost = bt_cost2(lp[c * 2], lp[c * 2 + 1], rw);
+                        if (c >= BS) hs -= hc[c % BS];
+                        hs += cost;
+                        hc[c % BS] = cost;
+                        if (c >= 2 * h) {
+                            const int j = c - 2 * h;
+                            V[j] += hs - ring[u][j];
+                            ring[u][j] = hs;
+                        }
                     }
                 }
                 if (i >= 2 * h) {
-                    const int yo = y0 + i - 2 * h;
-                    uint32_t *dst = Cf + ((size_t)yo * a.W1 + x0 + seg * CSEG) * D2 + dp;
+                    uint32_t *dst = Cf + (size_t)(y0 + i - 2 * h) * a.W1 * D2;
 #pragma unroll
                     for (int j = 0; j < CSEG; j++)
-                        if (x0 + seg * CSEG + j < a.W1) dst[(size_t)j * D2] = V[j];
+                        if (x0 + seg * CSEG + j < a.W1) dst[j * D2] = V[j];
                 }
-                __syncthreads();
+                cp_async_wait_all();                                // row i + 1 (in flight during this row) has landed
+                __syncthreads();                                    // ... for everyone, and buffer i & 1 is free
+                if (i + 2 < nrows) stage(clampi(y0 - h + i + 2, 0, a.H - 1), i & 1);
             }
         }
     }
@@ -753,10 +864,14 @@ sgbm_wta_kernel(WtaArgs a)
 
 }  // namespace
 
+static bool sgbm_fused_cost(const SgbmGeom &g) { return (g.D == 64 || g.D == 128 || g.D == 256) && g.bs <= 7 && g.W1 > 0; }
+
 size_t sgbm_work_bytes(const SgbmGeom &g, size_t *planes, size_t *vol)
 {
     const size_t Wp = align_up((size_t)g.W, 16);
-    const size_t pl = (size_t)12 * g.H * Wp;
+    size_t pl = (size_t)12 * g.H * Wp;
+    if (sgbm_fused_cost(g))                                            // GL + GR blocks of sgbm_planes2_kernel
+        pl = std::max(pl, (size_t)g.H * ((size_t)(g.W1 + 2 * PADL) * 32 + (size_t)12 * align_up((size_t)g.W + 2 * PADR, 8) * 2));
     const size_t v = (size_t)g.H * (g.W1 > 0 ? g.W1 : 0) * g.D;        // elements
     if (planes) *planes = pl;
     if (vol) *vol = v;
@@ -769,34 +884,37 @@ int launch_sgbm(const SgbmGeom &g, int n, PlaneU8 left, PlaneU8 right, PlaneS16 
     if (n <= 0 || g.W1 <= 0) return 0;
     const int Wp = (int)align_up((size_t)g.W, 16);
     const int h = g.bs / 2;
-    // 1. planes
-    sgbm_planes_kernel<<<dim3(cdiv(g.W, 256), g.H, 2 * n), 256, 0, st>>>(left, right, w.planes, w.frame_planes, g.W, g.H, Wp, g.ftzero);
     const size_t row_words = (size_t)g.W1 * g.D / 2, frame_words = w.frame_vol / 2;
-    const bool pow2D = (g.D & (g.D - 1)) == 0 && g.D >= 16 && g.D <= 256;
-    if (pow2D && g.bs <= 7 && !getenv("RTDM_SGBM_OLDCOST")) {       // larger windows: the register rings would spill
-        // 2+3. fused: BT cost, horizontal and vertical windows, + P2 -> C
-        CostArgs a;
+    // D = 64 / 128 / 256 and windows up to 7 (larger ones would spill the register rings)
+    const bool fusedcost = sgbm_fused_cost(g) && !getenv("RTDM_SGBM_OLDCOST");
+    if (fusedcost) {
+        // 1-3. planes in staging format, then fused BT cost + horizontal and vertical windows + P2 -> C
+        const int LW = g.W1 + 2 * PADL, WR = (int)align_up((size_t)g.W + 2 * PADR, 8);
+        sgbm_planes2_kernel<<<dim3(cdiv(g.W, 256), g.H, 2 * n), 256, 0, st>>>(left, right, w.planes, w.frame_planes, g.W, g.H,
+                                                                            g.ftzero, g.minX1, g.W1, LW, WR);
+        Cost2Args a;
         a.planes = w.planes; a.frame_planes = w.frame_planes;
-        a.Hs = nullptr; a.frame_vol = w.frame_vol;
-        a.W = g.W; a.H = g.H; a.Wp = Wp; a.D = g.D; a.minD = g.minD; a.h = h; a.minX1 = g.minX1; a.W1 = g.W1;
-        const int D2 = g.D / 2, TXk = (256 / D2) * CSEG, NXC = TXk + 2 * h, BY = 48;
+        a.C = reinterpret_cast<uint16_t *>(w.C); a.frame_vol = w.frame_vol;
+        a.W = g.W; a.H = g.H; a.D = g.D; a.minD = g.minD; a.minX1 = g.minX1; a.W1 = g.W1; a.LW = LW; a.WR = WR; a.BY = 48;
+        a.P2x2 = (uint32_t)g.P2 * 0x00010001u;
+        const int D2 = g.D / 2, TXk = (256 / D2) * CSEG, NXC = TXk + 2 * h;
         const size_t smem = 2 * ((size_t)NXC * 32 + (size_t)12 * RSTRIDE * 2);
-        const dim3 grid(cdiv(g.W1, TXk), cdiv(g.H, BY), n);
-        const uint32_t p2 = (uint32_t)g.P2 * 0x00010001u;
-        uint16_t *Cv = reinterpret_cast<uint16_t *>(w.C);
+        const dim3 grid(cdiv(g.W1, TXk), cdiv(g.H, a.BY), n);
 #define RTDM_COST_CASE(BS_)                                                                                             \
         case BS_:                                                                                                       \
             RTDM_CUDA(cudaFuncSetAttribute(sgbm_cost_fused_kernel<BS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            sgbm_cost_fused_kernel<BS_><<<grid, 256, smem, st>>>(a, Cv, p2, BY);                                        \
+            sgbm_cost_fused_kernel<BS_><<<grid, 256, smem, st>>>(a);                                                    \
             break;
         switch (g.bs) {
             RTDM_COST_CASE(1) RTDM_COST_CASE(3) RTDM_COST_CASE(5)
             default: RTDM_CUDA(cudaFuncSetAttribute(sgbm_cost_fused_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                     sgbm_cost_fused_kernel<7><<<grid, 256, smem, st>>>(a, Cv, p2, BY); break;
+                     sgbm_cost_fused_kernel<7><<<grid, 256, smem, st>>>(a); break;
         }
 #undef RTDM_COST_CASE
         if (launches) (*launches) += 2;
     } else {
+    // 1. planes
+    sgbm_planes_kernel<<<dim3(cdiv(g.W, 256), g.H, 2 * n), 256, 0, st>>>(left, right, w.planes, w.frame_planes, g.W, g.H, Wp, g.ftzero);
     // 2. BT cost + horizontal window -> Hs (stored in the S volume, which is rewritten by the first path)
     {
         CostArgs a;
