@@ -245,11 +245,6 @@ sgbm_planes2_kernel(PlaneU8 left, PlaneU8 right, uint8_t *planes, size_t frame_p
     }
 }
 
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
-{
-    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
-}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
@@ -300,28 +295,26 @@ sgbm_cost_fused_kernel(Cost2Args a)
     const uint8_t *gl = pf + (size_t)(x0 - h + PADL) * 32;
     const uint8_t *gr = pf + (size_t)a.H * a.LW * 32;
     const size_t lrow = (size_t)a.LW * 32, rrow = (size_t)12 * a.WR * 2;
-    // this thread's (at most two) 16-byte chunks of a row
-    int goff[2], soff[2];
+    // this thread's (at most two) 16-byte chunks of a row: global pointer for row 0 + row stride, shared offset
+    const uint8_t *gsrc[2]; uint32_t gstr[2], soff[2];
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(cs);
 #pragma unroll
     for (int q = 0; q < 2; q++) {
         const int t = threadIdx.x + q * 256;
-        goff[q] = -1; soff[q] = 0;
-        if (t < NL) { goff[q] = t * 16; soff[q] = t * 16; }
+        gsrc[q] = nullptr; gstr[q] = 0u; soff[q] = 0u;
+        if (t < NL) { gsrc[q] = gl + t * 16; gstr[q] = (uint32_t)lrow; soff[q] = sbase + t * 16; }
         else if (t < NL + 12 * NRC) {
             const int r = t - NL, ac = r / NRC, ch = r - ac * NRC, arr = ac >> 1, cpy = ac & 1;
             const int gcopy = cpy ? srcB : srcA, gi = (cpy ? iB : iA) + ch * 8;
-            goff[q] = (1 << 30) | (((arr * 2 + gcopy) * a.WR + gi) * 2);
-            soff[q] = lbytes + (ac * RSTRIDE + ch * 8) * 2;
+            gsrc[q] = gr + (size_t)((arr * 2 + gcopy) * a.WR + gi) * 2; gstr[q] = (uint32_t)rrow;
+            soff[q] = sbase + lbytes + (ac * RSTRIDE + ch * 8) * 2;
         }
     }
     auto stage = [&](int row, int b) {
 #pragma unroll
-        for (int q = 0; q < 2; q++) {
-            if (goff[q] >= 0) {
-                const uint8_t *src = (goff[q] >> 30) ? gr + (size_t)row * rrow + (goff[q] & 0x3FFFFFFF) : gl + (size_t)row * lrow + goff[q];
-                cp_async16(cs + b * bbytes + soff[q], src);
-            }
-        }
+        for (int q = 0; q < 2; q++)
+            if (gsrc[q])
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(soff[q] + b * bbytes), "l"(gsrc[q] + (size_t)row * gstr[q]) : "memory");
         cp_async_commit();
     };
 
@@ -337,7 +330,9 @@ sgbm_cost_fused_kernel(Cost2Args a)
     const int ta = lbytes + 2 * (E0 - xs - p0 + dA);
     const int tb = lbytes + RSTRIDE * 2 + 2 * (E0 - xs - 1 + p0 + dB) - 2;
     const int tl = seg * CSEG * 32;
-    uint32_t *Cf = reinterpret_cast<uint32_t *>(a.C + (size_t)f * a.frame_vol) + (size_t)(x0 + seg * CSEG) * D2 + dp;
+    uint32_t *cptr = reinterpret_cast<uint32_t *>(a.C + (size_t)f * a.frame_vol) + ((size_t)y0 * a.W1 + x0 + seg * CSEG) * D2 + dp;
+    const size_t crow = (size_t)a.W1 * D2;
+    const int ncols = a.W1 - (x0 + seg * CSEG);                       // columns of this thread inside the image (may be <= 0)
     stage(clampi(y0 - h, 0, a.H - 1), 0);
     if (nrows > 1) stage(clampi(y0 - h + 1, 0, a.H - 1), 1);
     cp_async_wait_all();
@@ -385,10 +380,15 @@ sgbm_cost_fused_kernel(Cost2Args a)
                     }
                 }
                 if (i >= 2 * h) {
-                    uint32_t *dst = Cf + (size_t)(y0 + i - 2 * h) * a.W1 * D2;
+                    if (ncols >= CSEG) {
 #pragma unroll
-                    for (int j = 0; j < CSEG; j++)
-                        if (x0 + seg * CSEG + j < a.W1) dst[j * D2] = V[j];
+                        for (int j = 0; j < CSEG; j++) cptr[j * D2] = V[j];
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < CSEG; j++)
+                            if (j < ncols) cptr[j * D2] = V[j];
+                    }
+                    cptr += crow;
                 }
                 cp_async_wait_all();                                // row i + 1 (in flight during this row) has landed
                 __syncthreads();                                    // ... for everyone, and buffer i & 1 is free
