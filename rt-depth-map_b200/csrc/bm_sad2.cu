@@ -47,36 +47,88 @@ struct Bm2Args {
 // ------------------------------------------------------------------------------------------------
 // texture: T(x, y) = sum over the (2h+1)^2 window of |L'[y+j][lcol(x+i)] - cap|, x in [0, W1)
 // ------------------------------------------------------------------------------------------------
-constexpr int TXW = 128, TXH = 64, TXT = 160;      // output columns / rows per CTA, threads (>= TXW + 2h)
+// No shared memory and no barriers: a thread owns 4 adjacent output columns of a band of TXH rows.  The horizontal
+// window sums of one image row come from the 4 + 2h bytes around them (6 aligned words, one uniform funnel shift,
+// VABSDIFF4 against cap, IDP.4A byte sums); the vertical window slides by adding the entering row's sums and
+// subtracting the leaving row's, both recomputed (the rows are L1 / L2 resident).  |L' - cap| <= 63, so the byte
+// sums fit the signed dot product and T <= 15 * 15 * 63 fits 16 bits.
+constexpr int TXH = 32, TXT = 128;
+template <int H_>
+__device__ __forceinline__ void tex_row_sums(const uint8_t *row, int col0, int W, uint32_t capx4, int s[4])
+{
+    constexpr int N = 2 * H_ + 1;                       // window taps; bytes needed: N + 3 <= 18
+    uint32_t w[5];
+    if (col0 + N + 2 <= W - 1) {
+        const uint32_t *p = reinterpret_cast<const uint32_t *>(row + (col0 & ~3));
+        const int sh = (col0 & 3) * 8;
+        uint32_t q[6];
+#pragma unroll
+        for (int k = 0; k < 6; k++) q[k] = p[k];
+#pragma unroll
+        for (int k = 0; k < 5; k++) w[k] = __funnelshift_r(q[k], q[k + 1], sh);
+    } else {
+        // right image border: columns beyond W - 1 replicate it
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int b = 0; b < 4; b++) v |= (uint32_t)row[min(col0 + 4 * k + b, W - 1)] << (8 * b);
+            w[k] = v;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 5; k++) w[k] = __vabsdiffu4(w[k], capx4);
+    // s[0] = bytes 0 .. N-1
+    int acc = 0;
+#pragma unroll
+    for (int k = 0; k < (N + 3) / 4; k++) {
+        const int nb = N - 4 * k >= 4 ? 4 : N - 4 * k;
+        const int m = nb == 4 ? 0x01010101 : (nb == 3 ? 0x00010101 : (nb == 2 ? 0x00000101 : 0x00000001));
+        acc = __dp4a((int)w[k], m, acc);
+    }
+    s[0] = acc;
+#pragma unroll
+    for (int i = 1; i < 4; i++) {
+        // + byte (N - 1 + i), - byte (i - 1)
+        const int bi = N - 1 + i, bo = i - 1;
+        acc = __dp4a((int)w[bi / 4], 1 << (8 * (bi % 4)), acc);
+        acc = __dp4a((int)w[bo / 4], (int)(0xFFu << (8 * (bo % 4))), acc);    // multiplier byte -1
+        s[i] = acc;
+    }
+}
+
+template <int H_>
 __global__ void __launch_bounds__(TXT)
 bm_texture_kernel(PlaneU8 Lp, uint16_t *tex, size_t tex_pitch, size_t tex_frame, int W, int H, int nd,
-                  int cap, int h, int W1, int row0, int row1)
+                  int cap, int W1, int row0, int row1)
 {
-    __shared__ int colsum[2][TXT];
-    const int f = blockIdx.z, c = threadIdx.x;
-    const int x0 = blockIdx.x * TXW, y0 = row0 + blockIdx.y * TXH, y1 = min(y0 + TXH, row1);
-    if (y0 >= y1) return;
-    const int lofs = nd - 1;
-    const bool colok = c < TXW + 2 * h;
-    const int lc = clampi(x0 - h + c, -lofs, W - lofs - 1) + lofs;
-    const uint8_t *L = Lp.p + (size_t)f * Lp.frame + lc;
-    // vertical window sum of |L' - cap| for this (virtual) column, sliding down the rows
-    int v = 0;
-    if (colok)
-        for (int r = y0 - h; r < y0 + h; r++) v += abs((int)L[(size_t)clampi(r, 0, H - 1) * Lp.pitch] - cap);
-    uint16_t *out = tex + (size_t)f * tex_frame;
+    const int f = blockIdx.z;
+    const int x1 = (blockIdx.x * TXT + threadIdx.x) * 4;
+    const int y0 = row0 + blockIdx.y * TXH, y1 = min(y0 + TXH, row1);
+    if (x1 >= W1 || y0 >= y1) return;
+    const int col0 = x1 + (nd - 1) - H_;                 // real column of window tap 0 (>= 0: nd - 1 >= 15 > H_)
+    const uint8_t *L = Lp.p + (size_t)f * Lp.frame;
+    const uint32_t capx4 = (uint32_t)cap * 0x01010101u;
+    int T[4] = {0, 0, 0, 0}, s[4];
+    for (int r = y0 - H_; r <= y0 + H_; r++) {
+        tex_row_sums<H_>(L + (size_t)clampi(r, 0, H - 1) * Lp.pitch, col0, W, capx4, s);
+#pragma unroll
+        for (int i = 0; i < 4; i++) T[i] += s[i];
+    }
+    uint16_t *out = tex + (size_t)f * tex_frame + (size_t)y0 * tex_pitch + x1;
+    const bool vec = ((tex_pitch & 3) == 0) && x1 + 3 < W1;
     for (int y = y0; y < y1; y++) {
-        if (colok) {
-            v += abs((int)L[(size_t)clampi(y + h, 0, H - 1) * Lp.pitch] - cap);
-            if (y > y0) v -= abs((int)L[(size_t)clampi(y - h - 1, 0, H - 1) * Lp.pitch] - cap);
-        }
-        int *cs = colsum[(y - y0) & 1];             // double buffer: one barrier per row
-        cs[c] = v;
-        __syncthreads();
-        if (c < TXW && x0 + c < W1) {
-            int s = 0;
-            for (int k = 0; k <= 2 * h; k++) s += cs[c + k];
-            out[(size_t)y * tex_pitch + x0 + c] = (uint16_t)s;
+        if (vec) *reinterpret_cast<uint2 *>(out) = make_uint2((uint32_t)T[0] | ((uint32_t)T[1] << 16), (uint32_t)T[2] | ((uint32_t)T[3] << 16));
+        else
+            for (int i = 0; i < 4 && x1 + i < W1; i++) out[i] = (uint16_t)T[i];
+        out += tex_pitch;
+        if (y + 1 < y1) {
+            tex_row_sums<H_>(L + (size_t)clampi(y + 1 + H_, 0, H - 1) * Lp.pitch, col0, W, capx4, s);
+#pragma unroll
+            for (int i = 0; i < 4; i++) T[i] += s[i];
+            tex_row_sums<H_>(L + (size_t)clampi(y - H_, 0, H - 1) * Lp.pitch, col0, W, capx4, s);
+#pragma unroll
+            for (int i = 0; i < 4; i++) T[i] -= s[i];
         }
     }
 }
@@ -480,8 +532,17 @@ int launch_bm_sad2(const BmGeom &g, int n, PlaneU8 Lp, PlaneU8 Rp, PlaneS16 disp
     if (!pick_tiling2(g, n, &t)) { set_error("bm_sad2: unsupported geometry"); return -RTDM_EINVAL; }
     const int h = g.bs / 2;
     {
-        dim3 grid(cdiv(g.W1, TXW), cdiv(g.row1 - g.row0, TXH), n);
-        bm_texture_kernel<<<grid, TXT, 0, st>>>(Lp, tex, tex_pitch, tex_frame, g.W, g.H, g.nd, g.cap, h, g.W1, g.row0, g.row1);
+        dim3 grid(cdiv(cdiv(g.W1, 4), TXT), cdiv(g.row1 - g.row0, TXH), n);
+#define RTDM_TEX_CASE(H_) bm_texture_kernel<H_><<<grid, TXT, 0, st>>>(Lp, tex, tex_pitch, tex_frame, g.W, g.H, g.nd, g.cap, g.W1, g.row0, g.row1)
+        switch (h) {
+            case 2: RTDM_TEX_CASE(2); break;
+            case 3: RTDM_TEX_CASE(3); break;
+            case 4: RTDM_TEX_CASE(4); break;
+            case 5: RTDM_TEX_CASE(5); break;
+            case 6: RTDM_TEX_CASE(6); break;
+            default: RTDM_TEX_CASE(7); break;
+        }
+#undef RTDM_TEX_CASE
     }
     Bm2Args a;
     a.Lp = Lp; a.Rp = Rp; a.disp = disp; a.cost = cost;
