@@ -146,13 +146,13 @@ morph_kernel(int W, int H, PlaneU8 src, PlaneU8W dst, MorphSE se, int op, const 
 
 // ------------------------------------------------------------------------------------------------
 // Binary fast path for SWMorphologicalFilter::run: erode, dilate, dilate, erode on {0,255} masks (what
-// inRange() feeds the filter, estimator.cpp:43).  One CTA packs a tile (+20 px halo) to 1 bit/pixel with
-// warp ballots, runs all four passes on 32-pixel words in shared memory (a run of the structuring element is
+// inRange() feeds the filter, estimator.cpp:43).  One CTA packs a tile (+20 px halo) to 1 bit/pixel (one thread
+// per 32-pixel word, 128-bit loads), runs all four passes on 32-pixel words in shared memory (a run of the structuring element is
 // an AND of two shifted power-of-two run words; dilate = erode of the complement) and unpacks the centre.
 // A frame that contains any other byte value raises its flag and is recomputed by the generic kernels.
 // ------------------------------------------------------------------------------------------------
-constexpr int BT_W = 7, BT_H = 32;               // output tile: 7 words (224 px) x 32 rows
-constexpr int BT_RW = BT_W + 2, BT_HALO = 20, BT_RR = BT_H + 2 * BT_HALO;
+constexpr int BT_W = 7;                          // output tile: 7 words (224 px) x BT_H rows (32: few frames, 90: batches)
+constexpr int BT_RW = BT_W + 2, BT_HALO = 20;
 
 constexpr int BT_MAXRUN = 6;                     // distinct runs the fast path keeps in shared memory
 
@@ -164,37 +164,45 @@ struct SeView {
     const int *rj1, *rL, *rowrun;
 };
 
-template <bool FIXED10>
+template <bool FIXED10, int BT_H>
 __global__ void __launch_bounds__(256)
-morph_binary_openclose_kernel(int W, int H, PlaneU8 src, PlaneU8W dst, MorphSE se, int *nonbinary)
+morph_binary_openclose_kernel(int W, int H, PlaneU8 src, PlaneU8W dst, MorphSE se, int *nonbinary, int vec)
 {
-    constexpr int NWORD = BT_RR * BT_RW;
-    __shared__ uint32_t buf[NWORD], inside[NWORD], runs[BT_MAXRUN][NWORD];
+    constexpr int BT_RR = BT_H + 2 * BT_HALO, NWORD = BT_RR * BT_RW;
+    __shared__ uint32_t buf[NWORD], inside[NWORD], runs[FIXED10 ? 4 : BT_MAXRUN][NWORD];
     const int f = blockIdx.z;
-    const int x0 = blockIdx.x * BT_W * 32 - 32, y0 = blockIdx.y * BT_H - BT_HALO;   // region origin
+    const int x0 = blockIdx.x * BT_W * 32 - 32, y0 = blockIdx.y * BT_H - BT_HALO;   // region origin (x0 % 32 == 0)
     const uint8_t *s = src.p + (size_t)f * src.frame;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
     bool bad = false;
-    // 8 independent byte loads in flight per lane before the ballots (the loop is latency-bound otherwise)
-    for (int i0 = warp; i0 < NWORD; i0 += 64) {
-        int v[8];
-        bool in[8];
+    // pack: one thread per 32-pixel word.  16-byte aligned planes: two 128-bit loads, the low bit of every byte
+    // gathered by a multiply ((t & 0x01010101) * 0x01020408 >> 24 = 4 pixels -> 4 bits); otherwise byte loads.
+    for (int i = threadIdx.x; i < NWORD; i += 256) {
+        const int r = i / BT_RW, w = i - r * BT_RW;
+        const int gx0 = x0 + 32 * w, gy = y0 + r;
+        uint32_t bits = 0u, ins = 0u;
+        if (gy >= 0 && gy < H && gx0 >= 0 && gx0 < W) {
+            const int nvalid = min(32, W - gx0);
+            ins = nvalid == 32 ? 0xFFFFFFFFu : (1u << nvalid) - 1u;
+            const uint8_t *p = s + (size_t)gy * src.pitch + gx0;
+            if (vec && nvalid == 32) {
+                const uint4 a = __ldg(reinterpret_cast<const uint4 *>(p)), b = __ldg(reinterpret_cast<const uint4 *>(p) + 1);
+                const uint32_t q[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
-            const int i = i0 + 8 * u;
-            const int r = i / BT_RW, w = i - r * BT_RW;
-            const int gx = x0 + 32 * w + lane, gy = y0 + r;
-            in[u] = i < NWORD && gx >= 0 && gx < W && gy >= 0 && gy < H;
-            v[u] = in[u] ? s[(size_t)gy * src.pitch + gx] : 0;
+                for (int k = 0; k < 8; k++) {
+                    const uint32_t t = q[k] & 0x01010101u;
+                    bad = bad || (q[k] != t * 255u);
+                    bits |= ((t * 0x01020408u) >> 24) << (4 * k);
+                }
+            } else {
+                for (int k = 0; k < nvalid; k++) {
+                    const int v = p[k];
+                    bits |= (uint32_t)(v == 255) << k;
+                    bad = bad || (v != 0 && v != 255);
+                }
+            }
         }
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-            const int i = i0 + 8 * u;
-            const uint32_t bits = __ballot_sync(0xFFFFFFFFu, v[u] == 255);
-            const uint32_t ins = __ballot_sync(0xFFFFFFFFu, in[u]);
-            bad = bad || (v[u] != 0 && v[u] != 255);
-            if (lane == 0 && i < NWORD) { buf[i] = bits; inside[i] = ins; }
-        }
+        buf[i] = bits; inside[i] = ins;
     }
     if (__any_sync(0xFFFFFFFFu, bad) && lane == 0) atomicOr(&nonbinary[f], 1);
     __syncthreads();
@@ -247,12 +255,23 @@ morph_binary_openclose_kernel(int W, int H, PlaneU8 src, PlaneU8W dst, MorphSE s
         }
         __syncthreads();
     }
-    // unpack the centre of the tile: words 1..BT_W, rows BT_HALO..BT_HALO+BT_H
+    // unpack the centre of the tile: words 1..BT_W, rows BT_HALO..BT_HALO+BT_H; one thread per word
     uint8_t *d = dst.p + (size_t)f * dst.frame;
-    for (int i = warp; i < BT_H * BT_W; i += 8) {
+    for (int i = threadIdx.x; i < BT_H * BT_W; i += 256) {
         const int r = BT_HALO + i / BT_W, w = 1 + i % BT_W;
-        const int gx = x0 + 32 * w + lane, gy = y0 + r;
-        if (gx < W && gy < H) d[(size_t)gy * dst.pitch + gx] = ((buf[r * BT_RW + w] >> lane) & 1u) ? 255 : 0;
+        const int gx0 = x0 + 32 * w, gy = y0 + r;
+        if (gy >= H || gx0 >= W) continue;
+        const uint32_t bits = buf[r * BT_RW + w];
+        uint8_t *o = d + (size_t)gy * dst.pitch + gx0;
+        if (vec && gx0 + 32 <= W) {
+            uint32_t q[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) q[k] = ((((bits >> (4 * k)) & 0xFu) * 0x00204081u) & 0x01010101u) * 255u;   // 4 bits -> 4 bytes
+            reinterpret_cast<uint4 *>(o)[0] = make_uint4(q[0], q[1], q[2], q[3]);
+            reinterpret_cast<uint4 *>(o)[1] = make_uint4(q[4], q[5], q[6], q[7]);
+        } else {
+            for (int k = 0; k < 32 && gx0 + k < W; k++) o[k] = ((bits >> k) & 1u) ? 255 : 0;
+        }
     }
 }
 
@@ -299,7 +318,6 @@ int launch_morph_openclose(int n, int W, int H, PlaneU8 src, PlaneU8W dst, Plane
     const bool bitpath = se.kw <= 16 && se.kh <= 16 && se.nrun <= BT_MAXRUN;            // 16 px of context per word side, halo 20 >= 4*ax
     if (bitpath && 4 * std::max(std::max(se.ax, se.kw - 1 - se.ax), std::max(se.ay, se.kh - 1 - se.ay)) <= BT_HALO) {
         RTDM_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * n, st));
-        dim3 grid(cdiv(W, BT_W * 32), cdiv(H, BT_H), n);
         // without aliasing the fast path writes dst directly (flagged frames are overwritten by the generic chain)
         if (!alias) fast = dst;
         // the reference's 10x10 ellipse gets the compile-time specialisation
@@ -307,8 +325,18 @@ int launch_morph_openclose(int n, int W, int H, PlaneU8 src, PlaneU8W dst, Plane
         bool fixed10 = se.kw == 10 && se.kh == 10 && se.ax == 5 && se.ay == 5 && se.nrun == 4;
         for (int u = 0; fixed10 && u < 4; u++) fixed10 = se.rj1[u] == f_rj1[u] && se.rL[u] == f_rL[u];
         for (int k = 0; fixed10 && k < 10; k++) fixed10 = se.rowrun[k] == f_rowrun[k];
-        if (fixed10) morph_binary_openclose_kernel<true><<<grid, 256, 0, st>>>(W, H, src, fast, se, flags);
-        else morph_binary_openclose_kernel<false><<<grid, 256, 0, st>>>(W, H, src, fast, se, flags);
+        const auto al16 = [](const void *p, size_t pitch, size_t frame) { return ((reinterpret_cast<uintptr_t>(p) | pitch | frame) & 15) == 0; };
+        const int vec = al16(src.p, src.pitch, src.frame) && al16(fast.p, fast.pitch, fast.frame);
+        // tall tiles (less halo work) once there are enough frames to fill the machine, short ones for latency
+        if (n >= 4) {
+            const dim3 grid(cdiv(W, BT_W * 32), cdiv(H, 90), n);
+            if (fixed10) morph_binary_openclose_kernel<true, 90><<<grid, 256, 0, st>>>(W, H, src, fast, se, flags, vec);
+            else morph_binary_openclose_kernel<false, 72><<<dim3(grid.x, cdiv(H, 72), n), 256, 0, st>>>(W, H, src, fast, se, flags, vec);
+        } else {
+            const dim3 grid(cdiv(W, BT_W * 32), cdiv(H, 32), n);
+            if (fixed10) morph_binary_openclose_kernel<true, 32><<<grid, 256, 0, st>>>(W, H, src, fast, se, flags, vec);
+            else morph_binary_openclose_kernel<false, 32><<<grid, 256, 0, st>>>(W, H, src, fast, se, flags, vec);
+        }
         if (launches) (*launches)++;
     } else {
         flags = nullptr;                                           // generic chain for every frame
