@@ -9,6 +9,7 @@
 //   cv::filterSpeckles     (App. A.4; oracle: orc_filter_speckles)
 //   cv::medianBlur(.., 3)  (App. A.6 tail; oracle: orc_median3_s16)
 #include "common.cuh"
+#include <cstdlib>
 
 namespace rtdm {
 
@@ -118,11 +119,24 @@ __device__ __forceinline__ int uf_find(const int32_t *lab, int i)
     return i;
 }
 
+// find with path halving: every visited node is re-pointed at its grandparent.  The plain stores race benignly with
+// concurrent unions (a node only ever moves to an ancestor, and ancestors have smaller indices).
+__device__ __forceinline__ int uf_find_halve(int32_t *lab, int i)
+{
+    int p = lab[i];
+    while (p != i) {
+        const int gp = lab[p];
+        if (gp != p) lab[i] = gp;
+        i = p; p = gp;
+    }
+    return i;
+}
+
 __device__ __forceinline__ void uf_union(int32_t *lab, int a, int b)
 {
     while (true) {
-        a = uf_find(lab, a);
-        b = uf_find(lab, b);
+        a = uf_find_halve(lab, a);
+        b = uf_find_halve(lab, b);
         if (a == b) return;
         if (a < b) { int t = a; a = b; b = t; }          // a > b : hook a under b
         int old = atomicMin(&lab[a], b);
@@ -246,10 +260,165 @@ speckle_apply_kernel(int W, int H, PlaneS16 img, int newVal, int maxSize, const 
         img.p[(size_t)f * img.frame + (size_t)y * img.pitch + x] = (int16_t)newVal;
 }
 
+// ---- 8 pixels per thread (W % 8 == 0, 16-byte aligned rows): 128-bit loads, one thread block per row ----------
+__device__ __forceinline__ void load8_s16(const int16_t *p, int v[8])
+{
+    const uint4 q = *reinterpret_cast<const uint4 *>(p);
+    v[0] = (int16_t)(q.x & 0xFFFFu); v[1] = (int16_t)(q.x >> 16); v[2] = (int16_t)(q.y & 0xFFFFu); v[3] = (int16_t)(q.y >> 16);
+    v[4] = (int16_t)(q.z & 0xFFFFu); v[5] = (int16_t)(q.z >> 16); v[6] = (int16_t)(q.w & 0xFFFFu); v[7] = (int16_t)(q.w >> 16);
+}
+
+__global__ void __launch_bounds__(1024)
+speckle_rowruns8_kernel(int W, int H, PlaneS16 img, int newVal, int maxDiff, int32_t *labels, int32_t *sizes, int32_t *runlen)
+{
+    extern __shared__ int cnt[];                         // [W] pixels per run, indexed by run-start column
+    __shared__ int warp_last[32];
+    const int y = blockIdx.x, f = blockIdx.y;
+    const int16_t *row = img.p + (size_t)f * img.frame + (size_t)y * img.pitch;
+    const size_t rowbase = ((size_t)f * H + y) * W;
+    int32_t *lab = labels + rowbase, *siz = sizes + rowbase, *rlen = runlen + rowbase;
+    const int x0 = threadIdx.x * 8;
+    const bool active = x0 < W;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    for (int x = threadIdx.x; x < W; x += blockDim.x) cnt[x] = 0;
+    int v[8];
+    if (active) load8_s16(row + x0, v);
+    else {
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = newVal;
+    }
+    int prev = __shfl_up_sync(0xFFFFFFFFu, v[7], 1);
+    if (lane == 0) prev = (active && x0 > 0) ? (int)row[x0 - 1] : newVal;
+    // bit k: pixel x0 + k continues the run of its left neighbour
+    uint32_t cont = 0u;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int p = k ? v[k - 1] : prev;
+        if (v[k] != newVal && (x0 + k) > 0 && p != newVal && abs(p - v[k]) <= maxDiff) cont |= 1u << k;
+    }
+    int run = -1;                                        // last run start (or invalid pixel) inside this thread's pixels
+    if (active && cont != 0xFFu) run = x0 + 31 - __clz((~cont) & 0xFFu);
+    // exclusive max-scan over the block
+    int incl = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl = max(incl, t);
+    }
+    if (lane == 31) warp_last[wid] = incl;
+    int carry = __shfl_up_sync(0xFFFFFFFFu, incl, 1);
+    if (lane == 0) carry = -1;
+    __syncthreads();
+    for (int w = 0; w < wid && w < nwarp; w++) carry = max(carry, warp_last[w]);
+    if (active) {
+        const int rowofs = y * W;
+        int cur = carry, pending = 0;
+        int o[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if (!((cont >> k) & 1u)) {
+                if (pending) atomicAdd(&cnt[cur], pending);
+                pending = 0;
+                cur = x0 + k;
+            }
+            if (v[k] == newVal) o[k] = -1;
+            else { o[k] = (x0 + k == cur) ? rowofs + x0 + k : ((rowofs + cur) | RUN_FLAG); pending++; }
+        }
+        if (pending) atomicAdd(&cnt[cur], pending);
+        reinterpret_cast<int4 *>(lab + x0)[0] = make_int4(o[0], o[1], o[2], o[3]);
+        reinterpret_cast<int4 *>(lab + x0)[1] = make_int4(o[4], o[5], o[6], o[7]);
+    }
+    __syncthreads();
+    if (active) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int c = cnt[x0 + k];
+            if (c > 0) { rlen[x0 + k] = c; siz[x0 + k] = 0; }      // only run starts own a counter
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128)
+speckle_vmerge8_kernel(int W, int H, PlaneS16 img, int newVal, int maxDiff, int32_t *labels)
+{
+    const int f = blockIdx.z;
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    const int y = blockIdx.y + 1;
+    if (x0 >= W || y >= H) return;
+    const int16_t *r1 = img.p + (size_t)f * img.frame + (size_t)y * img.pitch, *r0 = r1 - img.pitch;
+    int v[8], u[8];
+    load8_s16(r1 + x0, v);
+    load8_s16(r0 + x0, u);
+    // cheap reject: no vertical link at all in these 8 columns
+    uint32_t link = 0u;
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+        if (v[k] != newVal && u[k] != newVal && abs(u[k] - v[k]) <= maxDiff) link |= 1u << k;
+    if (!link) return;
+    const int vl = x0 > 0 ? (int)r1[x0 - 1] : newVal, ul = x0 > 0 ? (int)r0[x0 - 1] : newVal;
+    int32_t *lab = labels + (size_t)f * H * W;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        if (!((link >> k) & 1u)) continue;
+        const int pv = k ? v[k - 1] : vl, pu = k ? u[k - 1] : ul;
+        // skip if the left neighbours form the same vertical link already (same two runs)
+        if (pv != newVal && pu != newVal && abs(pv - v[k]) <= maxDiff && abs(pu - u[k]) <= maxDiff && abs(pu - pv) <= maxDiff) continue;
+        const int x = x0 + k;
+        int a = lab[y * W + x], b = lab[(y - 1) * W + x];     // pixel -> node (its run start)
+        a = (a & RUN_FLAG) ? (a & ~RUN_FLAG) : y * W + x;
+        b = (b & RUN_FLAG) ? (b & ~RUN_FLAG) : (y - 1) * W + x;
+        uf_union(lab, a, b);
+    }
+}
+
+// MODE 0: count (run start -> root, flatten, sizes[root] += run length); MODE 1: apply (runs of small components
+// are overwritten with newVal).  Both scan the labels 8 at a time; only run starts do any work.
+template <int MODE>
+__global__ void __launch_bounds__(256)
+speckle_runs8_kernel(int W, int H, PlaneS16 img, int newVal, int maxSize, int32_t *labels, int32_t *sizes, const int32_t *runlen)
+{
+    const int f = blockIdx.y;
+    const size_t N = (size_t)W * H;
+    const size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    if (i0 >= N) return;
+    int32_t *lab = labels + (size_t)f * N;
+    const int4 q0 = reinterpret_cast<const int4 *>(lab + i0)[0], q1 = reinterpret_cast<const int4 *>(lab + i0)[1];
+    const int l[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        if (l[k] < 0 || (l[k] & RUN_FLAG)) continue;          // invalid pixel or not a run start
+        const int i = (int)i0 + k;
+        if (MODE == 0) {
+            const int root = uf_find(lab, i);
+            lab[i] = root;                                   // flatten: only shortens the path to the final root
+            atomicAdd(&sizes[(size_t)f * N + root], runlen[(size_t)f * N + i]);
+        } else {
+            if (sizes[(size_t)f * N + l[k]] > maxSize) continue;      // l[k] is the root (flattened by MODE 0)
+            const int y = i / W, x = i - y * W, len = runlen[(size_t)f * N + i];
+            int16_t *p = img.p + (size_t)f * img.frame + (size_t)y * img.pitch + x;
+            for (int j = 0; j < len; j++) p[j] = (int16_t)newVal;
+        }
+    }
+}
+
 int launch_speckle(int n, int W, int H, PlaneS16 img, int newVal, int maxSize, int maxDiff,
                    int32_t *labels, int32_t *sizes, cudaStream_t st, int *launches, int32_t *runlen)
 {
     if (n <= 0) return 0;
+    const bool vec = W % 8 == 0 && W <= 8192 && ((reinterpret_cast<uintptr_t>(img.p) | (img.pitch * 2) | (img.frame * 2)) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(labels) & 15) == 0 && !getenv("RTDM_SPECKLE_SCALAR");
+    if (vec) {
+        const size_t N8 = ((size_t)W * H + 7) / 8;
+        const int nt = ((W / 8) + 31) & ~31;
+        speckle_rowruns8_kernel<<<dim3(H, n), nt, (size_t)W * sizeof(int), st>>>(W, H, img, newVal, maxDiff, labels, sizes, runlen);
+        if (H > 1)
+            speckle_vmerge8_kernel<<<dim3(cdiv(W / 8, 128), H - 1, n), 128, 0, st>>>(W, H, img, newVal, maxDiff, labels);
+        speckle_runs8_kernel<0><<<dim3((unsigned)((N8 + 255) / 256), n), 256, 0, st>>>(W, H, img, newVal, maxSize, labels, sizes, runlen);
+        speckle_runs8_kernel<1><<<dim3((unsigned)((N8 + 255) / 256), n), 256, 0, st>>>(W, H, img, newVal, maxSize, labels, sizes, runlen);
+        if (launches) (*launches) += (H > 1) ? 4 : 3;
+        RTDM_CUDA(cudaGetLastError());
+        return 0;
+    }
     speckle_rowruns_kernel<<<dim3(H, n), 256, (size_t)W * sizeof(int), st>>>(W, H, img, newVal, maxDiff, labels, sizes, runlen);
     if (H > 1)
         speckle_vmerge_kernel<<<dim3(cdiv(W, 256), H - 1, n), 256, 0, st>>>(W, H, img, newVal, maxDiff, labels);
