@@ -282,12 +282,12 @@ static int bm_pipeline(rtdm_bm *h, int n, PlaneU8 L, PlaneU8 R, int W, int H, Pl
         if (rc) return rc;
         mark();
     } else { mark(); mark(); }
-    rc = launch_validate_mask(n, W, H, minD, nd, p.disp12MaxDiff, g.lofs, g.W1,
-                              std::max(vr.x, 0), std::max(vr.x + vr.w, 0), row0, row1, raw, cost, out, st, &h->launches);
-    if (rc) return rc;
-    mark();
-    if (p.speckleRange >= 0 && p.speckleWindowSize > 0)
-        rc = launch_speckle(n, W, H, out, FILT, p.speckleWindowSize, p.speckleRange, wlab, wsiz, st, &h->launches, wrun);
+    // stage timing: "validate_mask" ends after the row kernel (which, fused, already holds the speckle filter's row-run pass)
+    struct Hook { decltype(mark) *m; } hook = {&mark};
+    rc = launch_validate_speckle(n, W, H, minD, nd, p.disp12MaxDiff, g.lofs, g.W1, std::max(vr.x, 0), std::max(vr.x + vr.w, 0),
+                                 row0, row1, raw, cost, out, p.speckleRange >= 0 && p.speckleWindowSize > 0, FILT,
+                                 p.speckleWindowSize, p.speckleRange, wlab, wsiz, wrun, st, &h->launches,
+                                 [](void *c) { (*static_cast<Hook *>(c)->m)(); }, &hook);
     mark();
     return rc;
 }

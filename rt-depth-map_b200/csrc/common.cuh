@@ -57,6 +57,11 @@ int launch_validate_mask(int n, int W, int H, int minD, int nd, int d12, int lof
 // filterSpeckles on n frames in place; labels, sizes, runlen: n*W*H int32 scratch each
 int launch_speckle(int n, int W, int H, PlaneS16 img, int newVal, int maxSize, int maxDiff,
                    int32_t *labels, int32_t *sizes, cudaStream_t st, int *launches, int32_t *runlen);
+int launch_validate_speckle(int n, int W, int H, int minD, int nd, int d12, int lofs, int W1,
+                            int vx0, int vx1, int row0, int row1, PlaneS16 raw, PlaneS16 cost, PlaneS16 out,
+                            bool speckle, int newVal, int maxSize, int maxDiff,
+                            int32_t *labels, int32_t *sizes, int32_t *runlen, cudaStream_t st, int *launches,
+                            void (*after_rows)(void *) = nullptr, void *ctx = nullptr);   // hook between the row pass and the rest (stage timing)
 int launch_median3(int n, int W, int H, PlaneS16 src, PlaneS16 dst, cudaStream_t st, int *launches);
 
 // ---- morphology (morph.cu) ---------------------------------------------------------------------

@@ -268,27 +268,115 @@ __device__ __forceinline__ void load8_s16(const int16_t *p, int v[8])
     v[4] = (int16_t)(q.z & 0xFFFFu); v[5] = (int16_t)(q.z >> 16); v[6] = (int16_t)(q.w & 0xFFFFu); v[7] = (int16_t)(q.w >> 16);
 }
 
+// Row kernel, one thread block per (row, frame), 8 pixels per thread:
+//   VALIDATE: validateDisparity + valid-rectangle mask of the raw row (same arithmetic as validate_mask_kernel),
+//             written to `img`; then, if `runs`, the row-run pass of the speckle filter on the values still in registers
+//   else    : the row-run pass alone on `img`.
+struct ValArgs {
+    int minD, nd, d12, lofs, W1, vx0, vx1, row0, row1;
+    PlaneS16 raw, cost;
+};
+
+template <bool VALIDATE>
 __global__ void __launch_bounds__(1024)
-speckle_rowruns8_kernel(int W, int H, PlaneS16 img, int newVal, int maxDiff, int32_t *labels, int32_t *sizes, int32_t *runlen)
+post_row8_kernel(int W, int H, PlaneS16 img, ValArgs va, int runs, int newVal, int maxDiff,
+                 int32_t *labels, int32_t *sizes, int32_t *runlen)
 {
-    extern __shared__ int cnt[];                         // [W] pixels per run, indexed by run-start column
-    __shared__ int warp_last[32];
+    extern __shared__ __align__(16) int row_smem[];
+    int *cnt = row_smem;                                 // [W] pixels per run, indexed by run-start column
+    __shared__ int warp_last[32], warp_tail[32];
     const int y = blockIdx.x, f = blockIdx.y;
-    const int16_t *row = img.p + (size_t)f * img.frame + (size_t)y * img.pitch;
-    const size_t rowbase = ((size_t)f * H + y) * W;
-    int32_t *lab = labels + rowbase, *siz = sizes + rowbase, *rlen = runlen + rowbase;
+    int16_t *row = img.p + (size_t)f * img.frame + (size_t)y * img.pitch;
     const int x0 = threadIdx.x * 8;
     const bool active = x0 < W;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    for (int x = threadIdx.x; x < W; x += blockDim.x) cnt[x] = 0;
     int v[8];
-    if (active) load8_s16(row + x0, v);
-    else {
+    if (VALIDATE) {
+        uint32_t *key = reinterpret_cast<uint32_t *>(row_smem + W);            // [W]
+        int16_t *sd = reinterpret_cast<int16_t *>(key + W);                    // [W] raw disparity row
+        const int INV = (va.minD - 1) * 16;
+        const bool inrows = y >= va.row0 && y < va.row1;                       // block-uniform
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = INV;
+        if (inrows) {
+            if (active) {
+                load8_s16(va.raw.p + (size_t)f * va.raw.frame + (size_t)y * va.raw.pitch + x0, v);
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    if (x0 + k < va.lofs || x0 + k >= va.lofs + va.W1) v[k] = INV;
+                if (va.d12 >= 0) {
+                    uint32_t pk[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) pk[k] = (uint32_t)(uint16_t)v[2 * k] | ((uint32_t)(uint16_t)v[2 * k + 1] << 16);
+                    *reinterpret_cast<uint4 *>(sd + x0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    reinterpret_cast<uint4 *>(key + x0)[0] = make_uint4(~0u, ~0u, ~0u, ~0u);
+                    reinterpret_cast<uint4 *>(key + x0)[1] = make_uint4(~0u, ~0u, ~0u, ~0u);
+                }
+            }
+            if (va.d12 >= 0) {
+                __syncthreads();
+                const int minX1 = max(va.minD + va.nd, 0), maxX1 = W + min(va.minD, 0);
+                if (active) {
+                    int c[8];
+                    load8_s16(va.cost.p + (size_t)f * va.cost.frame + (size_t)y * va.cost.pitch + x0, c);
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        const int x = x0 + k, d = v[k];
+                        if (x < minX1 || x >= maxX1 || d == INV) continue;
+                        const int x2 = x - ((d + 8) >> 4);
+                        if (x2 < 0 || x2 >= W) continue;
+                        atomicMin(&key[x2], ((uint32_t)(uint16_t)c[k] << 16) | (uint32_t)x);
+                    }
+                }
+                __syncthreads();
+                if (active) {
+                    const int lim = va.d12 * 16;
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        const int x = x0 + k, d = v[k];
+                        if (x < minX1 || x >= maxX1 || d == INV) continue;
+                        const int xa = x - (d >> 4), xb = x - ((d + 15) >> 4);
+                        bool bad = true;
+                        if (0 <= xa && xa < W) {
+                            const uint32_t kk = key[xa];
+                            const int d2 = (kk == 0xFFFFFFFFu) ? INV : (int)sd[kk & 0xFFFFu];
+                            bad = bad && (d2 > INV) && (abs(d2 - d) > lim);
+                        } else bad = false;
+                        if (0 <= xb && xb < W) {
+                            const uint32_t kk = key[xb];
+                            const int d2 = (kk == 0xFFFFFFFFu) ? INV : (int)sd[kk & 0xFFFFu];
+                            bad = bad && (d2 > INV) && (abs(d2 - d) > lim);
+                        } else bad = false;
+                        if (bad) v[k] = INV;
+                    }
+                }
+            }
+        }
+        if (active) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                if (x0 + k < va.vx0 || x0 + k >= va.vx1) v[k] = INV;
+#pragma unroll
+            for (int k = 0; k < 4; k++) pk[k] = (uint32_t)(uint16_t)v[2 * k] | ((uint32_t)(uint16_t)v[2 * k + 1] << 16);
+            *reinterpret_cast<uint4 *>(row + x0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+        if (!runs) return;                                                    // block-uniform
+    } else {
+        if (active) load8_s16(row + x0, v);
+    }
+    if (!active) {
 #pragma unroll
         for (int k = 0; k < 8; k++) v[k] = newVal;
     }
+    // ---- row runs ------------------------------------------------------------------------------------------
+    const size_t rowbase = ((size_t)f * H + y) * W;
+    int32_t *lab = labels + rowbase, *siz = sizes + rowbase, *rlen = runlen + rowbase;
+    for (int x = threadIdx.x; x < W; x += blockDim.x) cnt[x] = 0;
+    if (lane == 31) warp_tail[wid] = v[7];
+    __syncthreads();
     int prev = __shfl_up_sync(0xFFFFFFFFu, v[7], 1);
-    if (lane == 0) prev = (active && x0 > 0) ? (int)row[x0 - 1] : newVal;
+    if (lane == 0) prev = wid > 0 ? warp_tail[wid - 1] : newVal;
     // bit k: pixel x0 + k continues the run of its left neighbour
     uint32_t cont = 0u;
 #pragma unroll
@@ -401,24 +489,32 @@ speckle_runs8_kernel(int W, int H, PlaneS16 img, int newVal, int maxSize, int32_
     }
 }
 
-int launch_speckle(int n, int W, int H, PlaneS16 img, int newVal, int maxSize, int maxDiff,
-                   int32_t *labels, int32_t *sizes, cudaStream_t st, int *launches, int32_t *runlen)
+// can launch_speckle take the 8-pixel kernels for this geometry?  (launch_validate_speckle relies on it)
+static bool speckle_vec_ok(int W, PlaneS16 img, const int32_t *labels)
+{
+    return W % 8 == 0 && W <= 8192 && ((reinterpret_cast<uintptr_t>(img.p) | (img.pitch * 2) | (img.frame * 2)) & 15) == 0 &&
+           (reinterpret_cast<uintptr_t>(labels) & 15) == 0 && !getenv("RTDM_SPECKLE_SCALAR");
+}
+
+static int launch_speckle_impl(int n, int W, int H, PlaneS16 img, int newVal, int maxSize, int maxDiff,
+                               int32_t *labels, int32_t *sizes, cudaStream_t st, int *launches, int32_t *runlen, bool rowruns_done)
 {
     if (n <= 0) return 0;
-    const bool vec = W % 8 == 0 && W <= 8192 && ((reinterpret_cast<uintptr_t>(img.p) | (img.pitch * 2) | (img.frame * 2)) & 15) == 0 &&
-                     (reinterpret_cast<uintptr_t>(labels) & 15) == 0 && !getenv("RTDM_SPECKLE_SCALAR");
+    const bool vec = speckle_vec_ok(W, img, labels);
     if (vec) {
         const size_t N8 = ((size_t)W * H + 7) / 8;
         const int nt = ((W / 8) + 31) & ~31;
-        speckle_rowruns8_kernel<<<dim3(H, n), nt, (size_t)W * sizeof(int), st>>>(W, H, img, newVal, maxDiff, labels, sizes, runlen);
+        if (!rowruns_done)
+            post_row8_kernel<false><<<dim3(H, n), nt, (size_t)W * sizeof(int), st>>>(W, H, img, ValArgs(), 1, newVal, maxDiff, labels, sizes, runlen);
         if (H > 1)
             speckle_vmerge8_kernel<<<dim3(cdiv(W / 8, 128), H - 1, n), 128, 0, st>>>(W, H, img, newVal, maxDiff, labels);
         speckle_runs8_kernel<0><<<dim3((unsigned)((N8 + 255) / 256), n), 256, 0, st>>>(W, H, img, newVal, maxSize, labels, sizes, runlen);
         speckle_runs8_kernel<1><<<dim3((unsigned)((N8 + 255) / 256), n), 256, 0, st>>>(W, H, img, newVal, maxSize, labels, sizes, runlen);
-        if (launches) (*launches) += (H > 1) ? 4 : 3;
+        if (launches) (*launches) += ((H > 1) ? 4 : 3) - (rowruns_done ? 1 : 0);
         RTDM_CUDA(cudaGetLastError());
         return 0;
     }
+    if (rowruns_done) { set_error("speckle: fused row pass without the vector path"); return -RTDM_EINVAL; }
     speckle_rowruns_kernel<<<dim3(H, n), 256, (size_t)W * sizeof(int), st>>>(W, H, img, newVal, maxDiff, labels, sizes, runlen);
     if (H > 1)
         speckle_vmerge_kernel<<<dim3(cdiv(W, 256), H - 1, n), 256, 0, st>>>(W, H, img, newVal, maxDiff, labels);
@@ -428,6 +524,40 @@ int launch_speckle(int n, int W, int H, PlaneS16 img, int newVal, int maxSize, i
     if (launches) (*launches) += (H > 1) ? 4 : 3;
     RTDM_CUDA(cudaGetLastError());
     return 0;
+}
+
+int launch_speckle(int n, int W, int H, PlaneS16 img, int newVal, int maxSize, int maxDiff,
+                   int32_t *labels, int32_t *sizes, cudaStream_t st, int *launches, int32_t *runlen)
+{
+    return launch_speckle_impl(n, W, H, img, newVal, maxSize, maxDiff, labels, sizes, st, launches, runlen, false);
+}
+
+// validateDisparity + valid-rectangle mask (raw, cost -> out), then filterSpeckles on `out` when speckle is set.
+// With 16-byte aligned rows and W % 8 == 0 the two row passes are one kernel.
+int launch_validate_speckle(int n, int W, int H, int minD, int nd, int d12, int lofs, int W1,
+                            int vx0, int vx1, int row0, int row1, PlaneS16 raw, PlaneS16 cost, PlaneS16 out,
+                            bool speckle, int newVal, int maxSize, int maxDiff,
+                            int32_t *labels, int32_t *sizes, int32_t *runlen, cudaStream_t st, int *launches,
+                            void (*after_rows)(void *), void *ctx)
+{
+    if (n <= 0) { if (after_rows) after_rows(ctx); return 0; }
+    const auto al16 = [](PlaneS16 p) { return ((reinterpret_cast<uintptr_t>(p.p) | (p.pitch * 2) | (p.frame * 2)) & 15) == 0; };
+    if (speckle_vec_ok(W, out, labels) && al16(raw) && al16(cost) && !getenv("RTDM_POST_UNFUSED")) {
+        ValArgs va;
+        va.minD = minD; va.nd = nd; va.d12 = d12; va.lofs = lofs; va.W1 = W1; va.vx0 = vx0; va.vx1 = vx1; va.row0 = row0; va.row1 = row1;
+        va.raw = raw; va.cost = cost;
+        const int nt = ((W / 8) + 31) & ~31;
+        post_row8_kernel<true><<<dim3(H, n), nt, (size_t)W * 10 + 16, st>>>(W, H, out, va, speckle ? 1 : 0, newVal, maxDiff, labels, sizes, runlen);
+        if (launches) (*launches)++;
+        RTDM_CUDA(cudaGetLastError());
+        if (after_rows) after_rows(ctx);
+        if (!speckle) return 0;
+        return launch_speckle_impl(n, W, H, out, newVal, maxSize, maxDiff, labels, sizes, st, launches, runlen, true);
+    }
+    int rc = launch_validate_mask(n, W, H, minD, nd, d12, lofs, W1, vx0, vx1, row0, row1, raw, cost, out, st, launches);
+    if (after_rows) after_rows(ctx);
+    if (rc || !speckle) return rc;
+    return launch_speckle_impl(n, W, H, out, newVal, maxSize, maxDiff, labels, sizes, st, launches, runlen, false);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -35,6 +35,21 @@ def test_speckle_random_and_adversarial(gpu, orc):
     assert np.array_equal(gpu.filter_speckles(a, -16, 100, 32), orc.filter_speckles(a, -16, 100, 32))
 
 
+def test_speckle_vector_and_scalar_kernels_agree(gpu, orc, monkeypatch):
+    """W % 8 == 0 takes the 8-pixels-per-thread kernels; RTDM_SPECKLE_SCALAR forces the per-pixel ones."""
+    rng = np.random.default_rng(31)
+    for (W, H) in [(8, 1), (8, 9), (40, 50), (1280, 40), (2048, 3)]:
+        a = (rng.integers(0, 4, (H, W)) * 24).astype(np.int16)
+        a[rng.random((H, W)) < 0.3] = -16
+        a[:, : W // 3] = 48                                   # long runs crossing many threads
+        ref = orc.filter_speckles(a, -16, 60, 24)
+        monkeypatch.delenv("RTDM_SPECKLE_SCALAR", raising=False)
+        assert np.array_equal(gpu.filter_speckles(a, -16, 60, 24), ref), (W, H, "vector")
+        monkeypatch.setenv("RTDM_SPECKLE_SCALAR", "1")
+        assert np.array_equal(gpu.filter_speckles(a, -16, 60, 24), ref), (W, H, "scalar")
+    monkeypatch.delenv("RTDM_SPECKLE_SCALAR", raising=False)
+
+
 def test_median_matches_golden_and_oracle(gpu, orc):
     g = load_golden("post_median_131x97")
     assert np.array_equal(gpu.median3_s16(g["src"]), g["median"])
