@@ -684,6 +684,141 @@ sgbm_path4_kernel(PathArgs a)
 }
 
 // ------------------------------------------------------------------------------------------------
+// Row sweep: the three paths that come from the previous row (r = (-1,dy'), (0,dy'), (+1,dy')) advance together, so
+// C is read once and S is read-modified-written once for three directions instead of three times each.
+// One launch handles a tile of SW_R image rows for every frame; a CTA owns X = NS - 2*SW_R adjacent columns and
+// recomputes SW_R halo columns on both sides (a diagonal chain crosses at most one column per row, so everything
+// an owned pixel needs within the tile starts inside the halo).  LPC lanes per column as in sgbm_path4_kernel:
+// the vertical path's L stays in registers, the two diagonal paths hand their L to the neighbouring column through
+// shared memory (double buffered, one barrier per row).  Between tiles the last row's L of all three paths and
+// their minima travel through a small global "frontier" buffer (ping-pong).
+// ------------------------------------------------------------------------------------------------
+constexpr int SW_R = 8;
+
+struct SweepArgs {
+    const uint32_t *C; uint32_t *S; size_t frame_words;
+    const uint32_t *Fin; uint32_t *Fout;     // frontier [3][W1][wordsD] per frame (0: diagonal from x-1, 1: vertical, 2: diagonal from x+1)
+    const uint32_t *Min; uint32_t *Mout;     // minima   [3][W1] per frame
+    size_t frame_front;                      // words between consecutive frames of the four arrays above
+    int W1, H, P1, P2;
+    int ystart, ystep, nrows;                // rows of this tile: ystart, ystart + ystep, ...
+    int first;                               // first tile of the sweep: predecessors are outside the image
+};
+
+template <int LPC>
+__device__ __forceinline__ void path_core(const uint4 Lp, const uint32_t minLp, const uint4 c, int sl, uint32_t P1x2, uint32_t P2, uint32_t (&t)[4], uint32_t &m)
+{
+    uint32_t left = __shfl_up_sync(0xFFFFFFFFu, Lp.w, 1, LPC);
+    uint32_t right = __shfl_down_sync(0xFFFFFFFFu, Lp.x, 1, LPC);
+    if (sl == 0) left = 0x7FFF0000u;
+    if (sl == LPC - 1) right = 0x00007FFFu;
+    const uint32_t dx2 = (P2 + minLp) * 0x00010001u;
+    const uint32_t w[6] = {left, Lp.x, Lp.y, Lp.z, Lp.w, right};
+    const uint32_t cc[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint32_t lm1 = __byte_perm(w[k], w[k + 1], 0x5432);
+        const uint32_t lp1 = __byte_perm(w[k + 1], w[k + 2], 0x5432);
+        uint32_t v = __vimin3_u16x2(w[k + 1], __vadd2(lm1, P1x2), __vadd2(lp1, P1x2));
+        v = min2(v, dx2);
+        t[k] = __vsub2(__vadd2(v, cc[k]), dx2);
+    }
+    const uint32_t mm = min2(min2(t[0], t[1]), min2(t[2], t[3]));
+    m = min(mm & 0xFFFFu, mm >> 16);
+}
+
+template <int LPC, bool SAFE3>
+__global__ void __launch_bounds__(1024, 1)
+sgbm_sweep_kernel(SweepArgs a)
+{
+    constexpr int NS = 1024 / LPC, X = NS - 2 * SW_R, WQ = LPC;      // slots, owned columns, uint4 per column
+    extern __shared__ __align__(16) uint8_t sw[];
+    uint4 *exL = reinterpret_cast<uint4 *>(sw);                       // [2][NS + 2][WQ]  L of the path from x-1, by producing slot + 1
+    uint4 *exR = exL + 2 * (NS + 2) * WQ;                             // [2][NS + 2][WQ]  L of the path from x+1
+    uint32_t *mnL = reinterpret_cast<uint32_t *>(exR + 2 * (NS + 2) * WQ);   // [2][NS + 2]
+    uint32_t *mnR = mnL + 2 * (NS + 2);
+    const int tid = threadIdx.x, j = tid / LPC, sl = tid % LPC, grp = (tid & 31) / LPC;
+    const int f = blockIdx.y;
+    const int x = blockIdx.x * X - SW_R + j;
+    const bool inimg = x >= 0 && x < a.W1;
+    const bool own = inimg && j >= SW_R && j < SW_R + X;
+    const int wordsD = 4 * LPC;
+    // zero both exchange buffers (pads and out-of-image slots stay zero: L = 0, min = 0)
+    for (int i = tid; i < 2 * 2 * (NS + 2) * WQ; i += 1024) exL[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < 2 * 2 * (NS + 2); i += 1024) mnL[i] = 0u;
+    __syncthreads();
+    const size_t fw = (size_t)a.W1 * wordsD;                          // words per frontier direction
+    uint4 Lv = make_uint4(0u, 0u, 0u, 0u);
+    uint32_t minV = 0u;
+    if (!a.first && inimg) {
+        const uint32_t *F = a.Fin + (size_t)f * a.frame_front + (size_t)x * wordsD + sl * 4;
+        const uint32_t *M = a.Min + (size_t)f * a.frame_front + x;
+        exL[(0 * (NS + 2) + j + 1) * WQ + sl] = *reinterpret_cast<const uint4 *>(F);
+        Lv = *reinterpret_cast<const uint4 *>(F + fw);
+        exR[(0 * (NS + 2) + j + 1) * WQ + sl] = *reinterpret_cast<const uint4 *>(F + 2 * fw);
+        minV = M[a.W1];
+        if (sl == 0) { mnL[j + 1] = M[0]; mnR[j + 1] = M[2 * a.W1]; }
+    }
+    const uint32_t P1x2 = (uint32_t)a.P1 * 0x00010001u, P2 = (uint32_t)a.P2;
+    const long long rowq = (long long)a.ystep * a.W1 * (wordsD / 4);  // uint4 units per row step
+    const size_t off = (((size_t)f * a.frame_words) + ((size_t)a.ystart * a.W1 + (inimg ? x : 0)) * wordsD) / 4 + sl;
+    const uint4 *cp = reinterpret_cast<const uint4 *>(a.C) + off;
+    uint4 *sp = reinterpret_cast<uint4 *>(a.S) + off;
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    uint4 c = inimg ? __ldg(cp) : z, s = own ? *sp : z;
+    uint4 tL = z, tR = z;
+    uint32_t mL = 0u, mR = 0u;
+    __syncthreads();
+    for (int r = 0; r < a.nrows; r++) {
+        const int b = r & 1;
+        const bool more = r + 1 < a.nrows;
+        const uint4 cn = (inimg && more) ? __ldg(cp + rowq) : z;
+        const uint4 sn = (own && more) ? sp[rowq] : z;
+        const uint4 pL = exL[(b * (NS + 2) + j) * WQ + sl];           // path from (x-1, previous row): slot j-1
+        const uint4 pR = exR[(b * (NS + 2) + j + 2) * WQ + sl];       // path from (x+1, previous row): slot j+1
+        const uint32_t pmL = mnL[b * (NS + 2) + j], pmR = mnR[b * (NS + 2) + j + 2];
+        uint32_t t0[4], t1[4], t2[4], m0, m1, m2;
+        path_core<LPC>(pL, pmL, c, sl, P1x2, P2, t0, m0);
+        path_core<LPC>(Lv, minV, c, sl, P1x2, P2, t1, m1);
+        path_core<LPC>(pR, pmR, c, sl, P1x2, P2, t2, m2);
+        mL = group_min_u32<LPC>(m0, grp);
+        minV = group_min_u32<LPC>(m1, grp);
+        mR = group_min_u32<LPC>(m2, grp);
+        tL = make_uint4(t0[0], t0[1], t0[2], t0[3]);
+        Lv = make_uint4(t1[0], t1[1], t1[2], t1[3]);
+        tR = make_uint4(t2[0], t2[1], t2[2], t2[3]);
+        if (inimg) {
+            exL[((b ^ 1) * (NS + 2) + j + 1) * WQ + sl] = tL;
+            exR[((b ^ 1) * (NS + 2) + j + 1) * WQ + sl] = tR;
+            if (sl == 0) { mnL[(b ^ 1) * (NS + 2) + j + 1] = mL; mnR[(b ^ 1) * (NS + 2) + j + 1] = mR; }
+        }
+        if (own) {
+            const uint32_t sv[4] = {s.x, s.y, s.z, s.w};
+            uint32_t o[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (SAFE3) o[k] = min2(sv[k] + t0[k] + t1[k] + t2[k], 0x7FFF7FFFu);       // no 16-bit overflow possible
+                else o[k] = min2(__vadd2(min2(__vadd2(min2(__vadd2(sv[k], t0[k]), 0x7FFF7FFFu), t1[k]), 0x7FFF7FFFu), t2[k]), 0x7FFF7FFFu);
+            }
+            *sp = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        c = cn; s = sn;
+        cp += rowq; sp += rowq;
+        __syncthreads();
+    }
+    if (own) {
+        uint32_t *F = a.Fout + (size_t)f * a.frame_front + (size_t)x * wordsD + sl * 4;
+        *reinterpret_cast<uint4 *>(F) = tL;
+        *reinterpret_cast<uint4 *>(F + fw) = Lv;
+        *reinterpret_cast<uint4 *>(F + 2 * fw) = tR;
+        if (sl == 0) {
+            uint32_t *M = a.Mout + (size_t)f * a.frame_front + x;
+            M[0] = mL; M[a.W1] = minV; M[2 * a.W1] = mR;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // left-right check and sub-pixel fit from the per-pixel records of the fused last path; one CTA per (row, frame).
 // Same arithmetic as the second half of sgbm_wta_kernel.
 // ------------------------------------------------------------------------------------------------
@@ -872,6 +1007,9 @@ size_t sgbm_work_bytes(const SgbmGeom &g, size_t *planes, size_t *vol)
     size_t pl = (size_t)12 * g.H * Wp;
     if (sgbm_fused_cost(g))                                            // GL + GR blocks of sgbm_planes2_kernel
         pl = std::max(pl, (size_t)g.H * ((size_t)(g.W1 + 2 * PADL) * 32 + (size_t)12 * align_up((size_t)g.W + 2 * PADR, 8) * 2));
+    if (g.W1 > 0 && (g.D == 64 || g.D == 128))                          // WTA records + two sweep frontiers reuse the block
+        pl = std::max(pl, align_up((size_t)8 * g.H * g.W1, 256) + 2 * align_up(((size_t)3 * g.W1 * (g.D / 2) + (size_t)3 * g.W1) * 4, 256));
+    pl = align_up(pl, 256);
     const size_t v = (size_t)g.H * (g.W1 > 0 ? g.W1 : 0) * g.D;        // elements
     if (planes) *planes = pl;
     if (vol) *vol = v;
@@ -955,8 +1093,48 @@ int launch_sgbm(const SgbmGeom &g, int n, PlaneU8 left, PlaneU8 right, PlaneS16 
     const bool fast = (g.D == 128 || g.D == 64) && !getenv("RTDM_SGBM_OLDPATH");
     const bool fused = fast && g.uniq < 100 && !getenv("RTDM_SGBM_NOFUSE");
     const size_t frame_rec = w.frame_planes / 8;            // the BT planes are dead by now: their buffer takes the records
+    // the two vertical triplets as row sweeps (one C read and one S update for three paths)
+    const size_t rec_bytes = align_up((size_t)8 * g.H * g.W1, 256);
+    const size_t front_words = (size_t)3 * g.W1 * (g.D / 2), fmin_words = (size_t)3 * g.W1;
+    const size_t front_bytes = align_up((front_words + fmin_words) * 4, 256);
+    const bool sweep = fast && !getenv("RTDM_SGBM_NOSWEEP") && rec_bytes + 2 * front_bytes <= w.frame_planes;
+    const int pixmax = 2 * g.ftzero + 63, Lmax = 2 * g.P2 + g.bs * g.bs * pixmax;
+    const bool safe3 = 32767 + 3 * Lmax <= 65535;
+    auto launch_sweep = [&](int dy) -> int {
+        const int ntiles = cdiv(g.H, SW_R);
+        const int LPC = g.D / 8, NS = 1024 / LPC, X = NS - 2 * SW_R;
+        const size_t smem = (size_t)2 * 2 * (NS + 2) * LPC * 16 + (size_t)2 * 2 * (NS + 2) * 4;
+        for (int t = 0; t < ntiles; t++) {
+            SweepArgs a;
+            a.C = reinterpret_cast<const uint32_t *>(w.C); a.S = reinterpret_cast<uint32_t *>(w.S); a.frame_words = frame_words;
+            // frontier buffers live behind the WTA records inside every frame's (dead) planes block
+            uint8_t *fb = w.planes + rec_bytes;
+            uint32_t *F0 = reinterpret_cast<uint32_t *>(fb), *F1 = reinterpret_cast<uint32_t *>(fb + front_bytes);
+            a.Fin = (t & 1) ? F0 : F1; a.Fout = (t & 1) ? F1 : F0;
+            a.Min = a.Fin + front_words; a.Mout = a.Fout + front_words;
+            a.frame_front = w.frame_planes / 4;
+            a.W1 = g.W1; a.H = g.H; a.P1 = g.P1; a.P2 = g.P2;
+            a.ystart = dy > 0 ? t * SW_R : g.H - 1 - t * SW_R; a.ystep = dy; a.nrows = std::min(SW_R, g.H - t * SW_R);
+            a.first = t == 0;
+            const dim3 grid(cdiv(g.W1, X), n);
+#define RTDM_SWEEP(LPC_, SAFE_)                                                                                              \
+            do {                                                                                                             \
+                if (t == 0) RTDM_CUDA(cudaFuncSetAttribute(sgbm_sweep_kernel<LPC_, SAFE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+                sgbm_sweep_kernel<LPC_, SAFE_><<<grid, 1024, smem, st>>>(a);                                                 \
+            } while (0)
+            if (g.D == 128) { if (safe3) RTDM_SWEEP(16, true); else RTDM_SWEEP(16, false); }
+            else { if (safe3) RTDM_SWEEP(8, true); else RTDM_SWEEP(8, false); }
+#undef RTDM_SWEEP
+        }
+        if (launches) (*launches) += ntiles;
+        return 0;
+    };
     for (int k = 0; k < ndirs; k++) {
         const int di = (!hh && k == 4) ? 7 : k;
+        if (sweep && di >= 1 && di <= 6) {
+            if (di == 1 || di == 4) { const int rc = launch_sweep(di == 1 ? 1 : -1); if (rc) return rc; }
+            continue;                                       // di = 2, 3 / 5, 6 ride along
+        }
         PathArgs a;
         a.C = reinterpret_cast<const uint32_t *>(w.C); a.S = reinterpret_cast<uint32_t *>(w.S); a.frame_words = frame_words;
         a.W1 = g.W1; a.H = g.H; a.D = g.D; a.P1 = g.P1; a.P2 = g.P2; a.px = dirs[di][0]; a.py = dirs[di][1];
