@@ -139,12 +139,12 @@ def sgbm_compute(left, right, params: OrcParams, return_domain_flag=False):
 
 
 def sgbm_params(blockSize=5, minDisparity=0, numDisparities=128, uniquenessRatio=10, speckleWindowSize=100,
-                speckleRange=32, disp12MaxDiff=1, mode=0) -> OrcParams:
+                speckleRange=32, disp12MaxDiff=1, mode=0, P1=8 * 3 * 5 * 5, P2=32 * 3 * 5 * 5) -> OrcParams:
     """Parameters as SWSemiGlobalMatcher's constructor sets them (sgbm-sw.cpp:15-24)."""
     return make_params(preFilterCap=0, blockSize=blockSize, minDisparity=minDisparity,
                        numDisparities=numDisparities, uniquenessRatio=uniquenessRatio,
                        speckleWindowSize=speckleWindowSize, speckleRange=speckleRange,
-                       disp12MaxDiff=disp12MaxDiff, mode=mode, P1=8 * 3 * 5 * 5, P2=32 * 3 * 5 * 5)
+                       disp12MaxDiff=disp12MaxDiff, mode=mode, P1=P1, P2=P2)
 
 
 def morph(img, op, kw=10, kh=10):

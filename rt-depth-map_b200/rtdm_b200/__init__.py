@@ -266,14 +266,19 @@ class CUDAMatcherKonolige(_MatcherBase):
 class CUDASemiGlobalMatcher(_MatcherBase):
     """B200 peer of SWSemiGlobalMatcher; same constructor arguments (sgbm-sw.h:28-29).  P1/P2 are the
     reference's hard-coded 8*3*5*5 / 32*3*5*5 (sgbm-sw.cpp:17-18); ROI setters are no-ops
-    (sgbm-sw.h:32-33).  `mode` defaults to MODE_SGBM like the reference; MODE_HH selects 8 paths."""
+    (sgbm-sw.h:32-33).  `mode` defaults to MODE_SGBM like the reference; MODE_HH selects 8 paths; the
+    keyword-only P1 / P2 override the two penalties (cv::StereoSGBM::setP1 / setP2)."""
     _prefix = "rtdm_sgbm"
 
     def __init__(self, blockSize, minDisparity, numOfDisparities, uniquenessRatio, speckleWindowSize,
-                 speckleRange, disp12MaxDiff, *, mode=MODE_SGBM, max_width=1280, max_height=720,
+                 speckleRange, disp12MaxDiff, *, mode=MODE_SGBM, P1=None, P2=None, max_width=1280, max_height=720,
                  max_batch=1, device=0):
         p = RtdmParams()
         lib().rtdm_params_default_sgbm(C.byref(p))
+        if P1 is not None:
+            p.P1 = P1
+        if P2 is not None:
+            p.P2 = P2
         p.blockSize, p.minDisparity, p.numDisparities = blockSize, minDisparity, numOfDisparities
         p.uniquenessRatio, p.speckleWindowSize, p.speckleRange = uniquenessRatio, speckleWindowSize, speckleRange
         p.disp12MaxDiff, p.mode = disp12MaxDiff, mode

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 def _mk(rt, p, W, H, **kw):
     return rt.CUDASemiGlobalMatcher(p["blockSize"], p["minDisparity"], p["numDisparities"], p["uniquenessRatio"],
                                     p["speckleWindowSize"], p["speckleRange"], p["disp12MaxDiff"],
-                                    mode=p.get("mode", 0), max_width=W, max_height=H, **kw)
+                                    mode=p.get("mode", 0), P1=p.get("P1"), P2=p.get("P2"), max_width=W, max_height=H, **kw)
 
 
 @pytest.mark.parametrize("name", golden_names("sgbm_"))
@@ -78,6 +78,44 @@ def test_sgbm_720p_full_size(gpu, orc, mode):
         v = out[i][out[i] != -16]
         assert v.min() >= 0 and v.max() <= 127 * 16 + 15
         assert (out[i][:, :127] == -16).all()
+
+
+@pytest.mark.parametrize("env", [None, "RTDM_SGBM_NOSWEEP", "RTDM_SGBM_NOFUSE", "RTDM_SGBM_OLDCOST", "RTDM_SGBM_OLDPATH"])
+def test_sgbm_kernel_variants_agree_with_oracle(gpu, orc, env, monkeypatch):
+    """Every kernel choice of the matching stage (row sweeps / per-direction chains, WTA fused into the last path or
+    separate, fused or two-pass cost volume, 4-word or generic path kernel) is the same arithmetic."""
+    from rtdm_b200 import synth
+    for v in ("RTDM_SGBM_NOSWEEP", "RTDM_SGBM_NOFUSE", "RTDM_SGBM_OLDCOST", "RTDM_SGBM_OLDPATH"):
+        monkeypatch.delenv(v, raising=False)
+    if env:
+        monkeypatch.setenv(env, "1")
+    for (W, H, nd, bs, mode) in [(400, 150, 128, 5, 1), (331, 97, 64, 3, 0), (520, 60, 64, 7, 1)]:
+        p = dict(blockSize=bs, minDisparity=0, numDisparities=nd, uniquenessRatio=12, speckleWindowSize=50,
+                 speckleRange=2, disp12MaxDiff=1, mode=mode)
+        L, R, _ = synth.stereo_pair(W, H, nd, 4100 + W)
+        ref, outside = orc.sgbm_compute(L, R, orc.sgbm_params(**p), return_domain_flag=True)
+        assert not outside
+        got = _mk(gpu, p, W, H).compute(L, R)
+        assert np.array_equal(got, ref), (env, W, H, nd, bs, mode, int((got != ref).sum()))
+
+
+def test_sgbm_large_penalties_take_the_stepwise_clamp(gpu, orc):
+    """P2 large enough that three path costs next to S could overflow 16 bits (2*P2 + bs^2*93 > 10922): the sweep
+    kernel then clamps after every addition (cv::StereoSGBM's saturating adds) instead of once.  5-path mode, so
+    that S itself stays below the saturation value (the oracle's domain)."""
+    from rtdm_b200 import synth
+    checked = 0
+    for P2 in (4400, 4800):
+        p = dict(blockSize=5, minDisparity=0, numDisparities=64, uniquenessRatio=5, speckleWindowSize=0,
+                 speckleRange=0, disp12MaxDiff=1, mode=0, P1=700, P2=P2)
+        L, R, _ = synth.stereo_pair(360, 120, 64, 99)
+        ref, outside = orc.sgbm_compute(L, R, orc.sgbm_params(**p), return_domain_flag=True)
+        if outside:
+            continue
+        got = _mk(gpu, p, 360, 120).compute(L, R)
+        assert np.array_equal(got, ref), (P2, int((got != ref).sum()))
+        checked += 1
+    assert checked >= 1
 
 
 def test_sgbm_errors(gpu):
