@@ -346,20 +346,24 @@ def run_ours(args):
                 "stage_ms_per_step": {k: v / stage_calls for k, v in stage_ms.items()},
             }
         if stage_calls and wl == "sgbm720":
-            k_ms = stage_ms["matching"] / stage_calls           # planes + cost + box + 8 path launches + WTA, B frames
+            # the matching stage as a whole (planes, fused cost, first path, row sweeps, last path + WTA, LR check):
+            # SURVEY.md 8(d) rates it against the integer pipes (96 ops/de for MODE_HH); the HBM figures sit beside it
+            k_ms = stage_ms["matching"] / stage_calls
             ip = rt.measure_int_peak(local)
-            de = B * (W - ND) * H * ND
             hbm_ach = B * HBM_BYTES_PER_FRAME[wl] / (k_ms * 1e-3) / 1e9
             ach_int = B * W * H * ND * OPS_PER_DE[wl] / (k_ms * 1e-3) / 1e12
+            traffic = 2190e6 * B            # profiles/r01_launches_E_sgbm_hh.csv: 17.5 GB of DRAM traffic per 8 frames
             roofline = {
-                "kernel": "sgbm matching stage (sgbm_path_kernel x8 dominant, + cost/box/WTA)", "bound": "hbm",
-                "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
-                "traffic": 598e6 * 8 * B + 2.1e9 / 4 * B,
-                "traffic_note": "ncu dram bytes, profiles/r01_launches_sgbm.csv: 598 MB per frame per path launch x 8 + cost/box/WTA",
-                "peak_source": hbm_src, "algorithmic_bytes_per_frame": HBM_BYTES_PER_FRAME[wl],
-                "stage_ms_per_launch": k_ms, "frames_per_launch": B,
-                "int_alu": {"achieved": ach_int, "peak": ip["iadd3_tiops"], "unit": "Tiop/s", "frac": ach_int / ip["iadd3_tiops"],
-                            "ops_per_de": OPS_PER_DE[wl]},
+                "kernel": "sgbm matching stage (sgbm_sweep_kernel x2 passes dominant, + cost_fused, path4 first/last, lr)",
+                "bound": "int_alu", "achieved": ach_int, "peak": ip["iadd3_tiops"], "unit": "Tiop/s", "frac": ach_int / ip["iadd3_tiops"],
+                "traffic": traffic,
+                "traffic_note": "ncu dram bytes summed over the stage's launches, profiles/r01_launches_E_sgbm_hh.csv: 2.19 GB per frame",
+                "ops_per_de": OPS_PER_DE[wl], "stage_ms_per_launch": k_ms, "frames_per_launch": B,
+                "peak_source": "rtdm_measure_int_peak on this GPU (dependent-free IADD3, lane-ops/s)",
+                "int_peak_detail": ip,
+                "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak, "peak_source": hbm_src,
+                        "algorithmic_bytes_per_frame": HBM_BYTES_PER_FRAME[wl],
+                        "moved_gbs": traffic / (k_ms * 1e-3) / 1e9, "moved_frac_of_peak": traffic / (k_ms * 1e-3) / 1e9 / hbm_peak},
                 "stage_ms_per_step": {k: v / stage_calls for k, v in stage_ms.items()},
             }
         # ---- CPU baseline on a bounded sample (rank 0, N=1 only) -----------------------------------

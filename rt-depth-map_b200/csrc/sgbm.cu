@@ -206,19 +206,22 @@ __global__ void __launch_bounds__(256)
 sgbm_planes2_kernel(PlaneU8 left, PlaneU8 right, uint8_t *planes, size_t frame_planes, int W, int H, int ftzero,
                     int minX1, int W1, int LW, int WR)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    // a warp covers 30 pixels: lanes 1..30 own one each, lanes 0 and 31 only supply the neighbours' plane values
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int x = (blockIdx.x * (blockDim.x >> 5) + wid) * 30 + lane - 1, y = blockIdx.y;
     const int f = blockIdx.z >> 1, img = blockIdx.z & 1;
-    if (x >= W) return;
     const uint8_t *src = img ? right.p + (size_t)f * right.frame : left.p + (size_t)f * left.frame;
     const size_t sp = img ? right.pitch : left.pitch;
     uint32_t val[6];
 #pragma unroll
     for (int pl = 0; pl < 2; pl++) {
-        const int v = bt_plane_value(src, sp, W, H, x, y, pl, ftzero);
-        const int a = x > 0 ? (v + bt_plane_value(src, sp, W, H, x - 1, y, pl, ftzero)) / 2 : v;
-        const int b = x < W - 1 ? (v + bt_plane_value(src, sp, W, H, x + 1, y, pl, ftzero)) / 2 : v;
+        const int v = (x >= 0 && x < W) ? bt_plane_value(src, sp, W, H, x, y, pl, ftzero) : 0;
+        const int vm = __shfl_up_sync(0xFFFFFFFFu, v, 1), vp = __shfl_down_sync(0xFFFFFFFFu, v, 1);
+        const int a = x > 0 ? (v + vm) / 2 : v;
+        const int b = x < W - 1 ? (v + vp) / 2 : v;
         val[pl * 3 + 0] = (uint32_t)v; val[pl * 3 + 1] = (uint32_t)min(min(a, b), v); val[pl * 3 + 2] = (uint32_t)max(max(a, b), v);
     }
+    if (lane == 0 || lane == 31 || x >= W) return;
     const auto neg16 = [](uint32_t v) { return (0u - v) & 0xFFFFu; };
     uint8_t *pf = planes + (size_t)f * frame_planes;
     if (img == 0) {
@@ -1028,7 +1031,7 @@ int launch_sgbm(const SgbmGeom &g, int n, PlaneU8 left, PlaneU8 right, PlaneS16 
     if (fusedcost) {
         // 1-3. planes in staging format, then fused BT cost + horizontal and vertical windows + P2 -> C
         const int LW = g.W1 + 2 * PADL, WR = (int)align_up((size_t)g.W + 2 * PADR, 8);
-        sgbm_planes2_kernel<<<dim3(cdiv(g.W, 256), g.H, 2 * n), 256, 0, st>>>(left, right, w.planes, w.frame_planes, g.W, g.H,
+        sgbm_planes2_kernel<<<dim3(cdiv(g.W, 8 * 30), g.H, 2 * n), 256, 0, st>>>(left, right, w.planes, w.frame_planes, g.W, g.H,
                                                                             g.ftzero, g.minX1, g.W1, LW, WR);
         Cost2Args a;
         a.planes = w.planes; a.frame_planes = w.frame_planes;

@@ -5,20 +5,19 @@ G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 
 def launches(src, dst, title, per_launch_note):
     rows = list(csv.reader(l for l in open(os.path.join(G, src)) if l.startswith('"')))
-    h = rows[0]; ki, vi, mi = h.index('Kernel Name'), h.index('Metric Value'), h.index('Metric Name')
+    h = rows[0]; ki, vi, mi, ui, ii = h.index('Kernel Name'), h.index('Metric Value'), h.index('Metric Name'), h.index('Metric Unit'), h.index('ID')
+    scale = {'byte': 1e-6, 'Kbyte': 1e-3, 'Mbyte': 1.0, 'Gbyte': 1e3, 'ns': 1e-3, 'nsecond': 1e-3, 'us': 1.0, 'usecond': 1.0, 'ms': 1e3, 'msecond': 1e3}
     agg = collections.OrderedDict()
     for r in rows[1:]:
-        agg.setdefault(r[ki], collections.OrderedDict()).setdefault(r[mi], []).append(float(r[vi].replace(',', '')))
+        agg.setdefault(r[ki], collections.OrderedDict()).setdefault(r[mi], []).append(float(r[vi].replace(',', '')) * scale.get(r[ui], 1.0))
     out = [f"# {title}", f"# {per_launch_note}",
            "# per-launch times are cold-cache and serialised under ncu: compare SHARES, not absolutes",
-           "kernel,launches,avg_us,dram_read_MB,dram_write_MB,share_of_listed_time_pct"]
+           "kernel,launches,avg_us,dram_read_MB_per_launch,dram_write_MB_per_launch,share_of_listed_time_pct"]
     tot = sum(sum(m.get('gpu__time_duration.sum', [0])) for k, m in agg.items() if 'intpeak' not in k)
     for k, m in agg.items():
         if 'intpeak' in k: continue
         t = m.get('gpu__time_duration.sum', [0]); rd = m.get('dram__bytes_read.sum', [0]); wr = m.get('dram__bytes_write.sum', [0])
-        def mb(v, unit_guess):  # ncu prints bytes in varying units in csv; values here are already numeric in the unit column's scale
-            return v
-        out.append(f"\"{k}\",{len(t)},{sum(t)/len(t)/1e3:.1f},{sum(rd)/len(rd):.1f},{sum(wr)/len(wr):.1f},{sum(t)/tot*100:.1f}")
+        out.append(f"\"{k}\",{len(t)},{sum(t)/len(t):.1f},{sum(rd)/len(rd):.1f},{sum(wr)/len(wr):.1f},{sum(t)/tot*100:.1f}")
     open(os.path.join(P, dst), "w").write("\n".join(out) + "\n")
     print("\n".join(out))
 
@@ -34,11 +33,8 @@ def raw_summary(rep, dst):
     print("\n".join(out[:40]))
 
 if __name__ == "__main__":
-    launches("launches_r1d.csv", "r01_launches_D_bm_fast_kernel.csv",
-             "ncu launch list, round 1 capture D (fast BM kernel + binary filter fast path): python bench.py --steps 2 --warmup 3 --batch 16 --no-cpu",
-             "one launch = 16 frames 1280x720 nd=128; dram columns are in the unit ncu printed (MB for the large kernels, KB/B for tiny ones)")
-    launches("launches_sgbm_r1d.csv", "r01_launches_D_sgbm.csv",
-             "ncu launch list, round 1 capture D (SGBM MODE_HH): python bench.py --workload sgbm720 --steps 1 --warmup 3 --batch 4 --no-cpu",
-             "one launch = 4 frames 1280x720 nd=128; 8 path launches per step")
-    raw_summary("prof_bm_r1d.ncu-rep", "r01_prof_bm_r1d_summary.csv")
-    raw_summary("prof_sgbm_path_r1d.ncu-rep", "r01_prof_sgbm_path_r1d_summary.csv")
+    # usage: summarize_profiles.py launches <src.csv> <dst.csv> <title> <note>  |  raw <rep> <dst.csv>
+    if sys.argv[1] == "launches":
+        launches(*sys.argv[2:6])
+    else:
+        raw_summary(*sys.argv[2:4])
