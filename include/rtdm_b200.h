@@ -186,6 +186,34 @@ int rtdm_validate_disparity(int16_t *disp, size_t dstep, const int16_t *cost, si
                             int width, int height, int minDisparity, int numDisparities,
                             int disp12MaxDiff, int device);
 
+/* ---- depth epilogue (the step after the matcher) -------------------------- */
+/* Replaces, fused, what Estimator::run does with the matcher's output (estimator.cpp:75-77):
+ *     left_disp /= 16.;                                   CV_16S, round half to even
+ *     reprojectImageTo3D(left_disp, xyz, Q, true, CV_32F) Z = 10000 at the image's minimum disparity
+ *     calc_depth(xyz, ., filter_out, ., obj_boundings, .) estimator.cpp:206-263: per rectangle the mean of Z over
+ *                                                         pixels with mask != 0, Z != 10000, |Z| <= 10000
+ * disp  : the matcher's x16 CV_16S output (NOT yet divided), dstep in bytes
+ * Q     : 16 doubles, row-major 4x4 (cv::stereoRectify's reprojection matrix)
+ * mask  : the filter's output (CV_8UC1) or NULL for "every pixel", mstep in bytes
+ * rects : nregions x (x, y, width, height), inside the image (else -EINVAL, like cv::Mat::operator()(Rect))
+ * mean_z, count : nregions results (mean_z = 0 where count = 0); the reference's label is mean_z * unit / 10 cm
+ * xyz   : optional CV_32FC3 output image (height x width x 3 floats, xstep in bytes), NULL to skip
+ * The sums are accumulated in double like the reference's, but in parallel order: mean_z agrees with a serial
+ * sum to ~1e-13 relative. */
+typedef struct rtdm_depth rtdm_depth;
+int rtdm_depth_create(rtdm_depth **out, int max_width, int max_height, int max_regions, int device);
+void rtdm_depth_destroy(rtdm_depth *h);
+/* HOST pointers, synchronous */
+int rtdm_depth_run(rtdm_depth *h, const int16_t *disp, size_t dstep, int width, int height, const double *Q,
+                   const uint8_t *mask, size_t mstep, int nregions, const int *rects,
+                   double *mean_z, int *count, float *xyz, size_t xstep);
+/* disp / mask / xyz are DEVICE pointers (e.g. what rtdm_bm_compute_device and rtdm_morph_run_device just wrote);
+ * Q, rects, mean_z, count stay host pointers; the call returns after the few result bytes have arrived */
+int rtdm_depth_run_device(rtdm_depth *h, const int16_t *disp, size_t dstep, int width, int height, const double *Q,
+                          const uint8_t *mask, size_t mstep, int nregions, const int *rects,
+                          double *mean_z, int *count, float *xyz, size_t xstep, void *cuda_stream);
+int rtdm_depth_last_launches(const rtdm_depth *h);
+
 /* ---- measurement helper ------------------------------------------------------------------- */
 /* Measures the integer-ALU issue peak of the device with dependent-free packed-integer loops
  * (the roofline denominator SURVEY.md 8(d) asks for).  Results in 1e12 lane-ops/s. */

@@ -172,3 +172,69 @@ def median3_s16(img):
     out = np.empty((H, W), np.int16)
     lib().orc_median3_s16(_p(img), W, _p(out), W, W, H)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# Depth epilogue: numpy restatement of estimator.cpp:75-77 and calc_depth (:206-263)
+# ---------------------------------------------------------------------------------------------------
+DEPTH_BIG_Z = 10000.0
+
+
+def disp_div16(disp):
+    """`left_disp /= 16.` on a CV_16S Mat (estimator.cpp:75): saturate_cast<short>(cvRound(d / 16.)), i.e.
+    round-half-to-even of the x16 fixed-point disparity."""
+    d = np.asarray(disp, np.int16).astype(np.int32)
+    q, r = d >> 4, d & 15
+    q = q + (r > 8) + ((r == 8) & ((q & 1) == 1))
+    return q.astype(np.int16)
+
+
+def reproject_to_3d(disp16, Q):
+    """cv::reprojectImageTo3D(disp, xyz, Q, handleMissingValues = true, CV_32F) for a CV_16S disparity
+    (estimator.cpp:76).  OpenCV's arithmetic: the disparity goes through float, the homogeneous point is the
+    4x4 double product accumulated left to right from zero, its first three components are narrowed to float,
+    then multiplied by the double reciprocal of the fourth and narrowed again; pixels at the minimum disparity
+    of the whole image get Z = 10000."""
+    d16 = np.asarray(disp16, np.int16)
+    Q = np.asarray(Q, np.float64).reshape(4, 4)
+    H, W = d16.shape
+    x = np.arange(W, dtype=np.float64)[None, :].repeat(H, 0)
+    y = np.arange(H, dtype=np.float64)[:, None].repeat(W, 1)
+    d = d16.astype(np.float32).astype(np.float64)
+    hom = []
+    for i in range(4):
+        s = Q[i, 0] * x
+        s = s + Q[i, 1] * y
+        s = s + Q[i, 2] * d
+        s = s + Q[i, 3] * 1.0
+        hom.append(s)
+    out = np.empty((H, W, 3), np.float32)
+    with np.errstate(all="ignore"):
+        iw = 1.0 / hom[3]
+        for i in range(3):
+            out[..., i] = (hom[i].astype(np.float32).astype(np.float64) * iw).astype(np.float32)
+    out[..., 2][np.abs(d - float(d16.min())) <= np.finfo(np.float32).eps] = np.float32(DEPTH_BIG_Z)
+    return out
+
+
+def calc_depth(xyz, mask, rects):
+    """Estimator::calc_depth (estimator.cpp:206-263): per rectangle the mean Z over the pixels with mask != 0,
+    Z != 10000 (within FLT_EPSILON) and |Z| <= 10000, accumulated in double in row-major order.
+    Returns (mean_z [n] float64 -- 0 where no pixel qualifies --, count [n] int32)."""
+    means, counts = [], []
+    for (rx, ry, rw, rh) in rects:
+        z = xyz[ry:ry + rh, rx:rx + rw, 2].astype(np.float64)
+        m = np.asarray(mask)[ry:ry + rh, rx:rx + rw]
+        with np.errstate(all="ignore"):
+            skip = (np.abs(z - DEPTH_BIG_Z) < np.finfo(np.float32).eps) | (np.abs(z) > DEPTH_BIG_Z) | (m == 0)
+        res, cnt = 0.0, 0
+        for v in z[~skip].ravel():            # row-major, like the reference's two loops
+            res += float(v); cnt += 1
+        means.append(res / cnt if cnt else 0.0)
+        counts.append(cnt)
+    return np.asarray(means, np.float64), np.asarray(counts, np.int32)
+
+
+def distance_cm(mean_z, calibration_unit):
+    """The label the reference prints (estimator.cpp:252-254): res * calibrationUnit / 10, fixed, 0 decimals."""
+    return f"{mean_z * calibration_unit / 10.0:.0f} cm"

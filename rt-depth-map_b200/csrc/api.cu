@@ -892,6 +892,123 @@ extern "C" int rtdm_validate_disparity(int16_t *disp, size_t dstep, const int16_
     return rc;
 }
 
+// =================================================================================================
+// depth epilogue
+// =================================================================================================
+struct rtdm_depth {
+    int maxW, maxH, maxR, dev;
+    cudaStream_t st;
+    int16_t *dD; uint8_t *dM; float *dX;       // staging for the host entry point (dX allocated on first use)
+    int *rects, *minval, *counts; double *sums;
+    double *hsums; int *hcounts;               // pinned result staging
+    int launches;
+};
+
+extern "C" void rtdm_depth_destroy(rtdm_depth *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->dev);
+    cudaFree(h->dD); cudaFree(h->dM); cudaFree(h->dX); cudaFree(h->rects); cudaFree(h->minval); cudaFree(h->counts); cudaFree(h->sums);
+    cudaFreeHost(h->hsums); cudaFreeHost(h->hcounts);
+    if (h->st) cudaStreamDestroy(h->st);
+    delete h;
+}
+
+extern "C" int rtdm_depth_create(rtdm_depth **out, int max_width, int max_height, int max_regions, int device)
+{
+    if (!out) { set_error("depth_create: null argument"); return -RTDM_EINVAL; }
+    *out = nullptr;
+    if (max_width < 1 || max_height < 1 || max_regions < 0 || max_regions > 65535) { set_error("depth_create: bad geometry"); return -RTDM_EINVAL; }
+    int rc = check_device(device);
+    if (rc) return rc;
+    RTDM_CUDA(cudaSetDevice(device));
+    rtdm_depth *h = new (std::nothrow) rtdm_depth();
+    if (!h) return -RTDM_ENOMEM;
+    memset(h, 0, sizeof *h);
+    h->maxW = max_width; h->maxH = max_height; h->maxR = max_regions; h->dev = device;
+    const size_t N = (size_t)max_width * max_height, R = (size_t)std::max(max_regions, 1);
+    rc = cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) == cudaSuccess ? 0 : -RTDM_EIO;
+    if (!rc) rc = dev_alloc(&h->dD, N);
+    if (!rc) rc = dev_alloc(&h->dM, N);
+    if (!rc) rc = dev_alloc(&h->rects, 4 * R);
+    if (!rc) rc = dev_alloc(&h->minval, 1);
+    if (!rc) rc = dev_alloc(&h->counts, R);
+    if (!rc) rc = dev_alloc(&h->sums, R);
+    if (!rc) rc = cudaMallocHost((void **)&h->hsums, R * sizeof(double)) == cudaSuccess ? 0 : -RTDM_ENOMEM;
+    if (!rc) rc = cudaMallocHost((void **)&h->hcounts, R * sizeof(int)) == cudaSuccess ? 0 : -RTDM_ENOMEM;
+    if (rc) { rtdm_depth_destroy(h); return rc; }
+    *out = h;
+    return 0;
+}
+
+static int depth_run(rtdm_depth *h, const int16_t *disp, size_t dpitch, int W, int H, const double *Q, const uint8_t *mask, size_t mpitch,
+                     int nregions, const int *rects, double *mean_z, int *count, float *xyz, size_t xpitch, cudaStream_t st)
+{
+    if (nregions > 0) RTDM_CUDA(cudaMemcpyAsync(h->rects, rects, sizeof(int) * 4 * nregions, cudaMemcpyHostToDevice, st));
+    h->launches = 0;
+    int rc = launch_depth(disp, dpitch, W, H, Q, mask, mpitch, nregions, h->rects, h->minval, h->sums, h->counts, xyz, xpitch, st, &h->launches);
+    if (rc) return rc;
+    if (nregions > 0) {
+        RTDM_CUDA(cudaMemcpyAsync(h->hsums, h->sums, sizeof(double) * nregions, cudaMemcpyDeviceToHost, st));
+        RTDM_CUDA(cudaMemcpyAsync(h->hcounts, h->counts, sizeof(int) * nregions, cudaMemcpyDeviceToHost, st));
+    }
+    RTDM_CUDA(cudaStreamSynchronize(st));
+    for (int i = 0; i < nregions; i++) {
+        count[i] = h->hcounts[i];
+        mean_z[i] = h->hcounts[i] > 0 ? h->hsums[i] / h->hcounts[i] : 0.0;
+    }
+    return 0;
+}
+
+static int depth_check(rtdm_depth *h, const void *disp, int W, int H, const double *Q, int nregions, const int *rects,
+                       const double *mean_z, const int *count)
+{
+    if (!h || !disp || !Q || (nregions > 0 && (!rects || !mean_z || !count))) { set_error("depth: null argument"); return -RTDM_EINVAL; }
+    if (W < 1 || H < 1 || W > h->maxW || H > h->maxH || nregions < 0 || nregions > h->maxR) {
+        set_error("depth: geometry or region count exceeds what the handle was created for");
+        return -RTDM_EINVAL;
+    }
+    for (int i = 0; i < nregions; i++) {
+        const int *r = rects + 4 * i;
+        if (r[0] < 0 || r[1] < 0 || r[2] < 0 || r[3] < 0 || r[0] + r[2] > W || r[1] + r[3] > H) {
+            set_error("depth: rectangle outside the image");
+            return -RTDM_EINVAL;
+        }
+    }
+    return 0;
+}
+
+extern "C" int rtdm_depth_run_device(rtdm_depth *h, const int16_t *disp, size_t dstep, int width, int height, const double *Q,
+                                     const uint8_t *mask, size_t mstep, int nregions, const int *rects,
+                                     double *mean_z, int *count, float *xyz, size_t xstep, void *cuda_stream)
+{
+    int rc = depth_check(h, disp, width, height, Q, nregions, rects, mean_z, count);
+    if (rc) return rc;
+    if (dstep % 2 || xstep % 4) { set_error("depth: steps must be multiples of the element size"); return -RTDM_EINVAL; }
+    RTDM_CUDA(cudaSetDevice(h->dev));
+    return depth_run(h, disp, dstep / 2, width, height, Q, mask, mstep, nregions, rects, mean_z, count, xyz, xstep / 4,
+                     static_cast<cudaStream_t>(cuda_stream));
+}
+
+extern "C" int rtdm_depth_run(rtdm_depth *h, const int16_t *disp, size_t dstep, int width, int height, const double *Q,
+                              const uint8_t *mask, size_t mstep, int nregions, const int *rects,
+                              double *mean_z, int *count, float *xyz, size_t xstep)
+{
+    int rc = depth_check(h, disp, width, height, Q, nregions, rects, mean_z, count);
+    if (rc) return rc;
+    RTDM_CUDA(cudaSetDevice(h->dev));
+    const size_t W = (size_t)width;
+    RTDM_CUDA(cudaMemcpy2DAsync(h->dD, W * 2, disp, dstep, W * 2, height, cudaMemcpyHostToDevice, h->st));
+    if (mask) RTDM_CUDA(cudaMemcpy2DAsync(h->dM, W, mask, mstep, W, height, cudaMemcpyHostToDevice, h->st));
+    if (xyz && !h->dX) { rc = dev_alloc(&h->dX, (size_t)h->maxW * h->maxH * 3); if (rc) return rc; }
+    rc = depth_run(h, h->dD, W, width, height, Q, mask ? h->dM : nullptr, W, nregions, rects, mean_z, count, xyz ? h->dX : nullptr, W * 3, h->st);
+    if (rc) return rc;
+    if (xyz) RTDM_CUDA(cudaMemcpy2D(xyz, xstep, h->dX, W * 12, W * 12, height, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int rtdm_depth_last_launches(const rtdm_depth *h) { return h ? h->launches : 0; }
+
 extern "C" int rtdm_measure_int_peak(int device, double *tiops_iadd3, double *tiops_vimnmx,
                                      double *tiops_vabsdiff4, double *sm_mhz_est)
 {

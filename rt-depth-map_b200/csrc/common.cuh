@@ -95,6 +95,11 @@ size_t sgbm_work_bytes(const SgbmGeom &g, size_t *planes, size_t *vol);
 int launch_sgbm(const SgbmGeom &g, int n, PlaneU8 left, PlaneU8 right, PlaneS16 out, SgbmWork w,
                 cudaStream_t st, int *launches);
 
+// ---- depth epilogue (depth.cu): /16, reprojectImageTo3D, masked mean Z per rectangle ---------------
+int launch_depth(const int16_t *disp, size_t dpitch, int W, int H, const double *Q, const uint8_t *mask, size_t mpitch,
+                 int nregions, const int *rects_dev, int *minval, double *sums, int *counts, float *xyz, size_t xpitch,
+                 cudaStream_t st, int *launches);
+
 // ---- int peak microbenchmark (intpeak.cu) -------------------------------------------------------
 int measure_int_peak(int device, double *iadd3, double *vimnmx, double *vabsdiff4, double *mhz);
 

@@ -19,6 +19,7 @@
 #include <cstdio>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 #include "../../include/rtdm_b200.h"
 #include "cv_compat.h"
@@ -163,4 +164,36 @@ public:
     }
 private:
     rtdm_morph *h_ = nullptr;
+};
+
+// The step after the matcher, fused on the GPU.  Replaces in Estimator::run
+//     left_disp /= 16.;                                              estimator.cpp:75
+//     reprojectImageTo3D(left_disp, xyz, Q, true, CV_32F);           estimator.cpp:76
+//     calc_depth(xyz, left_disp, filter_out, img_rectified, obj_boundings, calibration_unit);   :77
+// by   depth.run(left_disp, Q, filter_out, obj_boundings, mean_z);   // left_disp still x16, as the matcher wrote it
+// and the label of region i is  mean_z[i] * calibration_unit / 10  cm  (estimator.cpp:252-254), drawn when count[i] > 0.
+class CUDADepthEpilogue {
+public:
+    CUDADepthEpilogue(int max_width, int max_height, int max_regions = 64, int device = 0)
+    {
+        int rc = rtdm_depth_create(&h_, max_width, max_height, max_regions, device);
+        if (rc) rtdm_detail::fail("CUDADepthEpilogue", rc);
+    }
+    ~CUDADepthEpilogue() { rtdm_depth_destroy(h_); }
+    // disp: CV_16SC1 x16 disparity; Q: 4x4 doubles, row-major (cv::Mat_<double>(4,4).ptr<double>()); mask: CV_8UC1 or empty
+    int run(const cv::Mat &disp, const double *Q, const cv::Mat &mask, const std::vector<cv::Rect> &regions,
+            std::vector<double> &mean_z, std::vector<int> *count = nullptr)
+    {
+        const int n = (int)regions.size();
+        std::vector<int> rects((size_t)4 * n), cnt((size_t)n);
+        for (int i = 0; i < n; i++) { rects[4 * i] = regions[i].x; rects[4 * i + 1] = regions[i].y; rects[4 * i + 2] = regions[i].width; rects[4 * i + 3] = regions[i].height; }
+        mean_z.assign((size_t)n, 0.0);
+        int rc = rtdm_depth_run(h_, disp.ptr<short>(), disp.step, disp.cols, disp.rows, Q, mask.empty() ? nullptr : mask.ptr<unsigned char>(),
+                                mask.empty() ? 0 : mask.step, n, rects.data(), mean_z.data(), cnt.data(), nullptr, 0);
+        if (rc) { std::fprintf(stderr, "CUDADepthEpilogue::run: %s\n", rtdm_last_error()); return -1; }
+        if (count) *count = cnt;
+        return 0;
+    }
+private:
+    rtdm_depth *h_ = nullptr;
 };

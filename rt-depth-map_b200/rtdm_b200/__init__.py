@@ -87,6 +87,11 @@ SIGNATURES = {
     "rtdm_median3_s16": (_i, [_vp, _sz, _vp, _sz, _i, _i, _i]),
     "rtdm_morph_op": (_i, [_vp, _sz, _vp, _sz, _i, _i, _i, _i, _i, _i]),
     "rtdm_validate_disparity": (_i, [_vp, _sz, _vp, _sz, _i, _i, _i, _i, _i, _i]),
+    "rtdm_depth_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i]),
+    "rtdm_depth_destroy": (None, [_vp]),
+    "rtdm_depth_run": (_i, [_vp, _vp, _sz, _i, _i, _vp, _vp, _sz, _i, _vp, _vp, _vp, _vp, _sz]),
+    "rtdm_depth_run_device": (_i, [_vp, _vp, _sz, _i, _i, _vp, _vp, _sz, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "rtdm_depth_last_launches": (_i, [_vp]),
     "rtdm_measure_int_peak": (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                    C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
@@ -387,6 +392,59 @@ class CUDAMorphologicalFilter(VideoFilterDevice):
 
 
 # ---- stand-alone stages ---------------------------------------------------------------------------
+class CUDADepthEpilogue:
+    """What Estimator::run does with the matcher's output (estimator.cpp:75-77), fused on the GPU:
+    `left_disp /= 16.`, `reprojectImageTo3D(left_disp, xyz, Q, true, CV_32F)` and `calc_depth` (masked mean Z per
+    bounding rectangle, estimator.cpp:206-263).  `run` takes host arrays, `run_device` device pointers."""
+
+    def __init__(self, max_width=1280, max_height=720, max_regions=64, device=0):
+        self._l = lib()
+        self._h = _vp()
+        self._vp = _vp
+        _check(self._l.rtdm_depth_create(C.byref(self._h), max_width, max_height, max_regions, device))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) and self._vp is not None:
+                self._l.rtdm_depth_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def run(self, disp, Q, mask, rects, want_xyz=False):
+        """disp: (H, W) int16 x16 disparity as the matcher returns it; Q: 4x4; mask: (H, W) uint8 or None;
+        rects: (n, 4) x, y, w, h.  Returns (mean_z [n] float64, count [n] int32[, xyz (H, W, 3) float32])."""
+        disp = np.ascontiguousarray(disp, np.int16)
+        H, W = disp.shape
+        Qa = np.ascontiguousarray(Q, np.float64).reshape(16)
+        r = np.ascontiguousarray(rects, np.int32).reshape(-1, 4)
+        n = r.shape[0]
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        mean, cnt = np.zeros(max(n, 1), np.float64), np.zeros(max(n, 1), np.int32)
+        xyz = np.empty((H, W, 3), np.float32) if want_xyz else None
+        _check(self._l.rtdm_depth_run(self._h, disp.ctypes.data, W * 2, W, H, Qa.ctypes.data,
+                                      None if m is None else m.ctypes.data, W, n, r.ctypes.data,
+                                      mean.ctypes.data, cnt.ctypes.data, None if xyz is None else xyz.ctypes.data, W * 12))
+        return (mean[:n], cnt[:n], xyz) if want_xyz else (mean[:n], cnt[:n])
+
+    def run_device(self, disp_ptr, dstep, W, H, Q, mask_ptr, mstep, rects, stream=0, xyz_ptr=None, xstep=0):
+        Qa = np.ascontiguousarray(Q, np.float64).reshape(16)
+        r = np.ascontiguousarray(rects, np.int32).reshape(-1, 4)
+        n = r.shape[0]
+        mean, cnt = np.zeros(max(n, 1), np.float64), np.zeros(max(n, 1), np.int32)
+        _check(self._l.rtdm_depth_run_device(self._h, disp_ptr, dstep, W, H, Qa.ctypes.data, mask_ptr, mstep, n, r.ctypes.data,
+                                             mean.ctypes.data, cnt.ctypes.data, xyz_ptr, xstep, stream))
+        return mean[:n], cnt[:n]
+
+    def last_launches(self) -> int:
+        return self._l.rtdm_depth_last_launches(self._h)
+
+
+def distance_cm(mean_z, calibration_unit):
+    """The label Estimator::calc_depth prints (estimator.cpp:252-254)."""
+    return f"{mean_z * calibration_unit / 10.0:.0f} cm"
+
+
 def filter_speckles(img, newVal, maxSpeckleSize, maxDiff, device=0):
     a = np.ascontiguousarray(img, np.int16).copy()
     H, W = a.shape

@@ -3,6 +3,7 @@
 //   host_adapter_main bm   W H nd bs left right out [rx ry rw rh]
 //   host_adapter_main sgbm W H nd bs left right out mode
 //   host_adapter_main morph W H in out
+//   host_adapter_main depth W H disp mask out x y w h   (Q is the fixed matrix of tests/test_host_adapters.py)
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -81,6 +82,23 @@ int main(int argc, char **argv)
             if (f->run(fin, fout) != 0) return 4;
             dump(argv[5], fout.data, (size_t)W * H);
             delete f;
+            return 0;
+        }
+        if (!std::strcmp(argv[1], "depth") && argc >= 11) {
+            int W = atoi(argv[2]), H = atoi(argv[3]);
+            std::vector<unsigned char> d = slurp(argv[4], (size_t)W * H * 2), m = slurp(argv[5], (size_t)W * H);
+            cv::Mat disp(H, W, CV_16SC1, d.data()), mask(H, W, CV_8UC1, m.data());
+            const double Q[16] = {1, 0, 0, -W / 2.0 + 0.37, 0, 1, 0, -H / 2.0 - 0.21, 0, 0, 0, 0.8 * W, 0, 0, 1 / 119.87, 0.004};
+            std::vector<cv::Rect> regions;
+            regions.push_back(cv::Rect(atoi(argv[7]), atoi(argv[8]), atoi(argv[9]), atoi(argv[10])));
+            regions.push_back(cv::Rect(0, 0, W, H));
+            CUDADepthEpilogue ep(W, H, 8);
+            std::vector<double> mean; std::vector<int> cnt;
+            if (ep.run(disp, Q, mask, regions, mean, &cnt) != 0) return 4;
+            FILE *f = std::fopen(argv[6], "w");
+            if (!f) return 2;
+            for (size_t i = 0; i < mean.size(); i++) std::fprintf(f, "%.17g %d\n", mean[i], cnt[i]);
+            std::fclose(f);
             return 0;
         }
     } catch (const std::exception &e) {

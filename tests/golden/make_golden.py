@@ -75,6 +75,21 @@ def main():
     for d12 in (0, 1, 3):
         t = raw.copy(); cv2.validateDisparity(t, cost, 0, 64, d12); v[f"d12_{d12}"] = t
     np.savez_compressed(os.path.join(OUT, "post_validate_320x240"), raw=raw, cost=cost, **v)
+    # depth epilogue: /16, reprojectImageTo3D(handleMissingValues, CV_32F), calc_depth
+    from oracle import oracle as orc
+    L, R, _ = synth.stereo_pair(320, 240, 64, 4100)
+    disp = cv2_ref.make_bm(31, 15, 0, 10, 64, 10, 100, 32, 1).compute(L, R)
+    d16 = disp.copy().astype(np.int16)
+    d16m = (cv2.divide(d16, 16.0)).astype(np.int16)                 # what `left_disp /= 16.` leaves in the CV_16S Mat
+    # Q as cv::stereoRectify builds it (backup/1280x720/extrinsics.yml layout): [1 0 0 -cx; 0 1 0 -cy; 0 0 0 f; 0 0 -1/Tx (cx-cx')/Tx]
+    Q = np.array([[1, 0, 0, -161.37], [0, 1, 0, -118.21], [0, 0, 0, 351.933], [0, 0, 1 / 59.87, -(161.37 - 160.9) / 59.87]], np.float64)
+    xyz = cv2.reprojectImageTo3D(d16m, Q, handleMissingValues=True, ddepth=cv2.CV_32F)
+    mask = synth.binary_mask(320, 240, 4101)
+    rects = np.array([[20, 30, 100, 80], [150, 10, 160, 200], [0, 0, 320, 240], [300, 200, 20, 40], [90, 90, 1, 1]], np.int32)
+    means, counts = orc.calc_depth(xyz, mask, rects)                # the reference's loop, restated (no cv2 routine to call)
+    np.savez_compressed(os.path.join(OUT, "depth_320x240"), disp=disp, div16=d16m, Q=Q, xyz=xyz, mask=mask, rects=rects,
+                        mean_z=means, count=counts)
+    print("depth_320x240", means, counts)
     print("done")
 
 

@@ -49,3 +49,13 @@ def test_adapters_match_oracle(exe, gpu, orc, tmp_path):
     mp = str(tmp_path / "m.raw"); m.tofile(mp)
     subprocess.check_call([exe, "morph", str(W), str(H), mp, op])
     assert np.array_equal(np.fromfile(op, np.uint8).reshape(H, W), orc.morph_open_close(m))
+    # depth epilogue peer (estimator.cpp:75-77) on the matcher's and the filter's outputs
+    dp, tp = str(tmp_path / "d.raw"), str(tmp_path / "depth.txt")
+    ref.tofile(dp); orc.morph_open_close(m).tofile(mp)
+    rect = (50, 40, 200, 150)
+    subprocess.check_call([exe, "depth", str(W), str(H), dp, mp, tp] + [str(v) for v in rect])
+    Q = np.array([[1, 0, 0, -W / 2.0 + 0.37], [0, 1, 0, -H / 2.0 - 0.21], [0, 0, 0, 0.8 * W], [0, 0, 1 / 119.87, 0.004]])
+    rm, rc = orc.calc_depth(orc.reproject_to_3d(orc.disp_div16(ref), Q), orc.morph_open_close(m), [rect, (0, 0, W, H)])
+    rows = [l.split() for l in open(tp).read().splitlines()]
+    assert [int(r[1]) for r in rows] == list(rc)
+    assert np.allclose([float(r[0]) for r in rows], rm, rtol=1e-12, atol=0)

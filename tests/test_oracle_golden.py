@@ -141,3 +141,19 @@ def test_sgbm_oracle_vs_cv2_random_params(orc):
         assert np.array_equal(ref, got), (p, int((ref != got).sum()))
         checked += 1
     assert checked >= 4
+
+
+def test_depth_oracle_matches_cv2_golden():
+    """Depth epilogue restatement (oracle.py: disp_div16, reproject_to_3d, calc_depth) against the fixture made
+    with cv2.divide / cv2.reprojectImageTo3D (tests/golden/make_golden.py)."""
+    from oracle import oracle as orc
+    g = load_golden("depth_320x240")
+    d16 = orc.disp_div16(g["disp"])
+    assert np.array_equal(d16, g["div16"])
+    xyz = orc.reproject_to_3d(d16, g["Q"])
+    assert np.array_equal(xyz.view(np.uint32), g["xyz"].view(np.uint32))
+    mean, cnt = orc.calc_depth(xyz, g["mask"], g["rects"])
+    assert np.array_equal(cnt, g["count"]) and np.array_equal(mean, g["mean_z"])
+    # round half to even on the x16 fixed point, negatives included
+    assert list(orc.disp_div16(np.array([[-24, -16, -8, 8, 24, 40, 7, 9]], np.int16))[0]) == [-2, -1, 0, 0, 2, 2, 0, 1]
+    assert orc.distance_cm(1607.4357, 1.0) == "161 cm"
