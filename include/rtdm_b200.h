@@ -109,6 +109,12 @@ int rtdm_bm_wait_oldest(rtdm_bm *h);
 int rtdm_bm_compute_device(rtdm_bm *h, int n, const uint8_t *left, size_t lstep, size_t lframe,
                            const uint8_t *right, size_t rstep, size_t rframe, int width, int height,
                            int16_t *disp, size_t dstep, size_t dframe, void *cuda_stream);
+/* The last stage of compute alone: cv::filterSpeckles with the handle's speckleWindowSize / speckleRange on n DEVICE
+ * frames, in place, asynchronous on `cuda_stream`.  The multi-GPU row-band split (rtdm_b200/rowband.py) runs the
+ * bands with the speckle filter off and applies it here to the stitched frame, because components cross bands
+ * (SURVEY.md 8(e)).  width * height may not exceed the handle's max_width * max_height. */
+int rtdm_bm_speckle_device(rtdm_bm *h, int n, int16_t *disp, size_t dstep, size_t dframe, int width, int height,
+                           void *cuda_stream);
 /* number of kernel launches issued by the last compute call on this handle */
 int rtdm_bm_last_launches(const rtdm_bm *h);
 /* which SAD/WTA kernel the last compute call used: 1 = generic (bm_sad.cu), 2 = fast path (bm_sad2.cu:

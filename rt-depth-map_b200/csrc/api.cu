@@ -437,6 +437,22 @@ extern "C" int rtdm_bm_compute(rtdm_bm *h, const uint8_t *left, size_t lstep, co
     return rtdm_bm_compute_batch(h, 1, left, lstep, 0, right, rstep, 0, width, height, disp, dstep, 0);
 }
 
+extern "C" int rtdm_bm_speckle_device(rtdm_bm *h, int n, int16_t *disp, size_t dstep, size_t dframe, int width, int height,
+                                      void *cuda_stream)
+{
+    if (!h || !disp) { set_error("bm_speckle: null argument"); return -RTDM_EINVAL; }
+    if (n < 1 || n > h->maxB || width < 1 || height < 1 || (size_t)width * height > (size_t)h->maxW * h->maxH || dstep % 2 || dframe % 2) {
+        set_error("bm_speckle: geometry or batch exceeds what the handle was created for");
+        return -RTDM_EINVAL;
+    }
+    RTDM_CUDA(cudaSetDevice(h->dev));
+    h->launches = 0;
+    if (!(h->p.speckleRange >= 0 && h->p.speckleWindowSize > 0)) return 0;
+    const int FILT = (h->p.minDisparity - 1) * 16;
+    return launch_speckle(n, width, height, PlaneS16{disp, dstep / 2, dframe / 2}, FILT, h->p.speckleWindowSize, h->p.speckleRange,
+                          h->labels, h->sizes, static_cast<cudaStream_t>(cuda_stream), &h->launches, h->runlen);
+}
+
 extern "C" int rtdm_bm_last_launches(const rtdm_bm *h) { return h ? h->launches : 0; }
 extern "C" int rtdm_bm_last_kernel(const rtdm_bm *h) { return h ? h->last_kernel : 0; }
 

@@ -59,6 +59,7 @@ SIGNATURES = {
     "rtdm_bm_submit_batch": (_i, [_vp, _i, _vp, _sz, _sz, _vp, _sz, _sz, _i, _i, _vp, _sz, _sz]),
     "rtdm_bm_wait": (_i, [_vp]),
     "rtdm_bm_wait_oldest": (_i, [_vp]),
+    "rtdm_bm_speckle_device": (_i, [_vp, _i, _vp, _sz, _sz, _i, _i, _vp]),
     "rtdm_bm_compute_device": (_i, [_vp, _i, _vp, _sz, _sz, _vp, _sz, _sz, _i, _i, _vp, _sz, _sz, _vp]),
     "rtdm_bm_last_launches": (_i, [_vp]),
     "rtdm_bm_debug_fetch": (_i, [_vp, _i, _vp, _sz]),
@@ -240,6 +241,10 @@ class CUDAMatcherKonolige(_MatcherBase):
         calls = _i()
         _check(self._l.rtdm_bm_stage_times(self._h, ms, C.byref(calls)))
         return dict(zip(self.STAGES, list(ms))), calls.value
+
+    def speckle_device(self, n, disp_ptr, dstep, dframe, W, H, stream=0):
+        """filterSpeckles with this matcher's parameters on n device frames in place (rtdm_bm_speckle_device)."""
+        _check(self._l.rtdm_bm_speckle_device(self._h, n, disp_ptr, dstep, dframe, W, H, stream))
 
     def submit_batch(self, left, right, out):
         """Streaming variant of compute_batch: (N, H, W) uint8 pinned arrays in, (N, H, W) int16 pinned array out;
