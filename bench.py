@@ -284,18 +284,25 @@ def run_ours(args):
     Dpn2 = torch.empty((B, H, W), dtype=torch.int16).pin_memory().numpy() if streaming else None
     acc = [0]
 
+    filter_first = bool(os.environ.get("RTDM_BENCH_FILTER_FIRST"))
+
     def e2e_step(i=0):
-        # the filter's copies and kernels run on its own stream underneath the matcher call
-        if filt is not None:
+        # the filter's copies and kernels run on its own stream underneath the matcher call; the matcher's copies
+        # are enqueued first because its kernels (the long pole) cannot start before their first chunk has arrived
+        if filt is not None and filter_first:
             filt.run_batch_async(Mpn, MOpn)
         if streaming:
             # depth-2 stream of batches: the copies of batch i+1 / i-1 run under the kernels of batch i; every
             # batch's result is read on the host one submission later
             matcher.submit_batch(Lpn, Rpn, Dpn2 if i & 1 else Dpn)
+            if filt is not None and not filter_first:
+                filt.run_batch_async(Mpn, MOpn)
             if i > 0:
                 matcher.wait_oldest()
                 acc[0] += int((Dpn if i & 1 else Dpn2)[0, H // 2, W // 2])
         else:
+            if filt is not None and not filter_first:
+                filt.run_batch_async(Mpn, MOpn)
             matcher.compute_batch(Lpn, Rpn, Dpn)
             acc[0] += int(Dpn[0, H // 2, W // 2])
         if filt is not None:
