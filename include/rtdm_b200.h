@@ -220,6 +220,25 @@ int rtdm_depth_run_device(rtdm_depth *h, const int16_t *disp, size_t dstep, int 
                           double *mean_z, int *count, float *xyz, size_t xstep, void *cuda_stream);
 int rtdm_depth_last_launches(const rtdm_depth *h);
 
+/* ---- rectification front-end (the step before the matcher) ---------------- */
+/* Replaces, fused, estimator.cpp:29-36 for one camera:
+ *     cvtColor(img, gray, CV_RGB2GRAY); remap(gray, rect, map1, map2, INTER_LINEAR); rect = rect(roif);
+ * map1 (CV_16SC2) and map2 (CV_16UC1) are the fixed-point maps of initUndistortRectifyMap(..., CV_16SC2, ...)
+ * (main.cpp:95-96), HOST pointers, full image size (src_height x src_width), steps in bytes; they are copied
+ * to the device once.  roi = Estimator's roif; the output is the CV_8UC1 crop the matcher receives. */
+typedef struct rtdm_rectify rtdm_rectify;
+int rtdm_rectify_create(rtdm_rectify **out, int src_width, int src_height, const int16_t *map1, size_t map1_step,
+                        const uint16_t *map2, size_t map2_step, int roi_x, int roi_y, int roi_width, int roi_height,
+                        int max_batch, int device);
+void rtdm_rectify_destroy(rtdm_rectify *h);
+/* n HOST frames CV_8UC3 in R,G,B order (what the decoder delivers, estimator.cpp:24-27) -> n crops */
+int rtdm_rectify_run(rtdm_rectify *h, int n, const uint8_t *rgb, size_t step, size_t frame,
+                     uint8_t *out, size_t ostep, size_t oframe);
+/* DEVICE pointers, asynchronous on cuda_stream: frames can stay on the GPU from here to the depth epilogue */
+int rtdm_rectify_run_device(rtdm_rectify *h, int n, const uint8_t *rgb, size_t step, size_t frame,
+                            uint8_t *out, size_t ostep, size_t oframe, void *cuda_stream);
+int rtdm_rectify_last_launches(const rtdm_rectify *h);
+
 /* ---- measurement helper ------------------------------------------------------------------- */
 /* Measures the integer-ALU issue peak of the device with dependent-free packed-integer loops
  * (the roofline denominator SURVEY.md 8(d) asks for).  Results in 1e12 lane-ops/s. */

@@ -238,3 +238,37 @@ def calc_depth(xyz, mask, rects):
 def distance_cm(mean_z, calibration_unit):
     """The label the reference prints (estimator.cpp:252-254): res * calibrationUnit / 10, fixed, 0 decimals."""
     return f"{mean_z * calibration_unit / 10.0:.0f} cm"
+
+
+# ---------------------------------------------------------------------------------------------------
+# Rectification front-end (SURVEY.md 8(f).2): numpy restatement of estimator.cpp:29-36
+# ---------------------------------------------------------------------------------------------------
+def rgb2gray(rgb):
+    """cvtColor(img, gray, CV_RGB2GRAY) on CV_8UC3 (estimator.cpp:29-30): OpenCV 4.x 15-bit fixed point,
+    (R*9798 + G*19235 + B*3735 + 2^14) >> 15."""
+    a = np.asarray(rgb, np.uint8).astype(np.int32)
+    return ((a[..., 0] * 9798 + a[..., 1] * 19235 + a[..., 2] * 3735 + (1 << 14)) >> 15).astype(np.uint8)
+
+
+def remap_linear_fixed(src, map1, map2):
+    """remap(src, dst, map1, map2, INTER_LINEAR) for CV_8UC1 with the fixed-point maps initUndistortRectifyMap(...,
+    CV_16SC2, ...) makes (estimator.cpp:32,35; main.cpp:95-96): map1 = integer source (x, y), map2 = fy << 5 | fx
+    (5-bit fractions).  Weights (32-fy)(32-fx)*32 ... sum to 2^15 exactly, result (sum + 2^14) >> 15;
+    BORDER_CONSTANT 0 outside the source."""
+    src = np.asarray(src, np.uint8); sh, sw = src.shape
+    m1 = np.asarray(map1, np.int16).astype(np.int64); m2 = np.asarray(map2, np.uint16).astype(np.int64)
+    sx, sy = m1[..., 0], m1[..., 1]
+    fx, fy = m2 & 31, (m2 >> 5) & 31
+
+    def at(y, x):
+        ok = (x >= 0) & (x < sw) & (y >= 0) & (y < sh)
+        return np.where(ok, src[np.clip(y, 0, sh - 1), np.clip(x, 0, sw - 1)].astype(np.int64), 0)
+    v = ((32 - fy) * (32 - fx) * 32) * at(sy, sx) + ((32 - fy) * fx * 32) * at(sy, sx + 1) \
+        + (fy * (32 - fx) * 32) * at(sy + 1, sx) + (fy * fx * 32) * at(sy + 1, sx + 1)
+    return ((v + (1 << 14)) >> 15).astype(np.uint8)
+
+
+def rectify(rgb, map1, map2, roi):
+    """gray -> remap -> crop to roi = (x, y, w, h): what the matcher receives as left_rect / right_rect."""
+    x, y, w, h = roi
+    return np.ascontiguousarray(remap_linear_fixed(rgb2gray(rgb), map1, map2)[y:y + h, x:x + w])

@@ -1026,6 +1026,98 @@ extern "C" int rtdm_depth_run(rtdm_depth *h, const int16_t *disp, size_t dstep, 
 
 extern "C" int rtdm_depth_last_launches(const rtdm_depth *h) { return h ? h->launches : 0; }
 
+// =================================================================================================
+// rectification front-end
+// =================================================================================================
+struct rtdm_rectify {
+    int W, H, rx, ry, rw, rh, maxB, dev;
+    cudaStream_t st;
+    int16_t *map1; uint16_t *map2;          // ROI part of the maps, tightly packed
+    uint8_t *dIn, *dOut;                    // staging for the host entry point
+    int launches;
+};
+
+extern "C" void rtdm_rectify_destroy(rtdm_rectify *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->dev);
+    cudaFree(h->map1); cudaFree(h->map2); cudaFree(h->dIn); cudaFree(h->dOut);
+    if (h->st) cudaStreamDestroy(h->st);
+    delete h;
+}
+
+extern "C" int rtdm_rectify_create(rtdm_rectify **out, int src_width, int src_height, const int16_t *map1, size_t map1_step,
+                                   const uint16_t *map2, size_t map2_step, int roi_x, int roi_y, int roi_width, int roi_height,
+                                   int max_batch, int device)
+{
+    if (!out || !map1 || !map2) { set_error("rectify_create: null argument"); return -RTDM_EINVAL; }
+    *out = nullptr;
+    if (src_width < 1 || src_height < 1 || max_batch < 1 || roi_x < 0 || roi_y < 0 || roi_width < 1 || roi_height < 1 ||
+        roi_x + roi_width > src_width || roi_y + roi_height > src_height) {
+        set_error("rectify_create: bad geometry (the ROI must lie inside the image)");
+        return -RTDM_EINVAL;
+    }
+    int rc = check_device(device);
+    if (rc) return rc;
+    RTDM_CUDA(cudaSetDevice(device));
+    rtdm_rectify *h = new (std::nothrow) rtdm_rectify();
+    if (!h) return -RTDM_ENOMEM;
+    memset(h, 0, sizeof *h);
+    h->W = src_width; h->H = src_height; h->rx = roi_x; h->ry = roi_y; h->rw = roi_width; h->rh = roi_height;
+    h->maxB = max_batch; h->dev = device;
+    const size_t RN = (size_t)roi_width * roi_height;
+    rc = cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) == cudaSuccess ? 0 : -RTDM_EIO;
+    if (!rc) rc = dev_alloc(&h->map1, 2 * RN);
+    if (!rc) rc = dev_alloc(&h->map2, RN);
+    if (!rc) rc = dev_alloc(&h->dIn, (size_t)src_width * src_height * 3 * max_batch);
+    if (!rc) rc = dev_alloc(&h->dOut, RN * max_batch);
+    if (!rc) {
+        cudaError_t e = cudaMemcpy2D(h->map1, (size_t)roi_width * 4, (const uint8_t *)map1 + (size_t)roi_y * map1_step + (size_t)roi_x * 4,
+                                     map1_step, (size_t)roi_width * 4, roi_height, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess)
+            e = cudaMemcpy2D(h->map2, (size_t)roi_width * 2, (const uint8_t *)map2 + (size_t)roi_y * map2_step + (size_t)roi_x * 2,
+                             map2_step, (size_t)roi_width * 2, roi_height, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) rc = cuda_fail(e, "rectify maps upload", __FILE__, __LINE__);
+    }
+    if (rc) { rtdm_rectify_destroy(h); return rc; }
+    *out = h;
+    return 0;
+}
+
+extern "C" int rtdm_rectify_run_device(rtdm_rectify *h, int n, const uint8_t *rgb, size_t step, size_t frame,
+                                       uint8_t *out, size_t ostep, size_t oframe, void *cuda_stream)
+{
+    if (!h || !rgb || !out) { set_error("rectify: null argument"); return -RTDM_EINVAL; }
+    if (n < 1 || step < (size_t)h->W * 3 || ostep < (size_t)h->rw) { set_error("rectify: bad batch or steps"); return -RTDM_EINVAL; }
+    RTDM_CUDA(cudaSetDevice(h->dev));
+    h->launches = 0;
+    return launch_rectify(n, rgb, step, frame, h->W, h->H, h->map1, h->map2, h->rw, h->rh, out, ostep, oframe,
+                          static_cast<cudaStream_t>(cuda_stream), &h->launches);
+}
+
+extern "C" int rtdm_rectify_run(rtdm_rectify *h, int n, const uint8_t *rgb, size_t step, size_t frame,
+                                uint8_t *out, size_t ostep, size_t oframe)
+{
+    if (!h || !rgb || !out) { set_error("rectify: null argument"); return -RTDM_EINVAL; }
+    if (n < 1 || n > h->maxB || step < (size_t)h->W * 3 || ostep < (size_t)h->rw) {
+        set_error("rectify: batch exceeds what the handle was created for, or bad steps");
+        return -RTDM_EINVAL;
+    }
+    RTDM_CUDA(cudaSetDevice(h->dev));
+    const size_t row = (size_t)h->W * 3, fin = row * h->H, fout = (size_t)h->rw * h->rh;
+    for (int k = 0; k < n; k++)
+        RTDM_CUDA(cudaMemcpy2DAsync(h->dIn + k * fin, row, rgb + k * frame, step, row, h->H, cudaMemcpyHostToDevice, h->st));
+    h->launches = 0;
+    int rc = launch_rectify(n, h->dIn, row, fin, h->W, h->H, h->map1, h->map2, h->rw, h->rh, h->dOut, h->rw, fout, h->st, &h->launches);
+    if (rc) return rc;
+    for (int k = 0; k < n; k++)
+        RTDM_CUDA(cudaMemcpy2DAsync(out + k * oframe, ostep, h->dOut + k * fout, h->rw, h->rw, h->rh, cudaMemcpyDeviceToHost, h->st));
+    RTDM_CUDA(cudaStreamSynchronize(h->st));
+    return 0;
+}
+
+extern "C" int rtdm_rectify_last_launches(const rtdm_rectify *h) { return h ? h->launches : 0; }
+
 extern "C" int rtdm_measure_int_peak(int device, double *tiops_iadd3, double *tiops_vimnmx,
                                      double *tiops_vabsdiff4, double *sm_mhz_est)
 {

@@ -100,6 +100,10 @@ int launch_depth(const int16_t *disp, size_t dpitch, int W, int H, const double 
                  int nregions, const int *rects_dev, int *minval, double *sums, int *counts, float *xyz, size_t xpitch,
                  cudaStream_t st, int *launches);
 
+// ---- rectification front-end (rectify.cu): RGB -> gray -> remap(INTER_LINEAR, fixed-point maps) -> ROI crop ------
+int launch_rectify(int n, const uint8_t *rgb, size_t pitch, size_t frame, int W, int H, const int16_t *map1, const uint16_t *map2,
+                   int rw, int rh, uint8_t *out, size_t opitch, size_t oframe, cudaStream_t st, int *launches);
+
 // ---- int peak microbenchmark (intpeak.cu) -------------------------------------------------------
 int measure_int_peak(int device, double *iadd3, double *vimnmx, double *vabsdiff4, double *mhz);
 

@@ -166,6 +166,32 @@ private:
     rtdm_morph *h_ = nullptr;
 };
 
+// The step before the matcher, fused on the GPU.  Replaces in Estimator::run, per camera,
+//     cvtColor(img[i], gray, CV_RGB2GRAY); remap(gray, rect, map1, map2, INTER_LINEAR); rect = rect(roif);   estimator.cpp:29-36
+// by   rectifier.run(img[i], rect);      // rect: CV_8UC1, roif.height x roif.width
+// map1 / map2 are the CV_16SC2 / CV_16UC1 maps main.cpp:95-96 builds with initUndistortRectifyMap.
+class CUDARectifier {
+public:
+    CUDARectifier(const cv::Mat &map1, const cv::Mat &map2, const cv::Rect &roif, int device = 0) : roi_(roif)
+    {
+        int rc = rtdm_rectify_create(&h_, map2.cols, map2.rows, map1.ptr<short>(), map1.step, map2.ptr<unsigned short>(), map2.step,
+                                     roif.x, roif.y, roif.width, roif.height, 1, device);
+        if (rc) rtdm_detail::fail("CUDARectifier", rc);
+    }
+    ~CUDARectifier() { rtdm_rectify_destroy(h_); }
+    // rgb: CV_8UC3 frame in R,G,B order (the decoder's output, estimator.cpp:24-27); rect is created like OutputArray::create
+    int run(const cv::Mat &rgb, cv::Mat &rect)
+    {
+        rect.create(roi_.height, roi_.width, CV_8UC1);
+        int rc = rtdm_rectify_run(h_, 1, rgb.ptr<unsigned char>(), rgb.step, 0, rect.ptr<unsigned char>(), rect.step, 0);
+        if (rc) { std::fprintf(stderr, "CUDARectifier::run: %s\n", rtdm_last_error()); return -1; }
+        return 0;
+    }
+private:
+    rtdm_rectify *h_ = nullptr;
+    cv::Rect roi_;
+};
+
 // The step after the matcher, fused on the GPU.  Replaces in Estimator::run
 //     left_disp /= 16.;                                              estimator.cpp:75
 //     reprojectImageTo3D(left_disp, xyz, Q, true, CV_32F);           estimator.cpp:76

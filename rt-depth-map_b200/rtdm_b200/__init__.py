@@ -88,6 +88,11 @@ SIGNATURES = {
     "rtdm_median3_s16": (_i, [_vp, _sz, _vp, _sz, _i, _i, _i]),
     "rtdm_morph_op": (_i, [_vp, _sz, _vp, _sz, _i, _i, _i, _i, _i, _i]),
     "rtdm_validate_disparity": (_i, [_vp, _sz, _vp, _sz, _i, _i, _i, _i, _i, _i]),
+    "rtdm_rectify_create": (_i, [C.POINTER(_vp), _i, _i, _vp, _sz, _vp, _sz, _i, _i, _i, _i, _i, _i]),
+    "rtdm_rectify_destroy": (None, [_vp]),
+    "rtdm_rectify_run": (_i, [_vp, _i, _vp, _sz, _sz, _vp, _sz, _sz]),
+    "rtdm_rectify_run_device": (_i, [_vp, _i, _vp, _sz, _sz, _vp, _sz, _sz, _vp]),
+    "rtdm_rectify_last_launches": (_i, [_vp]),
     "rtdm_depth_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i]),
     "rtdm_depth_destroy": (None, [_vp]),
     "rtdm_depth_run": (_i, [_vp, _vp, _sz, _i, _i, _vp, _vp, _sz, _i, _vp, _vp, _vp, _vp, _sz]),
@@ -397,6 +402,49 @@ class CUDAMorphologicalFilter(VideoFilterDevice):
 
 
 # ---- stand-alone stages ---------------------------------------------------------------------------
+class CUDARectifier:
+    """The step before the matcher (estimator.cpp:29-36), fused on the GPU for one camera:
+    cvtColor(RGB2GRAY) -> remap(INTER_LINEAR, the CV_16SC2 / CV_16UC1 maps of initUndistortRectifyMap) -> crop to
+    `roi` = (x, y, w, h).  `run` takes (H, W, 3) or (N, H, W, 3) uint8 RGB host arrays."""
+
+    def __init__(self, map1, map2, roi, *, max_batch=1, device=0):
+        self._l = lib()
+        self._h = _vp()
+        self._vp = _vp
+        m1 = np.ascontiguousarray(map1, np.int16); m2 = np.ascontiguousarray(map2, np.uint16)
+        H, W = m2.shape
+        if m1.shape != (H, W, 2):
+            raise RtdmError(-EINVAL, "CUDARectifier: map1 must be (H, W, 2) int16 and map2 (H, W) uint16")
+        self.W, self.H, self.roi, self.max_batch = W, H, tuple(int(v) for v in roi), max_batch
+        _check(self._l.rtdm_rectify_create(C.byref(self._h), W, H, m1.ctypes.data, W * 4, m2.ctypes.data, W * 2,
+                                           *self.roi, max_batch, device))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) and self._vp is not None:
+                self._l.rtdm_rectify_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def run(self, rgb):
+        a = np.ascontiguousarray(rgb, np.uint8)
+        single = a.ndim == 3
+        if single:
+            a = a[None]
+        N, H, W, _ = a.shape
+        rw, rh = self.roi[2], self.roi[3]
+        out = np.empty((N, rh, rw), np.uint8)
+        _check(self._l.rtdm_rectify_run(self._h, N, a.ctypes.data, W * 3, W * H * 3, out.ctypes.data, rw, rw * rh))
+        return out[0] if single else out
+
+    def run_device(self, n, rgb_ptr, step, frame, out_ptr, ostep, oframe, stream=0):
+        _check(self._l.rtdm_rectify_run_device(self._h, n, rgb_ptr, step, frame, out_ptr, ostep, oframe, stream))
+
+    def last_launches(self) -> int:
+        return self._l.rtdm_rectify_last_launches(self._h)
+
+
 class CUDADepthEpilogue:
     """What Estimator::run does with the matcher's output (estimator.cpp:75-77), fused on the GPU:
     `left_disp /= 16.`, `reprojectImageTo3D(left_disp, xyz, Q, true, CV_32F)` and `calc_depth` (masked mean Z per

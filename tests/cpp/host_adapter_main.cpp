@@ -3,6 +3,7 @@
 //   host_adapter_main bm   W H nd bs left right out [rx ry rw rh]
 //   host_adapter_main sgbm W H nd bs left right out mode
 //   host_adapter_main morph W H in out
+//   host_adapter_main rectify W H rgb map1 map2 out
 //   host_adapter_main depth W H disp mask out x y w h   (Q is the fixed matrix of tests/test_host_adapters.py)
 #include <cstdio>
 #include <cstdlib>
@@ -82,6 +83,20 @@ int main(int argc, char **argv)
             if (f->run(fin, fout) != 0) return 4;
             dump(argv[5], fout.data, (size_t)W * H);
             delete f;
+            return 0;
+        }
+        if (!std::strcmp(argv[1], "rectify") && argc >= 8) {
+            // rectify W H rgb map1 map2 out   (ROI fixed: 2 px margin)
+            int W = atoi(argv[2]), H = atoi(argv[3]);
+            std::vector<unsigned char> rgb = slurp(argv[4], (size_t)W * H * 3), m1 = slurp(argv[5], (size_t)W * H * 4), m2 = slurp(argv[6], (size_t)W * H * 2);
+            cv::Mat img(H, W, CV_8UC1, rgb.data(), (size_t)W * 3);            // the shim has no 3-channel type: only data/step are used
+            cv::Mat map1(H, W, CV_16SC1, m1.data(), (size_t)W * 4), map2(H, W, CV_16SC1, m2.data(), (size_t)W * 2);
+            CUDARectifier r(map1, map2, cv::Rect(2, 2, W - 4, H - 4));
+            cv::Mat rect;
+            if (r.run(img, rect) != 0) return 4;
+            std::vector<unsigned char> out((size_t)(W - 4) * (H - 4));
+            for (int y = 0; y < H - 4; y++) std::memcpy(&out[(size_t)y * (W - 4)], rect.ptr<unsigned char>(y), (size_t)W - 4);
+            dump(argv[7], out.data(), out.size());
             return 0;
         }
         if (!std::strcmp(argv[1], "depth") && argc >= 11) {

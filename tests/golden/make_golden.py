@@ -90,6 +90,21 @@ def main():
     np.savez_compressed(os.path.join(OUT, "depth_320x240"), disp=disp, div16=d16m, Q=Q, xyz=xyz, mask=mask, rects=rects,
                         mean_z=means, count=counts)
     print("depth_320x240", means, counts)
+    # rectification front-end: cvtColor RGB2GRAY, remap INTER_LINEAR with CV_16SC2 maps, ROI crop
+    rng = np.random.default_rng(4200)
+    H, W = 240, 320
+    base = cv2.GaussianBlur(rng.integers(0, 256, (H, W, 3)).astype(np.uint8), (0, 0), 1.5)
+    rgb = np.clip(base.astype(np.int16) + rng.integers(-20, 21, (H, W, 3)), 0, 255).astype(np.uint8)
+    K = np.array([[300., 0, 160.3], [0, 301., 119.6], [0, 0, 1]]); D = np.array([-0.31, 0.12, 0.001, -0.0007, 0.0])
+    Rm = cv2.Rodrigues(np.array([0.02, -0.03, 0.01]))[0]; P = np.array([[250., 0, 150, 0], [0, 250, 125, 0], [0, 0, 1, 0]])
+    m1, m2 = cv2.initUndistortRectifyMap(K, D, Rm, P, (W, H), cv2.CV_16SC2)       # main.cpp:95-96
+    gray = cv2.cvtColor(rgb, cv2.COLOR_RGB2GRAY)                                   # estimator.cpp:29
+    rect = cv2.remap(gray, m1, m2, cv2.INTER_LINEAR)                               # estimator.cpp:32
+    roi = (21, 13, 270, 200)
+    crop = np.ascontiguousarray(rect[roi[1]:roi[1] + roi[3], roi[0]:roi[0] + roi[2]])   # estimator.cpp:33
+    np.savez_compressed(os.path.join(OUT, "rectify_320x240"), rgb=rgb, map1=m1, map2=m2, gray=gray, rect=rect,
+                        roi=np.array(roi, np.int32), crop=crop)
+    print("rectify_320x240")
     print("done")
 
 

@@ -59,3 +59,13 @@ def test_adapters_match_oracle(exe, gpu, orc, tmp_path):
     rows = [l.split() for l in open(tp).read().splitlines()]
     assert [int(r[1]) for r in rows] == list(rc)
     assert np.allclose([float(r[0]) for r in rows], rm, rtol=1e-12, atol=0)
+    # rectifier peer (estimator.cpp:29-36)
+    rng = np.random.default_rng(3)
+    rgb = rng.integers(0, 256, (H, W, 3)).astype(np.uint8)
+    m1 = np.stack([np.clip(np.arange(W)[None, :] + rng.integers(-2, 3, (H, W)), -1, W), np.clip(np.arange(H)[:, None] + rng.integers(-2, 3, (H, W)), -1, H)], -1).astype(np.int16)
+    m2 = rng.integers(0, 1024, (H, W)).astype(np.uint16)
+    paths = [str(tmp_path / n) for n in ("rgb.raw", "m1.raw", "m2.raw", "rect.raw")]
+    rgb.tofile(paths[0]); m1.tofile(paths[1]); m2.tofile(paths[2])
+    subprocess.check_call([exe, "rectify", str(W), str(H)] + paths)
+    got = np.fromfile(paths[3], np.uint8).reshape(H - 4, W - 4)
+    assert np.array_equal(got, orc.rectify(rgb, m1, m2, (2, 2, W - 4, H - 4)))

@@ -157,3 +157,13 @@ def test_depth_oracle_matches_cv2_golden():
     # round half to even on the x16 fixed point, negatives included
     assert list(orc.disp_div16(np.array([[-24, -16, -8, 8, 24, 40, 7, 9]], np.int16))[0]) == [-2, -1, 0, 0, 2, 2, 0, 1]
     assert orc.distance_cm(1607.4357, 1.0) == "161 cm"
+
+
+def test_rectify_oracle_matches_cv2_golden():
+    """Rectification restatement (oracle.py: rgb2gray, remap_linear_fixed, rectify) against the fixture made with
+    cv2.cvtColor / cv2.remap and maps from cv2.initUndistortRectifyMap(CV_16SC2)."""
+    from oracle import oracle as orc
+    g = load_golden("rectify_320x240")
+    assert np.array_equal(orc.rgb2gray(g["rgb"]), g["gray"])
+    assert np.array_equal(orc.remap_linear_fixed(g["gray"], g["map1"], g["map2"]), g["rect"])
+    assert np.array_equal(orc.rectify(g["rgb"], g["map1"], g["map2"], tuple(g["roi"])), g["crop"])
