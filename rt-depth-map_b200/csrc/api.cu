@@ -95,7 +95,7 @@ struct rtdm_bm {
     cudaEvent_t done[2]; int busy[2]; unsigned seq;          // completion of the call that last used each set
     int launches;
     int lastW, lastH;
-    int last_kernel;             // 1 = generic bm_sad.cu kernel, 2 = fast bm_sad2.cu kernel
+    int last_kernel;             // 1 = generic bm_sad.cu kernel, 2 = fast bm_sad2.cu kernel, 3 = warp-specialised bm_sad3.cu kernel
     // optional per-stage CUDA-event timing (rtdm_bm_set_profiling)
     int prof;
     std::vector<cudaEvent_t> *ev;     // 5 events per profiled call: before prefilter, after each stage
@@ -274,11 +274,13 @@ static int bm_pipeline(rtdm_bm *h, int n, PlaneU8 L, PlaneU8 R, int W, int H, Pl
         // RTDM_BM_KERNEL=1 forces the generic kernel (A/B runs and tests); default: fast path when it applies
         const char *force = getenv("RTDM_BM_KERNEL");
         const bool fast = !(force && force[0] == '1') && bm_sad2_supported(g, n);
+        // RTDM_BM_KERNEL=2 keeps the bm_sad2.cu kernel where the warp-specialised bm_sad3.cu kernel would apply
+        const bool fast3 = fast && !(force && force[0] == '2') && bm_sad3_supported(g, n);
         if (fast)
-            rc = launch_bm_sad2(g, n, iL, iR, raw, cost, h->tex + (size_t)f0 * h->rframe, h->rpitch, h->rframe, st, &h->launches);
+            rc = launch_bm_sad2(g, n, iL, iR, raw, cost, h->tex + (size_t)f0 * h->rframe, h->rpitch, h->rframe, st, &h->launches, fast3);
         else
             rc = launch_bm_sad_wta(g, n, iL, iR, raw, cost, st, &h->launches);
-        h->last_kernel = fast ? 2 : 1;
+        h->last_kernel = fast3 ? 3 : (fast ? 2 : 1);
         if (rc) return rc;
         mark();
     } else { mark(); mark(); }

@@ -526,7 +526,7 @@ bool bm_sad2_supported(const BmGeom &g, int n)
 
 // tex: scratch of n * H * tex_pitch uint16
 int launch_bm_sad2(const BmGeom &g, int n, PlaneU8 Lp, PlaneU8 Rp, PlaneS16 disp, PlaneS16 cost,
-                   uint16_t *tex, size_t tex_pitch, size_t tex_frame, cudaStream_t st, int *launches)
+                   uint16_t *tex, size_t tex_pitch, size_t tex_frame, cudaStream_t st, int *launches, bool use3)
 {
     Tiling2 t;
     if (!pick_tiling2(g, n, &t)) { set_error("bm_sad2: unsupported geometry"); return -RTDM_EINVAL; }
@@ -543,6 +543,12 @@ int launch_bm_sad2(const BmGeom &g, int n, PlaneU8 Lp, PlaneU8 Rp, PlaneS16 disp
             default: RTDM_TEX_CASE(7); break;
         }
 #undef RTDM_TEX_CASE
+    }
+    if (use3) {
+        const int rc3 = launch_bm_sad3_core(g, n, Lp, Rp, disp, cost, tex, tex_pitch, tex_frame, st);
+        if (rc3) return rc3;
+        if (launches) (*launches) += 2;
+        return 0;
     }
     Bm2Args a;
     a.Lp = Lp; a.Rp = Rp; a.disp = disp; a.cost = cost;

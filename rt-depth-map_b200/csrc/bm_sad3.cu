@@ -1,0 +1,581 @@
+// bm_sad3.cu -- warp-specialised Konolige block-matching core (minDisparity == 0, blockSize 5 / 9 / 13,
+// numDisparities 64 / 128).  Same arithmetic as bm_sad.cu / bm_sad2.cu (oracle:
+// orc_bm_core); replaces findStereoCorrespondenceBM as reached from SWMatcherKonolige::compute
+// (reference stereo-matcher/bm-sw.cpp:33-38).
+//
+// bm_sad2's profile (profiles/r01_prof_bm_r1d_summary.csv) shows a latency-bound kernel: 12 warps per SM (158
+// registers for 12 columns of window sums per thread), half of the issue slots empty, producer and consumer
+// phases that never overlap.  This kernel splits the roles instead of the time:
+//
+//   one CTA per SM = stripe of TW <= 180 computed columns x band of BH rows of one frame,
+//   NG producer warps (one per group of G = 2h virtual columns) + 8 consumer warps, <= 80 registers each.
+//
+//   producer thread = (half group of h ADJACENT columns, disparity octet): vertical window sums V of its h columns
+//       slide down in 4h registers (VABSDIFF4, per-byte in + 128 - out deltas).  The first half of a group
+//       ("A") emits in-half PREFIX sums left to right, the second half ("B") emits SUFFIX sums right to left,
+//       both with the same straight-line code: B threads read byte-reversed (mirrored) copies of the rows, so
+//       their columns and their eight disparities simply come out in reverse order.  The two halves swap their
+//       totals with four shuffles and store the group total T in their own order.
+//       A (2h+1)-column window always spans two groups, so with i = x mod G
+//           i <  h :  SAD(x) = T[g]   - PreA[x - 1]  + PreA'[i]          (all in A order)
+//           i >= h :  SAD(x) = SufB[x] + T[g + 1]     - SufB'[i + 1]      (all in B order)
+//       i.e. always  a + b - c  with three 16-byte loads per octet, and no halo.
+//   consumer thread = one pixel: octet minima (packed u16x2, two octets per word), argmin octet by
+//       (min << 16 | octet) keys, exact position, texture / uniqueness / sub-pixel as in bm_sad2.
+//   The consumers also run the loader: the next prefiltered row enters a 16-row shared-memory ring as four
+//   "virtual" rows (left / right, forward / mirrored; the clamps of App. A.2 are applied here).
+//   Producers work on row y + 1 while consumers work on row y: the sums are double buffered and handed over
+//   through named barriers (bar.arrive / bar.sync), the only synchronisation per row.
+// The cost volume never leaves the SM; HBM traffic is the two prefiltered images in and disparity + cost out.
+#include "common.cuh"
+#include <algorithm>
+#include <cstdlib>
+#include <type_traits>
+
+namespace rtdm {
+namespace {
+
+constexpr int NCW = 8;                  // consumer warps
+constexpr int MAXT = 768;               // threads per CTA (producers + consumers)
+constexpr int SCR = 48;                 // consumer scratch bytes per thread (8 words + pad: conflict-free 128-bit rows)
+
+__host__ __device__ constexpr int ring_rows3(int h) { return 2 * h + 4 <= 16 ? 16 : 32; }
+
+__device__ __forceinline__ int clampi3(int v, int lo, int hi) { return min(max(v, lo), hi); }
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+struct Bm3Args {
+    PlaneU8 Lp, Rp;
+    PlaneS16 disp, cost;
+    const uint16_t *tex; size_t tex_pitch, tex_frame;      // texture window sums, [frame][y][x1]
+    int W, H, nd, cap, texThr, uniq;
+    int W1, row0, row1;
+    int TW, BH, NG;              // stripe width, band height, column groups (= producer warps x groups per warp)
+    int dbg;                     // timing experiments only: 1 = skip consumer maths, 2 = skip producer maths
+};
+
+// masks of the uniqueness test: entry rel + 1 (rel = mind - 8 * octet in -1 .. 8) has 0xFFFF in the 16-bit lanes
+// of the positions rel - 1 .. rel + 1 that fall inside the octet
+__constant__ uint4 c_zmask[10];
+
+// shared-memory geometry shared by host and device
+struct Geo3 {
+    int NCT, PP, BUFSZ, XOFF, TAOFF, TBOFF, ZOFF;   // one buffer: X[NCT] | TA[NG] | TB[NG] | zero row
+    int LF, LM, RF, RM, RMX, SLOT;                   // ring slot: byte offsets of the four virtual rows
+    int SCROFF, RINGOFF, total;
+};
+__host__ __device__ inline Geo3 make_geo3(int h, int nd, int NG)
+{
+    Geo3 q;
+    const int G = 2 * h;
+    q.NCT = NG * G;
+    q.PP = nd * 2 + 16;
+    q.XOFF = 0;
+    q.TAOFF = q.NCT * q.PP;
+    q.TBOFF = q.TAOFF + NG * q.PP;
+    q.ZOFF = q.TBOFF + NG * q.PP;
+    q.BUFSZ = q.ZOFF + q.PP;
+    q.LF = 0;
+    q.LM = q.NCT;
+    q.RF = 2 * q.NCT;
+    const int RFP = q.NCT + nd + 8;
+    q.RM = q.RF + RFP;
+    q.RMX = q.NCT + nd + 2;                    // mirrored right row: RMv[n] = Rv[RMX - n];  RMX == 2 (mod 4)
+    const int RMP = q.NCT + nd + 16;
+    q.SLOT = q.RM + RMP;
+    q.SCROFF = 2 * q.BUFSZ;
+    q.RINGOFF = q.SCROFF + NCW * 32 * SCR;
+    q.total = q.RINGOFF + ring_rows3(h) * q.SLOT;
+    return q;
+}
+
+// one word of a ring slot: which four virtual-row bytes it holds
+//   word index i inside the slot -> (right?, first forward virtual index cs, byte-reversed?)
+__device__ __forceinline__ void ring_word_src(const Geo3 &q, int i, int &right, int &cs, int &rev)
+{
+    const int b = 4 * i;
+    if (b < q.LM) { right = 0; rev = 0; cs = b; }
+    else if (b < q.RF) { right = 0; rev = 1; cs = q.NCT - 4 - (b - q.LM); }
+    else if (b < q.RM) { right = 1; rev = 0; cs = b - q.RF; }
+    else { right = 1; rev = 1; cs = q.RMX - 3 - (b - q.RM); }
+}
+
+template <int H_, int NO_>
+__global__ void __launch_bounds__(MAXT, 1)
+bm_sad3_kernel(Bm3Args a)
+{
+    constexpr int G = 2 * H_, RING = ring_rows3(H_);
+    constexpr int NLW = (H_ + 3) / 4, NRW = (H_ + 7 + 3) / 4;
+    constexpr int ND = NO_ * 8;
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int tid = threadIdx.x, f = blockIdx.z;
+    const int x0 = blockIdx.x * a.TW;
+    const int TWc = min(a.TW, a.W1 - x0);
+    const int y0 = a.row0 + blockIdx.y * a.BH, y1 = min(y0 + a.BH, a.row1);
+    if (TWc <= 0 || y0 >= y1) return;
+    const Geo3 q = make_geo3(H_, ND, a.NG);
+    const int NPT = a.NG * 2 * NO_;                    // producer threads (a multiple of 32)
+    const int NT = NPT + NCW * 32;
+    uint8_t *Ring = smem + q.RINGOFF;
+    const uint8_t *Lg = a.Lp.p + (size_t)f * a.Lp.frame;
+    const uint8_t *Rg = a.Rp.p + (size_t)f * a.Rp.frame;
+    const int lofs = ND - 1;
+
+    // real image column of forward virtual index v (left: Lv[v], right: Rv[v]); App. A.2 clamps
+    auto src_col = [&](int right, int v) {
+        const int xa = x0 - H_ + v;
+        return right ? clampi3(xa, 0, a.W - 1) : clampi3(xa, -lofs, a.W - lofs - 1) + lofs;
+    };
+
+    // ---- prologue: ring rows y0-h-1 .. y0+h+1 by all threads (byte gathers), zero rows ------------------
+    {
+        const int nw = q.SLOT / 4, nrows = 2 * H_ + 3;
+        for (int i = tid; i < nw * nrows; i += NT) {
+            const int r = i / nw, w = i - r * nw;
+            const int gy = y0 - H_ - 1 + r;
+            const int gyc = clampi3(gy, 0, a.H - 1);
+            int right, cs, rev;
+            ring_word_src(q, w, right, cs, rev);
+            const uint8_t *src = (right ? Rg + (size_t)gyc * a.Rp.pitch : Lg + (size_t)gyc * a.Lp.pitch);
+            uint32_t v = 0;
+#pragma unroll
+            for (int b = 0; b < 4; b++) v |= (uint32_t)src[src_col(right, cs + b)] << (8 * b);
+            if (rev) v = __byte_perm(v, 0, 0x0123);
+            *reinterpret_cast<uint32_t *>(Ring + (size_t)(gy & (RING - 1)) * q.SLOT + 4 * w) = v;
+        }
+        for (int i = tid; i < q.PP / 4; i += NT) {
+            reinterpret_cast<uint32_t *>(smem + q.ZOFF)[i] = 0u;
+            reinterpret_cast<uint32_t *>(smem + q.BUFSZ + q.ZOFF)[i] = 0u;
+        }
+    }
+    __syncthreads();
+
+    if (tid < NPT) {
+        // =========================================================================================
+        // producer
+        // =========================================================================================
+        const int hg = tid / NO_, j = tid - hg * NO_;
+        const int isB = hg & 1, g = hg >> 1;
+        // byte offsets of the thread's L and R streams inside a ring slot (both 4-byte aligned)
+        const int lbo = isB ? q.LM + (q.NCT - (g + 1) * G) : q.LF + g * G;
+        const int rbo = isB ? q.RM + (q.RMX - (g + 1) * G - 6 - 8 * j) : q.RF + g * G + 8 * j;
+        // R clamp (App. A.2, minD = 0): rbase(xc) = clip(xc, 0, W - nd); in virtual columns c = xc - x0 + h
+        const int cmin = H_ - x0, cmax = (a.W - ND) - x0 + H_;
+        uint32_t clmask = 0;
+        int crc = 0;
+#pragma unroll
+        for (int k = 0; k < H_; k++) {
+            const int c = isB ? g * G + G - 1 - k : g * G + k;
+            if (c < cmin) { clmask |= 1u << k; crc = cmin; }
+            if (c > cmax) { clmask |= 1u << k; crc = cmax; }
+        }
+        const bool wborder = __any_sync(0xFFFFFFFFu, clmask != 0);
+        // clamped columns read the R window of the nearest unclamped column: its stream offset in this thread's copy
+        const int cbo = isB ? q.RM + (q.RMX - crc - 8 * j - 7) : q.RF + crc + 8 * j;
+
+        uint32_t V[H_][4];
+#pragma unroll
+        for (int k = 0; k < H_; k++) V[k][0] = V[k][1] = V[k][2] = V[k][3] = 0u;
+
+        auto load_words = [&](const uint8_t *slot, uint32_t (&lw)[NLW], uint32_t (&rw)[NRW]) {
+            const uint32_t *lp = reinterpret_cast<const uint32_t *>(slot + lbo);
+            const uint32_t *rp = reinterpret_cast<const uint32_t *>(slot + rbo);
+#pragma unroll
+            for (int i = 0; i < NLW; i++) lw[i] = lp[i];
+#pragma unroll
+            for (int i = 0; i < NRW; i++) rw[i] = rp[i];
+        };
+        auto clamped_window = [&](const uint8_t *slot, uint32_t &c0w, uint32_t &c1w) {
+            const uint32_t *pw = reinterpret_cast<const uint32_t *>(slot + (cbo & ~3));
+            const int sh = (cbo & 3) * 8;
+            c0w = __funnelshift_r(pw[0], pw[1], sh);
+            c1w = __funnelshift_r(pw[1], pw[2], sh);
+        };
+        // |L - R| of column k (8 disparities in stream order)
+        auto ad_col = [&](const uint32_t (&lw)[NLW], const uint32_t (&rw)[NRW], int k, bool border, uint32_t c0w, uint32_t c1w,
+                          uint32_t &lo, uint32_t &hi) {
+            const int w = k >> 2, sft = k & 3;
+            const uint32_t l4 = __byte_perm(lw[w], 0, sft == 0 ? 0x0000 : (sft == 1 ? 0x1111 : (sft == 2 ? 0x2222 : 0x3333)));
+            uint32_t r0, r1;
+            if (sft == 0) { r0 = rw[w]; r1 = rw[w + 1]; }
+            else { r0 = __funnelshift_r(rw[w], rw[w + 1], 8 * sft); r1 = __funnelshift_r(rw[w + 1], rw[w + 2], 8 * sft); }
+            if (border && ((clmask >> k) & 1u)) { r0 = c0w; r1 = c1w; }
+            lo = __vabsdiffu4(l4, r0);
+            hi = __vabsdiffu4(l4, r1);
+        };
+
+        // vertical sums over rows y0-h-1 .. y0+h-1 (the first loop iteration removes row y0-h-1 again)
+        for (int r = y0 - H_ - 1; r < y0 + H_; r++) {
+            const uint8_t *slot = Ring + (size_t)(r & (RING - 1)) * q.SLOT;
+            uint32_t lw[NLW], rw[NRW], c0w = 0, c1w = 0;
+            load_words(slot, lw, rw);
+            if (wborder) clamped_window(slot, c0w, c1w);
+#pragma unroll
+            for (int k = 0; k < H_; k++) {
+                uint32_t lo, hi;
+                ad_col(lw, rw, k, wborder, c0w, c1w, lo, hi);
+                V[k][0] += __byte_perm(lo, 0, 0x4140);
+                V[k][1] += __byte_perm(lo, 0, 0x4342);
+                V[k][2] += __byte_perm(hi, 0, 0x4140);
+                V[k][3] += __byte_perm(hi, 0, 0x4342);
+            }
+        }
+
+        const int xst = q.XOFF + (hg * H_) * q.PP + 16 * j;                   // store base of the thread's h slots
+        const int tst = (isB ? q.TBOFF : q.TAOFF) + g * q.PP + 16 * j;
+
+        auto row = [&](int y, auto border_tag) {
+            constexpr bool BORDER = decltype(border_tag)::value;
+            uint8_t *buf = smem + (y & 1) * q.BUFSZ;
+            const uint8_t *sin = Ring + (size_t)((y + H_) & (RING - 1)) * q.SLOT;
+            const uint8_t *sout = Ring + (size_t)((y - H_ - 1) & (RING - 1)) * q.SLOT;
+            uint32_t lwi[NLW], rwi[NRW], lwo[NLW], rwo[NRW];
+            uint32_t ci0 = 0, ci1 = 0, co0 = 0, co1 = 0;
+            load_words(sin, lwi, rwi);
+            load_words(sout, lwo, rwo);
+            if (BORDER) { clamped_window(sin, ci0, ci1); clamped_window(sout, co0, co1); }
+            uint4 p = make_uint4(0, 0, 0, 0);
+            uint8_t *pdst = buf + xst;
+#pragma unroll
+            for (int k = 0; k < H_; k++) {
+                uint32_t lo, hi, olo, ohi;
+                ad_col(lwi, rwi, k, BORDER, ci0, ci1, lo, hi);
+                ad_col(lwo, rwo, k, BORDER, co0, co1, olo, ohi);
+                lo = lo + 0x80808080u - olo;                 // per byte: in + 128 - out (no borrow)
+                hi = hi + 0x80808080u - ohi;
+                V[k][0] += __byte_perm(lo, 0, 0x4140) - 0x00800080u;
+                V[k][1] += __byte_perm(lo, 0, 0x4342) - 0x00800080u;
+                V[k][2] += __byte_perm(hi, 0, 0x4140) - 0x00800080u;
+                V[k][3] += __byte_perm(hi, 0, 0x4342) - 0x00800080u;
+                p.x += V[k][0]; p.y += V[k][1]; p.z += V[k][2]; p.w += V[k][3];
+                *reinterpret_cast<uint4 *>(pdst + k * q.PP) = p;
+            }
+            // group total in this half's order: own half + the partner's, whose disparities run the other way
+            uint4 o;
+            o.x = __shfl_xor_sync(0xFFFFFFFFu, p.x, NO_);
+            o.y = __shfl_xor_sync(0xFFFFFFFFu, p.y, NO_);
+            o.z = __shfl_xor_sync(0xFFFFFFFFu, p.z, NO_);
+            o.w = __shfl_xor_sync(0xFFFFFFFFu, p.w, NO_);
+            p.x += __byte_perm(o.w, 0, 0x1032);
+            p.y += __byte_perm(o.z, 0, 0x1032);
+            p.z += __byte_perm(o.y, 0, 0x1032);
+            p.w += __byte_perm(o.x, 0, 0x1032);
+            *reinterpret_cast<uint4 *>(buf + tst) = p;
+        };
+
+        for (int y = y0; y < y1; y++) {
+            if (y - y0 >= 2) bar_sync(3 + (y & 1), NT);            // consumers are done with this buffer (row y - 2)
+            if (!(a.dbg & 2)) {
+                if (wborder) row(y, std::true_type());
+                else row(y, std::false_type());
+            }
+            bar_arrive(1 + (y & 1), NT);                           // sums of row y are complete
+        }
+    } else {
+        // =========================================================================================
+        // consumer (and loader)
+        // =========================================================================================
+        const int ct = tid - NPT, cw = ct >> 5, lane = ct & 31;
+        // ---- loader descriptors: up to two ring words per consumer thread ------------------------------
+        const int nw = q.SLOT / 4;
+        int d_dst[2], d_src[2], d_sh[2], d_right[2];
+        uint32_t d_sel[2];
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            const int i = ct + s * (NCW * 32);
+            d_dst[s] = -1; d_src[s] = -1; d_sh[s] = 0; d_right[s] = 0; d_sel[s] = 0x3210u;
+            if (i < nw) {
+                int right, cs, rev;
+                ring_word_src(q, i, right, cs, rev);
+                d_dst[s] = 4 * i; d_right[s] = right; d_sel[s] = rev ? 0x0123u : 0x3210u;
+                const int xa = x0 - H_ + cs;
+                const bool inr = right ? (xa >= 0 && xa + 3 <= a.W - 1) : (xa >= -lofs && xa + 3 <= a.W - lofs - 1);
+                if (inr) { const int gcol = right ? xa : xa + lofs; d_src[s] = gcol & ~3; d_sh[s] = (gcol & 3) * 8; }
+                else d_sh[s] = cs;
+            }
+        }
+        const bool two = __any_sync(0xFFFFFFFFu, d_dst[1] >= 0);
+        auto fetch_word = [&](int s, int gy, uint32_t &w0, uint32_t &w1) {
+            w0 = 0; w1 = 0;
+            if (d_dst[s] < 0) return;
+            const int gyc = clampi3(gy, 0, a.H - 1);
+            const uint8_t *src = d_right[s] ? Rg + (size_t)gyc * a.Rp.pitch : Lg + (size_t)gyc * a.Lp.pitch;
+            if (d_src[s] >= 0) {
+                const uint32_t *pw = reinterpret_cast<const uint32_t *>(src + d_src[s]);
+                w0 = pw[0]; w1 = pw[1];
+            } else {
+#pragma unroll
+                for (int b = 0; b < 4; b++) w0 |= (uint32_t)src[src_col(d_right[s], d_sh[s] + b)] << (8 * b);
+            }
+        };
+        auto commit_word = [&](int s, int gy, uint32_t w0, uint32_t w1) {
+            if (d_dst[s] < 0) return;
+            const uint32_t v = d_src[s] >= 0 ? __funnelshift_r(w0, w1, d_sh[s]) : w0;
+            *reinterpret_cast<uint32_t *>(Ring + (size_t)(gy & (RING - 1)) * q.SLOT + d_dst[s]) = __byte_perm(v, 0, d_sel[s]);
+        };
+
+        // ---- the pixel of this thread --------------------------------------------------------------------
+        int x = -1;
+        {
+            const int PW = (TWc + NCW - 1) / NCW;               // pixels per consumer warp (<= 32: TW <= 256)
+            if (lane < PW && cw * PW + lane < TWc) x = cw * PW + lane;
+        }
+        const int xx = max(x, 0);
+        const int gq = xx / G, gi = xx - gq * G;
+        const bool flip = gi >= H_;
+        int oa, ob, oc_;                                        // SAD = [oa] + [ob] - [oc_], byte offsets inside a buffer
+        if (!flip) {
+            oa = q.TAOFF + gq * q.PP;
+            ob = q.XOFF + ((gq + 1) * G + gi) * q.PP;
+            oc_ = gi > 0 ? q.XOFF + (xx - 1) * q.PP : q.ZOFF;
+        } else {
+            oa = q.XOFF + (gq * G + H_ + (G - 1 - gi)) * q.PP;
+            ob = q.TBOFF + (gq + 1) * q.PP;
+            oc_ = gi < G - 1 ? q.XOFF + ((gq + 1) * G + H_ + (G - 2 - gi)) * q.PP : q.ZOFF;
+        }
+        const uint32_t usel = flip ? 0x5476u : 0x3210u;         // un-reverse selector: (sv[r], sv[3 - r]) -> forward word r
+        const int xflip = flip ? 7 : 0;
+        uint8_t *scr = smem + q.SCROFF + ct * SCR;
+        int16_t *dptr = a.disp.p + (size_t)f * a.disp.frame + (size_t)y0 * a.disp.pitch + lofs + x0 + xx;
+        int16_t *cptr = a.cost.p ? a.cost.p + (size_t)f * a.cost.frame + (size_t)y0 * a.cost.pitch + lofs + x0 + xx : nullptr;
+        const uint16_t *tptr = a.tex + (size_t)f * a.tex_frame + (size_t)y0 * a.tex_pitch + x0 + xx;
+        const int16_t FILT = (int16_t)(-16);                    // (minD - 1) * 16 with minD = 0
+        int tsum = x >= 0 ? (int)*tptr : 0;
+
+        for (int y = y0; y < y1; y++) {
+            // loader: row y + h + 2 (rows up to y + h + 1 are in the ring); texture sum of the next row
+            const bool have_next = y + 1 < y1;
+            uint32_t f00 = 0, f01 = 0, f10 = 0, f11 = 0;
+            if (have_next) {
+                fetch_word(0, y + H_ + 2, f00, f01);
+                if (two) fetch_word(1, y + H_ + 2, f10, f11);
+            }
+            int tnext = 0;
+            if (have_next && x >= 0) tnext = (int)tptr[a.tex_pitch];
+            tptr += a.tex_pitch;
+
+            bar_sync(1 + (y & 1), NT);                          // the sums of row y are complete
+            const uint8_t *buf = smem + (y & 1) * q.BUFSZ;
+            int16_t dout = FILT;
+            int costv = 0;
+            bool okc = false;
+            if (x >= 0 && tsum >= a.texThr && !(a.dbg & 1)) {
+                const uint8_t *pa = buf + oa, *pb = buf + ob, *pc = buf + oc_;
+                auto sad4 = [&](int o, uint32_t (&sv)[4]) {
+                    const uint4 t = *reinterpret_cast<const uint4 *>(pa + 16 * o);
+                    const uint4 w = *reinterpret_cast<const uint4 *>(pb + 16 * o);
+                    const uint4 u = *reinterpret_cast<const uint4 *>(pc + 16 * o);
+                    sv[0] = t.x + w.x - u.x; sv[1] = t.y + w.y - u.y; sv[2] = t.z + w.z - u.z; sv[3] = t.w + w.w - u.w;
+                };
+                // exact octet in forward order (position p = disparity index 8 * o + p)
+                auto sad4f = [&](int o, uint32_t (&sv)[4]) {
+                    uint32_t r[4];
+                    sad4(o, r);
+                    sv[0] = __byte_perm(r[0], r[3], usel);
+                    sv[1] = __byte_perm(r[1], r[2], usel);
+                    sv[2] = __byte_perm(r[2], r[1], usel);
+                    sv[3] = __byte_perm(r[3], r[0], usel);
+                };
+                // pass 1: octet minima, two octets per word, and the argmin octet
+                uint32_t pm[NO_ / 2];
+                uint32_t best = 0xFFFFFFFFu;
+#pragma unroll
+                for (int k = 0; k < NO_ / 2; k++) {
+                    uint32_t s0[4], s1[4];
+                    sad4(2 * k, s0);
+                    sad4(2 * k + 1, s1);
+                    const uint32_t m0 = __vminu2(__vimin3_u16x2(s0[0], s0[1], s0[2]), s0[3]);
+                    const uint32_t m1 = __vminu2(__vimin3_u16x2(s1[0], s1[1], s1[2]), s1[3]);
+                    const uint32_t mm = __vminu2(__byte_perm(m0, m1, 0x5410), __byte_perm(m0, m1, 0x7632));
+                    pm[k] = mm;
+                    best = __vimin3_u32(best, (mm << 16) | (uint32_t)(2 * k), (mm & 0xFFFF0000u) | (uint32_t)(2 * k + 1));
+                }
+                const int minsad = (int)(best >> 16), oc = (int)(best & 0xFFFFu);
+                // exact position inside the argmin octet (first minimum) via (value << 3 | index) keys
+                int mind;
+                {
+                    uint32_t sv[4];
+                    sad4f(oc, sv);
+                    const uint32_t s0 = sv[0], s1 = sv[1], s2 = sv[2], s3 = sv[3];
+                    uint32_t k = __vimin3_u32((s0 & 0xFFFFu) * 8u, (s0 >> 16) * 8u + 1u, (s1 & 0xFFFFu) * 8u + 2u);
+                    k = __vimin3_u32(k, (s1 >> 16) * 8u + 3u, (s2 & 0xFFFFu) * 8u + 4u);
+                    k = __vimin3_u32(k, (s2 >> 16) * 8u + 5u, (s3 & 0xFFFFu) * 8u + 6u);
+                    k = min(k, (s3 >> 16) * 8u + 7u);
+                    mind = 8 * oc + (int)(k & 7u);
+                }
+                const int dp = mind + 1 < ND ? mind + 1 : ND - 2, dn = mind > 0 ? mind - 1 : 1;
+                const uint16_t *a16 = reinterpret_cast<const uint16_t *>(pa);
+                const uint16_t *b16 = reinterpret_cast<const uint16_t *>(pb);
+                const uint16_t *c16 = reinterpret_cast<const uint16_t *>(pc);
+                const int ip = dp ^ xflip, in = dn ^ xflip;
+                const int p = (int)a16[ip] + (int)b16[ip] - (int)c16[ip];
+                const int n = (int)a16[in] + (int)b16[in] - (int)c16[in];
+                bool ok = true;
+                if (a.uniq > 0) {
+                    const int thresh = minsad + (minsad * a.uniq / 100);
+                    const int zlo = max(mind - 1, 0), zhi = min(mind + 1, ND - 1);
+                    const int olo = zlo >> 3, ohi = zhi >> 3;
+                    // octets that do not touch [mind-1, mind+1]: their minimum decides
+                    uint4 *s4 = reinterpret_cast<uint4 *>(scr);
+                    uint16_t *s16 = reinterpret_cast<uint16_t *>(scr);
+#pragma unroll
+                    for (int k = 0; k < NO_ / 8; k++) s4[k] = make_uint4(pm[4 * k], pm[4 * k + 1], pm[4 * k + 2], pm[4 * k + 3]);
+                    s16[olo] = 0xFFFFu;
+                    s16[ohi] = 0xFFFFu;
+                    uint32_t m2 = 0xFFFFFFFFu;
+#pragma unroll
+                    for (int k = 0; k < NO_ / 8; k++) {
+                        const uint4 v = s4[k];
+                        m2 = __vminu2(m2, __vminu2(__vimin3_u16x2(v.x, v.y, v.z), v.w));
+                    }
+                    ok = (int)min(m2 & 0xFFFFu, m2 >> 16) > thresh;
+                    // the (at most two) touching octets: exact check with the neighbourhood masked out
+                    for (int oo = olo; ok && oo <= ohi; oo++) {
+                        uint32_t sv[4];
+                        sad4f(oo, sv);
+                        const uint4 Z = c_zmask[mind - 8 * oo + 1];
+                        const uint32_t mz = __vminu2(__vminu2(sv[0] | Z.x, sv[1] | Z.y), __vminu2(sv[2] | Z.z, sv[3] | Z.w));
+                        ok = (int)min(mz & 0xFFFFu, mz >> 16) > thresh;
+                    }
+                }
+                if (ok) {
+                    // v = (nd - mind - 1) * 256 + (q ? (p - n) * 256 / q : 0) + 15, C division (truncating);
+                    // q = p + n - 2 * minsad + |p - n| >= 2 |p - n| -> |quotient| <= 128, exact through one fp32 reciprocal
+                    const int dpn = p - n, adpn = abs(dpn);
+                    const int qd = p + n - 2 * minsad + adpn;
+                    int quo = 0;
+                    if (qd != 0) {
+                        const int num = adpn * 256;                                 // < 2^24
+                        int t = (int)((float)num * __frcp_rn((float)qd));
+                        const int rem = num - t * qd;
+                        t += rem >= qd ? 1 : 0;
+                        t -= rem < 0 ? 1 : 0;
+                        quo = dpn < 0 ? -t : t;
+                    }
+                    const int v = (ND - mind - 1) * 256 + quo + 15;
+                    dout = (int16_t)(v >> 4);
+                    costv = minsad;
+                    okc = true;
+                }
+            }
+            if (have_next) {
+                commit_word(0, y + H_ + 2, f00, f01);
+                if (two) commit_word(1, y + H_ + 2, f10, f11);
+            }
+            if (y + 2 < y1) bar_arrive(3 + (y & 1), NT);        // the buffer of row y may be overwritten (row y + 2)
+            if (x >= 0) {
+                *dptr = dout;
+                if (cptr && okc) *cptr = (int16_t)costv;
+            }
+            dptr += a.disp.pitch;
+            if (cptr) cptr += a.cost.pitch;
+            tsum = tnext;
+        }
+    }
+}
+
+struct Tiling3 { int NG, TW, BH, nstripes, nbands, NT; size_t smem; };
+
+bool pick_tiling3(const BmGeom &g, int n, Tiling3 *t)
+{
+    const int h = g.bs / 2;
+    if (g.minD != 0 || !(h == 2 || h == 4 || h == 6)) return false;
+    if (!(g.nd == 128 || g.nd == 64)) return false;
+    const int NO = g.nd / 8, G = 2 * h;
+    int ngmax = (MAXT - NCW * 32) / (2 * NO);            // producer threads = NG * 2 * NO
+    if (NO < 16) ngmax &= ~((16 / NO) - 1);              // whole producer warps
+    // shared memory: at most ~200 KB
+    while (ngmax > 2 && (size_t)make_geo3(h, g.nd, ngmax).total > 200 * 1024) ngmax--;
+    int twmax = std::min(ngmax * G - 2 * h, NCW * 32);
+    if (twmax < 16) return false;
+    t->nstripes = cdiv(g.W1, twmax);
+    t->TW = cdiv(g.W1, t->nstripes);
+    t->NG = cdiv(t->TW + 2 * h, G);
+    if (NO < 16) t->NG = (int)align_up(t->NG, 16 / NO);
+    if (t->NG > ngmax) return false;
+    t->NT = t->NG * 2 * NO + NCW * 32;
+    const int rows = g.row1 - g.row0;
+    int bhmax = 128;
+    while (bhmax > 32 && (long long)n * t->nstripes * cdiv(rows, bhmax) < 2 * 148) bhmax /= 2;
+    t->nbands = cdiv(rows, bhmax);
+    t->BH = cdiv(rows, t->nbands);
+    t->smem = (size_t)make_geo3(h, g.nd, t->NG).total;
+    return t->smem <= 200 * 1024;
+}
+
+bool g_zmask_ready[64] = {false};
+
+int upload_zmask()
+{
+    int dev = 0;
+    RTDM_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && g_zmask_ready[dev]) return 0;
+    uint32_t zm[10][4];
+    for (int e = 0; e < 10; e++) {
+        const int rel = e - 1;
+        for (int r = 0; r < 4; r++) {
+            uint32_t m = 0;
+            for (int s = 0; s < 2; s++) {
+                const int pos = 2 * r + s;
+                if (pos >= rel - 1 && pos <= rel + 1) m |= 0xFFFFu << (16 * s);
+            }
+            zm[e][r] = m;
+        }
+    }
+    RTDM_CUDA(cudaMemcpyToSymbol(c_zmask, zm, sizeof(zm)));
+    if (dev >= 0 && dev < 64) g_zmask_ready[dev] = true;
+    return 0;
+}
+
+template <int H_, int NO_>
+int launch3(const Bm3Args &a, const Tiling3 &t, int n, cudaStream_t st)
+{
+    RTDM_CUDA(cudaFuncSetAttribute(bm_sad3_kernel<H_, NO_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem));
+    bm_sad3_kernel<H_, NO_><<<dim3(t.nstripes, t.nbands, n), t.NT, t.smem, st>>>(a);
+    return 0;
+}
+
+}  // namespace
+
+bool bm_sad3_supported(const BmGeom &g, int n)
+{
+    Tiling3 t;
+    return g.W1 >= 1 && g.row1 > g.row0 && pick_tiling3(g, n, &t);
+}
+
+// SAD + WTA kernel only; the texture sums `tex` must have been produced already (bm_sad2.cu: bm_texture_kernel)
+int launch_bm_sad3_core(const BmGeom &g, int n, PlaneU8 Lp, PlaneU8 Rp, PlaneS16 disp, PlaneS16 cost,
+                        const uint16_t *tex, size_t tex_pitch, size_t tex_frame, cudaStream_t st)
+{
+    Tiling3 t;
+    if (!pick_tiling3(g, n, &t)) { set_error("bm_sad3: unsupported geometry"); return -RTDM_EINVAL; }
+    int rc = upload_zmask();
+    if (rc) return rc;
+    Bm3Args a;
+    a.Lp = Lp; a.Rp = Rp; a.disp = disp; a.cost = cost;
+    a.tex = tex; a.tex_pitch = tex_pitch; a.tex_frame = tex_frame;
+    a.W = g.W; a.H = g.H; a.nd = g.nd; a.cap = g.cap; a.texThr = g.texThr; a.uniq = g.uniq;
+    a.W1 = g.W1; a.row0 = g.row0; a.row1 = g.row1;
+    a.TW = t.TW; a.BH = t.BH; a.NG = t.NG;
+    { const char *e = getenv("RTDM_BM_DEBUG"); a.dbg = e ? atoi(e) : 0; }
+    const int h = g.bs / 2;
+    if (g.nd == 128) {
+        switch (h) {
+            case 2: rc = launch3<2, 16>(a, t, n, st); break;
+            case 4: rc = launch3<4, 16>(a, t, n, st); break;
+            default: rc = launch3<6, 16>(a, t, n, st); break;
+        }
+    } else {
+        switch (h) {
+            case 2: rc = launch3<2, 8>(a, t, n, st); break;
+            case 4: rc = launch3<4, 8>(a, t, n, st); break;
+            default: rc = launch3<6, 8>(a, t, n, st); break;
+        }
+    }
+    if (rc) return rc;
+    RTDM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace rtdm
