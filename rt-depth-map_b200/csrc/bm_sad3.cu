@@ -37,7 +37,6 @@ namespace {
 
 constexpr int NCW = 8;                  // consumer warps
 constexpr int MAXT = 768;               // threads per CTA (producers + consumers)
-constexpr int SCR = 48;                 // consumer scratch bytes per thread (8 words + pad: conflict-free 128-bit rows)
 
 __host__ __device__ constexpr int ring_rows3(int h) { return 2 * h + 4 <= 16 ? 16 : 32; }
 
@@ -60,10 +59,12 @@ struct Bm3Args {
 __constant__ uint4 c_zmask[10];
 
 // shared-memory geometry shared by host and device
+constexpr int MNP = 48;                 // bytes per pixel of the octet-minima rows (<= 16 x u16 + pad: conflict-free 128-bit rows)
 struct Geo3 {
-    int NCT, PP, BUFSZ, XOFF, TAOFF, TBOFF, ZOFF;   // one buffer: X[NCT] | TA[NG] | TB[NG] | zero row
+    // one buffer: X[NCT] | HA[NG] | HB[NG] | TA[NG] | TB[NG] | zero row (pitch PP each) | Mn[NCT] (pitch MNP)
+    int NCT, PP, BUFSZ, XOFF, HAOFF, HBOFF, TAOFF, TBOFF, ZOFF, MNOFF;
     int LF, LM, RF, RM, RMX, SLOT;                   // ring slot: byte offsets of the four virtual rows
-    int SCROFF, RINGOFF, total;
+    int RINGOFF, total;
 };
 __host__ __device__ inline Geo3 make_geo3(int h, int nd, int NG)
 {
@@ -72,10 +73,13 @@ __host__ __device__ inline Geo3 make_geo3(int h, int nd, int NG)
     q.NCT = NG * G;
     q.PP = nd * 2 + 16;
     q.XOFF = 0;
-    q.TAOFF = q.NCT * q.PP;
+    q.HAOFF = q.NCT * q.PP;
+    q.HBOFF = q.HAOFF + NG * q.PP;
+    q.TAOFF = q.HBOFF + NG * q.PP;
     q.TBOFF = q.TAOFF + NG * q.PP;
     q.ZOFF = q.TBOFF + NG * q.PP;
-    q.BUFSZ = q.ZOFF + q.PP;
+    q.MNOFF = q.ZOFF + q.PP;
+    q.BUFSZ = q.MNOFF + q.NCT * MNP;
     q.LF = 0;
     q.LM = q.NCT;
     q.RF = 2 * q.NCT;
@@ -84,8 +88,7 @@ __host__ __device__ inline Geo3 make_geo3(int h, int nd, int NG)
     q.RMX = q.NCT + nd + 2;                    // mirrored right row: RMv[n] = Rv[RMX - n];  RMX == 2 (mod 4)
     const int RMP = q.NCT + nd + 16;
     q.SLOT = q.RM + RMP;
-    q.SCROFF = 2 * q.BUFSZ;
-    q.RINGOFF = q.SCROFF + NCW * 32 * SCR;
+    q.RINGOFF = 2 * q.BUFSZ;
     q.total = q.RINGOFF + ring_rows3(h) * q.SLOT;
     return q;
 }
@@ -107,7 +110,7 @@ bm_sad3_kernel(Bm3Args a)
 {
     constexpr int G = 2 * H_, RING = ring_rows3(H_);
     constexpr int NLW = (H_ + 3) / 4, NRW = (H_ + 7 + 3) / 4;
-    constexpr int ND = NO_ * 8;
+    constexpr int ND = NO_ * 8, PP = ND * 2 + 16;
     extern __shared__ __align__(16) uint8_t smem[];
     const int tid = threadIdx.x, f = blockIdx.z;
     const int x0 = blockIdx.x * a.TW;
@@ -115,7 +118,7 @@ bm_sad3_kernel(Bm3Args a)
     const int y0 = a.row0 + blockIdx.y * a.BH, y1 = min(y0 + a.BH, a.row1);
     if (TWc <= 0 || y0 >= y1) return;
     const Geo3 q = make_geo3(H_, ND, a.NG);
-    const int NPT = a.NG * 2 * NO_;                    // producer threads (a multiple of 32)
+    const int NPT = ((a.NG * NO_ + 31) / 32) * 64;     // producer threads: whole warps of A halves + as many of B halves
     const int NT = NPT + NCW * 32;
     uint8_t *Ring = smem + q.RINGOFF;
     const uint8_t *Lg = a.Lp.p + (size_t)f * a.Lp.frame;
@@ -144,7 +147,7 @@ bm_sad3_kernel(Bm3Args a)
             if (rev) v = __byte_perm(v, 0, 0x0123);
             *reinterpret_cast<uint32_t *>(Ring + (size_t)(gy & (RING - 1)) * q.SLOT + 4 * w) = v;
         }
-        for (int i = tid; i < q.PP / 4; i += NT) {
+        for (int i = tid; i < PP / 4; i += NT) {
             reinterpret_cast<uint32_t *>(smem + q.ZOFF)[i] = 0u;
             reinterpret_cast<uint32_t *>(smem + q.BUFSZ + q.ZOFF)[i] = 0u;
         }
@@ -155,8 +158,12 @@ bm_sad3_kernel(Bm3Args a)
         // =========================================================================================
         // producer
         // =========================================================================================
-        const int hg = tid / NO_, j = tid - hg * NO_;
-        const int isB = hg & 1, g = hg >> 1;
+        // even producer warps hold A halves, odd warps B halves (type-uniform warps: phase 2 differs per type)
+        const int pw = tid >> 5, isB = pw & 1;
+        const int sidx = (pw >> 1) * 32 + (tid & 31);
+        const int g = sidx / NO_, j = sidx - g * NO_;
+        const int hg = 2 * g + isB;
+        const bool live = g < a.NG;                       // a trailing half warp may be idle (odd number of groups)
         // byte offsets of the thread's L and R streams inside a ring slot (both 4-byte aligned)
         const int lbo = isB ? q.LM + (q.NCT - (g + 1) * G) : q.LF + g * G;
         const int rbo = isB ? q.RM + (q.RMX - (g + 1) * G - 6 - 8 * j) : q.RF + g * G + 8 * j;
@@ -170,7 +177,7 @@ bm_sad3_kernel(Bm3Args a)
             if (c < cmin) { clmask |= 1u << k; crc = cmin; }
             if (c > cmax) { clmask |= 1u << k; crc = cmax; }
         }
-        const bool wborder = __any_sync(0xFFFFFFFFu, clmask != 0);
+        const bool wborder = __any_sync(0xFFFFFFFFu, live && clmask != 0);
         // clamped columns read the R window of the nearest unclamped column: its stream offset in this thread's copy
         const int cbo = isB ? q.RM + (q.RMX - crc - 8 * j - 7) : q.RF + crc + 8 * j;
 
@@ -206,7 +213,7 @@ bm_sad3_kernel(Bm3Args a)
         };
 
         // vertical sums over rows y0-h-1 .. y0+h-1 (the first loop iteration removes row y0-h-1 again)
-        for (int r = y0 - H_ - 1; r < y0 + H_; r++) {
+        for (int r = y0 - H_ - 1; live && r < y0 + H_; r++) {
             const uint8_t *slot = Ring + (size_t)(r & (RING - 1)) * q.SLOT;
             uint32_t lw[NLW], rw[NRW], c0w = 0, c1w = 0;
             load_words(slot, lw, rw);
@@ -222,55 +229,86 @@ bm_sad3_kernel(Bm3Args a)
             }
         }
 
-        const int xst = q.XOFF + (hg * H_) * q.PP + 16 * j;                   // store base of the thread's h slots
-        const int tst = (isB ? q.TBOFF : q.TAOFF) + g * q.PP + 16 * j;
+        const int xst = q.XOFF + (hg * H_) * PP + 16 * j;                    // store base of the thread's h slots
+        const int hst = (isB ? q.HBOFF : q.HAOFF) + g * PP + 16 * j;          // own half total
+        // phase 2: A half of group g makes the pixels gG + k, B half the pixels gG + G - 1 - k; both need group g + 1
+        const bool ph2 = live && g + 1 < a.NG;
+        const int nxt = q.XOFF + ((g + 1) * G + (isB ? H_ : 0)) * PP + 16 * j; // next group's half of the same type
+        const int mst = q.MNOFF + (isB ? g * G + G - 1 : g * G) * MNP + 2 * j;
+        const int mstep = isB ? -MNP : MNP;
+        auto rev4 = [](uint4 v) {
+            return make_uint4(__byte_perm(v.w, 0, 0x1032), __byte_perm(v.z, 0, 0x1032), __byte_perm(v.y, 0, 0x1032), __byte_perm(v.x, 0, 0x1032));
+        };
+        auto emit_min = [&](uint8_t *buf, int k, uint32_t s0, uint32_t s1, uint32_t s2, uint32_t s3) {
+            uint32_t m = __vminu2(__vimin3_u16x2(s0, s1, s2), s3);
+            m = __vminu2(m, m >> 16);
+            *reinterpret_cast<uint16_t *>(buf + mst + k * mstep) = (uint16_t)m;
+        };
 
         auto row = [&](int y, auto border_tag) {
             constexpr bool BORDER = decltype(border_tag)::value;
             uint8_t *buf = smem + (y & 1) * q.BUFSZ;
-            const uint8_t *sin = Ring + (size_t)((y + H_) & (RING - 1)) * q.SLOT;
-            const uint8_t *sout = Ring + (size_t)((y - H_ - 1) & (RING - 1)) * q.SLOT;
-            uint32_t lwi[NLW], rwi[NRW], lwo[NLW], rwo[NRW];
-            uint32_t ci0 = 0, ci1 = 0, co0 = 0, co1 = 0;
-            load_words(sin, lwi, rwi);
-            load_words(sout, lwo, rwo);
-            if (BORDER) { clamped_window(sin, ci0, ci1); clamped_window(sout, co0, co1); }
             uint4 p = make_uint4(0, 0, 0, 0);
-            uint8_t *pdst = buf + xst;
+            if (live) {
+                const uint8_t *sin = Ring + (size_t)((y + H_) & (RING - 1)) * q.SLOT;
+                const uint8_t *sout = Ring + (size_t)((y - H_ - 1) & (RING - 1)) * q.SLOT;
+                uint32_t lwi[NLW], rwi[NRW], lwo[NLW], rwo[NRW];
+                uint32_t ci0 = 0, ci1 = 0, co0 = 0, co1 = 0;
+                load_words(sin, lwi, rwi);
+                load_words(sout, lwo, rwo);
+                if (BORDER) { clamped_window(sin, ci0, ci1); clamped_window(sout, co0, co1); }
+                uint8_t *pdst = buf + xst;
 #pragma unroll
-            for (int k = 0; k < H_; k++) {
-                uint32_t lo, hi, olo, ohi;
-                ad_col(lwi, rwi, k, BORDER, ci0, ci1, lo, hi);
-                ad_col(lwo, rwo, k, BORDER, co0, co1, olo, ohi);
-                lo = lo + 0x80808080u - olo;                 // per byte: in + 128 - out (no borrow)
-                hi = hi + 0x80808080u - ohi;
-                V[k][0] += __byte_perm(lo, 0, 0x4140) - 0x00800080u;
-                V[k][1] += __byte_perm(lo, 0, 0x4342) - 0x00800080u;
-                V[k][2] += __byte_perm(hi, 0, 0x4140) - 0x00800080u;
-                V[k][3] += __byte_perm(hi, 0, 0x4342) - 0x00800080u;
-                p.x += V[k][0]; p.y += V[k][1]; p.z += V[k][2]; p.w += V[k][3];
-                *reinterpret_cast<uint4 *>(pdst + k * q.PP) = p;
+                for (int k = 0; k < H_; k++) {
+                    uint32_t lo, hi, olo, ohi;
+                    ad_col(lwi, rwi, k, BORDER, ci0, ci1, lo, hi);
+                    ad_col(lwo, rwo, k, BORDER, co0, co1, olo, ohi);
+                    lo = lo + 0x80808080u - olo;                 // per byte: in + 128 - out (no borrow)
+                    hi = hi + 0x80808080u - ohi;
+                    V[k][0] += __byte_perm(lo, 0, 0x4140) - 0x00800080u;
+                    V[k][1] += __byte_perm(lo, 0, 0x4342) - 0x00800080u;
+                    V[k][2] += __byte_perm(hi, 0, 0x4140) - 0x00800080u;
+                    V[k][3] += __byte_perm(hi, 0, 0x4342) - 0x00800080u;
+                    p.x += V[k][0]; p.y += V[k][1]; p.z += V[k][2]; p.w += V[k][3];
+                    *reinterpret_cast<uint4 *>(pdst + k * PP) = p;
+                }
+                *reinterpret_cast<uint4 *>(buf + hst) = p;       // half total, in this half's order
             }
-            // group total in this half's order: own half + the partner's, whose disparities run the other way
-            uint4 o;
-            o.x = __shfl_xor_sync(0xFFFFFFFFu, p.x, NO_);
-            o.y = __shfl_xor_sync(0xFFFFFFFFu, p.y, NO_);
-            o.z = __shfl_xor_sync(0xFFFFFFFFu, p.z, NO_);
-            o.w = __shfl_xor_sync(0xFFFFFFFFu, p.w, NO_);
-            p.x += __byte_perm(o.w, 0, 0x1032);
-            p.y += __byte_perm(o.z, 0, 0x1032);
-            p.z += __byte_perm(o.y, 0, 0x1032);
-            p.w += __byte_perm(o.x, 0, 0x1032);
-            *reinterpret_cast<uint4 *>(buf + tst) = p;
+            bar_sync(5, NPT);                                    // all prefix / suffix sums of row y are in shared memory
+            if (ph2) {
+                if (!isB) {
+                    // A pixels: SAD(gG + k) = T[g] - PreA[k - 1] + PreA'[k]
+                    const uint4 hb = rev4(*reinterpret_cast<const uint4 *>(buf + q.HBOFF + g * PP + 16 * j));
+                    uint4 run = make_uint4(p.x + hb.x, p.y + hb.y, p.z + hb.z, p.w + hb.w);
+                    *reinterpret_cast<uint4 *>(buf + q.TAOFF + g * PP + 16 * j) = run;
+#pragma unroll
+                    for (int k = 0; k < H_; k++) {
+                        const uint4 l = *reinterpret_cast<const uint4 *>(buf + nxt + k * PP);
+                        emit_min(buf, k, run.x + l.x, run.y + l.y, run.z + l.z, run.w + l.w);
+                        run.x -= V[k][0]; run.y -= V[k][1]; run.z -= V[k][2]; run.w -= V[k][3];
+                    }
+                } else {
+                    // B pixels: SAD(gG + G - 1 - k) = SufB[k] + T[g + 1] - SufB'[k - 1]
+                    const uint4 ha = rev4(*reinterpret_cast<const uint4 *>(buf + q.HAOFF + (g + 1) * PP + 16 * j));
+                    const uint4 hb = *reinterpret_cast<const uint4 *>(buf + q.HBOFF + (g + 1) * PP + 16 * j);
+                    uint4 run = make_uint4(ha.x + hb.x, ha.y + hb.y, ha.z + hb.z, ha.w + hb.w);
+                    *reinterpret_cast<uint4 *>(buf + q.TBOFF + (g + 1) * PP + 16 * j) = run;
+#pragma unroll
+                    for (int k = 0; k < H_; k++) {
+                        run.x += V[k][0]; run.y += V[k][1]; run.z += V[k][2]; run.w += V[k][3];
+                        uint4 l = make_uint4(0, 0, 0, 0);
+                        if (k > 0) l = *reinterpret_cast<const uint4 *>(buf + nxt + (k - 1) * PP);
+                        emit_min(buf, k, run.x - l.x, run.y - l.y, run.z - l.z, run.w - l.w);
+                    }
+                }
+            }
         };
 
         for (int y = y0; y < y1; y++) {
             if (y - y0 >= 2) bar_sync(3 + (y & 1), NT);            // consumers are done with this buffer (row y - 2)
-            if (!(a.dbg & 2)) {
-                if (wborder) row(y, std::true_type());
-                else row(y, std::false_type());
-            }
-            bar_arrive(1 + (y & 1), NT);                           // sums of row y are complete
+            if (wborder) row(y, std::true_type());
+            else row(y, std::false_type());
+            bar_arrive(1 + (y & 1), NT);                           // sums and octet minima of row y are complete
         }
     } else {
         // =========================================================================================
@@ -326,17 +364,17 @@ bm_sad3_kernel(Bm3Args a)
         const bool flip = gi >= H_;
         int oa, ob, oc_;                                        // SAD = [oa] + [ob] - [oc_], byte offsets inside a buffer
         if (!flip) {
-            oa = q.TAOFF + gq * q.PP;
-            ob = q.XOFF + ((gq + 1) * G + gi) * q.PP;
-            oc_ = gi > 0 ? q.XOFF + (xx - 1) * q.PP : q.ZOFF;
+            oa = q.TAOFF + gq * PP;
+            ob = q.XOFF + ((gq + 1) * G + gi) * PP;
+            oc_ = gi > 0 ? q.XOFF + (xx - 1) * PP : q.ZOFF;
         } else {
-            oa = q.XOFF + (gq * G + H_ + (G - 1 - gi)) * q.PP;
-            ob = q.TBOFF + (gq + 1) * q.PP;
-            oc_ = gi < G - 1 ? q.XOFF + ((gq + 1) * G + H_ + (G - 2 - gi)) * q.PP : q.ZOFF;
+            oa = q.XOFF + (gq * G + H_ + (G - 1 - gi)) * PP;
+            ob = q.TBOFF + (gq + 1) * PP;
+            oc_ = gi < G - 1 ? q.XOFF + ((gq + 1) * G + H_ + (G - 2 - gi)) * PP : q.ZOFF;
         }
         const uint32_t usel = flip ? 0x5476u : 0x3210u;         // un-reverse selector: (sv[r], sv[3 - r]) -> forward word r
         const int xflip = flip ? 7 : 0;
-        uint8_t *scr = smem + q.SCROFF + ct * SCR;
+        const int omn = q.MNOFF + xx * MNP;                     // octet minima of this pixel (made by the producers)
         int16_t *dptr = a.disp.p + (size_t)f * a.disp.frame + (size_t)y0 * a.disp.pitch + lofs + x0 + xx;
         int16_t *cptr = a.cost.p ? a.cost.p + (size_t)f * a.cost.frame + (size_t)y0 * a.cost.pitch + lofs + x0 + xx : nullptr;
         const uint16_t *tptr = a.tex + (size_t)f * a.tex_frame + (size_t)y0 * a.tex_pitch + x0 + xx;
@@ -377,20 +415,19 @@ bm_sad3_kernel(Bm3Args a)
                     sv[2] = __byte_perm(r[2], r[1], usel);
                     sv[3] = __byte_perm(r[3], r[0], usel);
                 };
-                // pass 1: octet minima, two octets per word, and the argmin octet
+                // pass 1: the octet minima come from the producers (two per word); argmin octet by (min << 16 | octet) keys
+                uint4 *s4 = reinterpret_cast<uint4 *>(const_cast<uint8_t *>(buf) + omn);
+                uint16_t *s16 = reinterpret_cast<uint16_t *>(s4);
                 uint32_t pm[NO_ / 2];
+#pragma unroll
+                for (int k = 0; k < NO_ / 8; k++) {
+                    const uint4 v = s4[k];
+                    pm[4 * k] = v.x; pm[4 * k + 1] = v.y; pm[4 * k + 2] = v.z; pm[4 * k + 3] = v.w;
+                }
                 uint32_t best = 0xFFFFFFFFu;
 #pragma unroll
-                for (int k = 0; k < NO_ / 2; k++) {
-                    uint32_t s0[4], s1[4];
-                    sad4(2 * k, s0);
-                    sad4(2 * k + 1, s1);
-                    const uint32_t m0 = __vminu2(__vimin3_u16x2(s0[0], s0[1], s0[2]), s0[3]);
-                    const uint32_t m1 = __vminu2(__vimin3_u16x2(s1[0], s1[1], s1[2]), s1[3]);
-                    const uint32_t mm = __vminu2(__byte_perm(m0, m1, 0x5410), __byte_perm(m0, m1, 0x7632));
-                    pm[k] = mm;
-                    best = __vimin3_u32(best, (mm << 16) | (uint32_t)(2 * k), (mm & 0xFFFF0000u) | (uint32_t)(2 * k + 1));
-                }
+                for (int k = 0; k < NO_ / 2; k++)
+                    best = __vimin3_u32(best, (pm[k] << 16) | (uint32_t)(2 * k), (pm[k] & 0xFFFF0000u) | (uint32_t)(2 * k + 1));
                 const int minsad = (int)(best >> 16), oc = (int)(best & 0xFFFFu);
                 // exact position inside the argmin octet (first minimum) via (value << 3 | index) keys
                 int mind;
@@ -417,10 +454,6 @@ bm_sad3_kernel(Bm3Args a)
                     const int zlo = max(mind - 1, 0), zhi = min(mind + 1, ND - 1);
                     const int olo = zlo >> 3, ohi = zhi >> 3;
                     // octets that do not touch [mind-1, mind+1]: their minimum decides
-                    uint4 *s4 = reinterpret_cast<uint4 *>(scr);
-                    uint16_t *s16 = reinterpret_cast<uint16_t *>(scr);
-#pragma unroll
-                    for (int k = 0; k < NO_ / 8; k++) s4[k] = make_uint4(pm[4 * k], pm[4 * k + 1], pm[4 * k + 2], pm[4 * k + 3]);
                     s16[olo] = 0xFFFFu;
                     s16[ohi] = 0xFFFFu;
                     uint32_t m2 = 0xFFFFFFFFu;
@@ -483,18 +516,15 @@ bool pick_tiling3(const BmGeom &g, int n, Tiling3 *t)
     if (g.minD != 0 || !(h == 2 || h == 4 || h == 6)) return false;
     if (!(g.nd == 128 || g.nd == 64)) return false;
     const int NO = g.nd / 8, G = 2 * h;
-    int ngmax = (MAXT - NCW * 32) / (2 * NO);            // producer threads = NG * 2 * NO
-    if (NO < 16) ngmax &= ~((16 / NO) - 1);              // whole producer warps
-    // shared memory: at most ~200 KB
+    int ngmax = (MAXT - NCW * 32) / 64 * 32 / NO;        // producer threads = whole warps of A halves + as many of B halves
     while (ngmax > 2 && (size_t)make_geo3(h, g.nd, ngmax).total > 200 * 1024) ngmax--;
     int twmax = std::min(ngmax * G - 2 * h, NCW * 32);
     if (twmax < 16) return false;
     t->nstripes = cdiv(g.W1, twmax);
     t->TW = cdiv(g.W1, t->nstripes);
     t->NG = cdiv(t->TW + 2 * h, G);
-    if (NO < 16) t->NG = (int)align_up(t->NG, 16 / NO);
     if (t->NG > ngmax) return false;
-    t->NT = t->NG * 2 * NO + NCW * 32;
+    t->NT = (t->NG * NO + 31) / 32 * 64 + NCW * 32;
     const int rows = g.row1 - g.row0;
     int bhmax = 128;
     while (bhmax > 32 && (long long)n * t->nstripes * cdiv(rows, bhmax) < 2 * 148) bhmax /= 2;
