@@ -64,7 +64,7 @@ struct Geo3 {
     // one buffer: X[NCT] | HA[NG] | HB[NG] | TA[NG] | TB[NG] | zero row (pitch PP each) | Mn[NCT] (pitch MNP)
     int NCT, PP, BUFSZ, XOFF, HAOFF, HBOFF, TAOFF, TBOFF, ZOFF, MNOFF;
     int LF, LM, RF, RM, RMX, SLOT;                   // ring slot: byte offsets of the four virtual rows
-    int RINGOFF, total;
+    int RINGOFF, DESCOFF, total;
 };
 __host__ __device__ inline Geo3 make_geo3(int h, int nd, int NG)
 {
@@ -89,7 +89,9 @@ __host__ __device__ inline Geo3 make_geo3(int h, int nd, int NG)
     const int RMP = q.NCT + nd + 16;
     q.SLOT = q.RM + RMP;
     q.RINGOFF = 2 * q.BUFSZ;
-    q.total = q.RINGOFF + ring_rows3(h) * q.SLOT;
+    q.DESCOFF = q.RINGOFF + ring_rows3(h) * q.SLOT;
+    q.DESCOFF = (q.DESCOFF + 15) & ~15;
+    q.total = q.DESCOFF + (q.SLOT / 4) * 8;
     return q;
 }
 
@@ -121,6 +123,7 @@ bm_sad3_kernel(Bm3Args a)
     const int NPT = ((a.NG * NO_ + 31) / 32) * 64;     // producer threads: whole warps of A halves + as many of B halves
     const int NT = NPT + NCW * 32;
     uint8_t *Ring = smem + q.RINGOFF;
+    int2 *Desc = reinterpret_cast<int2 *>(smem + q.DESCOFF);
     const uint8_t *Lg = a.Lp.p + (size_t)f * a.Lp.frame;
     const uint8_t *Rg = a.Rp.p + (size_t)f * a.Rp.frame;
     const int lofs = ND - 1;
@@ -146,6 +149,16 @@ bm_sad3_kernel(Bm3Args a)
             for (int b = 0; b < 4; b++) v |= (uint32_t)src[src_col(right, cs + b)] << (8 * b);
             if (rev) v = __byte_perm(v, 0, 0x0123);
             *reinterpret_cast<uint32_t *>(Ring + (size_t)(gy & (RING - 1)) * q.SLOT + 4 * w) = v;
+        }
+        // loader descriptors: x = aligned byte offset of the word pair in the image row (or -1 - first virtual index for
+        // a clamped gather: first virtual index), y = funnel shift | right image << 8 | byte-reversed << 9 | gather << 10
+        for (int i = tid; i < nw; i += NT) {
+            int right, cs, rev;
+            ring_word_src(q, i, right, cs, rev);
+            const int xa = x0 - H_ + cs;
+            const bool inr = right ? (xa >= 0 && xa + 3 <= a.W - 1) : (xa >= -lofs && xa + 3 <= a.W - lofs - 1);
+            const int gcol = right ? xa : xa + lofs;
+            Desc[i] = inr ? make_int2(gcol & ~3, ((gcol & 3) * 8) | (right << 8) | (rev << 9)) : make_int2(cs, (right << 8) | (rev << 9) | 0x400);
         }
         for (int i = tid; i < PP / 4; i += NT) {
             reinterpret_cast<uint32_t *>(smem + q.ZOFF)[i] = 0u;
@@ -245,8 +258,13 @@ bm_sad3_kernel(Bm3Args a)
             *reinterpret_cast<uint16_t *>(buf + mst + k * mstep) = (uint16_t)m;
         };
 
-        auto row = [&](int y, auto border_tag) {
+        // Even rows of the band add the byte deltas (in + 128 - out), odd rows subtract the mirrored deltas
+        // (out + 128 - in): V += d + 128, then V += d - 128.  No per-lane bias correction is needed: after an even
+        // row every column sum carries +128, so every (2h+1)-column window sum carries the same (2h+1) * 128, which
+        // the consumers subtract from the minimum and the two neighbours (BIASC).
+        auto row = [&](int y, auto border_tag, auto odd_tag) {
             constexpr bool BORDER = decltype(border_tag)::value;
+            constexpr bool ODD = decltype(odd_tag)::value;
             uint8_t *buf = smem + (y & 1) * q.BUFSZ;
             uint4 p = make_uint4(0, 0, 0, 0);
             if (live) {
@@ -263,12 +281,21 @@ bm_sad3_kernel(Bm3Args a)
                     uint32_t lo, hi, olo, ohi;
                     ad_col(lwi, rwi, k, BORDER, ci0, ci1, lo, hi);
                     ad_col(lwo, rwo, k, BORDER, co0, co1, olo, ohi);
-                    lo = lo + 0x80808080u - olo;                 // per byte: in + 128 - out (no borrow)
-                    hi = hi + 0x80808080u - ohi;
-                    V[k][0] += __byte_perm(lo, 0, 0x4140) - 0x00800080u;
-                    V[k][1] += __byte_perm(lo, 0, 0x4342) - 0x00800080u;
-                    V[k][2] += __byte_perm(hi, 0, 0x4140) - 0x00800080u;
-                    V[k][3] += __byte_perm(hi, 0, 0x4342) - 0x00800080u;
+                    if (!ODD) {
+                        lo = lo + 0x80808080u - olo;                 // per byte: in + 128 - out (no borrow)
+                        hi = hi + 0x80808080u - ohi;
+                        V[k][0] += __byte_perm(lo, 0, 0x4140);
+                        V[k][1] += __byte_perm(lo, 0, 0x4342);
+                        V[k][2] += __byte_perm(hi, 0, 0x4140);
+                        V[k][3] += __byte_perm(hi, 0, 0x4342);
+                    } else {
+                        lo = olo + 0x80808080u - lo;                 // per byte: out + 128 - in
+                        hi = ohi + 0x80808080u - hi;
+                        V[k][0] -= __byte_perm(lo, 0, 0x4140);
+                        V[k][1] -= __byte_perm(lo, 0, 0x4342);
+                        V[k][2] -= __byte_perm(hi, 0, 0x4140);
+                        V[k][3] -= __byte_perm(hi, 0, 0x4342);
+                    }
                     p.x += V[k][0]; p.y += V[k][1]; p.z += V[k][2]; p.w += V[k][3];
                     *reinterpret_cast<uint4 *>(pdst + k * PP) = p;
                 }
@@ -306,8 +333,13 @@ bm_sad3_kernel(Bm3Args a)
 
         for (int y = y0; y < y1; y++) {
             if (y - y0 >= 2) bar_sync(3 + (y & 1), NT);            // consumers are done with this buffer (row y - 2)
-            if (wborder) row(y, std::true_type());
-            else row(y, std::false_type());
+            if (((y - y0) & 1) && !(a.dbg & 8)) {
+                if (wborder) row(y, std::true_type(), std::true_type());
+                else row(y, std::false_type(), std::true_type());
+            } else {
+                if (wborder) row(y, std::true_type(), std::false_type());
+                else row(y, std::false_type(), std::false_type());
+            }
             bar_arrive(1 + (y & 1), NT);                           // sums and octet minima of row y are complete
         }
     } else {
@@ -315,48 +347,56 @@ bm_sad3_kernel(Bm3Args a)
         // consumer (and loader)
         // =========================================================================================
         const int ct = tid - NPT, cw = ct >> 5, lane = ct & 31;
-        // ---- loader descriptors: up to two ring words per consumer thread ------------------------------
-        const int nw = q.SLOT / 4;
-        int d_dst[2], d_src[2], d_sh[2], d_right[2];
-        uint32_t d_sel[2];
+        if (cw == NCW - 1) {
+            // ---- loader warp: row y + h + 2 enters the ring while the consumers work on row y ----------------
+            // (rows up to y + h + 1 are there; the slot it overwrites was last read by the producers in row y - 1)
+            constexpr int MAXW = 10;                            // ring words per lane (SLOT / 4 <= 320)
+            const int nw = q.SLOT / 4;
+            for (int y = y0; y < y1; y++) {
+                const bool have_next = y + 1 < y1;
+                uint32_t w0[MAXW], w1[MAXW];
+                const int gy = y + H_ + 2, gyc = clampi3(gy, 0, a.H - 1);
+                const uint8_t *lrow = Lg + (size_t)gyc * a.Lp.pitch, *rrow = Rg + (size_t)gyc * a.Rp.pitch;
+                if (have_next) {
 #pragma unroll
-        for (int s = 0; s < 2; s++) {
-            const int i = ct + s * (NCW * 32);
-            d_dst[s] = -1; d_src[s] = -1; d_sh[s] = 0; d_right[s] = 0; d_sel[s] = 0x3210u;
-            if (i < nw) {
-                int right, cs, rev;
-                ring_word_src(q, i, right, cs, rev);
-                d_dst[s] = 4 * i; d_right[s] = right; d_sel[s] = rev ? 0x0123u : 0x3210u;
-                const int xa = x0 - H_ + cs;
-                const bool inr = right ? (xa >= 0 && xa + 3 <= a.W - 1) : (xa >= -lofs && xa + 3 <= a.W - lofs - 1);
-                if (inr) { const int gcol = right ? xa : xa + lofs; d_src[s] = gcol & ~3; d_sh[s] = (gcol & 3) * 8; }
-                else d_sh[s] = cs;
+                    for (int s = 0; s < MAXW; s++) {
+                        const int i = lane + 32 * s;
+                        w0[s] = 0; w1[s] = 0;
+                        if (i < nw) {
+                            const int2 d = Desc[i];
+                            const uint8_t *src = (d.y & 0x100) ? rrow : lrow;
+                            if (!(d.y & 0x400)) {
+                                const uint32_t *pw = reinterpret_cast<const uint32_t *>(src + d.x);
+                                w0[s] = pw[0]; w1[s] = pw[1];
+                            } else {
+                                const int cs = d.x;
+#pragma unroll
+                                for (int b = 0; b < 4; b++) w0[s] |= (uint32_t)src[src_col((d.y >> 8) & 1, cs + b)] << (8 * b);
+                            }
+                        }
+                    }
+                }
+                bar_sync(1 + (y & 1), NT);                      // the producers have finished row y (and its ring reads)
+                if (have_next) {
+                    uint8_t *slot = Ring + (size_t)(gy & (RING - 1)) * q.SLOT;
+#pragma unroll
+                    for (int s = 0; s < MAXW; s++) {
+                        const int i = lane + 32 * s;
+                        if (i < nw) {
+                            const int2 d = Desc[i];
+                            const uint32_t v = !(d.y & 0x400) ? __funnelshift_r(w0[s], w1[s], d.y & 31) : w0[s];
+                            *reinterpret_cast<uint32_t *>(slot + 4 * i) = __byte_perm(v, 0, (d.y & 0x200) ? 0x0123u : 0x3210u);
+                        }
+                    }
+                }
+                if (y + 2 < y1) bar_arrive(3 + (y & 1), NT);
             }
+            return;
         }
-        const bool two = __any_sync(0xFFFFFFFFu, d_dst[1] >= 0);
-        auto fetch_word = [&](int s, int gy, uint32_t &w0, uint32_t &w1) {
-            w0 = 0; w1 = 0;
-            if (d_dst[s] < 0) return;
-            const int gyc = clampi3(gy, 0, a.H - 1);
-            const uint8_t *src = d_right[s] ? Rg + (size_t)gyc * a.Rp.pitch : Lg + (size_t)gyc * a.Lp.pitch;
-            if (d_src[s] >= 0) {
-                const uint32_t *pw = reinterpret_cast<const uint32_t *>(src + d_src[s]);
-                w0 = pw[0]; w1 = pw[1];
-            } else {
-#pragma unroll
-                for (int b = 0; b < 4; b++) w0 |= (uint32_t)src[src_col(d_right[s], d_sh[s] + b)] << (8 * b);
-            }
-        };
-        auto commit_word = [&](int s, int gy, uint32_t w0, uint32_t w1) {
-            if (d_dst[s] < 0) return;
-            const uint32_t v = d_src[s] >= 0 ? __funnelshift_r(w0, w1, d_sh[s]) : w0;
-            *reinterpret_cast<uint32_t *>(Ring + (size_t)(gy & (RING - 1)) * q.SLOT + d_dst[s]) = __byte_perm(v, 0, d_sel[s]);
-        };
-
         // ---- the pixel of this thread --------------------------------------------------------------------
         int x = -1;
         {
-            const int PW = (TWc + NCW - 1) / NCW;               // pixels per consumer warp (<= 32: TW <= 256)
+            const int PW = (TWc + NCW - 2) / (NCW - 1);          // pixels per WTA warp (<= 32: TW <= 224)
             if (lane < PW && cw * PW + lane < TWc) x = cw * PW + lane;
         }
         const int xx = max(x, 0);
@@ -382,13 +422,8 @@ bm_sad3_kernel(Bm3Args a)
         int tsum = x >= 0 ? (int)*tptr : 0;
 
         for (int y = y0; y < y1; y++) {
-            // loader: row y + h + 2 (rows up to y + h + 1 are in the ring); texture sum of the next row
+            // texture sum of the next row
             const bool have_next = y + 1 < y1;
-            uint32_t f00 = 0, f01 = 0, f10 = 0, f11 = 0;
-            if (have_next) {
-                fetch_word(0, y + H_ + 2, f00, f01);
-                if (two) fetch_word(1, y + H_ + 2, f10, f11);
-            }
             int tnext = 0;
             if (have_next && x >= 0) tnext = (int)tptr[a.tex_pitch];
             tptr += a.tex_pitch;
@@ -428,7 +463,8 @@ bm_sad3_kernel(Bm3Args a)
 #pragma unroll
                 for (int k = 0; k < NO_ / 2; k++)
                     best = __vimin3_u32(best, (pm[k] << 16) | (uint32_t)(2 * k), (pm[k] & 0xFFFF0000u) | (uint32_t)(2 * k + 1));
-                const int minsad = (int)(best >> 16), oc = (int)(best & 0xFFFFu);
+                const int BIASC = ((a.dbg & 8) ? (y - y0 + 1) : !((y - y0) & 1)) * (2 * H_ + 1) * 128;    // see the producers' row()
+                const int minsad = (int)(best >> 16) - BIASC, oc = (int)(best & 0xFFFFu);
                 // exact position inside the argmin octet (first minimum) via (value << 3 | index) keys
                 int mind;
                 {
@@ -446,11 +482,11 @@ bm_sad3_kernel(Bm3Args a)
                 const uint16_t *b16 = reinterpret_cast<const uint16_t *>(pb);
                 const uint16_t *c16 = reinterpret_cast<const uint16_t *>(pc);
                 const int ip = dp ^ xflip, in = dn ^ xflip;
-                const int p = (int)a16[ip] + (int)b16[ip] - (int)c16[ip];
-                const int n = (int)a16[in] + (int)b16[in] - (int)c16[in];
+                const int p = (int)a16[ip] + (int)b16[ip] - (int)c16[ip] - BIASC;
+                const int n = (int)a16[in] + (int)b16[in] - (int)c16[in] - BIASC;
                 bool ok = true;
                 if (a.uniq > 0) {
-                    const int thresh = minsad + (minsad * a.uniq / 100);
+                    const int thresh = minsad + (minsad * a.uniq / 100) + BIASC;     // compared with biased sums
                     const int zlo = max(mind - 1, 0), zhi = min(mind + 1, ND - 1);
                     const int olo = zlo >> 3, ohi = zhi >> 3;
                     // octets that do not touch [mind-1, mind+1]: their minimum decides
@@ -480,7 +516,7 @@ bm_sad3_kernel(Bm3Args a)
                     int quo = 0;
                     if (qd != 0) {
                         const int num = adpn * 256;                                 // < 2^24
-                        int t = (int)((float)num * __frcp_rn((float)qd));
+                        int t = (a.dbg & 16) ? (int)((float)num * __frcp_rn((float)qd)) : (int)__fdividef((float)num, (float)qd);
                         const int rem = num - t * qd;
                         t += rem >= qd ? 1 : 0;
                         t -= rem < 0 ? 1 : 0;
@@ -491,10 +527,6 @@ bm_sad3_kernel(Bm3Args a)
                     costv = minsad;
                     okc = true;
                 }
-            }
-            if (have_next) {
-                commit_word(0, y + H_ + 2, f00, f01);
-                if (two) commit_word(1, y + H_ + 2, f10, f11);
             }
             if (y + 2 < y1) bar_arrive(3 + (y & 1), NT);        // the buffer of row y may be overwritten (row y + 2)
             if (x >= 0) {
@@ -517,8 +549,8 @@ bool pick_tiling3(const BmGeom &g, int n, Tiling3 *t)
     if (!(g.nd == 128 || g.nd == 64)) return false;
     const int NO = g.nd / 8, G = 2 * h;
     int ngmax = (MAXT - NCW * 32) / 64 * 32 / NO;        // producer threads = whole warps of A halves + as many of B halves
-    while (ngmax > 2 && (size_t)make_geo3(h, g.nd, ngmax).total > 200 * 1024) ngmax--;
-    int twmax = std::min(ngmax * G - 2 * h, NCW * 32);
+    while (ngmax > 2 && ((size_t)make_geo3(h, g.nd, ngmax).total > 200 * 1024 || make_geo3(h, g.nd, ngmax).SLOT / 4 > 320)) ngmax--;   // 320: loader warp, 10 words per lane
+    int twmax = std::min(ngmax * G - 2 * h, (NCW - 1) * 32);
     if (twmax < 16) return false;
     t->nstripes = cdiv(g.W1, twmax);
     t->TW = cdiv(g.W1, t->nstripes);
