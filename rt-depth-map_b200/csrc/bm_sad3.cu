@@ -35,7 +35,8 @@
 namespace rtdm {
 namespace {
 
-constexpr int NCW = 8;                  // consumer warps
+constexpr int NCW = 8;                  // consumer-side warps: NCW - NLD winner-take-all warps + NLD loader warps
+constexpr int NLD = 2;
 constexpr int MAXT = 768;               // threads per CTA (producers + consumers)
 
 __host__ __device__ constexpr int ring_rows3(int h) { return 2 * h + 4 <= 16 ? 16 : 32; }
@@ -347,11 +348,20 @@ bm_sad3_kernel(Bm3Args a)
         // consumer (and loader)
         // =========================================================================================
         const int ct = tid - NPT, cw = ct >> 5, lane = ct & 31;
-        if (cw == NCW - 1) {
-            // ---- loader warp: row y + h + 2 enters the ring while the consumers work on row y ----------------
+        if (cw >= NCW - NLD) {
+            // ---- loader warps: row y + h + 2 enters the ring while the consumers work on row y ---------------
             // (rows up to y + h + 1 are there; the slot it overwrites was last read by the producers in row y - 1)
-            constexpr int MAXW = 10;                            // ring words per lane (SLOT / 4 <= 320)
+            constexpr int MAXW = 320 / (32 * NLD);              // ring words per lane (SLOT / 4 <= 320)
             const int nw = q.SLOT / 4;
+            const int ll = (cw - (NCW - NLD)) * 32 + lane;
+            int off[MAXW];
+            uint32_t meta[MAXW];                                // Desc.y | valid << 11
+#pragma unroll
+            for (int s = 0; s < MAXW; s++) {
+                const int i = ll + 32 * NLD * s;
+                off[s] = 0; meta[s] = 0;
+                if (i < nw) { const int2 d = Desc[i]; off[s] = d.x; meta[s] = (uint32_t)d.y | 0x800u; }
+            }
             for (int y = y0; y < y1; y++) {
                 const bool have_next = y + 1 < y1;
                 uint32_t w0[MAXW], w1[MAXW];
@@ -360,32 +370,27 @@ bm_sad3_kernel(Bm3Args a)
                 if (have_next) {
 #pragma unroll
                     for (int s = 0; s < MAXW; s++) {
-                        const int i = lane + 32 * s;
                         w0[s] = 0; w1[s] = 0;
-                        if (i < nw) {
-                            const int2 d = Desc[i];
-                            const uint8_t *src = (d.y & 0x100) ? rrow : lrow;
-                            if (!(d.y & 0x400)) {
-                                const uint32_t *pw = reinterpret_cast<const uint32_t *>(src + d.x);
+                        if (meta[s] & 0x800u) {
+                            const uint8_t *src = (meta[s] & 0x100u) ? rrow : lrow;
+                            if (!(meta[s] & 0x400u)) {
+                                const uint32_t *pw = reinterpret_cast<const uint32_t *>(src + off[s]);
                                 w0[s] = pw[0]; w1[s] = pw[1];
                             } else {
-                                const int cs = d.x;
 #pragma unroll
-                                for (int b = 0; b < 4; b++) w0[s] |= (uint32_t)src[src_col((d.y >> 8) & 1, cs + b)] << (8 * b);
+                                for (int b = 0; b < 4; b++) w0[s] |= (uint32_t)src[src_col((meta[s] >> 8) & 1, off[s] + b)] << (8 * b);
                             }
                         }
                     }
                 }
                 bar_sync(1 + (y & 1), NT);                      // the producers have finished row y (and its ring reads)
                 if (have_next) {
-                    uint8_t *slot = Ring + (size_t)(gy & (RING - 1)) * q.SLOT;
+                    uint8_t *slot = Ring + (size_t)(gy & (RING - 1)) * q.SLOT + 4 * ll;
 #pragma unroll
                     for (int s = 0; s < MAXW; s++) {
-                        const int i = lane + 32 * s;
-                        if (i < nw) {
-                            const int2 d = Desc[i];
-                            const uint32_t v = !(d.y & 0x400) ? __funnelshift_r(w0[s], w1[s], d.y & 31) : w0[s];
-                            *reinterpret_cast<uint32_t *>(slot + 4 * i) = __byte_perm(v, 0, (d.y & 0x200) ? 0x0123u : 0x3210u);
+                        if (meta[s] & 0x800u) {
+                            const uint32_t v = !(meta[s] & 0x400u) ? __funnelshift_r(w0[s], w1[s], meta[s] & 31u) : w0[s];
+                            *reinterpret_cast<uint32_t *>(slot + 128 * NLD * s) = __byte_perm(v, 0, (meta[s] & 0x200u) ? 0x0123u : 0x3210u);
                         }
                     }
                 }
@@ -396,7 +401,7 @@ bm_sad3_kernel(Bm3Args a)
         // ---- the pixel of this thread --------------------------------------------------------------------
         int x = -1;
         {
-            const int PW = (TWc + NCW - 2) / (NCW - 1);          // pixels per WTA warp (<= 32: TW <= 224)
+            const int PW = (TWc + NCW - NLD - 1) / (NCW - NLD);  // pixels per WTA warp (<= 32)
             if (lane < PW && cw * PW + lane < TWc) x = cw * PW + lane;
         }
         const int xx = max(x, 0);
@@ -550,7 +555,7 @@ bool pick_tiling3(const BmGeom &g, int n, Tiling3 *t)
     const int NO = g.nd / 8, G = 2 * h;
     int ngmax = (MAXT - NCW * 32) / 64 * 32 / NO;        // producer threads = whole warps of A halves + as many of B halves
     while (ngmax > 2 && ((size_t)make_geo3(h, g.nd, ngmax).total > 200 * 1024 || make_geo3(h, g.nd, ngmax).SLOT / 4 > 320)) ngmax--;   // 320: loader warp, 10 words per lane
-    int twmax = std::min(ngmax * G - 2 * h, (NCW - 1) * 32);
+    int twmax = std::min(ngmax * G - 2 * h, (NCW - NLD) * 32);
     if (twmax < 16) return false;
     t->nstripes = cdiv(g.W1, twmax);
     t->TW = cdiv(g.W1, t->nstripes);
