@@ -60,12 +60,12 @@ struct Bm3Args {
 __constant__ uint4 c_zmask[10];
 
 // shared-memory geometry shared by host and device
-constexpr int MNP = 48;                 // bytes per pixel of the octet-minima rows (<= 16 x u16 + pad: conflict-free 128-bit rows)
+constexpr int MNP = 80;                 // bytes per pixel of the octet-key rows (<= 16 x u32 + pad: conflict-free 128-bit rows)
 struct Geo3 {
     // one buffer: X[NCT] | HA[NG] | HB[NG] | TA[NG] | TB[NG] | zero row (pitch PP each) | Mn[NCT] (pitch MNP)
     int NCT, PP, BUFSZ, XOFF, HAOFF, HBOFF, TAOFF, TBOFF, ZOFF, MNOFF;
     int LF, LM, RF, RM, RMX, SLOT;                   // ring slot: byte offsets of the four virtual rows
-    int RINGOFF, DESCOFF, total;
+    int RINGOFF, DESCOFF, NITEM, total;
 };
 __host__ __device__ inline Geo3 make_geo3(int h, int nd, int NG)
 {
@@ -81,30 +81,43 @@ __host__ __device__ inline Geo3 make_geo3(int h, int nd, int NG)
     q.ZOFF = q.TBOFF + NG * q.PP;
     q.MNOFF = q.ZOFF + q.PP;
     q.BUFSZ = q.MNOFF + q.NCT * MNP;
-    q.LF = 0;
-    q.LM = q.NCT;
-    q.RF = 2 * q.NCT;
+    q.LF = 0;                                  // left rows are stored EXPANDED: one word = one pixel x 0x01010101
+    q.LM = 4 * q.NCT;
+    q.RF = 8 * q.NCT;
     const int RFP = q.NCT + nd + 8;
     q.RM = q.RF + RFP;
     q.RMX = q.NCT + nd + 2;                    // mirrored right row: RMv[n] = Rv[RMX - n];  RMX == 2 (mod 4)
     const int RMP = q.NCT + nd + 16;
-    q.SLOT = q.RM + RMP;
+    q.SLOT = (q.RM + RMP + 15) & ~15;         // 16-byte aligned slots: the expanded left rows move as 128-bit words
     q.RINGOFF = 2 * q.BUFSZ;
     q.DESCOFF = q.RINGOFF + ring_rows3(h) * q.SLOT;
     q.DESCOFF = (q.DESCOFF + 15) & ~15;
-    q.total = q.DESCOFF + (q.SLOT / 4) * 8;
+    q.NITEM = q.NCT / 2 + RFP / 4 + RMP / 4;   // loader items: one source word each (left: 4 expanded words out)
+    q.total = q.DESCOFF + q.NITEM * 8;
     return q;
 }
 
-// one word of a ring slot: which four virtual-row bytes it holds
-//   word index i inside the slot -> (right?, first forward virtual index cs, byte-reversed?)
-__device__ __forceinline__ void ring_word_src(const Geo3 &q, int i, int &right, int &cs, int &rev)
+// one loader item = four consecutive virtual-row bytes:
+//   item index i -> (right?, first forward virtual index cs, byte-reversed?, destination byte offset in the slot);
+//   left items are written as four expanded words (16 bytes), right items as one word
+__device__ __forceinline__ void ring_item_src(const Geo3 &q, int i, int &right, int &cs, int &rev, int &dst)
 {
-    const int b = 4 * i;
-    if (b < q.LM) { right = 0; rev = 0; cs = b; }
-    else if (b < q.RF) { right = 0; rev = 1; cs = q.NCT - 4 - (b - q.LM); }
-    else if (b < q.RM) { right = 1; rev = 0; cs = b - q.RF; }
-    else { right = 1; rev = 1; cs = q.RMX - 3 - (b - q.RM); }
+    const int nl = q.NCT / 4;
+    if (i < nl) { right = 0; rev = 0; cs = 4 * i; dst = q.LF + 16 * i; }
+    else if (i < 2 * nl) { const int m = i - nl; right = 0; rev = 1; cs = q.NCT - 4 - 4 * m; dst = q.LM + 16 * m; }
+    else {
+        const int b = 4 * (i - 2 * nl);               // byte offset from RF
+        right = 1; dst = q.RF + b;
+        if (q.RF + b < q.RM) { rev = 0; cs = b; }
+        else { rev = 1; cs = q.RMX - 3 - (q.RF + b - q.RM); }
+    }
+}
+__device__ __forceinline__ void ring_store(uint8_t *slot, int dst, bool left, uint32_t v)
+{
+    if (left)
+        *reinterpret_cast<uint4 *>(slot + dst) = make_uint4(__byte_perm(v, 0, 0x0000), __byte_perm(v, 0, 0x1111), __byte_perm(v, 0, 0x2222), __byte_perm(v, 0, 0x3333));
+    else
+        *reinterpret_cast<uint32_t *>(slot + dst) = v;
 }
 
 template <int H_, int NO_>
@@ -112,7 +125,7 @@ __global__ void __launch_bounds__(MAXT, 1)
 bm_sad3_kernel(Bm3Args a)
 {
     constexpr int G = 2 * H_, RING = ring_rows3(H_);
-    constexpr int NLW = (H_ + 3) / 4, NRW = (H_ + 7 + 3) / 4;
+    constexpr int NLW = H_, NRW = (H_ + 7 + 3) / 4;              // left: one expanded word per column
     constexpr int ND = NO_ * 8, PP = ND * 2 + 16;
     extern __shared__ __align__(16) uint8_t smem[];
     const int tid = threadIdx.x, f = blockIdx.z;
@@ -137,29 +150,30 @@ bm_sad3_kernel(Bm3Args a)
 
     // ---- prologue: ring rows y0-h-1 .. y0+h+1 by all threads (byte gathers), zero rows ------------------
     {
-        const int nw = q.SLOT / 4, nrows = 2 * H_ + 3;
+        const int nw = q.NITEM, nrows = 2 * H_ + 3;
         for (int i = tid; i < nw * nrows; i += NT) {
             const int r = i / nw, w = i - r * nw;
             const int gy = y0 - H_ - 1 + r;
             const int gyc = clampi3(gy, 0, a.H - 1);
-            int right, cs, rev;
-            ring_word_src(q, w, right, cs, rev);
+            int right, cs, rev, dst;
+            ring_item_src(q, w, right, cs, rev, dst);
             const uint8_t *src = (right ? Rg + (size_t)gyc * a.Rp.pitch : Lg + (size_t)gyc * a.Lp.pitch);
             uint32_t v = 0;
 #pragma unroll
             for (int b = 0; b < 4; b++) v |= (uint32_t)src[src_col(right, cs + b)] << (8 * b);
             if (rev) v = __byte_perm(v, 0, 0x0123);
-            *reinterpret_cast<uint32_t *>(Ring + (size_t)(gy & (RING - 1)) * q.SLOT + 4 * w) = v;
+            ring_store(Ring + (size_t)(gy & (RING - 1)) * q.SLOT, dst, !right, v);
         }
-        // loader descriptors: x = aligned byte offset of the word pair in the image row (or -1 - first virtual index for
-        // a clamped gather: first virtual index), y = funnel shift | right image << 8 | byte-reversed << 9 | gather << 10
+        // loader descriptors: x = aligned byte offset of the word pair in the image row (or, for a clamped gather, the
+        // first virtual index), y = funnel shift | right image << 8 | byte-reversed << 9 | gather << 10 | dst << 12
         for (int i = tid; i < nw; i += NT) {
-            int right, cs, rev;
-            ring_word_src(q, i, right, cs, rev);
+            int right, cs, rev, dst;
+            ring_item_src(q, i, right, cs, rev, dst);
             const int xa = x0 - H_ + cs;
             const bool inr = right ? (xa >= 0 && xa + 3 <= a.W - 1) : (xa >= -lofs && xa + 3 <= a.W - lofs - 1);
             const int gcol = right ? xa : xa + lofs;
-            Desc[i] = inr ? make_int2(gcol & ~3, ((gcol & 3) * 8) | (right << 8) | (rev << 9)) : make_int2(cs, (right << 8) | (rev << 9) | 0x400);
+            const int fl = (right << 8) | (rev << 9) | (dst << 12);
+            Desc[i] = inr ? make_int2(gcol & ~3, ((gcol & 3) * 8) | fl) : make_int2(cs, fl | 0x400);
         }
         for (int i = tid; i < PP / 4; i += NT) {
             reinterpret_cast<uint32_t *>(smem + q.ZOFF)[i] = 0u;
@@ -179,7 +193,7 @@ bm_sad3_kernel(Bm3Args a)
         const int hg = 2 * g + isB;
         const bool live = g < a.NG;                       // a trailing half warp may be idle (odd number of groups)
         // byte offsets of the thread's L and R streams inside a ring slot (both 4-byte aligned)
-        const int lbo = isB ? q.LM + (q.NCT - (g + 1) * G) : q.LF + g * G;
+        const int lbo = isB ? q.LM + 4 * (q.NCT - (g + 1) * G) : q.LF + 4 * g * G;      // 16-byte aligned
         const int rbo = isB ? q.RM + (q.RMX - (g + 1) * G - 6 - 8 * j) : q.RF + g * G + 8 * j;
         // R clamp (App. A.2, minD = 0): rbase(xc) = clip(xc, 0, W - nd); in virtual columns c = xc - x0 + h
         const int cmin = H_ - x0, cmax = (a.W - ND) - x0 + H_;
@@ -200,10 +214,15 @@ bm_sad3_kernel(Bm3Args a)
         for (int k = 0; k < H_; k++) V[k][0] = V[k][1] = V[k][2] = V[k][3] = 0u;
 
         auto load_words = [&](const uint8_t *slot, uint32_t (&lw)[NLW], uint32_t (&rw)[NRW]) {
-            const uint32_t *lp = reinterpret_cast<const uint32_t *>(slot + lbo);
             const uint32_t *rp = reinterpret_cast<const uint32_t *>(slot + rbo);
-#pragma unroll
-            for (int i = 0; i < NLW; i++) lw[i] = lp[i];
+            if (H_ >= 4) {
+                const uint4 t = *reinterpret_cast<const uint4 *>(slot + lbo);
+                lw[0] = t.x; lw[1] = t.y; lw[2] = t.z; lw[3] = t.w;
+            }
+            if (H_ % 4 == 2) {
+                const uint2 t = *reinterpret_cast<const uint2 *>(slot + lbo + 4 * (H_ - 2));
+                lw[H_ - 2] = t.x; lw[H_ - 1] = t.y;
+            }
 #pragma unroll
             for (int i = 0; i < NRW; i++) rw[i] = rp[i];
         };
@@ -217,7 +236,7 @@ bm_sad3_kernel(Bm3Args a)
         auto ad_col = [&](const uint32_t (&lw)[NLW], const uint32_t (&rw)[NRW], int k, bool border, uint32_t c0w, uint32_t c1w,
                           uint32_t &lo, uint32_t &hi) {
             const int w = k >> 2, sft = k & 3;
-            const uint32_t l4 = __byte_perm(lw[w], 0, sft == 0 ? 0x0000 : (sft == 1 ? 0x1111 : (sft == 2 ? 0x2222 : 0x3333)));
+            const uint32_t l4 = lw[k];
             uint32_t r0, r1;
             if (sft == 0) { r0 = rw[w]; r1 = rw[w + 1]; }
             else { r0 = __funnelshift_r(rw[w], rw[w + 1], 8 * sft); r1 = __funnelshift_r(rw[w + 1], rw[w + 2], 8 * sft); }
@@ -248,7 +267,7 @@ bm_sad3_kernel(Bm3Args a)
         // phase 2: A half of group g makes the pixels gG + k, B half the pixels gG + G - 1 - k; both need group g + 1
         const bool ph2 = live && g + 1 < a.NG;
         const int nxt = q.XOFF + ((g + 1) * G + (isB ? H_ : 0)) * PP + 16 * j; // next group's half of the same type
-        const int mst = q.MNOFF + (isB ? g * G + G - 1 : g * G) * MNP + 2 * j;
+        const int mst = q.MNOFF + (isB ? g * G + G - 1 : g * G) * MNP + 4 * j;
         const int mstep = isB ? -MNP : MNP;
         auto rev4 = [](uint4 v) {
             return make_uint4(__byte_perm(v.w, 0, 0x1032), __byte_perm(v.z, 0, 0x1032), __byte_perm(v.y, 0, 0x1032), __byte_perm(v.x, 0, 0x1032));
@@ -256,7 +275,7 @@ bm_sad3_kernel(Bm3Args a)
         auto emit_min = [&](uint8_t *buf, int k, uint32_t s0, uint32_t s1, uint32_t s2, uint32_t s3) {
             uint32_t m = __vminu2(__vimin3_u16x2(s0, s1, s2), s3);
             m = __vminu2(m, m >> 16);
-            *reinterpret_cast<uint16_t *>(buf + mst + k * mstep) = (uint16_t)m;
+            *reinterpret_cast<uint32_t *>(buf + mst + k * mstep) = m * 65536u + (uint32_t)j;      // (octet minimum << 16) | octet
         };
 
         // Even rows of the band add the byte deltas (in + 128 - out), odd rows subtract the mirrored deltas
@@ -351,8 +370,8 @@ bm_sad3_kernel(Bm3Args a)
         if (cw >= NCW - NLD) {
             // ---- loader warps: row y + h + 2 enters the ring while the consumers work on row y ---------------
             // (rows up to y + h + 1 are there; the slot it overwrites was last read by the producers in row y - 1)
-            constexpr int MAXW = 320 / (32 * NLD);              // ring words per lane (SLOT / 4 <= 320)
-            const int nw = q.SLOT / 4;
+            constexpr int MAXW = 320 / (32 * NLD);              // loader items per lane (NITEM <= 320)
+            const int nw = q.NITEM;
             const int ll = (cw - (NCW - NLD)) * 32 + lane;
             int off[MAXW];
             uint32_t meta[MAXW];                                // Desc.y | valid << 11
@@ -385,12 +404,13 @@ bm_sad3_kernel(Bm3Args a)
                 }
                 bar_sync(1 + (y & 1), NT);                      // the producers have finished row y (and its ring reads)
                 if (have_next) {
-                    uint8_t *slot = Ring + (size_t)(gy & (RING - 1)) * q.SLOT + 4 * ll;
+                    uint8_t *slot = Ring + (size_t)(gy & (RING - 1)) * q.SLOT;
 #pragma unroll
                     for (int s = 0; s < MAXW; s++) {
                         if (meta[s] & 0x800u) {
-                            const uint32_t v = !(meta[s] & 0x400u) ? __funnelshift_r(w0[s], w1[s], meta[s] & 31u) : w0[s];
-                            *reinterpret_cast<uint32_t *>(slot + 128 * NLD * s) = __byte_perm(v, 0, (meta[s] & 0x200u) ? 0x0123u : 0x3210u);
+                            uint32_t v = !(meta[s] & 0x400u) ? __funnelshift_r(w0[s], w1[s], meta[s] & 31u) : w0[s];
+                            v = __byte_perm(v, 0, (meta[s] & 0x200u) ? 0x0123u : 0x3210u);
+                            ring_store(slot, (int)(meta[s] >> 12), !(meta[s] & 0x100u), v);
                         }
                     }
                 }
@@ -455,19 +475,16 @@ bm_sad3_kernel(Bm3Args a)
                     sv[2] = __byte_perm(r[2], r[1], usel);
                     sv[3] = __byte_perm(r[3], r[0], usel);
                 };
-                // pass 1: the octet minima come from the producers (two per word); argmin octet by (min << 16 | octet) keys
+                // pass 1: (octet minimum << 16 | octet) keys made by the producers -> argmin octet (smallest octet on ties)
                 uint4 *s4 = reinterpret_cast<uint4 *>(const_cast<uint8_t *>(buf) + omn);
-                uint16_t *s16 = reinterpret_cast<uint16_t *>(s4);
-                uint32_t pm[NO_ / 2];
-#pragma unroll
-                for (int k = 0; k < NO_ / 8; k++) {
-                    const uint4 v = s4[k];
-                    pm[4 * k] = v.x; pm[4 * k + 1] = v.y; pm[4 * k + 2] = v.z; pm[4 * k + 3] = v.w;
-                }
+                uint32_t *s32 = reinterpret_cast<uint32_t *>(s4);
                 uint32_t best = 0xFFFFFFFFu;
 #pragma unroll
-                for (int k = 0; k < NO_ / 2; k++)
-                    best = __vimin3_u32(best, (pm[k] << 16) | (uint32_t)(2 * k), (pm[k] & 0xFFFF0000u) | (uint32_t)(2 * k + 1));
+                for (int k = 0; k < NO_ / 4; k++) {
+                    const uint4 v = s4[k];
+                    best = __vimin3_u32(best, v.x, v.y);
+                    best = __vimin3_u32(best, v.z, v.w);
+                }
                 const int BIASC = ((a.dbg & 8) ? (y - y0 + 1) : !((y - y0) & 1)) * (2 * H_ + 1) * 128;    // see the producers' row()
                 const int minsad = (int)(best >> 16) - BIASC, oc = (int)(best & 0xFFFFu);
                 // exact position inside the argmin octet (first minimum) via (value << 3 | index) keys
@@ -476,10 +493,10 @@ bm_sad3_kernel(Bm3Args a)
                     uint32_t sv[4];
                     sad4f(oc, sv);
                     const uint32_t s0 = sv[0], s1 = sv[1], s2 = sv[2], s3 = sv[3];
-                    uint32_t k = __vimin3_u32((s0 & 0xFFFFu) * 8u, (s0 >> 16) * 8u + 1u, (s1 & 0xFFFFu) * 8u + 2u);
-                    k = __vimin3_u32(k, (s1 >> 16) * 8u + 3u, (s2 & 0xFFFFu) * 8u + 4u);
-                    k = __vimin3_u32(k, (s2 >> 16) * 8u + 5u, (s3 & 0xFFFFu) * 8u + 6u);
-                    k = min(k, (s3 >> 16) * 8u + 7u);
+                    uint32_t k = __vimin3_u32(__umul24(s0 & 0xFFFFu, 8u), __umul24(s0 >> 16, 8u) + 1u, __umul24(s1 & 0xFFFFu, 8u) + 2u);
+                    k = __vimin3_u32(k, __umul24(s1 >> 16, 8u) + 3u, __umul24(s2 & 0xFFFFu, 8u) + 4u);
+                    k = __vimin3_u32(k, __umul24(s2 >> 16, 8u) + 5u, __umul24(s3 & 0xFFFFu, 8u) + 6u);
+                    k = min(k, __umul24(s3 >> 16, 8u) + 7u);
                     mind = 8 * oc + (int)(k & 7u);
                 }
                 const int dp = mind + 1 < ND ? mind + 1 : ND - 2, dn = mind > 0 ? mind - 1 : 1;
@@ -495,15 +512,16 @@ bm_sad3_kernel(Bm3Args a)
                     const int zlo = max(mind - 1, 0), zhi = min(mind + 1, ND - 1);
                     const int olo = zlo >> 3, ohi = zhi >> 3;
                     // octets that do not touch [mind-1, mind+1]: their minimum decides
-                    s16[olo] = 0xFFFFu;
-                    s16[ohi] = 0xFFFFu;
+                    s32[olo] = 0xFFFFFFFFu;
+                    s32[ohi] = 0xFFFFFFFFu;
                     uint32_t m2 = 0xFFFFFFFFu;
 #pragma unroll
-                    for (int k = 0; k < NO_ / 8; k++) {
+                    for (int k = 0; k < NO_ / 4; k++) {
                         const uint4 v = s4[k];
-                        m2 = __vminu2(m2, __vminu2(__vimin3_u16x2(v.x, v.y, v.z), v.w));
+                        m2 = __vimin3_u32(m2, v.x, v.y);
+                        m2 = __vimin3_u32(m2, v.z, v.w);
                     }
-                    ok = (int)min(m2 & 0xFFFFu, m2 >> 16) > thresh;
+                    ok = (int)(m2 >> 16) > thresh;
                     // the (at most two) touching octets: exact check with the neighbourhood masked out
                     for (int oo = olo; ok && oo <= ohi; oo++) {
                         uint32_t sv[4];
@@ -554,7 +572,7 @@ bool pick_tiling3(const BmGeom &g, int n, Tiling3 *t)
     if (!(g.nd == 128 || g.nd == 64)) return false;
     const int NO = g.nd / 8, G = 2 * h;
     int ngmax = (MAXT - NCW * 32) / 64 * 32 / NO;        // producer threads = whole warps of A halves + as many of B halves
-    while (ngmax > 2 && ((size_t)make_geo3(h, g.nd, ngmax).total > 200 * 1024 || make_geo3(h, g.nd, ngmax).SLOT / 4 > 320)) ngmax--;   // 320: loader warp, 10 words per lane
+    while (ngmax > 2 && ((size_t)make_geo3(h, g.nd, ngmax).total > 200 * 1024 || make_geo3(h, g.nd, ngmax).NITEM > 320)) ngmax--;   // 320: loader warp, 10 words per lane
     int twmax = std::min(ngmax * G - 2 * h, (NCW - NLD) * 32);
     if (twmax < 16) return false;
     t->nstripes = cdiv(g.W1, twmax);
