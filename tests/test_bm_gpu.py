@@ -10,15 +10,26 @@ from conftest import golden_names, load_golden
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["fast", "generic"])
+@pytest.fixture(params=["fast", "fast2", "generic"])
 def bm_kernel(request, monkeypatch):
-    """Runs a test once per SAD/WTA kernel: the fast path (bm_sad2.cu, where it applies) and the generic
-    kernel (bm_sad.cu, forced through RTDM_BM_KERNEL=1)."""
+    """Runs a test once per SAD/WTA kernel: the default selection (warp-specialised bm_sad3.cu where it applies,
+    else bm_sad2.cu, else generic), bm_sad2.cu kept where bm_sad3.cu would run (RTDM_BM_KERNEL=2), and the
+    generic kernel (bm_sad.cu, RTDM_BM_KERNEL=1)."""
     if request.param == "generic":
         monkeypatch.setenv("RTDM_BM_KERNEL", "1")
+    elif request.param == "fast2":
+        monkeypatch.setenv("RTDM_BM_KERNEL", "2")
     else:
         monkeypatch.delenv("RTDM_BM_KERNEL", raising=False)
     return request.param
+
+
+def _expected_kernel(bm_kernel, p):
+    if bm_kernel == "generic" or p["blockSize"] > 15 or p["minDisparity"] != 0:
+        return 1
+    if bm_kernel == "fast" and p["blockSize"] in (5, 9, 13) and p["numDisparities"] in (64, 128):
+        return 3
+    return 2
 
 
 def _mk(rt, p, W, H, **kw):
@@ -56,10 +67,7 @@ def test_bm_matches_cv2_golden(gpu, name, bm_kernel):
     assert got.dtype == np.int16 and got.shape == (H, W)
     assert np.array_equal(got, g["disp"]), f"{name} [{bm_kernel}]: {(got != g['disp']).sum()} pixels differ"
     assert m.last_launches() > 0
-    if bm_kernel == "generic":
-        assert m.last_kernel() == 1
-    elif p["blockSize"] <= 15 and p["minDisparity"] == 0:
-        assert m.last_kernel() == 2, "the fast path should cover blockSize 5..15 with minDisparity 0"
+    assert m.last_kernel() == _expected_kernel(bm_kernel, p), "kernel selection (generic / bm_sad2 / bm_sad3)"
 
 
 def test_bm_stages_match_oracle(gpu, orc, bm_kernel):
@@ -103,6 +111,38 @@ def test_bm_random_params_match_oracle(gpu, orc, bm_kernel):
         assert np.array_equal(ref, got), (p, W, H, int((ref != got).sum()))
         checked += 1
     assert checked >= 10
+
+
+@pytest.mark.parametrize("bs", [5, 9, 13])
+@pytest.mark.parametrize("nd", [64, 128])
+def test_bm_warp_specialised_kernel_matrix(gpu, orc, nd, bs):
+    """bm_sad3.cu over its whole domain (blockSize 5 / 9 / 13 x numDisparities 64 / 128): stripe borders (clamped
+    columns on both image sides), widths that are not a multiple of anything, odd heights, ROIs, texture and
+    uniqueness thresholds on and off, and every prefilter cap parity; raw WTA output and cost against the oracle's
+    core as well as the final map."""
+    from rtdm_b200 import synth
+    rng = np.random.default_rng(100 * nd + bs)
+    for i, (W, H) in enumerate([(nd + 40, 61), (333, 127), (640, 203), (nd + bs + 3, 40)]):
+        p = dict(preFilterCap=int(rng.integers(1, 32)), blockSize=bs, minDisparity=0,
+                 textureThreshold=int(rng.integers(0, 40)) * (i % 2), numDisparities=nd,
+                 uniquenessRatio=int(rng.integers(0, 25)) * ((i + 1) % 2 + i // 2), speckleWindowSize=100, speckleRange=32,
+                 disp12MaxDiff=int(rng.integers(-1, 3)))
+        if i == 2:
+            p["roi1"] = (17, 9, W - 40, H - 20)
+        L, R, _ = synth.stereo_pair(W, H, nd, 4000 + 10 * nd + bs + i)
+        m = _mk(gpu, p, W, H)
+        got = m.compute(L, R)
+        assert m.last_kernel() == 3
+        assert np.array_equal(got, orc.bm_compute(L, R, _orc_params(orc, p))), (p, W, H)
+        if p.get("roi1") is None:
+            Lp, Rp = orc.prefilter_xsobel(L, p["preFilterCap"]), orc.prefilter_xsobel(R, p["preFilterCap"])
+            h = bs // 2
+            rd, rc = orc.bm_core(Lp, Rp, h, H - h, p["preFilterCap"], bs, 0, nd, p["textureThreshold"], p["uniquenessRatio"])
+            gd, gc = m.debug_fetch(2, W, H), m.debug_fetch(3, W, H)
+            lofs = nd - 1
+            assert np.array_equal(gd[h:H - h, lofs:], rd[h:H - h, lofs:]), (p, W, H)
+            ok = rd[h:H - h, lofs:] >= 0
+            assert np.array_equal(gc[h:H - h, lofs:][ok], rc[h:H - h, lofs:][ok]), (p, W, H)
 
 
 def test_bm_degenerate_width(gpu, orc):
