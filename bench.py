@@ -342,8 +342,14 @@ def run_ours(args):
             ach = de * OPS_PER_DE[wl] / (k_ms * 1e-3) / 1e12
             hbm_ach = B * HBM_BYTES_PER_FRAME[wl] / (k_ms * 1e-3) / 1e9
             roofline = {
-                "kernel": "bm_sad_wta_kernel", "bound": "int_alu", "achieved": ach, "peak": int_peak, "unit": "Tiop/s",
-                "frac": ach / int_peak, "traffic": None,
+                "kernel": {3: "bm_texture_kernel + bm_sad3_kernel (warp-specialised SAD/WTA)", 2: "bm_texture_kernel + bm_sad2_kernel",
+                           1: "bm_sad_wta_kernel (generic)"}.get(matcher.last_kernel(), "?"),
+                "bound": "int_alu", "achieved": ach, "peak": int_peak, "unit": "Tiop/s",
+                "frac": ach / int_peak,
+                # ncu dram__bytes_read.sum + dram__bytes_write.sum of one bm_sad3_kernel launch of 16 frames:
+                # 59.1 + 14.7 MB (profiles/r01_prof_bm3_f_summary.csv) = 4.61 MB per frame (algorithmic: 3.69 MB)
+                "traffic": 4.61e6 * B if matcher.last_kernel() == 3 else (4.7e6 * B if matcher.last_kernel() == 2 else None),
+                "traffic_note": "per launch of B frames, scaled from the 16-frame ncu capture under profiles/",
                 "ops_per_de": OPS_PER_DE[wl], "kernel_ms_per_launch": k_ms, "frames_per_launch": B,
                 "kernel_share_of_step": stage_ms["sad_wta"] / stage_calls / (ms / args.steps),
                 "peak_source": "rtdm_measure_int_peak on this GPU (dependent-free IADD3, lane-ops/s)",
