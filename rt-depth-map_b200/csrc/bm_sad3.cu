@@ -35,9 +35,11 @@
 namespace rtdm {
 namespace {
 
-constexpr int NCW = 8;                  // consumer-side warps: NCW - NLD winner-take-all warps + NLD loader warps
-constexpr int NLD = 2;
-constexpr int MAXT = 768;               // threads per CTA (producers + consumers)
+// CTA shapes: WIDE = one CTA of <= 768 threads per SM (6 winner-take-all + 2 loader warps next to the producers),
+// PAIR = two CTAs of <= 384 threads per SM (3 + 1): narrower stripes (more halo), but two independent row pipelines
+// fill each other's barrier bubbles
+struct ShapeWide { static constexpr int NCW = 8, NLD = 2, MAXT = 768, MINB = 1, MAXW = 5; };    // MAXW: loader items per lane
+struct ShapePair { static constexpr int NCW = 4, NLD = 1, MAXT = 384, MINB = 2, MAXW = 6; };
 
 __host__ __device__ constexpr int ring_rows3(int h) { return 2 * h + 4 <= 16 ? 16 : 32; }
 
@@ -120,10 +122,11 @@ __device__ __forceinline__ void ring_store(uint8_t *slot, int dst, bool left, ui
         *reinterpret_cast<uint32_t *>(slot + dst) = v;
 }
 
-template <int H_, int NO_>
-__global__ void __launch_bounds__(MAXT, 1)
+template <int H_, int NO_, class SH>
+__global__ void __launch_bounds__(SH::MAXT, SH::MINB)
 bm_sad3_kernel(Bm3Args a)
 {
+    constexpr int NCW = SH::NCW, NLD = SH::NLD;
     constexpr int G = 2 * H_, RING = ring_rows3(H_);
     constexpr int NLW = H_, NRW = (H_ + 7 + 3) / 4;              // left: one expanded word per column
     constexpr int ND = NO_ * 8, PP = ND * 2 + 16;
@@ -370,7 +373,7 @@ bm_sad3_kernel(Bm3Args a)
         if (cw >= NCW - NLD) {
             // ---- loader warps: row y + h + 2 enters the ring while the consumers work on row y ---------------
             // (rows up to y + h + 1 are there; the slot it overwrites was last read by the producers in row y - 1)
-            constexpr int MAXW = 320 / (32 * NLD);              // loader items per lane (NITEM <= 320)
+            constexpr int MAXW = SH::MAXW;                      // loader items per lane (NITEM <= 32 * NLD * MAXW)
             const int nw = q.NITEM;
             const int ll = (cw - (NCW - NLD)) * 32 + lane;
             int off[MAXW];
@@ -563,7 +566,7 @@ bm_sad3_kernel(Bm3Args a)
     }
 }
 
-struct Tiling3 { int NG, TW, BH, nstripes, nbands, NT; size_t smem; };
+struct Tiling3 { int NG, TW, BH, nstripes, nbands, NT, pair; size_t smem; };
 
 bool pick_tiling3(const BmGeom &g, int n, Tiling3 *t)
 {
@@ -571,8 +574,16 @@ bool pick_tiling3(const BmGeom &g, int n, Tiling3 *t)
     if (g.minD != 0 || !(h == 2 || h == 4 || h == 6)) return false;
     if (!(g.nd == 128 || g.nd == 64)) return false;
     const int NO = g.nd / 8, G = 2 * h;
+    // RTDM_BM3_SHAPE = 0: one wide CTA per SM, 1: two narrower CTAs per SM
+    int pair = 0;
+    if (const char *e = getenv("RTDM_BM3_SHAPE")) pair = atoi(e) ? 1 : 0;
+    t->pair = pair;
+    const int NCW = pair ? ShapePair::NCW : ShapeWide::NCW, NLD = pair ? ShapePair::NLD : ShapeWide::NLD;
+    const int MAXT = pair ? ShapePair::MAXT : ShapeWide::MAXT;
+    const size_t smem_max = pair ? 110 * 1024 : 200 * 1024;
+    const int item_max = 32 * (pair ? ShapePair::MAXW : ShapeWide::MAXW);
     int ngmax = (MAXT - NCW * 32) / 64 * 32 / NO;        // producer threads = whole warps of A halves + as many of B halves
-    while (ngmax > 2 && ((size_t)make_geo3(h, g.nd, ngmax).total > 200 * 1024 || make_geo3(h, g.nd, ngmax).NITEM > 320)) ngmax--;   // 320: loader warp, 10 words per lane
+    while (ngmax > 2 && ((size_t)make_geo3(h, g.nd, ngmax).total > smem_max || make_geo3(h, g.nd, ngmax).NITEM > item_max * NLD)) ngmax--;   // 320: loader warp, 10 words per lane
     int twmax = std::min(ngmax * G - 2 * h, (NCW - NLD) * 32);
     if (twmax < 16) return false;
     t->nstripes = cdiv(g.W1, twmax);
@@ -582,11 +593,11 @@ bool pick_tiling3(const BmGeom &g, int n, Tiling3 *t)
     t->NT = (t->NG * NO + 31) / 32 * 64 + NCW * 32;
     const int rows = g.row1 - g.row0;
     int bhmax = 128;
-    while (bhmax > 32 && (long long)n * t->nstripes * cdiv(rows, bhmax) < 2 * 148) bhmax /= 2;
+    while (bhmax > 32 && (long long)n * t->nstripes * cdiv(rows, bhmax) < 2 * 148 * (pair ? 2 : 1)) bhmax /= 2;
     t->nbands = cdiv(rows, bhmax);
     t->BH = cdiv(rows, t->nbands);
     t->smem = (size_t)make_geo3(h, g.nd, t->NG).total;
-    return t->smem <= 200 * 1024;
+    return t->smem <= smem_max;
 }
 
 bool g_zmask_ready[64] = {false};
@@ -613,12 +624,17 @@ int upload_zmask()
     return 0;
 }
 
+template <int H_, int NO_, class SH>
+int launch3s(const Bm3Args &a, const Tiling3 &t, int n, cudaStream_t st)
+{
+    RTDM_CUDA(cudaFuncSetAttribute(bm_sad3_kernel<H_, NO_, SH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem));
+    bm_sad3_kernel<H_, NO_, SH><<<dim3(t.nstripes, t.nbands, n), t.NT, t.smem, st>>>(a);
+    return 0;
+}
 template <int H_, int NO_>
 int launch3(const Bm3Args &a, const Tiling3 &t, int n, cudaStream_t st)
 {
-    RTDM_CUDA(cudaFuncSetAttribute(bm_sad3_kernel<H_, NO_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem));
-    bm_sad3_kernel<H_, NO_><<<dim3(t.nstripes, t.nbands, n), t.NT, t.smem, st>>>(a);
-    return 0;
+    return t.pair ? launch3s<H_, NO_, ShapePair>(a, t, n, st) : launch3s<H_, NO_, ShapeWide>(a, t, n, st);
 }
 
 }  // namespace
