@@ -5,6 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.path.join(ROOT, "rt-depth-map_b200", "librtdm_b200.so")
 OUT = os.path.join(ROOT, "profiles")
 KERNELS = {                         # file tag -> substring of the mangled name
+    "bm_sad3_h6_d128": "bm_sad3_kernelILi6ELi16ENS0_9ShapeWide",
     "bm_sad2_h6": "bm_sad2_kernelILi6ELi1ELi192ELb0ELi2E",
     "sgbm_sweep_d128": "sgbm_sweep_kernelILi16ELb1E",
     "sgbm_cost_fused_bs5": "sgbm_cost_fused_kernelILi5E",
