@@ -239,6 +239,50 @@ int rtdm_rectify_run_device(rtdm_rectify *h, int n, const uint8_t *rgb, size_t s
                             uint8_t *out, size_t ostep, size_t oframe, void *cuda_stream);
 int rtdm_rectify_last_launches(const rtdm_rectify *h);
 
+/* ---- mask front-end (the step before the morphological filter) ------------ */
+/* Replaces, fused, estimator.cpp:38-43:
+ *     remap(img[0], img_rectified, map1, map2, INTER_LINEAR); img_rectified = img_rectified(roif);
+ *     cvtColor(img_rectified, img_rectified, COLOR_RGB2BGR); cvtColor(img_rectified, imgHSV, COLOR_BGR2HSV);
+ *     inRange(imgHSV, Scalar(iLowH, iLowS, iLowV), Scalar(iHighH, iHighS, iHighV), filter_in);
+ * maps / roi as for rtdm_rectify_create.  low / high: 3 ints each, (H, S, V), H in [0, 180).
+ * mask: CV_8UC1 roi_height x roi_width, 0 / 255 -- what SWMorphologicalFilter::run receives (it may be the filter
+ * plugin's own input buffer).  bgr: optional CV_8UC3 rectified crop in B,G,R order (the image the reference
+ * displays and labels), NULL to skip. */
+typedef struct rtdm_colormask rtdm_colormask;
+int rtdm_colormask_create(rtdm_colormask **out, int src_width, int src_height, const int16_t *map1, size_t map1_step,
+                          const uint16_t *map2, size_t map2_step, int roi_x, int roi_y, int roi_width, int roi_height,
+                          int max_batch, int device);
+void rtdm_colormask_destroy(rtdm_colormask *h);
+/* n HOST frames CV_8UC3 in R,G,B order (what the decoder delivers) -> n masks (and n BGR crops) */
+int rtdm_colormask_run(rtdm_colormask *h, int n, const uint8_t *rgb, size_t step, size_t frame, const int *low, const int *high,
+                       uint8_t *mask, size_t mstep, size_t mframe, uint8_t *bgr, size_t bstep, size_t bframe);
+/* DEVICE pointers, asynchronous on cuda_stream (e.g. mask = the device input of rtdm_morph_run_device) */
+int rtdm_colormask_run_device(rtdm_colormask *h, int n, const uint8_t *rgb, size_t step, size_t frame, const int *low, const int *high,
+                              uint8_t *mask, size_t mstep, size_t mframe, uint8_t *bgr, size_t bstep, size_t bframe, void *cuda_stream);
+int rtdm_colormask_last_launches(const rtdm_colormask *h);
+
+/* ---- mask back-end (the step after the morphological filter) -------------- */
+/* Replaces estimator.cpp:46-53 with Estimator::fill_bounding_rects_of_contours (:164-175) and
+ * Estimator::find_relevant_matching_region (:177-204):
+ *     findContours(filter_out, contours, hierarchy, CV_RETR_EXTERNAL, CV_CHAIN_APPROX_SIMPLE);
+ *     boundingRect per top-level contour, kept if area() >= min_obj_size, in OpenCV's contour order;
+ *     the rectangle spanning the kept boxes = what bm->setROI1() receives.
+ * mask: CV_8UC1, any non-zero value is foreground.  rects: up to max_regions x (x, y, width, height).
+ * *count = boxes kept; *ncontours = contours.size() (the reference skips the matcher when it is 0);
+ * roi = spanning rectangle; with no box kept it is the reference's own (1000000, 1000000, -2000000, -2000000).
+ * More than max_regions boxes: -EINVAL (nothing is truncated silently). */
+typedef struct rtdm_regions rtdm_regions;
+int rtdm_regions_create(rtdm_regions **out, int max_width, int max_height, int max_regions, int device);
+void rtdm_regions_destroy(rtdm_regions *h);
+/* HOST mask, synchronous */
+int rtdm_regions_run(rtdm_regions *h, const uint8_t *mask, size_t mstep, int width, int height, int min_obj_size,
+                     int *rects, int *count, int *ncontours, int *roi);
+/* DEVICE mask (e.g. what rtdm_morph_run_device just wrote); the few result ints come back to the host pointers
+ * before the call returns (they feed bm->setROI1 and rtdm_depth_run*'s rects, both host-side arguments) */
+int rtdm_regions_run_device(rtdm_regions *h, const uint8_t *mask, size_t mstep, int width, int height, int min_obj_size,
+                            int *rects, int *count, int *ncontours, int *roi, void *cuda_stream);
+int rtdm_regions_last_launches(const rtdm_regions *h);
+
 /* ---- measurement helper ------------------------------------------------------------------- */
 /* Measures the integer-ALU issue peak of the device with dependent-free packed-integer loops
  * (the roofline denominator SURVEY.md 8(d) asks for).  Results in 1e12 lane-ops/s. */

@@ -272,3 +272,90 @@ def rectify(rgb, map1, map2, roi):
     """gray -> remap -> crop to roi = (x, y, w, h): what the matcher receives as left_rect / right_rect."""
     x, y, w, h = roi
     return np.ascontiguousarray(remap_linear_fixed(rgb2gray(rgb), map1, map2)[y:y + h, x:x + w])
+
+
+# ---------------------------------------------------------------------------------------------------
+# Mask front-end and back-end (SURVEY.md 8(f).3): restatement of estimator.cpp:38-53 and :164-204
+# ---------------------------------------------------------------------------------------------------
+def _hsv_tables():
+    """OpenCV's RGB2HSV_b tables (imgproc color_hsv: hsv_shift = 12): sdiv[i] = cvRound((255 << 12) / i),
+    hdiv[i] = cvRound((180 << 12) / (6 i)); entry 0 is 0."""
+    sd = np.zeros(256, np.int64); hd = np.zeros(256, np.int64)
+    i = np.arange(1, 256, dtype=np.float64)
+    sd[1:] = np.rint((255 << 12) / i).astype(np.int64)
+    hd[1:] = np.rint((180 << 12) / (6.0 * i)).astype(np.int64)
+    return sd, hd
+
+
+def bgr2hsv(bgr):
+    """cvtColor(img, hsv, COLOR_BGR2HSV) on CV_8UC3 (estimator.cpp:42): H in [0, 180), integer algorithm
+    (v = max, diff = max - min, s = (diff * sdiv[v] + 2^11) >> 12, h from the sextant * hdiv[diff], + 180 if negative).
+    Pinned over all 2^24 colours against cv2 4.13.0 (tests/test_oracle_golden.py)."""
+    sd, hd = _hsv_tables()
+    a = np.asarray(bgr, np.uint8).astype(np.int64)
+    b, g, r = a[..., 0], a[..., 1], a[..., 2]
+    v = np.maximum(np.maximum(b, g), r); diff = v - np.minimum(np.minimum(b, g), r)
+    s = (diff * sd[v] + (1 << 11)) >> 12
+    h = np.where(v == r, g - b, np.where(v == g, b - r + 2 * diff, r - g + 4 * diff))
+    h = (h * hd[diff] + (1 << 11)) >> 12
+    h = h + np.where(h < 0, 180, 0)
+    return np.stack([h, s, v], -1).astype(np.uint8)
+
+
+def in_range(img, low, high):
+    """inRange(img, Scalar(low), Scalar(high), dst) on CV_8UC3 (estimator.cpp:43): 255 where every channel lies in
+    [low, high], else 0."""
+    a = np.asarray(img, np.uint8).astype(np.int64)
+    lo = np.asarray(low, np.int64).reshape(1, 1, 3); hi = np.asarray(high, np.int64).reshape(1, 1, 3)
+    return (((a >= lo) & (a <= hi)).all(-1) * 255).astype(np.uint8)
+
+
+def color_mask(rgb, map1, map2, roi, low, high):
+    """estimator.cpp:38-43: remap(img[0], INTER_LINEAR) on the 3-channel frame (same fixed-point weights per channel as
+    remap_linear_fixed), crop to roif, RGB -> BGR, BGR -> HSV, inRange -> filter_in.  Returns (mask, bgr_rectified)."""
+    x, y, w, h = roi
+    rgb = np.asarray(rgb, np.uint8)
+    rect = np.stack([remap_linear_fixed(rgb[..., c], map1, map2) for c in range(3)], -1)[y:y + h, x:x + w]
+    bgr = np.ascontiguousarray(rect[..., ::-1])
+    return in_range(bgr2hsv(bgr), low, high), bgr
+
+
+def contour_boxes(mask):
+    """findContours(mask, RETR_EXTERNAL, CHAIN_APPROX_SIMPLE) + boundingRect per top-level contour
+    (estimator.cpp:47, :164-175), as (x, y, w, h) in OpenCV's order.
+    A top-level contour is the outer border of an 8-connected component of non-zero pixels whose surrounding
+    background (4-connected, with a virtual zero frame around the image) is the frame's; components inside a hole of
+    another component are not listed.  OpenCV lists the contours in reverse order of discovery, discovery = raster
+    order of the component's first pixel.  Pinned against cv2 4.13.0 on random masks (tests/test_oracle_golden.py)."""
+    from scipy import ndimage
+    m = np.asarray(mask) != 0
+    H, W = m.shape
+    pad = np.zeros((H + 2, W + 2), bool); pad[1:-1, 1:-1] = m
+    fg, nf = ndimage.label(pad, structure=np.ones((3, 3), int))
+    bg, _ = ndimage.label(~pad, structure=[[0, 1, 0], [1, 1, 1], [0, 1, 0]])
+    frame = bg == bg[0, 0]
+    near = np.zeros_like(pad)
+    near[1:, :] |= frame[:-1, :]; near[:-1, :] |= frame[1:, :]; near[:, 1:] |= frame[:, :-1]; near[:, :-1] |= frame[:, 1:]
+    ext = np.zeros(nf + 1, bool)
+    ext[np.unique(fg[near & pad])] = True
+    out = []
+    for sl, lab in zip(ndimage.find_objects(fg), range(1, nf + 1)):
+        if not ext[lab]:
+            continue
+        ys, xs = sl
+        first = int(np.flatnonzero((fg[ys, xs] == lab).ravel())[0])
+        fy, fx = divmod(first, xs.stop - xs.start)
+        out.append((((ys.start - 1 + fy) * W + xs.start - 1 + fx), (xs.start - 1, ys.start - 1, xs.stop - xs.start, ys.stop - ys.start)))
+    out.sort(key=lambda t: -t[0])
+    return [b for _, b in out]
+
+
+def object_regions(mask, min_obj_size):
+    """fill_bounding_rects_of_contours + find_relevant_matching_region (estimator.cpp:164-204): the bounding boxes
+    with area (w * h) >= min_obj_size, and the rectangle spanning them all (what bm->setROI1 receives).  With no
+    box left the reference's roi is (1000000, 1000000, -2000000, -2000000); kept."""
+    bounds = [b for b in contour_boxes(mask) if b[2] * b[3] >= min_obj_size]
+    min_x = min_y = 1000000; max_x = max_y = -1000000
+    for x, y, w, h in bounds:
+        min_x = min(min_x, x); min_y = min(min_y, y); max_x = max(max_x, x + w); max_y = max(max_y, y + h)
+    return bounds, (min_x, min_y, max_x - min_x, max_y - min_y)

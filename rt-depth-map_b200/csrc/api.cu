@@ -1120,6 +1120,218 @@ extern "C" int rtdm_rectify_run(rtdm_rectify *h, int n, const uint8_t *rgb, size
 
 extern "C" int rtdm_rectify_last_launches(const rtdm_rectify *h) { return h ? h->launches : 0; }
 
+// ===================================================================================================
+// mask front-end (estimator.cpp:38-43) and back-end (estimator.cpp:46-53, :164-204)
+// ===================================================================================================
+struct rtdm_colormask {
+    int W, H, rx, ry, rw, rh, maxB, dev;
+    cudaStream_t st;
+    int16_t *map1; uint16_t *map2;          // ROI part of the maps, tightly packed
+    uint8_t *dIn, *dMask, *dBgr;            // staging for the host entry point
+    int launches;
+};
+
+extern "C" void rtdm_colormask_destroy(rtdm_colormask *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->dev);
+    cudaFree(h->map1); cudaFree(h->map2); cudaFree(h->dIn); cudaFree(h->dMask); cudaFree(h->dBgr);
+    if (h->st) cudaStreamDestroy(h->st);
+    delete h;
+}
+
+extern "C" int rtdm_colormask_create(rtdm_colormask **out, int src_width, int src_height, const int16_t *map1, size_t map1_step,
+                                     const uint16_t *map2, size_t map2_step, int roi_x, int roi_y, int roi_width, int roi_height,
+                                     int max_batch, int device)
+{
+    if (!out || !map1 || !map2) { set_error("colormask_create: null argument"); return -RTDM_EINVAL; }
+    *out = nullptr;
+    if (src_width < 1 || src_height < 1 || max_batch < 1 || roi_x < 0 || roi_y < 0 || roi_width < 1 || roi_height < 1 ||
+        roi_x + roi_width > src_width || roi_y + roi_height > src_height) {
+        set_error("colormask_create: bad geometry (the ROI must lie inside the image)");
+        return -RTDM_EINVAL;
+    }
+    int rc = check_device(device);
+    if (rc) return rc;
+    RTDM_CUDA(cudaSetDevice(device));
+    rtdm_colormask *h = new (std::nothrow) rtdm_colormask();
+    if (!h) return -RTDM_ENOMEM;
+    memset(h, 0, sizeof *h);
+    h->W = src_width; h->H = src_height; h->rx = roi_x; h->ry = roi_y; h->rw = roi_width; h->rh = roi_height;
+    h->maxB = max_batch; h->dev = device;
+    const size_t RN = (size_t)roi_width * roi_height;
+    rc = cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) == cudaSuccess ? 0 : -RTDM_EIO;
+    if (!rc) rc = dev_alloc(&h->map1, 2 * RN);
+    if (!rc) rc = dev_alloc(&h->map2, RN);
+    if (!rc) rc = dev_alloc(&h->dIn, (size_t)src_width * src_height * 3 * max_batch);
+    if (!rc) rc = dev_alloc(&h->dMask, RN * max_batch);
+    if (!rc) rc = dev_alloc(&h->dBgr, RN * 3 * max_batch);
+    if (!rc) {
+        cudaError_t e = cudaMemcpy2D(h->map1, (size_t)roi_width * 4, (const uint8_t *)map1 + (size_t)roi_y * map1_step + (size_t)roi_x * 4,
+                                     map1_step, (size_t)roi_width * 4, roi_height, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess)
+            e = cudaMemcpy2D(h->map2, (size_t)roi_width * 2, (const uint8_t *)map2 + (size_t)roi_y * map2_step + (size_t)roi_x * 2,
+                             map2_step, (size_t)roi_width * 2, roi_height, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) rc = cuda_fail(e, "colormask maps upload", __FILE__, __LINE__);
+    }
+    if (rc) { rtdm_colormask_destroy(h); return rc; }
+    *out = h;
+    return 0;
+}
+
+static int colormask_check_range(const int *low, const int *high)
+{
+    if (!low || !high) { set_error("colormask: null range"); return -RTDM_EINVAL; }
+    return 0;
+}
+
+extern "C" int rtdm_colormask_run_device(rtdm_colormask *h, int n, const uint8_t *rgb, size_t step, size_t frame, const int *low,
+                                         const int *high, uint8_t *mask, size_t mstep, size_t mframe, uint8_t *bgr, size_t bstep,
+                                         size_t bframe, void *cuda_stream)
+{
+    if (!h || !rgb || !mask) { set_error("colormask: null argument"); return -RTDM_EINVAL; }
+    int rc = colormask_check_range(low, high);
+    if (rc) return rc;
+    if (n < 1 || step < (size_t)h->W * 3 || mstep < (size_t)h->rw || (bgr && bstep < (size_t)h->rw * 3)) {
+        set_error("colormask: bad batch or steps");
+        return -RTDM_EINVAL;
+    }
+    RTDM_CUDA(cudaSetDevice(h->dev));
+    h->launches = 0;
+    return launch_colormask(n, rgb, step, frame, h->W, h->H, h->map1, h->map2, h->rw, h->rh, low, high, mask, mstep, mframe,
+                            bgr, bstep, bframe, static_cast<cudaStream_t>(cuda_stream), &h->launches);
+}
+
+extern "C" int rtdm_colormask_run(rtdm_colormask *h, int n, const uint8_t *rgb, size_t step, size_t frame, const int *low, const int *high,
+                                  uint8_t *mask, size_t mstep, size_t mframe, uint8_t *bgr, size_t bstep, size_t bframe)
+{
+    if (!h || !rgb || !mask) { set_error("colormask: null argument"); return -RTDM_EINVAL; }
+    int rc = colormask_check_range(low, high);
+    if (rc) return rc;
+    if (n < 1 || n > h->maxB || step < (size_t)h->W * 3 || mstep < (size_t)h->rw || (bgr && bstep < (size_t)h->rw * 3)) {
+        set_error("colormask: batch exceeds what the handle was created for, or bad steps");
+        return -RTDM_EINVAL;
+    }
+    RTDM_CUDA(cudaSetDevice(h->dev));
+    const size_t row = (size_t)h->W * 3, fin = row * h->H, fm = (size_t)h->rw * h->rh;
+    for (int k = 0; k < n; k++)
+        RTDM_CUDA(cudaMemcpy2DAsync(h->dIn + k * fin, row, rgb + k * frame, step, row, h->H, cudaMemcpyHostToDevice, h->st));
+    h->launches = 0;
+    rc = launch_colormask(n, h->dIn, row, fin, h->W, h->H, h->map1, h->map2, h->rw, h->rh, low, high, h->dMask, h->rw, fm,
+                          bgr ? h->dBgr : nullptr, (size_t)h->rw * 3, fm * 3, h->st, &h->launches);
+    if (rc) return rc;
+    for (int k = 0; k < n; k++) {
+        RTDM_CUDA(cudaMemcpy2DAsync(mask + k * mframe, mstep, h->dMask + k * fm, h->rw, h->rw, h->rh, cudaMemcpyDeviceToHost, h->st));
+        if (bgr)
+            RTDM_CUDA(cudaMemcpy2DAsync(bgr + k * bframe, bstep, h->dBgr + k * fm * 3, (size_t)h->rw * 3, (size_t)h->rw * 3, h->rh,
+                                        cudaMemcpyDeviceToHost, h->st));
+    }
+    RTDM_CUDA(cudaStreamSynchronize(h->st));
+    return 0;
+}
+
+extern "C" int rtdm_colormask_last_launches(const rtdm_colormask *h) { return h ? h->launches : 0; }
+
+struct rtdm_regions {
+    int maxW, maxH, maxR, dev;
+    cudaStream_t st;
+    uint8_t *dMask;                           // staging for the host entry point
+    int *labels, *ext, *keys, *out;
+    int4 *bb, *boxes;
+    int *hOut;                                // pinned result: 6 + 4 * maxR ints
+    int launches;
+};
+
+extern "C" void rtdm_regions_destroy(rtdm_regions *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->dev);
+    cudaFree(h->dMask); cudaFree(h->labels); cudaFree(h->ext); cudaFree(h->keys); cudaFree(h->out);
+    cudaFree(h->bb); cudaFree(h->boxes);
+    if (h->hOut) cudaFreeHost(h->hOut);
+    if (h->st) cudaStreamDestroy(h->st);
+    delete h;
+}
+
+extern "C" int rtdm_regions_create(rtdm_regions **out, int max_width, int max_height, int max_regions, int device)
+{
+    if (!out) { set_error("regions_create: null argument"); return -RTDM_EINVAL; }
+    *out = nullptr;
+    if (max_width < 1 || max_height < 1 || max_regions < 1 || (long long)max_width * max_height > (1LL << 30)) {
+        set_error("regions_create: bad geometry");
+        return -RTDM_EINVAL;
+    }
+    int rc = check_device(device);
+    if (rc) return rc;
+    RTDM_CUDA(cudaSetDevice(device));
+    rtdm_regions *h = new (std::nothrow) rtdm_regions();
+    if (!h) return -RTDM_ENOMEM;
+    memset(h, 0, sizeof *h);
+    h->maxW = max_width; h->maxH = max_height; h->maxR = max_regions; h->dev = device;
+    const size_t N = (size_t)max_width * max_height;
+    rc = cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) == cudaSuccess ? 0 : -RTDM_EIO;
+    if (!rc) rc = dev_alloc(&h->dMask, N);
+    if (!rc) rc = dev_alloc(&h->labels, N + 1);
+    if (!rc) rc = dev_alloc(&h->ext, N);
+    if (!rc) rc = dev_alloc(&h->bb, N);
+    if (!rc) rc = dev_alloc(&h->keys, (size_t)max_regions);
+    if (!rc) rc = dev_alloc(&h->boxes, (size_t)max_regions);
+    if (!rc) rc = dev_alloc(&h->out, 6 + 4 * (size_t)max_regions);
+    if (!rc && cudaMallocHost(&h->hOut, (6 + 4 * (size_t)max_regions) * sizeof(int)) != cudaSuccess) rc = -RTDM_ENOMEM;
+    if (rc) { rtdm_regions_destroy(h); return rc; }
+    *out = h;
+    return 0;
+}
+
+static int regions_finish(rtdm_regions *h, cudaStream_t st, int *rects, int *count, int *ncontours, int *roi)
+{
+    RTDM_CUDA(cudaMemcpyAsync(h->hOut, h->out, (6 + 4 * (size_t)h->maxR) * sizeof(int), cudaMemcpyDeviceToHost, st));
+    RTDM_CUDA(cudaStreamSynchronize(st));
+    const int n = h->hOut[0];
+    if (n > h->maxR) { set_error("regions: more boxes than max_regions"); return -RTDM_EINVAL; }
+    if (count) *count = n;
+    if (ncontours) *ncontours = h->hOut[1];
+    if (roi) { roi[0] = h->hOut[2]; roi[1] = h->hOut[3]; roi[2] = h->hOut[4] - h->hOut[2]; roi[3] = h->hOut[5] - h->hOut[3]; }
+    if (rects) memcpy(rects, h->hOut + 6, (size_t)n * 4 * sizeof(int));
+    return 0;
+}
+
+extern "C" int rtdm_regions_run_device(rtdm_regions *h, const uint8_t *mask, size_t mstep, int width, int height, int min_obj_size,
+                                       int *rects, int *count, int *ncontours, int *roi, void *cuda_stream)
+{
+    if (!h || !mask) { set_error("regions: null argument"); return -RTDM_EINVAL; }
+    if (width < 1 || height < 1 || width > h->maxW || height > h->maxH || mstep < (size_t)width) {
+        set_error("regions: size exceeds what the handle was created for, or bad step");
+        return -RTDM_EINVAL;
+    }
+    RTDM_CUDA(cudaSetDevice(h->dev));
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    h->launches = 0;
+    int rc = launch_regions(mask, mstep, width, height, min_obj_size, h->maxR, h->labels, h->bb, h->ext, h->keys, h->boxes,
+                            h->out, st, &h->launches);
+    if (rc) return rc;
+    return regions_finish(h, st, rects, count, ncontours, roi);
+}
+
+extern "C" int rtdm_regions_run(rtdm_regions *h, const uint8_t *mask, size_t mstep, int width, int height, int min_obj_size,
+                                int *rects, int *count, int *ncontours, int *roi)
+{
+    if (!h || !mask) { set_error("regions: null argument"); return -RTDM_EINVAL; }
+    if (width < 1 || height < 1 || width > h->maxW || height > h->maxH || mstep < (size_t)width) {
+        set_error("regions: size exceeds what the handle was created for, or bad step");
+        return -RTDM_EINVAL;
+    }
+    RTDM_CUDA(cudaSetDevice(h->dev));
+    RTDM_CUDA(cudaMemcpy2DAsync(h->dMask, width, mask, mstep, width, height, cudaMemcpyHostToDevice, h->st));
+    h->launches = 0;
+    int rc = launch_regions(h->dMask, width, width, height, min_obj_size, h->maxR, h->labels, h->bb, h->ext, h->keys, h->boxes,
+                            h->out, h->st, &h->launches);
+    if (rc) return rc;
+    return regions_finish(h, h->st, rects, count, ncontours, roi);
+}
+
+extern "C" int rtdm_regions_last_launches(const rtdm_regions *h) { return h ? h->launches : 0; }
+
 extern "C" int rtdm_measure_int_peak(int device, double *tiops_iadd3, double *tiops_vimnmx,
                                      double *tiops_vabsdiff4, double *sm_mhz_est)
 {

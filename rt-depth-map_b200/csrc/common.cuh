@@ -108,6 +108,13 @@ int launch_depth(const int16_t *disp, size_t dpitch, int W, int H, const double 
 int launch_rectify(int n, const uint8_t *rgb, size_t pitch, size_t frame, int W, int H, const int16_t *map1, const uint16_t *map2,
                    int rw, int rh, uint8_t *out, size_t opitch, size_t oframe, cudaStream_t st, int *launches);
 
+// ---- mask front-end / back-end (mask.cu): colour threshold before the filter, object boxes after it ---------------
+int launch_colormask(int n, const uint8_t *rgb, size_t pitch, size_t frame, int W, int H, const int16_t *map1, const uint16_t *map2,
+                     int rw, int rh, const int *lo, const int *hi, uint8_t *mask, size_t mpitch, size_t mframe,
+                     uint8_t *bgr, size_t bpitch, size_t bframe, cudaStream_t st, int *launches);
+int launch_regions(const uint8_t *mask, size_t pitch, int W, int H, int minSize, int maxR,
+                   int *labels, void *bb, int *ext, int *keys, void *boxes, int *out, cudaStream_t st, int *launches);
+
 // ---- int peak microbenchmark (intpeak.cu) -------------------------------------------------------
 int measure_int_peak(int device, double *iadd3, double *vimnmx, double *vabsdiff4, double *mhz);
 

@@ -192,6 +192,67 @@ private:
     cv::Rect roi_;
 };
 
+// The step before the morphological filter, fused on the GPU.  Replaces in Estimator::run
+//     remap(img[0], img_rectified, remap_left1, remap_left2, INTER_LINEAR); img_rectified = img_rectified(roif);   estimator.cpp:38-39
+//     cvtColor(img_rectified, img_rectified, COLOR_RGB2BGR); cvtColor(img_rectified, imgHSV, COLOR_BGR2HSV);      :40,:42
+//     inRange(imgHSV, Scalar(iLowH, iLowS, iLowV), Scalar(iHighH, iHighS, iHighV), filter_in);                    :43
+// by   colormask.run(img[0], low, high, filter_in, &img_rectified);
+// filter_in may wrap the filter plugin's own input buffer, as in the reference (estimator.cpp:141).
+class CUDAColorMask {
+public:
+    CUDAColorMask(const cv::Mat &map1, const cv::Mat &map2, const cv::Rect &roif, int device = 0) : roi_(roif)
+    {
+        int rc = rtdm_colormask_create(&h_, map2.cols, map2.rows, map1.ptr<short>(), map1.step, map2.ptr<unsigned short>(), map2.step,
+                                       roif.x, roif.y, roif.width, roif.height, 1, device);
+        if (rc) rtdm_detail::fail("CUDAColorMask", rc);
+    }
+    ~CUDAColorMask() { rtdm_colormask_destroy(h_); }
+    // rgb: CV_8UC3 frame in R,G,B order; low / high: (H, S, V); filter_in: CV_8UC1 roif.height x roif.width (created if
+    // it has another size); bgr_rectified: optional CV_8UC3 buffer of roif.height rows with step >= 3 * roif.width
+    int run(const cv::Mat &rgb, const int low[3], const int high[3], cv::Mat &filter_in, cv::Mat *bgr_rectified = nullptr)
+    {
+        if (filter_in.rows != roi_.height || filter_in.cols != roi_.width) filter_in.create(roi_.height, roi_.width, CV_8UC1);
+        int rc = rtdm_colormask_run(h_, 1, rgb.ptr<unsigned char>(), rgb.step, 0, low, high, filter_in.ptr<unsigned char>(), filter_in.step, 0,
+                                    bgr_rectified ? bgr_rectified->ptr<unsigned char>() : nullptr, bgr_rectified ? bgr_rectified->step : 0, 0);
+        if (rc) { std::fprintf(stderr, "CUDAColorMask::run: %s\n", rtdm_last_error()); return -1; }
+        return 0;
+    }
+private:
+    rtdm_colormask *h_ = nullptr;
+    cv::Rect roi_;
+};
+
+// The step after the morphological filter on the GPU.  Replaces in Estimator::run
+//     filter_out.copyTo(contInput); findContours(contInput, contours, hierarchy, CV_RETR_EXTERNAL, CV_CHAIN_APPROX_SIMPLE);   estimator.cpp:46-47
+//     fill_bounding_rects_of_contours(contours, hierarchy, obj_boundings, minObjSize);                                        :51 (:164-175)
+//     find_relevant_matching_region(obj_boundings, matching_roi);                                                             :52 (:177-204)
+// by   if (regions.run(filter_out, minObjSize, obj_boundings, matching_roi) > 0) { bm->setROI1(matching_roi); ... }
+// run returns contours.size() (the reference skips the matcher when it is 0), or -1 on error.
+class CUDAObjectRegions {
+public:
+    CUDAObjectRegions(int max_width, int max_height, int max_regions = 256, int device = 0) : max_(max_regions), buf_(4 * (size_t)max_regions)
+    {
+        int rc = rtdm_regions_create(&h_, max_width, max_height, max_regions, device);
+        if (rc) rtdm_detail::fail("CUDAObjectRegions", rc);
+    }
+    ~CUDAObjectRegions() { rtdm_regions_destroy(h_); }
+    int run(const cv::Mat &filter_out, int min_obj_size, std::vector<cv::Rect> &obj_boundings, cv::Rect &matching_roi)
+    {
+        int n = 0, nc = 0, roi[4] = {0, 0, 0, 0};
+        int rc = rtdm_regions_run(h_, filter_out.ptr<unsigned char>(), filter_out.step, filter_out.cols, filter_out.rows, min_obj_size,
+                                  buf_.data(), &n, &nc, roi);
+        if (rc) { std::fprintf(stderr, "CUDAObjectRegions::run: %s\n", rtdm_last_error()); return -1; }
+        obj_boundings.clear();
+        for (int i = 0; i < n; i++) obj_boundings.push_back(cv::Rect(buf_[4 * i], buf_[4 * i + 1], buf_[4 * i + 2], buf_[4 * i + 3]));
+        matching_roi = cv::Rect(roi[0], roi[1], roi[2], roi[3]);
+        return nc;
+    }
+private:
+    rtdm_regions *h_ = nullptr;
+    int max_;
+    std::vector<int> buf_;
+};
+
 // The step after the matcher, fused on the GPU.  Replaces in Estimator::run
 //     left_disp /= 16.;                                              estimator.cpp:75
 //     reprojectImageTo3D(left_disp, xyz, Q, true, CV_32F);           estimator.cpp:76

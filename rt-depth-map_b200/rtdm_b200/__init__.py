@@ -93,6 +93,16 @@ SIGNATURES = {
     "rtdm_rectify_run": (_i, [_vp, _i, _vp, _sz, _sz, _vp, _sz, _sz]),
     "rtdm_rectify_run_device": (_i, [_vp, _i, _vp, _sz, _sz, _vp, _sz, _sz, _vp]),
     "rtdm_rectify_last_launches": (_i, [_vp]),
+    "rtdm_colormask_create": (_i, [C.POINTER(_vp), _i, _i, _vp, _sz, _vp, _sz, _i, _i, _i, _i, _i, _i]),
+    "rtdm_colormask_destroy": (None, [_vp]),
+    "rtdm_colormask_run": (_i, [_vp, _i, _vp, _sz, _sz, _vp, _vp, _vp, _sz, _sz, _vp, _sz, _sz]),
+    "rtdm_colormask_run_device": (_i, [_vp, _i, _vp, _sz, _sz, _vp, _vp, _vp, _sz, _sz, _vp, _sz, _sz, _vp]),
+    "rtdm_colormask_last_launches": (_i, [_vp]),
+    "rtdm_regions_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i]),
+    "rtdm_regions_destroy": (None, [_vp]),
+    "rtdm_regions_run": (_i, [_vp, _vp, _sz, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "rtdm_regions_run_device": (_i, [_vp, _vp, _sz, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "rtdm_regions_last_launches": (_i, [_vp]),
     "rtdm_depth_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i]),
     "rtdm_depth_destroy": (None, [_vp]),
     "rtdm_depth_run": (_i, [_vp, _vp, _sz, _i, _i, _vp, _vp, _sz, _i, _vp, _vp, _vp, _vp, _sz]),
@@ -534,3 +544,104 @@ def measure_int_peak(device=0):
     _check(lib().rtdm_measure_int_peak(device, C.byref(a), C.byref(b), C.byref(c), C.byref(m)))
     return {"iadd3_tiops": a.value, "vimnmx_lop3_tiops": b.value, "vabsdiff4_iadd_tiops": c.value,
             "sm_mhz_if_64_lanes": m.value}
+
+
+class CUDAColorMask:
+    """The step before the morphological filter (estimator.cpp:38-43), fused on the GPU:
+    remap(RGB frame, INTER_LINEAR) -> crop to `roi` -> RGB2BGR -> BGR2HSV -> inRange(low, high) -> filter_in.
+    `run` takes (H, W, 3) or (N, H, W, 3) uint8 RGB host arrays; returns the 0/255 mask(s), and the rectified BGR
+    crop(s) the reference displays when `want_bgr`."""
+
+    def __init__(self, map1, map2, roi, *, max_batch=1, device=0):
+        self._l = lib()
+        self._h = _vp()
+        self._vp = _vp
+        m1 = np.ascontiguousarray(map1, np.int16); m2 = np.ascontiguousarray(map2, np.uint16)
+        H, W = m2.shape
+        if m1.shape != (H, W, 2):
+            raise RtdmError(-EINVAL, "CUDAColorMask: map1 must be (H, W, 2) int16 and map2 (H, W) uint16")
+        self.W, self.H, self.roi, self.max_batch = W, H, tuple(int(v) for v in roi), max_batch
+        _check(self._l.rtdm_colormask_create(C.byref(self._h), W, H, m1.ctypes.data, W * 4, m2.ctypes.data, W * 2,
+                                             *self.roi, max_batch, device))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) and self._vp is not None:
+                self._l.rtdm_colormask_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def run(self, rgb, low, high, want_bgr=False):
+        a = np.ascontiguousarray(rgb, np.uint8)
+        single = a.ndim == 3
+        if single:
+            a = a[None]
+        N, H, W, _ = a.shape
+        rw, rh = self.roi[2], self.roi[3]
+        lo = np.ascontiguousarray(low, np.int32); hi = np.ascontiguousarray(high, np.int32)
+        if lo.shape != (3,) or hi.shape != (3,):
+            raise RtdmError(-EINVAL, "CUDAColorMask: low and high are (H, S, V) triples")
+        mask = np.empty((N, rh, rw), np.uint8)
+        bgr = np.empty((N, rh, rw, 3), np.uint8) if want_bgr else None
+        _check(self._l.rtdm_colormask_run(self._h, N, a.ctypes.data, W * 3, W * H * 3, lo.ctypes.data, hi.ctypes.data,
+                                          mask.ctypes.data, rw, rw * rh, bgr.ctypes.data if want_bgr else None, rw * 3, rw * rh * 3))
+        if want_bgr:
+            return (mask[0], bgr[0]) if single else (mask, bgr)
+        return mask[0] if single else mask
+
+    def run_device(self, n, rgb_ptr, step, frame, low, high, mask_ptr, mstep, mframe, bgr_ptr=None, bstep=0, bframe=0, stream=0):
+        lo = np.ascontiguousarray(low, np.int32); hi = np.ascontiguousarray(high, np.int32)
+        _check(self._l.rtdm_colormask_run_device(self._h, n, rgb_ptr, step, frame, lo.ctypes.data, hi.ctypes.data,
+                                                 mask_ptr, mstep, mframe, bgr_ptr, bstep, bframe, stream))
+
+    def last_launches(self) -> int:
+        return self._l.rtdm_colormask_last_launches(self._h)
+
+
+class CUDAObjectRegions:
+    """The step after the morphological filter (estimator.cpp:46-53, :164-204) on the GPU: bounding boxes of the
+    top-level contours of the mask (findContours RETR_EXTERNAL + boundingRect, in OpenCV's order) with area >=
+    `min_obj_size`, and the rectangle spanning them (what bm->setROI1 receives).
+    `run` returns (rects (n, 4) int32 as x, y, w, h; roi (x, y, w, h); ncontours)."""
+
+    def __init__(self, max_width, max_height, max_regions=256, *, device=0):
+        self._l = lib()
+        self._h = _vp()
+        self._vp = _vp
+        self.max_regions = max_regions
+        _check(self._l.rtdm_regions_create(C.byref(self._h), max_width, max_height, max_regions, device))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) and self._vp is not None:
+                self._l.rtdm_regions_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def _finish(self, rects, cnt, nc, roi):
+        return rects[:cnt.value].copy(), tuple(int(v) for v in roi), int(nc.value)
+
+    def run(self, mask, min_obj_size):
+        m = np.asarray(mask)
+        if m.dtype != np.uint8 or m.ndim != 2:
+            raise RtdmError(-EINVAL, "CUDAObjectRegions: the mask must be a 2-D uint8 array")
+        if m.strides[1] != 1:
+            m = np.ascontiguousarray(m)
+        H, W = m.shape
+        rects = np.zeros((self.max_regions, 4), np.int32); roi = np.zeros(4, np.int32)
+        cnt, nc = C.c_int(0), C.c_int(0)
+        _check(self._l.rtdm_regions_run(self._h, m.ctypes.data, m.strides[0], W, H, int(min_obj_size), rects.ctypes.data,
+                                        C.addressof(cnt), C.addressof(nc), roi.ctypes.data))
+        return self._finish(rects, cnt, nc, roi)
+
+    def run_device(self, mask_ptr, mstep, width, height, min_obj_size, stream=0):
+        rects = np.zeros((self.max_regions, 4), np.int32); roi = np.zeros(4, np.int32)
+        cnt, nc = C.c_int(0), C.c_int(0)
+        _check(self._l.rtdm_regions_run_device(self._h, mask_ptr, mstep, width, height, int(min_obj_size), rects.ctypes.data,
+                                               C.addressof(cnt), C.addressof(nc), roi.ctypes.data, stream))
+        return self._finish(rects, cnt, nc, roi)
+
+    def last_launches(self) -> int:
+        return self._l.rtdm_regions_last_launches(self._h)

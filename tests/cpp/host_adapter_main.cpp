@@ -4,6 +4,7 @@
 //   host_adapter_main sgbm W H nd bs left right out mode
 //   host_adapter_main morph W H in out
 //   host_adapter_main rectify W H rgb map1 map2 out
+//   host_adapter_main mask W H rgb map1 map2 mask_out boxes_out
 //   host_adapter_main depth W H disp mask out x y w h   (Q is the fixed matrix of tests/test_host_adapters.py)
 #include <cstdio>
 #include <cstdlib>
@@ -97,6 +98,33 @@ int main(int argc, char **argv)
             std::vector<unsigned char> out((size_t)(W - 4) * (H - 4));
             for (int y = 0; y < H - 4; y++) std::memcpy(&out[(size_t)y * (W - 4)], rect.ptr<unsigned char>(y), (size_t)W - 4);
             dump(argv[7], out.data(), out.size());
+            return 0;
+        }
+        if (!std::strcmp(argv[1], "mask") && argc >= 9) {
+            // mask W H rgb map1 map2 mask_out boxes_out   (ROI fixed: 2 px margin; HSV range and minObjSize fixed)
+            int W = atoi(argv[2]), H = atoi(argv[3]);
+            std::vector<unsigned char> rgb = slurp(argv[4], (size_t)W * H * 3), m1 = slurp(argv[5], (size_t)W * H * 4), m2 = slurp(argv[6], (size_t)W * H * 2);
+            cv::Mat img(H, W, CV_8UC1, rgb.data(), (size_t)W * 3);
+            cv::Mat map1(H, W, CV_16SC1, m1.data(), (size_t)W * 4), map2(H, W, CV_16SC1, m2.data(), (size_t)W * 2);
+            const cv::Rect roif(2, 2, W - 4, H - 4);
+            CUDAColorMask cm(map1, map2, roif);
+            // like Estimator: filter_in / filter_out wrap the filter plugin's buffers (estimator.cpp:141-142)
+            VideoFilterDevice *f = new CUDAMorphologicalFilter(roif.width, roif.height, 8);
+            cv::Mat fin(roif.height, roif.width, CV_8UC1, f->getVideoInBuffer()), fout(roif.height, roif.width, CV_8UC1, f->getVideoOutBuffer());
+            const int low[3] = {20, 40, 40}, high[3] = {130, 255, 255};
+            if (cm.run(img, low, high, fin) != 0) return 4;
+            dump(argv[7], fin.data, (size_t)roif.width * roif.height);
+            if (f->run(fin, fout) != 0) return 4;
+            CUDAObjectRegions regions(roif.width, roif.height, 1024);
+            std::vector<cv::Rect> bounds; cv::Rect span;
+            const int nc = regions.run(fout, 60, bounds, span);
+            if (nc < 0) return 4;
+            FILE *o = std::fopen(argv[8], "w");
+            if (!o) return 2;
+            std::fprintf(o, "%d %d %d %d %d\n", nc, span.x, span.y, span.width, span.height);
+            for (size_t i = 0; i < bounds.size(); i++) std::fprintf(o, "%d %d %d %d\n", bounds[i].x, bounds[i].y, bounds[i].width, bounds[i].height);
+            std::fclose(o);
+            delete f;
             return 0;
         }
         if (!std::strcmp(argv[1], "depth") && argc >= 11) {

@@ -105,8 +105,54 @@ def main():
     np.savez_compressed(os.path.join(OUT, "rectify_320x240"), rgb=rgb, map1=m1, map2=m2, gray=gray, rect=rect,
                         roi=np.array(roi, np.int32), crop=crop)
     print("rectify_320x240")
+    make_mask()
     print("done")
 
 
+def cv_boxes(mask):
+    """estimator.cpp:47 + fill_bounding_rects_of_contours (:164-175) without the size filter: boundingRect of the
+    top-level contours, walking hierarchy[i][0] from contour 0 like the reference."""
+    import cv2
+    cs, hier = cv2.findContours(mask.copy(), cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)
+    out = []
+    if len(cs):
+        i = 0
+        while i >= 0:
+            out.append(tuple(int(v) for v in cv2.boundingRect(cs[i]))); i = int(hier[0][i][0])
+    return out
+
+
+def make_mask():
+    """mask front-end / back-end: estimator.cpp:38-53 with cv2 itself."""
+    import cv2
+    rng = np.random.default_rng(4300)
+    H, W = 240, 320
+    # coloured blobs on a noisy background, so that the HSV threshold selects connected objects with holes
+    base = cv2.GaussianBlur(rng.integers(0, 256, (H, W, 3)).astype(np.float32), (0, 0), 9.0)
+    base = (base - base.mean()) / base.std() * 70 + 128
+    rgb = np.clip(base + rng.integers(-6, 7, (H, W, 3)), 0, 255).astype(np.uint8)
+    K = np.array([[300., 0, 160.3], [0, 301., 119.6], [0, 0, 1]]); D = np.array([-0.31, 0.12, 0.001, -0.0007, 0.0])
+    Rm = cv2.Rodrigues(np.array([0.02, -0.03, 0.01]))[0]; P = np.array([[250., 0, 150, 0], [0, 250, 125, 0], [0, 0, 1, 0]])
+    m1, m2 = cv2.initUndistortRectifyMap(K, D, Rm, P, (W, H), cv2.CV_16SC2)
+    roi = (21, 13, 270, 200)
+    rect = cv2.remap(rgb, m1, m2, cv2.INTER_LINEAR)                                  # estimator.cpp:38
+    rect = np.ascontiguousarray(rect[roi[1]:roi[1] + roi[3], roi[0]:roi[0] + roi[2]])   # :39
+    bgr = cv2.cvtColor(rect, cv2.COLOR_RGB2BGR)                                      # :40
+    hsv = cv2.cvtColor(bgr, cv2.COLOR_BGR2HSV)                                       # :42
+    low, high = (30, 60, 50), (100, 255, 255)
+    filter_in = cv2.inRange(hsv, low, high)                                          # :43
+    k = cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (10, 10))
+    filter_out = cv2.erode(cv2.dilate(cv2.dilate(cv2.erode(filter_in, k), k), k), k)  # mf-sw.cpp:22-27
+    boxes_in, boxes_out = cv_boxes(filter_in), cv_boxes(filter_out)
+    np.savez_compressed(os.path.join(OUT, "mask_320x240"), rgb=rgb, map1=m1, map2=m2, roi=np.array(roi, np.int32),
+                        low=np.array(low, np.int32), high=np.array(high, np.int32), bgr=bgr, hsv=hsv, filter_in=filter_in,
+                        filter_out=filter_out, boxes_in=np.array(boxes_in, np.int32).reshape(-1, 4),
+                        boxes_out=np.array(boxes_out, np.int32).reshape(-1, 4))
+    print("mask_320x240", float((filter_in != 0).mean()), len(boxes_in), len(boxes_out))
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "mask":
+        make_mask()
+    else:
+        main()

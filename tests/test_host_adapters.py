@@ -69,3 +69,27 @@ def test_adapters_match_oracle(exe, gpu, orc, tmp_path):
     subprocess.check_call([exe, "rectify", str(W), str(H)] + paths)
     got = np.fromfile(paths[3], np.uint8).reshape(H - 4, W - 4)
     assert np.array_equal(got, orc.rectify(rgb, m1, m2, (2, 2, W - 4, H - 4)))
+
+
+@pytest.mark.gpu
+def test_mask_adapters_match_oracle(exe, gpu, orc, tmp_path):
+    """CUDAColorMask -> CUDAMorphologicalFilter (plugin-owned buffers) -> CUDAObjectRegions, driven from C++ the way
+    Estimator::run would (estimator.cpp:38-53)."""
+    import cv2
+    rng = np.random.default_rng(9)
+    W, H = 200, 150
+    base = cv2.GaussianBlur(rng.integers(0, 256, (H, W, 3)).astype(np.float32), (0, 0), 7.0)
+    rgb = np.clip((base - base.mean()) / base.std() * 70 + 128 + rng.integers(-5, 6, (H, W, 3)), 0, 255).astype(np.uint8)
+    m1 = np.stack([np.clip(np.arange(W)[None, :] + rng.integers(-1, 2, (H, W)), -1, W), np.clip(np.arange(H)[:, None] + rng.integers(-1, 2, (H, W)), -1, H)], -1).astype(np.int16)
+    m2 = rng.integers(0, 1024, (H, W)).astype(np.uint16)
+    paths = [str(tmp_path / n) for n in ("rgb.raw", "m1.raw", "m2.raw", "mask.raw", "boxes.txt")]
+    rgb.tofile(paths[0]); m1.tofile(paths[1]); m2.tofile(paths[2])
+    subprocess.check_call([exe, "mask", str(W), str(H)] + paths)
+    roi = (2, 2, W - 4, H - 4)
+    ref_mask, _ = orc.color_mask(rgb, m1, m2, roi, (20, 40, 40), (130, 255, 255))
+    assert np.array_equal(np.fromfile(paths[3], np.uint8).reshape(H - 4, W - 4), ref_mask)
+    out = orc.morph_open_close(ref_mask)
+    bounds, span = orc.object_regions(out, 60)
+    rows = [tuple(int(v) for v in l.split()) for l in open(paths[4]).read().splitlines()]
+    assert rows[0] == (len(orc.contour_boxes(out)),) + span
+    assert rows[1:] == bounds and len(bounds) >= 1

@@ -167,3 +167,45 @@ def test_rectify_oracle_matches_cv2_golden():
     assert np.array_equal(orc.rgb2gray(g["rgb"]), g["gray"])
     assert np.array_equal(orc.remap_linear_fixed(g["gray"], g["map1"], g["map2"]), g["rect"])
     assert np.array_equal(orc.rectify(g["rgb"], g["map1"], g["map2"], tuple(g["roi"])), g["crop"])
+
+
+def test_mask_oracle_matches_cv2_golden():
+    """Mask front-end / back-end restatement (oracle.py: color_mask, contour_boxes, object_regions) against the fixture
+    made with cv2 4.13.0 (remap of the 3-channel frame, RGB2BGR, BGR2HSV, inRange, findContours + boundingRect)."""
+    from oracle import oracle as orc
+    g = load_golden("mask_320x240")
+    roi = tuple(int(v) for v in g["roi"])
+    mask, bgr = orc.color_mask(g["rgb"], g["map1"], g["map2"], roi, g["low"], g["high"])
+    assert np.array_equal(bgr, g["bgr"])
+    assert np.array_equal(orc.bgr2hsv(g["bgr"]), g["hsv"])
+    assert np.array_equal(mask, g["filter_in"])
+    assert np.array_equal(orc.morph_open_close(g["filter_in"]), g["filter_out"])
+    for name in ("filter_in", "filter_out"):
+        boxes = np.array(orc.contour_boxes(g[name]), np.int32).reshape(-1, 4)
+        assert np.array_equal(boxes, g["boxes_" + name[7:]]), name
+    bounds, span = orc.object_regions(g["filter_out"], 400)
+    ref = [tuple(b) for b in g["boxes_out"] if b[2] * b[3] >= 400]
+    assert bounds == ref and len(bounds) >= 3
+    assert span == (min(b[0] for b in ref), min(b[1] for b in ref), max(b[0] + b[2] for b in ref) - min(b[0] for b in ref),
+                    max(b[1] + b[3] for b in ref) - min(b[1] for b in ref))
+    assert orc.object_regions(np.zeros((5, 7), np.uint8), 1) == ([], (1000000, 1000000, -2000000, -2000000))
+
+
+def test_mask_oracle_vs_cv2_live():
+    """Live against cv2 when it imports: every BGR colour through BGR2HSV, and contour boxes of random masks
+    (nested components, border contact, diagonal links)."""
+    cv2 = pytest.importorskip("cv2")
+    assert cv2.__version__ == "4.13.0"
+    from oracle import oracle as orc
+    from golden.make_golden import cv_boxes
+    rng = np.random.default_rng(5)
+    a = rng.integers(0, 256, (512, 512, 3)).astype(np.uint8)
+    a[:256, :256, 0] = np.arange(256)[None, :]; a[:256, :256, 1] = np.arange(256)[:, None]; a[:256, :256, 2] = 200
+    assert np.array_equal(orc.bgr2hsv(a), cv2.cvtColor(a, cv2.COLOR_BGR2HSV))
+    gray = np.repeat(np.arange(256, dtype=np.uint8)[None, :, None], 3, 2)
+    assert np.array_equal(orc.bgr2hsv(gray), cv2.cvtColor(gray, cv2.COLOR_BGR2HSV))
+    for t in range(25):
+        W, H = int(rng.integers(3, 160)), int(rng.integers(3, 120))
+        n = cv2.GaussianBlur(rng.integers(0, 256, (H, W)).astype(np.uint8), (0, 0), float(rng.uniform(0.6, 4)))
+        m = ((n > np.median(n) + int(rng.integers(-3, 4))) * int(rng.integers(1, 256))).astype(np.uint8)
+        assert cv_boxes(m) == orc.contour_boxes(m), (t, W, H)
