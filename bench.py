@@ -288,14 +288,19 @@ def run_ours(args):
 
     def e2e_step(i=0):
         # the filter's copies and kernels run on its own stream underneath the matcher call; the matcher's copies
-        # are enqueued first because its kernels (the long pole) cannot start before their first chunk has arrived
+        # are enqueued first because its kernels (the long pole) cannot start before their first chunk has arrived.
+        # Streaming use of both plugins: every batch's results (disparity maps AND filtered masks) are read on the host
+        # one submission later, so the host never blocks on work it has only just enqueued.
         if filt is not None and filter_first:
+            if i > 0:
+                filt.sync(); acc[0] += int(MOpn[0, H // 2, W // 2])
             filt.run_batch_async(Mpn, MOpn)
         if streaming:
-            # depth-2 stream of batches: the copies of batch i+1 / i-1 run under the kernels of batch i; every
-            # batch's result is read on the host one submission later
+            # depth-2 stream of batches: the copies of batch i+1 / i-1 run under the kernels of batch i
             matcher.submit_batch(Lpn, Rpn, Dpn2 if i & 1 else Dpn)
             if filt is not None and not filter_first:
+                if i > 0:
+                    filt.sync(); acc[0] += int(MOpn[0, H // 2, W // 2])
                 filt.run_batch_async(Mpn, MOpn)
             if i > 0:
                 matcher.wait_oldest()
@@ -305,20 +310,25 @@ def run_ours(args):
                 filt.run_batch_async(Mpn, MOpn)
             matcher.compute_batch(Lpn, Rpn, Dpn)
             acc[0] += int(Dpn[0, H // 2, W // 2])
-        if filt is not None:
-            filt.sync()
-            acc[0] += int(MOpn[0, H // 2, W // 2])
+            if filt is not None:
+                filt.sync()
+                acc[0] += int(MOpn[0, H // 2, W // 2])
 
     e2e_step()
     if streaming:
         matcher.wait()
+        if filt is not None:
+            filt.sync()
     barrier()
     t0 = time.perf_counter()
     for i in range(e2e_steps):
         e2e_step(i)
     if streaming:
-        matcher.wait()          # the last batch's result lands inside the timed region
+        matcher.wait()          # the last batch's results land inside the timed region
         acc[0] += int((Dpn2 if (e2e_steps - 1) & 1 else Dpn)[0, H // 2, W // 2])
+        if filt is not None:
+            filt.sync()
+            acc[0] += int(MOpn[0, H // 2, W // 2])
     torch.cuda.synchronize()
     e2e_fps, _, _ = sharding.whole_job_throughput(B * e2e_steps, (time.perf_counter() - t0) * 1e3, 1.0, dist, dev)
     h2d = B * 2 * W * H + (B * W * H if filt is not None else 0)
@@ -395,7 +405,7 @@ def run_ours(args):
                        "numDisparities": ND, "parallelism": f"frame-sharded x{world} (no collective)",
                        "l2": f"inputs+outputs per step = {(B * 4 * W * H + 2 * B * W * H) / 1e6:.0f} MB > 126 MB L2"},
             "e2e": {"value": e2e_fps * mde_per_frame(), "unit": "Mde/s", "fps": e2e_fps, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "api": ("rtdm_morph_run_batch_async + rtdm_bm_submit_batch (2 batches in flight) + rtdm_bm_wait_oldest + rtdm_morph_sync" if wl == "bm720" else "rtdm_sgbm_compute_batch") + ", pinned host buffers"},
+                    "d2h_bytes_per_step": d2h, "api": ("rtdm_bm_submit_batch (2 batches in flight) + rtdm_morph_run_batch_async, results of batch i read during batch i+1 (rtdm_bm_wait_oldest / rtdm_morph_sync)" if wl == "bm720" else "rtdm_sgbm_compute_batch") + ", pinned host buffers"},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         }
