@@ -142,6 +142,13 @@ int rtdm_sgbm_compute(rtdm_sgbm *h, const uint8_t *left, size_t lstep, const uin
 int rtdm_sgbm_compute_batch(rtdm_sgbm *h, int n, const uint8_t *left, size_t lstep, size_t lframe,
                             const uint8_t *right, size_t rstep, size_t rframe, int width,
                             int height, int16_t *disp, size_t dstep, size_t dframe);
+/* streaming variants, exactly as rtdm_bm_submit_batch / rtdm_bm_wait / rtdm_bm_wait_oldest: two calls may be in flight,
+ * the copies of batch k+1 / k-1 run under the kernels of batch k */
+int rtdm_sgbm_submit_batch(rtdm_sgbm *h, int n, const uint8_t *left, size_t lstep, size_t lframe,
+                           const uint8_t *right, size_t rstep, size_t rframe, int width, int height,
+                           int16_t *disp, size_t dstep, size_t dframe);
+int rtdm_sgbm_wait(rtdm_sgbm *h);
+int rtdm_sgbm_wait_oldest(rtdm_sgbm *h);
 int rtdm_sgbm_compute_device(rtdm_sgbm *h, int n, const uint8_t *left, size_t lstep, size_t lframe,
                              const uint8_t *right, size_t rstep, size_t rframe, int width,
                              int height, int16_t *disp, size_t dstep, size_t dframe,

@@ -489,6 +489,11 @@ struct rtdm_sgbm {
     int32_t *labels, *sizes, *runlen;
     uint8_t *dL, *dR; size_t spitch, sframe;
     int16_t *dD;      size_t dpitch, dframe;
+    uint8_t *dL2, *dR2; int16_t *dD2;            // staging set 1 (rtdm_sgbm_submit_batch alternates)
+    cudaStream_t lane[2];                        // H2D / D2H streams of the streaming host API
+    cudaEvent_t ev_in[2], ev_cmp[2], done[2];    // per staging set: inputs arrived, kernels finished, outputs delivered
+    int busy[2];
+    unsigned seq;
     int launches;
     int prof;
     std::vector<cudaEvent_t> *ev;     // 3 events per profiled sub-batch: start, after matching, after post-filters
@@ -525,6 +530,13 @@ extern "C" void rtdm_sgbm_destroy(rtdm_sgbm *h)
     cudaSetDevice(h->dev);
     cudaFree(h->planes); cudaFree(h->C); cudaFree(h->S); cudaFree(h->raw); cudaFree(h->labels); cudaFree(h->sizes); cudaFree(h->runlen);
     cudaFree(h->dL); cudaFree(h->dR); cudaFree(h->dD);
+    cudaFree(h->dL2); cudaFree(h->dR2); cudaFree(h->dD2);
+    for (int i = 0; i < 2; i++) {
+        if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
+        if (h->ev_cmp[i]) cudaEventDestroy(h->ev_cmp[i]);
+        if (h->done[i]) cudaEventDestroy(h->done[i]);
+        if (h->lane[i]) cudaStreamDestroy(h->lane[i]);
+    }
     if (h->ev) { for (cudaEvent_t e : *h->ev) cudaEventDestroy(e); delete h->ev; }
     if (h->st) cudaStreamDestroy(h->st);
     delete h;
@@ -571,6 +583,15 @@ extern "C" int rtdm_sgbm_create(rtdm_sgbm **out, const rtdm_params *p, int max_w
     if (!rc) rc = dev_alloc(&h->dL, h->sframe * B);
     if (!rc) rc = dev_alloc(&h->dR, h->sframe * B);
     if (!rc) rc = dev_alloc(&h->dD, h->dframe * B);
+    if (!rc) rc = dev_alloc(&h->dL2, h->sframe * B);
+    if (!rc) rc = dev_alloc(&h->dR2, h->sframe * B);
+    if (!rc) rc = dev_alloc(&h->dD2, h->dframe * B);
+    for (int i = 0; i < 2 && !rc; i++) {
+        if (cudaStreamCreateWithFlags(&h->lane[i], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->ev_cmp[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->done[i], cudaEventDisableTiming) != cudaSuccess) rc = -RTDM_EIO;
+    }
     if (rc) { rtdm_sgbm_destroy(h); return rc; }
     *out = h;
     return 0;
@@ -586,8 +607,24 @@ static int sgbm_pipeline(rtdm_sgbm *h, int n, PlaneU8 L, PlaneU8 R, int W, int H
     const int INVS = (g.minD - 1) * 16;
     size_t pl = 0, vol = 0;
     sgbm_work_bytes(g, &pl, &vol);
-    for (int f0 = 0; f0 < n; f0 += h->volB) {
-        const int m = std::min(h->volB, n - f0);
+    // sub-batch size: the row sweeps (59 % of the time) run one 1024-thread CTA per SM, frames x column tiles CTAs per
+    // launch -> among the sizes the volumes allow, take the one that fills whole waves best (720p x 128: 37 frames x 24
+    // tiles = 6.0 waves of 148 SMs; 32 frames would be 5.2 -> 6 waves)
+    int chunk = h->volB;
+    if (n > 1) {
+        const int ctas = sgbm_sweep_ctas_per_frame(g);
+        int nsm = 0;
+        if (ctas > 0 && cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->dev) == cudaSuccess && nsm > 0) {
+            double best = 0.0;
+            for (int m = 1; m <= std::min(h->volB, n); m++) {
+                const long long c = (long long)m * ctas, waves = (c + nsm - 1) / nsm;
+                const double eff = (double)c / (double)(waves * nsm);
+                if (eff >= best - 1e-9 || (m >= 8 && eff >= best - 0.02)) { if (eff > best) best = eff; chunk = m; }
+            }
+        }
+    }
+    for (int f0 = 0; f0 < n; f0 += chunk) {
+        const int m = std::min(chunk, n - f0);
         PlaneU8 l = {L.p + (size_t)f0 * L.frame, L.pitch, L.frame}, r = {R.p + (size_t)f0 * R.frame, R.pitch, R.frame};
         PlaneS16 o = {out.p + (size_t)f0 * out.frame, out.pitch, out.frame};
         PlaneS16 raw = {h->raw, h->rpitch, h->rframe};
@@ -665,9 +702,34 @@ extern "C" int rtdm_sgbm_compute_device(rtdm_sgbm *h, int n, const uint8_t *left
                          PlaneS16{disp, dstep / 2, dframe / 2}, st);
 }
 
-extern "C" int rtdm_sgbm_compute_batch(rtdm_sgbm *h, int n, const uint8_t *left, size_t lstep, size_t lframe,
-                                       const uint8_t *right, size_t rstep, size_t rframe, int width, int height,
-                                       int16_t *disp, size_t dstep, size_t dframe)
+extern "C" int rtdm_sgbm_wait(rtdm_sgbm *h)
+{
+    if (!h) return -RTDM_EINVAL;
+    RTDM_CUDA(cudaSetDevice(h->dev));
+    cudaError_t e0 = cudaStreamSynchronize(h->lane[1]);
+    { cudaError_t e = cudaStreamSynchronize(h->st); if (e0 == cudaSuccess) e0 = e; }
+    { cudaError_t e = cudaStreamSynchronize(h->lane[0]); if (e0 == cudaSuccess) e0 = e; }
+    h->busy[0] = h->busy[1] = 0;
+    RTDM_CUDA(e0);
+    return 0;
+}
+
+extern "C" int rtdm_sgbm_wait_oldest(rtdm_sgbm *h)
+{
+    if (!h) return -RTDM_EINVAL;
+    RTDM_CUDA(cudaSetDevice(h->dev));
+    const int newest = (int)((h->seq - 1u) & 1u), oldest = newest ^ 1;
+    const int set = h->busy[oldest] ? oldest : newest;       // only one in flight: that one
+    if (h->busy[set]) { RTDM_CUDA(cudaEventSynchronize(h->done[set])); h->busy[set] = 0; }
+    return 0;
+}
+
+// H2D on lane[0], kernels on the handle's stream, D2H on lane[1], chained by events; two staging sets, so the copies of
+// batch k+1 / k-1 run under the kernels of batch k (the cost volumes and scratch are used by one batch at a time: the
+// kernels of successive batches are ordered on the one compute stream)
+extern "C" int rtdm_sgbm_submit_batch(rtdm_sgbm *h, int n, const uint8_t *left, size_t lstep, size_t lframe,
+                                      const uint8_t *right, size_t rstep, size_t rframe, int width, int height,
+                                      int16_t *disp, size_t dstep, size_t dframe)
 {
     if (!h || !left || !right || !disp) { set_error("sgbm_compute: null argument"); return -RTDM_EINVAL; }
     if (n < 1 || n > h->maxB || width > h->maxW || height > h->maxH || width < 1 || height < 1) {
@@ -676,19 +738,37 @@ extern "C" int rtdm_sgbm_compute_batch(rtdm_sgbm *h, int n, const uint8_t *left,
     }
     RTDM_CUDA(cudaSetDevice(h->dev));
     h->launches = 0;
-    cudaStream_t st = h->st;
+    const int set = (int)(h->seq++ & 1u);
+    if (h->busy[set]) { RTDM_CUDA(cudaEventSynchronize(h->done[set])); h->busy[set] = 0; }
+    uint8_t *sL = set ? h->dL2 : h->dL, *sR = set ? h->dR2 : h->dR;
+    int16_t *sD = set ? h->dD2 : h->dD;
+    cudaStream_t s_in = h->lane[0], s_out = h->lane[1], st = h->st;
     for (int k = 0; k < n; k++) {
-        RTDM_CUDA(cudaMemcpy2DAsync(h->dL + k * h->sframe, h->spitch, left + k * lframe, lstep, width, height, cudaMemcpyHostToDevice, st));
-        RTDM_CUDA(cudaMemcpy2DAsync(h->dR + k * h->sframe, h->spitch, right + k * rframe, rstep, width, height, cudaMemcpyHostToDevice, st));
+        RTDM_CUDA(cudaMemcpy2DAsync(sL + k * h->sframe, h->spitch, left + k * lframe, lstep, width, height, cudaMemcpyHostToDevice, s_in));
+        RTDM_CUDA(cudaMemcpy2DAsync(sR + k * h->sframe, h->spitch, right + k * rframe, rstep, width, height, cudaMemcpyHostToDevice, s_in));
     }
-    int rc = sgbm_pipeline(h, n, PlaneU8{h->dL, h->spitch, h->sframe}, PlaneU8{h->dR, h->spitch, h->sframe}, width, height,
-                           PlaneS16{h->dD, h->dpitch, h->dframe}, st);
-    if (rc) return rc;
+    RTDM_CUDA(cudaEventRecord(h->ev_in[set], s_in));
+    RTDM_CUDA(cudaStreamWaitEvent(st, h->ev_in[set], 0));
+    int rc = sgbm_pipeline(h, n, PlaneU8{sL, h->spitch, h->sframe}, PlaneU8{sR, h->spitch, h->sframe}, width, height,
+                           PlaneS16{sD, h->dpitch, h->dframe}, st);
+    if (rc) { rtdm_sgbm_wait(h); return rc; }
+    RTDM_CUDA(cudaEventRecord(h->ev_cmp[set], st));
+    RTDM_CUDA(cudaStreamWaitEvent(s_out, h->ev_cmp[set], 0));
     for (int k = 0; k < n; k++)
-        RTDM_CUDA(cudaMemcpy2DAsync((uint8_t *)disp + k * dframe, dstep, h->dD + k * h->dframe, h->dpitch * 2,
-                                    (size_t)width * 2, height, cudaMemcpyDeviceToHost, st));
-    RTDM_CUDA(cudaStreamSynchronize(st));
+        RTDM_CUDA(cudaMemcpy2DAsync((uint8_t *)disp + k * dframe, dstep, sD + k * h->dframe, h->dpitch * 2,
+                                    (size_t)width * 2, height, cudaMemcpyDeviceToHost, s_out));
+    RTDM_CUDA(cudaEventRecord(h->done[set], s_out));
+    h->busy[set] = 1;
     return 0;
+}
+
+extern "C" int rtdm_sgbm_compute_batch(rtdm_sgbm *h, int n, const uint8_t *left, size_t lstep, size_t lframe,
+                                       const uint8_t *right, size_t rstep, size_t rframe, int width, int height,
+                                       int16_t *disp, size_t dstep, size_t dframe)
+{
+    int rc = rtdm_sgbm_submit_batch(h, n, left, lstep, lframe, right, rstep, rframe, width, height, disp, dstep, dframe);
+    if (rc) return rc;
+    return rtdm_sgbm_wait(h);
 }
 
 extern "C" int rtdm_sgbm_compute(rtdm_sgbm *h, const uint8_t *left, size_t lstep, const uint8_t *right,

@@ -96,6 +96,7 @@ struct SgbmWork {
     size_t frame_planes, frame_vol;
 };
 size_t sgbm_work_bytes(const SgbmGeom &g, size_t *planes, size_t *vol);
+int sgbm_sweep_ctas_per_frame(const SgbmGeom &g);
 int launch_sgbm(const SgbmGeom &g, int n, PlaneU8 left, PlaneU8 right, PlaneS16 out, SgbmWork w,
                 cudaStream_t st, int *launches);
 

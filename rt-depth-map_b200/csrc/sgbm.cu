@@ -1019,6 +1019,15 @@ size_t sgbm_work_bytes(const SgbmGeom &g, size_t *planes, size_t *vol)
     return pl + 2 * v * sizeof(uint16_t);
 }
 
+// CTAs per frame of one row-sweep launch (0 when the sweep kernels do not apply): the host layer sizes its sub-batches so
+// that frames x this fills whole waves of SMs (one 1024-thread CTA per SM)
+int sgbm_sweep_ctas_per_frame(const SgbmGeom &g)
+{
+    if (!(g.D == 64 || g.D == 128) || g.bs > 7) return 0;
+    const int LPC = g.D / 8, NS = 1024 / LPC, X = NS - 2 * SW_R;
+    return cdiv(g.W1, X);
+}
+
 int launch_sgbm(const SgbmGeom &g, int n, PlaneU8 left, PlaneU8 right, PlaneS16 out, SgbmWork w,
                 cudaStream_t st, int *launches)
 {

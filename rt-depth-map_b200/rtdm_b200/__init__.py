@@ -70,6 +70,9 @@ SIGNATURES = {
     "rtdm_sgbm_destroy": (None, [_vp]),
     "rtdm_sgbm_compute": (_i, [_vp, _vp, _sz, _vp, _sz, _i, _i, _vp, _sz]),
     "rtdm_sgbm_compute_batch": (_i, [_vp, _i, _vp, _sz, _sz, _vp, _sz, _sz, _i, _i, _vp, _sz, _sz]),
+    "rtdm_sgbm_submit_batch": (_i, [_vp, _i, _vp, _sz, _sz, _vp, _sz, _sz, _i, _i, _vp, _sz, _sz]),
+    "rtdm_sgbm_wait": (_i, [_vp]),
+    "rtdm_sgbm_wait_oldest": (_i, [_vp]),
     "rtdm_sgbm_compute_device": (_i, [_vp, _i, _vp, _sz, _sz, _vp, _sz, _sz, _i, _i, _vp, _sz, _sz, _vp]),
     "rtdm_sgbm_last_launches": (_i, [_vp]),
     "rtdm_sgbm_set_profiling": (_i, [_vp, _i]),
@@ -316,6 +319,21 @@ class CUDASemiGlobalMatcher(_MatcherBase):
         pass
 
     STAGES = ("matching", "median_speckle")
+
+    def submit_batch(self, left, right, out):
+        """Streaming variant of compute_batch (see CUDAMatcherKonolige.submit_batch): returns immediately, at most two
+        submissions in flight; wait_oldest() / wait() before reading `out`."""
+        N, H, W = left.shape
+        if not (left.flags.c_contiguous and right.flags.c_contiguous and out.flags.c_contiguous):
+            raise RtdmError(-EINVAL, "submit_batch: contiguous arrays required")
+        _check(self._l.rtdm_sgbm_submit_batch(self._h, N, left.ctypes.data, W, W * H, right.ctypes.data, W, W * H, W, H,
+                                              out.ctypes.data, W * 2, W * H * 2))
+
+    def wait(self):
+        _check(self._l.rtdm_sgbm_wait(self._h))
+
+    def wait_oldest(self):
+        _check(self._l.rtdm_sgbm_wait_oldest(self._h))
 
     def set_profiling(self, on: bool):
         _check(self._l.rtdm_sgbm_set_profiling(self._h, int(on)))

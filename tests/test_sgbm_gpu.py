@@ -124,3 +124,29 @@ def test_sgbm_errors(gpu):
     assert e.value.code == -gpu.EINVAL
     with pytest.raises(gpu.RtdmError):
         gpu.CUDASemiGlobalMatcher(4, 0, 64, 10, 100, 32, 1)
+
+
+def test_sgbm_streaming_submissions(gpu, orc):
+    """rtdm_sgbm_submit_batch keeps two batches in flight on alternating staging buffers: every submission's output
+    equals the blocking call's, in any interleaving of wait_oldest / wait."""
+    import torch
+    from rtdm_b200 import synth
+    W, H, nd, B = 320, 240, 64, 3
+    p = dict(blockSize=5, minDisparity=0, numDisparities=nd, uniquenessRatio=10, speckleWindowSize=100, speckleRange=32, disp12MaxDiff=1)
+    batches = []
+    for b in range(4):
+        fr = [synth.stereo_pair(W, H, nd, 8100 + 10 * b + i) for i in range(B)]
+        batches.append((torch.from_numpy(np.stack([f[0] for f in fr])).pin_memory().numpy(),
+                        torch.from_numpy(np.stack([f[1] for f in fr])).pin_memory().numpy()))
+    m = gpu.CUDASemiGlobalMatcher(p["blockSize"], 0, nd, 10, 100, 32, 1, mode=1, max_width=W, max_height=H, max_batch=B)
+    ref = [m.compute_batch(L, R).copy() for L, R in batches]
+    outs = [torch.empty((B, H, W), dtype=torch.int16).pin_memory().numpy() for _ in batches]
+    for i, (L, R) in enumerate(batches):
+        m.submit_batch(L, R, outs[i])
+        if i > 0:
+            m.wait_oldest()
+            assert np.array_equal(outs[i - 1], ref[i - 1]), i
+    m.wait()
+    assert np.array_equal(outs[-1], ref[-1])
+    op = orc.make_params(P1=600, P2=2400, preFilterCap=0, mode=1, **p)
+    assert np.array_equal(ref[0][0], orc.sgbm_compute(batches[0][0][0], batches[0][1][0], op))
