@@ -422,7 +422,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="bm720", choices=["bm720", "sgbm720"])
-    ap.add_argument("--batch", type=int, default=64, help="frames per step per GPU")
+    # 63: the SAD/WTA kernel runs 42 CTAs per 720p frame, one per SM -> 63 frames = 17.9 waves of 148 SMs (64: 18.2 -> 19)
+    ap.add_argument("--batch", type=int, default=63, help="frames per step per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -228,6 +228,46 @@ extern "C" int rtdm_bm_set_roi2(rtdm_bm *h, int x, int y, int w, int hgt)
     return 0;
 }
 
+static BmGeom bm_geom(const rtdm_params &p, int W, int H, ValidRect *vrout = nullptr)
+{
+    const int nd = p.numDisparities, minD = p.minDisparity;
+    BmGeom g;
+    g.W = W; g.H = H; g.nd = nd; g.minD = minD; g.bs = p.blockSize; g.cap = p.preFilterCap;
+    g.texThr = p.textureThreshold; g.uniq = p.uniquenessRatio;
+    g.lofs = std::max(nd - 1 + minD, 0); g.rofs = -std::min(nd - 1 + minD, 0);
+    g.W1 = W - g.rofs - nd + 1;
+    ValidRect vr = valid_rect(p.roi1, p.roi2, W, H, minD, nd, p.blockSize);
+    int row0 = std::min(std::max(vr.y, 0), H), row1 = std::min(std::max(vr.y + vr.h, 0), H);
+    if (vr.w == 0 || vr.h == 0 || g.lofs >= W || g.rofs >= W || g.W1 < 1) row0 = row1 = 0;
+    g.row0 = row0; g.row1 = row1;
+    if (vrout) *vrout = vr;
+    return g;
+}
+
+// chunk size of the host batch pipeline: at least two chunks per call from 32 frames on (copy / compute overlap inside
+// the call), and among those the split whose SAD/WTA launches leave the fewest partly filled waves
+// (720p x 128: 42 CTAs per frame, one CTA per SM -> multiples of 7 frames fill 2 waves of 148 SMs to 99 %)
+static int bm_chunk_for(const rtdm_bm *h, int n, int W, int H)
+{
+    int chunk = n >= 64 ? 32 : (n >= 32 ? 16 : (n >= 8 ? (n + 3) / 4 : n));
+    if (n < 16 || h->p.blockSize >= W || h->p.blockSize >= H) return chunk;
+    const BmGeom g = bm_geom(h->p, W, H);
+    const char *force = getenv("RTDM_BM_KERNEL");
+    if (force && (force[0] == '1' || force[0] == '2')) return chunk;
+    int nsm = 0;
+    if (cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->dev) != cudaSuccess || nsm < 1) return chunk;
+    long long best = -1;
+    for (int m = std::max(8, n / 4); m <= (n + 1) / 2 + 4 && m < n; m++) {
+        const int k = (n + m - 1) / m, last = n - (k - 1) * m;
+        const int c1 = bm_sad3_ctas_per_frame(g, m), c2 = bm_sad3_ctas_per_frame(g, last);
+        if (c1 <= 0 || c2 <= 0) return chunk;
+        const long long waves = (long long)(k - 1) * (((long long)m * c1 + nsm - 1) / nsm) + ((long long)last * c2 + nsm - 1) / nsm;
+        const long long score = waves * 16 + k;                 // fewer waves first, then fewer chunks
+        if (best < 0 || score < best) { best = score; chunk = m; }
+    }
+    return chunk;
+}
+
 // the kernel pipeline on device-resident frames
 static int bm_pipeline(rtdm_bm *h, int n, PlaneU8 L, PlaneU8 R, int W, int H, PlaneS16 out, cudaStream_t st, int f0 = 0)
 {
@@ -376,7 +416,7 @@ extern "C" int rtdm_bm_submit_batch(rtdm_bm *h, int n, const uint8_t *left, size
     // chained by events.  The kernels always see whole chunks in order (no concurrent kernels from different
     // chunks fighting for the SMs); the copies of chunk c+1 / c-1 overlap the kernels of chunk c.
     // the SAD kernel is ~12 % more efficient on 32-frame launches than on 16-frame ones (fuller waves)
-    int chunk = n >= 64 ? 32 : (n >= 32 ? 16 : (n >= 8 ? (n + 3) / 4 : n));
+    int chunk = bm_chunk_for(h, n, width, height);
     if (const char *e = getenv("RTDM_BM_CHUNK")) chunk = std::max(1, std::min(n, atoi(e)));
     const int nchunks = (n + chunk - 1) / chunk;
     if (!h->pev) h->pev = new std::vector<cudaEvent_t>();

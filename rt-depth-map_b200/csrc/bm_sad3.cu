@@ -645,6 +645,15 @@ bool bm_sad3_supported(const BmGeom &g, int n)
     return g.W1 >= 1 && g.row1 > g.row0 && pick_tiling3(g, n, &t);
 }
 
+// CTAs per frame of one launch of n frames (0 when the kernel does not apply): the host layer sizes its chunks so that
+// frames x this fills whole waves (one CTA per SM)
+int bm_sad3_ctas_per_frame(const BmGeom &g, int n)
+{
+    Tiling3 t;
+    if (!(g.W1 >= 1 && g.row1 > g.row0 && pick_tiling3(g, n, &t))) return 0;
+    return t.pair ? 0 : t.nstripes * t.nbands;
+}
+
 // SAD + WTA kernel only; the texture sums `tex` must have been produced already (bm_sad2.cu: bm_texture_kernel)
 int launch_bm_sad3_core(const BmGeom &g, int n, PlaneU8 Lp, PlaneU8 Rp, PlaneS16 disp, PlaneS16 cost,
                         const uint16_t *tex, size_t tex_pitch, size_t tex_frame, cudaStream_t st)
