@@ -272,3 +272,25 @@ def test_bm_large_frame_256_disparities(gpu, orc):
         got = _mk(gpu, p, W, H).compute(L, R)
         ref = orc.bm_compute(L, R, _orc_params(orc, p))
         assert np.array_equal(got, ref), (bs, int((got != ref).sum()))
+
+
+@pytest.mark.parametrize("shape", ["wide", "pair"])
+def test_bm_warp_specialised_kernel_is_deterministic_under_load(gpu, orc, shape, monkeypatch):
+    """The producer / consumer / loader warps of bm_sad3.cu hand rows over through named barriers and a shared-memory
+    ring: a protocol slip would show up as a rare, timing-dependent difference.  24 launches of a 12-frame 720p batch
+    (both CTA shapes) must all equal the oracle's maps."""
+    from rtdm_b200 import synth
+    monkeypatch.delenv("RTDM_BM_KERNEL", raising=False)
+    monkeypatch.setenv("RTDM_BM3_SHAPE", "1" if shape == "pair" else "0")
+    p = dict(preFilterCap=31, blockSize=13, minDisparity=0, textureThreshold=10, numDisparities=128,
+             uniquenessRatio=10, speckleWindowSize=100, speckleRange=32, disp12MaxDiff=1)
+    frames = [synth.stereo_pair(1280, 720, 128, 1000 + i) for i in range(3)]
+    ref = [orc.bm_compute(f[0], f[1], _orc_params(orc, p)) for f in frames]
+    B = 12
+    Ls = np.stack([frames[i % 3][0] for i in range(B)]); Rs = np.stack([frames[i % 3][1] for i in range(B)])
+    m = _mk(gpu, p, 1280, 720, max_batch=B)
+    for rep in range(24):
+        out = m.compute_batch(Ls, Rs)
+        assert m.last_kernel() == 3
+        for i in range(B):
+            assert np.array_equal(out[i], ref[i % 3]), (shape, rep, i, int((out[i] != ref[i % 3]).sum()))
