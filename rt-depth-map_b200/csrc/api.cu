@@ -246,7 +246,7 @@ static BmGeom bm_geom(const rtdm_params &p, int W, int H, ValidRect *vrout = nul
 
 // chunk size of the host batch pipeline: at least two chunks per call from 32 frames on (copy / compute overlap inside
 // the call), and among those the split whose SAD/WTA launches leave the fewest partly filled waves
-// (720p x 128: 42 CTAs per frame, one CTA per SM -> multiples of 7 frames fill 2 waves of 148 SMs to 99 %)
+// (bm_sad3_cost: waves x (band height + start-up) of the launch; 720p x 128, 63 frames -> 42 + 21)
 static int bm_chunk_for(const rtdm_bm *h, int n, int W, int H)
 {
     int chunk = n >= 64 ? 32 : (n >= 32 ? 16 : (n >= 8 ? (n + 3) / 4 : n));
@@ -254,15 +254,12 @@ static int bm_chunk_for(const rtdm_bm *h, int n, int W, int H)
     const BmGeom g = bm_geom(h->p, W, H);
     const char *force = getenv("RTDM_BM_KERNEL");
     if (force && (force[0] == '1' || force[0] == '2')) return chunk;
-    int nsm = 0;
-    if (cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->dev) != cudaSuccess || nsm < 1) return chunk;
     long long best = -1;
-    for (int m = std::max(8, n / 4); m <= (n + 1) / 2 + 4 && m < n; m++) {
+    for (int m = std::max(8, n / 4); m < n; m++) {
         const int k = (n + m - 1) / m, last = n - (k - 1) * m;
-        const int c1 = bm_sad3_ctas_per_frame(g, m), c2 = bm_sad3_ctas_per_frame(g, last);
-        if (c1 <= 0 || c2 <= 0) return chunk;
-        const long long waves = (long long)(k - 1) * (((long long)m * c1 + nsm - 1) / nsm) + ((long long)last * c2 + nsm - 1) / nsm;
-        const long long score = waves * 16 + k;                 // fewer waves first, then fewer chunks
+        const long long c1 = bm_sad3_cost(g, m), c2 = bm_sad3_cost(g, last);
+        if (c1 < 0 || c2 < 0) return chunk;
+        const long long score = ((k - 1) * c1 + c2) * 16 + k;       // fewer row steps first, then fewer chunks
         if (best < 0 || score < best) { best = score; chunk = m; }
     }
     return chunk;

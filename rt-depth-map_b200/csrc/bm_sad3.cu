@@ -566,7 +566,20 @@ bm_sad3_kernel(Bm3Args a)
     }
 }
 
-struct Tiling3 { int NG, TW, BH, nstripes, nbands, NT, pair; size_t smem; };
+struct Tiling3 { int NG, TW, BH, nstripes, nbands, NT, pair; size_t smem; long long cost; };
+
+// SMs of the current device (cached per device)
+int sm_count()
+{
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (!cached[dev]) {
+        int n = 0;
+        cached[dev] = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : 148;
+    }
+    return cached[dev];
+}
 
 bool pick_tiling3(const BmGeom &g, int n, Tiling3 *t)
 {
@@ -591,11 +604,21 @@ bool pick_tiling3(const BmGeom &g, int n, Tiling3 *t)
     t->NG = cdiv(t->TW + 2 * h, G);
     if (t->NG > ngmax) return false;
     t->NT = (t->NG * NO + 31) / 32 * 64 + NCW * 32;
+    // bands: a band pays ~START rows of start-up (ring prologue, 2h+1 rows of window sums) and the launch runs in waves
+    // of (SMs x CTAs per SM) CTAs -> take the band count with the smallest (waves + 1/2) x (band height + START); the
+    // half wave stands for the tail (stripes differ a little), and bands stay <= 128 rows: measured, a few long CTAs
+    // per SM (706-row bands, 3 waves) lose more to that tail than they save in start-up
     const int rows = g.row1 - g.row0;
-    int bhmax = 128;
-    while (bhmax > 32 && (long long)n * t->nstripes * cdiv(rows, bhmax) < 2 * 148 * (pair ? 2 : 1)) bhmax /= 2;
-    t->nbands = cdiv(rows, bhmax);
-    t->BH = cdiv(rows, t->nbands);
+    const int slots = sm_count() * (pair ? 2 : 1), START = 2 * h + 8;
+    long long best = -1;
+    for (int nb = 1; nb <= std::max(1, rows / 8) && nb <= 64; nb++) {
+        const int bh = cdiv(rows, nb);
+        if (cdiv(rows, bh) != nb || (bh > 128 && nb < std::max(1, rows / 8))) continue;
+        const long long waves = ((long long)n * t->nstripes * nb + slots - 1) / slots;
+        const long long cost = (2 * waves + 1) * (bh + START);
+        if (best < 0 || cost < best) { best = cost; t->nbands = nb; t->BH = bh; }
+    }
+    t->cost = best;
     t->smem = (size_t)make_geo3(h, g.nd, t->NG).total;
     return t->smem <= smem_max;
 }
@@ -645,13 +668,13 @@ bool bm_sad3_supported(const BmGeom &g, int n)
     return g.W1 >= 1 && g.row1 > g.row0 && pick_tiling3(g, n, &t);
 }
 
-// CTAs per frame of one launch of n frames (0 when the kernel does not apply): the host layer sizes its chunks so that
-// frames x this fills whole waves (one CTA per SM)
-int bm_sad3_ctas_per_frame(const BmGeom &g, int n)
+// estimated cost of one launch of n frames in row steps (waves x (band height + start-up)), -1 when the kernel does not
+// apply: the host layer sizes its chunks with it
+long long bm_sad3_cost(const BmGeom &g, int n)
 {
     Tiling3 t;
-    if (!(g.W1 >= 1 && g.row1 > g.row0 && pick_tiling3(g, n, &t))) return 0;
-    return t.pair ? 0 : t.nstripes * t.nbands;
+    if (!(g.W1 >= 1 && g.row1 > g.row0 && pick_tiling3(g, n, &t))) return -1;
+    return t.cost;
 }
 
 // SAD + WTA kernel only; the texture sums `tex` must have been produced already (bm_sad2.cu: bm_texture_kernel)
