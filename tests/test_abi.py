@@ -71,6 +71,31 @@ def test_no_cpu_fallback(rt):
     import numpy as np
     with pytest.raises(rt.RtdmError):
         rt.filter_speckles(np.zeros((8, 8), np.int16), -16, 10, 1)
+    # the steps either side of the plugins have no CPU path either
+    m1 = np.zeros((8, 8, 2), np.int16); m2 = np.zeros((8, 8), np.uint16)
+    for make in (lambda: rt.CUDAObjectRegions(64, 48), lambda: rt.CUDAColorMask(m1, m2, (0, 0, 8, 8)),
+                 lambda: rt.CUDARectifier(m1, m2, (0, 0, 8, 8)), lambda: rt.CUDADepthEpilogue(64, 48, 4),
+                 lambda: rt.CUDASemiGlobalMatcher(5, 0, 64, 10, 100, 32, 1)):
+        with pytest.raises(rt.RtdmError) as e:
+            make()
+        assert e.value.code == -rt.ENODEV
+
+
+def test_mask_entry_points_validate_arguments(rt):
+    """Argument checks of the mask front-end / back-end happen before any device work (same -EINVAL convention)."""
+    import numpy as np
+    m1 = np.zeros((8, 8, 2), np.int16); m2 = np.zeros((8, 8), np.uint16)
+    for roi in [(-1, 0, 4, 4), (0, 0, 9, 8), (0, 0, 0, 4), (6, 6, 4, 4)]:
+        with pytest.raises(rt.RtdmError) as e:
+            rt.CUDAColorMask(m1, m2, roi)
+        assert e.value.code == -rt.EINVAL, roi
+    with pytest.raises(rt.RtdmError) as e:
+        rt.CUDAColorMask(np.zeros((8, 8), np.int16), m2, (0, 0, 8, 8))
+    assert e.value.code == -rt.EINVAL
+    for args in [(0, 48, 16), (64, 0, 16), (64, 48, 0)]:
+        with pytest.raises(rt.RtdmError) as e:
+            rt.CUDAObjectRegions(*args)
+        assert e.value.code == -rt.EINVAL, args
 
 
 def test_product_does_not_reference_oracle():
