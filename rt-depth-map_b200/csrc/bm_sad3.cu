@@ -54,7 +54,7 @@ struct Bm3Args {
     int W, H, nd, cap, texThr, uniq;
     int W1, row0, row1;
     int TW, BH, NG;              // stripe width, band height, column groups (= producer warps x groups per warp)
-    int dbg;                     // timing experiments only: 1 = skip consumer maths, 2 = skip producer maths
+    int dbg;                     // timing experiments only (RTDM_BM_DEBUG): 1 = skip the winner-take-all maths
 };
 
 // masks of the uniqueness test: entry rel + 1 (rel = mind - 8 * octet in -1 .. 8) has 0xFFFF in the 16-bit lanes
@@ -356,7 +356,7 @@ bm_sad3_kernel(Bm3Args a)
 
         for (int y = y0; y < y1; y++) {
             if (y - y0 >= 2) bar_sync(3 + (y & 1), NT);            // consumers are done with this buffer (row y - 2)
-            if (((y - y0) & 1) && !(a.dbg & 8)) {
+            if ((y - y0) & 1) {
                 if (wborder) row(y, std::true_type(), std::true_type());
                 else row(y, std::false_type(), std::true_type());
             } else {
@@ -488,7 +488,7 @@ bm_sad3_kernel(Bm3Args a)
                     best = __vimin3_u32(best, v.x, v.y);
                     best = __vimin3_u32(best, v.z, v.w);
                 }
-                const int BIASC = ((a.dbg & 8) ? (y - y0 + 1) : !((y - y0) & 1)) * (2 * H_ + 1) * 128;    // see the producers' row()
+                const int BIASC = ((y - y0) & 1) ? 0 : (2 * H_ + 1) * 128;     // see the producers' row()
                 const int minsad = (int)(best >> 16) - BIASC, oc = (int)(best & 0xFFFFu);
                 // exact position inside the argmin octet (first minimum) via (value << 3 | index) keys
                 int mind;
@@ -542,7 +542,7 @@ bm_sad3_kernel(Bm3Args a)
                     int quo = 0;
                     if (qd != 0) {
                         const int num = adpn * 256;                                 // < 2^24
-                        int t = (a.dbg & 16) ? (int)((float)num * __frcp_rn((float)qd)) : (int)__fdividef((float)num, (float)qd);
+                        int t = (int)__fdividef((float)num, (float)qd);
                         const int rem = num - t * qd;
                         t += rem >= qd ? 1 : 0;
                         t -= rem < 0 ? 1 : 0;
