@@ -150,3 +150,18 @@ def test_sgbm_streaming_submissions(gpu, orc):
     assert np.array_equal(outs[-1], ref[-1])
     op = orc.make_params(P1=600, P2=2400, preFilterCap=0, mode=1, **p)
     assert np.array_equal(ref[0][0], orc.sgbm_compute(batches[0][0][0], batches[0][1][0], op))
+
+
+def test_sgbm_wave_sized_sub_batches_equal_single_frames(gpu):
+    """A 40-frame 720p call runs as wave-sized sub-batches (37 + 3 on 148 SMs): every frame must equal the map the
+    same matcher computes for it alone (sub-batch boundaries, frame offsets of all work buffers)."""
+    from rtdm_b200 import synth
+    W, H, nd, B = 1280, 720, 128, 40
+    fr = [synth.stereo_pair(W, H, nd, 8300 + i) for i in range(5)]
+    L = np.stack([fr[i % 5][0] for i in range(B)]); R = np.stack([fr[i % 5][1] for i in range(B)])
+    m = gpu.CUDASemiGlobalMatcher(5, 0, nd, 10, 100, 32, 1, mode=1, max_width=W, max_height=H, max_batch=B)
+    out = m.compute_batch(L, R)
+    single = [m.compute(fr[i][0], fr[i][1]) for i in range(5)]
+    for k in (0, 1, 17, 36, 37, 38, 39):
+        assert np.array_equal(out[k], single[k % 5]), k
+    assert len({out[k].tobytes() for k in range(0, B, 5)}) == 1            # the same frame at eight batch positions
