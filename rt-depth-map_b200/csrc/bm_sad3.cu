@@ -1,4 +1,4 @@
-// bm_sad3.cu -- warp-specialised Konolige block-matching core (minDisparity == 0, blockSize 5 / 9 / 13,
+// bm_sad3.cu -- warp-specialised Konolige block-matching core (minDisparity == 0, blockSize 5 .. 15,
 // numDisparities 64 / 128).  Same arithmetic as bm_sad.cu / bm_sad2.cu (oracle:
 // orc_bm_core); replaces findStereoCorrespondenceBM as reached from SWMatcherKonolige::compute
 // (reference stereo-matcher/bm-sw.cpp:33-38).
@@ -41,7 +41,7 @@ namespace {
 struct ShapeWide { static constexpr int NCW = 8, NLD = 2, MAXT = 768, MINB = 1, MAXW = 5; };    // MAXW: loader items per lane
 struct ShapePair { static constexpr int NCW = 4, NLD = 1, MAXT = 384, MINB = 2, MAXW = 6; };
 
-__host__ __device__ constexpr int ring_rows3(int h) { return 2 * h + 4 <= 16 ? 16 : 32; }
+__host__ __device__ constexpr int ring_rows3(int h) { return 2 * h + 4; }     // rows y-h-1 .. y+h+2 are live
 
 __device__ __forceinline__ int clampi3(int v, int lo, int hi) { return min(max(v, lo), hi); }
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -65,7 +65,7 @@ __constant__ uint4 c_zmask[10];
 constexpr int MNP = 80;                 // bytes per pixel of the octet-key rows (<= 16 x u32 + pad: conflict-free 128-bit rows)
 struct Geo3 {
     // one buffer: X[NCT] | HA[NG] | HB[NG] | TA[NG] | TB[NG] | zero row (pitch PP each) | Mn[NCT] (pitch MNP)
-    int NCT, PP, BUFSZ, XOFF, HAOFF, HBOFF, TAOFF, TBOFF, ZOFF, MNOFF;
+    int NCT, NCTP, PP, BUFSZ, XOFF, HAOFF, HBOFF, TAOFF, TBOFF, ZOFF, MNOFF;
     int LF, LM, RF, RM, RMX, SLOT;                   // ring slot: byte offsets of the four virtual rows
     int RINGOFF, DESCOFF, NITEM, total;
 };
@@ -74,6 +74,7 @@ __host__ __device__ inline Geo3 make_geo3(int h, int nd, int NG)
     Geo3 q;
     const int G = 2 * h;
     q.NCT = NG * G;
+    q.NCTP = (q.NCT + 3) & ~3;                 // virtual-row length in the ring (odd h: NG * 2h need not be a multiple of 4)
     q.PP = nd * 2 + 16;
     q.XOFF = 0;
     q.HAOFF = q.NCT * q.PP;
@@ -84,17 +85,17 @@ __host__ __device__ inline Geo3 make_geo3(int h, int nd, int NG)
     q.MNOFF = q.ZOFF + q.PP;
     q.BUFSZ = q.MNOFF + q.NCT * MNP;
     q.LF = 0;                                  // left rows are stored EXPANDED: one word = one pixel x 0x01010101
-    q.LM = 4 * q.NCT;
-    q.RF = 8 * q.NCT;
-    const int RFP = q.NCT + nd + 8;
+    q.LM = 4 * q.NCTP;
+    q.RF = 8 * q.NCTP;
+    const int RFP = q.NCTP + nd + 8;
     q.RM = q.RF + RFP;
-    q.RMX = q.NCT + nd + 2;                    // mirrored right row: RMv[n] = Rv[RMX - n];  RMX == 2 (mod 4)
-    const int RMP = q.NCT + nd + 16;
+    q.RMX = q.NCTP + nd + 2;                   // mirrored right row: RMv[n] = Rv[RMX - n];  RMX == 2 (mod 4)
+    const int RMP = q.NCTP + nd + 16;
     q.SLOT = (q.RM + RMP + 15) & ~15;         // 16-byte aligned slots: the expanded left rows move as 128-bit words
     q.RINGOFF = 2 * q.BUFSZ;
     q.DESCOFF = q.RINGOFF + ring_rows3(h) * q.SLOT;
     q.DESCOFF = (q.DESCOFF + 15) & ~15;
-    q.NITEM = q.NCT / 2 + RFP / 4 + RMP / 4;   // loader items: one source word each (left: 4 expanded words out)
+    q.NITEM = q.NCTP / 2 + RFP / 4 + RMP / 4;   // loader items: one source word each (left: 4 expanded words out)
     q.total = q.DESCOFF + q.NITEM * 8;
     return q;
 }
@@ -104,9 +105,9 @@ __host__ __device__ inline Geo3 make_geo3(int h, int nd, int NG)
 //   left items are written as four expanded words (16 bytes), right items as one word
 __device__ __forceinline__ void ring_item_src(const Geo3 &q, int i, int &right, int &cs, int &rev, int &dst)
 {
-    const int nl = q.NCT / 4;
+    const int nl = q.NCTP / 4;
     if (i < nl) { right = 0; rev = 0; cs = 4 * i; dst = q.LF + 16 * i; }
-    else if (i < 2 * nl) { const int m = i - nl; right = 0; rev = 1; cs = q.NCT - 4 - 4 * m; dst = q.LM + 16 * m; }
+    else if (i < 2 * nl) { const int m = i - nl; right = 0; rev = 1; cs = q.NCTP - 4 - 4 * m; dst = q.LM + 16 * m; }
     else {
         const int b = 4 * (i - 2 * nl);               // byte offset from RF
         right = 1; dst = q.RF + b;
@@ -128,7 +129,7 @@ bm_sad3_kernel(Bm3Args a)
 {
     constexpr int NCW = SH::NCW, NLD = SH::NLD;
     constexpr int G = 2 * H_, RING = ring_rows3(H_);
-    constexpr int NLW = H_, NRW = (H_ + 7 + 3) / 4;              // left: one expanded word per column
+    constexpr int NLW = H_, NRW = ((H_ % 2 ? 2 : 0) + H_ + 7 + 3) / 4;   // left: one expanded word per column; right: 8 + h - 1 bytes from a byte offset of 0 (or 2: odd h)
     constexpr int ND = NO_ * 8, PP = ND * 2 + 16;
     extern __shared__ __align__(16) uint8_t smem[];
     const int tid = threadIdx.x, f = blockIdx.z;
@@ -137,7 +138,7 @@ bm_sad3_kernel(Bm3Args a)
     const int y0 = a.row0 + blockIdx.y * a.BH, y1 = min(y0 + a.BH, a.row1);
     if (TWc <= 0 || y0 >= y1) return;
     const Geo3 q = make_geo3(H_, ND, a.NG);
-    const int NPT = ((a.NG * NO_ + 31) / 32) * 64;     // producer threads: whole warps of A halves + as many of B halves
+    const int NPT = 128 * (((a.NG + 1) / 2 + 32 / NO_ - 1) / (32 / NO_));   // producer threads: (A, B) x (even, odd groups) x warps
     const int NT = NPT + NCW * 32;
     uint8_t *Ring = smem + q.RINGOFF;
     int2 *Desc = reinterpret_cast<int2 *>(smem + q.DESCOFF);
@@ -165,7 +166,7 @@ bm_sad3_kernel(Bm3Args a)
 #pragma unroll
             for (int b = 0; b < 4; b++) v |= (uint32_t)src[src_col(right, cs + b)] << (8 * b);
             if (rev) v = __byte_perm(v, 0, 0x0123);
-            ring_store(Ring + (size_t)(gy & (RING - 1)) * q.SLOT, dst, !right, v);
+            ring_store(Ring + (size_t)((gy + RING) % RING) * q.SLOT, dst, !right, v);
         }
         // loader descriptors: x = aligned byte offset of the word pair in the image row (or, for a clamped gather, the
         // first virtual index), y = funnel shift | right image << 8 | byte-reversed << 9 | gather << 10 | dst << 12
@@ -189,14 +190,19 @@ bm_sad3_kernel(Bm3Args a)
         // =========================================================================================
         // producer
         // =========================================================================================
-        // even producer warps hold A halves, odd warps B halves (type-uniform warps: phase 2 differs per type)
-        const int pw = tid >> 5, isB = pw & 1;
-        const int sidx = (pw >> 1) * 32 + (tid & 31);
-        const int g = sidx / NO_, j = sidx - g * NO_;
+        // even producer warps hold A halves, odd warps B halves (type-uniform warps: phase 2 differs per type); within a
+        // type, warps alternate between even and odd groups, so that the byte alignment of a thread's streams (below)
+        // is the same for the whole warp
+        constexpr int SPW = 32 / NO_;                             // groups per warp
+        const int pw = tid >> 5, isB = pw & 1, widx = pw >> 1, par = widx & 1;
+        const int sub = (tid & 31) / NO_, j = (tid & 31) - sub * NO_;
+        const int g = 2 * ((widx >> 1) * SPW + sub) + par;
         const int hg = 2 * g + isB;
-        const bool live = g < a.NG;                       // a trailing half warp may be idle (odd number of groups)
-        // byte offsets of the thread's L and R streams inside a ring slot (both 4-byte aligned)
-        const int lbo = isB ? q.LM + 4 * (q.NCT - (g + 1) * G) : q.LF + 4 * g * G;      // 16-byte aligned
+        const bool live = g < a.NG;                               // trailing groups of the last warps may not exist
+        // byte offsets of the thread's L and R streams inside a ring slot.  The left stream is one word per column; the
+        // right stream starts `off` bytes into a word: 0 when 2h is a multiple of 4, else 0 or 2 by group parity
+        const int lbo = isB ? q.LM + 4 * (q.NCTP - (g + 1) * G) : q.LF + 4 * g * G;
+        const int off = (isB ? q.NCTP - (g + 1) * G : g * G) & 3;                 // warp-uniform
         const int rbo = isB ? q.RM + (q.RMX - (g + 1) * G - 6 - 8 * j) : q.RF + g * G + 8 * j;
         // R clamp (App. A.2, minD = 0): rbase(xc) = clip(xc, 0, W - nd); in virtual columns c = xc - x0 + h
         const int cmin = H_ - x0, cmax = (a.W - ND) - x0 + H_;
@@ -217,17 +223,24 @@ bm_sad3_kernel(Bm3Args a)
         for (int k = 0; k < H_; k++) V[k][0] = V[k][1] = V[k][2] = V[k][3] = 0u;
 
         auto load_words = [&](const uint8_t *slot, uint32_t (&lw)[NLW], uint32_t (&rw)[NRW]) {
-            const uint32_t *rp = reinterpret_cast<const uint32_t *>(slot + rbo);
-            if (H_ >= 4) {
+            const uint32_t *rp = reinterpret_cast<const uint32_t *>(slot + (rbo & ~3));
+            constexpr int W4 = (H_ % 2 == 0 && H_ >= 4) ? 4 : 0;      // even h: the left stream is 16-byte aligned
+            if (W4) {
                 const uint4 t = *reinterpret_cast<const uint4 *>(slot + lbo);
                 lw[0] = t.x; lw[1] = t.y; lw[2] = t.z; lw[3] = t.w;
             }
-            if (H_ % 4 == 2) {
-                const uint2 t = *reinterpret_cast<const uint2 *>(slot + lbo + 4 * (H_ - 2));
-                lw[H_ - 2] = t.x; lw[H_ - 1] = t.y;
+#pragma unroll
+            for (int i = W4; i + 1 < H_; i += 2) {                    // any h: 8-byte aligned
+                const uint2 t = *reinterpret_cast<const uint2 *>(slot + lbo + 4 * i);
+                lw[i] = t.x; lw[i + 1] = t.y;
             }
+            if ((H_ - W4) & 1) lw[H_ - 1] = *reinterpret_cast<const uint32_t *>(slot + lbo + 4 * (H_ - 1));
 #pragma unroll
             for (int i = 0; i < NRW; i++) rw[i] = rp[i];
+            if (H_ % 2 == 1 && off) {                                 // odd h, stream starts 2 bytes into its first word (warp-uniform)
+#pragma unroll
+                for (int i = 0; i < NRW; i++) rw[i] = __funnelshift_r(rw[i], i + 1 < NRW ? rw[i + 1] : 0u, 16);
+            }
         };
         auto clamped_window = [&](const uint8_t *slot, uint32_t &c0w, uint32_t &c1w) {
             const uint32_t *pw = reinterpret_cast<const uint32_t *>(slot + (cbo & ~3));
@@ -250,7 +263,7 @@ bm_sad3_kernel(Bm3Args a)
 
         // vertical sums over rows y0-h-1 .. y0+h-1 (the first loop iteration removes row y0-h-1 again)
         for (int r = y0 - H_ - 1; live && r < y0 + H_; r++) {
-            const uint8_t *slot = Ring + (size_t)(r & (RING - 1)) * q.SLOT;
+            const uint8_t *slot = Ring + (size_t)((r + RING) % RING) * q.SLOT;
             uint32_t lw[NLW], rw[NRW], c0w = 0, c1w = 0;
             load_words(slot, lw, rw);
             if (wborder) clamped_window(slot, c0w, c1w);
@@ -291,8 +304,8 @@ bm_sad3_kernel(Bm3Args a)
             uint8_t *buf = smem + (y & 1) * q.BUFSZ;
             uint4 p = make_uint4(0, 0, 0, 0);
             if (live) {
-                const uint8_t *sin = Ring + (size_t)((y + H_) & (RING - 1)) * q.SLOT;
-                const uint8_t *sout = Ring + (size_t)((y - H_ - 1) & (RING - 1)) * q.SLOT;
+                const uint8_t *sin = Ring + (size_t)((y + H_ + RING) % RING) * q.SLOT;
+                const uint8_t *sout = Ring + (size_t)((y - H_ - 1 + RING) % RING) * q.SLOT;
                 uint32_t lwi[NLW], rwi[NRW], lwo[NLW], rwo[NRW];
                 uint32_t ci0 = 0, ci1 = 0, co0 = 0, co1 = 0;
                 load_words(sin, lwi, rwi);
@@ -407,7 +420,7 @@ bm_sad3_kernel(Bm3Args a)
                 }
                 bar_sync(1 + (y & 1), NT);                      // the producers have finished row y (and its ring reads)
                 if (have_next) {
-                    uint8_t *slot = Ring + (size_t)(gy & (RING - 1)) * q.SLOT;
+                    uint8_t *slot = Ring + (size_t)((gy + RING) % RING) * q.SLOT;
 #pragma unroll
                     for (int s = 0; s < MAXW; s++) {
                         if (meta[s] & 0x800u) {
@@ -584,7 +597,7 @@ int sm_count()
 bool pick_tiling3(const BmGeom &g, int n, Tiling3 *t)
 {
     const int h = g.bs / 2;
-    if (g.minD != 0 || !(h == 2 || h == 4 || h == 6)) return false;
+    if (g.minD != 0 || h < 2 || h > 7) return false;
     if (!(g.nd == 128 || g.nd == 64)) return false;
     const int NO = g.nd / 8, G = 2 * h;
     // RTDM_BM3_SHAPE = 0: one wide CTA per SM, 1: two narrower CTAs per SM
@@ -593,9 +606,11 @@ bool pick_tiling3(const BmGeom &g, int n, Tiling3 *t)
     t->pair = pair;
     const int NCW = pair ? ShapePair::NCW : ShapeWide::NCW, NLD = pair ? ShapePair::NLD : ShapeWide::NLD;
     const int MAXT = pair ? ShapePair::MAXT : ShapeWide::MAXT;
-    const size_t smem_max = pair ? 110 * 1024 : 200 * 1024;
+    const size_t smem_max = pair ? 110 * 1024 : 220 * 1024;
     const int item_max = 32 * (pair ? ShapePair::MAXW : ShapeWide::MAXW);
-    int ngmax = (MAXT - NCW * 32) / 64 * 32 / NO;        // producer threads = whole warps of A halves + as many of B halves
+    // producer warps = (A, B) x (even, odd groups) x wpp, with (32 / NO) groups per warp
+    const int spw = 32 / NO, wpp_max = (MAXT - NCW * 32) / 128;
+    int ngmax = 2 * wpp_max * spw;
     while (ngmax > 2 && ((size_t)make_geo3(h, g.nd, ngmax).total > smem_max || make_geo3(h, g.nd, ngmax).NITEM > item_max * NLD)) ngmax--;   // 320: loader warp, 10 words per lane
     int twmax = std::min(ngmax * G - 2 * h, (NCW - NLD) * 32);
     if (twmax < 16) return false;
@@ -603,7 +618,7 @@ bool pick_tiling3(const BmGeom &g, int n, Tiling3 *t)
     t->TW = cdiv(g.W1, t->nstripes);
     t->NG = cdiv(t->TW + 2 * h, G);
     if (t->NG > ngmax) return false;
-    t->NT = (t->NG * NO + 31) / 32 * 64 + NCW * 32;
+    t->NT = 128 * (((t->NG + 1) / 2 + spw - 1) / spw) + NCW * 32;
     // bands: a band pays ~START rows of start-up (ring prologue, 2h+1 rows of window sums) and the launch runs in waves
     // of (SMs x CTAs per SM) CTAs -> take the band count with the smallest (waves + 1/2) x (band height + START); the
     // half wave stands for the tail (stripes differ a little), and bands stay <= 128 rows: measured, a few long CTAs
@@ -693,19 +708,12 @@ int launch_bm_sad3_core(const BmGeom &g, int n, PlaneU8 Lp, PlaneU8 Rp, PlaneS16
     a.TW = t.TW; a.BH = t.BH; a.NG = t.NG;
     { const char *e = getenv("RTDM_BM_DEBUG"); a.dbg = e ? atoi(e) : 0; }
     const int h = g.bs / 2;
-    if (g.nd == 128) {
-        switch (h) {
-            case 2: rc = launch3<2, 16>(a, t, n, st); break;
-            case 4: rc = launch3<4, 16>(a, t, n, st); break;
-            default: rc = launch3<6, 16>(a, t, n, st); break;
-        }
-    } else {
-        switch (h) {
-            case 2: rc = launch3<2, 8>(a, t, n, st); break;
-            case 4: rc = launch3<4, 8>(a, t, n, st); break;
-            default: rc = launch3<6, 8>(a, t, n, st); break;
-        }
+#define RTDM_SAD3_CASE(H_) case H_: rc = g.nd == 128 ? launch3<H_, 16>(a, t, n, st) : launch3<H_, 8>(a, t, n, st); break
+    switch (h) {
+        RTDM_SAD3_CASE(2); RTDM_SAD3_CASE(3); RTDM_SAD3_CASE(4); RTDM_SAD3_CASE(5); RTDM_SAD3_CASE(6);
+        default: rc = g.nd == 128 ? launch3<7, 16>(a, t, n, st) : launch3<7, 8>(a, t, n, st); break;
     }
+#undef RTDM_SAD3_CASE
     if (rc) return rc;
     RTDM_CUDA(cudaGetLastError());
     return 0;

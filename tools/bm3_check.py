@@ -32,6 +32,9 @@ tot += run(1280, 720, 128, 13, 1000)
 tot += run(640, 480, 128, 13, 5)
 tot += run(640, 480, 128, 9, 6)
 tot += run(640, 480, 64, 5, 7, uniq=0)
+tot += run(640, 480, 128, 15, 9)
+tot += run(333, 200, 64, 7, 10)
+tot += run(1280, 720, 128, 11, 1002)
 tot += run(401, 203, 64, 13, 8, tex=0)
 tot += run(1280, 720, 128, 13, 1001, roi=(100, 50, 934, 404))
 print("TOTAL DIFF", tot)
