@@ -1,5 +1,5 @@
 // bm_sad3.cu -- warp-specialised Konolige block-matching core (minDisparity == 0, blockSize 5 .. 15,
-// numDisparities 64 / 128).  Same arithmetic as bm_sad.cu / bm_sad2.cu (oracle:
+// numDisparities 32 / 64 / 128 / 256).  Same arithmetic as bm_sad.cu / bm_sad2.cu (oracle:
 // orc_bm_core); replaces findStereoCorrespondenceBM as reached from SWMatcherKonolige::compute
 // (reference stereo-matcher/bm-sw.cpp:33-38).
 //
@@ -62,7 +62,8 @@ struct Bm3Args {
 __constant__ uint4 c_zmask[10];
 
 // shared-memory geometry shared by host and device
-constexpr int MNP = 80;                 // bytes per pixel of the octet-key rows (<= 16 x u32 + pad: conflict-free 128-bit rows)
+// bytes per pixel of the octet-key rows: nd / 8 keys of 4 bytes + 16 bytes of padding (conflict-free 128-bit rows)
+__host__ __device__ constexpr int mnp_bytes(int nd) { return nd / 2 + 16; }
 struct Geo3 {
     // one buffer: X[NCT] | HA[NG] | HB[NG] | TA[NG] | TB[NG] | zero row (pitch PP each) | Mn[NCT] (pitch MNP)
     int NCT, NCTP, PP, BUFSZ, XOFF, HAOFF, HBOFF, TAOFF, TBOFF, ZOFF, MNOFF;
@@ -83,7 +84,7 @@ __host__ __device__ inline Geo3 make_geo3(int h, int nd, int NG)
     q.TBOFF = q.TAOFF + NG * q.PP;
     q.ZOFF = q.TBOFF + NG * q.PP;
     q.MNOFF = q.ZOFF + q.PP;
-    q.BUFSZ = q.MNOFF + q.NCT * MNP;
+    q.BUFSZ = q.MNOFF + q.NCT * mnp_bytes(nd);
     q.LF = 0;                                  // left rows are stored EXPANDED: one word = one pixel x 0x01010101
     q.LM = 4 * q.NCTP;
     q.RF = 8 * q.NCTP;
@@ -130,7 +131,7 @@ bm_sad3_kernel(Bm3Args a)
     constexpr int NCW = SH::NCW, NLD = SH::NLD;
     constexpr int G = 2 * H_, RING = ring_rows3(H_);
     constexpr int NLW = H_, NRW = ((H_ % 2 ? 2 : 0) + H_ + 7 + 3) / 4;   // left: one expanded word per column; right: 8 + h - 1 bytes from a byte offset of 0 (or 2: odd h)
-    constexpr int ND = NO_ * 8, PP = ND * 2 + 16;
+    constexpr int ND = NO_ * 8, PP = ND * 2 + 16, MNP = mnp_bytes(ND);
     extern __shared__ __align__(16) uint8_t smem[];
     const int tid = threadIdx.x, f = blockIdx.z;
     const int x0 = blockIdx.x * a.TW;
@@ -598,7 +599,7 @@ bool pick_tiling3(const BmGeom &g, int n, Tiling3 *t)
 {
     const int h = g.bs / 2;
     if (g.minD != 0 || h < 2 || h > 7) return false;
-    if (!(g.nd == 128 || g.nd == 64)) return false;
+    if (!(g.nd == 256 || g.nd == 128 || g.nd == 64 || g.nd == 32)) return false;
     const int NO = g.nd / 8, G = 2 * h;
     // RTDM_BM3_SHAPE = 0: one wide CTA per SM, 1: two narrower CTAs per SM
     int pair = 0;
@@ -708,12 +709,17 @@ int launch_bm_sad3_core(const BmGeom &g, int n, PlaneU8 Lp, PlaneU8 Rp, PlaneS16
     a.TW = t.TW; a.BH = t.BH; a.NG = t.NG;
     { const char *e = getenv("RTDM_BM_DEBUG"); a.dbg = e ? atoi(e) : 0; }
     const int h = g.bs / 2;
-#define RTDM_SAD3_CASE(H_) case H_: rc = g.nd == 128 ? launch3<H_, 16>(a, t, n, st) : launch3<H_, 8>(a, t, n, st); break
+#define RTDM_SAD3_ND(H_) (g.nd == 128 ? launch3<H_, 16>(a, t, n, st) : g.nd == 64 ? launch3<H_, 8>(a, t, n, st) : \
+                          g.nd == 256 ? launch3<H_, 32>(a, t, n, st) : launch3<H_, 4>(a, t, n, st))
     switch (h) {
-        RTDM_SAD3_CASE(2); RTDM_SAD3_CASE(3); RTDM_SAD3_CASE(4); RTDM_SAD3_CASE(5); RTDM_SAD3_CASE(6);
-        default: rc = g.nd == 128 ? launch3<7, 16>(a, t, n, st) : launch3<7, 8>(a, t, n, st); break;
+        case 2: rc = RTDM_SAD3_ND(2); break;
+        case 3: rc = RTDM_SAD3_ND(3); break;
+        case 4: rc = RTDM_SAD3_ND(4); break;
+        case 5: rc = RTDM_SAD3_ND(5); break;
+        case 6: rc = RTDM_SAD3_ND(6); break;
+        default: rc = RTDM_SAD3_ND(7); break;
     }
-#undef RTDM_SAD3_CASE
+#undef RTDM_SAD3_ND
     if (rc) return rc;
     RTDM_CUDA(cudaGetLastError());
     return 0;
