@@ -357,10 +357,12 @@ def run_ours(args):
                            1: "bm_sad_wta_kernel (generic)"}.get(matcher.last_kernel(), "?"),
                 "bound": "int_alu", "achieved": ach, "peak": int_peak, "unit": "Tiop/s",
                 "frac": ach / int_peak,
-                # ncu dram__bytes_read.sum + dram__bytes_write.sum of one bm_sad3_kernel launch of 16 frames:
-                # 59.1 + 14.7 MB (profiles/r01_prof_bm3_f_summary.csv) = 4.61 MB per frame (algorithmic: 3.69 MB)
-                "traffic": 4.61e6 * B if matcher.last_kernel() == 3 else (4.7e6 * B if matcher.last_kernel() == 2 else None),
-                "traffic_note": "per launch of B frames, scaled from the 16-frame ncu capture under profiles/",
+                # ncu dram__bytes_read.sum + dram__bytes_write.sum of one bm_sad3_kernel launch of 63 frames (capture H,
+                # profiles/r01_prof_bm3_h_summary.csv): 235.5 + 172.9 MB = 6.48 MB per frame -- the kernel reads the two
+                # prefiltered images and the texture sums (3.7 MB) and writes raw disparity + cost (3.7 MB, part of it still
+                # in L2 when the launch ends); the 4 B/pixel of SURVEY 8(d) count the path's own inputs and output only
+                "traffic": 6.48e6 * B if matcher.last_kernel() == 3 else (4.7e6 * B if matcher.last_kernel() == 2 else None),
+                "traffic_note": "per launch of B frames, scaled from the 63-frame ncu capture under profiles/ (capture H)",
                 "ops_per_de": OPS_PER_DE[wl], "kernel_ms_per_launch": k_ms, "frames_per_launch": B,
                 "kernel_share_of_step": stage_ms["sad_wta"] / stage_calls / (ms / args.steps),
                 "peak_source": "rtdm_measure_int_peak on this GPU (dependent-free IADD3, lane-ops/s)",
