@@ -1,5 +1,5 @@
 // bm_sad3.cu -- warp-specialised Konolige block-matching core (minDisparity == 0, blockSize 5 .. 15,
-// numDisparities 32 / 64 / 128 / 256).  Same arithmetic as bm_sad.cu / bm_sad2.cu (oracle:
+// numDisparities 32 / 48 / 64 / 96 / 128 / 192 / 256; the reference's default is 192 scaled by the frame width).  Same arithmetic as bm_sad.cu / bm_sad2.cu (oracle:
 // orc_bm_core); replaces findStereoCorrespondenceBM as reached from SWMatcherKonolige::compute
 // (reference stereo-matcher/bm-sw.cpp:33-38).
 //
@@ -62,8 +62,9 @@ struct Bm3Args {
 __constant__ uint4 c_zmask[10];
 
 // shared-memory geometry shared by host and device
-// bytes per pixel of the octet-key rows: nd / 8 keys of 4 bytes + 16 bytes of padding (conflict-free 128-bit rows)
-__host__ __device__ constexpr int mnp_bytes(int nd) { return nd / 2 + 16; }
+// bytes per pixel of the octet-key rows: nd / 8 keys of 4 bytes, rounded up to whole 128-bit words (the spare keys stay
+// 0xFFFFFFFF), padded to an ODD number of 16-byte units so that 128-bit rows of 8 neighbouring pixels hit 8 bank groups
+__host__ __device__ constexpr int mnp_bytes(int nd) { return (((nd / 2 + 15) / 16) | 1) * 16; }
 struct Geo3 {
     // one buffer: X[NCT] | HA[NG] | HB[NG] | TA[NG] | TB[NG] | zero row (pitch PP each) | Mn[NCT] (pitch MNP)
     int NCT, NCTP, PP, BUFSZ, XOFF, HAOFF, HBOFF, TAOFF, TBOFF, ZOFF, MNOFF;
@@ -184,6 +185,11 @@ bm_sad3_kernel(Bm3Args a)
             reinterpret_cast<uint32_t *>(smem + q.ZOFF)[i] = 0u;
             reinterpret_cast<uint32_t *>(smem + q.BUFSZ + q.ZOFF)[i] = 0u;
         }
+        if (NO_ % 4)                                            // spare keys of the last 128-bit word of every key row
+            for (int i = tid; i < q.NCT * (MNP / 4); i += NT) {
+                reinterpret_cast<uint32_t *>(smem + q.MNOFF)[i] = 0xFFFFFFFFu;
+                reinterpret_cast<uint32_t *>(smem + q.BUFSZ + q.MNOFF)[i] = 0xFFFFFFFFu;
+            }
     }
     __syncthreads();
 
@@ -199,7 +205,7 @@ bm_sad3_kernel(Bm3Args a)
         const int sub = (tid & 31) / NO_, j = (tid & 31) - sub * NO_;
         const int g = 2 * ((widx >> 1) * SPW + sub) + par;
         const int hg = 2 * g + isB;
-        const bool live = g < a.NG;                               // trailing groups of the last warps may not exist
+        const bool live = g < a.NG && sub < SPW;                  // trailing groups may not exist; 32 % NO_ lanes of a warp stay idle
         // byte offsets of the thread's L and R streams inside a ring slot.  The left stream is one word per column; the
         // right stream starts `off` bytes into a word: 0 when 2h is a multiple of 4, else 0 or 2 by group parity
         const int lbo = isB ? q.LM + 4 * (q.NCTP - (g + 1) * G) : q.LF + 4 * g * G;
@@ -497,7 +503,7 @@ bm_sad3_kernel(Bm3Args a)
                 uint32_t *s32 = reinterpret_cast<uint32_t *>(s4);
                 uint32_t best = 0xFFFFFFFFu;
 #pragma unroll
-                for (int k = 0; k < NO_ / 4; k++) {
+                for (int k = 0; k < (NO_ + 3) / 4; k++) {
                     const uint4 v = s4[k];
                     best = __vimin3_u32(best, v.x, v.y);
                     best = __vimin3_u32(best, v.z, v.w);
@@ -533,7 +539,7 @@ bm_sad3_kernel(Bm3Args a)
                     s32[ohi] = 0xFFFFFFFFu;
                     uint32_t m2 = 0xFFFFFFFFu;
 #pragma unroll
-                    for (int k = 0; k < NO_ / 4; k++) {
+                    for (int k = 0; k < (NO_ + 3) / 4; k++) {
                         const uint4 v = s4[k];
                         m2 = __vimin3_u32(m2, v.x, v.y);
                         m2 = __vimin3_u32(m2, v.z, v.w);
@@ -599,11 +605,11 @@ bool pick_tiling3(const BmGeom &g, int n, Tiling3 *t)
 {
     const int h = g.bs / 2;
     if (g.minD != 0 || h < 2 || h > 7) return false;
-    if (!(g.nd == 256 || g.nd == 128 || g.nd == 64 || g.nd == 32)) return false;
+    if (!(g.nd == 256 || g.nd == 192 || g.nd == 128 || g.nd == 96 || g.nd == 64 || g.nd == 48 || g.nd == 32)) return false;
     const int NO = g.nd / 8, G = 2 * h;
     // RTDM_BM3_SHAPE = 0: one wide CTA per SM, 1: two narrower CTAs per SM
     int pair = 0;
-    if (const char *e = getenv("RTDM_BM3_SHAPE")) pair = atoi(e) ? 1 : 0;
+    if (const char *e = getenv("RTDM_BM3_SHAPE")) pair = (atoi(e) && (g.nd == 64 || g.nd == 128)) ? 1 : 0;
     t->pair = pair;
     const int NCW = pair ? ShapePair::NCW : ShapeWide::NCW, NLD = pair ? ShapePair::NLD : ShapeWide::NLD;
     const int MAXT = pair ? ShapePair::MAXT : ShapeWide::MAXT;
@@ -673,7 +679,8 @@ int launch3s(const Bm3Args &a, const Tiling3 &t, int n, cudaStream_t st)
 template <int H_, int NO_>
 int launch3(const Bm3Args &a, const Tiling3 &t, int n, cudaStream_t st)
 {
-    return t.pair ? launch3s<H_, NO_, ShapePair>(a, t, n, st) : launch3s<H_, NO_, ShapeWide>(a, t, n, st);
+    if constexpr (NO_ == 8 || NO_ == 16) { if (t.pair) return launch3s<H_, NO_, ShapePair>(a, t, n, st); }
+    return launch3s<H_, NO_, ShapeWide>(a, t, n, st);
 }
 
 }  // namespace
@@ -710,7 +717,8 @@ int launch_bm_sad3_core(const BmGeom &g, int n, PlaneU8 Lp, PlaneU8 Rp, PlaneS16
     { const char *e = getenv("RTDM_BM_DEBUG"); a.dbg = e ? atoi(e) : 0; }
     const int h = g.bs / 2;
 #define RTDM_SAD3_ND(H_) (g.nd == 128 ? launch3<H_, 16>(a, t, n, st) : g.nd == 64 ? launch3<H_, 8>(a, t, n, st) : \
-                          g.nd == 256 ? launch3<H_, 32>(a, t, n, st) : launch3<H_, 4>(a, t, n, st))
+                          g.nd == 192 ? launch3<H_, 24>(a, t, n, st) : g.nd == 96 ? launch3<H_, 12>(a, t, n, st) : \
+                          g.nd == 48 ? launch3<H_, 6>(a, t, n, st) : g.nd == 256 ? launch3<H_, 32>(a, t, n, st) : launch3<H_, 4>(a, t, n, st))
     switch (h) {
         case 2: rc = RTDM_SAD3_ND(2); break;
         case 3: rc = RTDM_SAD3_ND(3); break;

@@ -48,7 +48,7 @@ int launch_bm_sad_wta(const BmGeom &g, int n, PlaneU8 Lp, PlaneU8 Rp, PlaneS16 d
 bool bm_sad2_supported(const BmGeom &g, int n);
 int launch_bm_sad2(const BmGeom &g, int n, PlaneU8 Lp, PlaneU8 Rp, PlaneS16 disp, PlaneS16 cost,
                    uint16_t *tex, size_t tex_pitch, size_t tex_frame, cudaStream_t st, int *launches, bool use3 = false);
-// warp-specialised fast path (bm_sad3.cu): minDisparity == 0, blockSize 5 .. 15, numDisparities 32 / 64 / 128 / 256
+// warp-specialised fast path (bm_sad3.cu): minDisparity == 0, blockSize 5 .. 15, numDisparities 32 / 48 / 64 / 96 / 128 / 192 / 256
 bool bm_sad3_supported(const BmGeom &g, int n);
 long long bm_sad3_cost(const BmGeom &g, int n);
 int launch_bm_sad3_core(const BmGeom &g, int n, PlaneU8 Lp, PlaneU8 Rp, PlaneS16 disp, PlaneS16 cost,

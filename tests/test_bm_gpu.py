@@ -27,7 +27,7 @@ def bm_kernel(request, monkeypatch):
 def _expected_kernel(bm_kernel, p):
     if bm_kernel == "generic" or p["blockSize"] > 15 or p["minDisparity"] != 0:
         return 1
-    if bm_kernel == "fast" and p["numDisparities"] in (32, 64, 128, 256):
+    if bm_kernel == "fast" and p["numDisparities"] in (32, 48, 64, 96, 128, 192, 256):
         return 3
     return 2
 
@@ -114,9 +114,10 @@ def test_bm_random_params_match_oracle(gpu, orc, bm_kernel):
 
 
 @pytest.mark.parametrize("bs", [5, 7, 9, 11, 13, 15])
-@pytest.mark.parametrize("nd", [32, 64, 128, 256])
+@pytest.mark.parametrize("nd", [32, 48, 64, 96, 128, 192, 256])
 def test_bm_warp_specialised_kernel_matrix(gpu, orc, nd, bs):
-    """bm_sad3.cu over its whole domain (blockSize 5 .. 15 x numDisparities 32 / 64 / 128 / 256): stripe borders (clamped
+    """bm_sad3.cu over its whole domain (blockSize 5 .. 15 x numDisparities 32 / 48 / 64 / 96 / 128 / 192 / 256;
+    192, 96 and 48 are what the reference's default -nd 192 scales to at 1280, 640 and 320 pixels of width): stripe borders (clamped
     columns on both image sides), widths that are not a multiple of anything, odd heights, ROIs, texture and
     uniqueness thresholds on and off, and every prefilter cap parity; raw WTA output and cost against the oracle's
     core as well as the final map."""

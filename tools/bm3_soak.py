@@ -10,7 +10,7 @@ rng = np.random.default_rng(int(sys.argv[1]) if len(sys.argv) > 1 else 1)
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 120
 bad = 0
 for t in range(N):
-    nd = int(rng.choice([32, 64, 128, 256])); bs = int(rng.choice([5, 7, 9, 11, 13, 15]))
+    nd = int(rng.choice([32, 48, 64, 96, 128, 192, 256])); bs = int(rng.choice([5, 7, 9, 11, 13, 15]))
     W = int(rng.integers(nd + bs + 2, 1500)); H = int(rng.integers(bs + 2, 260))
     if t % 7 == 0: W = nd - 1 + int(rng.choice([165, 166, 180, 181, 330, 331, 1153]))     # stripe-width boundaries
     B = int(rng.integers(1, 6))

@@ -3,7 +3,7 @@ sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/rt-depth-map_b2
 import numpy as np, torch
 import rtdm_b200 as rt
 from rtdm_b200 import synth
-for (W, H, nd, bs) in [(1280, 720, 256, 13), (1280, 720, 32, 13), (1280, 720, 128, 15), (1280, 720, 64, 9)]:
+for (W, H, nd, bs) in [(1280, 720, 192, 13), (640, 480, 96, 13), (320, 240, 48, 13), (1280, 720, 256, 13), (1280, 720, 32, 13), (1280, 720, 128, 15), (1280, 720, 64, 9)]:
     B = 16
     fr = [synth.stereo_pair(W, H, nd, 1000 + i) for i in range(2)]
     L = torch.from_numpy(np.stack([fr[i % 2][0] for i in range(B)])).cuda(); R = torch.from_numpy(np.stack([fr[i % 2][1] for i in range(B)])).cuda()
