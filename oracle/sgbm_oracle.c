@@ -232,7 +232,9 @@ int orc_sgbm_compute(const uint8_t *left, int lstep, const uint8_t *right, int r
 #pragma omp for schedule(static) reduction(| : outside)
             for (int y = 0; y < H; y++) {
                 int16_t *drow = disp + (size_t)y * dstep;
-                for (int x = 0; x < W; x++) { disp2[x] = INV; cost2[x] = 32767; }
+                /* cv2 initialises disp2 with the x16-SCALED invalid value (minD - 1) * 16, which for minD >= 2 passes the
+                 * `disp2 >= minD` test of the LR check below: unset entries then count as a (mismatching) disparity */
+                for (int x = 0; x < W; x++) { disp2[x] = INVS; cost2[x] = 32767; }
                 for (int x = W1 - 1; x >= 0; x--) {
                     const int16_t *Sp = S + ((size_t)y * W1 + x) * D;
                     int minS = 32767, best = -1;

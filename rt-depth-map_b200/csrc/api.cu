@@ -18,6 +18,31 @@ namespace rtdm {
 static thread_local std::string g_err;
 void set_error(const std::string &msg) { g_err = msg; }
 
+// the one place the library looks at the environment (see common.cuh: Switches); called by rtdm_*_create
+Switches read_switches()
+{
+    Switches sw;
+    auto geti = [](const char *name, int dflt) { const char *e = getenv(name); return e && *e ? atoi(e) : dflt; };
+    auto isset = [](const char *name) { const char *e = getenv(name); return (e && *e) ? 1 : 0; };
+    sw.bm_kernel = geti("RTDM_BM_KERNEL", 0);
+    sw.bm3_shape = geti("RTDM_BM3_SHAPE", 0);
+    sw.bm_chunk = geti("RTDM_BM_CHUNK", 0);
+    sw.bm_variant = geti("RTDM_BM_VARIANT", 1);
+    sw.bm_occ3 = isset("RTDM_BM_OCC3");
+    sw.bm_nofuse = isset("RTDM_BM_NOFUSE");
+#ifdef RTDM_DEV
+    sw.bm_debug = geti("RTDM_BM_DEBUG", 0);
+#endif
+    sw.speckle_scalar = isset("RTDM_SPECKLE_SCALAR");
+    sw.post_unfused = isset("RTDM_POST_UNFUSED");
+    sw.sgbm_oldcost = isset("RTDM_SGBM_OLDCOST");
+    sw.sgbm_oldpath = isset("RTDM_SGBM_OLDPATH");
+    sw.sgbm_nofuse = isset("RTDM_SGBM_NOFUSE");
+    sw.sgbm_nosweep = isset("RTDM_SGBM_NOSWEEP");
+    sw.sgbm_sweep_rows = geti("RTDM_SGBM_SWEEP_ROWS", 0);
+    return sw;
+}
+
 int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
 {
     char buf[512];
@@ -80,6 +105,7 @@ using namespace rtdm;
 // =================================================================================================
 struct rtdm_bm {
     rtdm_params p;
+    Switches sw;                 // development switches as they were when the handle was created
     int maxW, maxH, maxB, dev;
     cudaStream_t st;
     cudaStream_t lane[3];        // streams of the chunked host-batch pipeline (copy/compute overlap)
@@ -88,6 +114,7 @@ struct rtdm_bm {
     int16_t *raw, *cost;         size_t rpitch, rframe;      // raw WTA disparity + cost (elements)
     int32_t *labels, *sizes, *runlen;
     uint16_t *tex;                                           // texture window sums (rpitch / rframe)
+    int16_t *spill;                                          // minDisparity > 0: [maxB][minD], see BmGeom::spill
     // staging for the host entry points
     uint8_t *dL, *dR;            size_t spitch, sframe;      // device copies of the inputs  (staging set 0)
     int16_t *dD;                 size_t dpitch, dframe;      // device copy of the output (elements)
@@ -157,6 +184,7 @@ extern "C" void rtdm_bm_destroy(rtdm_bm *h)
     cudaSetDevice(h->dev);
     cudaFree(h->Lp); cudaFree(h->Rp); cudaFree(h->raw); cudaFree(h->cost);
     cudaFree(h->labels); cudaFree(h->sizes); cudaFree(h->runlen); cudaFree(h->dL); cudaFree(h->dR); cudaFree(h->dD); cudaFree(h->tex);
+    cudaFree(h->spill);
     cudaFree(h->dL2); cudaFree(h->dR2); cudaFree(h->dD2);
     for (int i = 0; i < 2; i++) if (h->done[i]) cudaEventDestroy(h->done[i]);
     if (h->ev) { for (cudaEvent_t e : *h->ev) cudaEventDestroy(e); delete h->ev; }
@@ -180,10 +208,10 @@ extern "C" int rtdm_bm_create(rtdm_bm **out, const rtdm_params *p, int max_width
     rc = check_device(device);
     if (rc) return rc;
     RTDM_CUDA(cudaSetDevice(device));
-    rtdm_bm *h = new (std::nothrow) rtdm_bm();
+    rtdm_bm *h = new (std::nothrow) rtdm_bm();      // value-initialised: every member zero, switches at their defaults
     if (!h) return -RTDM_ENOMEM;
-    memset(h, 0, sizeof *h);
     h->p = *p; h->maxW = max_width; h->maxH = max_height; h->maxB = max_batch; h->dev = device;
+    h->sw = read_switches();
     const size_t B = (size_t)max_batch;
     h->ppitch = align_up((size_t)max_width + 160, 64);          // over-read slack for the band loader
     h->pframe = h->ppitch * max_height;
@@ -198,6 +226,7 @@ extern "C" int rtdm_bm_create(rtdm_bm **out, const rtdm_params *p, int max_width
     if (!rc) rc = dev_alloc(&h->raw, h->rframe * B);
     if (!rc) rc = dev_alloc(&h->cost, h->rframe * B);
     if (!rc) rc = dev_alloc(&h->tex, h->rframe * B);
+    if (!rc && p->minDisparity > 0) rc = dev_alloc(&h->spill, (size_t)p->minDisparity * B);
     if (!rc) rc = dev_alloc(&h->labels, (size_t)max_width * max_height * B);
     if (!rc) rc = dev_alloc(&h->sizes, (size_t)max_width * max_height * B);
     if (!rc) rc = dev_alloc(&h->runlen, (size_t)max_width * max_height * B);
@@ -228,10 +257,12 @@ extern "C" int rtdm_bm_set_roi2(rtdm_bm *h, int x, int y, int w, int hgt)
     return 0;
 }
 
-static BmGeom bm_geom(const rtdm_params &p, int W, int H, ValidRect *vrout = nullptr)
+static BmGeom bm_geom(const rtdm_bm *h, int W, int H, ValidRect *vrout = nullptr)
 {
+    const rtdm_params &p = h->p;
     const int nd = p.numDisparities, minD = p.minDisparity;
     BmGeom g;
+    g.sw = h->sw;
     g.W = W; g.H = H; g.nd = nd; g.minD = minD; g.bs = p.blockSize; g.cap = p.preFilterCap;
     g.texThr = p.textureThreshold; g.uniq = p.uniquenessRatio;
     g.lofs = std::max(nd - 1 + minD, 0); g.rofs = -std::min(nd - 1 + minD, 0);
@@ -251,9 +282,8 @@ static int bm_chunk_for(const rtdm_bm *h, int n, int W, int H)
 {
     int chunk = n >= 64 ? 32 : (n >= 32 ? 16 : (n >= 8 ? (n + 3) / 4 : n));
     if (n < 16 || h->p.blockSize >= W || h->p.blockSize >= H) return chunk;
-    const BmGeom g = bm_geom(h->p, W, H);
-    const char *force = getenv("RTDM_BM_KERNEL");
-    if (force && (force[0] == '1' || force[0] == '2')) return chunk;
+    const BmGeom g = bm_geom(h, W, H);
+    if (h->sw.bm_kernel == 1 || h->sw.bm_kernel == 2) return chunk;
     long long best = -1;
     for (int m = std::max(8, n / 4); m < n; m++) {
         const int k = (n + m - 1) / m, last = n - (k - 1) * m;
@@ -279,15 +309,11 @@ static int bm_pipeline(rtdm_bm *h, int n, PlaneU8 L, PlaneU8 R, int W, int H, Pl
     h->lastW = W; h->lastH = H;
     const int nd = p.numDisparities, minD = p.minDisparity;
     const int FILT = (minD - 1) * 16;
-    BmGeom g;
-    g.W = W; g.H = H; g.nd = nd; g.minD = minD; g.bs = p.blockSize; g.cap = p.preFilterCap;
-    g.texThr = p.textureThreshold; g.uniq = p.uniquenessRatio;
-    g.lofs = std::max(nd - 1 + minD, 0); g.rofs = -std::min(nd - 1 + minD, 0);
-    g.W1 = W - g.rofs - nd + 1;
-    ValidRect vr = valid_rect(p.roi1, p.roi2, W, H, minD, nd, p.blockSize);
-    int row0 = std::min(std::max(vr.y, 0), H), row1 = std::min(std::max(vr.y + vr.h, 0), H);
-    if (vr.w == 0 || vr.h == 0 || g.lofs >= W || g.rofs >= W || g.W1 < 1) row0 = row1 = 0;
-    g.row0 = row0; g.row1 = row1;
+    ValidRect vr;
+    BmGeom g = bm_geom(h, W, H, &vr);
+    const int row0 = g.row0, row1 = g.row1;
+    // minDisparity > 0: what the last computed row writes past its end lands in row `row1` (App. B.3)
+    if (h->spill && row1 > row0 && row1 < H) g.spill = h->spill + (size_t)f0 * minD;
     int rc = 0;
     auto mark = [&]() {
         if (!h->prof) return;
@@ -308,11 +334,10 @@ static int bm_pipeline(rtdm_bm *h, int n, PlaneU8 L, PlaneU8 R, int W, int H, Pl
         if (rc) return rc;
         mark();
         PlaneU8 iL = {wLp, h->ppitch, h->pframe}, iR = {wRp, h->ppitch, h->pframe};
-        // RTDM_BM_KERNEL=1 forces the generic kernel (A/B runs and tests); default: fast path when it applies
-        const char *force = getenv("RTDM_BM_KERNEL");
-        const bool fast = !(force && force[0] == '1') && bm_sad2_supported(g, n);
-        // RTDM_BM_KERNEL=2 keeps the bm_sad2.cu kernel where the warp-specialised bm_sad3.cu kernel would apply
-        const bool fast3 = fast && !(force && force[0] == '2') && bm_sad3_supported(g, n);
+        // Switches::bm_kernel = 1 forces the generic kernel (A/B runs and tests); default: fast path when it applies
+        const bool fast = h->sw.bm_kernel != 1 && bm_sad2_supported(g, n);
+        // bm_kernel = 2 keeps the bm_sad2.cu kernel where the warp-specialised bm_sad3.cu kernel would apply
+        const bool fast3 = fast && h->sw.bm_kernel != 2 && bm_sad3_supported(g, n);
         if (fast)
             rc = launch_bm_sad2(g, n, iL, iR, raw, cost, h->tex + (size_t)f0 * h->rframe, h->rpitch, h->rframe, st, &h->launches, fast3);
         else
@@ -326,7 +351,7 @@ static int bm_pipeline(rtdm_bm *h, int n, PlaneU8 L, PlaneU8 R, int W, int H, Pl
     rc = launch_validate_speckle(n, W, H, minD, nd, p.disp12MaxDiff, g.lofs, g.W1, std::max(vr.x, 0), std::max(vr.x + vr.w, 0),
                                  row0, row1, raw, cost, out, p.speckleRange >= 0 && p.speckleWindowSize > 0, FILT,
                                  p.speckleWindowSize, p.speckleRange, wlab, wsiz, wrun, st, &h->launches,
-                                 [](void *c) { (*static_cast<Hook *>(c)->m)(); }, &hook);
+                                 [](void *c) { (*static_cast<Hook *>(c)->m)(); }, &hook, g.spill, h->sw);
     mark();
     return rc;
 }
@@ -398,29 +423,20 @@ extern "C" int rtdm_bm_wait_oldest(rtdm_bm *h)
     return 0;
 }
 
-extern "C" int rtdm_bm_submit_batch(rtdm_bm *h, int n, const uint8_t *left, size_t lstep, size_t lframe,
-                                    const uint8_t *right, size_t rstep, size_t rframe, int width, int height,
-                                    int16_t *disp, size_t dstep, size_t dframe)
+// enqueues one host batch on staging set `set`; any failure returns at once -- the caller drains the streams
+static int bm_enqueue_batch(rtdm_bm *h, int set, int n, const uint8_t *left, size_t lstep, size_t lframe,
+                            const uint8_t *right, size_t rstep, size_t rframe, int width, int height,
+                            int16_t *disp, size_t dstep, size_t dframe)
 {
-    if (!h || !left || !right || !disp) { set_error("bm_compute: null argument"); return -RTDM_EINVAL; }
-    if (n < 1 || n > h->maxB || width > h->maxW || height > h->maxH || width < 1 || height < 1) {
-        set_error("bm: frame geometry or batch exceeds what the handle was created for");
-        return -RTDM_EINVAL;
-    }
-    RTDM_CUDA(cudaSetDevice(h->dev));
-    h->launches = 0;
     // three-stage pipeline over chunks of frames: H2D on lane[0], kernels on the handle's stream, D2H on lane[1],
     // chained by events.  The kernels always see whole chunks in order (no concurrent kernels from different
     // chunks fighting for the SMs); the copies of chunk c+1 / c-1 overlap the kernels of chunk c.
     // the SAD kernel is ~12 % more efficient on 32-frame launches than on 16-frame ones (fuller waves)
     int chunk = bm_chunk_for(h, n, width, height);
-    if (const char *e = getenv("RTDM_BM_CHUNK")) chunk = std::max(1, std::min(n, atoi(e)));
+    if (h->sw.bm_chunk > 0) chunk = std::max(1, std::min(n, h->sw.bm_chunk));
     const int nchunks = (n + chunk - 1) / chunk;
     if (!h->pev) h->pev = new std::vector<cudaEvent_t>();
     cudaStream_t s_in = h->lane[0], s_out = h->lane[1], s_cmp = h->st;
-    // staging set of this call; wait (host side) for the call that used it two submissions ago
-    const int set = (int)(h->seq++ & 1u);
-    if (h->busy[set]) { RTDM_CUDA(cudaEventSynchronize(h->done[set])); h->busy[set] = 0; }
     uint8_t *sL = set ? h->dL2 : h->dL, *sR = set ? h->dR2 : h->dR;
     int16_t *sD = set ? h->dD2 : h->dD;
     while ((int)h->pev->size() < 4 * nchunks) {
@@ -432,8 +448,9 @@ extern "C" int rtdm_bm_submit_batch(rtdm_bm *h, int n, const uint8_t *left, size
     for (int c = 0; c < nchunks && !rc; c++) {
         const int f0 = c * chunk, m = std::min(chunk, n - f0);
         cudaEvent_t ev_in = (*h->pev)[2 * (set * nchunks + c)], ev_done = (*h->pev)[2 * (set * nchunks + c) + 1];
-        const bool lpacked = lstep == (size_t)width && h->spitch == (size_t)width && lframe == h->sframe;
-        const bool rpacked = rstep == (size_t)width && h->spitch == (size_t)width && rframe == h->sframe;
+        // one contiguous copy when the caller's frames are laid out like the staging planes (a single frame has no frame step)
+        const bool lpacked = lstep == (size_t)width && h->spitch == (size_t)width && (n == 1 || lframe == h->sframe);
+        const bool rpacked = rstep == (size_t)width && h->spitch == (size_t)width && (n == 1 || rframe == h->sframe);
         if (lpacked) RTDM_CUDA(cudaMemcpyAsync(sL + f0 * h->sframe, left + f0 * lframe, (size_t)m * h->sframe, cudaMemcpyHostToDevice, s_in));
         if (rpacked) RTDM_CUDA(cudaMemcpyAsync(sR + f0 * h->sframe, right + f0 * rframe, (size_t)m * h->sframe, cudaMemcpyHostToDevice, s_in));
         for (int k = f0; k < f0 + m; k++) {
@@ -450,16 +467,40 @@ extern "C" int rtdm_bm_submit_batch(rtdm_bm *h, int n, const uint8_t *left, size
         if (rc) break;
         RTDM_CUDA(cudaEventRecord(ev_done, s_cmp));
         RTDM_CUDA(cudaStreamWaitEvent(s_out, ev_done, 0));
-        const bool dpacked = dstep == (size_t)width * 2 && h->dpitch == (size_t)width && dframe == h->dframe * 2;
-        if (dpacked) RTDM_CUDA(cudaMemcpyAsync((uint8_t *)disp + f0 * dframe, sD + f0 * h->dframe, (size_t)m * dframe, cudaMemcpyDeviceToHost, s_out));
+        const bool dpacked = dstep == (size_t)width * 2 && h->dpitch == (size_t)width && (n == 1 || dframe == h->dframe * 2);
+        if (dpacked) RTDM_CUDA(cudaMemcpyAsync((uint8_t *)disp + f0 * dframe, sD + f0 * h->dframe, (size_t)m * h->dframe * 2, cudaMemcpyDeviceToHost, s_out));
         else for (int k = f0; k < f0 + m; k++)
             RTDM_CUDA(cudaMemcpy2DAsync((uint8_t *)disp + k * dframe, dstep, sD + k * h->dframe, h->dpitch * 2,
                                         (size_t)width * 2, height, cudaMemcpyDeviceToHost, s_out));
     }
-    if (rc) { rtdm_bm_wait(h); return rc; }
+    if (rc) return rc;
     RTDM_CUDA(cudaEventRecord(h->done[set], s_out));          // after the last D2H of this call
     h->busy[set] = 1;
     return 0;
+}
+
+extern "C" int rtdm_bm_submit_batch(rtdm_bm *h, int n, const uint8_t *left, size_t lstep, size_t lframe,
+                                    const uint8_t *right, size_t rstep, size_t rframe, int width, int height,
+                                    int16_t *disp, size_t dstep, size_t dframe)
+{
+    if (!h || !left || !right || !disp) { set_error("bm_compute: null argument"); return -RTDM_EINVAL; }
+    if (n < 1 || n > h->maxB || width > h->maxW || height > h->maxH || width < 1 || height < 1) {
+        set_error("bm: frame geometry or batch exceeds what the handle was created for");
+        return -RTDM_EINVAL;
+    }
+    RTDM_CUDA(cudaSetDevice(h->dev));
+    h->launches = 0;
+    // staging set of this call; wait (host side) for the call that used it two submissions ago
+    const int set = (int)(h->seq++ & 1u);
+    if (h->busy[set]) { RTDM_CUDA(cudaEventSynchronize(h->done[set])); h->busy[set] = 0; }
+    const int rc = bm_enqueue_batch(h, set, n, left, lstep, lframe, right, rstep, rframe, width, height, disp, dstep, dframe);
+    if (rc) {
+        // copies to or from the caller's buffers may already be in flight: never return before they have drained
+        const std::string why = rtdm_last_error();
+        rtdm_bm_wait(h);
+        set_error(why);
+    }
+    return rc;
 }
 
 extern "C" int rtdm_bm_compute_batch(rtdm_bm *h, int n, const uint8_t *left, size_t lstep, size_t lframe,
@@ -490,7 +531,7 @@ extern "C" int rtdm_bm_speckle_device(rtdm_bm *h, int n, int16_t *disp, size_t d
     if (!(h->p.speckleRange >= 0 && h->p.speckleWindowSize > 0)) return 0;
     const int FILT = (h->p.minDisparity - 1) * 16;
     return launch_speckle(n, width, height, PlaneS16{disp, dstep / 2, dframe / 2}, FILT, h->p.speckleWindowSize, h->p.speckleRange,
-                          h->labels, h->sizes, static_cast<cudaStream_t>(cuda_stream), &h->launches, h->runlen);
+                          h->labels, h->sizes, cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->st, &h->launches, h->runlen, h->sw);
 }
 
 extern "C" int rtdm_bm_last_launches(const rtdm_bm *h) { return h ? h->launches : 0; }
@@ -517,6 +558,7 @@ extern "C" int rtdm_bm_debug_fetch(rtdm_bm *h, int what, void *dst, size_t dst_b
 // =================================================================================================
 struct rtdm_sgbm {
     rtdm_params p;
+    Switches sw;                 // development switches as they were when the handle was created
     int maxW, maxH, maxB, dev;
     int volB;                    // frames the cost volumes are sized for (sub-batches of the call)
     cudaStream_t st;
@@ -547,9 +589,10 @@ static int sgbm_check_params(const rtdm_params *p)
     return 0;
 }
 
-static SgbmGeom sgbm_geom(const rtdm_params &p, int W, int H)
+static SgbmGeom sgbm_geom(const rtdm_params &p, const Switches &sw, int W, int H)
 {
     SgbmGeom g;
+    g.sw = sw;
     g.W = W; g.H = H; g.D = p.numDisparities; g.minD = p.minDisparity; g.bs = p.blockSize;
     g.P1 = p.P1 > 0 ? p.P1 : 2; g.P2 = std::max(p.P2 > 0 ? p.P2 : 5, g.P1 + 1);
     g.uniq = p.uniquenessRatio >= 0 ? p.uniquenessRatio : 10;
@@ -593,11 +636,11 @@ extern "C" int rtdm_sgbm_create(rtdm_sgbm **out, const rtdm_params *p, int max_w
     rc = check_device(device);
     if (rc) return rc;
     RTDM_CUDA(cudaSetDevice(device));
-    rtdm_sgbm *h = new (std::nothrow) rtdm_sgbm();
+    rtdm_sgbm *h = new (std::nothrow) rtdm_sgbm();      // value-initialised: every member zero, switches at their defaults
     if (!h) return -RTDM_ENOMEM;
-    memset(h, 0, sizeof *h);
     h->p = *p; h->maxW = max_width; h->maxH = max_height; h->maxB = max_batch; h->dev = device;
-    SgbmGeom g = sgbm_geom(*p, max_width, max_height);
+    h->sw = read_switches();
+    SgbmGeom g = sgbm_geom(*p, h->sw, max_width, max_height);
     size_t pl = 0, vol = 0;
     sgbm_work_bytes(g, &pl, &vol);
     h->frame_planes = pl; h->frame_vol = vol;
@@ -640,7 +683,7 @@ static int sgbm_pipeline(rtdm_sgbm *h, int n, PlaneU8 L, PlaneU8 R, int W, int H
         set_error("sgbm: frame geometry or batch exceeds what the handle was created for");
         return -RTDM_EINVAL;
     }
-    SgbmGeom g = sgbm_geom(h->p, W, H);
+    SgbmGeom g = sgbm_geom(h->p, h->sw, W, H);
     const int INVS = (g.minD - 1) * 16;
     size_t pl = 0, vol = 0;
     sgbm_work_bytes(g, &pl, &vol);
@@ -688,7 +731,7 @@ static int sgbm_pipeline(rtdm_sgbm *h, int n, PlaneU8 L, PlaneU8 R, int W, int H
         int rc = launch_median3(m, W, H, raw, o, st, &h->launches);
         if (rc) return rc;
         if (h->p.speckleWindowSize > 0) {
-            rc = launch_speckle(m, W, H, o, INVS, h->p.speckleWindowSize, 16 * h->p.speckleRange, h->labels, h->sizes, st, &h->launches, h->runlen);
+            rc = launch_speckle(m, W, H, o, INVS, h->p.speckleWindowSize, 16 * h->p.speckleRange, h->labels, h->sizes, st, &h->launches, h->runlen, h->sw);
             if (rc) return rc;
         }
         mark();
@@ -764,6 +807,32 @@ extern "C" int rtdm_sgbm_wait_oldest(rtdm_sgbm *h)
 // H2D on lane[0], kernels on the handle's stream, D2H on lane[1], chained by events; two staging sets, so the copies of
 // batch k+1 / k-1 run under the kernels of batch k (the cost volumes and scratch are used by one batch at a time: the
 // kernels of successive batches are ordered on the one compute stream)
+static int sgbm_enqueue_batch(rtdm_sgbm *h, int set, int n, const uint8_t *left, size_t lstep, size_t lframe,
+                              const uint8_t *right, size_t rstep, size_t rframe, int width, int height,
+                              int16_t *disp, size_t dstep, size_t dframe)
+{
+    uint8_t *sL = set ? h->dL2 : h->dL, *sR = set ? h->dR2 : h->dR;
+    int16_t *sD = set ? h->dD2 : h->dD;
+    cudaStream_t s_in = h->lane[0], s_out = h->lane[1], st = h->st;
+    for (int k = 0; k < n; k++) {
+        RTDM_CUDA(cudaMemcpy2DAsync(sL + k * h->sframe, h->spitch, left + k * lframe, lstep, width, height, cudaMemcpyHostToDevice, s_in));
+        RTDM_CUDA(cudaMemcpy2DAsync(sR + k * h->sframe, h->spitch, right + k * rframe, rstep, width, height, cudaMemcpyHostToDevice, s_in));
+    }
+    RTDM_CUDA(cudaEventRecord(h->ev_in[set], s_in));
+    RTDM_CUDA(cudaStreamWaitEvent(st, h->ev_in[set], 0));
+    int rc = sgbm_pipeline(h, n, PlaneU8{sL, h->spitch, h->sframe}, PlaneU8{sR, h->spitch, h->sframe}, width, height,
+                           PlaneS16{sD, h->dpitch, h->dframe}, st);
+    if (rc) return rc;
+    RTDM_CUDA(cudaEventRecord(h->ev_cmp[set], st));
+    RTDM_CUDA(cudaStreamWaitEvent(s_out, h->ev_cmp[set], 0));
+    for (int k = 0; k < n; k++)
+        RTDM_CUDA(cudaMemcpy2DAsync((uint8_t *)disp + k * dframe, dstep, sD + k * h->dframe, h->dpitch * 2,
+                                    (size_t)width * 2, height, cudaMemcpyDeviceToHost, s_out));
+    RTDM_CUDA(cudaEventRecord(h->done[set], s_out));
+    h->busy[set] = 1;
+    return 0;
+}
+
 extern "C" int rtdm_sgbm_submit_batch(rtdm_sgbm *h, int n, const uint8_t *left, size_t lstep, size_t lframe,
                                       const uint8_t *right, size_t rstep, size_t rframe, int width, int height,
                                       int16_t *disp, size_t dstep, size_t dframe)
@@ -777,26 +846,13 @@ extern "C" int rtdm_sgbm_submit_batch(rtdm_sgbm *h, int n, const uint8_t *left, 
     h->launches = 0;
     const int set = (int)(h->seq++ & 1u);
     if (h->busy[set]) { RTDM_CUDA(cudaEventSynchronize(h->done[set])); h->busy[set] = 0; }
-    uint8_t *sL = set ? h->dL2 : h->dL, *sR = set ? h->dR2 : h->dR;
-    int16_t *sD = set ? h->dD2 : h->dD;
-    cudaStream_t s_in = h->lane[0], s_out = h->lane[1], st = h->st;
-    for (int k = 0; k < n; k++) {
-        RTDM_CUDA(cudaMemcpy2DAsync(sL + k * h->sframe, h->spitch, left + k * lframe, lstep, width, height, cudaMemcpyHostToDevice, s_in));
-        RTDM_CUDA(cudaMemcpy2DAsync(sR + k * h->sframe, h->spitch, right + k * rframe, rstep, width, height, cudaMemcpyHostToDevice, s_in));
+    const int rc = sgbm_enqueue_batch(h, set, n, left, lstep, lframe, right, rstep, rframe, width, height, disp, dstep, dframe);
+    if (rc) {
+        const std::string why = rtdm_last_error();
+        rtdm_sgbm_wait(h);
+        set_error(why);
     }
-    RTDM_CUDA(cudaEventRecord(h->ev_in[set], s_in));
-    RTDM_CUDA(cudaStreamWaitEvent(st, h->ev_in[set], 0));
-    int rc = sgbm_pipeline(h, n, PlaneU8{sL, h->spitch, h->sframe}, PlaneU8{sR, h->spitch, h->sframe}, width, height,
-                           PlaneS16{sD, h->dpitch, h->dframe}, st);
-    if (rc) { rtdm_sgbm_wait(h); return rc; }
-    RTDM_CUDA(cudaEventRecord(h->ev_cmp[set], st));
-    RTDM_CUDA(cudaStreamWaitEvent(s_out, h->ev_cmp[set], 0));
-    for (int k = 0; k < n; k++)
-        RTDM_CUDA(cudaMemcpy2DAsync((uint8_t *)disp + k * dframe, dstep, sD + k * h->dframe, h->dpitch * 2,
-                                    (size_t)width * 2, height, cudaMemcpyDeviceToHost, s_out));
-    RTDM_CUDA(cudaEventRecord(h->done[set], s_out));
-    h->busy[set] = 1;
-    return 0;
+    return rc;
 }
 
 extern "C" int rtdm_sgbm_compute_batch(rtdm_sgbm *h, int n, const uint8_t *left, size_t lstep, size_t lframe,
@@ -967,7 +1023,7 @@ extern "C" int rtdm_filter_speckles(int16_t *img, size_t step, int width, int he
         cudaError_t e = cudaMemcpy2D(d, (size_t)width * 2, img, step, (size_t)width * 2, height, cudaMemcpyHostToDevice);
         if (e != cudaSuccess) rc = cuda_fail(e, "memcpy2d", __FILE__, __LINE__);
     }
-    if (!rc) rc = launch_speckle(1, width, height, PlaneS16{d, (size_t)width, N}, newVal, maxSpeckleSize, maxDiff, lab, siz, 0, nullptr, rl);
+    if (!rc) rc = launch_speckle(1, width, height, PlaneS16{d, (size_t)width, N}, newVal, maxSpeckleSize, maxDiff, lab, siz, 0, nullptr, rl, read_switches());
     if (!rc) {
         cudaError_t e = cudaMemcpy2D(img, step, d, (size_t)width * 2, (size_t)width * 2, height, cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) rc = cuda_fail(e, "memcpy2d", __FILE__, __LINE__);
@@ -1130,7 +1186,7 @@ extern "C" int rtdm_depth_run_device(rtdm_depth *h, const int16_t *disp, size_t 
     if (dstep % 2 || xstep % 4) { set_error("depth: steps must be multiples of the element size"); return -RTDM_EINVAL; }
     RTDM_CUDA(cudaSetDevice(h->dev));
     return depth_run(h, disp, dstep / 2, width, height, Q, mask, mstep, nregions, rects, mean_z, count, xyz, xstep / 4,
-                     static_cast<cudaStream_t>(cuda_stream));
+                     cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->st);
 }
 
 extern "C" int rtdm_depth_run(rtdm_depth *h, const int16_t *disp, size_t dstep, int width, int height, const double *Q,
@@ -1218,7 +1274,7 @@ extern "C" int rtdm_rectify_run_device(rtdm_rectify *h, int n, const uint8_t *rg
     RTDM_CUDA(cudaSetDevice(h->dev));
     h->launches = 0;
     return launch_rectify(n, rgb, step, frame, h->W, h->H, h->map1, h->map2, h->rw, h->rh, out, ostep, oframe,
-                          static_cast<cudaStream_t>(cuda_stream), &h->launches);
+                          cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->st, &h->launches);
 }
 
 extern "C" int rtdm_rectify_run(rtdm_rectify *h, int n, const uint8_t *rgb, size_t step, size_t frame,
@@ -1323,7 +1379,7 @@ extern "C" int rtdm_colormask_run_device(rtdm_colormask *h, int n, const uint8_t
     RTDM_CUDA(cudaSetDevice(h->dev));
     h->launches = 0;
     return launch_colormask(n, rgb, step, frame, h->W, h->H, h->map1, h->map2, h->rw, h->rh, low, high, mask, mstep, mframe,
-                            bgr, bstep, bframe, static_cast<cudaStream_t>(cuda_stream), &h->launches);
+                            bgr, bstep, bframe, cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->st, &h->launches);
 }
 
 extern "C" int rtdm_colormask_run(rtdm_colormask *h, int n, const uint8_t *rgb, size_t step, size_t frame, const int *low, const int *high,
@@ -1429,7 +1485,7 @@ extern "C" int rtdm_regions_run_device(rtdm_regions *h, const uint8_t *mask, siz
         return -RTDM_EINVAL;
     }
     RTDM_CUDA(cudaSetDevice(h->dev));
-    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->st;
     h->launches = 0;
     int rc = launch_regions(mask, mstep, width, height, min_obj_size, h->maxR, h->labels, h->bb, h->ext, h->keys, h->boxes,
                             h->out, st, &h->launches);

@@ -37,6 +37,7 @@ struct BmKArgs {
     int NC;                  // TW + 2h virtual columns
     int LP, RP;              // smem row pitches (bytes) of the left / right band
     int VP, SP;              // smem pitches (bytes) of the V rows and SAD rows
+    int16_t *spill;          // BmGeom::spill
 };
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
@@ -257,10 +258,13 @@ bm_sad_wta_kernel(BmKArgs a)
                     const int q = p + n - 2 * minsad + abs(p - n);
                     const int v = (nd - mind - 1 + a.minD) * 256 + (q != 0 ? ((p - n) * 256) / q : 0) + 15;
                     dout = (int16_t)(v >> 4);
-                    if (costf) costf[(size_t)y * a.cost.pitch + a.lofs + x0 + x] = (int16_t)minsad;
+                    if (costf && a.lofs + x0 + x < a.W) costf[(size_t)y * a.cost.pitch + a.lofs + x0 + x] = (int16_t)minsad;
                 }
             }
-            dispf[(size_t)y * a.disp.pitch + a.lofs + x0 + x] = dout;
+            // minDisparity > 0: the last minD computed columns lie beyond the row (cv2 lets them run into the next row)
+            const int xo = a.lofs + x0 + x;
+            if (xo < a.W) dispf[(size_t)y * a.disp.pitch + xo] = dout;
+            else if (a.spill && y == a.row1 - 1) a.spill[(size_t)blockIdx.z * a.minD + (xo - a.W)] = dout;
         }
         // the next iteration's stage-1 writes touch only Vs/Ts (read in stage 2, already fenced by
         // the second barrier); Ss is rewritten only after the next first barrier.
@@ -315,7 +319,7 @@ int launch_bm_sad_wta(const BmGeom &g, int n, PlaneU8 Lp, PlaneU8 Rp, PlaneS16 d
     a.Lp = Lp; a.Rp = Rp; a.disp = disp; a.cost = cost;
     a.W = g.W; a.H = g.H; a.nd = g.nd; a.minD = g.minD; a.h = g.bs / 2; a.cap = g.cap;
     a.texThr = g.texThr; a.uniq = g.uniq; a.lofs = g.lofs; a.rofs = g.rofs; a.W1 = g.W1;
-    a.row0 = g.row0; a.row1 = g.row1;
+    a.row0 = g.row0; a.row1 = g.row1; a.spill = g.spill;
     a.TW = t.TW; a.BH = t.BH; a.NO = g.nd / 8; a.NC = t.NC;
     a.LP = t.LP; a.RP = t.RP; a.VP = t.VP; a.SP = t.SP;
     // the L/R bands must end on a 16-byte boundary so that Vs (uint4 accesses) is aligned

@@ -475,8 +475,7 @@ bool pick_tiling2(const BmGeom &g, int n, Tiling2 *t)
     t->CT = 2 * h * t->KT;
     t->NO = g.nd / 8;
     // variant: RTDM_BM_VARIANT = 0: 192 threads + suffix sums, 1: 192 prefix-only, 2: 256 + suffix, 3: 256 prefix-only
-    int variant = 1;
-    if (const char *e = getenv("RTDM_BM_VARIANT")) variant = atoi(e);
+    const int variant = g.sw.bm_variant;
     t->NT = (variant & 2) ? 256 : 192;
     t->SUF = (variant & 1) ? 0 : 1;
     const int NT2 = t->NT;
@@ -509,9 +508,9 @@ int launch2v(const Bm2Args &a, const Tiling2 &t, int n, cudaStream_t st)
 }
 
 template <int H_, int KT_>
-int launch2(const Bm2Args &a, const Tiling2 &t, int n, cudaStream_t st)
+int launch2(const Bm2Args &a, const Tiling2 &t, int n, cudaStream_t st, bool occ3)
 {
-    if (t.NT == 192 && !t.SUF && t.smem <= 74 * 1024 && getenv("RTDM_BM_OCC3")) return launch2v<H_, KT_, 192, false, 3>(a, t, n, st);
+    if (t.NT == 192 && !t.SUF && t.smem <= 74 * 1024 && occ3) return launch2v<H_, KT_, 192, false, 3>(a, t, n, st);
     if (t.NT == 192) return t.SUF ? launch2v<H_, KT_, 192, true>(a, t, n, st) : launch2v<H_, KT_, 192, false>(a, t, n, st);
     return t.SUF ? launch2v<H_, KT_, 256, true>(a, t, n, st) : launch2v<H_, KT_, 256, false>(a, t, n, st);
 }
@@ -555,16 +554,16 @@ int launch_bm_sad2(const BmGeom &g, int n, PlaneU8 Lp, PlaneU8 Rp, PlaneS16 disp
     a.tex = tex; a.tex_pitch = tex_pitch; a.tex_frame = tex_frame;
     a.W = g.W; a.H = g.H; a.nd = g.nd; a.cap = g.cap; a.texThr = g.texThr; a.uniq = g.uniq;
     a.W1 = g.W1; a.row0 = g.row0; a.row1 = g.row1;
-    { const char *e = getenv("RTDM_BM_DEBUG"); a.dbg = e ? atoi(e) : 0; }
+    a.dbg = g.sw.bm_debug;
     a.TW = t.TW; a.BH = t.BH; a.NO = t.NO; a.NGT = t.NGT; a.LVP = t.LVP; a.RVP = t.RVP; a.PP = t.PP;
     int rc = 0;
     switch (h) {
-        case 2: rc = launch2<2, 3>(a, t, n, st); break;
-        case 3: rc = launch2<3, 2>(a, t, n, st); break;
-        case 4: rc = launch2<4, 1>(a, t, n, st); break;
-        case 5: rc = launch2<5, 1>(a, t, n, st); break;
-        case 6: rc = launch2<6, 1>(a, t, n, st); break;
-        default: rc = launch2<7, 1>(a, t, n, st); break;
+        case 2: rc = launch2<2, 3>(a, t, n, st, g.sw.bm_occ3 != 0); break;
+        case 3: rc = launch2<3, 2>(a, t, n, st, g.sw.bm_occ3 != 0); break;
+        case 4: rc = launch2<4, 1>(a, t, n, st, g.sw.bm_occ3 != 0); break;
+        case 5: rc = launch2<5, 1>(a, t, n, st, g.sw.bm_occ3 != 0); break;
+        case 6: rc = launch2<6, 1>(a, t, n, st, g.sw.bm_occ3 != 0); break;
+        default: rc = launch2<7, 1>(a, t, n, st, g.sw.bm_occ3 != 0); break;
     }
     if (rc) return rc;
     if (launches) (*launches) += 2;

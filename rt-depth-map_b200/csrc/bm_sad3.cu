@@ -608,8 +608,7 @@ bool pick_tiling3(const BmGeom &g, int n, Tiling3 *t)
     if (!(g.nd == 256 || g.nd == 192 || g.nd == 128 || g.nd == 96 || g.nd == 64 || g.nd == 48 || g.nd == 32)) return false;
     const int NO = g.nd / 8, G = 2 * h;
     // RTDM_BM3_SHAPE = 0: one wide CTA per SM, 1: two narrower CTAs per SM
-    int pair = 0;
-    if (const char *e = getenv("RTDM_BM3_SHAPE")) pair = (atoi(e) && (g.nd == 64 || g.nd == 128)) ? 1 : 0;
+    const int pair = (g.sw.bm3_shape && (g.nd == 64 || g.nd == 128)) ? 1 : 0;
     t->pair = pair;
     const int NCW = pair ? ShapePair::NCW : ShapeWide::NCW, NLD = pair ? ShapePair::NLD : ShapeWide::NLD;
     const int MAXT = pair ? ShapePair::MAXT : ShapeWide::MAXT;
@@ -714,7 +713,7 @@ int launch_bm_sad3_core(const BmGeom &g, int n, PlaneU8 Lp, PlaneU8 Rp, PlaneS16
     a.W = g.W; a.H = g.H; a.nd = g.nd; a.cap = g.cap; a.texThr = g.texThr; a.uniq = g.uniq;
     a.W1 = g.W1; a.row0 = g.row0; a.row1 = g.row1;
     a.TW = t.TW; a.BH = t.BH; a.NG = t.NG;
-    { const char *e = getenv("RTDM_BM_DEBUG"); a.dbg = e ? atoi(e) : 0; }
+    a.dbg = g.sw.bm_debug;
     const int h = g.bs / 2;
 #define RTDM_SAD3_ND(H_) (g.nd == 128 ? launch3<H_, 16>(a, t, n, st) : g.nd == 64 ? launch3<H_, 8>(a, t, n, st) : \
                           g.nd == 192 ? launch3<H_, 24>(a, t, n, st) : g.nd == 96 ? launch3<H_, 12>(a, t, n, st) : \

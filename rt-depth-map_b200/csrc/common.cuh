@@ -24,6 +24,25 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 // ---------------------------------------------------------------------------------------------
 // image planes: n frames, `pitch` bytes (u8) or elements (i16) per row, `frame` per frame
 // ---------------------------------------------------------------------------------------------
+// Development switches: kernel selection for A/B timing runs and for the tests' kernel matrix.  They come from the
+// environment and are read ONCE, by read_switches() in rtdm_*_create (and the stand-alone host stages) -- never on the
+// compute path of a live handle.  None of them changes a result; the one that did (RTDM_BM_DEBUG, which skips whole
+// stages for timing ablations) only exists in builds with -DRTDM_DEV.
+struct Switches {
+    int bm_kernel = 0;          // RTDM_BM_KERNEL: 1 = generic bm_sad.cu, 2 = bm_sad2.cu where bm_sad3.cu would run
+    int bm3_shape = 0;          // RTDM_BM3_SHAPE: 1 = two 384-thread CTAs per SM
+    int bm_chunk = 0;           // RTDM_BM_CHUNK: frames per chunk of the host batch pipeline (0 = automatic)
+    int bm_variant = 1;         // RTDM_BM_VARIANT (bm_sad2.cu CTA variants)
+    int bm_occ3 = 0;            // RTDM_BM_OCC3
+    int bm_debug = 0;           // RTDM_BM_DEBUG, RTDM_DEV builds only
+    int bm_nofuse = 0;          // RTDM_BM_NOFUSE: separate texture kernel instead of the fused prefilter + texture kernel
+    int speckle_scalar = 0;     // RTDM_SPECKLE_SCALAR: per-pixel speckle kernels
+    int post_unfused = 0;       // RTDM_POST_UNFUSED: separate validate / row-run kernels
+    int sgbm_oldcost = 0, sgbm_oldpath = 0, sgbm_nofuse = 0, sgbm_nosweep = 0;   // RTDM_SGBM_*
+    int sgbm_sweep_rows = 0;    // RTDM_SGBM_SWEEP_ROWS: rows per sweep launch (0 = default)
+};
+Switches read_switches();
+
 struct PlaneU8 { const uint8_t *p; size_t pitch; size_t frame; };
 struct PlaneU8W { uint8_t *p; size_t pitch; size_t frame; };
 struct PlaneS16 { int16_t *p; size_t pitch; size_t frame; };   // pitch / frame in ELEMENTS
@@ -39,6 +58,11 @@ struct BmGeom {
     int W, H, nd, minD, bs, cap, texThr, uniq;
     int lofs, rofs, W1;
     int row0, row1;          // rows to compute (valid rect rows)
+    // minDisparity > 0 only: cv::StereoBM writes the computed columns lofs + x >= W of a row into the first minD pixels
+    // of the NEXT row; all of them are overwritten or masked again except those of the last
+    // computed row, which stay in row `row1`.  spill[frame * minD + k] receives them (nullptr: not wanted)
+    int16_t *spill = nullptr;
+    Switches sw;
 };
 size_t bm_sad_smem_bytes(const BmGeom &g, int TW, int BH);
 int launch_bm_sad_wta(const BmGeom &g, int n, PlaneU8 Lp, PlaneU8 Rp, PlaneS16 disp, PlaneS16 cost,
@@ -58,15 +82,19 @@ int launch_bm_sad3_core(const BmGeom &g, int n, PlaneU8 Lp, PlaneU8 Rp, PlaneS16
 // validateDisparity (if d12 >= 0) + valid-rect mask; reads raw disp/cost, writes `out`
 int launch_validate_mask(int n, int W, int H, int minD, int nd, int d12, int lofs, int W1,
                          int vx0, int vx1, int row0, int row1,
-                         PlaneS16 raw, PlaneS16 cost, PlaneS16 out, cudaStream_t st, int *launches);
+                         PlaneS16 raw, PlaneS16 cost, PlaneS16 out, cudaStream_t st, int *launches,
+                         const int16_t *spill = nullptr);
 // filterSpeckles on n frames in place; labels, sizes, runlen: n*W*H int32 scratch each
 int launch_speckle(int n, int W, int H, PlaneS16 img, int newVal, int maxSize, int maxDiff,
-                   int32_t *labels, int32_t *sizes, cudaStream_t st, int *launches, int32_t *runlen);
+                   int32_t *labels, int32_t *sizes, cudaStream_t st, int *launches, int32_t *runlen,
+                   const Switches &sw = Switches());
 int launch_validate_speckle(int n, int W, int H, int minD, int nd, int d12, int lofs, int W1,
                             int vx0, int vx1, int row0, int row1, PlaneS16 raw, PlaneS16 cost, PlaneS16 out,
                             bool speckle, int newVal, int maxSize, int maxDiff,
                             int32_t *labels, int32_t *sizes, int32_t *runlen, cudaStream_t st, int *launches,
-                            void (*after_rows)(void *) = nullptr, void *ctx = nullptr);   // hook between the row pass and the rest (stage timing)
+                            void (*after_rows)(void *) = nullptr, void *ctx = nullptr,    // hook between the row pass and the rest (stage timing)
+                            const int16_t *spill = nullptr,                               // BmGeom::spill (minDisparity > 0)
+                            const Switches &sw = Switches());
 int launch_median3(int n, int W, int H, PlaneS16 src, PlaneS16 dst, cudaStream_t st, int *launches);
 
 // ---- morphology (morph.cu) ---------------------------------------------------------------------
@@ -87,6 +115,7 @@ int launch_morph_openclose(int n, int W, int H, PlaneU8 src, PlaneU8W dst, Plane
 struct SgbmGeom {
     int W, H, D, minD, bs, P1, P2, uniq, d12, ftzero, mode;
     int minX1, maxX1, W1;
+    Switches sw;
 };
 struct SgbmWork {
     uint8_t *planes;    // per frame: BT planes (see sgbm.cu)

@@ -22,7 +22,7 @@ namespace rtdm {
 __global__ void __launch_bounds__(256)
 validate_mask_kernel(int W, int H, int minD, int nd, int d12, int lofs, int W1,
                      int vx0, int vx1, int row0, int row1,
-                     PlaneS16 raw, PlaneS16 cost, PlaneS16 out)
+                     PlaneS16 raw, PlaneS16 cost, PlaneS16 out, const int16_t *spill)
 {
     extern __shared__ uint32_t vm_smem[];
     uint32_t *key = vm_smem;                                 // [W]
@@ -31,7 +31,9 @@ validate_mask_kernel(int W, int H, int minD, int nd, int d12, int lofs, int W1,
     const int INV = (minD - 1) * 16;
     int16_t *orow = out.p + (size_t)f * out.frame + (size_t)y * out.pitch;
     if (y < row0 || y >= row1) {
-        for (int x = threadIdx.x; x < W; x += blockDim.x) orow[x] = (int16_t)INV;
+        // row1 keeps what the last computed row wrote beyond its end (minDisparity > 0, BmGeom::spill)
+        const bool sp = spill && y == row1 && row1 > row0;
+        for (int x = threadIdx.x; x < W; x += blockDim.x) orow[x] = (sp && x < minD) ? spill[(size_t)f * minD + x] : (int16_t)INV;
         return;
     }
     const int16_t *drow = raw.p + (size_t)f * raw.frame + (size_t)y * raw.pitch;
@@ -86,13 +88,13 @@ validate_mask_kernel(int W, int H, int minD, int nd, int d12, int lofs, int W1,
 
 int launch_validate_mask(int n, int W, int H, int minD, int nd, int d12, int lofs, int W1,
                          int vx0, int vx1, int row0, int row1,
-                         PlaneS16 raw, PlaneS16 cost, PlaneS16 out, cudaStream_t st, int *launches)
+                         PlaneS16 raw, PlaneS16 cost, PlaneS16 out, cudaStream_t st, int *launches, const int16_t *spill)
 {
     if (n <= 0) return 0;
     dim3 grid(H, n);
     size_t smem = (size_t)W * 6 + 8;
     validate_mask_kernel<<<grid, 256, smem, st>>>(W, H, minD, nd, d12, lofs, W1, vx0, vx1, row0, row1,
-                                                 raw, cost, out);
+                                                 raw, cost, out, spill);
     if (launches) (*launches)++;
     RTDM_CUDA(cudaGetLastError());
     return 0;
@@ -275,6 +277,7 @@ __device__ __forceinline__ void load8_s16(const int16_t *p, int v[8])
 struct ValArgs {
     int minD, nd, d12, lofs, W1, vx0, vx1, row0, row1;
     PlaneS16 raw, cost;
+    const int16_t *spill;       // BmGeom::spill (minDisparity > 0), else nullptr
 };
 
 template <bool VALIDATE>
@@ -357,6 +360,11 @@ post_row8_kernel(int W, int H, PlaneS16 img, ValArgs va, int runs, int newVal, i
 #pragma unroll
             for (int k = 0; k < 8; k++)
                 if (x0 + k < va.vx0 || x0 + k >= va.vx1) v[k] = INV;
+            if (va.spill && y == va.row1 && va.row1 > va.row0) {                 // block-uniform; minDisparity > 0 only
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    if (x0 + k < va.minD) v[k] = va.spill[(size_t)f * va.minD + x0 + k];
+            }
 #pragma unroll
             for (int k = 0; k < 4; k++) pk[k] = (uint32_t)(uint16_t)v[2 * k] | ((uint32_t)(uint16_t)v[2 * k + 1] << 16);
             *reinterpret_cast<uint4 *>(row + x0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -490,17 +498,18 @@ speckle_runs8_kernel(int W, int H, PlaneS16 img, int newVal, int maxSize, int32_
 }
 
 // can launch_speckle take the 8-pixel kernels for this geometry?  (launch_validate_speckle relies on it)
-static bool speckle_vec_ok(int W, PlaneS16 img, const int32_t *labels)
+static bool speckle_vec_ok(int W, PlaneS16 img, const int32_t *labels, const Switches &sw)
 {
     return W % 8 == 0 && W <= 8192 && ((reinterpret_cast<uintptr_t>(img.p) | (img.pitch * 2) | (img.frame * 2)) & 15) == 0 &&
-           (reinterpret_cast<uintptr_t>(labels) & 15) == 0 && !getenv("RTDM_SPECKLE_SCALAR");
+           (reinterpret_cast<uintptr_t>(labels) & 15) == 0 && !sw.speckle_scalar;
 }
 
 static int launch_speckle_impl(int n, int W, int H, PlaneS16 img, int newVal, int maxSize, int maxDiff,
-                               int32_t *labels, int32_t *sizes, cudaStream_t st, int *launches, int32_t *runlen, bool rowruns_done)
+                               int32_t *labels, int32_t *sizes, cudaStream_t st, int *launches, int32_t *runlen, bool rowruns_done,
+                               const Switches &sw)
 {
     if (n <= 0) return 0;
-    const bool vec = speckle_vec_ok(W, img, labels);
+    const bool vec = speckle_vec_ok(W, img, labels, sw);
     if (vec) {
         const size_t N8 = ((size_t)W * H + 7) / 8;
         const int nt = ((W / 8) + 31) & ~31;
@@ -527,9 +536,9 @@ static int launch_speckle_impl(int n, int W, int H, PlaneS16 img, int newVal, in
 }
 
 int launch_speckle(int n, int W, int H, PlaneS16 img, int newVal, int maxSize, int maxDiff,
-                   int32_t *labels, int32_t *sizes, cudaStream_t st, int *launches, int32_t *runlen)
+                   int32_t *labels, int32_t *sizes, cudaStream_t st, int *launches, int32_t *runlen, const Switches &sw)
 {
-    return launch_speckle_impl(n, W, H, img, newVal, maxSize, maxDiff, labels, sizes, st, launches, runlen, false);
+    return launch_speckle_impl(n, W, H, img, newVal, maxSize, maxDiff, labels, sizes, st, launches, runlen, false, sw);
 }
 
 // validateDisparity + valid-rectangle mask (raw, cost -> out), then filterSpeckles on `out` when speckle is set.
@@ -538,26 +547,29 @@ int launch_validate_speckle(int n, int W, int H, int minD, int nd, int d12, int 
                             int vx0, int vx1, int row0, int row1, PlaneS16 raw, PlaneS16 cost, PlaneS16 out,
                             bool speckle, int newVal, int maxSize, int maxDiff,
                             int32_t *labels, int32_t *sizes, int32_t *runlen, cudaStream_t st, int *launches,
-                            void (*after_rows)(void *), void *ctx)
+                            void (*after_rows)(void *), void *ctx, const int16_t *spill, const Switches &sw)
 {
     if (n <= 0) { if (after_rows) after_rows(ctx); return 0; }
     const auto al16 = [](PlaneS16 p) { return ((reinterpret_cast<uintptr_t>(p.p) | (p.pitch * 2) | (p.frame * 2)) & 15) == 0; };
-    if (speckle_vec_ok(W, out, labels) && al16(raw) && al16(cost) && !getenv("RTDM_POST_UNFUSED")) {
+    if (speckle_vec_ok(W, out, labels, sw) && al16(raw) && al16(cost) && !sw.post_unfused) {
         ValArgs va;
         va.minD = minD; va.nd = nd; va.d12 = d12; va.lofs = lofs; va.W1 = W1; va.vx0 = vx0; va.vx1 = vx1; va.row0 = row0; va.row1 = row1;
-        va.raw = raw; va.cost = cost;
+        va.raw = raw; va.cost = cost; va.spill = spill;
         const int nt = ((W / 8) + 31) & ~31;
+        // rows wider than ~4900 pixels need more than the default 48 KB of dynamic shared memory (W <= 8192: 82 KB)
+        if ((size_t)W * 10 + 16 > 48 * 1024)
+            RTDM_CUDA(cudaFuncSetAttribute(post_row8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)W * 10 + 16)));
         post_row8_kernel<true><<<dim3(H, n), nt, (size_t)W * 10 + 16, st>>>(W, H, out, va, speckle ? 1 : 0, newVal, maxDiff, labels, sizes, runlen);
         if (launches) (*launches)++;
         RTDM_CUDA(cudaGetLastError());
         if (after_rows) after_rows(ctx);
         if (!speckle) return 0;
-        return launch_speckle_impl(n, W, H, out, newVal, maxSize, maxDiff, labels, sizes, st, launches, runlen, true);
+        return launch_speckle_impl(n, W, H, out, newVal, maxSize, maxDiff, labels, sizes, st, launches, runlen, true, sw);
     }
-    int rc = launch_validate_mask(n, W, H, minD, nd, d12, lofs, W1, vx0, vx1, row0, row1, raw, cost, out, st, launches);
+    int rc = launch_validate_mask(n, W, H, minD, nd, d12, lofs, W1, vx0, vx1, row0, row1, raw, cost, out, st, launches, spill);
     if (after_rows) after_rows(ctx);
     if (rc || !speckle) return rc;
-    return launch_speckle_impl(n, W, H, out, newVal, maxSize, maxDiff, labels, sizes, st, launches, runlen, false);
+    return launch_speckle_impl(n, W, H, out, newVal, maxSize, maxDiff, labels, sizes, st, launches, runlen, false, sw);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -870,12 +870,12 @@ sgbm_lr_kernel(LrArgs a)
             bool bad = true;
             if (0 <= _x && _x < a.W) {
                 const uint32_t k = key2[_x];
-                const int d2 = (k == 0xFFFFFFFFu) ? INV : (int)best[0xFFFF - (int)(k & 0xFFFFu)] + a.minD;
+                const int d2 = (k == 0xFFFFFFFFu) ? INVS : (int)best[0xFFFF - (int)(k & 0xFFFFu)] + a.minD;
                 bad = bad && d2 >= a.minD && abs(d2 - _d) > a.d12;
             } else bad = false;
             if (0 <= x_ && x_ < a.W) {
                 const uint32_t k = key2[x_];
-                const int d2 = (k == 0xFFFFFFFFu) ? INV : (int)best[0xFFFF - (int)(k & 0xFFFFu)] + a.minD;
+                const int d2 = (k == 0xFFFFFFFFu) ? INVS : (int)best[0xFFFF - (int)(k & 0xFFFFu)] + a.minD;
                 bad = bad && d2 >= a.minD && abs(d2 - d_) > a.d12;
             } else bad = false;
             if (bad) d1 = INVS;
@@ -986,12 +986,12 @@ sgbm_wta_kernel(WtaArgs a)
             bool bad = true;
             if (0 <= _x && _x < a.W) {
                 const uint32_t k = key2[_x];
-                const int d2 = (k == 0xFFFFFFFFu) ? INV : (int)best[0xFFFF - (int)(k & 0xFFFFu)] + a.minD;
+                const int d2 = (k == 0xFFFFFFFFu) ? INVS : (int)best[0xFFFF - (int)(k & 0xFFFFu)] + a.minD;
                 bad = bad && d2 >= a.minD && abs(d2 - _d) > a.d12;
             } else bad = false;
             if (0 <= x_ && x_ < a.W) {
                 const uint32_t k = key2[x_];
-                const int d2 = (k == 0xFFFFFFFFu) ? INV : (int)best[0xFFFF - (int)(k & 0xFFFFu)] + a.minD;
+                const int d2 = (k == 0xFFFFFFFFu) ? INVS : (int)best[0xFFFF - (int)(k & 0xFFFFu)] + a.minD;
                 bad = bad && d2 >= a.minD && abs(d2 - d_) > a.d12;
             } else bad = false;
             if (bad) d1 = INVS;
@@ -1036,7 +1036,7 @@ int launch_sgbm(const SgbmGeom &g, int n, PlaneU8 left, PlaneU8 right, PlaneS16 
     const int h = g.bs / 2;
     const size_t row_words = (size_t)g.W1 * g.D / 2, frame_words = w.frame_vol / 2;
     // D = 64 / 128 / 256 and windows up to 7 (larger ones would spill the register rings)
-    const bool fusedcost = sgbm_fused_cost(g) && !getenv("RTDM_SGBM_OLDCOST");
+    const bool fusedcost = sgbm_fused_cost(g) && !g.sw.sgbm_oldcost;
     if (fusedcost) {
         // 1-3. planes in staging format, then fused BT cost + horizontal and vertical windows + P2 -> C
         const int LW = g.W1 + 2 * PADL, WR = (int)align_up((size_t)g.W + 2 * PADR, 8);
@@ -1102,14 +1102,14 @@ int launch_sgbm(const SgbmGeom &g, int n, PlaneU8 left, PlaneU8 right, PlaneS16 
     const bool hh = g.mode == RTDM_SGBM_MODE_HH;
     const int ndirs = hh ? 8 : 5;
     const int K2 = g.D <= 64 ? 1 : (g.D <= 128 ? 2 : 4);   // u16x2 words per lane (divides D/2 for any D % 16 == 0)
-    const bool fast = (g.D == 128 || g.D == 64) && !getenv("RTDM_SGBM_OLDPATH");
-    const bool fused = fast && g.uniq < 100 && !getenv("RTDM_SGBM_NOFUSE");
+    const bool fast = (g.D == 128 || g.D == 64) && !g.sw.sgbm_oldpath;
+    const bool fused = fast && g.uniq < 100 && !g.sw.sgbm_nofuse;
     const size_t frame_rec = w.frame_planes / 8;            // the BT planes are dead by now: their buffer takes the records
     // the two vertical triplets as row sweeps (one C read and one S update for three paths)
     const size_t rec_bytes = align_up((size_t)8 * g.H * g.W1, 256);
     const size_t front_words = (size_t)3 * g.W1 * (g.D / 2), fmin_words = (size_t)3 * g.W1;
     const size_t front_bytes = align_up((front_words + fmin_words) * 4, 256);
-    const bool sweep = fast && !getenv("RTDM_SGBM_NOSWEEP") && rec_bytes + 2 * front_bytes <= w.frame_planes;
+    const bool sweep = fast && !g.sw.sgbm_nosweep && rec_bytes + 2 * front_bytes <= w.frame_planes;
     const int pixmax = 2 * g.ftzero + 63, Lmax = 2 * g.P2 + g.bs * g.bs * pixmax;
     const bool safe3 = 32767 + 3 * Lmax <= 65535;
     auto launch_sweep = [&](int dy) -> int {

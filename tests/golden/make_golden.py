@@ -27,6 +27,14 @@ BM_CASES = {
     "bm_roi_320x240_nd64_bs15": (320, 240, 1004, dict(preFilterCap=31, blockSize=15, minDisparity=0, textureThreshold=10, numDisparities=64, uniquenessRatio=10, speckleWindowSize=100, speckleRange=32, disp12MaxDiff=1, roi1=(40, 30, 240, 180), roi2=(10, 20, 280, 200))),
     "bm_norm_320x240_nd64_bs11": (320, 240, 1005, dict(preFilterCap=25, blockSize=11, minDisparity=0, textureThreshold=20, numDisparities=64, uniquenessRatio=15, speckleWindowSize=50, speckleRange=16, disp12MaxDiff=2, preFilterType=0, preFilterSize=9)),
     "bm_cap63_200x120_nd48_bs11": (200, 120, 1006, dict(preFilterCap=63, blockSize=11, minDisparity=0, textureThreshold=10, numDisparities=48, uniquenessRatio=10, speckleWindowSize=100, speckleRange=32, disp12MaxDiff=-1)),
+    # minDisparity != 0 (a constructor argument of both reference peers, bm-sw.h:28-30): positive values make cv2 write the
+    # last minD computed columns of a row into the next row -- the ROI case keeps such a row visible
+    "bm_mind16_320x240_nd64_bs15": (320, 240, 1007, dict(preFilterCap=31, blockSize=15, minDisparity=16, textureThreshold=10, numDisparities=64, uniquenessRatio=10, speckleWindowSize=100, speckleRange=32, disp12MaxDiff=1)),
+    "bm_mindneg16_320x240_nd64_bs13": (320, 240, 1008, dict(preFilterCap=31, blockSize=13, minDisparity=-16, textureThreshold=10, numDisparities=64, uniquenessRatio=10, speckleWindowSize=100, speckleRange=32, disp12MaxDiff=1)),
+    "bm_mind16roi_320x240_nd64_bs15": (320, 240, 99, dict(preFilterCap=31, blockSize=15, minDisparity=16, textureThreshold=10, numDisparities=64, uniquenessRatio=10, speckleWindowSize=0, speckleRange=32, disp12MaxDiff=-1, roi1=(30, 20, 250, 180))),
+    # the reference's real operating point at 1280x720: the calibrated ROI crop 934x404 (backup/1280x720/extrinsics.yml:56-57 via
+    # main.cpp:80-85), -nd 192 (cmdline-parser.cpp:22), main.cpp:134-135's literals, setROI1 from the object boxes (estimator.cpp:54)
+    "bm_op_934x404_nd192_bs13": (934, 404, 1009, dict(preFilterCap=31, blockSize=13, minDisparity=0, textureThreshold=10, numDisparities=192, uniquenessRatio=10, speckleWindowSize=100, speckleRange=32, disp12MaxDiff=1, roi1=(260, 60, 520, 280))),
 }
 
 SGBM_CASES = {
@@ -34,21 +42,33 @@ SGBM_CASES = {
     "sgbm_hh_320x240_nd64_bs5": (320, 240, 2001, dict(blockSize=5, minDisparity=0, numDisparities=64, uniquenessRatio=10, speckleWindowSize=100, speckleRange=32, disp12MaxDiff=1, mode=1)),
     "sgbm_mode0_233x157_nd32_bs3": (233, 157, 2002, dict(blockSize=3, minDisparity=0, numDisparities=32, uniquenessRatio=5, speckleWindowSize=0, speckleRange=0, disp12MaxDiff=2, mode=0)),
     "sgbm_hh_233x157_nd48_bs7": (233, 157, 2003, dict(blockSize=7, minDisparity=0, numDisparities=48, uniquenessRatio=15, speckleWindowSize=60, speckleRange=8, disp12MaxDiff=1, mode=1)),
+    # minDisparity != 0 (sgbm-sw.h:28-29).  For minD >= 2 cv2's LR check treats never-written disp2 entries as disparities
+    # (they hold the x16-scaled invalid value, which passes its `>= minD` test)
+    "sgbm_hh_mind16_320x240_nd64_bs5": (320, 240, 2004, dict(blockSize=5, minDisparity=16, numDisparities=64, uniquenessRatio=10, speckleWindowSize=100, speckleRange=32, disp12MaxDiff=1, mode=1)),
+    "sgbm_mode0_mind16_320x240_nd64_bs5": (320, 240, 2005, dict(blockSize=5, minDisparity=16, numDisparities=64, uniquenessRatio=10, speckleWindowSize=100, speckleRange=32, disp12MaxDiff=1, mode=0)),
+    "sgbm_hh_mindneg16_233x157_nd48_bs5": (233, 157, 2006, dict(blockSize=5, minDisparity=-16, numDisparities=48, uniquenessRatio=10, speckleWindowSize=100, speckleRange=32, disp12MaxDiff=1, mode=1)),
 }
 
 
-def main():
+def main(only=None):
+    """only: names of BM / SGBM cases to (re)generate; None = every fixture."""
     cv2 = cv2_ref.cv2_pinned()
     for name, (W, H, seed, p) in BM_CASES.items():
+        if only is not None and name not in only:
+            continue
         L, R, _ = synth.stereo_pair(W, H, p["numDisparities"], seed)
         disp = cv2_ref.make_bm(**p).compute(L, R)
         np.savez_compressed(os.path.join(OUT, name), left=L, right=R, disp=disp, params=json.dumps(p))
         print(name, disp.shape, float((disp >= 0).mean()))
     for name, (W, H, seed, p) in SGBM_CASES.items():
+        if only is not None and name not in only:
+            continue
         L, R, _ = synth.stereo_pair(W, H, p["numDisparities"], seed)
         disp = cv2_ref.make_sgbm(**p).compute(L, R)
         np.savez_compressed(os.path.join(OUT, name), left=L, right=R, disp=disp, params=json.dumps(p))
         print(name, disp.shape, float((disp >= 0).mean()))
+    if only is not None:
+        return
     # morphology: the ROI-sized binary mask of the 720p calibration, a full 720p gray image, tiny edge cases
     for name, img in {
         "morph_mask_934x404": synth.binary_mask(934, 404, 3000),
@@ -154,5 +174,7 @@ def make_mask():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "mask":
         make_mask()
+    elif len(sys.argv) > 1:
+        main(set(sys.argv[1:]))         # python tests/golden/make_golden.py <case name> ...
     else:
         main()

@@ -295,3 +295,95 @@ def test_bm_warp_specialised_kernel_is_deterministic_under_load(gpu, orc, shape,
         assert m.last_kernel() == 3
         for i in range(B):
             assert np.array_equal(out[i], ref[i % 3]), (shape, rep, i, int((out[i] != ref[i % 3]).sum()))
+
+
+@pytest.mark.parametrize("minD", [16, -16, 5, -37, 40])
+def test_bm_min_disparity_matches_oracle(gpu, orc, minD):
+    """minDisparity is a constructor argument of the reference peer (bm-sw.h:28-30) that main.cpp leaves at 0; the
+    library accepts any value (generic kernel), so every value must be right.  The oracle is pinned against cv2 for
+    these values by the bm_mind* fixtures, including cv2's row spill for minD > 0 (the last minD
+    computed columns of the last valid row land in the first pixels of the row below the valid rectangle) -- the
+    whole map is compared, not only the valid rectangle."""
+    from rtdm_b200 import synth
+    rng = np.random.default_rng(1000 + minD)
+    for i, (W, H, nd, bs) in enumerate([(320, 240, 64, 15), (233, 157, 48, 9), (400, 200, 128, 13), (640, 120, 32, 21)]):
+        p = dict(preFilterCap=int(rng.integers(1, 32)), blockSize=bs, minDisparity=minD, textureThreshold=10 * (i % 2),
+                 numDisparities=nd, uniquenessRatio=int(rng.integers(0, 20)), speckleWindowSize=100 * ((i + 1) % 2),
+                 speckleRange=32, disp12MaxDiff=int(rng.integers(-1, 3)))
+        if i in (1, 2):
+            p["roi1"] = (30, 20, W - 70, H - 50)        # valid rectangle ends above the last row: the spill row stays visible
+        L, R, _ = synth.stereo_pair(W, H, nd, 8000 + 10 * i + minD)
+        m = _mk(gpu, p, W, H)
+        got = m.compute(L, R)
+        ref = orc.bm_compute(L, R, _orc_params(orc, p))
+        assert m.last_kernel() == 1
+        assert np.array_equal(got, ref), (p, W, H, int((got != ref).sum()), np.argwhere(got != ref)[:5])
+        # batch of 3 (one spill row per frame)
+        if i == 1:
+            mb = _mk(gpu, p, W, H, max_batch=3)
+            fr = [synth.stereo_pair(W, H, nd, 8100 + k) for k in range(3)]
+            out = mb.compute_batch(np.stack([f[0] for f in fr]), np.stack([f[1] for f in fr]))
+            for k in range(3):
+                assert np.array_equal(out[k], orc.bm_compute(fr[k][0], fr[k][1], _orc_params(orc, p))), (minD, k)
+
+
+def test_bm_reference_operating_point(gpu, orc, bm_kernel):
+    """What Estimator::run really does per frame (estimator.cpp:54-56, main.cpp:131-135): the 934x404 calibrated ROI crop
+    as a strided view of the 1280x720 rectified image, -nd 192, setROI1 with a fresh rectangle every frame, one frame,
+    synchronous.  Against the cv2 fixture for one rectangle and the oracle for the others."""
+    g = load_golden("bm_op_934x404_nd192_bs13")
+    p = json.loads(str(g["params"]))
+    H, W = g["left"].shape
+    fullL = np.zeros((720, 1280), np.uint8); fullR = np.zeros((720, 1280), np.uint8)
+    fullL[150:150 + H, 170:170 + W] = g["left"]; fullR[150:150 + H, 170:170 + W] = g["right"]
+    Lv, Rv = fullL[150:150 + H, 170:170 + W], fullR[150:150 + H, 170:170 + W]      # step = full image width (estimator.cpp:33,36)
+    m = _mk(gpu, dict(p, roi1=None), W, H)
+    m.setROI1(p["roi1"])
+    got = m.compute(Lv, Rv)
+    assert np.array_equal(got, g["disp"]), int((got != g["disp"]).sum())
+    assert m.last_kernel() == _expected_kernel(bm_kernel, p)
+    for roi in [(0, 0, W, H), (400, 100, 300, 200), (600, 10, 334, 390), (10, 300, 900, 104)]:
+        m.setROI1(roi)
+        ref = orc.bm_compute(g["left"], g["right"], _orc_params(orc, dict(p, roi1=roi)))
+        assert np.array_equal(m.compute(Lv, Rv), ref), roi
+
+
+def test_bm_streaming_63_frame_720p_batches(gpu, orc):
+    """The exact call pattern bench.py times: rtdm_bm_submit_batch with 63-frame 1280x720 batches (the host pipeline
+    splits them into wave-sized chunks), two submissions in flight, results read one submission later.  Three
+    submissions of the same 63 DISTINCT frames in rotated order: all must agree frame by frame, and the frames next to
+    every possible chunk boundary must equal the oracle's maps."""
+    from rtdm_b200 import synth
+    p = dict(preFilterCap=31, blockSize=13, minDisparity=0, textureThreshold=10, numDisparities=128,
+             uniquenessRatio=10, speckleWindowSize=100, speckleRange=32, disp12MaxDiff=1)
+    W, H, B = 1280, 720, 63
+    fr = [synth.stereo_pair(W, H, 128, 1000 + i) for i in range(B)]
+    Ls = np.stack([f[0] for f in fr]); Rs = np.stack([f[1] for f in fr])
+    m = _mk(gpu, p, W, H, max_batch=B)
+    outs, ins = [], []
+    for s in range(3):
+        k = 7 * s
+        Lr, Rr = np.roll(Ls, k, axis=0), np.roll(Rs, k, axis=0)        # frame i of the batch = frame (i - k) % B of the set
+        ins.append((Lr, Rr))
+        outs.append(np.full((B, H, W), 12345, np.int16))
+        m.submit_batch(Lr, Rr, outs[s])
+        if s >= 1:
+            m.wait_oldest()
+    m.wait()
+    assert m.last_kernel() == 3
+    for s in (1, 2):
+        assert np.array_equal(np.roll(outs[s], -7 * s, axis=0), outs[0]), s
+    for i in (0, 1, 15, 16, 20, 21, 27, 28, 31, 32, 34, 35, 41, 42, 47, 48, 62):
+        ref = orc.bm_compute(Ls[i], Rs[i], _orc_params(orc, p))
+        assert np.array_equal(outs[0][i], ref), (i, int((outs[0][i] != ref).sum()))
+
+
+def test_bm_wide_frame_fused_row_kernel(gpu, orc):
+    """Rows wider than 4912 pixels: the fused validate + row-run kernel needs more than 48 KB of dynamic shared memory."""
+    from rtdm_b200 import synth
+    W, H, nd = 5120, 48, 64
+    L, R, _ = synth.stereo_pair(W, H, nd, 31337)
+    p = dict(preFilterCap=31, blockSize=9, minDisparity=0, textureThreshold=10, numDisparities=nd,
+             uniquenessRatio=10, speckleWindowSize=100, speckleRange=32, disp12MaxDiff=1)
+    got = _mk(gpu, p, W, H).compute(L, R)
+    assert np.array_equal(got, orc.bm_compute(L, R, _orc_params(orc, p)))

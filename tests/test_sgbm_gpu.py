@@ -165,3 +165,24 @@ def test_sgbm_wave_sized_sub_batches_equal_single_frames(gpu):
     for k in (0, 1, 17, 36, 37, 38, 39):
         assert np.array_equal(out[k], single[k % 5]), k
     assert len({out[k].tobytes() for k in range(0, B, 5)}) == 1            # the same frame at eight batch positions
+
+
+@pytest.mark.parametrize("minD", [16, -16, 5, -37])
+def test_sgbm_min_disparity_matches_oracle(gpu, orc, minD):
+    """minDisparity != 0 (sgbm-sw.h:28-29).  The oracle is pinned against cv2 for it by the sgbm_*mind* fixtures: for
+    minD >= 2 cv2's LR check lets never-written disp2 entries (they hold (minD - 1) * 16) pass its `>= minD` test."""
+    from rtdm_b200 import synth
+    rng = np.random.default_rng(2000 + minD)
+    checked = 0
+    for i, (W, H, nd, bs) in enumerate([(320, 240, 64, 5), (233, 157, 48, 3), (400, 200, 128, 5), (300, 90, 32, 7), (500, 64, 96, 1)]):
+        p = dict(blockSize=bs, minDisparity=minD, numDisparities=nd, uniquenessRatio=int(rng.integers(0, 20)),
+                 speckleWindowSize=100 * (i % 2), speckleRange=int(rng.integers(1, 8)), disp12MaxDiff=int(rng.integers(-1, 3)),
+                 mode=i % 2)
+        L, R, _ = synth.stereo_pair(W, H, nd, 9000 + 10 * i + minD)
+        ref, outside = orc.sgbm_compute(L, R, orc.sgbm_params(**p), return_domain_flag=True)
+        if outside:
+            continue
+        got = _mk(gpu, p, W, H).compute(L, R)
+        assert np.array_equal(ref, got), (p, W, H, int((ref != got).sum()))
+        checked += 1
+    assert checked >= 4
