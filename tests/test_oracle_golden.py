@@ -209,3 +209,23 @@ def test_mask_oracle_vs_cv2_live():
         n = cv2.GaussianBlur(rng.integers(0, 256, (H, W)).astype(np.uint8), (0, 0), float(rng.uniform(0.6, 4)))
         m = ((n > np.median(n) + int(rng.integers(-3, 4))) * int(rng.integers(1, 256))).astype(np.uint8)
         assert cv_boxes(m) == orc.contour_boxes(m), (t, W, H)
+
+
+def test_oracle_vs_cv2_min_disparity(orc):
+    """minDisparity != 0, both matchers, live against cv2 (BM: whole map incl. the App. B.3 spill row)."""
+    cv2_ref = _cv2()
+    from rtdm_b200 import synth
+    for minD in (16, -16, 5, -37, 2, 1):
+        for (W, H, nd, bs) in [(320, 240, 64, 15), (233, 157, 48, 9)]:
+            L, R, _ = synth.stereo_pair(W, H, nd, 1234 + minD)
+            for roi in (None, (30, 20, W - 70, H - 50)):
+                p = dict(preFilterCap=31, blockSize=bs, minDisparity=minD, textureThreshold=10, numDisparities=nd,
+                         uniquenessRatio=10, speckleWindowSize=100 if roi is None else 0, speckleRange=32,
+                         disp12MaxDiff=1 if roi is None else -1, roi1=roi)
+                assert np.array_equal(cv2_ref.make_bm(**p).compute(L, R), orc.bm_compute(L, R, _bm_params(orc, p))), (minD, W, roi)
+            for mode in (0, 1):
+                ps = dict(blockSize=5, minDisparity=minD, numDisparities=nd, uniquenessRatio=10, speckleWindowSize=100,
+                          speckleRange=32, disp12MaxDiff=1, mode=mode)
+                got, outside = orc.sgbm_compute(L, R, orc.sgbm_params(**ps), return_domain_flag=True)
+                assert not outside
+                assert np.array_equal(cv2_ref.make_sgbm(**ps).compute(L, R), got), (minD, W, mode)
