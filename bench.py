@@ -462,7 +462,7 @@ def bench_bm(ctx, K, frames):
             "kernel": {3: "bm_sad3_kernel (warp-specialised SAD/WTA)", 2: "bm_sad2_kernel", 1: "bm_sad_wta_kernel (generic)"}.get(matcher.last_kernel(), "?"),
             "bound": "int_alu", "achieved": ach, "peak": ip["iadd3_tiops"], "unit": "Tiop/s", "frac": ach / ip["iadd3_tiops"],
             "whole_step_frac": de * OPS_PER_DE["bm720"] / (step_ms * 1e-3) / 1e12 / ip["iadd3_tiops"],
-            "traffic": tr.get("dram_bytes_per_frame", 0) * B or None,
+            "traffic": (tr.get("dram_bytes_per_frame") or 0) * B or None,
             "traffic_note": tr.get("source"),
             "ops_per_de": OPS_PER_DE["bm720"], "kernel_ms_per_launch": k_ms, "frames_per_launch": B,
             "kernel_share_of_step": k_ms / step_ms,
@@ -547,7 +547,7 @@ def bench_sgbm(ctx, K, frames, name):
         hbm_ach = B * HBM_BYTES_PER_FRAME[name] / (k_ms * 1e-3) / 1e9
         ach = B * W * H * ND * OPS_PER_DE[name] / (k_ms * 1e-3) / 1e12
         tr = ctx.traffic.get("sgbm_" + name, {})
-        traffic = tr.get("dram_bytes_per_frame", 0) * B or None
+        traffic = (tr.get("dram_bytes_per_frame") or 0) * B or None
         res["roofline"] = {
             "kernel": "sgbm matching stage (sgbm_cost_fused + sgbm_path4 first/last + sgbm_sweep row sweeps + sgbm_lr)",
             "bound": "int_alu", "achieved": ach, "peak": ip["iadd3_tiops"], "unit": "Tiop/s", "frac": ach / ip["iadd3_tiops"],
@@ -680,7 +680,7 @@ def run_ours(args):
     if wl in ("all", "sgbm720"):
         for name in SGBM_MODES:
             sg[name] = bench_sgbm(ctx, K, frames, name)
-    lat = bench_latency(ctx) if (wl == "all" and rank == 0) else None
+    lat = bench_latency(ctx) if (wl == "all" and rank == 0 and not args.no_latency) else None
     barrier()
 
     failure = None
@@ -769,7 +769,11 @@ def main():
     ap.add_argument("--workload", default="all", choices=["all", "bm720", "sgbm720"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     ap.add_argument("--no-check", action="store_true", help="skip the parity check of the timed outputs")
+    ap.add_argument("--no-latency", action="store_true", help="skip the per-frame latency leg")
+    ap.add_argument("--min-region-s", type=float, default=MIN_REGION_S,
+                    help="minimum length of every timed region (profiling runs under ncu pass 0: K steps exactly)")
     args = ap.parse_args()
+    globals()["MIN_REGION_S"] = max(0.0, args.min_region_s)
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":
