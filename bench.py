@@ -616,8 +616,12 @@ def make_checker():
             if kind == "mask":
                 return cv2_ref.morph_open_close(x)
             if kind == "op":
+                # cv2 never writes the rows of stripes that lie wholly outside the valid rectangle (a fresh output Mat
+                # holds heap garbage there, run to run different); the reference reuses one left_disp Mat, so hand cv2
+                # an output that already holds FILTERED (-16), which is what this library writes there
                 bm_op.setROI1(x[3])
-                return bm_op.compute(x[0], x[1]), cv2_ref.morph_open_close(x[2])
+                out = np.full(x[0].shape, -16, np.int16)
+                return bm_op.compute(x[0], x[1], out), cv2_ref.morph_open_close(x[2])
             return sg[kind].compute(x[0], x[1])
         return check, f"cv2 {cv2.__version__}"
     from oracle import oracle
@@ -688,7 +692,7 @@ def run_ours(args):
         # ---- parity of what the timed regions produced (e2e output buffers + device-side outputs) ---------
         parity = None
         if ctx.checker is not None:
-            parity = {"checker": checker_name, "mismatching_pixels": 0}
+            parity = {"checker": checker_name, "mismatching_pixels": 0, "by_leg": {}}
             Lh, Rh, Mh = frames
             if bm is not None:
                 Dp, MOp, (dsel, msel) = bm["_out"]
@@ -705,6 +709,7 @@ def run_ours(args):
                 bad += int((refm != MOp[BM_BATCH - 1]).sum())
                 parity["bm"] = len(idx); parity["masks"] = 2
                 parity["mismatching_pixels"] += bad
+                parity["by_leg"]["bm"] = bad
             for name, r in sg.items():
                 Dp, dsel = r["_out"]
                 idx = [0, SGBM_BATCH // 3, (2 * SGBM_BATCH) // 3, SGBM_BATCH - 1]
@@ -716,11 +721,13 @@ def run_ours(args):
                         bad += int((ref != dsel[0 if i == 0 else 1]).sum())
                 parity["sgbm_" + name] = len(idx)
                 parity["mismatching_pixels"] += bad
+                parity["by_leg"]["sgbm_" + name] = bad
             if sg:
                 parity["sgbm"] = sum(parity["sgbm_" + n] for n in sg)
             if lat is not None:
                 parity["latency_frames"] = lat["_parity"][0]
                 parity["mismatching_pixels"] += lat["_parity"][1]
+                parity["by_leg"]["latency"] = lat["_parity"][1]
         # ---- CPU baselines on bounded samples (rank 0, N=1 only) ------------------------------------------
         if world == 1 and not args.no_cpu:
             sub = (frames[0][:16], frames[1][:16], frames[2][:16])
