@@ -456,10 +456,10 @@ def bench_bm(ctx, K, frames):
         de = B * W * H * ND
         ach = de * OPS_PER_DE["bm720"] / (k_ms * 1e-3) / 1e12
         hbm_ach = B * HBM_BYTES_PER_FRAME["bm720"] / (k_ms * 1e-3) / 1e9
-        tr = ctx.traffic.get("bm_sad3", {}) if matcher.last_kernel() == 3 else {}
+        tr = ctx.traffic.get({3: "bm_sad3", 4: "bm_sad4"}.get(matcher.last_kernel(), "-"), {})
         step_ms = ms / nsteps
         res["roofline"] = {
-            "kernel": {3: "bm_sad3_kernel (warp-specialised SAD/WTA)", 2: "bm_sad2_kernel", 1: "bm_sad_wta_kernel (generic)"}.get(matcher.last_kernel(), "?"),
+            "kernel": {4: "bm_sad4_kernel (TMA-staged, warp-specialised SAD/WTA)", 3: "bm_sad3_kernel (warp-specialised SAD/WTA)", 2: "bm_sad2_kernel", 1: "bm_sad_wta_kernel (generic)"}.get(matcher.last_kernel(), "?"),
             "bound": "int_alu", "achieved": ach, "peak": ip["iadd3_tiops"], "unit": "Tiop/s", "frac": ach / ip["iadd3_tiops"],
             "whole_step_frac": de * OPS_PER_DE["bm720"] / (step_ms * 1e-3) / 1e12 / ip["iadd3_tiops"],
             "traffic": (tr.get("dram_bytes_per_frame") or 0) * B or None,

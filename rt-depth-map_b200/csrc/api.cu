@@ -111,6 +111,7 @@ struct rtdm_bm {
     cudaStream_t lane[3];        // streams of the chunked host-batch pipeline (copy/compute overlap)
     // per-batch device workspace (maxB frames)
     uint8_t *Lp, *Rp;            size_t ppitch, pframe;      // prefiltered planes (bytes)
+    uint32_t *LE; uint8_t *RPs;  size_t lepitch, leframe, rppitch, rpframe;   // staged layouts for bm_sad4.cu's TMA boxes (common.cuh: BmStaged)
     int16_t *raw, *cost;         size_t rpitch, rframe;      // raw WTA disparity + cost (elements)
     int32_t *labels, *sizes, *runlen;
     uint16_t *tex;                                           // texture window sums (rpitch / rframe)
@@ -122,7 +123,7 @@ struct rtdm_bm {
     cudaEvent_t done[2]; int busy[2]; unsigned seq;          // completion of the call that last used each set
     int launches;
     int lastW, lastH;
-    int last_kernel;             // 1 = generic bm_sad.cu kernel, 2 = fast bm_sad2.cu kernel, 3 = warp-specialised bm_sad3.cu kernel
+    int last_kernel;             // 1 = generic bm_sad.cu kernel, 2 = fast bm_sad2.cu kernel, 3 = warp-specialised bm_sad3.cu kernel, 4 = TMA-staged bm_sad4.cu kernel
     // optional per-stage CUDA-event timing (rtdm_bm_set_profiling)
     int prof;
     std::vector<cudaEvent_t> *ev;     // 5 events per profiled call: before prefilter, after each stage
@@ -184,7 +185,7 @@ extern "C" void rtdm_bm_destroy(rtdm_bm *h)
     cudaSetDevice(h->dev);
     cudaFree(h->Lp); cudaFree(h->Rp); cudaFree(h->raw); cudaFree(h->cost);
     cudaFree(h->labels); cudaFree(h->sizes); cudaFree(h->runlen); cudaFree(h->dL); cudaFree(h->dR); cudaFree(h->dD); cudaFree(h->tex);
-    cudaFree(h->spill);
+    cudaFree(h->spill); cudaFree(h->LE); cudaFree(h->RPs);
     cudaFree(h->dL2); cudaFree(h->dR2); cudaFree(h->dD2);
     for (int i = 0; i < 2; i++) if (h->done[i]) cudaEventDestroy(h->done[i]);
     if (h->ev) { for (cudaEvent_t e : *h->ev) cudaEventDestroy(e); delete h->ev; }
@@ -223,6 +224,13 @@ extern "C" int rtdm_bm_create(rtdm_bm **out, const rtdm_params *p, int max_width
         rc = (int)cudaStreamCreateWithFlags(&h->lane[i], cudaStreamNonBlocking) == cudaSuccess ? 0 : -RTDM_EIO;
     if (!rc) rc = dev_alloc(&h->Lp, h->pframe * B + 4096);
     if (!rc) rc = dev_alloc(&h->Rp, h->pframe * B + 4096);
+    // staged planes only where bm_sad4.cu can run (minDisparity 0, blockSize 5 .. 15)
+    h->lepitch = align_up((size_t)max_width + BmStaged::LPADL + BmStaged::LPADR, 4); h->leframe = h->lepitch * max_height;
+    h->rppitch = align_up((size_t)max_width + BmStaged::RPADL + BmStaged::RPADR, 16); h->rpframe = h->rppitch * max_height;
+    if (!rc && p->minDisparity == 0 && p->blockSize <= 15) {
+        rc = dev_alloc(&h->LE, h->leframe * B + 1024);          // + 4 KB: a bulk copy may run past the last row
+        if (!rc) rc = dev_alloc(&h->RPs, h->rpframe * B + 4096);
+    }
     if (!rc) rc = dev_alloc(&h->raw, h->rframe * B);
     if (!rc) rc = dev_alloc(&h->cost, h->rframe * B);
     if (!rc) rc = dev_alloc(&h->tex, h->rframe * B);
@@ -284,10 +292,11 @@ static int bm_chunk_for(const rtdm_bm *h, int n, int W, int H)
     if (n < 16 || h->p.blockSize >= W || h->p.blockSize >= H) return chunk;
     const BmGeom g = bm_geom(h, W, H);
     if (h->sw.bm_kernel == 1 || h->sw.bm_kernel == 2) return chunk;
+    const bool k4 = h->sw.bm_kernel != 3 && h->LE && bm_sad4_supported(g, n);
     long long best = -1;
     for (int m = std::max(8, n / 4); m < n; m++) {
         const int k = (n + m - 1) / m, last = n - (k - 1) * m;
-        const long long c1 = bm_sad3_cost(g, m), c2 = bm_sad3_cost(g, last);
+        const long long c1 = k4 ? bm_sad4_cost(g, m) : bm_sad3_cost(g, m), c2 = k4 ? bm_sad4_cost(g, last) : bm_sad3_cost(g, last);
         if (c1 < 0 || c2 < 0) return chunk;
         const long long score = ((k - 1) * c1 + c2) * 16 + k;       // fewer row steps first, then fewer chunks
         if (best < 0 || score < best) { best = score; chunk = m; }
@@ -328,20 +337,29 @@ static int bm_pipeline(rtdm_bm *h, int n, PlaneU8 L, PlaneU8 R, int W, int H, Pl
     PlaneS16 cost = {h->cost + (size_t)f0 * h->rframe, h->rpitch, h->rframe};
     int32_t *wlab = h->labels + (size_t)f0 * W * H, *wsiz = h->sizes + (size_t)f0 * W * H, *wrun = h->runlen + (size_t)f0 * W * H;
     mark();
+    bool fast4 = false;
     if (row1 > row0) {
         PlaneU8W oL = {wLp, h->ppitch, h->pframe}, oR = {wRp, h->ppitch, h->pframe};
-        rc = launch_prefilter(p.preFilterType, p.preFilterSize, p.preFilterCap, n, W, H, L, R, oL, oR, st, &h->launches);
+        // Switches::bm_kernel = 1 forces the generic kernel (A/B runs and tests); default: fast path when it applies
+        const bool fast = h->sw.bm_kernel != 1 && bm_sad2_supported(g, n);
+        // bm_kernel = 2 keeps the bm_sad2.cu kernel where the warp-specialised kernels would apply, 3 the bm_sad3.cu kernel
+        const bool fast3 = fast && h->sw.bm_kernel != 2 && bm_sad3_supported(g, n);
+        fast4 = fast3 && h->sw.bm_kernel != 3 && h->LE && bm_sad4_supported(g, n);
+        const BmStaged sp = {h->LE + (size_t)f0 * h->leframe, h->lepitch, h->leframe, h->RPs + (size_t)f0 * h->rpframe, h->rppitch, h->rpframe};
+        rc = launch_prefilter(p.preFilterType, p.preFilterSize, p.preFilterCap, n, W, H, L, R, oL, oR, st, &h->launches, fast4 ? &sp : nullptr);
         if (rc) return rc;
         mark();
         PlaneU8 iL = {wLp, h->ppitch, h->pframe}, iR = {wRp, h->ppitch, h->pframe};
-        // Switches::bm_kernel = 1 forces the generic kernel (A/B runs and tests); default: fast path when it applies
-        const bool fast = h->sw.bm_kernel != 1 && bm_sad2_supported(g, n);
-        // bm_kernel = 2 keeps the bm_sad2.cu kernel where the warp-specialised bm_sad3.cu kernel would apply
-        const bool fast3 = fast && h->sw.bm_kernel != 2 && bm_sad3_supported(g, n);
-        if (fast)
+        if (fast4) {
+            uint16_t *tex = h->tex + (size_t)f0 * h->rframe;
+            rc = launch_bm_texture(g, n, iL, tex, h->rpitch, h->rframe, st);
+            if (!rc) rc = launch_bm_sad4_core(g, n, sp, raw, cost, tex, h->rpitch, h->rframe, st);
+            h->launches += 2;
+        } else if (fast)
             rc = launch_bm_sad2(g, n, iL, iR, raw, cost, h->tex + (size_t)f0 * h->rframe, h->rpitch, h->rframe, st, &h->launches, fast3);
         else
             rc = launch_bm_sad_wta(g, n, iL, iR, raw, cost, st, &h->launches);
+        if (fast4) h->last_kernel = 4; else
         h->last_kernel = fast3 ? 3 : (fast ? 2 : 1);
         if (rc) return rc;
         mark();
@@ -545,7 +563,10 @@ extern "C" int rtdm_bm_debug_fetch(rtdm_bm *h, int what, void *dst, size_t dst_b
     const int W = h->lastW, H = h->lastH;
     if (what == 0 || what == 1) {
         if (dst_bytes < (size_t)W * H) return -RTDM_EINVAL;
-        RTDM_CUDA(cudaMemcpy2D(dst, W, what ? h->Rp : h->Lp, h->ppitch, W, H, cudaMemcpyDeviceToHost));
+        if (what == 1 && h->last_kernel == 4)       // the right image only exists in its staged layout
+            RTDM_CUDA(cudaMemcpy2D(dst, W, h->RPs + BmStaged::RPADL, h->rppitch, W, H, cudaMemcpyDeviceToHost));
+        else
+            RTDM_CUDA(cudaMemcpy2D(dst, W, what ? h->Rp : h->Lp, h->ppitch, W, H, cudaMemcpyDeviceToHost));
     } else if (what == 2 || what == 3) {
         if (dst_bytes < (size_t)W * H * 2) return -RTDM_EINVAL;
         RTDM_CUDA(cudaMemcpy2D(dst, (size_t)W * 2, what == 3 ? h->cost : h->raw, h->rpitch * 2, (size_t)W * 2, H, cudaMemcpyDeviceToHost));

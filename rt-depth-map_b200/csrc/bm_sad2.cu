@@ -523,6 +523,24 @@ bool bm_sad2_supported(const BmGeom &g, int n)
     return g.W1 >= 1 && g.row1 > g.row0 && pick_tiling2(g, n, &t);
 }
 
+int launch_bm_texture(const BmGeom &g, int n, PlaneU8 Lp, uint16_t *tex, size_t tex_pitch, size_t tex_frame, cudaStream_t st)
+{
+    const int h = g.bs / 2;
+    dim3 grid(cdiv(cdiv(g.W1, 4), TXT), cdiv(g.row1 - g.row0, TXH), n);
+#define RTDM_TEX_CASE(H_) bm_texture_kernel<H_><<<grid, TXT, 0, st>>>(Lp, tex, tex_pitch, tex_frame, g.W, g.H, g.nd, g.cap, g.W1, g.row0, g.row1)
+    switch (h) {
+        case 2: RTDM_TEX_CASE(2); break;
+        case 3: RTDM_TEX_CASE(3); break;
+        case 4: RTDM_TEX_CASE(4); break;
+        case 5: RTDM_TEX_CASE(5); break;
+        case 6: RTDM_TEX_CASE(6); break;
+        default: RTDM_TEX_CASE(7); break;
+    }
+#undef RTDM_TEX_CASE
+    RTDM_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // tex: scratch of n * H * tex_pitch uint16
 int launch_bm_sad2(const BmGeom &g, int n, PlaneU8 Lp, PlaneU8 Rp, PlaneS16 disp, PlaneS16 cost,
                    uint16_t *tex, size_t tex_pitch, size_t tex_frame, cudaStream_t st, int *launches, bool use3)
@@ -531,17 +549,8 @@ int launch_bm_sad2(const BmGeom &g, int n, PlaneU8 Lp, PlaneU8 Rp, PlaneS16 disp
     if (!pick_tiling2(g, n, &t)) { set_error("bm_sad2: unsupported geometry"); return -RTDM_EINVAL; }
     const int h = g.bs / 2;
     {
-        dim3 grid(cdiv(cdiv(g.W1, 4), TXT), cdiv(g.row1 - g.row0, TXH), n);
-#define RTDM_TEX_CASE(H_) bm_texture_kernel<H_><<<grid, TXT, 0, st>>>(Lp, tex, tex_pitch, tex_frame, g.W, g.H, g.nd, g.cap, g.W1, g.row0, g.row1)
-        switch (h) {
-            case 2: RTDM_TEX_CASE(2); break;
-            case 3: RTDM_TEX_CASE(3); break;
-            case 4: RTDM_TEX_CASE(4); break;
-            case 5: RTDM_TEX_CASE(5); break;
-            case 6: RTDM_TEX_CASE(6); break;
-            default: RTDM_TEX_CASE(7); break;
-        }
-#undef RTDM_TEX_CASE
+        const int rct = launch_bm_texture(g, n, Lp, tex, tex_pitch, tex_frame, st);
+        if (rct) return rct;
     }
     if (use3) {
         const int rc3 = launch_bm_sad3_core(g, n, Lp, Rp, disp, cost, tex, tex_pitch, tex_frame, st);

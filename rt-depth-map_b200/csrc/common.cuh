@@ -29,7 +29,7 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 // compute path of a live handle.  None of them changes a result; the one that did (RTDM_BM_DEBUG, which skips whole
 // stages for timing ablations) only exists in builds with -DRTDM_DEV.
 struct Switches {
-    int bm_kernel = 0;          // RTDM_BM_KERNEL: 1 = generic bm_sad.cu, 2 = bm_sad2.cu where bm_sad3.cu would run
+    int bm_kernel = 0;          // RTDM_BM_KERNEL: 1 = generic bm_sad.cu, 2 = bm_sad2.cu, 3 = bm_sad3.cu where bm_sad4.cu would run
     int bm3_shape = 0;          // RTDM_BM3_SHAPE: 1 = two 384-thread CTAs per SM
     int bm_chunk = 0;           // RTDM_BM_CHUNK: frames per chunk of the host batch pipeline (0 = automatic)
     int bm_variant = 1;         // RTDM_BM_VARIANT (bm_sad2.cu CTA variants)
@@ -47,11 +47,24 @@ struct PlaneU8 { const uint8_t *p; size_t pitch; size_t frame; };
 struct PlaneU8W { uint8_t *p; size_t pitch; size_t frame; };
 struct PlaneS16 { int16_t *p; size_t pitch; size_t frame; };   // pitch / frame in ELEMENTS
 
+// Prefiltered planes in the layouts bm_sad4.cu's bulk copies read (all pitches / frame steps in ELEMENTS):
+//   LE  u32 [frame][H][le_pitch]: LE[LPADL + x] = left pixel x times 0x01010101 for x < W, the last pixel again for W <= x < W + LPADR
+//   RP  u8  [frame][H][rp_pitch]: RP[RPADL + x] = right pixel x; RPADL copies of pixel 0 before, RPADR copies of pixel W - 1 after
+// Row starts are 16-byte aligned (le_pitch % 4 == 0, rp_pitch % 16 == 0); the planes end with >= 4 KB of slack (a copy may
+// run past the last row).  The replicated columns are App. A.2's clamps.  LPADL = 1 makes the first left column of every
+// stripe (x0 - HP + numDisparities - 1, x0 and HP multiples of 4) a 16-byte boundary.
+struct BmStaged {
+    static constexpr int LPADL = 1, LPADR = 8, RPADL = 16, RPADR = 16;
+    uint32_t *LE; size_t le_pitch, le_frame;
+    uint8_t *RP; size_t rp_pitch, rp_frame;
+};
+
 // ---- prefilter (prefilter.cu) ------------------------------------------------------------------
-// type: RTDM_PREFILTER_*.  Both images of all n frames in one launch.
+// type: RTDM_PREFILTER_*.  Both images of all n frames in one launch.  With `staged` the left image is written twice
+// (plain plane outL for the texture kernel + expanded plane) and the right image only in its staged layout (outR unused).
 int launch_prefilter(int type, int winsize, int cap, int n, int W, int H,
                      PlaneU8 left, PlaneU8 right, PlaneU8W outL, PlaneU8W outR,
-                     cudaStream_t st, int *launches);
+                     cudaStream_t st, int *launches, const BmStaged *staged = nullptr);
 
 // ---- block matching core (bm_sad.cu) -----------------------------------------------------------
 struct BmGeom {
@@ -77,6 +90,14 @@ bool bm_sad3_supported(const BmGeom &g, int n);
 long long bm_sad3_cost(const BmGeom &g, int n);
 int launch_bm_sad3_core(const BmGeom &g, int n, PlaneU8 Lp, PlaneU8 Rp, PlaneS16 disp, PlaneS16 cost,
                         const uint16_t *tex, size_t tex_pitch, size_t tex_frame, cudaStream_t st);
+
+// TMA-staged warp-specialised fast path (bm_sad4.cu): same domain as bm_sad3.cu; reads the BmStaged planes
+bool bm_sad4_supported(const BmGeom &g, int n);
+long long bm_sad4_cost(const BmGeom &g, int n);
+int launch_bm_sad4_core(const BmGeom &g, int n, const BmStaged &sp, PlaneS16 disp, PlaneS16 cost,
+                        const uint16_t *tex, size_t tex_pitch, size_t tex_frame, cudaStream_t st);
+// texture window sums of the prefiltered left image (bm_sad2.cu: bm_texture_kernel), blockSize 5 .. 15
+int launch_bm_texture(const BmGeom &g, int n, PlaneU8 Lp, uint16_t *tex, size_t tex_pitch, size_t tex_frame, cudaStream_t st);
 
 // ---- post-processing (postproc.cu) -------------------------------------------------------------
 // validateDisparity (if d12 >= 0) + valid-rect mask; reads raw disp/cost, writes `out`

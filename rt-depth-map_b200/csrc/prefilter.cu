@@ -10,11 +10,55 @@ namespace rtdm {
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
 
+// ---- the layouts bm_sad4.cu stages with TMA (common.cuh: BmStaged); LE == nullptr: not wanted ------------------
+__device__ __forceinline__ uint4 splat4(uint32_t v) { return make_uint4(v, v, v, v); }
+// one aligned word o = pixels x0 .. x0+3 of row y (all inside the image; x0 % 4 == 0)
+__device__ __forceinline__ void staged_store_word(const BmStaged &s, int img, int f, int y, int x0, uint32_t o, bool first, bool last)
+{
+    if (img == 0) {
+        uint32_t *e = s.LE + (size_t)f * s.le_frame + (size_t)y * s.le_pitch + BmStaged::LPADL + x0;     // 4 (mod 16) bytes
+        e[0] = __byte_perm(o, 0, 0x0000); e[1] = __byte_perm(o, 0, 0x1111); e[2] = __byte_perm(o, 0, 0x2222); e[3] = __byte_perm(o, 0, 0x3333);
+        if (first) e[-1] = e[0];
+        if (last) {
+            const uint32_t v = __byte_perm(o, 0, 0x3333);
+#pragma unroll
+            for (int i = 0; i < BmStaged::LPADR; i++) e[4 + i] = v;
+        }
+    } else {
+        uint8_t *r = s.RP + (size_t)f * s.rp_frame + (size_t)y * s.rp_pitch;
+        *reinterpret_cast<uint32_t *>(r + BmStaged::RPADL + x0) = o;
+        if (first) *reinterpret_cast<uint4 *>(r) = splat4(__byte_perm(o, 0, 0x0000));                // BmStaged::RPADL = 16
+        if (last) {
+            const uint32_t v = __byte_perm(o, 0, 0x3333);
+            uint32_t *t = reinterpret_cast<uint32_t *>(r + BmStaged::RPADL + x0 + 4);
+            t[0] = v; t[1] = v; t[2] = v; t[3] = v;                                                   // BmStaged::RPADR = 16
+        }
+    }
+}
+// one pixel (any width / alignment)
+__device__ __forceinline__ void staged_store_px(const BmStaged &s, int img, int f, int y, int x, int W, uint32_t v)
+{
+    if (img == 0) {
+        uint32_t *e = s.LE + (size_t)f * s.le_frame + (size_t)y * s.le_pitch + BmStaged::LPADL;
+        e[x] = v * 0x01010101u;
+        if (x == 0) e[-1] = v * 0x01010101u;
+        if (x == W - 1)
+            for (int i = 0; i < BmStaged::LPADR; i++) e[W + i] = v * 0x01010101u;
+    } else {
+        uint8_t *r = s.RP + (size_t)f * s.rp_frame + (size_t)y * s.rp_pitch;
+        r[BmStaged::RPADL + x] = (uint8_t)v;
+        if (x == 0)
+            for (int i = 0; i < BmStaged::RPADL; i++) r[i] = (uint8_t)v;
+        if (x == W - 1)
+            for (int i = 0; i < BmStaged::RPADR; i++) r[BmStaged::RPADL + W + i] = (uint8_t)v;
+    }
+}
+
 // x-Sobel: dst = clip(d(y-1) + 2 d(y) + d(y+1), -cap, cap) + cap with d(r) = r[x+1]-r[x-1];
 // rows reflect-101, first/last column = cap, and an odd last row = cap (OpenCV pairs rows).
 __global__ void __launch_bounds__(256)
 prefilter_xsobel_kernel(PlaneU8 left, PlaneU8 right, PlaneU8W outL, PlaneU8W outR,
-                        int W, int H, int cap)
+                        int W, int H, int cap, BmStaged sg)
 {
     const int img = blockIdx.z & 1, f = blockIdx.z >> 1;
     const uint8_t *src = (img ? right.p + (size_t)f * right.frame : left.p + (size_t)f * left.frame);
@@ -48,6 +92,10 @@ prefilter_xsobel_kernel(PlaneU8 left, PlaneU8 right, PlaneU8W outL, PlaneU8W out
             o[i] = (uint8_t)v;
         }
     }
+    if (sg.LE) {
+        for (int i = 0; i < 4 && x0 + i < W; i++) staged_store_px(sg, img, f, y, x0 + i, W, o[i]);
+        if (img) return;
+    }
     uint8_t *d = dst + (size_t)y * dp + x0;
     if (x0 + 3 < W && ((reinterpret_cast<uintptr_t>(d) & 3) == 0)) {
         *reinterpret_cast<uchar4 *>(d) = make_uchar4(o[0], o[1], o[2], o[3]);
@@ -73,7 +121,7 @@ __device__ __forceinline__ void sobel_row_diff(const uint8_t *row, int wi, int n
 }
 
 __global__ void __launch_bounds__(128)
-prefilter_xsobel4_kernel(PlaneU8 left, PlaneU8 right, PlaneU8W outL, PlaneU8W outR, int W, int H, int cap)
+prefilter_xsobel4_kernel(PlaneU8 left, PlaneU8 right, PlaneU8W outL, PlaneU8W outR, int W, int H, int cap, BmStaged sg)
 {
     const int img = blockIdx.z & 1, f = blockIdx.z >> 1;
     const uint8_t *src = (img ? right.p + (size_t)f * right.frame : left.p + (size_t)f * left.frame);
@@ -104,7 +152,8 @@ prefilter_xsobel4_kernel(PlaneU8 left, PlaneU8 right, PlaneU8W outL, PlaneU8W ou
             if (wi == nw - 1) o = (o & 0x00FFFFFFu) | ((uint32_t)cap << 24);
             pl = cl; ph = ch; cl = nl; ch = nh;
         }
-        *d = o;
+        if (sg.LE) staged_store_word(sg, img, f, y, 4 * wi, o, wi == 0, wi == nw - 1);
+        if (!sg.LE || !img) *d = o;
         d = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(d) + dp);
     }
 }
@@ -114,7 +163,7 @@ prefilter_xsobel4_kernel(PlaneU8 left, PlaneU8 right, PlaneU8W outL, PlaneU8W ou
 // which never wrap 16 bits for ws <= 255).
 __global__ void __launch_bounds__(256)
 prefilter_norm_kernel(PlaneU8 left, PlaneU8 right, PlaneU8W outL, PlaneU8W outR,
-                      int W, int H, int ws, int cap)
+                      int W, int H, int ws, int cap, BmStaged stg)
 {
     const int img = blockIdx.z & 1, f = blockIdx.z >> 1;
     const uint8_t *src = (img ? right.p + (size_t)f * right.frame : left.p + (size_t)f * left.frame);
@@ -137,27 +186,34 @@ prefilter_norm_kernel(PlaneU8 left, PlaneU8 right, PlaneU8W outL, PlaneU8W outR,
     const int c = cur[x], l = cur[max(x - 1, 0)], r = cur[min(x + 1, W - 1)];
     const int u = src[(size_t)max(y - 1, 0) * sp + x], d = src[(size_t)min(y + 1, H - 1) * sp + x];
     int val = ((4 * c + l + r + u + d) * sg - sum * ss) >> 10;
-    dst[(size_t)y * dp + x] = (uint8_t)(clampi(val, -cap, cap) + cap);
+    const uint32_t o = (uint32_t)(clampi(val, -cap, cap) + cap);
+    if (stg.LE) {
+        staged_store_px(stg, img, f, y, x, W, o);
+        if (img) return;
+    }
+    dst[(size_t)y * dp + x] = (uint8_t)o;
 }
 
 int launch_prefilter(int type, int winsize, int cap, int n, int W, int H,
                      PlaneU8 left, PlaneU8 right, PlaneU8W outL, PlaneU8W outR,
-                     cudaStream_t st, int *launches)
+                     cudaStream_t st, int *launches, const BmStaged *staged)
 {
     if (n <= 0) return 0;
+    BmStaged sg = {nullptr, 0, 0, nullptr, 0, 0};
+    if (staged) sg = *staged;
     if (type == RTDM_PREFILTER_XSOBEL) {
         const auto al4 = [](const void *p, size_t pitch, size_t frame) { return ((reinterpret_cast<uintptr_t>(p) | pitch | frame) & 3) == 0; };
         if (W % 4 == 0 && W >= 8 && al4(left.p, left.pitch, left.frame) && al4(right.p, right.pitch, right.frame) &&
-            al4(outL.p, outL.pitch, outL.frame) && al4(outR.p, outR.pitch, outR.frame)) {
+            al4(outL.p, outL.pitch, outL.frame) && (staged || al4(outR.p, outR.pitch, outR.frame))) {
             dim3 grid(cdiv(W / 4, 128), cdiv(H, PFB), 2 * n);
-            prefilter_xsobel4_kernel<<<grid, 128, 0, st>>>(left, right, outL, outR, W, H, cap);
+            prefilter_xsobel4_kernel<<<grid, 128, 0, st>>>(left, right, outL, outR, W, H, cap, sg);
         } else {
             dim3 grid(cdiv(cdiv(W, 4), 256), H, 2 * n);
-            prefilter_xsobel_kernel<<<grid, 256, 0, st>>>(left, right, outL, outR, W, H, cap);
+            prefilter_xsobel_kernel<<<grid, 256, 0, st>>>(left, right, outL, outR, W, H, cap, sg);
         }
     } else {
         dim3 grid(cdiv(W, 256), H, 2 * n);
-        prefilter_norm_kernel<<<grid, 256, 0, st>>>(left, right, outL, outR, W, H, winsize, cap);
+        prefilter_norm_kernel<<<grid, 256, 0, st>>>(left, right, outL, outR, W, H, winsize, cap, sg);
     }
     if (launches) (*launches)++;
     RTDM_CUDA(cudaGetLastError());

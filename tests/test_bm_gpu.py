@@ -10,15 +10,17 @@ from conftest import golden_names, load_golden
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["fast", "fast2", "generic"])
+@pytest.fixture(params=["fast", "fast3", "fast2", "generic"])
 def bm_kernel(request, monkeypatch):
-    """Runs a test once per SAD/WTA kernel: the default selection (warp-specialised bm_sad3.cu where it applies,
-    else bm_sad2.cu, else generic), bm_sad2.cu kept where bm_sad3.cu would run (RTDM_BM_KERNEL=2), and the
+    """Runs a test once per SAD/WTA kernel: the default selection (TMA-staged bm_sad4.cu where it applies, else
+    bm_sad2.cu, else generic), bm_sad3.cu / bm_sad2.cu kept where bm_sad4.cu would run (RTDM_BM_KERNEL=3 / 2), and the
     generic kernel (bm_sad.cu, RTDM_BM_KERNEL=1)."""
     if request.param == "generic":
         monkeypatch.setenv("RTDM_BM_KERNEL", "1")
     elif request.param == "fast2":
         monkeypatch.setenv("RTDM_BM_KERNEL", "2")
+    elif request.param == "fast3":
+        monkeypatch.setenv("RTDM_BM_KERNEL", "3")
     else:
         monkeypatch.delenv("RTDM_BM_KERNEL", raising=False)
     return request.param
@@ -27,8 +29,8 @@ def bm_kernel(request, monkeypatch):
 def _expected_kernel(bm_kernel, p):
     if bm_kernel == "generic" or p["blockSize"] > 15 or p["minDisparity"] != 0:
         return 1
-    if bm_kernel == "fast" and p["numDisparities"] in (32, 48, 64, 96, 128, 192, 256):
-        return 3
+    if bm_kernel in ("fast", "fast3") and p["numDisparities"] in (32, 48, 64, 96, 128, 192, 256):
+        return 4 if bm_kernel == "fast" else 3
     return 2
 
 
@@ -67,7 +69,7 @@ def test_bm_matches_cv2_golden(gpu, name, bm_kernel):
     assert got.dtype == np.int16 and got.shape == (H, W)
     assert np.array_equal(got, g["disp"]), f"{name} [{bm_kernel}]: {(got != g['disp']).sum()} pixels differ"
     assert m.last_launches() > 0
-    assert m.last_kernel() == _expected_kernel(bm_kernel, p), "kernel selection (generic / bm_sad2 / bm_sad3)"
+    assert m.last_kernel() == _expected_kernel(bm_kernel, p), "kernel selection (generic / bm_sad2 / bm_sad3 / bm_sad4)"
 
 
 def test_bm_stages_match_oracle(gpu, orc, bm_kernel):
@@ -113,15 +115,20 @@ def test_bm_random_params_match_oracle(gpu, orc, bm_kernel):
     assert checked >= 10
 
 
+@pytest.mark.parametrize("kern", [4, 3])
 @pytest.mark.parametrize("bs", [5, 7, 9, 11, 13, 15])
 @pytest.mark.parametrize("nd", [32, 48, 64, 96, 128, 192, 256])
-def test_bm_warp_specialised_kernel_matrix(gpu, orc, nd, bs):
-    """bm_sad3.cu over its whole domain (blockSize 5 .. 15 x numDisparities 32 / 48 / 64 / 96 / 128 / 192 / 256;
+def test_bm_warp_specialised_kernel_matrix(gpu, orc, nd, bs, kern, monkeypatch):
+    """bm_sad4.cu (TMA-staged) and bm_sad3.cu over their whole domain (blockSize 5 .. 15 x numDisparities 32 / 48 / 64 / 96 / 128 / 192 / 256;
     192, 96 and 48 are what the reference's default -nd 192 scales to at 1280, 640 and 320 pixels of width): stripe borders (clamped
     columns on both image sides), widths that are not a multiple of anything, odd heights, ROIs, texture and
     uniqueness thresholds on and off, and every prefilter cap parity; raw WTA output and cost against the oracle's
     core as well as the final map."""
     from rtdm_b200 import synth
+    if kern == 3:
+        monkeypatch.setenv("RTDM_BM_KERNEL", "3")
+    else:
+        monkeypatch.delenv("RTDM_BM_KERNEL", raising=False)
     rng = np.random.default_rng(100 * nd + bs)
     for i, (W, H) in enumerate([(nd + 40, 61), (333, 127), (640, 203), (nd + bs + 3, 40)]):
         p = dict(preFilterCap=int(rng.integers(1, 32)), blockSize=bs, minDisparity=0,
@@ -133,7 +140,7 @@ def test_bm_warp_specialised_kernel_matrix(gpu, orc, nd, bs):
         L, R, _ = synth.stereo_pair(W, H, nd, 4000 + 10 * nd + bs + i)
         m = _mk(gpu, p, W, H)
         got = m.compute(L, R)
-        assert m.last_kernel() == 3
+        assert m.last_kernel() == kern
         assert np.array_equal(got, orc.bm_compute(L, R, _orc_params(orc, p))), (p, W, H)
         if p.get("roi1") is None:
             Lp, Rp = orc.prefilter_xsobel(L, p["preFilterCap"]), orc.prefilter_xsobel(R, p["preFilterCap"])
@@ -275,13 +282,17 @@ def test_bm_large_frame_256_disparities(gpu, orc):
         assert np.array_equal(got, ref), (bs, int((got != ref).sum()))
 
 
-@pytest.mark.parametrize("shape", ["wide", "pair"])
+@pytest.mark.parametrize("shape", ["tma", "wide", "pair"])
 def test_bm_warp_specialised_kernel_is_deterministic_under_load(gpu, orc, shape, monkeypatch):
-    """The producer / consumer / loader warps of bm_sad3.cu hand rows over through named barriers and a shared-memory
-    ring: a protocol slip would show up as a rare, timing-dependent difference.  24 launches of a 12-frame 720p batch
-    (both CTA shapes) must all equal the oracle's maps."""
+    """The producer / winner-take-all warps of bm_sad4.cu / bm_sad3.cu hand rows over through named barriers, mbarriers and
+    a shared-memory ring (fed by TMA in bm_sad4.cu, by loader warps in bm_sad3.cu): a protocol slip would show up as a
+    rare, timing-dependent difference.  24 launches of a 12-frame 720p batch (bm_sad4.cu and both CTA shapes of
+    bm_sad3.cu) must all equal the oracle's maps."""
     from rtdm_b200 import synth
-    monkeypatch.delenv("RTDM_BM_KERNEL", raising=False)
+    if shape == "tma":
+        monkeypatch.delenv("RTDM_BM_KERNEL", raising=False)
+    else:
+        monkeypatch.setenv("RTDM_BM_KERNEL", "3")
     monkeypatch.setenv("RTDM_BM3_SHAPE", "1" if shape == "pair" else "0")
     p = dict(preFilterCap=31, blockSize=13, minDisparity=0, textureThreshold=10, numDisparities=128,
              uniquenessRatio=10, speckleWindowSize=100, speckleRange=32, disp12MaxDiff=1)
@@ -292,7 +303,7 @@ def test_bm_warp_specialised_kernel_is_deterministic_under_load(gpu, orc, shape,
     m = _mk(gpu, p, 1280, 720, max_batch=B)
     for rep in range(24):
         out = m.compute_batch(Ls, Rs)
-        assert m.last_kernel() == 3
+        assert m.last_kernel() == (4 if shape == "tma" else 3)
         for i in range(B):
             assert np.array_equal(out[i], ref[i % 3]), (shape, rep, i, int((out[i] != ref[i % 3]).sum()))
 
@@ -370,7 +381,7 @@ def test_bm_streaming_63_frame_720p_batches(gpu, orc):
         if s >= 1:
             m.wait_oldest()
     m.wait()
-    assert m.last_kernel() == 3
+    assert m.last_kernel() == 4
     for s in (1, 2):
         assert np.array_equal(np.roll(outs[s], -7 * s, axis=0), outs[0]), s
     for i in (0, 1, 15, 16, 20, 21, 27, 28, 31, 32, 34, 35, 41, 42, 47, 48, 62):
