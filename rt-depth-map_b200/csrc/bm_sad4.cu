@@ -12,10 +12,10 @@
 //     asynchronous copies (cp.async.bulk.shared.global, SASS UBLKCP: one left, one right) issued by ONE elected lane per
 //     row and signalled on an mbarrier per ring slot (SYNCS); the border clamps of App. A.2 are the replicated columns,
 //     what a copy reads beyond them only feeds pixels that are never written.  No loader warps, no descriptors, no byte
-//     gathers in the band start-up.  Bulk copies need 16-byte aligned sources: stripes start at multiples of 4 pixels, the
-//     virtual-column origin of a stripe is x0 - HP with HP = h rounded up to 4 (HP - h idle columns), the expanded plane
-//     stores pixel x at element x + 1 (numDisparities - 1 = 3 mod 4), and the right row is copied from the 16-byte
-//     boundary below its first byte.  (The tensor-map form, cp.async.bulk.tensor / UTMALDG, raises "illegal instruction"
+//     gathers in the band start-up.  Bulk copies need 16-byte aligned sources: stripe s starts at pixel s * TW - (HP - h)
+//     with TW a multiple of 4 and HP = h rounded up to 4, so that its first virtual column x0 - h is a multiple of 4 (the
+//     HP - h pixels left of the image in stripe 0 are computed and dropped), the expanded plane stores pixel x at element
+//     x + 1 (numDisparities - 1 = 3 mod 4), and the right row is copied from the 16-byte boundary below its first byte.  (The tensor-map form, cp.async.bulk.tensor / UTMALDG, raises "illegal instruction"
 //     on this pool's B200s in every variant tried -- tools/probe/tma_probe.cu -- while the bulk form runs.)
 //   * No mirrored copies.  The second half ("B") of a column group emits its in-half SUFFIX sums from the same forward
 //     rows with its own compile-time shifts (warps are type-uniform), so every sum in shared memory is in forward
@@ -40,7 +40,8 @@ namespace rtdm {
 namespace {
 
 constexpr int NCW4 = 6;                    // winner-take-all warps (<= 192 pixels per stripe)
-constexpr int MAXT4 = 704;                 // 16 producer warps + NCW4
+constexpr int NFW4 = 1;                    // feeder warp: one lane issues the bulk copies of the ring
+constexpr int MAXT4 = 736;                 // 16 producer warps + NCW4 + NFW4
 constexpr int RING_EXTRA = 2;              // ring rows in flight beyond the 2h + 3 live ones
 
 __host__ __device__ constexpr int ring_rows4(int h) { return 2 * h + 3 + RING_EXTRA; }
@@ -73,7 +74,7 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar) : "memory");
 }
-__host__ __device__ constexpr int hp_of(int h) { return (h + 3) & ~3; }     // virtual-column origin of a stripe: x0 - hp_of(h)
+__host__ __device__ constexpr int hp_of(int h) { return (h + 3) & ~3; }     // stripe s starts at pixel s * TW - (hp_of(h) - h)
 
 struct Bm4Args {
     PlaneS16 disp, cost;
@@ -176,7 +177,6 @@ __device__ __forceinline__ void producer4(uint8_t *smem, const Geo4 &q, const Bm
     constexpr int ND = NO_ * 8, PP = ND * 2 + 16, MNP = mnp_bytes4(ND);
     constexpr int SPW = 32 / NO_;                             // groups per producer warp
     constexpr int isB = ISB ? 1 : 0;
-    constexpr int HP = hp_of(H_);
     const int tid = threadIdx.x;
     uint8_t *Ring = smem + q.RINGOFF;
         // even producer warps hold A halves, odd warps B halves (type-uniform warps).  Even h: a warp holds SPW adjacent
@@ -188,11 +188,11 @@ __device__ __forceinline__ void producer4(uint8_t *smem, const Geo4 &q, const Bm
         const bool live = g < a.NG && sub < SPW;                  // trailing groups may not exist; 32 % NO_ lanes of a warp stay idle
         const int cb = g * G + (isB ? H_ : 0);                    // first virtual column of this thread (forward order, both types)
         const int lbo = 4 * cb;                                   // expanded left row: one word per column
-        const int rsh = (x0 - HP + BmStaged::RPADL) & 12;          // the right row was copied from the 16-byte boundary below its first byte
+        const int rsh = (x0 - H_ + BmStaged::RPADL) & 12;          // the right row was copied from the 16-byte boundary below its first byte
         const int rbo = q.LFB + rsh + cb + 8 * j;                 // right row: byte stream
         const int roff = cb & 3;                                  // even h: 0 (A) / h & 3 (B); odd h: warp-uniform
-        // R clamp (App. A.2, minD = 0): rbase(xc) = clip(xc, 0, W - nd); in virtual columns c = xc - x0 + HP
-        const int cmin = HP - x0, cmax = (a.W - ND) - x0 + HP;
+        // R clamp (App. A.2, minD = 0): rbase(xc) = clip(xc, 0, W - nd); in virtual columns c = xc - x0 + h
+        const int cmin = H_ - x0, cmax = (a.W - ND) - x0 + H_;
         uint32_t clmask = 0;
         int crc = 0;
 #pragma unroll
@@ -390,14 +390,14 @@ bm_sad4_kernel(Bm4Args a)
     constexpr int SPW = 32 / NO_;                             // groups per producer warp
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int tid = threadIdx.x, f = blockIdx.z;
-    const int x0 = blockIdx.x * a.TW;
+    const int x0 = blockIdx.x * a.TW - (HP - H_);             // first pixel of the stripe (negative in stripe 0 when h % 4 != 0)
     const int TWc = min(a.TW, a.W1 - x0);
     const int y0 = a.row0 + blockIdx.y * a.BH, y1 = min(y0 + a.BH, a.row1);
     if (TWc <= 0 || y0 >= y1) return;
     uint8_t *smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
     const Geo4 q = make_geo4(H_, ND, a.NG);
     const int NPT = producer_threads4(H_, NO_, a.NG);
-    const int NT = NPT + NCW4 * 32;
+    const int NT = NPT + (NCW4 + NFW4) * 32;
     uint8_t *Ring = smem + q.RINGOFF;
     const uint32_t ring_s = smem_u32(Ring), bar_s = smem_u32(smem + q.BAROFF);
     const int lofs = ND - 1;
@@ -436,33 +436,45 @@ bm_sad4_kernel(Bm4Args a)
         }
     } else {
         // =========================================================================================
-        // winner-take-all warps (lane 0 of the first one also feeds the TMA ring)
+        // winner-take-all warps and the feeder warp of the TMA ring
         // =========================================================================================
         const int ct = tid - NPT, cw = ct >> 5, lane = ct & 31;
-        const bool feeder = ct == 0;
-        const uint32_t lbytes = (uint32_t)(4 * q.NCTP), rbytes = (uint32_t)q.RBY;
-        // first virtual column = image column x0 - HP (right) / x0 - HP + lofs (left); both copies start 16-byte aligned
-        const uint32_t *srcL = a.sp.LE + (size_t)f * a.sp.le_frame + (x0 - HP + lofs + BmStaged::LPADL);
-        const uint8_t *srcR = a.sp.RP + (size_t)f * a.sp.rp_frame + ((x0 - HP + BmStaged::RPADL) & ~15);
-        auto feed = [&](int t) {                                  // band-relative ring row t -> slot t % RING
-            const int s = t % RING;
-            const int gy = clampi4(y0 - H_ - 1 + t, 0, a.H - 1);
-            const uint32_t bar = bar_s + 8 * s, dst = ring_s + s * q.SLOT;
-            mbar_expect_tx(bar, lbytes + rbytes);
-            bulk_load(dst, srcL + (size_t)gy * a.sp.le_pitch, lbytes, bar);
-            bulk_load(dst + q.LFB, srcR + (size_t)gy * a.sp.rp_pitch, rbytes, bar);
-        };
-        if (feeder)
-            for (int t = 0; t < RING && t <= t_last; t++) feed(t);
+        if (cw == NCW4) {
+            // ---- feeder warp: lane 0 keeps the ring RING_EXTRA rows ahead of the producers -----------------------
+            const uint32_t lbytes = (uint32_t)(4 * q.NCTP), rbytes = (uint32_t)q.RBY;
+            // first virtual column = image column x0 - h (right) / x0 - h + lofs (left); both copies start 16-byte aligned
+            const uint32_t *srcL = a.sp.LE + (size_t)f * a.sp.le_frame + (x0 - H_ + lofs + BmStaged::LPADL);
+            const uint8_t *srcR = a.sp.RP + (size_t)f * a.sp.rp_frame + ((x0 - H_ + BmStaged::RPADL) & ~15);
+            int slot = 0;
+            auto feed = [&](int t) {                              // band-relative ring row t -> the next slot
+                const int gy = clampi4(y0 - H_ - 1 + t, 0, a.H - 1);
+                const uint32_t bar = bar_s + 8 * slot, dst = ring_s + slot * q.SLOT;
+                mbar_expect_tx(bar, lbytes + rbytes);
+                bulk_load(dst, srcL + (size_t)gy * a.sp.le_pitch, lbytes, bar);
+                bulk_load(dst + q.LFB, srcR + (size_t)gy * a.sp.rp_pitch, rbytes, bar);
+                if (++slot == RING) slot = 0;
+            };
+            if (lane == 0)
+                for (int t = 0; t < RING && t <= t_last; t++) feed(t);
+#pragma unroll 1
+            for (int y = y0; y < y1; y++) {
+                // the producers have finished row y: ring row y - y0 (its "out" row) is dead, its slot takes row y - y0 + RING
+                bar_sync4(1 + (y & 1), NT);
+                const int t = (y - y0) + RING;
+                if (lane == 0 && t <= t_last) feed(t);
+                if (y + 2 < y1) bar_arrive4(3 + (y & 1), NT);
+            }
+            return;
+        }
 
         // ---- the pixel of this thread --------------------------------------------------------------------
         int x = -1;
         {
             const int PW = (TWc + NCW4 - 1) / NCW4;                // pixels per warp (<= 32)
-            if (lane < PW && cw * PW + lane < TWc) x = cw * PW + lane;
+            if (lane < PW && cw * PW + lane < TWc && x0 + cw * PW + lane >= 0) x = cw * PW + lane;
         }
         const int xx = max(x, 0);
-        const int xv = xx + (HP - H_);                           // pixel xx's window starts at virtual column xv
+        const int xv = xx;                                      // pixel xx's window starts at virtual column xx
         const int gq = xv / G, gi = xv - gq * G;
         const bool second = gi >= H_;
         int oa, ob, oc_;                                        // SAD = [oa] + [ob] - [oc_], byte offsets inside a buffer
@@ -490,11 +502,7 @@ bm_sad4_kernel(Bm4Args a)
             if (have_next && x >= 0) tnext = (int)tptr[a.tex_pitch];
             tptr += a.tex_pitch;
 
-            bar_sync4(1 + (y & 1), NT);                         // the sums of row y are complete (and the producers' ring reads of row y)
-            if (feeder) {
-                const int t = (y - y0) + RING;                  // the slot of ring row y - y0 is free
-                if (t <= t_last) feed(t);
-            }
+            bar_sync4(1 + (y & 1), NT);                         // the sums of row y are complete
             const uint8_t *buf = smem + (y & 1) * q.BUFSZ;
             int16_t dout = FILT;
             int costv = 0;
@@ -615,19 +623,20 @@ bool pick_tiling4(const BmGeom &g, int n, Tiling4 *t)
     if (!(g.nd == 256 || g.nd == 192 || g.nd == 128 || g.nd == 96 || g.nd == 64 || g.nd == 48 || g.nd == 32)) return false;
     const int NO = g.nd / 8, G = 2 * h;
     const size_t smem_max = 224 * 1024;
-    const int E = hp_of(h) - h;                      // idle virtual columns left of a stripe's first window
+    const int E = hp_of(h) - h;                      // pixels stripe 0 starts left of the image
     int ngmax = 2;
-    while (producer_threads4(h, NO, ngmax + 1) + NCW4 * 32 <= MAXT4 && (size_t)make_geo4(h, g.nd, ngmax + 1).total <= smem_max)
+    while (producer_threads4(h, NO, ngmax + 1) + (NCW4 + NFW4) * 32 <= MAXT4 && (size_t)make_geo4(h, g.nd, ngmax + 1).total <= smem_max)
         ngmax++;
-    if (producer_threads4(h, NO, ngmax) + NCW4 * 32 > MAXT4 || (size_t)make_geo4(h, g.nd, ngmax).total > smem_max) return false;
-    const int twmax = std::min(ngmax * G - 2 * h - E, NCW4 * 32) & ~3;
+    if (producer_threads4(h, NO, ngmax) + (NCW4 + NFW4) * 32 > MAXT4 || (size_t)make_geo4(h, g.nd, ngmax).total > smem_max) return false;
+    const int twmax = std::min(ngmax * G - 2 * h, NCW4 * 32) & ~3;
     if (twmax < 16) return false;
-    t->nstripes = cdiv(g.W1, twmax);
-    t->TW = (cdiv(g.W1, t->nstripes) + 3) & ~3;      // stripes start at multiples of 4 pixels (16-byte aligned bulk copies)
-    t->nstripes = cdiv(g.W1, t->TW);
-    t->NG = cdiv(t->TW + E + 2 * h, G);
+    // stripe s covers the pixels [s * TW - E, (s + 1) * TW - E): its first virtual column is a multiple of 4 (16-byte aligned bulk copies)
+    t->nstripes = cdiv(g.W1 + E, twmax);
+    t->TW = (cdiv(g.W1 + E, t->nstripes) + 3) & ~3;
+    t->nstripes = cdiv(g.W1 + E, t->TW);
+    t->NG = cdiv(t->TW + 2 * h, G);
     if (t->NG > ngmax) return false;
-    t->NT = producer_threads4(h, NO, t->NG) + NCW4 * 32;
+    t->NT = producer_threads4(h, NO, t->NG) + (NCW4 + NFW4) * 32;
     // bands: a band pays ~START rows of start-up (2h+1 rows of window sums) and the launch runs in waves of one CTA per
     // SM -> take the band count with the smallest (waves + 1/2) x (band height + START); the half wave stands for the
     // tail (stripes differ a little), and bands stay <= 128 rows (bm_sad3.cu: taller bands lose more to that tail)
