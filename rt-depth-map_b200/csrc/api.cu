@@ -351,10 +351,8 @@ static int bm_pipeline(rtdm_bm *h, int n, PlaneU8 L, PlaneU8 R, int W, int H, Pl
         mark();
         PlaneU8 iL = {wLp, h->ppitch, h->pframe}, iR = {wRp, h->ppitch, h->pframe};
         if (fast4) {
-            uint16_t *tex = h->tex + (size_t)f0 * h->rframe;
-            rc = launch_bm_texture(g, n, iL, tex, h->rpitch, h->rframe, st);
-            if (!rc) rc = launch_bm_sad4_core(g, n, sp, raw, cost, tex, h->rpitch, h->rframe, st);
-            h->launches += 2;
+            rc = launch_bm_sad4_core(g, n, sp, raw, cost, st);
+            h->launches += 1;
         } else if (fast)
             rc = launch_bm_sad2(g, n, iL, iR, raw, cost, h->tex + (size_t)f0 * h->rframe, h->rpitch, h->rframe, st, &h->launches, fast3);
         else
@@ -563,9 +561,13 @@ extern "C" int rtdm_bm_debug_fetch(rtdm_bm *h, int what, void *dst, size_t dst_b
     const int W = h->lastW, H = h->lastH;
     if (what == 0 || what == 1) {
         if (dst_bytes < (size_t)W * H) return -RTDM_EINVAL;
-        if (what == 1 && h->last_kernel == 4)       // the right image only exists in its staged layout
+        if (what == 1 && h->last_kernel == 4)       // the images only exist in their staged layouts
             RTDM_CUDA(cudaMemcpy2D(dst, W, h->RPs + BmStaged::RPADL, h->rppitch, W, H, cudaMemcpyDeviceToHost));
-        else
+        else if (what == 0 && h->last_kernel == 4) {
+            std::vector<uint32_t> tmp((size_t)W * H);
+            RTDM_CUDA(cudaMemcpy2D(tmp.data(), (size_t)W * 4, h->LE + BmStaged::LPADL, h->lepitch * 4, (size_t)W * 4, H, cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < tmp.size(); i++) static_cast<uint8_t *>(dst)[i] = (uint8_t)(tmp[i] & 0xFFu);
+        } else
             RTDM_CUDA(cudaMemcpy2D(dst, W, what ? h->Rp : h->Lp, h->ppitch, W, H, cudaMemcpyDeviceToHost));
     } else if (what == 2 || what == 3) {
         if (dst_bytes < (size_t)W * H * 2) return -RTDM_EINVAL;

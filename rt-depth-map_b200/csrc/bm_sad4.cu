@@ -21,6 +21,9 @@
 //     rows with its own compile-time shifts (warps are type-uniform), so every sum in shared memory is in forward
 //     disparity order: the byte reversals of the half totals (8 PRMT per producer thread and row) and the un-reversal in
 //     the winner-take-all warps are gone, and a ring row is 5 instead of 10 bytes per column.
+//   * The texture window sums (textureThreshold test) are made in the kernel, by the otherwise idle warp that feeds the
+//     ring, from the expanded left rows already in shared memory: the separate texture kernel and the plain prefiltered
+//     planes are gone.
 //   * Even half-widths keep the groups of a warp ADJACENT (bm_sad3 interleaved them by parity for the odd half-widths),
 //     which takes the two-way bank conflicts off the right-row loads and the octet-key stores.
 //
@@ -78,8 +81,7 @@ __host__ __device__ constexpr int hp_of(int h) { return (h + 3) & ~3; }     // s
 
 struct Bm4Args {
     PlaneS16 disp, cost;
-    const uint16_t *tex; size_t tex_pitch, tex_frame;      // texture window sums, [frame][y][x1]
-    int W, H, nd, texThr, uniq;
+    int W, H, nd, cap, texThr, uniq;
     int W1, row0, row1;
     int TW, BH, NG;              // stripe width (a multiple of 4), band height, column groups
     BmStaged sp;                 // the staged planes (prefilter.cu)
@@ -98,7 +100,7 @@ struct Geo4 {
     // one sums buffer: X[NCT] | HA[NG] | HB[NG] | TA[NG] | TB[NG] | zero row (pitch PP each) | Mn[NCT] (pitch MNP)
     int NCT, NCTP, PP, BUFSZ, XOFF, HAOFF, HBOFF, TAOFF, TBOFF, ZOFF, MNOFF;
     int LFB, RBY, SLOT;                              // ring slot: expanded left row (LFB bytes), then RBY bytes of the right row
-    int RINGOFF, BAROFF, total;
+    int RINGOFF, BAROFF, TEXOFF, total;              // TEX: 2 x 256 u16 texture sums (row parity)
 };
 __host__ __device__ inline Geo4 make_geo4(int h, int nd, int NG)
 {
@@ -122,7 +124,8 @@ __host__ __device__ inline Geo4 make_geo4(int h, int nd, int NG)
     q.SLOT = q.LFB + ((q.RBY + 127) & ~127);
     q.RINGOFF = 2 * q.BUFSZ;
     q.BAROFF = q.RINGOFF + ring_rows4(h) * q.SLOT;
-    q.total = q.BAROFF + 8 * ring_rows4(h) + 128;    // + slack to align the carve-up to 128 bytes
+    q.TEXOFF = (q.BAROFF + 8 * ring_rows4(h) + 15) & ~15;
+    q.total = q.TEXOFF + 2 * 256 * 2 + 128;          // + slack to align the carve-up to 128 bytes
     return q;
 }
 
@@ -456,13 +459,78 @@ bm_sad4_kernel(Bm4Args a)
             };
             if (lane == 0)
                 for (int t = 0; t < RING && t <= t_last; t++) feed(t);
+
+            // texture: T(x) = sum over the (2h+1)^2 window of |L' - cap| from the expanded left rows of the
+            // ring.  Lane l owns the pixels [8l, 8l + 8): per ring row the 2h + 8 bytes |L' - cap| they touch are compacted
+            // from 6 expanded 128-bit words (24 columns), the 8 horizontal window sums come from IDP.4A byte sums (first
+            // window, then + entering - leaving byte), and the vertical window slides by adding the entering row's sums and
+            // subtracting the leaving row's.  No cross-lane traffic.
+            constexpr int NTAP = 2 * H_ + 1;
+            const uint32_t capx4 = (uint32_t)a.cap * 0x01010101u;
+            const bool tlane = 8 * lane < TWc;
+            int T[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) T[i] = 0;
+            auto row_sums = [&](const uint8_t *slot_p, int (&R)[8]) {
+                const uint4 *p4 = reinterpret_cast<const uint4 *>(slot_p + 32 * lane);
+                uint32_t w[6];
+#pragma unroll
+                for (int k = 0; k < 6; k++) {
+                    const uint4 v = p4[k];                                        // 4 expanded columns
+                    const uint32_t lo = __byte_perm(v.x, v.y, 0x0040), hi = __byte_perm(v.z, v.w, 0x0040);
+                    w[k] = __vabsdiffu4(__byte_perm(lo, hi, 0x5410), capx4);      // |L' - cap| <= 63 per byte
+                }
+                int acc = 0;
+#pragma unroll
+                for (int k = 0; k < (NTAP + 3) / 4; k++) {
+                    const int nb = NTAP - 4 * k >= 4 ? 4 : NTAP - 4 * k;
+                    const int m = nb == 4 ? 0x01010101 : (nb == 3 ? 0x00010101 : (nb == 2 ? 0x00000101 : 0x00000001));
+                    acc = __dp4a((int)w[k], m, acc);
+                }
+                R[0] = acc;
+#pragma unroll
+                for (int i = 1; i < 8; i++) {
+                    const int bi = NTAP - 1 + i, bo = i - 1;                      // + byte bi, - byte bo
+                    acc = __dp4a((int)w[bi / 4], 1 << (8 * (bi % 4)), acc);
+                    acc = __dp4a((int)w[bo / 4], (int)(0xFFu << (8 * (bo % 4))), acc);   // multiplier byte -1
+                    R[i] = acc;
+                }
+            };
+            uint16_t *TEX = reinterpret_cast<uint16_t *>(smem + q.TEXOFF);
+            for (int t = 0; t <= 2 * H_; t++) {                   // ring rows 0 .. 2h (the first row step removes row 0 again)
+                mbar_wait(bar_s + 8 * t, 0);
+                if (tlane) {
+                    int R[8];
+                    row_sums(Ring + t * q.SLOT, R);
+#pragma unroll
+                    for (int i = 0; i < 8; i++) T[i] += R[i];
+                }
+            }
+            auto tex_row = [&](int r) {                           // texture sums of band row r -> TEX[r & 1]
+                const int tin = r + 2 * H_ + 1;
+                mbar_wait(bar_s + 8 * (tin % RING), (uint32_t)(tin / RING) & 1u);
+                if (tlane) {
+                    int Ri[8], Ro[8];
+                    row_sums(Ring + (tin % RING) * q.SLOT, Ri);
+                    row_sums(Ring + (r % RING) * q.SLOT, Ro);
+#pragma unroll
+                    for (int i = 0; i < 8; i++) T[i] += Ri[i] - Ro[i];
+                    *reinterpret_cast<uint4 *>(TEX + (r & 1) * 256 + 8 * lane) =
+                        make_uint4((uint32_t)T[0] | ((uint32_t)T[1] << 16), (uint32_t)T[2] | ((uint32_t)T[3] << 16),
+                                   (uint32_t)T[4] | ((uint32_t)T[5] << 16), (uint32_t)T[6] | ((uint32_t)T[7] << 16));
+                }
+                __syncwarp();                                     // lane 0 refills a ring slot next
+            };
+            tex_row(0);
 #pragma unroll 1
             for (int y = y0; y < y1; y++) {
-                // the producers have finished row y: ring row y - y0 (its "out" row) is dead, its slot takes row y - y0 + RING
+                // the producers have finished row y: ring row y - y0 (its "out" row) is dead, its slot takes row y - y0 + RING;
+                // the winner-take-all warps have finished row y - 1: TEX[(y + 1) & 1] is free
                 bar_sync4(1 + (y & 1), NT);
+                if (y + 2 < y1) bar_arrive4(3 + (y & 1), NT);   // (this warp reads no sums: it only has to be counted)
                 const int t = (y - y0) + RING;
                 if (lane == 0 && t <= t_last) feed(t);
-                if (y + 2 < y1) bar_arrive4(3 + (y & 1), NT);
+                if (y + 1 < y1) tex_row(y - y0 + 1);
             }
             return;
         }
@@ -490,19 +558,13 @@ bm_sad4_kernel(Bm4Args a)
         const int omn = q.MNOFF + xv * MNP;                     // octet minima of this pixel (made by the producers)
         int16_t *dptr = a.disp.p + (size_t)f * a.disp.frame + (size_t)y0 * a.disp.pitch + lofs + x0 + xx;
         int16_t *cptr = a.cost.p ? a.cost.p + (size_t)f * a.cost.frame + (size_t)y0 * a.cost.pitch + lofs + x0 + xx : nullptr;
-        const uint16_t *tptr = a.tex + (size_t)f * a.tex_frame + (size_t)y0 * a.tex_pitch + x0 + xx;
+        const uint16_t *tex16 = reinterpret_cast<const uint16_t *>(smem + q.TEXOFF) + xx;
         const int16_t FILT = (int16_t)(-16);                    // (minD - 1) * 16 with minD = 0
-        int tsum = x >= 0 ? (int)*tptr : 0;
 
 #pragma unroll 1
         for (int y = y0; y < y1; y++) {
-            // texture sum of the next row
-            const bool have_next = y + 1 < y1;
-            int tnext = 0;
-            if (have_next && x >= 0) tnext = (int)tptr[a.tex_pitch];
-            tptr += a.tex_pitch;
-
-            bar_sync4(1 + (y & 1), NT);                         // the sums of row y are complete
+            bar_sync4(1 + (y & 1), NT);                         // the sums of row y are complete (and its texture sums)
+            const int tsum = (int)tex16[((y - y0) & 1) * 256];
             const uint8_t *buf = smem + (y & 1) * q.BUFSZ;
             int16_t dout = FILT;
             int costv = 0;
@@ -597,7 +659,6 @@ bm_sad4_kernel(Bm4Args a)
             }
             dptr += a.disp.pitch;
             if (cptr) cptr += a.cost.pitch;
-            tsum = tnext;
         }
     }
 }
@@ -704,10 +765,8 @@ long long bm_sad4_cost(const BmGeom &g, int n)
     return t.cost;
 }
 
-// SAD + WTA kernel only; the staged planes come from the prefilter (prefilter.cu: BmStaged), the texture sums `tex`
-// from bm_sad2.cu: bm_texture_kernel
-int launch_bm_sad4_core(const BmGeom &g, int n, const BmStaged &sp, PlaneS16 disp, PlaneS16 cost,
-                        const uint16_t *tex, size_t tex_pitch, size_t tex_frame, cudaStream_t st)
+// texture sums + SAD + WTA; the staged planes come from the prefilter (prefilter.cu: BmStaged)
+int launch_bm_sad4_core(const BmGeom &g, int n, const BmStaged &sp, PlaneS16 disp, PlaneS16 cost, cudaStream_t st)
 {
     Tiling4 t;
     if (!pick_tiling4(g, n, &t)) { set_error("bm_sad4: unsupported geometry"); return -RTDM_EINVAL; }
@@ -716,8 +775,7 @@ int launch_bm_sad4_core(const BmGeom &g, int n, const BmStaged &sp, PlaneS16 dis
     const int h = g.bs / 2;
     Bm4Args a;
     a.disp = disp; a.cost = cost;
-    a.tex = tex; a.tex_pitch = tex_pitch; a.tex_frame = tex_frame;
-    a.W = g.W; a.H = g.H; a.nd = g.nd; a.texThr = g.texThr; a.uniq = g.uniq;
+    a.W = g.W; a.H = g.H; a.nd = g.nd; a.cap = g.cap; a.texThr = g.texThr; a.uniq = g.uniq;
     a.W1 = g.W1; a.row0 = g.row0; a.row1 = g.row1;
     a.TW = t.TW; a.BH = t.BH; a.NG = t.NG;
     a.sp = sp;

@@ -60,8 +60,8 @@ struct BmStaged {
 };
 
 // ---- prefilter (prefilter.cu) ------------------------------------------------------------------
-// type: RTDM_PREFILTER_*.  Both images of all n frames in one launch.  With `staged` the left image is written twice
-// (plain plane outL for the texture kernel + expanded plane) and the right image only in its staged layout (outR unused).
+// type: RTDM_PREFILTER_*.  Both images of all n frames in one launch.  With `staged` both images are written in their
+// staged layouts only (outL / outR unused).
 int launch_prefilter(int type, int winsize, int cap, int n, int W, int H,
                      PlaneU8 left, PlaneU8 right, PlaneU8W outL, PlaneU8W outR,
                      cudaStream_t st, int *launches, const BmStaged *staged = nullptr);
@@ -94,8 +94,7 @@ int launch_bm_sad3_core(const BmGeom &g, int n, PlaneU8 Lp, PlaneU8 Rp, PlaneS16
 // TMA-staged warp-specialised fast path (bm_sad4.cu): same domain as bm_sad3.cu; reads the BmStaged planes
 bool bm_sad4_supported(const BmGeom &g, int n);
 long long bm_sad4_cost(const BmGeom &g, int n);
-int launch_bm_sad4_core(const BmGeom &g, int n, const BmStaged &sp, PlaneS16 disp, PlaneS16 cost,
-                        const uint16_t *tex, size_t tex_pitch, size_t tex_frame, cudaStream_t st);
+int launch_bm_sad4_core(const BmGeom &g, int n, const BmStaged &sp, PlaneS16 disp, PlaneS16 cost, cudaStream_t st);
 // texture window sums of the prefiltered left image (bm_sad2.cu: bm_texture_kernel), blockSize 5 .. 15
 int launch_bm_texture(const BmGeom &g, int n, PlaneU8 Lp, uint16_t *tex, size_t tex_pitch, size_t tex_frame, cudaStream_t st);
 

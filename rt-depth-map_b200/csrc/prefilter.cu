@@ -94,7 +94,7 @@ prefilter_xsobel_kernel(PlaneU8 left, PlaneU8 right, PlaneU8W outL, PlaneU8W out
     }
     if (sg.LE) {
         for (int i = 0; i < 4 && x0 + i < W; i++) staged_store_px(sg, img, f, y, x0 + i, W, o[i]);
-        if (img) return;
+        return;
     }
     uint8_t *d = dst + (size_t)y * dp + x0;
     if (x0 + 3 < W && ((reinterpret_cast<uintptr_t>(d) & 3) == 0)) {
@@ -153,7 +153,7 @@ prefilter_xsobel4_kernel(PlaneU8 left, PlaneU8 right, PlaneU8W outL, PlaneU8W ou
             pl = cl; ph = ch; cl = nl; ch = nh;
         }
         if (sg.LE) staged_store_word(sg, img, f, y, 4 * wi, o, wi == 0, wi == nw - 1);
-        if (!sg.LE || !img) *d = o;
+        else *d = o;
         d = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(d) + dp);
     }
 }
@@ -189,7 +189,7 @@ prefilter_norm_kernel(PlaneU8 left, PlaneU8 right, PlaneU8W outL, PlaneU8W outR,
     const uint32_t o = (uint32_t)(clampi(val, -cap, cap) + cap);
     if (stg.LE) {
         staged_store_px(stg, img, f, y, x, W, o);
-        if (img) return;
+        return;
     }
     dst[(size_t)y * dp + x] = (uint8_t)o;
 }
@@ -204,7 +204,7 @@ int launch_prefilter(int type, int winsize, int cap, int n, int W, int H,
     if (type == RTDM_PREFILTER_XSOBEL) {
         const auto al4 = [](const void *p, size_t pitch, size_t frame) { return ((reinterpret_cast<uintptr_t>(p) | pitch | frame) & 3) == 0; };
         if (W % 4 == 0 && W >= 8 && al4(left.p, left.pitch, left.frame) && al4(right.p, right.pitch, right.frame) &&
-            al4(outL.p, outL.pitch, outL.frame) && (staged || al4(outR.p, outR.pitch, outR.frame))) {
+            (staged || (al4(outL.p, outL.pitch, outL.frame) && al4(outR.p, outR.pitch, outR.frame)))) {
             dim3 grid(cdiv(W / 4, 128), cdiv(H, PFB), 2 * n);
             prefilter_xsobel4_kernel<<<grid, 128, 0, st>>>(left, right, outL, outR, W, H, cap, sg);
         } else {
