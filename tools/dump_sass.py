@@ -4,7 +4,9 @@ import collections, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.path.join(ROOT, "rt-depth-map_b200", "librtdm_b200.so")
 OUT = os.path.join(ROOT, "profiles")
+ROUND = "r02"
 KERNELS = {                         # file tag -> substring of the mangled name
+    "bm_sad4_h6_d128": "bm_sad4_kernelILi6ELi16E",
     "bm_sad3_h6_d128": "bm_sad3_kernelILi6ELi16ENS0_9ShapeWide",
     "bm_sad2_h6": "bm_sad2_kernelILi6ELi1ELi192ELb0ELi2E",
     "sgbm_sweep_d128": "sgbm_sweep_kernelILi16ELb1E",
@@ -18,7 +20,7 @@ rows = []
 for tag, key in KERNELS.items():
     body = next(c for c in chunks if c.startswith("\t\tFunction : ") and key in c.split("\n", 1)[0])
     lines = [re.sub(r"\s*/\* 0x[0-9a-f]+ \*/\s*$", "", l) for l in body.splitlines() if not re.match(r"^\s*/\* 0x[0-9a-f]+ \*/\s*$", l)]
-    with open(os.path.join(OUT, f"r01_sass_{tag}.txt"), "w") as f:
+    with open(os.path.join(OUT, f"{ROUND}_sass_{tag}.txt"), "w") as f:
         f.write(f"# cuobjdump -sass librtdm_b200.so, function containing '{key}' (sm_100a, encodings stripped)\n")
         f.write("\n".join(lines) + "\n")
     ops = collections.Counter()
@@ -29,7 +31,7 @@ for tag, key in KERNELS.items():
     n = sum(ops.values())
     rows.append((tag, n, ops))
     print(tag, n, ops.most_common(8))
-with open(os.path.join(OUT, "r01_sass_instruction_mix.csv"), "w") as f:
+with open(os.path.join(OUT, f"{ROUND}_sass_instruction_mix.csv"), "w") as f:
     f.write("# static SASS instruction mix of the dominant kernels (counts over the whole function, all unrolled variants)\n")
     f.write("kernel,total,top opcodes (count)\n")
     for tag, n, ops in rows:
