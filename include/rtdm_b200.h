@@ -117,8 +117,10 @@ int rtdm_bm_speckle_device(rtdm_bm *h, int n, int16_t *disp, size_t dstep, size_
                            void *cuda_stream);
 /* number of kernel launches issued by the last compute call on this handle */
 int rtdm_bm_last_launches(const rtdm_bm *h);
-/* which SAD/WTA kernel the last compute call used: 1 = generic (bm_sad.cu), 2 = fast path (bm_sad2.cu:
- * minDisparity 0, blockSize 5..15).  The environment variable RTDM_BM_KERNEL=1 forces the generic one. */
+/* which SAD/WTA kernel the last compute call used: 1 = generic (bm_sad.cu), 2 = bm_sad2.cu, 3 = warp-specialised
+ * bm_sad3.cu, 4 = TMA-staged warp-specialised bm_sad4.cu (the default wherever it applies: minDisparity 0, blockSize 5..15,
+ * numDisparities 32 / 48 / 64 / 96 / 128 / 192 / 256).  The environment variable RTDM_BM_KERNEL = 1 / 2 / 3, read when the
+ * handle is created, keeps the older kernel (A/B timing, the tests' kernel matrix). */
 int rtdm_bm_last_kernel(const rtdm_bm *h);
 /* Per-stage device timing with CUDA events recorded on the launching stream (used by bench.py for
  * the roofline of the dominant kernel).  While enabled every compute call records 5 events.
@@ -130,6 +132,31 @@ int rtdm_bm_stage_times(rtdm_bm *h, double *ms_sum, int *calls);
  * what: 0 = prefiltered left, 1 = prefiltered right (uint8, width bytes per row),
  *       2 = raw WTA disparity before validate/mask/speckle, 3 = cost (int16, width per row). */
 int rtdm_bm_debug_fetch(rtdm_bm *h, int what, void *dst, size_t dst_bytes);
+
+/* ---- one large frame over several GPUs: row bands (optional part) ---------------------------------
+ * Same call as SWMatcherKonolige::compute (bm-sw.cpp:33-38) for ONE frame, computed by n_gpus devices of this process:
+ * device i computes the output rows [H*i/n, H*(i+1)/n) from its input rows + a halo of blockSize/2 + 1 rows (every stage
+ * before the speckle filter is local to a few rows), the int16 bands travel to devices[0] as peer copies
+ * (cudaMemcpyPeerAsync: NVLink / NVSwitch when the devices are peers), and devices[0] runs cv::filterSpeckles on the
+ * stitched frame, because components cross bands.  Bit-exact against rtdm_bm_compute.  The same device may be listed
+ * several times (bands then run one after the other; used by the single-GPU tests).  minDisparity must be <= 0 (the
+ * row spill of SURVEY.md App. B.3 crosses bands).  SGBM does not split this way (its vertical paths span the image). */
+typedef struct rtdm_bm_rowband rtdm_bm_rowband;
+int rtdm_bm_rowband_create(rtdm_bm_rowband **out, const rtdm_params *p, int max_width, int max_height,
+                           int n_gpus, const int *devices);
+void rtdm_bm_rowband_destroy(rtdm_bm_rowband *h);
+/* replace StereoBM::setROI1 / setROI2 for the split matcher (bm-sw.cpp:40-48) */
+int rtdm_bm_rowband_set_roi1(rtdm_bm_rowband *h, int x, int y, int w, int hgt);
+int rtdm_bm_rowband_set_roi2(rtdm_bm_rowband *h, int x, int y, int w, int hgt);
+/* HOST pointers; every device receives only its own input rows + halo; blocking */
+int rtdm_bm_rowband_compute(rtdm_bm_rowband *h, const uint8_t *left, size_t lstep, const uint8_t *right, size_t rstep,
+                            int width, int height, int16_t *disp, size_t dstep);
+/* DEVICE pointers on devices[0] (inputs and output); the other devices fetch their input rows + halo as peer
+ * copies.  Blocking (returns when `disp` is complete). */
+int rtdm_bm_rowband_compute_device(rtdm_bm_rowband *h, const uint8_t *left, size_t lstep, const uint8_t *right, size_t rstep,
+                                   int width, int height, int16_t *disp, size_t dstep);
+/* kernel launches of the last call, summed over the devices */
+int rtdm_bm_rowband_last_launches(const rtdm_bm_rowband *h);
 
 /* ---- SWSemiGlobalMatcher peer ------------------------------------------------------------ */
 /* replaces SWSemiGlobalMatcher::SWSemiGlobalMatcher (sgbm-sw.cpp:12-25) */

@@ -577,6 +577,207 @@ extern "C" int rtdm_bm_debug_fetch(rtdm_bm *h, int what, void *dst, size_t dst_b
 }
 
 // =================================================================================================
+// BM, one frame split into row bands over several GPUs of this process (rtdm_b200.h: rtdm_bm_rowband_*)
+// =================================================================================================
+struct rtdm_bm_rowband {
+    rtdm_params p;
+    int n, maxW, maxH;
+    std::vector<int> dev;
+    std::vector<rtdm_bm *> band;      // one matcher per band, speckle filter off, sized for the tallest band + halo
+    rtdm_bm *full;                    // devices[0]: the speckle stage of the stitched frame
+    int16_t *gather;                  // devices[0]: stitched frame, [maxH][full->dpitch]
+    std::vector<cudaEvent_t> done;    // per band: its rows have arrived in `gather`
+    int launches;
+};
+
+// output rows [y0, y1) of band i and the input rows [i0, i1) it needs; i0 is even so that the x-Sobel's "odd last row"
+// rule (OpenCV pairs rows) lands on the same absolute row as in the whole frame
+static void rowband_rows(int H, int n, int i, int halo, int *y0, int *y1, int *i0, int *i1)
+{
+    *y0 = (int)((long long)H * i / n); *y1 = (int)((long long)H * (i + 1) / n);
+    *i0 = std::max(0, *y0 - halo) & ~1;
+    *i1 = std::min(H, *y1 + halo);
+}
+static int rowband_halo(const rtdm_params &p)
+{
+    return p.blockSize / 2 + (p.preFilterType == RTDM_PREFILTER_XSOBEL ? 1 : p.preFilterSize / 2 + 1);
+}
+
+extern "C" void rtdm_bm_rowband_destroy(rtdm_bm_rowband *h)
+{
+    if (!h) return;
+    for (rtdm_bm *b : h->band) rtdm_bm_destroy(b);
+    if (!h->dev.empty()) cudaSetDevice(h->dev[0]);
+    for (cudaEvent_t e : h->done) if (e) cudaEventDestroy(e);
+    cudaFree(h->gather);
+    rtdm_bm_destroy(h->full);
+    delete h;
+}
+
+extern "C" int rtdm_bm_rowband_create(rtdm_bm_rowband **out, const rtdm_params *p, int max_width, int max_height,
+                                      int n_gpus, const int *devices)
+{
+    if (!out || !p || !devices) { set_error("bm_rowband_create: null argument"); return -RTDM_EINVAL; }
+    *out = nullptr;
+    if (n_gpus < 1 || n_gpus > 64) { set_error("bm_rowband_create: 1 .. 64 bands"); return -RTDM_EINVAL; }
+    if (p->minDisparity > 0) { set_error("bm_rowband: minDisparity > 0 is not supported (row spill crosses bands)"); return -RTDM_EINVAL; }
+    int rc = bm_check_params(p);
+    if (rc) return rc;
+    rtdm_bm_rowband *h = new (std::nothrow) rtdm_bm_rowband();
+    if (!h) return -RTDM_ENOMEM;
+    h->p = *p; h->n = n_gpus; h->maxW = max_width; h->maxH = max_height; h->full = nullptr; h->gather = nullptr;
+    h->dev.assign(devices, devices + n_gpus);
+    const int halo = rowband_halo(*p);
+    int hb = 1;
+    for (int i = 0; i < n_gpus; i++) {
+        int y0, y1, i0, i1;
+        rowband_rows(max_height, n_gpus, i, halo, &y0, &y1, &i0, &i1);
+        hb = std::max(hb, i1 - i0 + 2);            // + 2: smaller frames shift the band edges by a row
+    }
+    hb = std::min(hb, max_height);
+    rtdm_params pb = *p;
+    pb.speckleWindowSize = 0;                       // the bands run without the speckle filter
+    for (int i = 0; i < n_gpus && !rc; i++) {
+        rtdm_bm *b = nullptr;
+        rc = rtdm_bm_create(&b, &pb, max_width, hb, 1, devices[i]);
+        if (!rc) h->band.push_back(b);
+    }
+    if (!rc) rc = rtdm_bm_create(&h->full, p, max_width, max_height, 1, devices[0]);
+    if (!rc) {
+        cudaSetDevice(devices[0]);
+        rc = dev_alloc(&h->gather, h->full->dframe);
+        for (int i = 0; i < n_gpus && !rc; i++) {
+            cudaEvent_t e = nullptr;
+            rc = cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess ? 0 : -RTDM_EIO;
+            h->done.push_back(e);
+        }
+        // peer access in both directions between devices[0] and every other device (bands in, input rows out); devices that
+        // are not peers still work: the copies are then staged through the host by the driver
+        for (int i = 1; i < n_gpus && !rc; i++) {
+            if (devices[i] == devices[0]) continue;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, devices[0], devices[i]) == cudaSuccess && can) {
+                cudaSetDevice(devices[0]);
+                if (cudaDeviceEnablePeerAccess(devices[i], 0) != cudaSuccess) cudaGetLastError();   // already enabled is fine
+                cudaSetDevice(devices[i]);
+                if (cudaDeviceEnablePeerAccess(devices[0], 0) != cudaSuccess) cudaGetLastError();
+            }
+        }
+    }
+    if (rc) { rtdm_bm_rowband_destroy(h); return rc; }
+    *out = h;
+    return 0;
+}
+
+extern "C" int rtdm_bm_rowband_set_roi1(rtdm_bm_rowband *h, int x, int y, int w, int hgt)
+{
+    if (!h) return -RTDM_EINVAL;
+    h->p.roi1[0] = x; h->p.roi1[1] = y; h->p.roi1[2] = w; h->p.roi1[3] = hgt;
+    return 0;
+}
+extern "C" int rtdm_bm_rowband_set_roi2(rtdm_bm_rowband *h, int x, int y, int w, int hgt)
+{
+    if (!h) return -RTDM_EINVAL;
+    h->p.roi2[0] = x; h->p.roi2[1] = y; h->p.roi2[2] = w; h->p.roi2[3] = hgt;
+    return 0;
+}
+extern "C" int rtdm_bm_rowband_last_launches(const rtdm_bm_rowband *h) { return h ? h->launches : 0; }
+
+// on_device: left / right / disp live on devices[0]; else in host memory
+static int rowband_run(rtdm_bm_rowband *h, bool on_device, const uint8_t *left, size_t lstep, const uint8_t *right, size_t rstep,
+                       int W, int H, int16_t *disp, size_t dstep)
+{
+    if (!h || !left || !right || !disp) { set_error("bm_rowband: null argument"); return -RTDM_EINVAL; }
+    if (W < 1 || H < 1 || W > h->maxW || H > h->maxH || dstep % 2) { set_error("bm_rowband: frame geometry exceeds what the handle was created for"); return -RTDM_EINVAL; }
+    if (h->p.blockSize >= W || h->p.blockSize >= H) { set_error("bm: blockSize must be smaller than the image"); return -RTDM_EINVAL; }
+    const int halo = rowband_halo(h->p), n = h->n;
+    rtdm_bm *full = h->full;
+    const size_t gp = full->dpitch;                 // elements per row of the stitched frame on devices[0]
+    h->launches = 0;
+    int rc = 0;
+    for (int i = 0; i < n && !rc; i++) {
+        int y0, y1, i0, i1;
+        rowband_rows(H, n, i, halo, &y0, &y1, &i0, &i1);
+        if (y1 <= y0) continue;
+        rtdm_bm *b = h->band[i];
+        const int hb = i1 - i0;
+        if (hb > b->maxH) { set_error("bm_rowband: band taller than the handle's workspace"); rc = -RTDM_EINVAL; break; }
+        RTDM_CUDA(cudaSetDevice(h->dev[i]));
+        // a ROI-less matcher derives its valid rows from its image height; inside a band that must be the FULL image's rows,
+        // so the whole-image rectangle is passed explicitly, shifted into band coordinates
+        const bool r1 = h->p.roi1[2] > 0 && h->p.roi1[3] > 0, r2 = h->p.roi2[2] > 0 && h->p.roi2[3] > 0;
+        b->p.roi1[0] = r1 ? h->p.roi1[0] : 0; b->p.roi1[1] = (r1 ? h->p.roi1[1] : 0) - i0; b->p.roi1[2] = r1 ? h->p.roi1[2] : W; b->p.roi1[3] = r1 ? h->p.roi1[3] : H;
+        b->p.roi2[0] = r2 ? h->p.roi2[0] : 0; b->p.roi2[1] = (r2 ? h->p.roi2[1] : 0) - i0; b->p.roi2[2] = r2 ? h->p.roi2[2] : W; b->p.roi2[3] = r2 ? h->p.roi2[3] : H;
+        // input rows [i0, i1) -> this device's staging planes (H2D, or a peer copy from devices[0])
+        const cudaMemcpyKind kin = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+        if (on_device && h->dev[i] == h->dev[0]) {
+            // same device: no copy, the pipeline reads the caller's rows in place
+        } else {
+            RTDM_CUDA(cudaMemcpy2DAsync(b->dL, b->spitch, left + (size_t)i0 * lstep, lstep, W, hb, kin, b->st));
+            RTDM_CUDA(cudaMemcpy2DAsync(b->dR, b->spitch, right + (size_t)i0 * rstep, rstep, W, hb, kin, b->st));
+        }
+        const bool inplace = on_device && h->dev[i] == h->dev[0];
+        PlaneU8 L = {inplace ? left + (size_t)i0 * lstep : b->dL, inplace ? lstep : b->spitch, 0};
+        PlaneU8 R = {inplace ? right + (size_t)i0 * rstep : b->dR, inplace ? rstep : b->spitch, 0};
+        PlaneS16 out = {b->dD, b->dpitch, 0};
+        b->launches = 0;
+        rc = bm_pipeline(b, 1, L, R, W, hb, out, b->st);
+        if (rc) break;
+        h->launches += b->launches;
+        // rows [y0, y1) of the band -> the stitched frame on devices[0]
+        const int16_t *src = b->dD + (size_t)(y0 - i0) * b->dpitch;
+        int16_t *dst = h->gather + (size_t)y0 * gp;
+        if (b->dpitch == gp)
+            RTDM_CUDA(cudaMemcpyPeerAsync(dst, h->dev[0], src, h->dev[i], (size_t)(y1 - y0) * gp * 2, b->st));
+        else
+            RTDM_CUDA(cudaMemcpy2DAsync(dst, gp * 2, src, b->dpitch * 2, (size_t)W * 2, y1 - y0, cudaMemcpyDeviceToDevice, b->st));
+        RTDM_CUDA(cudaEventRecord(h->done[i], b->st));
+    }
+    // devices[0]: wait for the bands, speckle filter on the stitched frame, result to the caller
+    cudaSetDevice(h->dev[0]);
+    if (!rc) {
+        for (int i = 0; i < n; i++) {
+            int y0, y1, i0, i1;
+            rowband_rows(H, n, i, halo, &y0, &y1, &i0, &i1);
+            if (y1 > y0) RTDM_CUDA(cudaStreamWaitEvent(full->st, h->done[i], 0));
+        }
+        if (h->p.speckleRange >= 0 && h->p.speckleWindowSize > 0) {
+            full->launches = 0;
+            rc = launch_speckle(1, W, H, PlaneS16{h->gather, gp, 0}, (h->p.minDisparity - 1) * 16, h->p.speckleWindowSize, h->p.speckleRange,
+                                full->labels, full->sizes, full->st, &full->launches, full->runlen, full->sw);
+            h->launches += full->launches;
+        }
+        if (!rc)
+            RTDM_CUDA(cudaMemcpy2DAsync(disp, dstep, h->gather, gp * 2, (size_t)W * 2, H,
+                                        on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, full->st));
+    }
+    // drain every stream that was touched (also after an error: copies from the caller's buffers may be in flight)
+    cudaError_t e0 = cudaSuccess;
+    for (int i = 0; i < n; i++) {
+        cudaSetDevice(h->dev[i]);
+        const cudaError_t e = cudaStreamSynchronize(h->band[i]->st);
+        if (e0 == cudaSuccess) e0 = e;
+    }
+    cudaSetDevice(h->dev[0]);
+    { const cudaError_t e = cudaStreamSynchronize(full->st); if (e0 == cudaSuccess) e0 = e; }
+    if (rc) return rc;
+    RTDM_CUDA(e0);
+    return 0;
+}
+
+extern "C" int rtdm_bm_rowband_compute(rtdm_bm_rowband *h, const uint8_t *left, size_t lstep, const uint8_t *right, size_t rstep,
+                                       int width, int height, int16_t *disp, size_t dstep)
+{
+    return rowband_run(h, false, left, lstep, right, rstep, width, height, disp, dstep);
+}
+
+extern "C" int rtdm_bm_rowband_compute_device(rtdm_bm_rowband *h, const uint8_t *left, size_t lstep, const uint8_t *right, size_t rstep,
+                                              int width, int height, int16_t *disp, size_t dstep)
+{
+    return rowband_run(h, true, left, lstep, right, rstep, width, height, disp, dstep);
+}
+
+// =================================================================================================
 // SGBM
 // =================================================================================================
 struct rtdm_sgbm {

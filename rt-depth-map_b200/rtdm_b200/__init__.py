@@ -64,6 +64,13 @@ SIGNATURES = {
     "rtdm_bm_last_launches": (_i, [_vp]),
     "rtdm_bm_debug_fetch": (_i, [_vp, _i, _vp, _sz]),
     "rtdm_bm_last_kernel": (_i, [_vp]),
+    "rtdm_bm_rowband_create": (_i, [C.POINTER(_vp), C.POINTER(RtdmParams), _i, _i, _i, C.POINTER(_i)]),
+    "rtdm_bm_rowband_destroy": (None, [_vp]),
+    "rtdm_bm_rowband_set_roi1": (_i, [_vp, _i, _i, _i, _i]),
+    "rtdm_bm_rowband_set_roi2": (_i, [_vp, _i, _i, _i, _i]),
+    "rtdm_bm_rowband_compute": (_i, [_vp, _vp, _sz, _vp, _sz, _i, _i, _vp, _sz]),
+    "rtdm_bm_rowband_compute_device": (_i, [_vp, _vp, _sz, _vp, _sz, _i, _i, _vp, _sz]),
+    "rtdm_bm_rowband_last_launches": (_i, [_vp]),
     "rtdm_bm_set_profiling": (_i, [_vp, _i]),
     "rtdm_bm_stage_times": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(_i)]),
     "rtdm_sgbm_create": (_i, [C.POINTER(_vp), C.POINTER(RtdmParams), _i, _i, _i, _i]),
@@ -289,6 +296,64 @@ class CUDAMatcherKonolige(_MatcherBase):
         a = np.empty((height, width), dt)
         _check(self._l.rtdm_bm_debug_fetch(self._h, what, a.ctypes.data, a.nbytes))
         return a
+
+
+class CUDARowBandMatcherKonolige(BlockMatcher):
+    """One large frame split into row bands over several GPUs of this process (rtdm_bm_rowband_*: SURVEY.md 8(e),
+    optional part).  Constructor arguments as CUDAMatcherKonolige plus `devices` (a device may be listed more than
+    once: its bands then run one after the other).  The bands reach devices[0] as peer copies; the speckle filter runs
+    there on the stitched frame.  Bit-exact against CUDAMatcherKonolige."""
+
+    def __init__(self, roi1, roi2, preFilterCap, blockSize, minDisparity, textureThreshold,
+                 numOfDisparities, maxDisparity, uniquenessRatio, speckleWindowSize, speckleRange,
+                 disp12MaxDiff, *, devices, preFilterType=PREFILTER_XSOBEL, preFilterSize=9,
+                 max_width=1280, max_height=720):
+        self._l = lib()
+        self._h = _vp()
+        p = RtdmParams()
+        self._l.rtdm_params_default_bm(C.byref(p))
+        p.preFilterType, p.preFilterSize, p.preFilterCap = preFilterType, preFilterSize, preFilterCap
+        p.blockSize, p.minDisparity, p.numDisparities = blockSize, minDisparity, numOfDisparities
+        p.textureThreshold, p.uniquenessRatio = textureThreshold, uniquenessRatio
+        p.speckleWindowSize, p.speckleRange, p.disp12MaxDiff = speckleWindowSize, speckleRange, disp12MaxDiff
+        self.params, self.devices = p, list(devices)
+        arr = (_i * len(self.devices))(*self.devices)
+        _check(self._l.rtdm_bm_rowband_create(C.byref(self._h), C.byref(p), max_width, max_height, len(self.devices), arr))
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value and _vp is not None:
+            try:
+                self._l.rtdm_bm_rowband_destroy(h)
+            except Exception:       # interpreter shutdown
+                pass
+            self._h.value = None
+
+    close = __del__
+
+    def setROI1(self, roi1):
+        _check(self._l.rtdm_bm_rowband_set_roi1(self._h, *_rect(roi1)))
+
+    def setROI2(self, roi2):
+        _check(self._l.rtdm_bm_rowband_set_roi2(self._h, *_rect(roi2)))
+
+    def compute(self, left, right, out=None):
+        left, right = _u8_2d(left, "left"), _u8_2d(right, "right")
+        if left.shape != right.shape:
+            raise RtdmError(-EINVAL, "left and right must have the same size")
+        H, W = left.shape
+        if out is None or out.shape != (H, W) or out.dtype != np.int16 or out.strides[1] != 2:
+            out = np.empty((H, W), np.int16)
+        _check(self._l.rtdm_bm_rowband_compute(self._h, left.ctypes.data, left.strides[0], right.ctypes.data,
+                                               right.strides[0], W, H, out.ctypes.data, out.strides[0]))
+        return out
+
+    def compute_device(self, left_ptr, lstep, right_ptr, rstep, width, height, disp_ptr, dstep):
+        """Inputs and output resident on devices[0]; blocking."""
+        _check(self._l.rtdm_bm_rowband_compute_device(self._h, left_ptr, lstep, right_ptr, rstep, width, height, disp_ptr, dstep))
+
+    def last_launches(self) -> int:
+        return self._l.rtdm_bm_rowband_last_launches(self._h)
 
 
 class CUDASemiGlobalMatcher(_MatcherBase):

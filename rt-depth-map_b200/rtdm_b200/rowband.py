@@ -81,7 +81,8 @@ def compute_frame_distributed(band_fn, speckle_fn, left, right, dist, halo: int,
 
 
 class RowBandKonolige:
-    """Device flavour: every rank holds the frame's input rows on its GPU, computes its band with
+    """torch.distributed flavour (one process per GPU, NCCL gather); the single-process flavour behind the C ABI, with
+    peer copies instead of a collective, is rtdm_b200.CUDARowBandMatcherKonolige (rtdm_bm_rowband_*).  Device flavour: every rank holds the frame's input rows on its GPU, computes its band with
     CUDAMatcherKonolige (speckle off), rank 0 gathers the bands over NCCL and runs the speckle stage of a
     full-size handle on the stitched frame.  Constructor arguments as CUDAMatcherKonolige; `dist` is an initialised
     torch.distributed module (None = single process, all bands computed locally one after the other)."""
@@ -112,6 +113,7 @@ class RowBandKonolige:
             return
         W, hb = self.W, i1 - i0
         tmp = self.torch.empty((hb, W), dtype=self.torch.int16, device=self.dev)
+        tmp.record_stream(self.stream)                    # freed by the caching allocator only after self.stream is done with it
         self.band.setROI1((0, -i0, W, self.H)); self.band.setROI2((0, -i0, W, self.H))
         self.band.compute_device(1, L[i0:i1].data_ptr(), W, W * hb, R[i0:i1].data_ptr(), W, W * hb, W, hb,
                                  tmp.data_ptr(), W * 2, W * hb * 2, self.stream.cuda_stream)
@@ -121,6 +123,8 @@ class RowBandKonolige:
     def compute(self, L, R):
         torch, W, H = self.torch, self.W, self.H
         rows = [shard_range(H, r, self.world) for r in range(self.world)]
+        # L / R (and everything allocated below) are produced on torch's current stream; the matcher runs on self.stream
+        self.stream.wait_stream(torch.cuda.current_stream(self.dev))
         if self.dist is None:
             full = torch.empty((H, W), dtype=torch.int16, device=self.dev)
             for r in range(self.world):
@@ -128,6 +132,8 @@ class RowBandKonolige:
         else:
             maxr = max(b - a for a, b in rows)
             send = torch.zeros((maxr, W), dtype=torch.int16, device=self.dev)
+            self.stream.wait_stream(torch.cuda.current_stream(self.dev))     # the zero fill
+            send.record_stream(self.stream)
             y0, y1 = rows[self.rank]
             self._band_device(L, R, self.rank, send[: y1 - y0])
             self.stream.synchronize()
@@ -136,6 +142,8 @@ class RowBandKonolige:
             if self.rank != 0:
                 return None
             full = torch.cat([recv[r][: rows[r][1] - rows[r][0]] for r in range(self.world)], dim=0).contiguous()
+            self.stream.wait_stream(torch.cuda.current_stream(self.dev))     # the gather and the cat ran on the current stream
+            full.record_stream(self.stream)
         self.full.speckle_device(1, full.data_ptr(), W * 2, W * H * 2, W, H, self.stream.cuda_stream)
         self.stream.synchronize()
         return full
