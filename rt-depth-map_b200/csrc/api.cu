@@ -607,8 +607,8 @@ extern "C" void rtdm_bm_rowband_destroy(rtdm_bm_rowband *h)
 {
     if (!h) return;
     for (rtdm_bm *b : h->band) rtdm_bm_destroy(b);
+    for (size_t i = 0; i < h->done.size(); i++) if (h->done[i]) { cudaSetDevice(h->dev[i]); cudaEventDestroy(h->done[i]); }
     if (!h->dev.empty()) cudaSetDevice(h->dev[0]);
-    for (cudaEvent_t e : h->done) if (e) cudaEventDestroy(e);
     cudaFree(h->gather);
     rtdm_bm_destroy(h->full);
     delete h;
@@ -646,11 +646,13 @@ extern "C" int rtdm_bm_rowband_create(rtdm_bm_rowband **out, const rtdm_params *
     if (!rc) {
         cudaSetDevice(devices[0]);
         rc = dev_alloc(&h->gather, h->full->dframe);
-        for (int i = 0; i < n_gpus && !rc; i++) {
+        for (int i = 0; i < n_gpus && !rc; i++) {          // an event is recorded on a stream of ITS device
             cudaEvent_t e = nullptr;
+            cudaSetDevice(devices[i]);
             rc = cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess ? 0 : -RTDM_EIO;
             h->done.push_back(e);
         }
+        cudaSetDevice(devices[0]);
         // peer access in both directions between devices[0] and every other device (bands in, input rows out); devices that
         // are not peers still work: the copies are then staged through the host by the driver
         for (int i = 1; i < n_gpus && !rc; i++) {
