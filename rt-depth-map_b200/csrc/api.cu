@@ -40,6 +40,9 @@ Switches read_switches()
     sw.sgbm_nofuse = isset("RTDM_SGBM_NOFUSE");
     sw.sgbm_nosweep = isset("RTDM_SGBM_NOSWEEP");
     sw.sgbm_sweep_rows = geti("RTDM_SGBM_SWEEP_ROWS", 0);
+    sw.sgbm_novpass = isset("RTDM_SGBM_NOVPASS");
+    sw.sgbm_vpass_min = geti("RTDM_SGBM_VPASS_MIN", 2);
+    sw.sgbm_vpass_maxcl = geti("RTDM_SGBM_VPASS_MAXCL", 0);
     return sw;
 }
 
@@ -917,7 +920,17 @@ static int sgbm_pipeline(rtdm_sgbm *h, int n, PlaneU8 L, PlaneU8 R, int W, int H
     // launch -> among the sizes the volumes allow, take the one that fills whole waves best (720p x 128: 37 frames x 24
     // tiles = 6.0 waves of 148 SMs; 32 frames would be 5.2 -> 6 waves)
     int chunk = h->volB;
-    if (n > 1) {
+    // whole-height pass (batches): one cluster per frame, `q` frames at a time -> sub-batches are multiples of q
+    const int q = n >= h->sw.sgbm_vpass_min ? sgbm_vpass_frames_in_flight(g) : 0;
+    if (q > 0) {
+        if (n <= chunk) chunk = n;                               // one sub-batch; the pass itself loops over rounds of q frames
+        else {
+            if (chunk > q) chunk -= chunk % q;
+            const int rounds = cdiv(n, chunk);                   // spread the frames evenly over the sub-batches ...
+            const int even = cdiv(cdiv(n, rounds), q) * q;       // ... in multiples of q
+            if (even <= chunk) chunk = even;
+        }
+    } else if (n > 1) {
         const int ctas = sgbm_sweep_ctas_per_frame(g);
         int nsm = 0;
         if (ctas > 0 && cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->dev) == cudaSuccess && nsm > 0) {

@@ -614,8 +614,7 @@ __device__ __forceinline__ void path_step(uint4 &Lp, uint32_t &minLp, const uint
     for (int k = 0; k < 4; k++) {
         const uint32_t lm1 = __byte_perm(w[k], w[k + 1], 0x5432);      // (L[d-1], L[d])   for the pair (d, d+1)
         const uint32_t lp1 = __byte_perm(w[k + 1], w[k + 2], 0x5432);  // (L[d+1], L[d+2])
-        uint32_t v = __vimin3_u16x2(w[k + 1], __vadd2(lm1, P1x2), __vadd2(lp1, P1x2));
-        v = min2(v, dx2);
+        const uint32_t v = __vimin3_u16x2(w[k + 1], __vadd2(min2(lm1, lp1), P1x2), dx2);   // min(a + P1, b + P1) = min(a, b) + P1
         t[k] = __vsub2(__vadd2(v, cc[k]), dx2);
     }
     const uint32_t m = min2(min2(t[0], t[1]), min2(t[2], t[3]));
@@ -722,8 +721,7 @@ __device__ __forceinline__ void path_core(const uint4 Lp, const uint32_t minLp, 
     for (int k = 0; k < 4; k++) {
         const uint32_t lm1 = __byte_perm(w[k], w[k + 1], 0x5432);
         const uint32_t lp1 = __byte_perm(w[k + 1], w[k + 2], 0x5432);
-        uint32_t v = __vimin3_u16x2(w[k + 1], __vadd2(lm1, P1x2), __vadd2(lp1, P1x2));
-        v = min2(v, dx2);
+        const uint32_t v = __vimin3_u16x2(w[k + 1], __vadd2(min2(lm1, lp1), P1x2), dx2);   // min(a + P1, b + P1) = min(a, b) + P1
         t[k] = __vsub2(__vadd2(v, cc[k]), dx2);
     }
     const uint32_t mm = min2(min2(t[0], t[1]), min2(t[2], t[3]));
@@ -819,6 +817,197 @@ sgbm_sweep_kernel(SweepArgs a)
             M[0] = mL; M[a.W1] = minV; M[2 * a.W1] = mR;
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Whole-height pass: the same three paths as sgbm_sweep_kernel, but ONE persistent launch per direction.  The CTAs of a
+// thread-block cluster lie side by side across the image (XC = 2 * NS columns each, no halo, no recomputation) and walk
+// down (or up) all H rows of a frame together; a cluster takes frames cid, cid + nclusters, ...  What a diagonal path needs
+// from the neighbouring CTA -- one column's L (LPC x 16 bytes) and its minimum per row and side -- goes straight into the
+// neighbour's exchange buffer through distributed shared memory (st.shared::cluster) and is announced on the neighbour's
+// mbarrier (remote arrive.release.cluster / try_wait.acquire.cluster); there is no frontier in global memory and no
+// relaunch every 8 rows.  Neighbours stay within one row of each other by construction (each needs the other's previous
+// row), which is also the flow control of the double-buffered pads.  A thread owns two columns, NS apart ("halves"); even
+// CTAs do the left half first, odd CTAs the right half, so every boundary column is produced half a row before the
+// neighbour consumes it and the ~0.2 us exchange latency never sits on the critical path (tools/probe/cluster_probe.cu).
+// The last row of a frame hands zeros on (the state of a path that enters the image), so the next frame starts without a
+// special case and the row counter T that selects buffers and barrier phases simply runs on.
+// ------------------------------------------------------------------------------------------------
+struct VPassArgs {
+    const uint32_t *C; uint32_t *S; size_t frame_words;
+    int W1, H, P1, P2;
+    int ystart, ystep;                       // first row and row step of the pass
+    int nframes, ncta;                       // frames of this launch; CTAs per cluster (= per frame)
+};
+
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t a, uint32_t rank) { uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank)); return r; }
+// remote store that reports its bytes to the remote mbarrier when it has landed: no fence on the sender's side
+__device__ __forceinline__ void st_async_v4(uint32_t a, const uint4 v, uint32_t bar)
+{
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+                 ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void st_async_b32(uint32_t a, const uint32_t v, uint32_t bar)
+{
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(a), "r"(v), "r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_cta(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0u;
+}
+__device__ __forceinline__ void l2_prefetch_bulk(const void *p, uint32_t bytes) { asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void cluster_sync_all() { asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
+constexpr int VP_AHEAD = 3;                  // rows between the L2 prefetch and their use
+
+template <int LPC, bool SAFE3>
+__global__ void __launch_bounds__(1024, 1)
+sgbm_vpass_kernel(VPassArgs a)
+{
+    constexpr int NS = 1024 / LPC, XC = 2 * NS, WQ = LPC, NP = XC + 2;   // slots per half, columns per CTA, uint4 per column, pads
+    extern __shared__ __align__(16) uint8_t sw[];
+    uint4 *exL = reinterpret_cast<uint4 *>(sw);                       // [2][NP][WQ]  L of the path from x-1, stored at producing column + 1
+    uint4 *exR = exL + 2 * NP * WQ;                                   // [2][NP][WQ]  L of the path from x+1
+    uint32_t *mnL = reinterpret_cast<uint32_t *>(exR + 2 * NP * WQ);  // [2][NP]
+    uint32_t *mnR = mnL + 2 * NP;
+    // behind the minima: four mbarriers, fullL[2] then fullR[2] (OFF_BAR)
+    constexpr uint32_t OFF_EXR = 2u * NP * WQ * 16u, OFF_MNL = 2u * OFF_EXR, OFF_MNR = OFF_MNL + 2u * NP * 4u, OFF_BAR = OFF_MNR + 2u * NP * 4u;
+    constexpr uint32_t TXB = LPC * 16u + 4u;                          // bytes a neighbour sends per row and side: one column's L + its minimum
+    const int tid = threadIdx.x, j = tid / LPC, sl = tid % LPC, grp = (tid & 31) / LPC;
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const int ncta = a.ncta, ncl = gridDim.x / ncta, cid = blockIdx.x / ncta;
+    const int wordsD = 4 * LPC;
+    for (int i = tid; i < 2 * 2 * NP * WQ; i += 1024) exL[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < 2 * 2 * NP; i += 1024) mnL[i] = 0u;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(sw);
+    const bool hasL = rank > 0u, hasR = (int)rank + 1 < ncta;
+    if (tid == 0) {
+        // one arrival (the receiving group's own arrive.expect_tx) + TXB bytes of st.async per phase; phase 0 is armed here
+        for (int b = 0; b < 4; b++) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sbase + OFF_BAR + 8u * b), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int b = 0; b < 4; b++)
+            if (b < 2 ? hasL : hasR)
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sbase + OFF_BAR + 8u * b), "r"(TXB) : "memory");
+    }
+    __syncthreads();
+    cluster_sync_all();
+    // q = position in the row's schedule (compile time), half = q ^ h0 (even CTAs left half first, odd CTAs right half first)
+    const int h0 = (int)(rank & 1u);
+    int colq[2]; bool inq[2];
+#pragma unroll
+    for (int q = 0; q < 2; q++) { colq[q] = (q ^ h0) * NS + j; inq[q] = (int)rank * XC + colq[q] < a.W1; }
+    // boundary groups: column 0 (half 0, j == 0) talks to the left neighbour, column XC - 1 (half 1, j == NS - 1) to the right one
+    const bool bndL = hasL && j == 0, bndR = hasR && j == NS - 1;
+    const uint32_t remR = hasR ? mapa_u32(sbase, rank + 1u) : 0u, remL = hasL ? mapa_u32(sbase, rank - 1u) : 0u;
+    const uint32_t P1x2 = (uint32_t)a.P1 * 0x00010001u, P2 = (uint32_t)a.P2;
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    const uint4 *Cq = reinterpret_cast<const uint4 *>(a.C);
+    uint4 *Sq = reinterpret_cast<uint4 *>(a.S);
+    // offsets in uint4 units: frame 0, first row of the pass, this thread's column of schedule position q
+    const size_t frameq = a.frame_words / 4;
+    const long long rowq = (long long)a.ystep * a.W1 * (wordsD / 4);
+    size_t base0[2], off[2];
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        base0[q] = ((size_t)a.ystart * a.W1 + (size_t)((int)rank * XC + (inq[q] ? colq[q] : 0))) * (wordsD / 4) + sl;
+        off[q] = base0[q] + (size_t)cid * frameq;
+    }
+    uint4 Lv[2] = {z, z};
+    uint32_t minV[2] = {0u, 0u};
+    uint32_t T = 0u;
+    bool broken = false;                                              // a wait ran out: stop waiting (wrong results, but no hang)
+    uint4 c = z, s = z;
+    if (cid < a.nframes && inq[0]) { c = __ldg(Cq + off[0]); s = Sq[off[0]]; }
+    for (int f = cid; f < a.nframes; f += ncl) {
+        const bool lastframe = f + ncl >= a.nframes;
+        for (int r = 0; r < a.H; r++, T++) {
+            const uint32_t b = T & 1u;
+            const uint32_t ph = ((T - (b ? 1u : 2u)) >> 1) & 1u;      // phase of buffer b's barriers that row T consumes (T >= 1)
+            const bool lastrow = r == a.H - 1;
+            if (tid == 0) {
+                // this CTA's segment of row r + VP_AHEAD (C and S: contiguous [column][d]) is pulled into L2 by the copy engine;
+                // the register prefetch one step ahead then only pays L2 latency
+                int pr = r + VP_AHEAD, pf = f;
+                if (pr >= a.H) { pr -= a.H; pf += ncl; }
+                if (pf < a.nframes) {
+                    const size_t o = ((size_t)pf * a.frame_words) + ((size_t)(a.ystart + pr * a.ystep) * a.W1 + (size_t)((int)rank * XC)) * wordsD;
+                    const uint32_t bytes = (uint32_t)min(XC, a.W1 - (int)rank * XC) * wordsD * 4u;
+                    l2_prefetch_bulk(a.C + o, bytes);
+                    l2_prefetch_bulk(a.S + o, bytes);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                // next step's C and S: the other column of this row, or the first column of the next row / next frame
+                uint4 cn = z, sn = z;
+                if (q == 0) {
+                    if (inq[1]) { cn = __ldg(Cq + off[1]); sn = Sq[off[1]]; }
+                } else {
+                    const bool more = !lastrow || !lastframe;
+                    const size_t o = lastrow ? base0[0] + (size_t)(f + ncl) * frameq : (size_t)((long long)off[0] + rowq);
+                    if (more && inq[0]) { cn = __ldg(Cq + o); sn = Sq[o]; }
+                }
+                const int col = colq[q];
+                const bool half0 = (q ^ h0) == 0;
+                if (T > 0u && !broken && (half0 ? bndL : bndR)) {
+                    const uint32_t bar = sbase + OFF_BAR + 8u * ((half0 ? 0u : 2u) + b);
+                    int spin = 0;
+                    while (!mbar_try_cta(bar, ph)) if (++spin > (1 << 18)) { broken = true; break; }
+                    // armed again for the row after next (the neighbour's next send into this buffer)
+                    if (sl == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(TXB) : "memory");
+                }
+                const uint4 pL = exL[(b * NP + col) * WQ + sl];
+                const uint4 pR = exR[(b * NP + col + 2) * WQ + sl];
+                const uint32_t pmL = mnL[b * NP + col], pmR = mnR[b * NP + col + 2];
+                uint32_t t0[4], t1[4], t2[4], m0, m1, m2;
+                path_core<LPC>(pL, pmL, c, sl, P1x2, P2, t0, m0);
+                path_core<LPC>(Lv[q], minV[q], c, sl, P1x2, P2, t1, m1);
+                path_core<LPC>(pR, pmR, c, sl, P1x2, P2, t2, m2);
+                uint32_t mL = group_min_u32<LPC>(m0, grp);
+                minV[q] = group_min_u32<LPC>(m1, grp);
+                uint32_t mR = group_min_u32<LPC>(m2, grp);
+                uint4 tL = make_uint4(t0[0], t0[1], t0[2], t0[3]);
+                Lv[q] = make_uint4(t1[0], t1[1], t1[2], t1[3]);
+                uint4 tR = make_uint4(t2[0], t2[1], t2[2], t2[3]);
+                if (inq[q]) {
+                    const uint32_t sv[4] = {s.x, s.y, s.z, s.w};
+                    uint32_t o[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        if (SAFE3) o[k] = min2(sv[k] + t0[k] + t1[k] + t2[k], 0x7FFF7FFFu);       // no 16-bit overflow possible
+                        else o[k] = min2(__vadd2(min2(__vadd2(min2(__vadd2(sv[k], t0[k]), 0x7FFF7FFFu), t1[k]), 0x7FFF7FFFu), t2[k]), 0x7FFF7FFFu);
+                    }
+                    Sq[off[q]] = make_uint4(o[0], o[1], o[2], o[3]);
+                }
+                if (lastrow) { tL = z; tR = z; Lv[q] = z; mL = 0u; mR = 0u; minV[q] = 0u; }     // the next frame's paths enter the image
+                if (inq[q]) {
+                    exL[((b ^ 1u) * NP + col + 1) * WQ + sl] = tL;
+                    exR[((b ^ 1u) * NP + col + 1) * WQ + sl] = tR;
+                    if (sl == 0) { mnL[(b ^ 1u) * NP + col + 1] = mL; mnR[(b ^ 1u) * NP + col + 1] = mR; }
+                }
+                if (!(lastframe && lastrow)) {
+                    if (!half0 && bndR) {            // column XC - 1: its rightward diagonal is the right neighbour's left pad (slot 0)
+                        const uint32_t bar = remR + OFF_BAR + 8u * (b ^ 1u);
+                        st_async_v4(remR + ((b ^ 1u) * NP * WQ + sl) * 16u, tL, bar);
+                        if (sl == 0) st_async_b32(remR + OFF_MNL + ((b ^ 1u) * NP) * 4u, mL, bar);
+                    }
+                    if (half0 && bndL) {             // column 0: its leftward diagonal is the left neighbour's right pad (slot XC + 1)
+                        const uint32_t bar = remL + OFF_BAR + 8u * (2u + (b ^ 1u));
+                        st_async_v4(remL + OFF_EXR + (((b ^ 1u) * NP + XC + 1) * WQ + sl) * 16u, tR, bar);
+                        if (sl == 0) st_async_b32(remL + OFF_MNR + ((b ^ 1u) * NP + XC + 1) * 4u, mR, bar);
+                    }
+                }
+                c = cn; s = sn;
+            }
+            off[0] = (size_t)((long long)off[0] + rowq); off[1] = (size_t)((long long)off[1] + rowq);
+            __syncthreads();
+        }
+        off[0] = base0[0] + (size_t)(f + ncl) * frameq; off[1] = base0[1] + (size_t)(f + ncl) * frameq;
+    }
+    cluster_sync_all();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1028,6 +1217,75 @@ int sgbm_sweep_ctas_per_frame(const SgbmGeom &g)
     return cdiv(g.W1, X);
 }
 
+// Whole-height pass (sgbm_vpass_kernel): CTAs per frame = cluster size, dynamic shared memory, and how many clusters the
+// device keeps resident at once (0: the pass does not apply -- other D, more than 16 CTAs per row, RTDM_SGBM_NOVPASS).
+namespace {
+struct VPassPlan { int ncta, nclusters; size_t smem; };
+
+template <int LPC, bool SAFE3>
+int vpass_config(int ncta, size_t smem, int *nclusters)
+{
+    RTDM_CUDA(cudaFuncSetAttribute(sgbm_vpass_kernel<LPC, SAFE3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (ncta > 8) RTDM_CUDA(cudaFuncSetAttribute(sgbm_vpass_kernel<LPC, SAFE3>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)ncta; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.gridDim = dim3((unsigned)ncta); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = smem; cfg.attrs = at; cfg.numAttrs = 1;
+    int ncl = 0;
+    if (cudaOccupancyMaxActiveClusters(&ncl, sgbm_vpass_kernel<LPC, SAFE3>, &cfg) != cudaSuccess) { cudaGetLastError(); ncl = 0; }
+    *nclusters = ncl;
+    return 0;
+}
+
+template <int LPC, bool SAFE3>
+int vpass_launch(const VPassArgs &a, int nclusters, size_t smem, cudaStream_t st)
+{
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)a.ncta; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.gridDim = dim3((unsigned)(a.ncta * nclusters)); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    RTDM_CUDA(cudaLaunchKernelEx(&cfg, sgbm_vpass_kernel<LPC, SAFE3>, a));
+    return 0;
+}
+
+bool sgbm_safe3(const SgbmGeom &g)
+{
+    const int pixmax = 2 * g.ftzero + 63, Lmax = 2 * g.P2 + g.bs * g.bs * pixmax;
+    return 32767 + 3 * Lmax <= 65535;
+}
+
+int vpass_plan(const SgbmGeom &g, VPassPlan *p)
+{
+    p->ncta = 0; p->nclusters = 0; p->smem = 0;
+    if (!(g.D == 64 || g.D == 128) || g.W1 <= 0 || g.sw.sgbm_oldpath || g.sw.sgbm_nosweep || g.sw.sgbm_novpass) return 0;
+    const int LPC = g.D / 8, NS = 1024 / LPC, XC = 2 * NS, NP = XC + 2;
+    const int ncta = cdiv(g.W1, XC);
+    if (ncta > 16) return 0;
+    const size_t smem = (size_t)2 * 2 * NP * LPC * 16 + (size_t)2 * 2 * NP * 4 + 32;
+    const bool safe3 = sgbm_safe3(g);
+    int ncl = 0, rc;
+    if (g.D == 128) rc = safe3 ? vpass_config<16, true>(ncta, smem, &ncl) : vpass_config<16, false>(ncta, smem, &ncl);
+    else rc = safe3 ? vpass_config<8, true>(ncta, smem, &ncl) : vpass_config<8, false>(ncta, smem, &ncl);
+    if (rc) return rc;
+    if (ncl < 1) return 0;
+    if (g.sw.sgbm_vpass_maxcl > 0) ncl = std::min(ncl, g.sw.sgbm_vpass_maxcl);
+    p->ncta = ncta; p->nclusters = ncl; p->smem = smem;
+    return 0;
+}
+}  // namespace
+
+// frames one whole-height pass works on at the same time (0 when the pass does not apply): the host layer makes its
+// sub-batches multiples of it
+int sgbm_vpass_frames_in_flight(const SgbmGeom &g)
+{
+    VPassPlan p;
+    if (vpass_plan(g, &p)) { cudaGetLastError(); return 0; }
+    return p.nclusters;
+}
+
 int launch_sgbm(const SgbmGeom &g, int n, PlaneU8 left, PlaneU8 right, PlaneS16 out, SgbmWork w,
                 cudaStream_t st, int *launches)
 {
@@ -1110,9 +1368,24 @@ int launch_sgbm(const SgbmGeom &g, int n, PlaneU8 left, PlaneU8 right, PlaneS16 
     const size_t front_words = (size_t)3 * g.W1 * (g.D / 2), fmin_words = (size_t)3 * g.W1;
     const size_t front_bytes = align_up((front_words + fmin_words) * 4, 256);
     const bool sweep = fast && !g.sw.sgbm_nosweep && rec_bytes + 2 * front_bytes <= w.frame_planes;
-    const int pixmax = 2 * g.ftzero + 63, Lmax = 2 * g.P2 + g.bs * g.bs * pixmax;
-    const bool safe3 = 32767 + 3 * Lmax <= 65535;
+    const bool safe3 = sgbm_safe3(g);
+    // whole-height cluster pass for batches (a single frame keeps only one cluster busy: the tiled sweep is quicker there)
+    VPassPlan vp = {0, 0, 0};
+    if (fast && n >= g.sw.sgbm_vpass_min) { const int rc = vpass_plan(g, &vp); if (rc) return rc; }
+    auto launch_vpass = [&](int dy) -> int {
+        VPassArgs a;
+        a.C = reinterpret_cast<const uint32_t *>(w.C); a.S = reinterpret_cast<uint32_t *>(w.S); a.frame_words = frame_words;
+        a.W1 = g.W1; a.H = g.H; a.P1 = g.P1; a.P2 = g.P2;
+        a.ystart = dy > 0 ? 0 : g.H - 1; a.ystep = dy; a.nframes = n; a.ncta = vp.ncta;
+        const int ncl = std::min(vp.nclusters, n);
+        int rc;
+        if (g.D == 128) rc = safe3 ? vpass_launch<16, true>(a, ncl, vp.smem, st) : vpass_launch<16, false>(a, ncl, vp.smem, st);
+        else rc = safe3 ? vpass_launch<8, true>(a, ncl, vp.smem, st) : vpass_launch<8, false>(a, ncl, vp.smem, st);
+        if (launches) (*launches)++;
+        return rc;
+    };
     auto launch_sweep = [&](int dy) -> int {
+        if (vp.nclusters > 0) return launch_vpass(dy);
         const int ntiles = cdiv(g.H, SW_R);
         const int LPC = g.D / 8, NS = 1024 / LPC, X = NS - 2 * SW_R;
         const size_t smem = (size_t)2 * 2 * (NS + 2) * LPC * 16 + (size_t)2 * 2 * (NS + 2) * 4;

@@ -99,6 +99,45 @@ def test_sgbm_kernel_variants_agree_with_oracle(gpu, orc, env, monkeypatch):
         assert np.array_equal(got, ref), (env, W, H, nd, bs, mode, int((got != ref).sum()))
 
 
+@pytest.mark.parametrize("case", [
+    # W, H, nd, bs, mode, batch, cap on clusters (None: what the device keeps resident), P2
+    (400, 150, 128, 5, 1, 3, None, None),      # 3 CTAs per cluster (128 columns each), one frame per cluster
+    (331, 97, 64, 3, 0, 2, None, None),        # D = 64: 256 columns per CTA, 2 CTAs
+    (700, 64, 128, 5, 1, 5, 2, None),          # 5 CTAs, 5 frames over 2 clusters: 3 frames, then 2, per cluster
+    (200, 51, 64, 5, 1, 4, 1, None),           # 1 CTA, odd height: the buffer parity flips from frame to frame
+    (453, 33, 128, 3, 0, 7, 3, None),          # last CTA holds 69 of its 128 columns
+    (360, 120, 64, 5, 0, 3, 1, 4400),          # step-wise clamp instantiation
+])
+def test_sgbm_cluster_pass_matches_oracle(gpu, orc, case, monkeypatch):
+    """Batches take sgbm_vpass_kernel (one thread-block cluster per frame, neighbours exchanging boundary columns through
+    distributed shared memory); single frames take the tiled sweeps.  Both must be the oracle's arithmetic, for every
+    cluster size, with several frames per cluster, and with the last CTA partly outside the image."""
+    from rtdm_b200 import synth
+    W, H, nd, bs, mode, B, maxcl, P2 = case
+    for v in ("RTDM_SGBM_NOSWEEP", "RTDM_SGBM_NOFUSE", "RTDM_SGBM_OLDCOST", "RTDM_SGBM_OLDPATH", "RTDM_SGBM_NOVPASS", "RTDM_SGBM_VPASS_MAXCL"):
+        monkeypatch.delenv(v, raising=False)
+    if maxcl:
+        monkeypatch.setenv("RTDM_SGBM_VPASS_MAXCL", str(maxcl))
+    p = dict(blockSize=bs, minDisparity=0, numDisparities=nd, uniquenessRatio=12, speckleWindowSize=0 if P2 else 50,
+             speckleRange=2, disp12MaxDiff=1, mode=mode)
+    if P2:
+        p.update(P1=700, P2=P2, uniquenessRatio=5)
+    fr = [synth.stereo_pair(W, H, nd, 5200 + 7 * i + W) for i in range(B)]
+    L = np.stack([f[0] for f in fr]); R = np.stack([f[1] for f in fr])
+    m = _mk(gpu, p, W, H, max_batch=B)
+    out = m.compute_batch(L, R)
+    assert m.last_launches() <= 2 + 2 + 2 + 1 + 1 + 4            # planes, cost, 2 horizontal paths, 2 passes, LR, median, speckle
+    checked = 0
+    for i in range(B):
+        ref, outside = orc.sgbm_compute(L[i], R[i], orc.sgbm_params(**p), return_domain_flag=True)
+        if outside:
+            continue
+        assert np.array_equal(out[i], ref), (case, i, int((out[i] != ref).sum()))
+        assert np.array_equal(m.compute(L[i], R[i]), ref), (case, i, "tiled sweeps")
+        checked += 1
+    assert checked >= 1
+
+
 def test_sgbm_large_penalties_take_the_stepwise_clamp(gpu, orc):
     """P2 large enough that three path costs next to S could overflow 16 bits (2*P2 + bs^2*93 > 10922): the sweep
     kernel then clamps after every addition (cv::StereoSGBM's saturating adds) instead of once.  5-path mode, so
