@@ -41,7 +41,7 @@ Switches read_switches()
     sw.sgbm_nosweep = isset("RTDM_SGBM_NOSWEEP");
     sw.sgbm_sweep_rows = geti("RTDM_SGBM_SWEEP_ROWS", 0);
     sw.sgbm_novpass = isset("RTDM_SGBM_NOVPASS");
-    sw.sgbm_vpass_min = geti("RTDM_SGBM_VPASS_MIN", 2);
+    sw.sgbm_vpass_min = geti("RTDM_SGBM_VPASS_MIN", 0);
     sw.sgbm_vpass_maxcl = geti("RTDM_SGBM_VPASS_MAXCL", 0);
     return sw;
 }
@@ -921,7 +921,7 @@ static int sgbm_pipeline(rtdm_sgbm *h, int n, PlaneU8 L, PlaneU8 R, int W, int H
     // tiles = 6.0 waves of 148 SMs; 32 frames would be 5.2 -> 6 waves)
     int chunk = h->volB;
     // whole-height pass (batches): one cluster per frame, `q` frames at a time -> sub-batches are multiples of q
-    const int q = n >= h->sw.sgbm_vpass_min ? sgbm_vpass_frames_in_flight(g) : 0;
+    const int q = sgbm_vpass_frames_in_flight(g, std::min(n, chunk));
     if (q > 0) {
         if (n <= chunk) chunk = n;                               // one sub-batch; the pass itself loops over rounds of q frames
         else {
@@ -1110,6 +1110,14 @@ extern "C" int rtdm_sgbm_compute(rtdm_sgbm *h, const uint8_t *left, size_t lstep
 }
 
 extern "C" int rtdm_sgbm_last_launches(const rtdm_sgbm *h) { return h ? h->launches : 0; }
+
+extern "C" int rtdm_sgbm_batch_quantum(rtdm_sgbm *h, int width, int height)
+{
+    if (!h || width < 1 || height < 1 || width > h->maxW || height > h->maxH) { set_error("sgbm_batch_quantum: bad argument"); return -RTDM_EINVAL; }
+    RTDM_CUDA(cudaSetDevice(h->dev));
+    const int q = sgbm_vpass_frames_in_flight(sgbm_geom(h->p, h->sw, width, height), h->volB);
+    return q > 0 ? q : 1;
+}
 
 // =================================================================================================
 // morphological filter

@@ -41,7 +41,7 @@ struct Switches {
     int sgbm_oldcost = 0, sgbm_oldpath = 0, sgbm_nofuse = 0, sgbm_nosweep = 0;   // RTDM_SGBM_*
     int sgbm_sweep_rows = 0;    // RTDM_SGBM_SWEEP_ROWS: rows per sweep launch (0 = default)
     int sgbm_novpass = 0;       // RTDM_SGBM_NOVPASS: tiled row sweeps (sgbm_sweep_kernel) instead of the whole-height cluster pass
-    int sgbm_vpass_min = 2;     // RTDM_SGBM_VPASS_MIN: smallest batch that takes the whole-height pass
+    int sgbm_vpass_min = 0;     // RTDM_SGBM_VPASS_MIN: smallest batch that takes the whole-height pass (0 = half the resident clusters)
     int sgbm_vpass_maxcl = 0;   // RTDM_SGBM_VPASS_MAXCL: cap on the clusters of a pass (tests: forces several frames per cluster)
 };
 Switches read_switches();
@@ -150,7 +150,7 @@ struct SgbmWork {
 };
 size_t sgbm_work_bytes(const SgbmGeom &g, size_t *planes, size_t *vol);
 int sgbm_sweep_ctas_per_frame(const SgbmGeom &g);
-int sgbm_vpass_frames_in_flight(const SgbmGeom &g);
+int sgbm_vpass_frames_in_flight(const SgbmGeom &g, int n);
 int launch_sgbm(const SgbmGeom &g, int n, PlaneU8 left, PlaneU8 right, PlaneS16 out, SgbmWork w,
                 cudaStream_t st, int *launches);
 

@@ -82,6 +82,7 @@ SIGNATURES = {
     "rtdm_sgbm_wait_oldest": (_i, [_vp]),
     "rtdm_sgbm_compute_device": (_i, [_vp, _i, _vp, _sz, _sz, _vp, _sz, _sz, _i, _i, _vp, _sz, _sz, _vp]),
     "rtdm_sgbm_last_launches": (_i, [_vp]),
+    "rtdm_sgbm_batch_quantum": (_i, [_vp, _i, _i]),
     "rtdm_sgbm_set_profiling": (_i, [_vp, _i]),
     "rtdm_sgbm_stage_times": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(_i)]),
     "rtdm_morph_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _i]),
@@ -399,6 +400,12 @@ class CUDASemiGlobalMatcher(_MatcherBase):
 
     def wait_oldest(self):
         _check(self._l.rtdm_sgbm_wait_oldest(self._h))
+
+    def batch_quantum(self, width: int, height: int) -> int:
+        """Frames the aggregation passes work on at once for this size: batches that are multiples of it run fullest."""
+        q = self._l.rtdm_sgbm_batch_quantum(self._h, int(width), int(height))
+        _check(min(q, 0))
+        return q
 
     def set_profiling(self, on: bool):
         _check(self._l.rtdm_sgbm_set_profiling(self._h, int(on)))

@@ -61,10 +61,17 @@ def test_sgbm_degenerate_width(gpu, orc):
     assert np.array_equal(got, orc.sgbm_compute(L, R, orc.sgbm_params(**p)))
 
 
+@pytest.mark.parametrize("vpass", [False, True])
 @pytest.mark.parametrize("mode", [0, 1])
-def test_sgbm_720p_full_size(gpu, orc, mode):
-    """BASELINE config 3: 1280x720, nd=128, bs=5, P1=600, P2=2400; MODE_SGBM and MODE_HH; batch of 2."""
+def test_sgbm_720p_full_size(gpu, orc, mode, vpass, monkeypatch):
+    """BASELINE config 3: 1280x720, nd=128, bs=5, P1=600, P2=2400; MODE_SGBM and MODE_HH; batch of 2, as tiled sweeps
+    (what a batch this small takes) and forced through the whole-height pass (a cluster of 9 CTAs per frame)."""
     from rtdm_b200 import synth
+    monkeypatch.delenv("RTDM_SGBM_NOVPASS", raising=False)
+    if vpass:
+        monkeypatch.setenv("RTDM_SGBM_VPASS_MIN", "2")
+    else:
+        monkeypatch.delenv("RTDM_SGBM_VPASS_MIN", raising=False)
     p = dict(blockSize=5, minDisparity=0, numDisparities=128, uniquenessRatio=10, speckleWindowSize=100,
              speckleRange=32, disp12MaxDiff=1, mode=mode)
     frames = [synth.stereo_pair(1280, 720, 128, 1000 + i) for i in range(2)]
@@ -78,6 +85,7 @@ def test_sgbm_720p_full_size(gpu, orc, mode):
         v = out[i][out[i] != -16]
         assert v.min() >= 0 and v.max() <= 127 * 16 + 15
         assert (out[i][:, :127] == -16).all()
+    assert (m.last_launches() <= 12) == vpass
 
 
 @pytest.mark.parametrize("env", [None, "RTDM_SGBM_NOSWEEP", "RTDM_SGBM_NOFUSE", "RTDM_SGBM_OLDCOST", "RTDM_SGBM_OLDPATH"])
@@ -114,8 +122,9 @@ def test_sgbm_cluster_pass_matches_oracle(gpu, orc, case, monkeypatch):
     cluster size, with several frames per cluster, and with the last CTA partly outside the image."""
     from rtdm_b200 import synth
     W, H, nd, bs, mode, B, maxcl, P2 = case
-    for v in ("RTDM_SGBM_NOSWEEP", "RTDM_SGBM_NOFUSE", "RTDM_SGBM_OLDCOST", "RTDM_SGBM_OLDPATH", "RTDM_SGBM_NOVPASS", "RTDM_SGBM_VPASS_MAXCL"):
+    for v in ("RTDM_SGBM_NOSWEEP", "RTDM_SGBM_NOFUSE", "RTDM_SGBM_OLDCOST", "RTDM_SGBM_OLDPATH", "RTDM_SGBM_NOVPASS", "RTDM_SGBM_VPASS_MAXCL", "RTDM_SGBM_VPASS_MIN"):
         monkeypatch.delenv(v, raising=False)
+    monkeypatch.setenv("RTDM_SGBM_VPASS_MIN", "2")               # by default small batches take the tiled sweeps
     if maxcl:
         monkeypatch.setenv("RTDM_SGBM_VPASS_MAXCL", str(maxcl))
     p = dict(blockSize=bs, minDisparity=0, numDisparities=nd, uniquenessRatio=12, speckleWindowSize=0 if P2 else 50,
@@ -126,7 +135,7 @@ def test_sgbm_cluster_pass_matches_oracle(gpu, orc, case, monkeypatch):
     L = np.stack([f[0] for f in fr]); R = np.stack([f[1] for f in fr])
     m = _mk(gpu, p, W, H, max_batch=B)
     out = m.compute_batch(L, R)
-    assert m.last_launches() <= 2 + 2 + 2 + 1 + 1 + 4            # planes, cost, 2 horizontal paths, 2 passes, LR, median, speckle
+    assert m.last_launches() <= 2 + 2 + 2 + 1 + 1 + 4            # planes, cost, 2 horizontal paths, 2 passes, LR, median, speckle: no tiled sweeps
     checked = 0
     for i in range(B):
         ref, outside = orc.sgbm_compute(L[i], R[i], orc.sgbm_params(**p), return_domain_flag=True)
