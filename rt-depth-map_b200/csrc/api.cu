@@ -43,6 +43,7 @@ Switches read_switches()
     sw.sgbm_novpass = isset("RTDM_SGBM_NOVPASS");
     sw.sgbm_vpass_min = geti("RTDM_SGBM_VPASS_MIN", 0);
     sw.sgbm_vpass_maxcl = geti("RTDM_SGBM_VPASS_MAXCL", 0);
+    sw.sgbm_vpass_shape = geti("RTDM_SGBM_VPASS_SHAPE", 0);
     return sw;
 }
 

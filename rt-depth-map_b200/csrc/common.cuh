@@ -42,6 +42,7 @@ struct Switches {
     int sgbm_sweep_rows = 0;    // RTDM_SGBM_SWEEP_ROWS: rows per sweep launch (0 = default)
     int sgbm_novpass = 0;       // RTDM_SGBM_NOVPASS: tiled row sweeps (sgbm_sweep_kernel) instead of the whole-height cluster pass
     int sgbm_vpass_min = 0;     // RTDM_SGBM_VPASS_MIN: smallest batch that takes the whole-height pass (0 = half the resident clusters)
+    int sgbm_vpass_shape = 0;   // RTDM_SGBM_VPASS_SHAPE: 1 = 512 threads x 4 columns per thread instead of 1024 x 2
     int sgbm_vpass_maxcl = 0;   // RTDM_SGBM_VPASS_MAXCL: cap on the clusters of a pass (tests: forces several frames per cluster)
 };
 Switches read_switches();

@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include <stdlib.h>
 #include <algorithm>
+#include <type_traits>
 
 namespace rtdm {
 namespace {
@@ -838,6 +839,7 @@ struct VPassArgs {
     int W1, H, P1, P2;
     int ystart, ystep;                       // first row and row step of the pass
     int nframes, ncta;                       // frames of this launch; CTAs per cluster (= per frame)
+    uint32_t one;                            // 1: a multiplier the compiler cannot fold (see vcore)
 };
 
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t a, uint32_t rank) { uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank)); return r; }
@@ -862,26 +864,54 @@ __device__ __forceinline__ void cluster_sync_all() { asm volatile("barrier.clust
 
 constexpr int VP_AHEAD = 3;                  // rows between the L2 prefetch and their use
 
-template <int LPC, bool SAFE3>
-__global__ void __launch_bounds__(1024, 1)
+// One step of one path for a lane's 8 disparities in the pass kernel.  `minLp` and the returned `m` are the minimum over d
+// SPLATTED into both halves, so the 32-bit minimum over a column's lanes is the splatted column minimum and P2 + min is one
+// add.  The packed 16-bit minima / add-minima only issue on the ALU pipe (64 lanes per clock and SM), which is what bounds
+// the pass, so the plain 32-bit arithmetic is written as multiply-add with `one`, a run-time 1 the compiler cannot see
+// through and therefore keeps as IMAD -- the other integer pipe.  v + C - (P2 + min): every 16-bit half of the result is a
+// path cost (0 <= L < 65536, v >= min), so no carry or borrow crosses the halves and 32-bit arithmetic is exact.
+template <int LPC>
+__device__ __forceinline__ void vcore(const uint4 Lp, const uint32_t minLp, const uint4 c, int sl, uint32_t one, uint32_t P1x2, uint32_t P2x2,
+                                      uint32_t (&t)[4], uint32_t &m)
+{
+    uint32_t left = __shfl_up_sync(0xFFFFFFFFu, Lp.w, 1, LPC);
+    uint32_t right = __shfl_down_sync(0xFFFFFFFFu, Lp.x, 1, LPC);
+    if (sl == 0) left = 0x7FFF0000u;                       // L[-1] = MAX_COST (upper half is used)
+    if (sl == LPC - 1) right = 0x00007FFFu;                // L[D]  = MAX_COST (lower half is used)
+    const uint32_t dx2 = P2x2 + minLp, ndx2 = 0u - dx2;
+    const uint32_t w[6] = {left, Lp.x, Lp.y, Lp.z, Lp.w, right};
+    const uint32_t cc[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const uint32_t lm1 = __byte_perm(w[i], w[i + 1], 0x5432);      // (L[d-1], L[d])   for the pair (d, d+1)
+        const uint32_t lp1 = __byte_perm(w[i + 1], w[i + 2], 0x5432);  // (L[d+1], L[d+2])
+        const uint32_t v = __vimin3_u16x2(w[i + 1], __vadd2(min2(lm1, lp1), P1x2), dx2);   // min(a + P1, b + P1) = min(a, b) + P1
+        t[i] = (v * one + cc[i]) * one + ndx2;
+    }
+    const uint32_t mm = min2(min2(t[0], t[1]), min2(t[2], t[3]));
+    m = min2(mm, __byte_perm(mm, mm, 0x1032));
+}
+
+// NT threads per CTA, a thread owns NQ columns NS = NT / LPC apart ("quarters"; XC = NQ * NS columns per CTA).  1024 x 2 is the
+// default; 512 x 4 (RTDM_SGBM_VPASS_SHAPE=1: 128 registers per thread, nothing recomputed) has too few warps to hide the
+// shuffle / reduction latencies: 823 against 656 us per MODE_HH frame when both were measured.
+template <int LPC, int NT, int NQ, bool SAFE3>
+__global__ void __launch_bounds__(NT, 1)
 sgbm_vpass_kernel(VPassArgs a)
 {
-    constexpr int NS = 1024 / LPC, XC = 2 * NS, WQ = LPC, NP = XC + 2;   // slots per half, columns per CTA, uint4 per column, pads
+    constexpr int NS = NT / LPC, XC = NQ * NS, WQ = LPC, NP = XC + 2;     // slots per quarter, columns per CTA, uint4 per column, pads
     extern __shared__ __align__(16) uint8_t sw[];
-    uint4 *exL = reinterpret_cast<uint4 *>(sw);                       // [2][NP][WQ]  L of the path from x-1, stored at producing column + 1
-    uint4 *exR = exL + 2 * NP * WQ;                                   // [2][NP][WQ]  L of the path from x+1
-    uint32_t *mnL = reinterpret_cast<uint32_t *>(exR + 2 * NP * WQ);  // [2][NP]
-    uint32_t *mnR = mnL + 2 * NP;
-    // behind the minima: four mbarriers, fullL[2] then fullR[2] (OFF_BAR)
-    constexpr uint32_t OFF_EXR = 2u * NP * WQ * 16u, OFF_MNL = 2u * OFF_EXR, OFF_MNR = OFF_MNL + 2u * NP * 4u, OFF_BAR = OFF_MNR + 2u * NP * 4u;
+    // exL [2][NP][WQ] uint4: L of the path from x-1, stored at producing column + 1; exR the same for the path from x+1;
+    // mnL, mnR [2][NP] their minima; then four mbarriers, fullL[2] and fullR[2]
+    constexpr uint32_t BUFB = NP * WQ * 16u, BUFM = NP * 4u;
+    constexpr uint32_t OFF_EXR = 2u * BUFB, OFF_MNL = 2u * OFF_EXR, OFF_MNR = OFF_MNL + 2u * BUFM, OFF_BAR = OFF_MNR + 2u * BUFM;
     constexpr uint32_t TXB = LPC * 16u + 4u;                          // bytes a neighbour sends per row and side: one column's L + its minimum
     const int tid = threadIdx.x, j = tid / LPC, sl = tid % LPC, grp = (tid & 31) / LPC;
     uint32_t rank;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
     const int ncta = a.ncta, ncl = gridDim.x / ncta, cid = blockIdx.x / ncta;
     const int wordsD = 4 * LPC;
-    for (int i = tid; i < 2 * 2 * NP * WQ; i += 1024) exL[i] = make_uint4(0u, 0u, 0u, 0u);
-    for (int i = tid; i < 2 * 2 * NP; i += 1024) mnL[i] = 0u;
+    for (uint32_t i = tid * 16u; i < OFF_BAR; i += NT * 16u) *reinterpret_cast<uint4 *>(sw + i) = make_uint4(0u, 0u, 0u, 0u);
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(sw);
     const bool hasL = rank > 0u, hasR = (int)rank + 1 < ncta;
     if (tid == 0) {
@@ -894,118 +924,137 @@ sgbm_vpass_kernel(VPassArgs a)
     }
     __syncthreads();
     cluster_sync_all();
-    // q = position in the row's schedule (compile time), half = q ^ h0 (even CTAs left half first, odd CTAs right half first)
-    const int h0 = (int)(rank & 1u);
-    int colq[2]; bool inq[2];
+    // q = position in the row's schedule (compile time); even CTAs go through their quarters left to right, odd CTAs right to
+    // left, so column 0 / XC - 1 of a CTA is produced NQ - 1 steps before the neighbour consumes it
+    const bool odd = (rank & 1u) != 0u;
+    bool inq[NQ];
+    int bq[NQ];                                  // 1: this thread's column at position q is column 0 (talks to the left neighbour), 2: column XC - 1
+    uint32_t aq[NQ], mq[NQ];                     // byte offsets of this thread's exL / mnL READ entries (buffer 0) in sw
+    // C / S addresses: 32-bit offsets in uint4 units from the volume base (the volumes of a call stay below 2^32 x 16 bytes:
+    // vpass_plan), formed by one IMAD.WIDE; loads are unconditional -- a column outside the image reads column 0 of its CTA
+    // and only its stores are predicated
+    uint32_t off[NQ];
+    const uint32_t frameq = (uint32_t)(a.frame_words / 4);
+    const uint32_t rowq = (uint32_t)(a.ystep * a.W1 * (wordsD / 4));                       // two's complement for the upward pass
+    const uint32_t framestep = (uint32_t)ncl * frameq - (uint32_t)(a.H - 1) * rowq;         // last row of a frame -> first row of this cluster's next
 #pragma unroll
-    for (int q = 0; q < 2; q++) { colq[q] = (q ^ h0) * NS + j; inq[q] = (int)rank * XC + colq[q] < a.W1; }
-    // boundary groups: column 0 (half 0, j == 0) talks to the left neighbour, column XC - 1 (half 1, j == NS - 1) to the right one
-    const bool bndL = hasL && j == 0, bndR = hasR && j == NS - 1;
+    for (int q = 0; q < NQ; q++) {
+        const int quarter = odd ? NQ - 1 - q : q, col = quarter * NS + j;
+        inq[q] = (int)rank * XC + col < a.W1;
+        bq[q] = (quarter == 0 && hasL && j == 0) ? 1 : ((quarter == NQ - 1 && hasR && j == NS - 1) ? 2 : 0);
+        aq[q] = (uint32_t)(col * WQ + sl) * 16u;
+        mq[q] = OFF_MNL + (uint32_t)col * 4u;
+        off[q] = (uint32_t)cid * frameq + (uint32_t)(a.ystart * a.W1 + (int)rank * XC + (inq[q] ? col : 0)) * (uint32_t)(wordsD / 4) + (uint32_t)sl;
+    }
     const uint32_t remR = hasR ? mapa_u32(sbase, rank + 1u) : 0u, remL = hasL ? mapa_u32(sbase, rank - 1u) : 0u;
-    const uint32_t P1x2 = (uint32_t)a.P1 * 0x00010001u, P2 = (uint32_t)a.P2;
+    const uint32_t P1x2 = (uint32_t)a.P1 * 0x00010001u, P2x2 = (uint32_t)a.P2 * 0x00010001u;
+    const uint32_t one = a.one;                                       // 1, opaque to the compiler (see vcore)
     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
     const uint4 *Cq = reinterpret_cast<const uint4 *>(a.C);
     uint4 *Sq = reinterpret_cast<uint4 *>(a.S);
-    // offsets in uint4 units: frame 0, first row of the pass, this thread's column of schedule position q
-    const size_t frameq = a.frame_words / 4;
-    const long long rowq = (long long)a.ystep * a.W1 * (wordsD / 4);
-    size_t base0[2], off[2];
+    uint4 Lv[NQ];
+    uint32_t minV[NQ];
 #pragma unroll
-    for (int q = 0; q < 2; q++) {
-        base0[q] = ((size_t)a.ystart * a.W1 + (size_t)((int)rank * XC + (inq[q] ? colq[q] : 0))) * (wordsD / 4) + sl;
-        off[q] = base0[q] + (size_t)cid * frameq;
-    }
-    uint4 Lv[2] = {z, z};
-    uint32_t minV[2] = {0u, 0u};
+    for (int q = 0; q < NQ; q++) { Lv[q] = z; minV[q] = 0u; }
     uint32_t T = 0u;
     bool broken = false;                                              // a wait ran out: stop waiting (wrong results, but no hang)
     uint4 c = z, s = z;
-    if (cid < a.nframes && inq[0]) { c = __ldg(Cq + off[0]); s = Sq[off[0]]; }
+    if (cid < a.nframes) { c = __ldg(Cq + off[0]); s = Sq[off[0]]; }
+
+    // one image row; LAST: the frame's last row hands zeros on (the state of a path that enters the image), so the next frame
+    // starts without a special case and the row counter T that selects buffers and barrier phases simply runs on
+    auto row = [&](auto last_tag, int f, int r, bool lastframe) {
+        constexpr bool LAST = decltype(last_tag)::value;
+        const uint32_t b = T & 1u;
+        const uint32_t ph = ((T - (b ? 1u : 2u)) >> 1) & 1u;          // phase of buffer b's barriers that row T consumes (T >= 1)
+        const uint32_t rb = b * BUFB, wb = BUFB - rb, rm = b * BUFM, wm = BUFM - rm;       // read / write buffer offsets
+        if (tid == 0) {
+            // this CTA's segment of row r + VP_AHEAD (C and S: contiguous [column][d]) is pulled into L2 by the copy engine;
+            // the register prefetch one step ahead then only pays L2 latency
+            int pr = r + VP_AHEAD, pf = f;
+            if (pr >= a.H) { pr -= a.H; pf += ncl; }
+            if (pf < a.nframes) {
+                const size_t o = ((size_t)pf * a.frame_words) + ((size_t)(a.ystart + pr * a.ystep) * a.W1 + (size_t)((int)rank * XC)) * wordsD;
+                const uint32_t bytes = (uint32_t)min(XC, a.W1 - (int)rank * XC) * wordsD * 4u;
+                l2_prefetch_bulk(a.C + o, bytes);
+                l2_prefetch_bulk(a.S + o, bytes);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+            // next step's C and S: the next column of this row, or the first column of the next row / next frame
+            const uint32_t on = q + 1 < NQ ? off[q + 1] : (!LAST ? off[0] + rowq : (lastframe ? off[0] : off[0] + framestep));
+            const uint4 cn = __ldg(Cq + on), sn = Sq[on];
+            if (bq[q] != 0 && T > 0u && !broken) {
+                const uint32_t bar = sbase + OFF_BAR + 8u * ((bq[q] == 1 ? 0u : 2u) + b);
+                int spin = 0;
+                while (!mbar_try_cta(bar, ph)) if (++spin > (1 << 18)) { broken = true; break; }
+                // armed again for the row after next (the neighbour's next send into this buffer)
+                if (sl == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(TXB) : "memory");
+            }
+            const uint4 pL = *reinterpret_cast<const uint4 *>(sw + aq[q] + rb);                           // column - 1's entry
+            const uint4 pR = *reinterpret_cast<const uint4 *>(sw + aq[q] + rb + OFF_EXR + 2u * WQ * 16u);  // column + 1's entry
+            const uint32_t pmL = *reinterpret_cast<const uint32_t *>(sw + mq[q] + rm);
+            const uint32_t pmR = *reinterpret_cast<const uint32_t *>(sw + mq[q] + rm + 2u * BUFM + 8u);
+            uint32_t t0[4], t1[4], t2[4], m0, m1, m2;
+            vcore<LPC>(pL, pmL, c, sl, one, P1x2, P2x2, t0, m0);
+            vcore<LPC>(Lv[q], minV[q], c, sl, one, P1x2, P2x2, t1, m1);
+            vcore<LPC>(pR, pmR, c, sl, one, P1x2, P2x2, t2, m2);
+            if (inq[q]) {
+                const uint32_t sv[4] = {s.x, s.y, s.z, s.w};
+                uint32_t o[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    if (SAFE3) o[i] = min2(t2[i] * one + (t1[i] * one + (t0[i] * one + sv[i])), 0x7FFF7FFFu);   // no 16-bit overflow possible
+                    else o[i] = min2(__vadd2(min2(__vadd2(min2(__vadd2(sv[i], t0[i]), 0x7FFF7FFFu), t1[i]), 0x7FFF7FFFu), t2[i]), 0x7FFF7FFFu);
+                }
+                Sq[off[q]] = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+            uint4 tL, tR;
+            uint32_t mL, mR;
+            if (LAST) { tL = z; tR = z; Lv[q] = z; mL = 0u; mR = 0u; minV[q] = 0u; }
+            else {
+                mL = group_min_u32<LPC>(m0, grp);
+                minV[q] = group_min_u32<LPC>(m1, grp);
+                mR = group_min_u32<LPC>(m2, grp);
+                tL = make_uint4(t0[0], t0[1], t0[2], t0[3]);
+                Lv[q] = make_uint4(t1[0], t1[1], t1[2], t1[3]);
+                tR = make_uint4(t2[0], t2[1], t2[2], t2[3]);
+            }
+            if (inq[q]) {
+                *reinterpret_cast<uint4 *>(sw + aq[q] + wb + WQ * 16u) = tL;                               // own entry: slot column + 1
+                *reinterpret_cast<uint4 *>(sw + aq[q] + wb + OFF_EXR + WQ * 16u) = tR;
+                if (sl == 0) {
+                    *reinterpret_cast<uint32_t *>(sw + mq[q] + wm + 4u) = mL;
+                    *reinterpret_cast<uint32_t *>(sw + mq[q] + wm + 2u * BUFM + 4u) = mR;
+                }
+            }
+            if (bq[q] != 0 && !(LAST && lastframe)) {
+                if (bq[q] == 2) {                // column XC - 1: its rightward diagonal is the right neighbour's left pad (slot 0)
+                    const uint32_t bar = remR + OFF_BAR + 8u * (b ^ 1u);
+                    st_async_v4(remR + wb + (uint32_t)sl * 16u, tL, bar);
+                    if (sl == 0) st_async_b32(remR + OFF_MNL + wm, mL, bar);
+                } else {                         // column 0: its leftward diagonal is the left neighbour's right pad (slot XC + 1)
+                    const uint32_t bar = remL + OFF_BAR + 8u * (2u + (b ^ 1u));
+                    st_async_v4(remL + OFF_EXR + wb + (uint32_t)((XC + 1) * WQ + sl) * 16u, tR, bar);
+                    if (sl == 0) st_async_b32(remL + OFF_MNR + wm + (uint32_t)(XC + 1) * 4u, mR, bar);
+                }
+            }
+            c = cn; s = sn;
+        }
+        T++;
+        __syncthreads();
+    };
     for (int f = cid; f < a.nframes; f += ncl) {
         const bool lastframe = f + ncl >= a.nframes;
-        for (int r = 0; r < a.H; r++, T++) {
-            const uint32_t b = T & 1u;
-            const uint32_t ph = ((T - (b ? 1u : 2u)) >> 1) & 1u;      // phase of buffer b's barriers that row T consumes (T >= 1)
-            const bool lastrow = r == a.H - 1;
-            if (tid == 0) {
-                // this CTA's segment of row r + VP_AHEAD (C and S: contiguous [column][d]) is pulled into L2 by the copy engine;
-                // the register prefetch one step ahead then only pays L2 latency
-                int pr = r + VP_AHEAD, pf = f;
-                if (pr >= a.H) { pr -= a.H; pf += ncl; }
-                if (pf < a.nframes) {
-                    const size_t o = ((size_t)pf * a.frame_words) + ((size_t)(a.ystart + pr * a.ystep) * a.W1 + (size_t)((int)rank * XC)) * wordsD;
-                    const uint32_t bytes = (uint32_t)min(XC, a.W1 - (int)rank * XC) * wordsD * 4u;
-                    l2_prefetch_bulk(a.C + o, bytes);
-                    l2_prefetch_bulk(a.S + o, bytes);
-                }
-            }
+        for (int r = 0; r < a.H - 1; r++) {
+            row(std::false_type(), f, r, lastframe);
 #pragma unroll
-            for (int q = 0; q < 2; q++) {
-                // next step's C and S: the other column of this row, or the first column of the next row / next frame
-                uint4 cn = z, sn = z;
-                if (q == 0) {
-                    if (inq[1]) { cn = __ldg(Cq + off[1]); sn = Sq[off[1]]; }
-                } else {
-                    const bool more = !lastrow || !lastframe;
-                    const size_t o = lastrow ? base0[0] + (size_t)(f + ncl) * frameq : (size_t)((long long)off[0] + rowq);
-                    if (more && inq[0]) { cn = __ldg(Cq + o); sn = Sq[o]; }
-                }
-                const int col = colq[q];
-                const bool half0 = (q ^ h0) == 0;
-                if (T > 0u && !broken && (half0 ? bndL : bndR)) {
-                    const uint32_t bar = sbase + OFF_BAR + 8u * ((half0 ? 0u : 2u) + b);
-                    int spin = 0;
-                    while (!mbar_try_cta(bar, ph)) if (++spin > (1 << 18)) { broken = true; break; }
-                    // armed again for the row after next (the neighbour's next send into this buffer)
-                    if (sl == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(TXB) : "memory");
-                }
-                const uint4 pL = exL[(b * NP + col) * WQ + sl];
-                const uint4 pR = exR[(b * NP + col + 2) * WQ + sl];
-                const uint32_t pmL = mnL[b * NP + col], pmR = mnR[b * NP + col + 2];
-                uint32_t t0[4], t1[4], t2[4], m0, m1, m2;
-                path_core<LPC>(pL, pmL, c, sl, P1x2, P2, t0, m0);
-                path_core<LPC>(Lv[q], minV[q], c, sl, P1x2, P2, t1, m1);
-                path_core<LPC>(pR, pmR, c, sl, P1x2, P2, t2, m2);
-                uint32_t mL = group_min_u32<LPC>(m0, grp);
-                minV[q] = group_min_u32<LPC>(m1, grp);
-                uint32_t mR = group_min_u32<LPC>(m2, grp);
-                uint4 tL = make_uint4(t0[0], t0[1], t0[2], t0[3]);
-                Lv[q] = make_uint4(t1[0], t1[1], t1[2], t1[3]);
-                uint4 tR = make_uint4(t2[0], t2[1], t2[2], t2[3]);
-                if (inq[q]) {
-                    const uint32_t sv[4] = {s.x, s.y, s.z, s.w};
-                    uint32_t o[4];
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        if (SAFE3) o[k] = min2(sv[k] + t0[k] + t1[k] + t2[k], 0x7FFF7FFFu);       // no 16-bit overflow possible
-                        else o[k] = min2(__vadd2(min2(__vadd2(min2(__vadd2(sv[k], t0[k]), 0x7FFF7FFFu), t1[k]), 0x7FFF7FFFu), t2[k]), 0x7FFF7FFFu);
-                    }
-                    Sq[off[q]] = make_uint4(o[0], o[1], o[2], o[3]);
-                }
-                if (lastrow) { tL = z; tR = z; Lv[q] = z; mL = 0u; mR = 0u; minV[q] = 0u; }     // the next frame's paths enter the image
-                if (inq[q]) {
-                    exL[((b ^ 1u) * NP + col + 1) * WQ + sl] = tL;
-                    exR[((b ^ 1u) * NP + col + 1) * WQ + sl] = tR;
-                    if (sl == 0) { mnL[(b ^ 1u) * NP + col + 1] = mL; mnR[(b ^ 1u) * NP + col + 1] = mR; }
-                }
-                if (!(lastframe && lastrow)) {
-                    if (!half0 && bndR) {            // column XC - 1: its rightward diagonal is the right neighbour's left pad (slot 0)
-                        const uint32_t bar = remR + OFF_BAR + 8u * (b ^ 1u);
-                        st_async_v4(remR + ((b ^ 1u) * NP * WQ + sl) * 16u, tL, bar);
-                        if (sl == 0) st_async_b32(remR + OFF_MNL + ((b ^ 1u) * NP) * 4u, mL, bar);
-                    }
-                    if (half0 && bndL) {             // column 0: its leftward diagonal is the left neighbour's right pad (slot XC + 1)
-                        const uint32_t bar = remL + OFF_BAR + 8u * (2u + (b ^ 1u));
-                        st_async_v4(remL + OFF_EXR + (((b ^ 1u) * NP + XC + 1) * WQ + sl) * 16u, tR, bar);
-                        if (sl == 0) st_async_b32(remL + OFF_MNR + ((b ^ 1u) * NP + XC + 1) * 4u, mR, bar);
-                    }
-                }
-                c = cn; s = sn;
-            }
-            off[0] = (size_t)((long long)off[0] + rowq); off[1] = (size_t)((long long)off[1] + rowq);
-            __syncthreads();
+            for (int q = 0; q < NQ; q++) off[q] += rowq;
         }
-        off[0] = base0[0] + (size_t)(f + ncl) * frameq; off[1] = base0[1] + (size_t)(f + ncl) * frameq;
+        row(std::true_type(), f, a.H - 1, lastframe);
+#pragma unroll
+        for (int q = 0; q < NQ; q++) off[q] += framestep;
     }
     cluster_sync_all();
 }
@@ -1222,32 +1271,32 @@ int sgbm_sweep_ctas_per_frame(const SgbmGeom &g)
 namespace {
 struct VPassPlan { int ncta, nclusters; size_t smem; };
 
-template <int LPC, bool SAFE3>
+template <int LPC, int NT, int NQ, bool SAFE3>
 int vpass_config(int ncta, size_t smem, int *nclusters)
 {
-    RTDM_CUDA(cudaFuncSetAttribute(sgbm_vpass_kernel<LPC, SAFE3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (ncta > 8) RTDM_CUDA(cudaFuncSetAttribute(sgbm_vpass_kernel<LPC, SAFE3>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    RTDM_CUDA(cudaFuncSetAttribute(sgbm_vpass_kernel<LPC, NT, NQ, SAFE3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (ncta > 8) RTDM_CUDA(cudaFuncSetAttribute(sgbm_vpass_kernel<LPC, NT, NQ, SAFE3>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = (unsigned)ncta; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.gridDim = dim3((unsigned)ncta); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = smem; cfg.attrs = at; cfg.numAttrs = 1;
+    cfg.gridDim = dim3((unsigned)ncta); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = smem; cfg.attrs = at; cfg.numAttrs = 1;
     int ncl = 0;
-    if (cudaOccupancyMaxActiveClusters(&ncl, sgbm_vpass_kernel<LPC, SAFE3>, &cfg) != cudaSuccess) { cudaGetLastError(); ncl = 0; }
+    if (cudaOccupancyMaxActiveClusters(&ncl, sgbm_vpass_kernel<LPC, NT, NQ, SAFE3>, &cfg) != cudaSuccess) { cudaGetLastError(); ncl = 0; }
     *nclusters = ncl;
     return 0;
 }
 
-template <int LPC, bool SAFE3>
+template <int LPC, int NT, int NQ, bool SAFE3>
 int vpass_launch(const VPassArgs &a, int nclusters, size_t smem, cudaStream_t st)
 {
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = (unsigned)a.ncta; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.gridDim = dim3((unsigned)(a.ncta * nclusters)); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cfg.gridDim = dim3((unsigned)(a.ncta * nclusters)); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cfg.attrs = at; cfg.numAttrs = 1;
-    RTDM_CUDA(cudaLaunchKernelEx(&cfg, sgbm_vpass_kernel<LPC, SAFE3>, a));
+    RTDM_CUDA(cudaLaunchKernelEx(&cfg, sgbm_vpass_kernel<LPC, NT, NQ, SAFE3>, a));
     return 0;
 }
 
@@ -1261,14 +1310,16 @@ int vpass_plan(const SgbmGeom &g, VPassPlan *p)
 {
     p->ncta = 0; p->nclusters = 0; p->smem = 0;
     if (!(g.D == 64 || g.D == 128) || g.W1 <= 0 || g.sw.sgbm_oldpath || g.sw.sgbm_nosweep || g.sw.sgbm_novpass) return 0;
-    const int LPC = g.D / 8, NS = 1024 / LPC, XC = 2 * NS, NP = XC + 2;
+    const int LPC = g.D / 8, XC = 2 * 1024 / LPC, NP = XC + 2;                      // 1024 x 2 and 512 x 4: the same columns per CTA
     const int ncta = cdiv(g.W1, XC);
     if (ncta > 16) return 0;
-    const size_t smem = (size_t)2 * 2 * NP * LPC * 16 + (size_t)2 * 2 * NP * 4 + 32;
-    const bool safe3 = sgbm_safe3(g);
+    const size_t smem = (size_t)2 * 2 * NP * LPC * 16 + (size_t)2 * 2 * NP * 4 + 32;       // exchange, minima, 4 mbarriers
+    const bool safe3 = sgbm_safe3(g), wide = g.sw.sgbm_vpass_shape != 1;
     int ncl = 0, rc;
-    if (g.D == 128) rc = safe3 ? vpass_config<16, true>(ncta, smem, &ncl) : vpass_config<16, false>(ncta, smem, &ncl);
-    else rc = safe3 ? vpass_config<8, true>(ncta, smem, &ncl) : vpass_config<8, false>(ncta, smem, &ncl);
+#define RTDM_VP(LPC_, SAFE_) (wide ? vpass_config<LPC_, 1024, 2, SAFE_>(ncta, smem, &ncl) : vpass_config<LPC_, 512, 4, SAFE_>(ncta, smem, &ncl))
+    if (g.D == 128) rc = safe3 ? RTDM_VP(16, true) : RTDM_VP(16, false);
+    else rc = safe3 ? RTDM_VP(8, true) : RTDM_VP(8, false);
+#undef RTDM_VP
     if (rc) return rc;
     if (ncl < 1) return 0;
     if (g.sw.sgbm_vpass_maxcl > 0) ncl = std::min(ncl, g.sw.sgbm_vpass_maxcl);
@@ -1384,17 +1435,20 @@ int launch_sgbm(const SgbmGeom &g, int n, PlaneU8 left, PlaneU8 right, PlaneS16 
     if (fast && n >= 2) {
         const int rc = vpass_plan(g, &vp);
         if (rc) return rc;
-        if (!vpass_wanted(g, vp, n)) vp.nclusters = 0;
+        if (!vpass_wanted(g, vp, n) || (unsigned long long)n * (w.frame_vol / 8) >= (1ull << 32)) vp.nclusters = 0;   // 32-bit uint4 offsets
     }
     auto launch_vpass = [&](int dy) -> int {
         VPassArgs a;
         a.C = reinterpret_cast<const uint32_t *>(w.C); a.S = reinterpret_cast<uint32_t *>(w.S); a.frame_words = frame_words;
         a.W1 = g.W1; a.H = g.H; a.P1 = g.P1; a.P2 = g.P2;
-        a.ystart = dy > 0 ? 0 : g.H - 1; a.ystep = dy; a.nframes = n; a.ncta = vp.ncta;
+        a.ystart = dy > 0 ? 0 : g.H - 1; a.ystep = dy; a.nframes = n; a.ncta = vp.ncta; a.one = 1u;
         const int ncl = std::min(vp.nclusters, n);
+        const bool wide = g.sw.sgbm_vpass_shape != 1;
         int rc;
-        if (g.D == 128) rc = safe3 ? vpass_launch<16, true>(a, ncl, vp.smem, st) : vpass_launch<16, false>(a, ncl, vp.smem, st);
-        else rc = safe3 ? vpass_launch<8, true>(a, ncl, vp.smem, st) : vpass_launch<8, false>(a, ncl, vp.smem, st);
+#define RTDM_VP(LPC_, SAFE_) (wide ? vpass_launch<LPC_, 1024, 2, SAFE_>(a, ncl, vp.smem, st) : vpass_launch<LPC_, 512, 4, SAFE_>(a, ncl, vp.smem, st))
+        if (g.D == 128) rc = safe3 ? RTDM_VP(16, true) : RTDM_VP(16, false);
+        else rc = safe3 ? RTDM_VP(8, true) : RTDM_VP(8, false);
+#undef RTDM_VP
         if (launches) (*launches)++;
         return rc;
     };
