@@ -444,6 +444,7 @@ struct PathArgs {
     int nchains;
     uint2 *rec; size_t frame_rec;    // fused last path: per-pixel WTA records
     int mul;                         // 100 - uniquenessRatio
+    uint32_t one;                    // 1: a multiplier the compiler cannot fold (see vcore)
 };
 
 __device__ __forceinline__ uint32_t min2(uint32_t a, uint32_t b) { return __vminu2(a, b); }
@@ -601,13 +602,14 @@ __device__ __forceinline__ uint2 wta_record(const uint32_t (&sv)[4], int sl, int
 
 template <int LPC, int MODE>
 __device__ __forceinline__ void path_step(uint4 &Lp, uint32_t &minLp, const uint4 c, const uint4 s, uint4 *sp, uint2 *rp,
-                                          bool live, int sl, int grp, uint32_t P1x2, uint32_t P2, int mul)
+                                          bool live, int sl, int grp, uint32_t P1x2, uint32_t P2, int mul, uint32_t one)
 {
     uint32_t left = __shfl_up_sync(0xFFFFFFFFu, Lp.w, 1, LPC);
     uint32_t right = __shfl_down_sync(0xFFFFFFFFu, Lp.x, 1, LPC);
     if (sl == 0) left = 0x7FFF0000u;                       // L[-1] = MAX_COST (upper half is used)
     if (sl == LPC - 1) right = 0x00007FFFu;                // L[D]  = MAX_COST (lower half is used)
-    const uint32_t dx2 = (P2 + minLp) * 0x00010001u;       // P2 + min_k L_r(p - r, k) < 65536
+    // as in vcore: minLp is the chain's minimum splatted into both halves, the plain 32-bit arithmetic is multiply-add by `one`
+    const uint32_t dx2 = P2 + minLp, ndx2 = 0u - dx2;      // P2 + min_k L_r(p - r, k) < 65536
     const uint32_t w[6] = {left, Lp.x, Lp.y, Lp.z, Lp.w, right};
     const uint32_t cc[4] = {c.x, c.y, c.z, c.w};
     uint32_t t[4];
@@ -616,14 +618,16 @@ __device__ __forceinline__ void path_step(uint4 &Lp, uint32_t &minLp, const uint
         const uint32_t lm1 = __byte_perm(w[k], w[k + 1], 0x5432);      // (L[d-1], L[d])   for the pair (d, d+1)
         const uint32_t lp1 = __byte_perm(w[k + 1], w[k + 2], 0x5432);  // (L[d+1], L[d+2])
         const uint32_t v = __vimin3_u16x2(w[k + 1], __vadd2(min2(lm1, lp1), P1x2), dx2);   // min(a + P1, b + P1) = min(a, b) + P1
-        t[k] = __vsub2(__vadd2(v, cc[k]), dx2);
+        t[k] = (v * one + cc[k]) * one + ndx2;
     }
-    const uint32_t m = min2(min2(t[0], t[1]), min2(t[2], t[3]));
+    const uint32_t mm = min2(min2(t[0], t[1]), min2(t[2], t[3]));
+    const uint32_t m = min2(mm, __byte_perm(mm, mm, 0x1032));
     if (MODE == 0) {
         if (live) *sp = make_uint4(t[0], t[1], t[2], t[3]);
     } else {
-        const uint32_t sv[4] = {min2(__vadd2(s.x, t[0]), 0x7FFF7FFFu), min2(__vadd2(s.y, t[1]), 0x7FFF7FFFu),
-                                min2(__vadd2(s.z, t[2]), 0x7FFF7FFFu), min2(__vadd2(s.w, t[3]), 0x7FFF7FFFu)};
+        // S <= 32767 and L < 32768 per half: the sum cannot carry into the other half
+        const uint32_t sv[4] = {min2(t[0] * one + s.x, 0x7FFF7FFFu), min2(t[1] * one + s.y, 0x7FFF7FFFu),
+                                min2(t[2] * one + s.z, 0x7FFF7FFFu), min2(t[3] * one + s.w, 0x7FFF7FFFu)};
         if (MODE == 1) {
             if (live) *sp = make_uint4(sv[0], sv[1], sv[2], sv[3]);
         } else {
@@ -632,7 +636,7 @@ __device__ __forceinline__ void path_step(uint4 &Lp, uint32_t &minLp, const uint
         }
     }
     Lp = make_uint4(t[0], t[1], t[2], t[3]);
-    minLp = group_min_u32<LPC>(min(m & 0xFFFFu, m >> 16), grp);
+    minLp = group_min_u32<LPC>(m, grp);
 }
 
 template <int LPC, int MODE>
@@ -659,7 +663,7 @@ sgbm_path4_kernel(PathArgs a)
         len = min(nx, ny);
     }
     const int maxlen = __reduce_max_sync(0xFFFFFFFFu, len);
-    const uint32_t P1x2 = (uint32_t)a.P1 * 0x00010001u, P2 = (uint32_t)a.P2;
+    const uint32_t P1x2 = (uint32_t)a.P1 * 0x00010001u, P2 = (uint32_t)a.P2 * 0x00010001u;
     const int wordsD = 8 * LPC / 2;
     const long long stepp = (long long)sy * a.W1 + sx;                        // pixels
     const long long stepq = stepp * (wordsD / 4);                             // uint4 units
@@ -676,11 +680,11 @@ sgbm_path4_kernel(PathArgs a)
         const bool m1 = i + 1 < len;
         c1 = m1 ? __ldg(cp + stepq) : z;
         s1 = (MODE != 0 && m1) ? sp[stepq] : z;
-        path_step<LPC, MODE>(Lp, minLp, c0, s0, sp, rp, i < len, sl, grp, P1x2, P2, a.mul);
+        path_step<LPC, MODE>(Lp, minLp, c0, s0, sp, rp, i < len, sl, grp, P1x2, P2, a.mul, a.one);
         const bool m2 = i + 2 < len;
         c0 = m2 ? __ldg(cp + 2 * stepq) : z;
         s0 = (MODE != 0 && m2) ? sp[2 * stepq] : z;
-        path_step<LPC, MODE>(Lp, minLp, c1, s1, sp + stepq, rp + stepp, m1, sl, grp, P1x2, P2, a.mul);
+        path_step<LPC, MODE>(Lp, minLp, c1, s1, sp + stepq, rp + stepp, m1, sl, grp, P1x2, P2, a.mul, a.one);
         cp += 2 * stepq; sp += 2 * stepq;
         if (MODE == 2) rp += 2 * stepp;
     }
@@ -706,27 +710,35 @@ struct SweepArgs {
     int W1, H, P1, P2;
     int ystart, ystep, nrows;                // rows of this tile: ystart, ystart + ystep, ...
     int first;                               // first tile of the sweep: predecessors are outside the image
+    uint32_t one;                            // 1: a multiplier the compiler cannot fold (see vcore)
 };
 
+// One step of one path for a lane's 8 disparities (row sweeps and whole-height passes).  `minLp` and the returned `m` are the minimum over d
+// SPLATTED into both halves, so the 32-bit minimum over a column's lanes is the splatted column minimum and P2 + min is one
+// add.  The packed 16-bit minima / add-minima only issue on the ALU pipe (64 lanes per clock and SM), which is what bounds
+// the pass, so the plain 32-bit arithmetic is written as multiply-add with `one`, a run-time 1 the compiler cannot see
+// through and therefore keeps as IMAD -- the other integer pipe.  v + C - (P2 + min): every 16-bit half of the result is a
+// path cost (0 <= L < 65536, v >= min), so no carry or borrow crosses the halves and 32-bit arithmetic is exact.
 template <int LPC>
-__device__ __forceinline__ void path_core(const uint4 Lp, const uint32_t minLp, const uint4 c, int sl, uint32_t P1x2, uint32_t P2, uint32_t (&t)[4], uint32_t &m)
+__device__ __forceinline__ void vcore(const uint4 Lp, const uint32_t minLp, const uint4 c, int sl, uint32_t one, uint32_t P1x2, uint32_t P2x2,
+                                      uint32_t (&t)[4], uint32_t &m)
 {
     uint32_t left = __shfl_up_sync(0xFFFFFFFFu, Lp.w, 1, LPC);
     uint32_t right = __shfl_down_sync(0xFFFFFFFFu, Lp.x, 1, LPC);
-    if (sl == 0) left = 0x7FFF0000u;
-    if (sl == LPC - 1) right = 0x00007FFFu;
-    const uint32_t dx2 = (P2 + minLp) * 0x00010001u;
+    if (sl == 0) left = 0x7FFF0000u;                       // L[-1] = MAX_COST (upper half is used)
+    if (sl == LPC - 1) right = 0x00007FFFu;                // L[D]  = MAX_COST (lower half is used)
+    const uint32_t dx2 = P2x2 + minLp, ndx2 = 0u - dx2;
     const uint32_t w[6] = {left, Lp.x, Lp.y, Lp.z, Lp.w, right};
     const uint32_t cc[4] = {c.x, c.y, c.z, c.w};
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const uint32_t lm1 = __byte_perm(w[k], w[k + 1], 0x5432);
-        const uint32_t lp1 = __byte_perm(w[k + 1], w[k + 2], 0x5432);
-        const uint32_t v = __vimin3_u16x2(w[k + 1], __vadd2(min2(lm1, lp1), P1x2), dx2);   // min(a + P1, b + P1) = min(a, b) + P1
-        t[k] = __vsub2(__vadd2(v, cc[k]), dx2);
+    for (int i = 0; i < 4; i++) {
+        const uint32_t lm1 = __byte_perm(w[i], w[i + 1], 0x5432);      // (L[d-1], L[d])   for the pair (d, d+1)
+        const uint32_t lp1 = __byte_perm(w[i + 1], w[i + 2], 0x5432);  // (L[d+1], L[d+2])
+        const uint32_t v = __vimin3_u16x2(w[i + 1], __vadd2(min2(lm1, lp1), P1x2), dx2);   // min(a + P1, b + P1) = min(a, b) + P1
+        t[i] = (v * one + cc[i]) * one + ndx2;
     }
     const uint32_t mm = min2(min2(t[0], t[1]), min2(t[2], t[3]));
-    m = min(mm & 0xFFFFu, mm >> 16);
+    m = min2(mm, __byte_perm(mm, mm, 0x1032));
 }
 
 template <int LPC, bool SAFE3>
@@ -761,7 +773,7 @@ sgbm_sweep_kernel(SweepArgs a)
         minV = M[a.W1];
         if (sl == 0) { mnL[j + 1] = M[0]; mnR[j + 1] = M[2 * a.W1]; }
     }
-    const uint32_t P1x2 = (uint32_t)a.P1 * 0x00010001u, P2 = (uint32_t)a.P2;
+    const uint32_t P1x2 = (uint32_t)a.P1 * 0x00010001u, P2 = (uint32_t)a.P2 * 0x00010001u;
     const long long rowq = (long long)a.ystep * a.W1 * (wordsD / 4);  // uint4 units per row step
     const size_t off = (((size_t)f * a.frame_words) + ((size_t)a.ystart * a.W1 + (inimg ? x : 0)) * wordsD) / 4 + sl;
     const uint4 *cp = reinterpret_cast<const uint4 *>(a.C) + off;
@@ -780,9 +792,9 @@ sgbm_sweep_kernel(SweepArgs a)
         const uint4 pR = exR[(b * (NS + 2) + j + 2) * WQ + sl];       // path from (x+1, previous row): slot j+1
         const uint32_t pmL = mnL[b * (NS + 2) + j], pmR = mnR[b * (NS + 2) + j + 2];
         uint32_t t0[4], t1[4], t2[4], m0, m1, m2;
-        path_core<LPC>(pL, pmL, c, sl, P1x2, P2, t0, m0);
-        path_core<LPC>(Lv, minV, c, sl, P1x2, P2, t1, m1);
-        path_core<LPC>(pR, pmR, c, sl, P1x2, P2, t2, m2);
+        vcore<LPC>(pL, pmL, c, sl, a.one, P1x2, P2, t0, m0);
+        vcore<LPC>(Lv, minV, c, sl, a.one, P1x2, P2, t1, m1);
+        vcore<LPC>(pR, pmR, c, sl, a.one, P1x2, P2, t2, m2);
         mL = group_min_u32<LPC>(m0, grp);
         minV = group_min_u32<LPC>(m1, grp);
         mR = group_min_u32<LPC>(m2, grp);
@@ -863,34 +875,6 @@ __device__ __forceinline__ void l2_prefetch_bulk(const void *p, uint32_t bytes) 
 __device__ __forceinline__ void cluster_sync_all() { asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
 constexpr int VP_AHEAD = 3;                  // rows between the L2 prefetch and their use
-
-// One step of one path for a lane's 8 disparities in the pass kernel.  `minLp` and the returned `m` are the minimum over d
-// SPLATTED into both halves, so the 32-bit minimum over a column's lanes is the splatted column minimum and P2 + min is one
-// add.  The packed 16-bit minima / add-minima only issue on the ALU pipe (64 lanes per clock and SM), which is what bounds
-// the pass, so the plain 32-bit arithmetic is written as multiply-add with `one`, a run-time 1 the compiler cannot see
-// through and therefore keeps as IMAD -- the other integer pipe.  v + C - (P2 + min): every 16-bit half of the result is a
-// path cost (0 <= L < 65536, v >= min), so no carry or borrow crosses the halves and 32-bit arithmetic is exact.
-template <int LPC>
-__device__ __forceinline__ void vcore(const uint4 Lp, const uint32_t minLp, const uint4 c, int sl, uint32_t one, uint32_t P1x2, uint32_t P2x2,
-                                      uint32_t (&t)[4], uint32_t &m)
-{
-    uint32_t left = __shfl_up_sync(0xFFFFFFFFu, Lp.w, 1, LPC);
-    uint32_t right = __shfl_down_sync(0xFFFFFFFFu, Lp.x, 1, LPC);
-    if (sl == 0) left = 0x7FFF0000u;                       // L[-1] = MAX_COST (upper half is used)
-    if (sl == LPC - 1) right = 0x00007FFFu;                // L[D]  = MAX_COST (lower half is used)
-    const uint32_t dx2 = P2x2 + minLp, ndx2 = 0u - dx2;
-    const uint32_t w[6] = {left, Lp.x, Lp.y, Lp.z, Lp.w, right};
-    const uint32_t cc[4] = {c.x, c.y, c.z, c.w};
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const uint32_t lm1 = __byte_perm(w[i], w[i + 1], 0x5432);      // (L[d-1], L[d])   for the pair (d, d+1)
-        const uint32_t lp1 = __byte_perm(w[i + 1], w[i + 2], 0x5432);  // (L[d+1], L[d+2])
-        const uint32_t v = __vimin3_u16x2(w[i + 1], __vadd2(min2(lm1, lp1), P1x2), dx2);   // min(a + P1, b + P1) = min(a, b) + P1
-        t[i] = (v * one + cc[i]) * one + ndx2;
-    }
-    const uint32_t mm = min2(min2(t[0], t[1]), min2(t[2], t[3]));
-    m = min2(mm, __byte_perm(mm, mm, 0x1032));
-}
 
 // NT threads per CTA, a thread owns NQ columns NS = NT / LPC apart ("quarters"; XC = NQ * NS columns per CTA).  1024 x 2 is the
 // default; 512 x 4 (RTDM_SGBM_VPASS_SHAPE=1: 128 registers per thread, nothing recomputed) has too few warps to hide the
@@ -1310,6 +1294,7 @@ int vpass_plan(const SgbmGeom &g, VPassPlan *p)
 {
     p->ncta = 0; p->nclusters = 0; p->smem = 0;
     if (!(g.D == 64 || g.D == 128) || g.W1 <= 0 || g.sw.sgbm_oldpath || g.sw.sgbm_nosweep || g.sw.sgbm_novpass) return 0;
+    if (g.P2 + g.bs * g.bs * (2 * g.ftzero + 63) >= 32768) return 0;               // see `fast` in launch_sgbm
     const int LPC = g.D / 8, XC = 2 * 1024 / LPC, NP = XC + 2;                      // 1024 x 2 and 512 x 4: the same columns per CTA
     const int ncta = cdiv(g.W1, XC);
     if (ncta > 16) return 0;
@@ -1421,7 +1406,9 @@ int launch_sgbm(const SgbmGeom &g, int n, PlaneU8 left, PlaneU8 right, PlaneS16 
     const bool hh = g.mode == RTDM_SGBM_MODE_HH;
     const int ndirs = hh ? 8 : 5;
     const int K2 = g.D <= 64 ? 1 : (g.D <= 128 ? 2 : 4);   // u16x2 words per lane (divides D/2 for any D % 16 == 0)
-    const bool fast = (g.D == 128 || g.D == 64) && !g.sw.sgbm_oldpath;
+    // the 4-word kernels add S and L as whole words: needs L <= C <= P2 + bs^2 * (2 * ftzero + 63) < 32768 next to S <= 32767
+    // (any sane setting; the defaults give 4725), otherwise the generic chain kernel runs
+    const bool fast = (g.D == 128 || g.D == 64) && !g.sw.sgbm_oldpath && g.P2 + g.bs * g.bs * (2 * g.ftzero + 63) < 32768;
     const bool fused = fast && g.uniq < 100 && !g.sw.sgbm_nofuse;
     const size_t frame_rec = w.frame_planes / 8;            // the BT planes are dead by now: their buffer takes the records
     // the two vertical triplets as row sweeps (one C read and one S update for three paths)
@@ -1468,7 +1455,7 @@ int launch_sgbm(const SgbmGeom &g, int n, PlaneU8 left, PlaneU8 right, PlaneS16 
             a.frame_front = w.frame_planes / 4;
             a.W1 = g.W1; a.H = g.H; a.P1 = g.P1; a.P2 = g.P2;
             a.ystart = dy > 0 ? t * SW_R : g.H - 1 - t * SW_R; a.ystep = dy; a.nrows = std::min(SW_R, g.H - t * SW_R);
-            a.first = t == 0;
+            a.first = t == 0; a.one = 1u;
             const dim3 grid(cdiv(g.W1, X), n);
 #define RTDM_SWEEP(LPC_, SAFE_)                                                                                              \
             do {                                                                                                             \
@@ -1492,7 +1479,7 @@ int launch_sgbm(const SgbmGeom &g, int n, PlaneU8 left, PlaneU8 right, PlaneS16 
         a.C = reinterpret_cast<const uint32_t *>(w.C); a.S = reinterpret_cast<uint32_t *>(w.S); a.frame_words = frame_words;
         a.W1 = g.W1; a.H = g.H; a.D = g.D; a.P1 = g.P1; a.P2 = g.P2; a.px = dirs[di][0]; a.py = dirs[di][1];
         a.first = (k == 0);
-        a.rec = reinterpret_cast<uint2 *>(w.planes); a.frame_rec = frame_rec; a.mul = 100 - g.uniq;
+        a.rec = reinterpret_cast<uint2 *>(w.planes); a.frame_rec = frame_rec; a.mul = 100 - g.uniq; a.one = 1u;
         const int sx = -a.px, sy = -a.py;
         a.nchains = (sy != 0 ? g.W1 : 0) + (sx != 0 ? (sy != 0 ? g.H - 1 : g.H) : 0);
         if (fast) {
