@@ -101,6 +101,42 @@ private:
     rtdm_bm *h_ = nullptr;
 };
 
+// One large frame as row bands over several GPUs of this process (rtdm_bm_rowband_*: every device gets its own input
+// rows + halo, the int16 bands come back to devices[0] as peer copies, the speckle filter runs there).  Same constructor
+// arguments as SWMatcherKonolige plus the device list; bit-exact against CUDAMatcherKonolige.  minDisparity <= 0.
+class CUDARowBandMatcherKonolige : public BlockMatcher {
+public:
+    CUDARowBandMatcherKonolige(cv::Rect &roi1, cv::Rect &roi2, int preFilterCap, int blockSize, int minDisparity,
+                               int textureThreshold, int numOfDisparities, int maxDisparity, int uniquenessRatio,
+                               int speckleWindowSize, int speckleRange, int disp12MaxDiff,
+                               int n_gpus, const int *devices, int max_width = 1280, int max_height = 720)
+    {
+        (void)roi1; (void)roi2; (void)maxDisparity;
+        rtdm_params p;
+        rtdm_params_default_bm(&p);
+        p.preFilterCap = preFilterCap; p.blockSize = blockSize; p.minDisparity = minDisparity;
+        p.textureThreshold = textureThreshold; p.numDisparities = numOfDisparities;
+        p.uniquenessRatio = uniquenessRatio; p.speckleWindowSize = speckleWindowSize;
+        p.speckleRange = speckleRange; p.disp12MaxDiff = disp12MaxDiff;
+        int rc = rtdm_bm_rowband_create(&h_, &p, max_width, max_height, n_gpus, devices);
+        if (rc) rtdm_detail::fail("CUDARowBandMatcherKonolige", rc);
+    }
+    ~CUDARowBandMatcherKonolige() { rtdm_bm_rowband_destroy(h_); }
+    void setROI1(cv::Rect r) override { rtdm_bm_rowband_set_roi1(h_, r.x, r.y, r.width, r.height); }
+    void setROI2(cv::Rect r) override { rtdm_bm_rowband_set_roi2(h_, r.x, r.y, r.width, r.height); }
+    int compute(cv::InputArray left, cv::InputArray right, cv::OutputArray out) override
+    {
+        const cv::Mat l = left.getMat(), r = right.getMat();
+        out.create(l.rows, l.cols, CV_16SC1);
+        cv::Mat d = out.getMat();
+        int rc = rtdm_bm_rowband_compute(h_, l.data, l.step, r.data, r.step, l.cols, l.rows, (int16_t *)d.data, d.step);
+        if (rc) { std::fprintf(stderr, "CUDARowBandMatcherKonolige::compute: %s\n", rtdm_last_error()); return -1; }
+        return 0;
+    }
+private:
+    rtdm_bm_rowband *h_ = nullptr;
+};
+
 class CUDASemiGlobalMatcher : public BlockMatcher {
 public:
     // same arguments as SWSemiGlobalMatcher (sgbm-sw.h:28-29); P1 = 8*3*5*5, P2 = 32*3*5*5 as in

@@ -51,7 +51,12 @@ int main(int argc, char **argv)
             }
             cv::Mat lv = lf(cv::Rect(8, 0, W, H)), rv = rf(cv::Rect(8, 0, W, H));
             cv::Rect roi;
-            BlockMatcher *bm = new CUDAMatcherKonolige(roi, roi, 31, bs, 0, 10, nd, nd, 10, 100, 32, 1, W, H);
+            // RTDM_TEST_ROWBANDS=k: the same frame as k row bands (all on device 0 here: bands then run one after the other)
+            const char *rbenv = std::getenv("RTDM_TEST_ROWBANDS");
+            const int nb = rbenv ? atoi(rbenv) : 0;
+            const int devs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            BlockMatcher *bm = nb > 1 ? static_cast<BlockMatcher *>(new CUDARowBandMatcherKonolige(roi, roi, 31, bs, 0, 10, nd, nd, 10, 100, 32, 1, nb > 8 ? 8 : nb, devs, W, H))
+                                      : static_cast<BlockMatcher *>(new CUDAMatcherKonolige(roi, roi, 31, bs, 0, 10, nd, nd, 10, 100, 32, 1, W, H));
             if (argc >= 13) bm->setROI1(cv::Rect(atoi(argv[9]), atoi(argv[10]), atoi(argv[11]), atoi(argv[12])));
             cv::Mat disp;
             if (bm->compute(lv, rv, disp) != 0) return 4;

@@ -41,6 +41,10 @@ def test_adapters_match_oracle(exe, gpu, orc, tmp_path):
     got = np.fromfile(op, np.int16).reshape(H, W)
     ref = orc.bm_compute(L, R, orc.make_params(blockSize=bs, numDisparities=nd, roi1=roi))
     assert np.array_equal(got, ref)
+    # the row-band peer (rtdm_bm_rowband_*): three bands of the same frame
+    subprocess.check_call([exe, "bm", str(W), str(H), str(nd), str(bs), lp, rp, op] + [str(v) for v in roi],
+                          env=dict(os.environ, RTDM_TEST_ROWBANDS="3"))
+    assert np.array_equal(np.fromfile(op, np.int16).reshape(H, W), ref)
     for mode in (0, 1):
         subprocess.check_call([exe, "sgbm", str(W), str(H), str(nd), "5", lp, rp, op, str(mode)])
         got = np.fromfile(op, np.int16).reshape(H, W)
