@@ -956,7 +956,7 @@ sgbm_vpass_kernel(VPassArgs a)
             // this CTA's segment of row r + VP_AHEAD (C and S: contiguous [column][d]) is pulled into L2 by the copy engine;
             // the register prefetch one step ahead then only pays L2 latency
             int pr = r + VP_AHEAD, pf = f;
-            if (pr >= a.H) { pr -= a.H; pf += ncl; }
+            while (pr >= a.H) { pr -= a.H; pf += ncl; }                   // (frames of fewer than VP_AHEAD rows)
             if (pf < a.nframes) {
                 const size_t o = ((size_t)pf * a.frame_words) + ((size_t)(a.ystart + pr * a.ystep) * a.W1 + (size_t)((int)rank * XC)) * wordsD;
                 const uint32_t bytes = (uint32_t)min(XC, a.W1 - (int)rank * XC) * wordsD * 4u;

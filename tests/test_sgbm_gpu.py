@@ -147,6 +147,47 @@ def test_sgbm_cluster_pass_matches_oracle(gpu, orc, case, monkeypatch):
     assert checked >= 1
 
 
+def test_sgbm_cluster_pass_equals_tiled_sweeps_on_random_geometries(gpu, monkeypatch):
+    """The two aggregation variants against each other (both are pinned to the oracle elsewhere): random widths (1 .. 5
+    CTAs per cluster, partly filled last CTA), heights from one row up (the first row of a pass needs no neighbour data, the
+    last row hands zeros to the next frame), D = 64 and 128, both modes, batches that give a cluster 1 .. 4 frames."""
+    from rtdm_b200 import synth
+    rng = np.random.default_rng(77)
+    cases = [(300, 1, 128, 5, 1, 3, 2), (300, 2, 128, 5, 1, 3, 1), (200, 3, 64, 3, 0, 5, 2)]
+    for _ in range(9):
+        nd = int(rng.choice([64, 128]))
+        W = nd + int(rng.integers(8, 640)); H = int(rng.integers(4, 70))
+        cases.append((W, H, nd, int(rng.choice([3, 5, 7])), int(rng.integers(0, 2)), int(rng.integers(2, 9)), int(rng.integers(1, 4))))
+    for (W, H, nd, bs, mode, B, maxcl) in cases:
+        fr = [synth.stereo_pair(W, H, nd, 9100 + 3 * i + W + H) for i in range(B)]
+        L = np.stack([f[0] for f in fr]); R = np.stack([f[1] for f in fr])
+        outs = []
+        for novpass in (False, True):
+            for v in ("RTDM_SGBM_NOVPASS", "RTDM_SGBM_VPASS_MIN", "RTDM_SGBM_VPASS_MAXCL"):
+                monkeypatch.delenv(v, raising=False)
+            if novpass:
+                monkeypatch.setenv("RTDM_SGBM_NOVPASS", "1")
+            else:
+                monkeypatch.setenv("RTDM_SGBM_VPASS_MIN", "2"); monkeypatch.setenv("RTDM_SGBM_VPASS_MAXCL", str(maxcl))
+            m = gpu.CUDASemiGlobalMatcher(bs, 0, nd, 10, 60, 4, 1, mode=mode, max_width=W, max_height=H, max_batch=B)
+            outs.append(m.compute_batch(L, R).copy())
+            if not novpass:
+                assert m.last_launches() <= 12, (W, H, nd, bs, mode, B, maxcl, m.last_launches())     # one launch per pass, no tiles
+        assert np.array_equal(outs[0], outs[1]), (W, H, nd, bs, mode, B, maxcl, int((outs[0] != outs[1]).sum()))
+
+
+def test_sgbm_batch_quantum(gpu):
+    """rtdm_sgbm_batch_quantum: the clusters in flight for sizes that take the whole-height pass (one frame each), 1 otherwise."""
+    m = gpu.CUDASemiGlobalMatcher(5, 0, 128, 10, 100, 32, 1, mode=1, max_width=1280, max_height=720, max_batch=45)
+    q = m.batch_quantum(1280, 720)
+    assert 1 <= q <= 148 // 9 + 1
+    assert m.batch_quantum(320, 240) >= q                      # fewer CTAs per cluster: at least as many clusters
+    m96 = gpu.CUDASemiGlobalMatcher(5, 0, 96, 10, 100, 32, 1, max_width=640, max_height=480, max_batch=4)
+    assert m96.batch_quantum(640, 480) == 1                    # D = 96: tiled / chain kernels
+    with pytest.raises(gpu.RtdmError):
+        m.batch_quantum(4000, 720)
+
+
 def test_sgbm_large_penalties_take_the_stepwise_clamp(gpu, orc):
     """P2 large enough that three path costs next to S could overflow 16 bits (2*P2 + bs^2*93 > 10922): the sweep
     kernel then clamps after every addition (cv::StereoSGBM's saturating adds) instead of once.  5-path mode, so
