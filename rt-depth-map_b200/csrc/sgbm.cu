@@ -269,6 +269,14 @@ __device__ __forceinline__ uint32_t bt_cost2(const uint4 l0, const uint4 l1, con
     return m0 + ((m1 >> 2) & 0x3FFF3FFFu);
 }
 
+// the same with the six right-image words already in registers
+__device__ __forceinline__ uint32_t bt_cost2r(const uint4 l0, const uint4 l1, const uint32_t (&r)[6])
+{
+    const uint32_t m0 = bt_plane2(l0, r[0], r[1], r[2]);
+    const uint32_t m1 = bt_plane2(l1, r[3], r[4], r[5]);
+    return m0 + ((m1 >> 2) & 0x3FFF3FFFu);
+}
+
 template <int BS>
 __global__ void __launch_bounds__(256, 2)
 sgbm_cost_fused_kernel(Cost2Args a)
@@ -289,10 +297,12 @@ sgbm_cost_fused_kernel(Cost2Args a)
     const int eg0 = a.W - 1 + PADR - xr_hi;
     const int sA = eg0 + p0, sB = eg0 + 1 - p0;
     const int srcA = sA & 1, srcB = sB & 1;                            // which global copy
-    const int iA = (sA - srcA) & ~7, iB = (sB - srcB) & ~7;            // first global element staged
-    const int dA = sA - srcA - iA, dB = sB - srcB - iB;                // staged index of e = p0 / e = 1 - p0
+    // first global element staged; copy A starts at least two elements below the first pair it serves: interior tiles take
+    // the odd columns' pairs from copy A as well (high half of one word, low half of the next), which reaches one word lower
+    const int iA = (sA - srcA - 2) & ~7, iB = (sB - srcB) & ~7;
+    const int dA = sA - srcA - iA, dB = sB - srcB - iB;                // staged index of e = p0 / e = 1 - p0 (2 <= dA <= 9, dB <= 7)
     const int nelem = (cl1 - clampi(x0 - h, 0, a.W1 - 1)) + a.D + 2;   // elements needed from e = 0
-    const int NRC = (nelem + 7 + 7) / 8;                               // chunks per array copy (dA, dB <= 6)
+    const int NRC = (max(dA, dB) + nelem + 7) / 8;                     // chunks per array copy
     const int NL = NXC * 2;
     const int lbytes = NXC * 32, rbytes = 12 * RSTRIDE * 2, bbytes = lbytes + rbytes;
     const uint8_t *pf = a.planes + (size_t)f * a.frame_planes;
@@ -310,8 +320,10 @@ sgbm_cost_fused_kernel(Cost2Args a)
         else if (t < NL + 12 * NRC) {
             const int r = t - NL, ac = r / NRC, ch = r - ac * NRC, arr = ac >> 1, cpy = ac & 1;
             const int gcopy = cpy ? srcB : srcA, gi = (cpy ? iB : iA) + ch * 8;
-            gsrc[q] = gr + (size_t)((arr * 2 + gcopy) * a.WR + gi) * 2; gstr[q] = (uint32_t)rrow;
-            soff[q] = sbase + lbytes + (ac * RSTRIDE + ch * 8) * 2;
+            if (edge || cpy == 0) {                                    // interior tiles never read copy B
+                gsrc[q] = gr + (size_t)((arr * 2 + gcopy) * a.WR + gi) * 2; gstr[q] = (uint32_t)rrow;
+                soff[q] = sbase + lbytes + (ac * RSTRIDE + ch * 8) * 2;
+            }
         }
     }
     auto stage = [&](int row, int b) {
@@ -330,9 +342,8 @@ sgbm_cost_fused_kernel(Cost2Args a)
         for (int u = 0; u < BS; u++) ring[u][j] = 0u;
     }
     const int nrows = (y1 - y0) + 2 * h;
-    // byte offsets inside a buffer: even c reads A at ta - 2c, odd c reads B at tb - 2(c - 1)
+    // byte offset inside a buffer: even c reads copy A at ta - 2c (edge tiles compute their offsets per column)
     const int ta = lbytes + 2 * (E0 - xs - p0 + dA);
-    const int tb = lbytes + RSTRIDE * 2 + 2 * (E0 - xs - 1 + p0 + dB) - 2;
     const int tl = seg * CSEG * 32;
     uint32_t *cptr = reinterpret_cast<uint32_t *>(a.C + (size_t)f * a.frame_vol) + ((size_t)y0 * a.W1 + x0 + seg * CSEG) * D2 + dp;
     const size_t crow = (size_t)a.W1 * D2;
@@ -350,12 +361,25 @@ sgbm_cost_fused_kernel(Cost2Args a)
                 const uint4 *lp = reinterpret_cast<const uint4 *>(xb + tl);
                 uint32_t hc[BS], hs = 0u;
                 if (!edge) {
+                    // columns in pairs: the even column's six words come from copy A (one word per array, stepping down),
+                    // the odd column's pairs straddle two of those words -- 42 instead of 72 shared-memory loads per row
+                    // (the kernel is bound by shared-memory bandwidth), the byte permutes go to the half-idle ALU pipe
                     const uint32_t *pa = reinterpret_cast<const uint32_t *>(xb + ta);
-                    const uint32_t *pb = reinterpret_cast<const uint32_t *>(xb + tb);
+                    uint32_t cur[6], nxt[6], odd[6];
+#pragma unroll
+                    for (int q = 0; q < 6; q++) cur[q] = pa[q * RSTRIDE];
 #pragma unroll
                     for (int c = 0; c < NC; c++) {
-                        const uint32_t *rw = (c & 1) ? pb - (c - 1) / 2 : pa - c / 2;
-                        const uint32_t cost = bt_cost2(lp[c * 2], lp[c * 2 + 1], rw);
+                        uint32_t cost;
+                        if ((c & 1) == 0) {
+#pragma unroll
+                            for (int q = 0; q < 6; q++) nxt[q] = pa[q * RSTRIDE - (c / 2 + 1)];
+                            cost = bt_cost2r(lp[c * 2], lp[c * 2 + 1], cur);
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 6; q++) { odd[q] = __byte_perm(nxt[q], cur[q], 0x5432); cur[q] = nxt[q]; }
+                            cost = bt_cost2r(lp[c * 2], lp[c * 2 + 1], odd);
+                        }
                         if (c >= BS) hs -= hc[c % BS];
                         hs += cost;
                         hc[c % BS] = cost;
