@@ -188,6 +188,27 @@ def test_sgbm_batch_quantum(gpu):
         m.batch_quantum(4000, 720)
 
 
+@pytest.mark.parametrize("case", [(560, 70, 256, 5, 0), (700, 48, 256, 3, 1), (430, 64, 256, 7, 0), (300, 90, 192, 5, 1)])
+def test_sgbm_wide_disparity_ranges_match_oracle(gpu, orc, case):
+    """numDisparities 256 (fused cost kernel with two 8-column segments per CTA, generic chain kernel for the paths) and 192
+    (the reference's default -nd at 1280 pixels: no fused kernel applies) on a batch of 3."""
+    from rtdm_b200 import synth
+    W, H, nd, bs, mode = case
+    p = dict(blockSize=bs, minDisparity=0, numDisparities=nd, uniquenessRatio=10, speckleWindowSize=60, speckleRange=4,
+             disp12MaxDiff=1, mode=mode)
+    fr = [synth.stereo_pair(W, H, nd, 7700 + i + W) for i in range(3)]
+    L = np.stack([f[0] for f in fr]); R = np.stack([f[1] for f in fr])
+    out = _mk(gpu, p, W, H, max_batch=3).compute_batch(L, R)
+    checked = 0
+    for i in range(3):
+        ref, outside = orc.sgbm_compute(L[i], R[i], orc.sgbm_params(**p), return_domain_flag=True)
+        if outside:
+            continue
+        assert np.array_equal(out[i], ref), (case, i, int((out[i] != ref).sum()))
+        checked += 1
+    assert checked >= 1
+
+
 def test_sgbm_large_penalties_take_the_stepwise_clamp(gpu, orc):
     """P2 large enough that three path costs next to S could overflow 16 bits (2*P2 + bs^2*93 > 10922): the sweep
     kernel then clamps after every addition (cv::StereoSGBM's saturating adds) instead of once.  5-path mode, so
