@@ -917,9 +917,9 @@ static int sgbm_pipeline(rtdm_sgbm *h, int n, PlaneU8 L, PlaneU8 R, int W, int H
     const int INVS = (g.minD - 1) * 16;
     size_t pl = 0, vol = 0;
     sgbm_work_bytes(g, &pl, &vol);
-    // sub-batch size: the row sweeps (59 % of the time) run one 1024-thread CTA per SM, frames x column tiles CTAs per
-    // launch -> among the sizes the volumes allow, take the one that fills whole waves best (720p x 128: 37 frames x 24
-    // tiles = 6.0 waves of 148 SMs; 32 frames would be 5.2 -> 6 waves)
+    // sub-batch size.  Calls that take the tiled row sweeps (one 1024-thread CTA per SM, frames x column tiles CTAs per launch):
+    // among the sizes the volumes allow, the one that fills whole waves best (720p x 128: 37 frames x 24 tiles = 6.0 waves
+    // of 148 SMs; 32 frames would be 5.2 -> 6 waves).  Calls that take the whole-height passes: see below.
     int chunk = h->volB;
     // whole-height pass (batches): one cluster per frame, `q` frames at a time -> sub-batches are multiples of q
     const int q = sgbm_vpass_frames_in_flight(g, std::min(n, chunk));

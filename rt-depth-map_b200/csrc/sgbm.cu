@@ -5,16 +5,18 @@
 // SWSemiGlobalMatcher::compute (reference stereo-matcher/sgbm-sw.cpp:32-37).  Arithmetic per
 // SURVEY.md App. A.6 (restated and pinned in oracle/sgbm_oracle.c).
 //
-// Pipeline per batch of frames (volumes are [frame][y][x1][d] uint16, x1 in [0, W1)):
-//   sgbm_planes_kernel   : per pixel (value, lo, hi) of the x-Sobel plane and the raw plane, both images
-//   sgbm_cost_hsum_kernel: BT pixel cost of a row tile in shared memory -> horizontal box sum -> Hs volume
-//   sgbm_vsum_kernel     : C = P2 + vertical box sum of Hs (clamped rows)
-//   sgbm_path_kernel     : one launch per path direction; ONE WARP PER PATH CHAIN, the previous L_r
-//                          vector lives in registers (packed u16x2, D/32 words per lane), neighbours
-//                          d-1 / d+1 and min_k L_r(k) through warp shuffles; S += L_r
-//   sgbm_wta_kernel      : per row: warp argmin per pixel, uniqueness, sub-pixel, disp2 by atomicMin
-//                          (OpenCV's right-to-left strict '>' scan == min over (cost, -x)), LR check
-// then launch_median3 and launch_speckle (postproc.cu).
+// Pipeline per batch of frames (volumes are [frame][y][x1][d] uint16, x1 in [0, W1)).  D = 64 / 128 (the fast path):
+//   sgbm_planes2_kernel     : per pixel (value, lo, hi) of the x-Sobel plane and the raw plane in the cost kernel's staging format
+//   sgbm_cost_fused_kernel  : BT pixel cost -> horizontal window -> vertical window + P2 -> C, rows staged by cp.async
+//   sgbm_path4_kernel<.,0>  : left-to-right path, S = L (16 / 8 lanes per chain, 8 disparities per lane, L in registers)
+//   sgbm_vpass_kernel       : the three paths that come from the previous row, all H rows in one persistent launch, one
+//                             thread-block cluster per frame, boundary columns exchanged through distributed shared memory
+//                             (batches); sgbm_sweep_kernel: the same three paths in 8-row tiles with halo columns and a
+//                             frontier buffer (single frames, small batches).  Once per direction (MODE_HH: down and up)
+//   sgbm_path4_kernel<.,2>  : right-to-left path with S + L kept in registers and the winner-take-all taken right there
+//   sgbm_lr_kernel          : disp2 by atomicMin (OpenCV's right-to-left strict '>' scan == min over (cost, -x)), sub-pixel, LR check
+// Other D (16 .. 256, % 16): sgbm_planes / sgbm_cost_hsum / sgbm_vsum (D = 256: the fused cost kernel), one sgbm_path_kernel
+// launch per direction (one warp per chain), sgbm_wta_kernel.  Then launch_median3 and launch_speckle (postproc.cu).
 // Every pixel belongs to exactly one chain per direction, so the S read-modify-write needs no atomics.
 #include "common.cuh"
 #include <stdlib.h>
