@@ -635,7 +635,7 @@ __device__ __forceinline__ void path_step(uint4 &Lp, uint32_t &minLp, const uint
     if (sl == 0) left = 0x7FFF0000u;                       // L[-1] = MAX_COST (upper half is used)
     if (sl == LPC - 1) right = 0x00007FFFu;                // L[D]  = MAX_COST (lower half is used)
     // as in vcore: minLp is the chain's minimum splatted into both halves, the plain 32-bit arithmetic is multiply-add by `one`
-    const uint32_t dx2 = P2 + minLp, ndx2 = 0u - dx2;      // P2 + min_k L_r(p - r, k) < 65536
+    const uint32_t dx2 = minLp * one + P2, ndx2 = 0u - dx2;      // P2 + min_k L_r(p - r, k) < 65536
     const uint32_t w[6] = {left, Lp.x, Lp.y, Lp.z, Lp.w, right};
     const uint32_t cc[4] = {c.x, c.y, c.z, c.w};
     uint32_t t[4];
@@ -643,7 +643,7 @@ __device__ __forceinline__ void path_step(uint4 &Lp, uint32_t &minLp, const uint
     for (int k = 0; k < 4; k++) {
         const uint32_t lm1 = __byte_perm(w[k], w[k + 1], 0x5432);      // (L[d-1], L[d])   for the pair (d, d+1)
         const uint32_t lp1 = __byte_perm(w[k + 1], w[k + 2], 0x5432);  // (L[d+1], L[d+2])
-        const uint32_t v = __vimin3_u16x2(w[k + 1], __vadd2(min2(lm1, lp1), P1x2), dx2);   // min(a + P1, b + P1) = min(a, b) + P1
+        const uint32_t v = __vimin3_u16x2(w[k + 1], min2(lm1, lp1) * one + P1x2, dx2);   // min(a + P1, b + P1) = min(a, b) + P1
         t[k] = (v * one + cc[k]) * one + ndx2;
     }
     const uint32_t mm = min2(min2(t[0], t[1]), min2(t[2], t[3]));
@@ -753,14 +753,15 @@ __device__ __forceinline__ void vcore(const uint4 Lp, const uint32_t minLp, cons
     uint32_t right = __shfl_down_sync(0xFFFFFFFFu, Lp.x, 1, LPC);
     if (sl == 0) left = 0x7FFF0000u;                       // L[-1] = MAX_COST (upper half is used)
     if (sl == LPC - 1) right = 0x00007FFFu;                // L[D]  = MAX_COST (lower half is used)
-    const uint32_t dx2 = P2x2 + minLp, ndx2 = 0u - dx2;
+    const uint32_t dx2 = minLp * one + P2x2, ndx2 = 0u - dx2;
     const uint32_t w[6] = {left, Lp.x, Lp.y, Lp.z, Lp.w, right};
     const uint32_t cc[4] = {c.x, c.y, c.z, c.w};
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const uint32_t lm1 = __byte_perm(w[i], w[i + 1], 0x5432);      // (L[d-1], L[d])   for the pair (d, d+1)
         const uint32_t lp1 = __byte_perm(w[i + 1], w[i + 2], 0x5432);  // (L[d+1], L[d+2])
-        const uint32_t v = __vimin3_u16x2(w[i + 1], __vadd2(min2(lm1, lp1), P1x2), dx2);   // min(a + P1, b + P1) = min(a, b) + P1
+        // min(a + P1, b + P1) = min(a, b) + P1, and MAX_COST + P1 < 65536: the add is plain (IMAD), the three-way minimum one ALU op
+        const uint32_t v = __vimin3_u16x2(w[i + 1], min2(lm1, lp1) * one + P1x2, dx2);
         t[i] = (v * one + cc[i]) * one + ndx2;
     }
     const uint32_t mm = min2(min2(t[0], t[1]), min2(t[2], t[3]));
