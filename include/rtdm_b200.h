@@ -174,6 +174,8 @@ int rtdm_sgbm_compute_batch(rtdm_sgbm *h, int n, const uint8_t *left, size_t lst
 int rtdm_sgbm_submit_batch(rtdm_sgbm *h, int n, const uint8_t *left, size_t lstep, size_t lframe,
                            const uint8_t *right, size_t rstep, size_t rframe, int width, int height,
                            int16_t *disp, size_t dstep, size_t dframe);
+/* both waits (and the next call on the handle) return -EIO if a whole-height aggregation pass had to give up waiting for a
+ * neighbouring thread block's data (a broken launch: the maps of that call are invalid) */
 int rtdm_sgbm_wait(rtdm_sgbm *h);
 int rtdm_sgbm_wait_oldest(rtdm_sgbm *h);
 int rtdm_sgbm_compute_device(rtdm_sgbm *h, int n, const uint8_t *left, size_t lstep, size_t lframe,

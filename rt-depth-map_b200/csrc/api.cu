@@ -806,7 +806,19 @@ struct rtdm_sgbm {
     int launches;
     int prof;
     std::vector<cudaEvent_t> *ev;     // 3 events per profiled sub-batch: start, after matching, after post-filters
+    int *err_host, *err_dev;          // host-mapped flag raised by sgbm_vpass_kernel when a neighbour's data never arrives
 };
+
+// the whole-height pass gives up waiting instead of hanging; whoever next calls or waits on the handle learns about it
+static int sgbm_check_exchange(rtdm_sgbm *h)
+{
+    if (h->err_host && *reinterpret_cast<volatile int *>(h->err_host)) {
+        *reinterpret_cast<volatile int *>(h->err_host) = 0;
+        set_error("sgbm: the cluster pass's neighbour exchange timed out; the maps of the last call are invalid");
+        return -RTDM_EIO;
+    }
+    return 0;
+}
 
 static int sgbm_check_params(const rtdm_params *p)
 {
@@ -849,6 +861,7 @@ extern "C" void rtdm_sgbm_destroy(rtdm_sgbm *h)
     }
     if (h->ev) { for (cudaEvent_t e : *h->ev) cudaEventDestroy(e); delete h->ev; }
     if (h->st) cudaStreamDestroy(h->st);
+    if (h->err_host) cudaFreeHost(h->err_host);
     delete h;
 }
 
@@ -883,6 +896,10 @@ extern "C" int rtdm_sgbm_create(rtdm_sgbm **out, const rtdm_params *p, int max_w
     h->spitch = align_up((size_t)max_width, 64); h->sframe = h->spitch * max_height;
     h->dpitch = h->rpitch; h->dframe = h->rframe;
     rc = (int)cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) == cudaSuccess ? 0 : -RTDM_EIO;
+    if (!rc && cudaHostAlloc((void **)&h->err_host, sizeof(int), cudaHostAllocMapped) == cudaSuccess) {
+        *h->err_host = 0;
+        if (cudaHostGetDevicePointer((void **)&h->err_dev, h->err_host, 0) != cudaSuccess) h->err_dev = nullptr;   // no flag: tiled sweeps only
+    } else cudaGetLastError();
     if (!rc) rc = dev_alloc(&h->planes, pl * VB);
     if (!rc) rc = dev_alloc(&h->C, vol * VB + 64);
     if (!rc) rc = dev_alloc(&h->S, vol * VB + 64);
@@ -913,6 +930,7 @@ static int sgbm_pipeline(rtdm_sgbm *h, int n, PlaneU8 L, PlaneU8 R, int W, int H
         set_error("sgbm: frame geometry or batch exceeds what the handle was created for");
         return -RTDM_EINVAL;
     }
+    { const int rc = sgbm_check_exchange(h); if (rc) return rc; }
     SgbmGeom g = sgbm_geom(h->p, h->sw, W, H);
     const int INVS = (g.minD - 1) * 16;
     size_t pl = 0, vol = 0;
@@ -959,7 +977,7 @@ static int sgbm_pipeline(rtdm_sgbm *h, int n, PlaneU8 L, PlaneU8 R, int W, int H
         if (g.W1 > 0) {
             SgbmWork w;
             memset(&w, 0, sizeof w);
-            w.planes = h->planes; w.C = (int16_t *)h->C; w.S = (int16_t *)h->S; w.frame_planes = pl; w.frame_vol = vol;
+            w.planes = h->planes; w.C = (int16_t *)h->C; w.S = (int16_t *)h->S; w.frame_planes = pl; w.frame_vol = vol; w.err = h->err_dev;
             int rc = launch_sgbm(g, m, l, r, raw, w, st, &h->launches);
             if (rc) return rc;
         } else {
@@ -1031,7 +1049,7 @@ extern "C" int rtdm_sgbm_wait(rtdm_sgbm *h)
     { cudaError_t e = cudaStreamSynchronize(h->lane[0]); if (e0 == cudaSuccess) e0 = e; }
     h->busy[0] = h->busy[1] = 0;
     RTDM_CUDA(e0);
-    return 0;
+    return sgbm_check_exchange(h);
 }
 
 extern "C" int rtdm_sgbm_wait_oldest(rtdm_sgbm *h)
@@ -1041,7 +1059,7 @@ extern "C" int rtdm_sgbm_wait_oldest(rtdm_sgbm *h)
     const int newest = (int)((h->seq - 1u) & 1u), oldest = newest ^ 1;
     const int set = h->busy[oldest] ? oldest : newest;       // only one in flight: that one
     if (h->busy[set]) { RTDM_CUDA(cudaEventSynchronize(h->done[set])); h->busy[set] = 0; }
-    return 0;
+    return sgbm_check_exchange(h);
 }
 
 // H2D on lane[0], kernels on the handle's stream, D2H on lane[1], chained by events; two staging sets, so the copies of

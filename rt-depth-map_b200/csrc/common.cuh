@@ -147,6 +147,7 @@ struct SgbmWork {
     int16_t *C;         // cost volume      [H][W1][D]
     int16_t *S;         // aggregated volume [H][W1][D]
     int16_t *disp2;     // per-row scratch
+    int *err;           // device pointer of a host-mapped flag the whole-height pass raises when its neighbour exchange breaks
     size_t frame_planes, frame_vol;
 };
 size_t sgbm_work_bytes(const SgbmGeom &g, size_t *planes, size_t *vol);

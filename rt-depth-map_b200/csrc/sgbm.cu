@@ -879,6 +879,7 @@ struct VPassArgs {
     int ystart, ystep;                       // first row and row step of the pass
     int nframes, ncta;                       // frames of this launch; CTAs per cluster (= per frame)
     uint32_t one;                            // 1: a multiplier the compiler cannot fold (see vcore)
+    int *err;                                // host-mapped flag: raised when a neighbour's data did not arrive (see `broken`)
 };
 
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t a, uint32_t rank) { uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank)); return r; }
@@ -968,7 +969,9 @@ sgbm_vpass_kernel(VPassArgs a)
 #pragma unroll
     for (int q = 0; q < NQ; q++) { Lv[q] = z; minV[q] = 0u; }
     uint32_t T = 0u;
-    bool broken = false;                                              // a wait ran out: stop waiting (wrong results, but no hang)
+    // a wait ran out (the neighbour is at most a row behind: 2^18 failed polls mean the exchange is broken): stop waiting, so
+    // that the launch ends, and raise the host-mapped flag -- the next call or wait on the handle fails with -EIO
+    bool broken = false;
     uint4 c = z, s = z;
     if (cid < a.nframes) { c = __ldg(Cq + off[0]); s = Sq[off[0]]; }
 
@@ -999,7 +1002,7 @@ sgbm_vpass_kernel(VPassArgs a)
             if (bq[q] != 0 && T > 0u && !broken) {
                 const uint32_t bar = sbase + OFF_BAR + 8u * ((bq[q] == 1 ? 0u : 2u) + b);
                 int spin = 0;
-                while (!mbar_try_cta(bar, ph)) if (++spin > (1 << 18)) { broken = true; break; }
+                while (!mbar_try_cta(bar, ph)) if (++spin > (1 << 18)) { broken = true; *reinterpret_cast<volatile int *>(a.err) = 1; break; }
                 // armed again for the row after next (the neighbour's next send into this buffer)
                 if (sl == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(TXB) : "memory");
             }
@@ -1446,7 +1449,7 @@ int launch_sgbm(const SgbmGeom &g, int n, PlaneU8 left, PlaneU8 right, PlaneS16 
     const bool safe3 = sgbm_safe3(g);
     // whole-height cluster pass for batches that fill at least half of the resident clusters
     VPassPlan vp = {0, 0, 0};
-    if (fast && n >= 2) {
+    if (fast && n >= 2 && w.err) {
         const int rc = vpass_plan(g, &vp);
         if (rc) return rc;
         if (!vpass_wanted(g, vp, n) || (unsigned long long)n * (w.frame_vol / 8) >= (1ull << 32)) vp.nclusters = 0;   // 32-bit uint4 offsets
@@ -1455,7 +1458,7 @@ int launch_sgbm(const SgbmGeom &g, int n, PlaneU8 left, PlaneU8 right, PlaneS16 
         VPassArgs a;
         a.C = reinterpret_cast<const uint32_t *>(w.C); a.S = reinterpret_cast<uint32_t *>(w.S); a.frame_words = frame_words;
         a.W1 = g.W1; a.H = g.H; a.P1 = g.P1; a.P2 = g.P2;
-        a.ystart = dy > 0 ? 0 : g.H - 1; a.ystep = dy; a.nframes = n; a.ncta = vp.ncta; a.one = 1u;
+        a.ystart = dy > 0 ? 0 : g.H - 1; a.ystep = dy; a.nframes = n; a.ncta = vp.ncta; a.one = 1u; a.err = w.err;
         const int ncl = std::min(vp.nclusters, n);
         const bool wide = g.sw.sgbm_vpass_shape != 1;
         int rc;
