@@ -178,7 +178,7 @@ sgbm_cost_hsum_kernel(CostArgs a)
 }
 
 // ------------------------------------------------------------------------------------------------
-// Fused cost path (D = 64, 128, 256; blockSize <= 7): BT pixel cost -> horizontal window -> vertical window + P2
+// Fused cost path (D = 48, 64, 96, 128, 192, 256; blockSize <= 7): BT pixel cost -> horizontal window -> vertical window + P2
 // -> C, without the Hs volume.
 //
 // sgbm_planes2_kernel writes the per-pixel (value, lo, hi) of both BT planes in the form the cost kernel consumes,
@@ -187,7 +187,7 @@ sgbm_cost_hsum_kernel(CostArgs a)
 //         x1 (replicated 8 columns beyond both ends: the window's column clamp becomes a plain read);
 //   right GR[y][6 arrays: value, lo, -hi per plane][2 copies][WR] s16, REVERSED (index eg = W - 1 + 16 - x, so a larger disparity is a larger
 //         address) and stored twice, copy 1 shifted by one element, so that any (d, d + 1) pair is one aligned word.
-// sgbm_cost_fused_kernel: CTA = (tile of TXk = (256 / D2) * CSEG cost columns, band of rows, frame); a thread owns
+// sgbm_cost_fused_kernel: CTA = (tile of TXk = (256 / D2) * CSEG cost columns, band of rows, frame; (256 / D2) * D2 threads); a thread owns
 // one disparity pair and CSEG adjacent columns.  Per row it computes the CSEG + 2h pixel costs of its columns
 // (sliding horizontal sum in registers) and pushes the CSEG horizontal sums into per-column vertical rings that
 // also live in registers (BS x CSEG words); a row of C leaves once the ring is full.  Rows are replicate-clamped
@@ -285,7 +285,7 @@ sgbm_cost_fused_kernel(Cost2Args a)
 {
     constexpr int h = BS / 2, NC = CSEG + 2 * h;
     extern __shared__ __align__(16) uint8_t cs[];
-    const int D2 = a.D / 2, nseg = 256 / D2, TXk = nseg * CSEG, NXC = TXk + 2 * h;
+    const int D2 = a.D / 2, NT = blockDim.x, nseg = NT / D2, TXk = nseg * CSEG, NXC = TXk + 2 * h;   // NT = (256 / D2) * D2 threads
     const int dp = threadIdx.x % D2, seg = threadIdx.x / D2;
     const int x0 = blockIdx.x * TXk, y0 = blockIdx.y * a.BY, y1 = min(y0 + a.BY, a.H), f = blockIdx.z;
     const bool edge = x0 - h < 0 || x0 + TXk - 1 + h > a.W1 - 1;
@@ -316,7 +316,7 @@ sgbm_cost_fused_kernel(Cost2Args a)
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(cs);
 #pragma unroll
     for (int q = 0; q < 2; q++) {
-        const int t = threadIdx.x + q * 256;
+        const int t = threadIdx.x + q * NT;
         gsrc[q] = nullptr; gstr[q] = 0u; soff[q] = 0u;
         if (t < NL) { gsrc[q] = gl + t * 16; gstr[q] = (uint32_t)lrow; soff[q] = sbase + t * 16; }
         else if (t < NL + 12 * NRC) {
@@ -585,15 +585,101 @@ __device__ __forceinline__ uint32_t group_min_u32(uint32_t v, int grp)
     return r;
 }
 
+// NW packed words (2 NW disparities) of one lane: the specialised kernels below keep a lane's share of a pixel's D values in
+// registers.  D = 2 * NW * LPC with LPC lanes per pixel: NW = 4 gives 64 / 128 (LPC 8 / 16), NW = 3 gives 48 / 96 / 192 (LPC 8 /
+// 16 / 32) -- the reference's default `-nd 192` scaled to 320 / 640 / 1280 pixel frames (utils/cmdline-parser.h:85-89).
+template <int NW> struct PV { uint32_t w[NW]; };
+
+template <int NW>
+__device__ __forceinline__ PV<NW> pv_zero()
+{
+    PV<NW> r;
+#pragma unroll
+    for (int k = 0; k < NW; k++) r.w[k] = 0u;
+    return r;
+}
+
+// loads / stores at word pointers: one 128-bit access for NW = 4 (16-byte aligned by construction), NW 32-bit accesses else
+// (a lane's 12 bytes are only 4-byte aligned; the lanes of a pixel still cover one contiguous run)
+template <int NW>
+__device__ __forceinline__ PV<NW> pv_ldg(const uint32_t *p)
+{
+    PV<NW> r;
+    if constexpr (NW == 4) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4 *>(p));
+        r.w[0] = q.x; r.w[1] = q.y; r.w[2] = q.z; r.w[3] = q.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < NW; k++) r.w[k] = __ldg(p + k);
+    }
+    return r;
+}
+
+template <int NW>
+__device__ __forceinline__ PV<NW> pv_ld(const uint32_t *p)
+{
+    PV<NW> r;
+    if constexpr (NW == 4) {
+        const uint4 q = *reinterpret_cast<const uint4 *>(p);
+        r.w[0] = q.x; r.w[1] = q.y; r.w[2] = q.z; r.w[3] = q.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < NW; k++) r.w[k] = p[k];
+    }
+    return r;
+}
+
+template <int NW>
+__device__ __forceinline__ void pv_st(uint32_t *p, const PV<NW> &v)
+{
+    if constexpr (NW == 4) *reinterpret_cast<uint4 *>(p) = make_uint4(v.w[0], v.w[1], v.w[2], v.w[3]);
+    else {
+#pragma unroll
+        for (int k = 0; k < NW; k++) p[k] = v.w[k];
+    }
+}
+
+// One step of one path for a lane's 2 NW disparities (horizontal chains, row sweeps, whole-height passes).  `minLp` and the
+// returned `m` are the minimum over d SPLATTED into both halves, so the 32-bit minimum over a pixel's lanes is the splatted
+// minimum and P2 + min is one add.  The packed 16-bit minima only issue on the ALU pipe (64 lanes per clock and SM), which
+// is what bounds the passes, so the plain 32-bit arithmetic is written as multiply-add with `one`, a run-time 1 the compiler
+// cannot see through and therefore keeps as IMAD -- the other integer pipe.  v + C - (P2 + min): every 16-bit half of the
+// result is a path cost (0 <= L < 65536, v >= min), so no carry or borrow crosses the halves and 32-bit arithmetic is exact.
+template <int LPC, int NW>
+__device__ __forceinline__ void vcoreN(const PV<NW> &Lp, const uint32_t minLp, const PV<NW> &c, int sl, uint32_t one, uint32_t P1x2, uint32_t P2x2,
+                                       uint32_t (&t)[NW], uint32_t &m)
+{
+    uint32_t left = __shfl_up_sync(0xFFFFFFFFu, Lp.w[NW - 1], 1, LPC);
+    uint32_t right = __shfl_down_sync(0xFFFFFFFFu, Lp.w[0], 1, LPC);
+    if (sl == 0) left = 0x7FFF0000u;                       // L[-1] = MAX_COST (upper half is used)
+    if (sl == LPC - 1) right = 0x00007FFFu;                // L[D]  = MAX_COST (lower half is used)
+    const uint32_t dx2 = minLp * one + P2x2, ndx2 = 0u - dx2;      // P2 + min_k L_r(p - r, k) < 65536
+    uint32_t w[NW + 2];
+    w[0] = left; w[NW + 1] = right;
+#pragma unroll
+    for (int i = 0; i < NW; i++) w[i + 1] = Lp.w[i];
+    uint32_t mm = 0xFFFFFFFFu;
+#pragma unroll
+    for (int i = 0; i < NW; i++) {
+        const uint32_t lm1 = __byte_perm(w[i], w[i + 1], 0x5432);      // (L[d-1], L[d])   for the pair (d, d+1)
+        const uint32_t lp1 = __byte_perm(w[i + 1], w[i + 2], 0x5432);  // (L[d+1], L[d+2])
+        // min(a + P1, b + P1) = min(a, b) + P1, and MAX_COST + P1 < 65536: the add is plain (IMAD), the three-way minimum one ALU op
+        const uint32_t v = __vimin3_u16x2(w[i + 1], min2(lm1, lp1) * one + P1x2, dx2);
+        t[i] = (v * one + c.w[i]) * one + ndx2;
+        mm = i == 0 ? t[0] : min2(mm, t[i]);
+    }
+    m = min2(mm, __byte_perm(mm, mm, 0x1032));
+}
+
 // record of one pixel: x = minS | code << 16 (code = best d, | 0x8000 when the uniqueness test failed, 0xFFFF when
 // the pixel is degenerate), y = S[d-1] | S[d+1] << 16
-template <int LPC>
-__device__ __forceinline__ uint2 wta_record(const uint32_t (&sv)[4], int sl, int grp, int mul)
+template <int LPC, int NW>
+__device__ __forceinline__ uint2 wta_record(const uint32_t (&sv)[NW], int sl, int grp, int mul)
 {
-    const uint32_t dbase = 8u * (uint32_t)sl;
+    const uint32_t dbase = 2u * NW * (uint32_t)sl;
     uint32_t key = 0xFFFFFFFFu;
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
+    for (int k = 0; k < NW; k++) {
         const uint32_t d0 = dbase + 2u * k;
         key = min(key, min((sv[k] << 16) | d0, (sv[k] & 0xFFFF0000u) | (d0 + 1u)));      // first minimum wins
     }
@@ -602,7 +688,7 @@ __device__ __forceinline__ uint2 wta_record(const uint32_t (&sv)[4], int sl, int
     // smallest S outside [bd - 1, bd + 1]
     uint32_t m2 = 0xFFFFFFFFu;
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
+    for (int k = 0; k < NW; k++) {
         const uint32_t d0 = dbase + 2u * k;
         uint32_t w = sv[k];
         if (d0 - bd + 1u <= 2u) w |= 0x0000FFFFu;
@@ -615,10 +701,12 @@ __device__ __forceinline__ uint2 wta_record(const uint32_t (&sv)[4], int sl, int
     uint32_t nb[2];
 #pragma unroll
     for (int q = 0; q < 2; q++) {
-        const uint32_t dq = q ? min(bd + 1u, 8u * LPC - 1u) : (bd > 0u ? bd - 1u : 0u);
-        const uint32_t wi = (dq >> 1) & 3u;
-        uint32_t v = wi == 0u ? sv[0] : (wi == 1u ? sv[1] : (wi == 2u ? sv[2] : sv[3]));
-        v = __shfl_sync(0xFFFFFFFFu, v, grp * LPC + (int)(dq >> 3));
+        const uint32_t dq = q ? min(bd + 1u, 2u * NW * LPC - 1u) : (bd > 0u ? bd - 1u : 0u);
+        const uint32_t owner = dq / (2u * NW), wi = (dq >> 1) - owner * NW;
+        uint32_t v = sv[NW - 1];
+#pragma unroll
+        for (int k = NW - 2; k >= 0; k--) v = wi == (uint32_t)k ? sv[k] : v;
+        v = __shfl_sync(0xFFFFFFFFu, v, grp * LPC + (int)owner);
         nb[q] = (dq & 1u) ? v >> 16 : v & 0xFFFFu;
     }
     uint32_t code = bd | (viol ? 0x8000u : 0u);
@@ -626,46 +714,35 @@ __device__ __forceinline__ uint2 wta_record(const uint32_t (&sv)[4], int sl, int
     return make_uint2(minS | (code << 16), nb[0] | (nb[1] << 16));
 }
 
-template <int LPC, int MODE>
-__device__ __forceinline__ void path_step(uint4 &Lp, uint32_t &minLp, const uint4 c, const uint4 s, uint4 *sp, uint2 *rp,
+template <int LPC, int NW, int MODE>
+__device__ __forceinline__ void path_step(PV<NW> &Lp, uint32_t &minLp, const PV<NW> &c, const PV<NW> &s, uint32_t *sp, uint2 *rp,
                                           bool live, int sl, int grp, uint32_t P1x2, uint32_t P2, int mul, uint32_t one)
 {
-    uint32_t left = __shfl_up_sync(0xFFFFFFFFu, Lp.w, 1, LPC);
-    uint32_t right = __shfl_down_sync(0xFFFFFFFFu, Lp.x, 1, LPC);
-    if (sl == 0) left = 0x7FFF0000u;                       // L[-1] = MAX_COST (upper half is used)
-    if (sl == LPC - 1) right = 0x00007FFFu;                // L[D]  = MAX_COST (lower half is used)
-    // as in vcore: minLp is the chain's minimum splatted into both halves, the plain 32-bit arithmetic is multiply-add by `one`
-    const uint32_t dx2 = minLp * one + P2, ndx2 = 0u - dx2;      // P2 + min_k L_r(p - r, k) < 65536
-    const uint32_t w[6] = {left, Lp.x, Lp.y, Lp.z, Lp.w, right};
-    const uint32_t cc[4] = {c.x, c.y, c.z, c.w};
-    uint32_t t[4];
+    uint32_t t[NW], m;
+    vcoreN<LPC, NW>(Lp, minLp, c, sl, one, P1x2, P2, t, m);
+    PV<NW> tv;
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const uint32_t lm1 = __byte_perm(w[k], w[k + 1], 0x5432);      // (L[d-1], L[d])   for the pair (d, d+1)
-        const uint32_t lp1 = __byte_perm(w[k + 1], w[k + 2], 0x5432);  // (L[d+1], L[d+2])
-        const uint32_t v = __vimin3_u16x2(w[k + 1], min2(lm1, lp1) * one + P1x2, dx2);   // min(a + P1, b + P1) = min(a, b) + P1
-        t[k] = (v * one + cc[k]) * one + ndx2;
-    }
-    const uint32_t mm = min2(min2(t[0], t[1]), min2(t[2], t[3]));
-    const uint32_t m = min2(mm, __byte_perm(mm, mm, 0x1032));
+    for (int k = 0; k < NW; k++) tv.w[k] = t[k];
     if (MODE == 0) {
-        if (live) *sp = make_uint4(t[0], t[1], t[2], t[3]);
+        if (live) pv_st<NW>(sp, tv);
     } else {
         // S <= 32767 and L < 32768 per half: the sum cannot carry into the other half
-        const uint32_t sv[4] = {min2(t[0] * one + s.x, 0x7FFF7FFFu), min2(t[1] * one + s.y, 0x7FFF7FFFu),
-                                min2(t[2] * one + s.z, 0x7FFF7FFFu), min2(t[3] * one + s.w, 0x7FFF7FFFu)};
+        uint32_t sv[NW];
+        PV<NW> so;
+#pragma unroll
+        for (int k = 0; k < NW; k++) { sv[k] = min2(t[k] * one + s.w[k], 0x7FFF7FFFu); so.w[k] = sv[k]; }
         if (MODE == 1) {
-            if (live) *sp = make_uint4(sv[0], sv[1], sv[2], sv[3]);
+            if (live) pv_st<NW>(sp, so);
         } else {
-            const uint2 rec = wta_record<LPC>(sv, sl, grp, mul);
+            const uint2 rec = wta_record<LPC, NW>(sv, sl, grp, mul);
             if (live && sl == 0) *rp = rec;
         }
     }
-    Lp = make_uint4(t[0], t[1], t[2], t[3]);
+    Lp = tv;
     minLp = group_min_u32<LPC>(m, grp);
 }
 
-template <int LPC, int MODE>
+template <int LPC, int NW, int MODE>
 __global__ void __launch_bounds__(128)
 sgbm_path4_kernel(PathArgs a)
 {
@@ -690,28 +767,28 @@ sgbm_path4_kernel(PathArgs a)
     }
     const int maxlen = __reduce_max_sync(0xFFFFFFFFu, len);
     const uint32_t P1x2 = (uint32_t)a.P1 * 0x00010001u, P2 = (uint32_t)a.P2 * 0x00010001u;
-    const int wordsD = 8 * LPC / 2;
+    constexpr int wordsD = NW * LPC;
     const long long stepp = (long long)sy * a.W1 + sx;                        // pixels
-    const long long stepq = stepp * (wordsD / 4);                             // uint4 units
+    const long long stepw = stepp * wordsD;                                   // words
     const size_t pix0 = (size_t)y * a.W1 + x;
-    const size_t off = (((size_t)f * a.frame_words) + pix0 * wordsD) / 4 + sl;
-    const uint4 *cp = reinterpret_cast<const uint4 *>(a.C) + off;
-    uint4 *sp = reinterpret_cast<uint4 *>(a.S) + off;
+    const size_t off = (size_t)f * a.frame_words + pix0 * wordsD + (size_t)sl * NW;
+    const uint32_t *cp = a.C + off;
+    uint32_t *sp = a.S + off;
     uint2 *rp = MODE == 2 ? a.rec + (size_t)f * a.frame_rec + pix0 : nullptr;
-    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-    uint4 Lp = z;                                           // out-of-image predecessor: L = 0
+    const PV<NW> z = pv_zero<NW>();
+    PV<NW> Lp = z;                                          // out-of-image predecessor: L = 0
     uint32_t minLp = 0u;
-    uint4 c0 = len > 0 ? __ldg(cp) : z, s0 = (MODE != 0 && len > 0) ? *sp : z, c1, s1;
+    PV<NW> c0 = len > 0 ? pv_ldg<NW>(cp) : z, s0 = (MODE != 0 && len > 0) ? pv_ld<NW>(sp) : z, c1, s1;
     for (int i = 0; i < maxlen; i += 2) {
         const bool m1 = i + 1 < len;
-        c1 = m1 ? __ldg(cp + stepq) : z;
-        s1 = (MODE != 0 && m1) ? sp[stepq] : z;
-        path_step<LPC, MODE>(Lp, minLp, c0, s0, sp, rp, i < len, sl, grp, P1x2, P2, a.mul, a.one);
+        c1 = m1 ? pv_ldg<NW>(cp + stepw) : z;
+        s1 = (MODE != 0 && m1) ? pv_ld<NW>(sp + stepw) : z;
+        path_step<LPC, NW, MODE>(Lp, minLp, c0, s0, sp, rp, i < len, sl, grp, P1x2, P2, a.mul, a.one);
         const bool m2 = i + 2 < len;
-        c0 = m2 ? __ldg(cp + 2 * stepq) : z;
-        s0 = (MODE != 0 && m2) ? sp[2 * stepq] : z;
-        path_step<LPC, MODE>(Lp, minLp, c1, s1, sp + stepq, rp + stepp, m1, sl, grp, P1x2, P2, a.mul, a.one);
-        cp += 2 * stepq; sp += 2 * stepq;
+        c0 = m2 ? pv_ldg<NW>(cp + 2 * stepw) : z;
+        s0 = (MODE != 0 && m2) ? pv_ld<NW>(sp + 2 * stepw) : z;
+        path_step<LPC, NW, MODE>(Lp, minLp, c1, s1, sp + stepw, rp + stepp, m1, sl, grp, P1x2, P2, a.mul, a.one);
+        cp += 2 * stepw; sp += 2 * stepw;
         if (MODE == 2) rp += 2 * stepp;
     }
 }
@@ -739,33 +816,13 @@ struct SweepArgs {
     uint32_t one;                            // 1: a multiplier the compiler cannot fold (see vcore)
 };
 
-// One step of one path for a lane's 8 disparities (row sweeps and whole-height passes).  `minLp` and the returned `m` are the minimum over d
-// SPLATTED into both halves, so the 32-bit minimum over a column's lanes is the splatted column minimum and P2 + min is one
-// add.  The packed 16-bit minima / add-minima only issue on the ALU pipe (64 lanes per clock and SM), which is what bounds
-// the pass, so the plain 32-bit arithmetic is written as multiply-add with `one`, a run-time 1 the compiler cannot see
-// through and therefore keeps as IMAD -- the other integer pipe.  v + C - (P2 + min): every 16-bit half of the result is a
-// path cost (0 <= L < 65536, v >= min), so no carry or borrow crosses the halves and 32-bit arithmetic is exact.
+// the tiled sweep keeps its uint4 form (8 disparities per lane)
 template <int LPC>
 __device__ __forceinline__ void vcore(const uint4 Lp, const uint32_t minLp, const uint4 c, int sl, uint32_t one, uint32_t P1x2, uint32_t P2x2,
                                       uint32_t (&t)[4], uint32_t &m)
 {
-    uint32_t left = __shfl_up_sync(0xFFFFFFFFu, Lp.w, 1, LPC);
-    uint32_t right = __shfl_down_sync(0xFFFFFFFFu, Lp.x, 1, LPC);
-    if (sl == 0) left = 0x7FFF0000u;                       // L[-1] = MAX_COST (upper half is used)
-    if (sl == LPC - 1) right = 0x00007FFFu;                // L[D]  = MAX_COST (lower half is used)
-    const uint32_t dx2 = minLp * one + P2x2, ndx2 = 0u - dx2;
-    const uint32_t w[6] = {left, Lp.x, Lp.y, Lp.z, Lp.w, right};
-    const uint32_t cc[4] = {c.x, c.y, c.z, c.w};
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const uint32_t lm1 = __byte_perm(w[i], w[i + 1], 0x5432);      // (L[d-1], L[d])   for the pair (d, d+1)
-        const uint32_t lp1 = __byte_perm(w[i + 1], w[i + 2], 0x5432);  // (L[d+1], L[d+2])
-        // min(a + P1, b + P1) = min(a, b) + P1, and MAX_COST + P1 < 65536: the add is plain (IMAD), the three-way minimum one ALU op
-        const uint32_t v = __vimin3_u16x2(w[i + 1], min2(lm1, lp1) * one + P1x2, dx2);
-        t[i] = (v * one + cc[i]) * one + ndx2;
-    }
-    const uint32_t mm = min2(min2(t[0], t[1]), min2(t[2], t[3]));
-    m = min2(mm, __byte_perm(mm, mm, 0x1032));
+    const PV<4> l = {{Lp.x, Lp.y, Lp.z, Lp.w}}, cc = {{c.x, c.y, c.z, c.w}};
+    vcoreN<LPC, 4>(l, minLp, cc, sl, one, P1x2, P2x2, t, m);
 }
 
 template <int LPC, bool SAFE3>
@@ -893,6 +950,15 @@ __device__ __forceinline__ void st_async_b32(uint32_t a, const uint32_t v, uint3
 {
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(a), "r"(v), "r"(bar) : "memory");
 }
+template <int NW>
+__device__ __forceinline__ void st_async_pv(uint32_t a, const PV<NW> &v, uint32_t bar)
+{
+    if constexpr (NW == 4) st_async_v4(a, make_uint4(v.w[0], v.w[1], v.w[2], v.w[3]), bar);
+    else {
+#pragma unroll
+        for (int k = 0; k < NW; k++) st_async_b32(a + 4u * k, v.w[k], bar);
+    }
+}
 __device__ __forceinline__ bool mbar_try_cta(uint32_t bar, uint32_t parity)
 {
     uint32_t ok;
@@ -907,22 +973,23 @@ constexpr int VP_AHEAD = 3;                  // rows between the L2 prefetch and
 // NT threads per CTA, a thread owns NQ columns NS = NT / LPC apart ("quarters"; XC = NQ * NS columns per CTA).  1024 x 2 is the
 // default; 512 x 4 (RTDM_SGBM_VPASS_SHAPE=1: 128 registers per thread, nothing recomputed) has too few warps to hide the
 // shuffle / reduction latencies: 823 against 656 us per MODE_HH frame when both were measured.
-template <int LPC, int NT, int NQ, bool SAFE3>
+template <int LPC, int NW, int NT, int NQ, bool SAFE3>
 __global__ void __launch_bounds__(NT, 1)
 sgbm_vpass_kernel(VPassArgs a)
 {
-    constexpr int NS = NT / LPC, XC = NQ * NS, WQ = LPC, NP = XC + 2;     // slots per quarter, columns per CTA, uint4 per column, pads
+    constexpr int NS = NT / LPC, XC = NQ * NS, NP = XC + 2;               // slots per quarter, columns per CTA, columns + pads
+    constexpr uint32_t CB = LPC * NW * 4u;                                // bytes of one column's L in the exchange buffers
     extern __shared__ __align__(16) uint8_t sw[];
-    // exL [2][NP][WQ] uint4: L of the path from x-1, stored at producing column + 1; exR the same for the path from x+1;
+    // exL [2][NP][CB bytes]: L of the path from x-1, stored at producing column + 1; exR the same for the path from x+1;
     // mnL, mnR [2][NP] their minima; then four mbarriers, fullL[2] and fullR[2]
-    constexpr uint32_t BUFB = NP * WQ * 16u, BUFM = NP * 4u;
+    constexpr uint32_t BUFB = NP * CB, BUFM = NP * 4u;
     constexpr uint32_t OFF_EXR = 2u * BUFB, OFF_MNL = 2u * OFF_EXR, OFF_MNR = OFF_MNL + 2u * BUFM, OFF_BAR = OFF_MNR + 2u * BUFM;
-    constexpr uint32_t TXB = LPC * 16u + 4u;                          // bytes a neighbour sends per row and side: one column's L + its minimum
+    constexpr uint32_t TXB = CB + 4u;                                 // bytes a neighbour sends per row and side: one column's L + its minimum
     const int tid = threadIdx.x, j = tid / LPC, sl = tid % LPC, grp = (tid & 31) / LPC;
     uint32_t rank;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
     const int ncta = a.ncta, ncl = gridDim.x / ncta, cid = blockIdx.x / ncta;
-    const int wordsD = 4 * LPC;
+    constexpr int wordsD = NW * LPC;
     for (uint32_t i = tid * 16u; i < OFF_BAR; i += NT * 16u) *reinterpret_cast<uint4 *>(sw + i) = make_uint4(0u, 0u, 0u, 0u);
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(sw);
     const bool hasL = rank > 0u, hasR = (int)rank + 1 < ncta;
@@ -942,29 +1009,27 @@ sgbm_vpass_kernel(VPassArgs a)
     bool inq[NQ];
     int bq[NQ];                                  // 1: this thread's column at position q is column 0 (talks to the left neighbour), 2: column XC - 1
     uint32_t aq[NQ], mq[NQ];                     // byte offsets of this thread's exL / mnL READ entries (buffer 0) in sw
-    // C / S addresses: 32-bit offsets in uint4 units from the volume base (the volumes of a call stay below 2^32 x 16 bytes:
-    // vpass_plan), formed by one IMAD.WIDE; loads are unconditional -- a column outside the image reads column 0 of its CTA
-    // and only its stores are predicated
+    // C / S addresses: 32-bit WORD offsets from the volume base (the volumes of a call stay below 2^32 words: launch_sgbm),
+    // formed by one IMAD.WIDE; loads are unconditional -- a column outside the image reads column 0 of its CTA and only its
+    // stores are predicated
     uint32_t off[NQ];
-    const uint32_t frameq = (uint32_t)(a.frame_words / 4);
-    const uint32_t rowq = (uint32_t)(a.ystep * a.W1 * (wordsD / 4));                       // two's complement for the upward pass
-    const uint32_t framestep = (uint32_t)ncl * frameq - (uint32_t)(a.H - 1) * rowq;         // last row of a frame -> first row of this cluster's next
+    const uint32_t framew = (uint32_t)a.frame_words;
+    const uint32_t roww = (uint32_t)(a.ystep * a.W1 * wordsD);                             // two's complement for the upward pass
+    const uint32_t framestep = (uint32_t)ncl * framew - (uint32_t)(a.H - 1) * roww;         // last row of a frame -> first row of this cluster's next
 #pragma unroll
     for (int q = 0; q < NQ; q++) {
         const int quarter = odd ? NQ - 1 - q : q, col = quarter * NS + j;
         inq[q] = (int)rank * XC + col < a.W1;
         bq[q] = (quarter == 0 && hasL && j == 0) ? 1 : ((quarter == NQ - 1 && hasR && j == NS - 1) ? 2 : 0);
-        aq[q] = (uint32_t)(col * WQ + sl) * 16u;
+        aq[q] = (uint32_t)(col * LPC + sl) * (NW * 4u);
         mq[q] = OFF_MNL + (uint32_t)col * 4u;
-        off[q] = (uint32_t)cid * frameq + (uint32_t)(a.ystart * a.W1 + (int)rank * XC + (inq[q] ? col : 0)) * (uint32_t)(wordsD / 4) + (uint32_t)sl;
+        off[q] = (uint32_t)cid * framew + (uint32_t)(a.ystart * a.W1 + (int)rank * XC + (inq[q] ? col : 0)) * (uint32_t)wordsD + (uint32_t)(sl * NW);
     }
     const uint32_t remR = hasR ? mapa_u32(sbase, rank + 1u) : 0u, remL = hasL ? mapa_u32(sbase, rank - 1u) : 0u;
     const uint32_t P1x2 = (uint32_t)a.P1 * 0x00010001u, P2x2 = (uint32_t)a.P2 * 0x00010001u;
     const uint32_t one = a.one;                                       // 1, opaque to the compiler (see vcore)
-    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-    const uint4 *Cq = reinterpret_cast<const uint4 *>(a.C);
-    uint4 *Sq = reinterpret_cast<uint4 *>(a.S);
-    uint4 Lv[NQ];
+    const PV<NW> z = pv_zero<NW>();
+    PV<NW> Lv[NQ];
     uint32_t minV[NQ];
 #pragma unroll
     for (int q = 0; q < NQ; q++) { Lv[q] = z; minV[q] = 0u; }
@@ -972,8 +1037,8 @@ sgbm_vpass_kernel(VPassArgs a)
     // a wait ran out (the neighbour is at most a row behind: 2^18 failed polls mean the exchange is broken): stop waiting, so
     // that the launch ends, and raise the host-mapped flag -- the next call or wait on the handle fails with -EIO
     bool broken = false;
-    uint4 c = z, s = z;
-    if (cid < a.nframes) { c = __ldg(Cq + off[0]); s = Sq[off[0]]; }
+    PV<NW> c = z, s = z;
+    if (cid < a.nframes) { c = pv_ldg<NW>(a.C + off[0]); s = pv_ld<NW>(a.S + off[0]); }
 
     // one image row; LAST: the frame's last row hands zeros on (the state of a path that enters the image), so the next frame
     // starts without a special case and the row counter T that selects buffers and barrier phases simply runs on
@@ -997,8 +1062,8 @@ sgbm_vpass_kernel(VPassArgs a)
 #pragma unroll
         for (int q = 0; q < NQ; q++) {
             // next step's C and S: the next column of this row, or the first column of the next row / next frame
-            const uint32_t on = q + 1 < NQ ? off[q + 1] : (!LAST ? off[0] + rowq : (lastframe ? off[0] : off[0] + framestep));
-            const uint4 cn = __ldg(Cq + on), sn = Sq[on];
+            const uint32_t on = q + 1 < NQ ? off[q + 1] : (!LAST ? off[0] + roww : (lastframe ? off[0] : off[0] + framestep));
+            const PV<NW> cn = pv_ldg<NW>(a.C + on), sn = pv_ld<NW>(a.S + on);
             if (bq[q] != 0 && T > 0u && !broken) {
                 const uint32_t bar = sbase + OFF_BAR + 8u * ((bq[q] == 1 ? 0u : 2u) + b);
                 int spin = 0;
@@ -1006,38 +1071,36 @@ sgbm_vpass_kernel(VPassArgs a)
                 // armed again for the row after next (the neighbour's next send into this buffer)
                 if (sl == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(TXB) : "memory");
             }
-            const uint4 pL = *reinterpret_cast<const uint4 *>(sw + aq[q] + rb);                           // column - 1's entry
-            const uint4 pR = *reinterpret_cast<const uint4 *>(sw + aq[q] + rb + OFF_EXR + 2u * WQ * 16u);  // column + 1's entry
+            const PV<NW> pL = pv_ld<NW>(reinterpret_cast<const uint32_t *>(sw + aq[q] + rb));                      // column - 1's entry
+            const PV<NW> pR = pv_ld<NW>(reinterpret_cast<const uint32_t *>(sw + aq[q] + rb + OFF_EXR + 2u * CB));   // column + 1's entry
             const uint32_t pmL = *reinterpret_cast<const uint32_t *>(sw + mq[q] + rm);
             const uint32_t pmR = *reinterpret_cast<const uint32_t *>(sw + mq[q] + rm + 2u * BUFM + 8u);
-            uint32_t t0[4], t1[4], t2[4], m0, m1, m2;
-            vcore<LPC>(pL, pmL, c, sl, one, P1x2, P2x2, t0, m0);
-            vcore<LPC>(Lv[q], minV[q], c, sl, one, P1x2, P2x2, t1, m1);
-            vcore<LPC>(pR, pmR, c, sl, one, P1x2, P2x2, t2, m2);
+            uint32_t t0[NW], t1[NW], t2[NW], m0, m1, m2;
+            vcoreN<LPC, NW>(pL, pmL, c, sl, one, P1x2, P2x2, t0, m0);
+            vcoreN<LPC, NW>(Lv[q], minV[q], c, sl, one, P1x2, P2x2, t1, m1);
+            vcoreN<LPC, NW>(pR, pmR, c, sl, one, P1x2, P2x2, t2, m2);
             if (inq[q]) {
-                const uint32_t sv[4] = {s.x, s.y, s.z, s.w};
-                uint32_t o[4];
+                PV<NW> o;
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    if (SAFE3) o[i] = min2(t2[i] * one + (t1[i] * one + (t0[i] * one + sv[i])), 0x7FFF7FFFu);   // no 16-bit overflow possible
-                    else o[i] = min2(__vadd2(min2(__vadd2(min2(__vadd2(sv[i], t0[i]), 0x7FFF7FFFu), t1[i]), 0x7FFF7FFFu), t2[i]), 0x7FFF7FFFu);
+                for (int i = 0; i < NW; i++) {
+                    if (SAFE3) o.w[i] = min2(t2[i] * one + (t1[i] * one + (t0[i] * one + s.w[i])), 0x7FFF7FFFu);   // no 16-bit overflow possible
+                    else o.w[i] = min2(__vadd2(min2(__vadd2(min2(__vadd2(s.w[i], t0[i]), 0x7FFF7FFFu), t1[i]), 0x7FFF7FFFu), t2[i]), 0x7FFF7FFFu);
                 }
-                Sq[off[q]] = make_uint4(o[0], o[1], o[2], o[3]);
+                pv_st<NW>(a.S + off[q], o);
             }
-            uint4 tL, tR;
+            PV<NW> tL, tR;
             uint32_t mL, mR;
             if (LAST) { tL = z; tR = z; Lv[q] = z; mL = 0u; mR = 0u; minV[q] = 0u; }
             else {
                 mL = group_min_u32<LPC>(m0, grp);
                 minV[q] = group_min_u32<LPC>(m1, grp);
                 mR = group_min_u32<LPC>(m2, grp);
-                tL = make_uint4(t0[0], t0[1], t0[2], t0[3]);
-                Lv[q] = make_uint4(t1[0], t1[1], t1[2], t1[3]);
-                tR = make_uint4(t2[0], t2[1], t2[2], t2[3]);
+#pragma unroll
+                for (int i = 0; i < NW; i++) { tL.w[i] = t0[i]; Lv[q].w[i] = t1[i]; tR.w[i] = t2[i]; }
             }
             if (inq[q]) {
-                *reinterpret_cast<uint4 *>(sw + aq[q] + wb + WQ * 16u) = tL;                               // own entry: slot column + 1
-                *reinterpret_cast<uint4 *>(sw + aq[q] + wb + OFF_EXR + WQ * 16u) = tR;
+                pv_st<NW>(reinterpret_cast<uint32_t *>(sw + aq[q] + wb + CB), tL);                         // own entry: slot column + 1
+                pv_st<NW>(reinterpret_cast<uint32_t *>(sw + aq[q] + wb + OFF_EXR + CB), tR);
                 if (sl == 0) {
                     *reinterpret_cast<uint32_t *>(sw + mq[q] + wm + 4u) = mL;
                     *reinterpret_cast<uint32_t *>(sw + mq[q] + wm + 2u * BUFM + 4u) = mR;
@@ -1046,11 +1109,11 @@ sgbm_vpass_kernel(VPassArgs a)
             if (bq[q] != 0 && !(LAST && lastframe)) {
                 if (bq[q] == 2) {                // column XC - 1: its rightward diagonal is the right neighbour's left pad (slot 0)
                     const uint32_t bar = remR + OFF_BAR + 8u * (b ^ 1u);
-                    st_async_v4(remR + wb + (uint32_t)sl * 16u, tL, bar);
+                    st_async_pv<NW>(remR + wb + (uint32_t)sl * (NW * 4u), tL, bar);
                     if (sl == 0) st_async_b32(remR + OFF_MNL + wm, mL, bar);
                 } else {                         // column 0: its leftward diagonal is the left neighbour's right pad (slot XC + 1)
                     const uint32_t bar = remL + OFF_BAR + 8u * (2u + (b ^ 1u));
-                    st_async_v4(remL + OFF_EXR + wb + (uint32_t)((XC + 1) * WQ + sl) * 16u, tR, bar);
+                    st_async_pv<NW>(remL + OFF_EXR + wb + (uint32_t)((XC + 1) * LPC + sl) * (NW * 4u), tR, bar);
                     if (sl == 0) st_async_b32(remL + OFF_MNR + wm + (uint32_t)(XC + 1) * 4u, mR, bar);
                 }
             }
@@ -1064,7 +1127,7 @@ sgbm_vpass_kernel(VPassArgs a)
         for (int r = 0; r < a.H - 1; r++) {
             row(std::false_type(), f, r, lastframe);
 #pragma unroll
-            for (int q = 0; q < NQ; q++) off[q] += rowq;
+            for (int q = 0; q < NQ; q++) off[q] += roww;
         }
         row(std::true_type(), f, a.H - 1, lastframe);
 #pragma unroll
@@ -1254,7 +1317,24 @@ sgbm_wta_kernel(WtaArgs a)
 
 }  // namespace
 
-static bool sgbm_fused_cost(const SgbmGeom &g) { return (g.D == 64 || g.D == 128 || g.D == 256) && g.bs <= 7 && g.W1 > 0; }
+static bool sgbm_fused_cost(const SgbmGeom &g) { return (g.D == 48 || g.D == 64 || g.D == 96 || g.D == 128 || g.D == 192 || g.D == 256) && g.bs <= 7 && g.W1 > 0; }
+
+// disparity counts of the specialised aggregation kernels: D = 2 * NW * LPC (PV<NW> per lane, LPC lanes per pixel)
+static bool sgbm_fast_d(int D, int *lpc = nullptr, int *nw = nullptr)
+{
+    int l = 0, k = 0;
+    switch (D) {
+        case 48: l = 8; k = 3; break;
+        case 64: l = 8; k = 4; break;
+        case 96: l = 16; k = 3; break;
+        case 128: l = 16; k = 4; break;
+        case 192: l = 32; k = 3; break;
+        default: return false;
+    }
+    if (lpc) *lpc = l;
+    if (nw) *nw = k;
+    return true;
+}
 
 size_t sgbm_work_bytes(const SgbmGeom &g, size_t *planes, size_t *vol)
 {
@@ -1262,7 +1342,7 @@ size_t sgbm_work_bytes(const SgbmGeom &g, size_t *planes, size_t *vol)
     size_t pl = (size_t)12 * g.H * Wp;
     if (sgbm_fused_cost(g))                                            // GL + GR blocks of sgbm_planes2_kernel
         pl = std::max(pl, (size_t)g.H * ((size_t)(g.W1 + 2 * PADL) * 32 + (size_t)12 * align_up((size_t)g.W + 2 * PADR, 8) * 2));
-    if (g.W1 > 0 && (g.D == 64 || g.D == 128))                          // WTA records + two sweep frontiers reuse the block
+    if (g.W1 > 0 && sgbm_fast_d(g.D))                                   // WTA records + two sweep frontiers reuse the block
         pl = std::max(pl, align_up((size_t)8 * g.H * g.W1, 256) + 2 * align_up(((size_t)3 * g.W1 * (g.D / 2) + (size_t)3 * g.W1) * 4, 256));
     pl = align_up(pl, 256);
     const size_t v = (size_t)g.H * (g.W1 > 0 ? g.W1 : 0) * g.D;        // elements
@@ -1285,23 +1365,23 @@ int sgbm_sweep_ctas_per_frame(const SgbmGeom &g)
 namespace {
 struct VPassPlan { int ncta, nclusters; size_t smem; };
 
-template <int LPC, int NT, int NQ, bool SAFE3>
+template <int LPC, int NW, int NT, int NQ, bool SAFE3>
 int vpass_config(int ncta, size_t smem, int *nclusters)
 {
-    RTDM_CUDA(cudaFuncSetAttribute(sgbm_vpass_kernel<LPC, NT, NQ, SAFE3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (ncta > 8) RTDM_CUDA(cudaFuncSetAttribute(sgbm_vpass_kernel<LPC, NT, NQ, SAFE3>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    RTDM_CUDA(cudaFuncSetAttribute(sgbm_vpass_kernel<LPC, NW, NT, NQ, SAFE3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (ncta > 8) RTDM_CUDA(cudaFuncSetAttribute(sgbm_vpass_kernel<LPC, NW, NT, NQ, SAFE3>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = (unsigned)ncta; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.gridDim = dim3((unsigned)ncta); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = smem; cfg.attrs = at; cfg.numAttrs = 1;
     int ncl = 0;
-    if (cudaOccupancyMaxActiveClusters(&ncl, sgbm_vpass_kernel<LPC, NT, NQ, SAFE3>, &cfg) != cudaSuccess) { cudaGetLastError(); ncl = 0; }
+    if (cudaOccupancyMaxActiveClusters(&ncl, sgbm_vpass_kernel<LPC, NW, NT, NQ, SAFE3>, &cfg) != cudaSuccess) { cudaGetLastError(); ncl = 0; }
     *nclusters = ncl;
     return 0;
 }
 
-template <int LPC, int NT, int NQ, bool SAFE3>
+template <int LPC, int NW, int NT, int NQ, bool SAFE3>
 int vpass_launch(const VPassArgs &a, int nclusters, size_t smem, cudaStream_t st)
 {
     cudaLaunchConfig_t cfg = {};
@@ -1310,7 +1390,7 @@ int vpass_launch(const VPassArgs &a, int nclusters, size_t smem, cudaStream_t st
     at[0].val.clusterDim.x = (unsigned)a.ncta; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.gridDim = dim3((unsigned)(a.ncta * nclusters)); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cfg.attrs = at; cfg.numAttrs = 1;
-    RTDM_CUDA(cudaLaunchKernelEx(&cfg, sgbm_vpass_kernel<LPC, NT, NQ, SAFE3>, a));
+    RTDM_CUDA(cudaLaunchKernelEx(&cfg, sgbm_vpass_kernel<LPC, NW, NT, NQ, SAFE3>, a));
     return 0;
 }
 
@@ -1320,21 +1400,34 @@ bool sgbm_safe3(const SgbmGeom &g)
     return 32767 + 3 * Lmax <= 65535;
 }
 
+// one switch over (D, shape, clamp variant) for the plan and the launch
+#define RTDM_VPASS_DISPATCH(FN, ...)                                                                                                      \
+    ([&]() -> int {                                                                                                                       \
+        const bool alt = g.sw.sgbm_vpass_shape == 1;                                                                                      \
+        switch (g.D) {                                                                                                                    \
+            case 128: return alt ? (safe3 ? FN<16, 4, 512, 4, true>(__VA_ARGS__) : FN<16, 4, 512, 4, false>(__VA_ARGS__))                 \
+                                 : (safe3 ? FN<16, 4, 1024, 2, true>(__VA_ARGS__) : FN<16, 4, 1024, 2, false>(__VA_ARGS__));              \
+            case 64: return safe3 ? FN<8, 4, 1024, 2, true>(__VA_ARGS__) : FN<8, 4, 1024, 2, false>(__VA_ARGS__);                          \
+            case 48: return safe3 ? FN<8, 3, 1024, 2, true>(__VA_ARGS__) : FN<8, 3, 1024, 2, false>(__VA_ARGS__);                          \
+            case 96: return safe3 ? FN<16, 3, 1024, 2, true>(__VA_ARGS__) : FN<16, 3, 1024, 2, false>(__VA_ARGS__);                        \
+            default: return safe3 ? FN<32, 3, 1024, 4, true>(__VA_ARGS__) : FN<32, 3, 1024, 4, false>(__VA_ARGS__);    /* 192 */          \
+        }                                                                                                                                 \
+    })()
+
 int vpass_plan(const SgbmGeom &g, VPassPlan *p)
 {
     p->ncta = 0; p->nclusters = 0; p->smem = 0;
-    if (!(g.D == 64 || g.D == 128) || g.W1 <= 0 || g.sw.sgbm_oldpath || g.sw.sgbm_nosweep || g.sw.sgbm_novpass) return 0;
+    int LPC = 0, NW = 0;
+    if (!sgbm_fast_d(g.D, &LPC, &NW) || g.W1 <= 0 || g.sw.sgbm_oldpath || g.sw.sgbm_nosweep || g.sw.sgbm_novpass) return 0;
     if (g.P2 + g.bs * g.bs * (2 * g.ftzero + 63) >= 32768) return 0;               // see `fast` in launch_sgbm
-    const int LPC = g.D / 8, XC = 2 * 1024 / LPC, NP = XC + 2;                      // 1024 x 2 and 512 x 4: the same columns per CTA
+    // columns per CTA: 1024 threads x 2 columns per thread (D = 192, one pixel per warp: x 4); 512 x 4 gives the same
+    const int XC = (g.D == 192 ? 4 : 2) * 1024 / LPC, NP = XC + 2;
     const int ncta = cdiv(g.W1, XC);
     if (ncta > 16) return 0;
-    const size_t smem = (size_t)2 * 2 * NP * LPC * 16 + (size_t)2 * 2 * NP * 4 + 32;       // exchange, minima, 4 mbarriers
-    const bool safe3 = sgbm_safe3(g), wide = g.sw.sgbm_vpass_shape != 1;
-    int ncl = 0, rc;
-#define RTDM_VP(LPC_, SAFE_) (wide ? vpass_config<LPC_, 1024, 2, SAFE_>(ncta, smem, &ncl) : vpass_config<LPC_, 512, 4, SAFE_>(ncta, smem, &ncl))
-    if (g.D == 128) rc = safe3 ? RTDM_VP(16, true) : RTDM_VP(16, false);
-    else rc = safe3 ? RTDM_VP(8, true) : RTDM_VP(8, false);
-#undef RTDM_VP
+    const size_t smem = (size_t)2 * 2 * NP * LPC * NW * 4 + (size_t)2 * 2 * NP * 4 + 32;   // exchange, minima, 4 mbarriers
+    const bool safe3 = sgbm_safe3(g);
+    int ncl = 0;
+    const int rc = RTDM_VPASS_DISPATCH(vpass_config, ncta, smem, &ncl);
     if (rc) return rc;
     if (ncl < 1) return 0;
     if (g.sw.sgbm_vpass_maxcl > 0) ncl = std::min(ncl, g.sw.sgbm_vpass_maxcl);
@@ -1369,7 +1462,7 @@ int launch_sgbm(const SgbmGeom &g, int n, PlaneU8 left, PlaneU8 right, PlaneS16 
     const int Wp = (int)align_up((size_t)g.W, 16);
     const int h = g.bs / 2;
     const size_t row_words = (size_t)g.W1 * g.D / 2, frame_words = w.frame_vol / 2;
-    // D = 64 / 128 / 256 and windows up to 7 (larger ones would spill the register rings)
+    // D = 48 / 64 / 96 / 128 / 192 / 256 and windows up to 7 (larger ones would spill the register rings)
     const bool fusedcost = sgbm_fused_cost(g) && !g.sw.sgbm_oldcost;
     if (fusedcost) {
         // 1-3. planes in staging format, then fused BT cost + horizontal and vertical windows + P2 -> C
@@ -1381,18 +1474,18 @@ int launch_sgbm(const SgbmGeom &g, int n, PlaneU8 left, PlaneU8 right, PlaneS16 
         a.C = reinterpret_cast<uint16_t *>(w.C); a.frame_vol = w.frame_vol;
         a.W = g.W; a.H = g.H; a.D = g.D; a.minD = g.minD; a.minX1 = g.minX1; a.W1 = g.W1; a.LW = LW; a.WR = WR; a.BY = 48;
         a.P2x2 = (uint32_t)g.P2 * 0x00010001u;
-        const int D2 = g.D / 2, TXk = (256 / D2) * CSEG, NXC = TXk + 2 * h;
+        const int D2 = g.D / 2, NT = (256 / D2) * D2, TXk = (256 / D2) * CSEG, NXC = TXk + 2 * h;
         const size_t smem = 2 * ((size_t)NXC * 32 + (size_t)12 * RSTRIDE * 2);
         const dim3 grid(cdiv(g.W1, TXk), cdiv(g.H, a.BY), n);
 #define RTDM_COST_CASE(BS_)                                                                                             \
         case BS_:                                                                                                       \
             RTDM_CUDA(cudaFuncSetAttribute(sgbm_cost_fused_kernel<BS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            sgbm_cost_fused_kernel<BS_><<<grid, 256, smem, st>>>(a);                                                    \
+            sgbm_cost_fused_kernel<BS_><<<grid, NT, smem, st>>>(a);                                                     \
             break;
         switch (g.bs) {
             RTDM_COST_CASE(1) RTDM_COST_CASE(3) RTDM_COST_CASE(5)
             default: RTDM_CUDA(cudaFuncSetAttribute(sgbm_cost_fused_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                     sgbm_cost_fused_kernel<7><<<grid, 256, smem, st>>>(a); break;
+                     sgbm_cost_fused_kernel<7><<<grid, NT, smem, st>>>(a); break;
         }
 #undef RTDM_COST_CASE
         if (launches) (*launches) += 2;
@@ -1438,21 +1531,23 @@ int launch_sgbm(const SgbmGeom &g, int n, PlaneU8 left, PlaneU8 right, PlaneS16 
     const int K2 = g.D <= 64 ? 1 : (g.D <= 128 ? 2 : 4);   // u16x2 words per lane (divides D/2 for any D % 16 == 0)
     // the 4-word kernels add S and L as whole words: needs L <= C <= P2 + bs^2 * (2 * ftzero + 63) < 32768 next to S <= 32767
     // (any sane setting; the defaults give 4725), otherwise the generic chain kernel runs
-    const bool fast = (g.D == 128 || g.D == 64) && !g.sw.sgbm_oldpath && g.P2 + g.bs * g.bs * (2 * g.ftzero + 63) < 32768;
+    int LPC = 0, NW = 0;
+    const bool fast = sgbm_fast_d(g.D, &LPC, &NW) && !g.sw.sgbm_oldpath && g.P2 + g.bs * g.bs * (2 * g.ftzero + 63) < 32768;
     const bool fused = fast && g.uniq < 100 && !g.sw.sgbm_nofuse;
     const size_t frame_rec = w.frame_planes / 8;            // the BT planes are dead by now: their buffer takes the records
     // the two vertical triplets as row sweeps (one C read and one S update for three paths)
     const size_t rec_bytes = align_up((size_t)8 * g.H * g.W1, 256);
     const size_t front_words = (size_t)3 * g.W1 * (g.D / 2), fmin_words = (size_t)3 * g.W1;
     const size_t front_bytes = align_up((front_words + fmin_words) * 4, 256);
-    const bool sweep = fast && !g.sw.sgbm_nosweep && rec_bytes + 2 * front_bytes <= w.frame_planes;
+    // (tiled sweeps: 8 disparities per lane only; the 6-disparity forms run per-direction chains where the whole-height pass does not apply)
+    const bool sweep = fast && NW == 4 && !g.sw.sgbm_nosweep && rec_bytes + 2 * front_bytes <= w.frame_planes;
     const bool safe3 = sgbm_safe3(g);
     // whole-height cluster pass for batches that fill at least half of the resident clusters
     VPassPlan vp = {0, 0, 0};
     if (fast && n >= 2 && w.err) {
         const int rc = vpass_plan(g, &vp);
         if (rc) return rc;
-        if (!vpass_wanted(g, vp, n) || (unsigned long long)n * (w.frame_vol / 8) >= (1ull << 32)) vp.nclusters = 0;   // 32-bit uint4 offsets
+        if (!vpass_wanted(g, vp, n) || (unsigned long long)n * frame_words >= (1ull << 32)) vp.nclusters = 0;         // 32-bit word offsets
     }
     auto launch_vpass = [&](int dy) -> int {
         VPassArgs a;
@@ -1460,12 +1555,7 @@ int launch_sgbm(const SgbmGeom &g, int n, PlaneU8 left, PlaneU8 right, PlaneS16 
         a.W1 = g.W1; a.H = g.H; a.P1 = g.P1; a.P2 = g.P2;
         a.ystart = dy > 0 ? 0 : g.H - 1; a.ystep = dy; a.nframes = n; a.ncta = vp.ncta; a.one = 1u; a.err = w.err;
         const int ncl = std::min(vp.nclusters, n);
-        const bool wide = g.sw.sgbm_vpass_shape != 1;
-        int rc;
-#define RTDM_VP(LPC_, SAFE_) (wide ? vpass_launch<LPC_, 1024, 2, SAFE_>(a, ncl, vp.smem, st) : vpass_launch<LPC_, 512, 4, SAFE_>(a, ncl, vp.smem, st))
-        if (g.D == 128) rc = safe3 ? RTDM_VP(16, true) : RTDM_VP(16, false);
-        else rc = safe3 ? RTDM_VP(8, true) : RTDM_VP(8, false);
-#undef RTDM_VP
+        const int rc = RTDM_VPASS_DISPATCH(vpass_launch, a, ncl, vp.smem, st);
         if (launches) (*launches)++;
         return rc;
     };
@@ -1501,7 +1591,7 @@ int launch_sgbm(const SgbmGeom &g, int n, PlaneU8 left, PlaneU8 right, PlaneS16 
     };
     for (int k = 0; k < ndirs; k++) {
         const int di = (!hh && k == 4) ? 7 : k;
-        if (sweep && di >= 1 && di <= 6) {
+        if ((sweep || vp.nclusters > 0) && di >= 1 && di <= 6) {
             if (di == 1 || di == 4) { const int rc = launch_sweep(di == 1 ? 1 : -1); if (rc) return rc; }
             continue;                                       // di = 2, 3 / 5, 6 ride along
         }
@@ -1514,17 +1604,22 @@ int launch_sgbm(const SgbmGeom &g, int n, PlaneU8 left, PlaneU8 right, PlaneS16 
         a.nchains = (sy != 0 ? g.W1 : 0) + (sx != 0 ? (sy != 0 ? g.H - 1 : g.H) : 0);
         if (fast) {
             const int mode = k == 0 ? 0 : ((fused && k == ndirs - 1) ? 2 : 1);
-            const int cpc = g.D == 128 ? 8 : 16;             // chains per 128-thread CTA
+            const int cpc = 4 * (32 / LPC);                   // chains per 128-thread CTA
             const dim3 grid(cdiv(a.nchains, cpc), n);
-            if (g.D == 128) {
-                if (mode == 0) sgbm_path4_kernel<16, 0><<<grid, 128, 0, st>>>(a);
-                else if (mode == 1) sgbm_path4_kernel<16, 1><<<grid, 128, 0, st>>>(a);
-                else sgbm_path4_kernel<16, 2><<<grid, 128, 0, st>>>(a);
-            } else {
-                if (mode == 0) sgbm_path4_kernel<8, 0><<<grid, 128, 0, st>>>(a);
-                else if (mode == 1) sgbm_path4_kernel<8, 1><<<grid, 128, 0, st>>>(a);
-                else sgbm_path4_kernel<8, 2><<<grid, 128, 0, st>>>(a);
+#define RTDM_PATH(LPC_, NW_)                                                                   \
+            do {                                                                               \
+                if (mode == 0) sgbm_path4_kernel<LPC_, NW_, 0><<<grid, 128, 0, st>>>(a);       \
+                else if (mode == 1) sgbm_path4_kernel<LPC_, NW_, 1><<<grid, 128, 0, st>>>(a);  \
+                else sgbm_path4_kernel<LPC_, NW_, 2><<<grid, 128, 0, st>>>(a);                 \
+            } while (0)
+            switch (g.D) {
+                case 128: RTDM_PATH(16, 4); break;
+                case 64: RTDM_PATH(8, 4); break;
+                case 48: RTDM_PATH(8, 3); break;
+                case 96: RTDM_PATH(16, 3); break;
+                default: RTDM_PATH(32, 3); break;           // 192
             }
+#undef RTDM_PATH
         } else {
             // sub-warp chains where D/2 words split evenly into 8 or 16 lanes of 4 words (D = 64, 128)
             // (only when there are enough chains to still fill the machine: ~9.5k resident warps)

@@ -115,6 +115,10 @@ def test_sgbm_kernel_variants_agree_with_oracle(gpu, orc, env, monkeypatch):
     (200, 51, 64, 5, 1, 4, 1, None),           # 1 CTA, odd height: the buffer parity flips from frame to frame
     (453, 33, 128, 3, 0, 7, 3, None),          # last CTA holds 69 of its 128 columns
     (360, 120, 64, 5, 0, 3, 1, 4400),          # step-wise clamp instantiation
+    (500, 40, 192, 5, 1, 4, 2, None),          # D = 192 (the reference's default -nd): one pixel per warp, 6 disparities per lane, 4 columns per thread
+    (420, 50, 96, 3, 0, 3, 1, None),           # D = 96: 16 lanes x 6 disparities
+    (400, 45, 48, 5, 1, 5, 2, None),           # D = 48: 8 lanes x 6 disparities
+    (330, 36, 192, 3, 0, 2, None, 4400),       # D = 192, step-wise clamp
 ])
 def test_sgbm_cluster_pass_matches_oracle(gpu, orc, case, monkeypatch):
     """Batches take sgbm_vpass_kernel (one thread-block cluster per frame, neighbours exchanging boundary columns through
@@ -154,8 +158,8 @@ def test_sgbm_cluster_pass_equals_tiled_sweeps_on_random_geometries(gpu, monkeyp
     from rtdm_b200 import synth
     rng = np.random.default_rng(77)
     cases = [(300, 1, 128, 5, 1, 3, 2), (300, 2, 128, 5, 1, 3, 1), (200, 3, 64, 3, 0, 5, 2)]
-    for _ in range(9):
-        nd = int(rng.choice([64, 128]))
+    for _ in range(14):
+        nd = int(rng.choice([48, 64, 96, 128, 192]))
         W = nd + int(rng.integers(8, 640)); H = int(rng.integers(4, 70))
         cases.append((W, H, nd, int(rng.choice([3, 5, 7])), int(rng.integers(0, 2)), int(rng.integers(2, 9)), int(rng.integers(1, 4))))
     for (W, H, nd, bs, mode, B, maxcl) in cases:
@@ -188,10 +192,12 @@ def test_sgbm_batch_quantum(gpu):
         m.batch_quantum(4000, 720)
 
 
-@pytest.mark.parametrize("case", [(560, 70, 256, 5, 0), (700, 48, 256, 3, 1), (430, 64, 256, 7, 0), (300, 90, 192, 5, 1)])
+@pytest.mark.parametrize("case", [(560, 70, 256, 5, 0), (700, 48, 256, 3, 1), (430, 64, 256, 7, 0), (300, 90, 192, 5, 1), (934, 404, 192, 5, 0),
+                                  (320, 240, 48, 5, 1), (640, 200, 96, 7, 0), (250, 80, 96, 1, 1), (200, 60, 48, 3, 0)])
 def test_sgbm_wide_disparity_ranges_match_oracle(gpu, orc, case):
-    """numDisparities 256 (fused cost kernel with two 8-column segments per CTA, generic chain kernel for the paths) and 192
-    (the reference's default -nd at 1280 pixels: no fused kernel applies) on a batch of 3."""
+    """numDisparities 256 (fused cost kernel with two 8-column segments per CTA, generic chain kernel for the paths) and the
+    reference's default -nd 192 scaled to the frame width (192 / 96 / 48 at 1280 / 640 / 320 pixels; the operating point
+    934x404x192): 6 disparities per lane in the specialised chain kernels, on a batch of 3."""
     from rtdm_b200 import synth
     W, H, nd, bs, mode = case
     p = dict(blockSize=bs, minDisparity=0, numDisparities=nd, uniquenessRatio=10, speckleWindowSize=60, speckleRange=4,
