@@ -183,7 +183,9 @@ int rtdm_sgbm_compute_device(rtdm_sgbm *h, int n, const uint8_t *left, size_t ls
                              int height, int16_t *disp, size_t dstep, size_t dframe,
                              void *cuda_stream);
 int rtdm_sgbm_last_launches(const rtdm_sgbm *h);
-/* Frames the matching stage works on at the same time for this frame size (one thread-block cluster per frame in the
+/* (numDisparities 48 / 64 / 96 / 128 / 192 -- the reference's default -nd 192 at 1280 pixels, scaled by the width as
+ * utils/cmdline-parser.h:85-89 does -- take the specialised kernels; the other multiples of 16 up to 256 take generic ones.)
+ * Frames the matching stage works on at the same time for this frame size (one thread-block cluster per frame in the
  * whole-height aggregation passes: 15 on a B200 at 1280x720x128): batches that are multiples of it keep every cluster
  * busy to the end.  1 when the size takes the tiled sweeps (any batch size is as good as another), < 0 on error.
  * No reference peer: SWSemiGlobalMatcher::compute (sgbm-sw.cpp:32-37) is one frame per call. */

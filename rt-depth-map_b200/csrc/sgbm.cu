@@ -5,15 +5,16 @@
 // SWSemiGlobalMatcher::compute (reference stereo-matcher/sgbm-sw.cpp:32-37).  Arithmetic per
 // SURVEY.md App. A.6 (restated and pinned in oracle/sgbm_oracle.c).
 //
-// Pipeline per batch of frames (volumes are [frame][y][x1][d] uint16, x1 in [0, W1)).  D = 64 / 128 (the fast path):
+// Pipeline per batch of frames (volumes are [frame][y][x1][d] uint16, x1 in [0, W1)).  D = 48 / 64 / 96 / 128 / 192 (the fast path):
 //   sgbm_planes2_kernel     : per pixel (value, lo, hi) of the x-Sobel plane and the raw plane in the cost kernel's staging format
 //   sgbm_cost_fused_kernel  : BT pixel cost -> horizontal window -> vertical window + P2 -> C, rows staged by cp.async
-//   sgbm_path4_kernel<.,0>  : left-to-right path, S = L (16 / 8 lanes per chain, 8 disparities per lane, L in registers)
+//   sgbm_path4_kernel<.,.,0>: left-to-right path, S = L (8 / 16 / 32 lanes per chain, 8 or 6 disparities per lane, L in registers)
 //   sgbm_vpass_kernel       : the three paths that come from the previous row, all H rows in one persistent launch, one
 //                             thread-block cluster per frame, boundary columns exchanged through distributed shared memory
 //                             (batches); sgbm_sweep_kernel: the same three paths in 8-row tiles with halo columns and a
-//                             frontier buffer (single frames, small batches).  Once per direction (MODE_HH: down and up)
-//   sgbm_path4_kernel<.,2>  : right-to-left path with S + L kept in registers and the winner-take-all taken right there
+//                             frontier buffer (single frames, small batches at D = 64 / 128; per-direction chains at the other
+//                             D).  Once per direction (MODE_HH: down and up)
+//   sgbm_path4_kernel<.,.,2>: right-to-left path with S + L kept in registers and the winner-take-all taken right there
 //   sgbm_lr_kernel          : disp2 by atomicMin (OpenCV's right-to-left strict '>' scan == min over (cost, -x)), sub-pixel, LR check
 // Other D (16 .. 256, % 16): sgbm_planes / sgbm_cost_hsum / sgbm_vsum (D = 256: the fused cost kernel), one sgbm_path_kernel
 // launch per direction (one warp per chain), sgbm_wta_kernel.  Then launch_median3 and launch_speckle (postproc.cu).
@@ -1329,7 +1330,7 @@ static bool sgbm_fast_d(int D, int *lpc = nullptr, int *nw = nullptr)
         case 96: l = 16; k = 3; break;
         case 128: l = 16; k = 4; break;
         case 192: l = 32; k = 3; break;
-        default: return false;
+        default: return false;                  // (256 = 32 lanes x 8: the pass's exchange buffers would need 266 KB)
     }
     if (lpc) *lpc = l;
     if (nw) *nw = k;
@@ -1421,10 +1422,15 @@ int vpass_plan(const SgbmGeom &g, VPassPlan *p)
     if (!sgbm_fast_d(g.D, &LPC, &NW) || g.W1 <= 0 || g.sw.sgbm_oldpath || g.sw.sgbm_nosweep || g.sw.sgbm_novpass) return 0;
     if (g.P2 + g.bs * g.bs * (2 * g.ftzero + 63) >= 32768) return 0;               // see `fast` in launch_sgbm
     // columns per CTA: 1024 threads x 2 columns per thread (D = 192, one pixel per warp: x 4); 512 x 4 gives the same
-    const int XC = (g.D == 192 ? 4 : 2) * 1024 / LPC, NP = XC + 2;
+    const int XC = (LPC == 32 ? 4 : 2) * 1024 / LPC, NP = XC + 2;
     const int ncta = cdiv(g.W1, XC);
     if (ncta > 16) return 0;
     const size_t smem = (size_t)2 * 2 * NP * LPC * NW * 4 + (size_t)2 * 2 * NP * 4 + 32;   // exchange, minima, 4 mbarriers
+    int dev = 0, optin = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess || smem > (size_t)optin) {
+        cudaGetLastError();
+        return 0;
+    }
     const bool safe3 = sgbm_safe3(g);
     int ncl = 0;
     const int rc = RTDM_VPASS_DISPATCH(vpass_config, ncta, smem, &ncl);
