@@ -12,7 +12,8 @@ One "step" = one pass of the hot path over one batch of synthetic rectified fram
           MODE_HH (8 paths) and once as MODE_SGBM (5 paths, the reference's literal default, sgbm-sw.cpp:15).
   latency (the "latency" object): Estimator::run's real call pattern (estimator.cpp:45,54-56; main.cpp:131-135):
           one frame, synchronous, host pointers: filter run on a 934x404 mask, setROI1, BM compute on the 934x404
-          ROI crop (strided views of 1280x720 images) with numDisparities 192 -- beside cv2 doing the same.
+          ROI crop (strided views of 1280x720 images) with numDisparities 192 -- beside cv2 doing the same; plus
+          the reference's other matcher on the same views (SWSemiGlobalMatcher::compute, MODE_SGBM, `sgbm_ms`).
 Metric: Mde/s = W*H*numDisparities*frames / s / 1e6; whole-job aggregate.
 
 `value`  : device-resident inputs/outputs, CUDA events on the launching stream, max over ranks; the K steps are
@@ -251,7 +252,16 @@ def cpu_latency(iters=12):
         t2 = time.perf_counter()
         if i >= 0:
             tf += t1 - t0; tb += t2 - t1
+    sg = cv2_ref.make_sgbm(mode=SGBM_MODES["mode_sgbm"], **dict(SGBM_PARAMS, numDisparities=OPND))
+    ts, sg_iters = 0.0, 3
+    for i in range(-1, sg_iters):
+        k = i % len(Ls)
+        t0 = time.perf_counter()
+        sg.compute(Ls[k][OPY:OPY + OPH, OPX:OPX + OPW], Rs[k][OPY:OPY + OPH, OPX:OPX + OPW])
+        if i >= 0:
+            ts += time.perf_counter() - t0
     return {"filter_ms": tf / iters * 1e3, "bm_ms": tb / iters * 1e3, "frame_ms": (tf + tb) / iters * 1e3, "frames": iters,
+            "sgbm_ms": ts / sg_iters * 1e3, "sgbm_frames": sg_iters,
             "impl": f"cv2 {cv2.__version__}, {os.cpu_count()} threads"}
 
 
@@ -595,9 +605,26 @@ def bench_latency(ctx, iters=60):
             ref_d, ref_m = ctx.checker("op", (Ls[k][OPY:OPY + OPH, OPX:OPX + OPW], Rs[k][OPY:OPY + OPH, OPX:OPX + OPW], Ms[k], rois[i % len(rois)]))
             mism += int((ref_d != out).sum()) + int((ref_m != filt.getVideoOutBuffer()).sum())
             checked += 1
+    # the reference's other matcher at the same operating point: SWSemiGlobalMatcher::compute (sgbm-sw.cpp:32-37; MODE_SGBM is
+    # its literal default, P1 / P2 hard-coded), same strided views, one frame per call
+    sg = rt.CUDASemiGlobalMatcher(SGBM_PARAMS["blockSize"], 0, OPND, SGBM_PARAMS["uniquenessRatio"], SGBM_PARAMS["speckleWindowSize"],
+                                  SGBM_PARAMS["speckleRange"], SGBM_PARAMS["disp12MaxDiff"], mode=SGBM_MODES["mode_sgbm"],
+                                  max_width=OPW, max_height=OPH, device=ctx.local)
+    ts, sg_iters = 0.0, max(4, iters // 4)
+    for i in range(-2, sg_iters):
+        k = i % len(Ls)
+        Lv, Rv = Lp[k][OPY:OPY + OPH, OPX:OPX + OPW], Rp[k][OPY:OPY + OPH, OPX:OPX + OPW]
+        t0 = time.perf_counter()
+        sg.compute(Lv, Rv, out)
+        if i >= 0:
+            ts += time.perf_counter() - t0
+        if i == 0 and ctx.checker is not None:
+            mism += int((ctx.checker("op_sgbm", (Ls[k][OPY:OPY + OPH, OPX:OPX + OPW], Rs[k][OPY:OPY + OPH, OPX:OPX + OPW])) != out).sum())
+            checked += 1
     return {"ours": {"filter_ms": tf / iters * 1e3, "bm_ms": tb / iters * 1e3, "frame_ms": (tf + tb) / iters * 1e3, "frames": iters,
                      "api": "rtdm_morph_run + rtdm_bm_set_roi1 + rtdm_bm_compute, host pointers, synchronous",
-                     "kernel": bm.last_kernel()},
+                     "kernel": bm.last_kernel(), "sgbm_ms": ts / sg_iters * 1e3, "sgbm_frames": sg_iters,
+                     "sgbm_api": f"rtdm_sgbm_compute, MODE_SGBM {OPW}x{OPH} nd={OPND} bs={SGBM_PARAMS['blockSize']}, host pointers, synchronous"},
             "_parity": (checked, mism)}
 
 
@@ -610,6 +637,7 @@ def make_checker():
         bm = cv2_ref.make_bm(**BM_PARAMS)
         bm_op = cv2_ref.make_bm(**dict(BM_PARAMS, numDisparities=OPND))
         sg = {n: cv2_ref.make_sgbm(mode=m, **SGBM_PARAMS) for n, m in SGBM_MODES.items()}
+        sg_op = cv2_ref.make_sgbm(mode=SGBM_MODES["mode_sgbm"], **dict(SGBM_PARAMS, numDisparities=OPND))
 
         def check(kind, x):
             if kind == "bm":
@@ -623,6 +651,8 @@ def make_checker():
                 bm_op.setROI1(x[3])
                 out = np.full(x[0].shape, -16, np.int16)
                 return bm_op.compute(x[0], x[1], out), cv2_ref.morph_open_close(x[2])
+            if kind == "op_sgbm":
+                return sg_op.compute(x[0], x[1])
             return sg[kind].compute(x[0], x[1])
         return check, f"cv2 {cv2.__version__}"
     from oracle import oracle
@@ -635,6 +665,9 @@ def make_checker():
         if kind == "op":
             return (oracle.bm_compute(np.ascontiguousarray(x[0]), np.ascontiguousarray(x[1]),
                                       oracle.make_params(**dict(BM_PARAMS, numDisparities=OPND, roi1=x[3]))), oracle.morph_open_close(x[2]))
+        if kind == "op_sgbm":
+            return oracle.sgbm_compute(np.ascontiguousarray(x[0]), np.ascontiguousarray(x[1]),
+                                       oracle.make_params(P1=600, P2=2400, preFilterCap=0, mode=SGBM_MODES["mode_sgbm"], **dict(SGBM_PARAMS, numDisparities=OPND)))
         return oracle.sgbm_compute(x[0], x[1], oracle.make_params(P1=600, P2=2400, preFilterCap=0, mode=SGBM_MODES[kind], **SGBM_PARAMS))
     return check, "oracle/stereo_oracle.c"
 
