@@ -54,7 +54,7 @@ SGBM_MODES = {"mode_hh": 1, "mode_sgbm": 0}
 OPS_PER_DE = {"bm720": 8, "mode_hh": 96, "mode_sgbm": 72}       # SURVEY.md 8(d) algorithmic integer ops per de
 HBM_BYTES_PER_FRAME = {"bm720": 4 * W * H, "mode_hh": 4 * (W - ND) * H * ND + 4 * W * H, "mode_sgbm": 4 * (W - ND) * H * ND + 4 * W * H}
 MIN_REGION_S = 1.0          # every timed region lasts at least this long
-BM_BATCH, SGBM_BATCH = 63, 45
+BM_BATCH, SGBM_BATCH = 63, 60
 # Estimator's real operating point (latency leg)
 OPW, OPH, OPND, OPX, OPY = 934, 404, 192, 173, 158      # backup/1280x720/extrinsics.yml:56-57 via main.cpp:80-85; -nd 192
 
@@ -487,7 +487,7 @@ def bench_bm(ctx, K, frames):
 def bench_sgbm(ctx, K, frames, name):
     torch, rt = ctx.torch, ctx.rt
     from rtdm_b200 import sharding
-    # 2 x 212 MB of cost volumes per frame; 45 frames = 3 rounds of the 15 thread-block clusters (one frame each, 9 CTAs)
+    # 2 x 212 MB of cost volumes per frame; 60 frames = 4 rounds of the 15 thread-block clusters (one frame each, 9 CTAs)
     # a B200 keeps resident in the whole-height aggregation passes (rtdm_sgbm_batch_quantum)
     B = SGBM_BATCH
     Lh, Rh = frames[0][:B], frames[1][:B]
@@ -509,7 +509,7 @@ def bench_sgbm(ctx, K, frames, name):
         for _ in range(max(2, min(ctx.args.warmup, 3))):
             step()
     launches_per_step = matcher.last_launches()
-    Ks = max(2, min(K, 8))                                 # a 45-frame step lasts ~30 ms
+    Ks = max(2, min(K, 8))                                 # a 60-frame step lasts ~36 ms
     ctx.before_timed = lambda: matcher.set_profiling(True)
     ms, repeats = timed_region(ctx, step, st, Ks)
     nsteps = Ks * repeats

@@ -888,9 +888,9 @@ extern "C" int rtdm_sgbm_create(rtdm_sgbm **out, const rtdm_params *p, int max_w
     sgbm_work_bytes(g, &pl, &vol);
     h->frame_planes = pl; h->frame_vol = vol;
     // the two cost volumes are the big consumers (2 x 2 bytes x H x W1 x D per frame): keep at most
-    // ~24 GB of them resident and run larger calls as sub-batches
+    // ~40 GB of them resident (of 180 GB) and run larger calls as sub-batches
     const size_t per_frame = std::max<size_t>(1, vol * 4);
-    h->volB = (int)std::max<size_t>(1, std::min<size_t>((size_t)max_batch, (size_t)24e9 / per_frame));
+    h->volB = (int)std::max<size_t>(1, std::min<size_t>((size_t)max_batch, (size_t)40e9 / per_frame));
     const size_t B = (size_t)max_batch, VB = (size_t)h->volB;
     h->rpitch = align_up((size_t)max_width, 8); h->rframe = h->rpitch * max_height;
     h->spitch = align_up((size_t)max_width, 64); h->sframe = h->spitch * max_height;
