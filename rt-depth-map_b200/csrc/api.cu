@@ -27,6 +27,8 @@ Switches read_switches()
     sw.bm_kernel = geti("RTDM_BM_KERNEL", 0);
     sw.bm3_shape = geti("RTDM_BM3_SHAPE", 0);
     sw.bm_chunk = geti("RTDM_BM_CHUNK", 0);
+    sw.bm_fork_min = geti("RTDM_BM_FORK_MIN", 16);
+    sw.bm_fork_parts = geti("RTDM_BM_FORK_PARTS", 2);
     sw.bm_variant = geti("RTDM_BM_VARIANT", 1);
     sw.bm_occ3 = isset("RTDM_BM_OCC3");
     sw.bm_nofuse = isset("RTDM_BM_NOFUSE");
@@ -113,6 +115,8 @@ struct rtdm_bm {
     int maxW, maxH, maxB, dev;
     cudaStream_t st;
     cudaStream_t lane[3];        // streams of the chunked host-batch pipeline (copy/compute overlap)
+    cudaStream_t aux[3];         // extra streams of the post-processing fork (bm_pipeline)
+    cudaEvent_t ev_fork[4];      // [0]: SAD stage done (main -> aux streams), [1 + i]: aux stream i done (-> main)
     // per-batch device workspace (maxB frames)
     uint8_t *Lp, *Rp;            size_t ppitch, pframe;      // prefiltered planes (bytes)
     uint32_t *LE; uint8_t *RPs;  size_t lepitch, leframe, rppitch, rpframe;   // staged layouts for bm_sad4.cu's TMA boxes (common.cuh: BmStaged)
@@ -196,6 +200,8 @@ extern "C" void rtdm_bm_destroy(rtdm_bm *h)
     if (h->pev) { for (cudaEvent_t e : *h->pev) cudaEventDestroy(e); delete h->pev; }
     if (h->st) cudaStreamDestroy(h->st);
     for (int i = 0; i < 3; i++) if (h->lane[i]) cudaStreamDestroy(h->lane[i]);
+    for (int i = 0; i < 3; i++) if (h->aux[i]) cudaStreamDestroy(h->aux[i]);
+    for (int i = 0; i < 4; i++) if (h->ev_fork[i]) cudaEventDestroy(h->ev_fork[i]);
     delete h;
 }
 
@@ -226,6 +232,10 @@ extern "C" int rtdm_bm_create(rtdm_bm **out, const rtdm_params *p, int max_width
     rc = (int)cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) == cudaSuccess ? 0 : -RTDM_EIO;
     for (int i = 0; i < 3 && !rc; i++)
         rc = (int)cudaStreamCreateWithFlags(&h->lane[i], cudaStreamNonBlocking) == cudaSuccess ? 0 : -RTDM_EIO;
+    for (int i = 0; i < 3 && !rc; i++)
+        rc = cudaStreamCreateWithFlags(&h->aux[i], cudaStreamNonBlocking) == cudaSuccess ? 0 : -RTDM_EIO;
+    for (int i = 0; i < 4 && !rc; i++)
+        rc = cudaEventCreateWithFlags(&h->ev_fork[i], cudaEventDisableTiming) == cudaSuccess ? 0 : -RTDM_EIO;
     if (!rc) rc = dev_alloc(&h->Lp, h->pframe * B + 4096);
     if (!rc) rc = dev_alloc(&h->Rp, h->pframe * B + 4096);
     // staged planes only where bm_sad4.cu can run (minDisparity 0, blockSize 5 .. 15)
@@ -368,8 +378,33 @@ static int bm_pipeline(rtdm_bm *h, int n, PlaneU8 L, PlaneU8 R, int W, int H, Pl
     } else { mark(); mark(); }
     // stage timing: "validate_mask" ends after the row kernel (which, fused, already holds the speckle filter's row-run pass)
     struct Hook { decltype(mark) *m; } hook = {&mark};
+    const bool speckle = p.speckleRange >= 0 && p.speckleWindowSize > 0;
+    // The row pass and the speckle filter are chains of small latency-bound kernels (160 / 128 / 256 threads, 32 registers): for
+    // a large call the two halves of the batch go through them on two streams at once and fill each other's idle issue slots
+    const int nparts = (n >= h->sw.bm_fork_min && h->sw.bm_fork_min > 0 && !g.spill) ? std::max(2, std::min(4, h->sw.bm_fork_parts)) : 1;
+    if (nparts > 1) {
+        RTDM_CUDA(cudaEventRecord(h->ev_fork[0], st));
+        for (int part = 0; part < nparts; part++) {
+            const int fa = (int)((long long)n * part / nparts), fb = (int)((long long)n * (part + 1) / nparts), m = fb - fa;
+            const bool last = part == nparts - 1;                       // the last part stays on the call's stream (and carries the stage marks)
+            cudaStream_t ps = last ? st : h->aux[part];
+            if (!last) RTDM_CUDA(cudaStreamWaitEvent(ps, h->ev_fork[0], 0));
+            const size_t px = (size_t)fa * W * H;
+            const PlaneS16 rawP = {raw.p + (size_t)fa * raw.frame, raw.pitch, raw.frame}, costP = {cost.p + (size_t)fa * cost.frame, cost.pitch, cost.frame};
+            const PlaneS16 outP = {out.p + (size_t)fa * out.frame, out.pitch, out.frame};
+            rc = launch_validate_speckle(m, W, H, minD, nd, p.disp12MaxDiff, g.lofs, g.W1, std::max(vr.x, 0), std::max(vr.x + vr.w, 0),
+                                         row0, row1, rawP, costP, outP, speckle, FILT, p.speckleWindowSize, p.speckleRange,
+                                         wlab + px, wsiz + px, wrun + px, ps, &h->launches,
+                                         last ? [](void *c) { (*static_cast<Hook *>(c)->m)(); } : (void (*)(void *))nullptr, last ? &hook : nullptr, nullptr, h->sw);
+            if (rc) return rc;
+            if (!last) RTDM_CUDA(cudaEventRecord(h->ev_fork[1 + part], ps));
+        }
+        for (int part = 0; part + 1 < nparts; part++) RTDM_CUDA(cudaStreamWaitEvent(st, h->ev_fork[1 + part], 0));
+        mark();
+        return rc;
+    }
     rc = launch_validate_speckle(n, W, H, minD, nd, p.disp12MaxDiff, g.lofs, g.W1, std::max(vr.x, 0), std::max(vr.x + vr.w, 0),
-                                 row0, row1, raw, cost, out, p.speckleRange >= 0 && p.speckleWindowSize > 0, FILT,
+                                 row0, row1, raw, cost, out, speckle, FILT,
                                  p.speckleWindowSize, p.speckleRange, wlab, wsiz, wrun, st, &h->launches,
                                  [](void *c) { (*static_cast<Hook *>(c)->m)(); }, &hook, g.spill, h->sw);
     mark();

@@ -32,6 +32,8 @@ struct Switches {
     int bm_kernel = 0;          // RTDM_BM_KERNEL: 1 = generic bm_sad.cu, 2 = bm_sad2.cu, 3 = bm_sad3.cu where bm_sad4.cu would run
     int bm3_shape = 0;          // RTDM_BM3_SHAPE: 1 = two 384-thread CTAs per SM
     int bm_chunk = 0;           // RTDM_BM_CHUNK: frames per chunk of the host batch pipeline (0 = automatic)
+    int bm_fork_min = 16;       // RTDM_BM_FORK_MIN: smallest call whose row pass + speckle filter run as parts on several streams (0 = never)
+    int bm_fork_parts = 2;      // RTDM_BM_FORK_PARTS: 2 .. 4 parts
     int bm_variant = 1;         // RTDM_BM_VARIANT (bm_sad2.cu CTA variants)
     int bm_occ3 = 0;            // RTDM_BM_OCC3
     int bm_debug = 0;           // RTDM_BM_DEBUG, RTDM_DEV builds only
