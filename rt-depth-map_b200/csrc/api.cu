@@ -975,7 +975,7 @@ static int sgbm_pipeline(rtdm_sgbm *h, int n, PlaneU8 L, PlaneU8 R, int W, int H
     // of 148 SMs; 32 frames would be 5.2 -> 6 waves).  Calls that take the whole-height passes: see below.
     int chunk = h->volB;
     // whole-height pass (batches): one cluster per frame, `q` frames at a time -> sub-batches are multiples of q
-    const int q = sgbm_vpass_frames_in_flight(g, std::min(n, chunk));
+    const int q = n >= 2 ? sgbm_vpass_frames_in_flight(g, std::min(n, chunk)) : 0;      // (a single frame never takes the pass: skip the occupancy query)
     if (q > 0) {
         if (n <= chunk) chunk = n;                               // one sub-batch; the pass itself loops over rounds of q frames
         else {
