@@ -9,10 +9,11 @@ KERNELS = {                         # file tag -> substring of the mangled name
     "bm_sad4_h6_d128": "bm_sad4_kernelILi6ELi16E",
     "bm_sad3_h6_d128": "bm_sad3_kernelILi6ELi16ENS0_9ShapeWide",
     "bm_sad2_h6": "bm_sad2_kernelILi6ELi1ELi192ELb0ELi2E",
-    "sgbm_vpass_d128": "sgbm_vpass_kernelILi16ELi1024ELi2ELb1E",
+    "sgbm_vpass_d128": "sgbm_vpass_kernelILi16ELi4ELi1024ELi2ELb1E",
+    "sgbm_vpass_d192": "sgbm_vpass_kernelILi32ELi3ELi1024ELi4ELb1E",
     "sgbm_sweep_d128": "sgbm_sweep_kernelILi16ELb1E",
     "sgbm_cost_fused_bs5": "sgbm_cost_fused_kernelILi5E",
-    "sgbm_path4_d128_last": "sgbm_path4_kernelILi16ELi2E",
+    "sgbm_path4_d128_last": "sgbm_path4_kernelILi16ELi4ELi2E",
     "post_row8_validate": "post_row8_kernelILb1E",
 }
 txt = subprocess.run(["cuobjdump", "-sass", SO], capture_output=True, text=True, check=True).stdout
